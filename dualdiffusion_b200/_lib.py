@@ -1,0 +1,110 @@
+"""ctypes binding of the C-ABI library (include/dualdiffusion_b200.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  If the shared object is missing it is
+built in-tree (nvcc cross-compiles); if that fails, or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+_lib: Optional[C.CDLL] = None
+
+c_void_p, c_int, c_long, c_float = C.c_void_p, C.c_int, C.c_long, C.c_float
+
+
+class ConvEpilogue(C.Structure):
+    """struct dd_conv_epilogue"""
+    _fields_ = [("mode", c_int), ("mode2", c_int), ("alpha", c_float), ("beta", c_float), ("clip", c_float),
+                ("scale", c_void_p), ("scale2", c_void_p), ("residual", c_void_p), ("out2", c_void_p)]
+
+
+class AffineDesc(C.Structure):
+    """struct dd_affine_desc"""
+    _fields_ = [("w", c_void_p), ("gain", c_void_p), ("out", c_void_p), ("O", c_int), ("I", c_int),
+                ("groups", c_int), ("w_is_bf16", c_int), ("bias", c_float), ("normalize", c_int)]
+
+
+EPI_NONE, EPI_SCALE_SILU, EPI_RESIDUAL = 0, 1, 2
+EPI2_NONE, EPI2_SILU, EPI2_SCALE = 0, 1, 2
+WFMT_BF16_OTI, WFMT_F32_OIT = 0, 1
+WPERM_NONE, WPERM_QK = 0, 1
+
+_SIGNATURES = {
+    "dd_last_error": (C.c_char_p, []),
+    "dd_abi_version": (c_int, []),
+    "dd_device_info": (c_int, [C.POINTER(c_int)] * 3),
+    "dd_weight_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,
+                               c_int, c_void_p]),
+    "dd_mpconv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  C.POINTER(ConvEpilogue), c_void_p]),
+    "dd_mpconv_forward_naive": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p]),
+    "dd_conv_in": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                           c_void_p]),
+    "dd_conv_out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
+                            c_int, c_int, c_void_p]),
+    "dd_noise_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_float,
+                                   c_void_p, c_int, c_int, c_void_p]),
+    "dd_emb_affine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dd_pixnorm_silu": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p]),
+    "dd_cat_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_int,
+                            c_int, c_int, c_void_p]),
+    "dd_avgpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_long, c_void_p]),
+    "dd_sampler_update": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                  c_long, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) the shared library; raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dd_abi_version() != 1:
+        raise RuntimeError(f"dualdiffusion_b200: ABI mismatch ({lib.dd_abi_version()} != 1); rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().dd_last_error().decode(errors="replace")
+        raise RuntimeError(f"dualdiffusion_b200 C-ABI call failed ({status}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dualdiffusion_b200 has no CPU path: tensors must live on a CUDA device")

@@ -1,0 +1,209 @@
+// Small-sequence attention of the EDM2 UNet blocks (N = H*W <= 640 tokens, head_dim 64):
+// reference modules/unets/unet_edm2_b4.py:137-151.
+//
+// Per (batch, head, 64-query tile) CTA: K and V of the head are cosine-normalised (mp_tools.normalize over
+// the head channels, eps 1e-4) while they are staged into shared memory (V transposed), then a
+// FlashAttention-style online-softmax loop runs QK^T and PV on the tensor cores (mma.sync m16n8k16 bf16,
+// fp32 accumulate).  The block's `mp_silu(y * (emb_linear_v(emb) + 1))` (:150-151) is the epilogue.
+// Attention is 0.8 % of the UNet FLOPs; the kernel is sized for latency, not peak.
+#include "common.cuh"
+#include "dualdiffusion_b200.h"
+
+namespace {
+
+constexpr int kD = 64;            // head dim
+constexpr int kQTile = 64;        // queries per CTA (4 warps x 16 rows)
+constexpr int kKStride = kD + 8;  // bf16 elements per K/Q smem row (conflict-free fragment loads)
+constexpr float kNormEps = 1e-4f;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Load one token's 64-channel head vector with 8 lanes (one uint4 each), cosine-normalise it.
+// Returns the lane's 8 normalised values; `active` false yields zeros.
+__device__ __forceinline__ void load_norm8(const __nv_bfloat16* src, bool active, float (&f)[8]) {
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (active) q = __ldg(reinterpret_cast<const uint4*>(src));
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(u[j]);
+        f[2 * j] = t.x; f[2 * j + 1] = t.y;
+        ss += t.x * t.x + t.y * t.y;
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    const float inv = 1.f / (kNormEps + sqrtf(ss) * 0.125f);   // ||x|| / sqrt(64)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+}
+
+__global__ void __launch_bounds__(128)
+attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
+                 const float* __restrict__ scale_v, __nv_bfloat16* __restrict__ out, int N, int heads, int npad) {
+    extern __shared__ __align__(16) uint8_t smem_att[];
+    const int C = heads * kD;
+    const int vstride = npad + 8;
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);            // [npad][kKStride]
+    __nv_bfloat16* Vt = Ks + (size_t)npad * kKStride;                          // [kD][vstride]
+    __nv_bfloat16* Qs = Vt + (size_t)kD * vstride;                             // [kQTile][kKStride]
+
+    const int q0 = blockIdx.x * kQTile, head = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = tid & 7;          // which 8-channel slice of the head vector this lane loads
+    const int tok_in_pass = tid >> 3; // 16 tokens per pass
+
+    const __nv_bfloat16* q_base = qk + (size_t)b * N * 2 * C + head * kD + sub * 8;
+    const __nv_bfloat16* k_base = q_base + C;
+    const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kD + sub * 8;
+
+    for (int j0 = 0; j0 < npad; j0 += 16) {
+        const int j = j0 + tok_in_pass;
+        float f[8];
+        load_norm8(k_base + (size_t)j * 2 * C, j < N, f);
+        uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(Ks + (size_t)j * kKStride + sub * 8) = pk;
+        load_norm8(v_base + (size_t)j * C, j < N, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Vt[(size_t)(sub * 8 + i) * vstride + j] = __float2bfloat16_rn(f[i]);
+    }
+    for (int r0 = 0; r0 < kQTile; r0 += 16) {
+        const int r = r0 + tok_in_pass;
+        float f[8];
+        load_norm8(q_base + (size_t)(q0 + r) * 2 * C, q0 + r < N, f);
+        uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(Qs + (size_t)r * kKStride + sub * 8) = pk;
+    }
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = warp * 16;
+    // Q fragments for the 4 k-steps over head_dim
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const __nv_bfloat16* p0 = Qs + (size_t)(row0 + g) * kKStride + kk * 16 + 2 * t;
+        const __nv_bfloat16* p1 = p0 + 8 * kKStride;
+        qa[kk][0] = *reinterpret_cast<const uint32_t*>(p0);
+        qa[kk][1] = *reinterpret_cast<const uint32_t*>(p1);
+        qa[kk][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        qa[kk][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
+    }
+
+    const float sl2 = 0.125f * 1.44269504089f;   // 1/sqrt(64) * log2(e)
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
+
+    for (int kb = 0; kb < npad; kb += 64) {
+        float s[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+            const __nv_bfloat16* kp = Ks + (size_t)(kb + n * 8 + g) * kKStride + 2 * t;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp + kk * 16);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + kk * 16 + 8);
+                mma_bf16_16816(s[n], qa[kk], b0, b1);
+            }
+        }
+        // mask padded keys, block row max
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const int key = kb + n * 8 + 2 * t;
+            if (key >= N) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+            if (key + 1 >= N) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
+            mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
+        }
+        float corr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);     // finite: every 64-key block holds >= 1 real key
+            corr[r] = exp2f((m_run[r] - m_new) * sl2);
+            m_run[r] = m_new;
+            l_run[r] *= corr[r];
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) { o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1]; }
+        // probabilities -> bf16 A fragments
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float p0 = exp2f((s[n][0] - m_run[0]) * sl2), p1 = exp2f((s[n][1] - m_run[0]) * sl2);
+            const float p2 = exp2f((s[n][2] - m_run[1]) * sl2), p3 = exp2f((s[n][3] - m_run[1]) * sl2);
+            l_run[0] += p0 + p1;
+            l_run[1] += p2 + p3;
+            pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        // O += P V
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const __nv_bfloat16* vp = Vt + (size_t)(n * 8 + g) * vstride + kb + 2 * t;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp + kk * 16);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + kk * 16 + 8);
+                mma_bf16_16816(o[n], pa[kk], b0, b1);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv_l[2] = {1.f / l_run[0], 1.f / l_run[1]};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int q = q0 + row0 + g + r * 8;
+        if (q >= N) continue;
+        __nv_bfloat16* op = out + ((size_t)b * N + q) * C + head * kD;
+        const float* sc = scale_v + (size_t)b * C + head * kD;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const int d = n * 8 + 2 * t;
+            const float y0 = o[n][2 * r + 0] * inv_l[r] * __ldg(sc + d);
+            const float y1 = o[n][2 * r + 1] * inv_l[r] * __ldg(sc + d + 1);
+            *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_f(y0), mp_silu_f(y1));
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int dd_attention(const void* qk, const void* v, const float* scale_v, void* out, int B, int N, int heads,
+                            int head_dim, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(qk && v && scale_v && out, "dd_attention: null pointer");
+    DD_REQUIRE(head_dim == kD, "dd_attention: head_dim=%d unsupported (64)", head_dim);
+    DD_REQUIRE(N > 0 && N <= 640, "dd_attention: N=%d unsupported (1..640)", N);
+    const int npad = ceil_div(N, 64) * 64;
+    const size_t smem = ((size_t)npad * kKStride + (size_t)kD * (npad + 8) + (size_t)kQTile * kKStride) * 2;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        DD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const dim3 grid(ceil_div(N, kQTile), heads, B);
+    attention_kernel<<<grid, 128, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+                                                  static_cast<const __nv_bfloat16*>(v), scale_v,
+                                                  static_cast<__nv_bfloat16*>(out), N, heads, npad);
+    DD_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,593 @@
+// HBM-bound glue kernels of the EDM2 UNet hot path: weight preparation, UNet stem/head convolutions
+// (tiny channel counts, CUDA cores), embeddings, pixel-norm / concat / resample fusions and the EDM
+// sampler step.  All of them are coalesced 128-bit-vector streaming kernels; reference call sites are
+// cited in include/dualdiffusion_b200.h.
+#include "common.cuh"
+#include "dualdiffusion_b200.h"
+
+#include <algorithm>
+#include <math.h>
+
+namespace {
+
+constexpr float kNormEps = 1e-4f;   // modules/mp_tools.py:43
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    __syncthreads();
+    return t;
+}
+
+template <bool kBf16>
+__device__ __forceinline__ float load_w(const void* w, size_t i) {
+    if constexpr (kBf16) return __bfloat162float(static_cast<const __nv_bfloat16*>(w)[i]);
+    else return static_cast<const float*>(w)[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// weight prep
+// ------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void weight_prep_kernel(const void* __restrict__ w, void* __restrict__ out, int out_format, int O, int I_g,
+                                   int taps, const float* __restrict__ gain_dev, float gain_host, int normalize,
+                                   int perm, int head_dim) {
+    __shared__ float red[32];
+    const int o = blockIdx.x;
+    const int fan_in = I_g * taps;
+    const size_t base = (size_t)o * fan_in;
+    float scale = gain_host * (gain_dev ? *gain_dev : 1.f) * rsqrtf((float)fan_in);
+    if (normalize) {
+        float ss = 0.f;
+        for (int i = threadIdx.x; i < fan_in; i += blockDim.x) {
+            const float v = load_w<kBf16>(w, base + i);
+            ss += v * v;
+        }
+        ss = block_sum(ss, red);
+        scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)fan_in));
+    }
+    int o_dst = o;
+    if (perm == DD_WPERM_QK) {
+        const int head = o / (2 * head_dim), rem = o % (2 * head_dim);
+        o_dst = (rem & 1) * (O / 2) + head * head_dim + (rem >> 1);
+    }
+    if (out_format == DD_WFMT_BF16_OTI) {
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(out) + (size_t)o_dst * fan_in;
+        for (int j = threadIdx.x; j < fan_in; j += blockDim.x) {      // j = tap * I_g + i  (coalesced writes)
+            const int tap = j / I_g, i = j - tap * I_g;
+            dst[j] = __float2bfloat16_rn(load_w<kBf16>(w, base + (size_t)i * taps + tap) * scale);
+        }
+    } else {
+        float* dst = static_cast<float*>(out) + (size_t)o_dst * fan_in;
+        for (int j = threadIdx.x; j < fan_in; j += blockDim.x) dst[j] = load_w<kBf16>(w, base + j) * scale;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pixel norm + mp_silu  (one warp per pixel, channels in registers)
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxVecPerLane = 10;    // C <= 10*32*8 = 2560
+
+__global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restrict__ x_out, uint4* __restrict__ s_out,
+                                    long npix, int C) {
+    const int lane = threadIdx.x & 31;
+    const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const int nvec = C >> 3;
+    const uint4* src = t + pix * nvec;
+    uint4 reg[kMaxVecPerLane];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+        const int v = lane + k * 32;
+        if (v < nvec) {
+            reg[k] = __ldg(src + v);
+            const uint32_t u[4] = {reg[k].x, reg[k].y, reg[k].z, reg[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(u[j]); ss += f.x * f.x + f.y * f.y; }
+        }
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)C));
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+        const int v = lane + k * 32;
+        if (v < nvec) {
+            const uint32_t u[4] = {reg[k].x, reg[k].y, reg[k].z, reg[k].w};
+            uint32_t xo[4], so[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_bf16x2(u[j]);
+                f.x *= inv; f.y *= inv;
+                xo[j] = pack_bf16x2(f.x, f.y);
+                so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
+            }
+            x_out[pix * nvec + v] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+            s_out[pix * nvec + v] = make_uint4(so[0], so[1], so[2], so[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder input: (optional nearest x2 upsample of a) ++ (optional skip b), scaled, plus mp_silu
+// ------------------------------------------------------------------------------------------
+__global__ void cat_silu_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb, float wa,
+                                float wb, int up, uint4* __restrict__ xcat, uint4* __restrict__ s, int B, int H, int W) {
+    const int vt = va + vb;
+    const long total = (long)B * H * W * vt;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % vt);
+        const long pix = idx / vt;
+        uint4 q;
+        float sc;
+        if (v < va) {
+            long apix = pix;
+            if (up) {
+                const int w = (int)(pix % W), h = (int)((pix / W) % H), bb = (int)(pix / ((long)W * H));
+                apix = ((long)bb * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+            }
+            q = __ldg(a + apix * va + v);
+            sc = wa;
+        } else {
+            q = __ldg(b + pix * vb + (v - va));
+            sc = wb;
+        }
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+        uint32_t xo[4], so[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf16x2(u[j]);
+            f.x *= sc; f.y *= sc;
+            xo[j] = pack_bf16x2(f.x, f.y);
+            so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
+        }
+        if (xcat) xcat[idx] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+        s[idx] = make_uint4(so[0], so[1], so[2], so[3]);
+    }
+}
+
+__global__ void avgpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long total = (long)B * Ho * Wo * nvec;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % nvec);
+        const long pix = idx / nvec;
+        const int w = (int)(pix % Wo), h = (int)((pix / Wo) % Ho), b = (int)(pix / ((long)Wo * Ho));
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const uint4 q = __ldg(x + (((long)b * H + 2 * h + dy) * W + 2 * w + dx) * nvec + v);
+                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(u[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+            }
+        out[idx] = make_uint4(pack_bf16x2(acc[0] * .25f, acc[1] * .25f), pack_bf16x2(acc[2] * .25f, acc[3] * .25f),
+                              pack_bf16x2(acc[4] * .25f, acc[5] * .25f), pack_bf16x2(acc[6] * .25f, acc[7] * .25f));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// UNet stem: preconditioning + constant/positional channels + 3x3 conv (CT = Cin+2 input channels)
+// ------------------------------------------------------------------------------------------
+constexpr int kStemPix = 32;
+
+template <int CT>
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const float* __restrict__ x_in, const float* __restrict__ sigma, float sigma_data,
+               const float* __restrict__ ln_freqs, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+               int B, int H, int W, int Cout) {
+    __shared__ float patch[CT][3][kStemPix + 2];
+    const int w0 = blockIdx.x * kStemPix, h = blockIdx.y, b = blockIdx.z;
+    const float sg = sigma[b];
+    const float c_in = rsqrtf(sigma_data * sigma_data + sg * sg);
+    constexpr int kCin = CT - 2;
+    for (int i = threadIdx.x; i < CT * 3 * (kStemPix + 2); i += blockDim.x) {
+        const int px = i % (kStemPix + 2), dy = (i / (kStemPix + 2)) % 3, c = i / (3 * (kStemPix + 2));
+        const int hh = h + dy - 1, ww = w0 + px - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            if (c < kCin) v = c_in * x_in[(((size_t)b * kCin + c) * H + hh) * W + ww];
+            else if (c == kCin) v = 1.f;
+            else v = ln_freqs[hh];
+        }
+        patch[c][dy][px] = v;
+    }
+    __syncthreads();
+    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+        float wr[CT * 9];
+#pragma unroll
+        for (int i = 0; i < CT * 9; ++i) wr[i] = __ldg(w + (size_t)co * CT * 9 + i);
+        for (int px = 0; px < kStemPix; ++px) {
+            if (w0 + px >= W) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) acc += wr[c * 9 + dy * 3 + dx] * patch[c][dy][px + dx];
+            out[(((size_t)b * H + h) * W + w0 + px) * Cout + co] = __float2bfloat16_rn(acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// UNet head: 3x3 conv to a handful of channels + EDM output preconditioning (warp per pixel)
+// ------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ x_in,
+                const float* __restrict__ sigma, float sigma_data, const float* __restrict__ x_ref,
+                float* __restrict__ d_out, int B, int C, int H, int W) {
+    extern __shared__ float wsm[];   // [9][COUT][C]
+    for (int i = threadIdx.x; i < 9 * COUT * C; i += blockDim.x) {
+        const int c = i % C, co = (i / C) % COUT, tap = i / (C * COUT);
+        wsm[i] = w[((size_t)co * C + c) * 9 + tap];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, nvec = C >> 3;
+    const long npix = (long)B * H * W;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += warps_total) {
+        const int wq = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+        float acc[COUT];
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const uint4* src = x + (((long)b * H + hh) * W + ww) * nvec;
+            for (int v = lane; v < nvec; v += 32) {
+                const uint4 q = __ldg(src + v);
+                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(u[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const float* wp = wsm + ((size_t)tap * COUT + co) * C + v * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[co] += f[j] * wp[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = warp_sum(acc[co]);
+        if (lane == 0) {
+            const float sg = sigma[b];
+            const float sd2 = sigma_data * sigma_data;
+            const float c_skip = sd2 / (sg * sg + sd2);
+            const float c_out = sg * sigma_data * rsqrtf(sg * sg + sd2);
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const size_t o = (((size_t)b * COUT + co) * H + h) * W + wq;
+                float d = c_skip * x_in[o] + c_out * acc[co];
+                if (x_ref) {   // unet_edm2_b4.py:293-294, tensor-valued mp_sum
+                    const size_t plane = (size_t)H * W;
+                    const float r = x_ref[((size_t)b * (COUT + 1) + co) * plane + (size_t)h * W + wq];
+                    const float t = x_ref[((size_t)b * (COUT + 1) + COUT) * plane + (size_t)h * W + wq];
+                    d = (r + t * (d - r)) * rsqrtf((1.f - t) * (1.f - t) + t * t);
+                }
+                d_out[o] = d;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// embeddings
+// ------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void noise_embedding_kernel(const float* __restrict__ sigma, const float* __restrict__ freqs,
+                                       const float* __restrict__ phases, int cnoise, const void* __restrict__ w,
+                                       int normalize, const float* __restrict__ label, float t, float* __restrict__ out,
+                                       int cemb) {
+    extern __shared__ float four[];
+    const int b = blockIdx.y;
+    const float c_noise = logf(sigma[b]) * 0.25f;
+    for (int i = threadIdx.x; i < cnoise; i += blockDim.x)
+        four[i] = cosf(c_noise * freqs[i] + phases[i]) * 1.41421356237f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= cemb) return;
+    float acc = 0.f, ss = 0.f;
+    for (int i = lane; i < cnoise; i += 32) {
+        const float wv = load_w<kBf16>(w, (size_t)o * cnoise + i);
+        acc += wv * four[i];
+        ss += wv * wv;
+    }
+    acc = warp_sum(acc);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+        float scale = rsqrtf((float)cnoise);
+        if (normalize) scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)cnoise));
+        const float e = acc * scale;
+        const float l = label[(size_t)b * cemb + o];
+        const float m = (e + t * (l - e)) * rsqrtf((1.f - t) * (1.f - t) + t * t);
+        out[(size_t)b * cemb + o] = mp_silu_f(m);
+    }
+}
+
+__global__ void emb_affine_kernel(const dd_affine_desc* __restrict__ descs, const float* __restrict__ emb, int B,
+                                  int cemb) {
+    const dd_affine_desc d = descs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= d.O) return;
+    const int g = o / (d.O / d.groups);
+    const float* e0 = emb + (size_t)g * d.I;
+    const float gain = d.gain ? *d.gain : 1.f;
+    for (int b0 = 0; b0 < B; b0 += 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float ss = 0.f;
+        for (int i = lane; i < d.I; i += 32) {
+            const float wv = d.w_is_bf16 ? load_w<true>(d.w, (size_t)o * d.I + i) : load_w<false>(d.w, (size_t)o * d.I + i);
+            ss += wv * wv;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (b0 + j < B) acc[j] += wv * e0[(size_t)(b0 + j) * cemb + i];
+        }
+        ss = warp_sum(ss);
+        float scale = gain * rsqrtf((float)d.I);
+        if (d.normalize) scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)d.I));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = warp_sum(acc[j]);
+            if (lane == 0 && b0 + j < B) d.out[(size_t)(b0 + j) * d.O + o] = d.bias + a * scale;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// EDM sampler step (fp32 state)
+// ------------------------------------------------------------------------------------------
+__global__ void sampler_cfg_lerp_kernel(const float4* __restrict__ d, const float4* __restrict__ sample, float cfg,
+                                        float t_hat, float4* __restrict__ cfg_out, float4* __restrict__ xhat, long n4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 c = d[i], u = d[i + n4], s = sample[i];
+        float4 o, x;
+        o.x = u.x + cfg * (c.x - u.x); o.y = u.y + cfg * (c.y - u.y);
+        o.z = u.z + cfg * (c.z - u.z); o.w = u.w + cfg * (c.w - u.w);
+        x.x = o.x + t_hat * (s.x - o.x); x.y = o.y + t_hat * (s.y - o.y);
+        x.z = o.z + t_hat * (s.z - o.z); x.w = o.w + t_hat * (s.w - o.w);
+        cfg_out[i] = o;
+        if (xhat) xhat[i] = x;
+    }
+}
+
+__global__ void sampler_update_kernel(const float4* __restrict__ cfg1, const float4* __restrict__ d2, float cfg,
+                                      int use_heun, float t, float p, const float4* __restrict__ noise,
+                                      float4* __restrict__ sample, float4* __restrict__ cfg_out, long n4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 o = cfg1[i];
+        if (use_heun) {
+            const float4 c = d2[i], u = d2[i + n4];
+            o.x = o.x + 0.5f * ((u.x + cfg * (c.x - u.x)) - o.x);
+            o.y = o.y + 0.5f * ((u.y + cfg * (c.y - u.y)) - o.y);
+            o.z = o.z + 0.5f * ((u.z + cfg * (c.z - u.z)) - o.z);
+            o.w = o.w + 0.5f * ((u.w + cfg * (c.w - u.w)) - o.w);
+        }
+        float4 s = sample[i];
+        s.x = o.x + t * (s.x - o.x); s.y = o.y + t * (s.y - o.y);
+        s.z = o.z + t * (s.z - o.z); s.w = o.w + t * (s.w - o.w);
+        if (noise) {
+            const float4 nz = noise[i];
+            s.x += p * nz.x; s.y += p * nz.y; s.z += p * nz.z; s.w += p * nz.w;
+        }
+        sample[i] = s;
+        if (cfg_out) cfg_out[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// naive reference convolution (tests only)
+// ------------------------------------------------------------------------------------------
+__global__ void conv_naive_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                  __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cin, int Cout, int ks,
+                                  int groups) {
+    const int cin_g = Cin / groups, cout_g = Cout / groups;
+    const long total = (long)B * H * W * Cout;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % Cout);
+        const long pix = idx / Cout;
+        const int wq = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+        const int g = co / cout_g;
+        float acc = 0.f;
+        for (int tap = 0; tap < ks * ks; ++tap) {
+            const int hh = h + tap / ks - ks / 2, ww = wq + tap % ks - ks / 2;
+            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+            const __nv_bfloat16* xp = x + (((long)b * H + hh) * W + ww) * Cin + g * cin_g;
+            const __nv_bfloat16* wp = w + ((size_t)co * ks * ks + tap) * cin_g;
+            for (int i = 0; i < cin_g; ++i) acc += __bfloat162float(xp[i]) * __bfloat162float(wp[i]);
+        }
+        out[idx] = __float2bfloat16_rn(acc);
+    }
+}
+
+inline int grid_for(long total, int block, int cap_mult = 8) {
+    const long blocks = (total + block - 1) / block;
+    return (int)std::max<long>(1, std::min<long>(blocks, (long)dd_num_sms() * cap_mult));
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_format, int O, int I_g, int taps,
+                              const float* gain_dev, float gain_host, int normalize, int perm, int head_dim,
+                              void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(w && out && O > 0 && I_g > 0 && taps > 0, "dd_weight_prep: bad arguments");
+    DD_REQUIRE(out_format == DD_WFMT_BF16_OTI || out_format == DD_WFMT_F32_OIT, "dd_weight_prep: bad out_format");
+    DD_REQUIRE(perm == DD_WPERM_NONE || (perm == DD_WPERM_QK && head_dim > 0 && O % (2 * head_dim) == 0),
+               "dd_weight_prep: bad permutation arguments");
+    if (w_is_bf16)
+        weight_prep_kernel<true><<<O, 128, 0, stream>>>(w, out, out_format, O, I_g, taps, gain_dev, gain_host, normalize,
+                                                        perm, head_dim);
+    else
+        weight_prep_kernel<false><<<O, 128, 0, stream>>>(w, out, out_format, O, I_g, taps, gain_dev, gain_host,
+                                                         normalize, perm, head_dim);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_pixnorm_silu(const void* t, void* x_out, void* s_out, long npix, int C, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(t && x_out && s_out, "dd_pixnorm_silu: null pointer");
+    DD_REQUIRE(C % 8 == 0 && C <= kMaxVecPerLane * 256, "dd_pixnorm_silu: C=%d unsupported", C);
+    if (npix == 0) return 0;
+    const int warps = 8;
+    pixnorm_silu_kernel<<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, stream>>>(
+        static_cast<const uint4*>(t), static_cast<uint4*>(x_out), static_cast<uint4*>(s_out), npix, C);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_cat_silu(const void* a, int Ca, const void* b, int Cb, float wa, float wb, int upsample, void* xcat_out,
+                           void* s_out, int B, int H, int W, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(a && s_out && Ca > 0 && Ca % 8 == 0 && Cb % 8 == 0, "dd_cat_silu: bad arguments");
+    DD_REQUIRE(Cb == 0 || b, "dd_cat_silu: skip pointer missing");
+    DD_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "dd_cat_silu: upsample needs even output size");
+    const long total = (long)B * H * W * ((Ca + Cb) / 8);
+    if (total == 0) return 0;
+    cat_silu_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(a), Ca / 8,
+                                                              static_cast<const uint4*>(b), Cb / 8, wa, wb, upsample,
+                                                              static_cast<uint4*>(xcat_out), static_cast<uint4*>(s_out),
+                                                              B, H, W);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_avgpool2(const void* x, void* out, int B, int H, int W, int C, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "dd_avgpool2: bad arguments");
+    const long total = (long)B * (H / 2) * (W / 2) * (C / 8);
+    if (total == 0) return 0;
+    avgpool2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), B,
+                                                              H, W, C / 8);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_conv_in(const float* x_in, const float* sigma, float sigma_data, const float* ln_freqs,
+                          const float* w, void* out, int B, int Cin, int H, int W, int Cout, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x_in && sigma && ln_freqs && w && out, "dd_conv_in: null pointer");
+    const dim3 grid(ceil_div(W, kStemPix), H, B);
+#define DD_LAUNCH_STEM(CT)                                                                                       \
+    conv_in_kernel<CT><<<grid, 256, 0, stream>>>(x_in, sigma, sigma_data, ln_freqs, w,                          \
+                                                 static_cast<__nv_bfloat16*>(out), B, H, W, Cout)
+    switch (Cin) {
+        case 1: DD_LAUNCH_STEM(3); break;
+        case 2: DD_LAUNCH_STEM(4); break;
+        case 4: DD_LAUNCH_STEM(6); break;
+        case 8: DD_LAUNCH_STEM(10); break;
+        default: DD_REQUIRE(false, "dd_conv_in: in_channels=%d unsupported (1,2,4,8)", Cin);
+    }
+#undef DD_LAUNCH_STEM
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_conv_out(const void* x, const float* w, const float* x_in, const float* sigma, float sigma_data,
+                           const float* x_ref, float* d_out, int B, int C, int H, int W, int Cout, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && w && x_in && sigma && d_out, "dd_conv_out: null pointer");
+    DD_REQUIRE(C % 8 == 0, "dd_conv_out: C must be a multiple of 8");
+    const size_t smem = (size_t)9 * Cout * C * sizeof(float);
+    DD_REQUIRE(smem <= 200 * 1024, "dd_conv_out: weights (%zu B) do not fit in shared memory", smem);
+    const int grid = std::min<long>((long)dd_num_sms() * 2, ((long)B * H * W + 7) / 8);
+#define DD_LAUNCH_HEAD(CO)                                                                                           \
+    do {                                                                                                             \
+        DD_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                           (int)smem));                                                              \
+        conv_out_kernel<CO><<<grid, 256, smem, stream>>>(static_cast<const uint4*>(x), w, x_in, sigma, sigma_data,   \
+                                                         x_ref, d_out, B, C, H, W);                                  \
+    } while (0)
+    switch (Cout) {
+        case 1: DD_LAUNCH_HEAD(1); break;
+        case 2: DD_LAUNCH_HEAD(2); break;
+        case 4: DD_LAUNCH_HEAD(4); break;
+        case 8: DD_LAUNCH_HEAD(8); break;
+        default: DD_REQUIRE(false, "dd_conv_out: out_channels=%d unsupported (1,2,4,8)", Cout);
+    }
+#undef DD_LAUNCH_HEAD
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_noise_embedding(const float* sigma, const float* freqs, const float* phases, int cnoise,
+                                  const void* w_noise, int w_is_bf16, int normalize, const float* label_emb,
+                                  float label_balance, float* emb_out, int B, int cemb, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(sigma && freqs && phases && w_noise && label_emb && emb_out, "dd_noise_embedding: null pointer");
+    const dim3 grid(ceil_div(cemb, 8), B);
+    const size_t smem = (size_t)cnoise * sizeof(float);
+    if (w_is_bf16)
+        noise_embedding_kernel<true><<<grid, 256, smem, stream>>>(sigma, freqs, phases, cnoise, w_noise, normalize,
+                                                                  label_emb, label_balance, emb_out, cemb);
+    else
+        noise_embedding_kernel<false><<<grid, 256, smem, stream>>>(sigma, freqs, phases, cnoise, w_noise, normalize,
+                                                                   label_emb, label_balance, emb_out, cemb);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_emb_affine(const dd_affine_desc* descs_dev, int n_descs, int max_O, const float* emb, int B, int cemb,
+                             void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && emb && n_descs > 0 && max_O > 0, "dd_emb_affine: bad arguments");
+    const dim3 grid(ceil_div(max_O, 8), n_descs);
+    emb_affine_kernel<<<grid, 256, 0, stream>>>(descs_dev, emb, B, cemb);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_sampler_cfg_lerp(const float* d_2b, const float* sample, float cfg_scale, float t_hat, float* cfg_out,
+                                   float* x_hat_out, long n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(d_2b && sample && cfg_out, "dd_sampler_cfg_lerp: null pointer");
+    DD_REQUIRE(n % 4 == 0, "dd_sampler_cfg_lerp: element count must be a multiple of 4");
+    if (n == 0) return 0;
+    sampler_cfg_lerp_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(d_2b), reinterpret_cast<const float4*>(sample), cfg_scale, t_hat,
+        reinterpret_cast<float4*>(cfg_out), reinterpret_cast<float4*>(x_hat_out), n / 4);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_sampler_update(const float* cfg1, const float* d2_2b, float cfg_scale, int use_heun, float t, float p,
+                                 const float* noise, float* sample, float* cfg_out, long n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(cfg1 && sample && (!use_heun || d2_2b), "dd_sampler_update: null pointer");
+    DD_REQUIRE(n % 4 == 0, "dd_sampler_update: element count must be a multiple of 4");
+    if (n == 0) return 0;
+    sampler_update_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(cfg1), reinterpret_cast<const float4*>(d2_2b), cfg_scale, use_heun, t, p,
+        reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(sample), reinterpret_cast<float4*>(cfg_out),
+        n / 4);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_mpconv_forward_naive(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
+                                       int ksize, int groups, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && w && out, "dd_mpconv_forward_naive: null pointer");
+    const long total = (long)B * H * W * Cout;
+    if (total == 0) return 0;
+    conv_naive_kernel<<<grid_for(total, 256, 32), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(out), B,
+        H, W, Cin, Cout, ksize, groups);
+    DD_CHECK_LAUNCH();
+    return 0;
+}

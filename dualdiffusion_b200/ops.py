@@ -1,0 +1,193 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is plumbing here (device memory + streams):
+every function allocates its outputs with torch and enqueues exactly the C-ABI call(s) named in
+include/dualdiffusion_b200.h on torch's current CUDA stream.  Activations are NHWC bf16 tensors
+of logical shape [B, H, W, C]."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+launch_count = 0   # number of C-ABI kernel launches issued (bench.py reports it as gpu_launches)
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _is_bf16(t: Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return 1
+    if t.dtype == torch.float32:
+        return 0
+    raise TypeError(f"weights must be fp32 or bf16, got {t.dtype}")
+
+
+def weight_prep(w: Tensor, gain: Optional[Tensor] = None, gain_host: float = 1.0, normalize: bool = False,
+                fmt: int = L.WFMT_BF16_OTI, qk_head_dim: int = 0, out: Optional[Tensor] = None) -> Tensor:
+    """MPConv weight path (reference modules/mp_tools.py:359-364) fused into one pass."""
+    L.require_cuda(w)
+    w = w.contiguous()
+    O = w.shape[0]
+    I_g = w.shape[1]
+    taps = 1
+    for s in w.shape[2:]:
+        taps *= s
+    if out is None:
+        if fmt == L.WFMT_BF16_OTI:
+            out = torch.empty((O, taps, I_g), device=w.device, dtype=torch.bfloat16)
+        else:
+            out = torch.empty((O, I_g, taps), device=w.device, dtype=torch.float32)
+    perm = L.WPERM_QK if qk_head_dim else L.WPERM_NONE
+    L.check(L.load().dd_weight_prep(L.ptr(w), _is_bf16(w), L.ptr(out), fmt, O, I_g, taps, L.ptr(gain), gain_host,
+                                    int(normalize), perm, qk_head_dim, L.stream_ptr()))
+    _count()
+    return out
+
+
+def mpconv(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1, *, epi: int = L.EPI_NONE,
+           epi2: int = L.EPI2_NONE, alpha: float = 1.0, beta: float = 0.0, clip: float = 0.0,
+           scale: Optional[Tensor] = None, scale2: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+           out: Optional[Tensor] = None, out2: Optional[Tensor] = None):
+    """tcgen05 implicit-GEMM MPConv (reference modules/mp_tools.py:369) with fused block epilogue."""
+    B, H, W, Cin = x.shape
+    Cout = w_prepped.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16)
+    if epi2 != L.EPI2_NONE and out2 is None:
+        out2 = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16)
+    e = L.ConvEpilogue(epi, epi2, alpha, beta, clip, L.ptr(scale), L.ptr(scale2), L.ptr(residual), L.ptr(out2))
+    L.check(L.load().dd_mpconv_forward(L.ptr(x), L.ptr(w_prepped), L.ptr(out), B, H, W, Cin, Cout, ksize, groups,
+                                       C.byref(e), L.stream_ptr()))
+    _count()
+    return (out, out2) if epi2 != L.EPI2_NONE else out
+
+
+def mpconv_naive(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1) -> Tensor:
+    B, H, W, Cin = x.shape
+    Cout = w_prepped.shape[0]
+    out = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_mpconv_forward_naive(L.ptr(x), L.ptr(w_prepped), L.ptr(out), B, H, W, Cin, Cout, ksize, groups,
+                                             L.stream_ptr()))
+    _count()
+    return out
+
+
+def conv_in(x_in: Tensor, sigma: Tensor, sigma_data: float, ln_freqs: Tensor, w_f32: Tensor,
+            out: Optional[Tensor] = None) -> Tensor:
+    B, Cin, H, W = x_in.shape
+    Cout = w_f32.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), device=x_in.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_conv_in(L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(ln_freqs), L.ptr(w_f32), L.ptr(out), B, Cin,
+                                H, W, Cout, L.stream_ptr()))
+    _count()
+    return out
+
+
+def conv_out(x: Tensor, w_f32: Tensor, x_in: Tensor, sigma: Tensor, sigma_data: float,
+             x_ref: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    B, H, W, Cc = x.shape
+    Cout = w_f32.shape[0]
+    if out is None:
+        out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
+    L.check(L.load().dd_conv_out(L.ptr(x), L.ptr(w_f32), L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(x_ref), L.ptr(out),
+                                 B, Cc, H, W, Cout, L.stream_ptr()))
+    _count()
+    return out
+
+
+def noise_embedding(sigma: Tensor, freqs: Tensor, phases: Tensor, w_noise: Tensor, label_emb: Tensor,
+                    label_balance: float, normalize: bool = False, out: Optional[Tensor] = None) -> Tensor:
+    B = sigma.numel()
+    cemb, cnoise = w_noise.shape
+    if out is None:
+        out = torch.empty((B, cemb), device=sigma.device, dtype=torch.float32)
+    L.check(L.load().dd_noise_embedding(L.ptr(sigma), L.ptr(freqs), L.ptr(phases), cnoise, L.ptr(w_noise),
+                                        _is_bf16(w_noise), int(normalize), L.ptr(label_emb), label_balance, L.ptr(out),
+                                        B, cemb, L.stream_ptr()))
+    _count()
+    return out
+
+
+def make_affine_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int]:
+    """Pack dd_affine_desc records into a device buffer.  Each entry: w, gain, out, groups, bias, normalize."""
+    arr = (L.AffineDesc * len(entries))()
+    max_o = 0
+    for i, e in enumerate(entries):
+        w = e["w"]
+        O, I = w.shape[0], w.shape[1]
+        arr[i] = L.AffineDesc(L.ptr(w), L.ptr(e.get("gain")), L.ptr(e["out"]), O, I, e.get("groups", 1), _is_bf16(w),
+                              e.get("bias", 0.0), int(e.get("normalize", False)))
+        max_o = max(max_o, O)
+    raw = bytes(arr)
+    buf = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    return buf, max_o
+
+
+def emb_affine(descs: Tensor, n: int, max_o: int, emb: Tensor) -> None:
+    B, cemb = emb.shape
+    L.check(L.load().dd_emb_affine(L.ptr(descs), n, max_o, L.ptr(emb), B, cemb, L.stream_ptr()))
+    _count()
+
+
+def pixnorm_silu(t: Tensor, x_out: Optional[Tensor] = None, s_out: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    Cc = t.shape[-1]
+    npix = t.numel() // Cc
+    if x_out is None:
+        x_out = torch.empty_like(t)
+    if s_out is None:
+        s_out = torch.empty_like(t)
+    L.check(L.load().dd_pixnorm_silu(L.ptr(t), L.ptr(x_out), L.ptr(s_out), npix, Cc, L.stream_ptr()))
+    _count()
+    return x_out, s_out
+
+
+def cat_silu(a: Tensor, b: Optional[Tensor], wa: float, wb: float, upsample: bool, need_cat: bool = True):
+    B, Ha, Wa, Ca = a.shape
+    H, W = (Ha * 2, Wa * 2) if upsample else (Ha, Wa)
+    Cb = 0 if b is None else b.shape[-1]
+    xcat = torch.empty((B, H, W, Ca + Cb), device=a.device, dtype=torch.bfloat16) if need_cat else None
+    s = torch.empty((B, H, W, Ca + Cb), device=a.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_cat_silu(L.ptr(a), Ca, L.ptr(b), Cb, wa, wb, int(upsample), L.ptr(xcat), L.ptr(s), B, H, W,
+                                 L.stream_ptr()))
+    _count()
+    return xcat, s
+
+
+def avgpool2(x: Tensor) -> Tensor:
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, H // 2, W // 2, Cc), device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_avgpool2(L.ptr(x), L.ptr(out), B, H, W, Cc, L.stream_ptr()))
+    _count()
+    return out
+
+
+def attention(qk: Tensor, v: Tensor, scale_v: Tensor, heads: int, head_dim: int = 64) -> Tensor:
+    B, H, W, Cc = v.shape
+    out = torch.empty_like(v)
+    L.check(L.load().dd_attention(L.ptr(qk), L.ptr(v), L.ptr(scale_v), L.ptr(out), B, H * W, heads, head_dim,
+                                  L.stream_ptr()))
+    _count()
+    return out
+
+
+def sampler_cfg_lerp(d_2b: Tensor, sample: Tensor, cfg_scale: float, t_hat: float, cfg_out: Tensor,
+                     x_hat_out: Optional[Tensor]) -> None:
+    L.check(L.load().dd_sampler_cfg_lerp(L.ptr(d_2b), L.ptr(sample), cfg_scale, t_hat, L.ptr(cfg_out), L.ptr(x_hat_out),
+                                         sample.numel(), L.stream_ptr()))
+    _count()
+
+
+def sampler_update(cfg1: Tensor, d2_2b: Optional[Tensor], cfg_scale: float, use_heun: bool, t: float, p: float,
+                   noise: Optional[Tensor], sample: Tensor, cfg_out: Optional[Tensor]) -> None:
+    L.check(L.load().dd_sampler_update(L.ptr(cfg1), L.ptr(d2_2b), cfg_scale, int(use_heun), t, p, L.ptr(noise),
+                                       L.ptr(sample), L.ptr(cfg_out), sample.numel(), L.stream_ptr()))
+    _count()

@@ -1,0 +1,150 @@
+/*
+ * dualdiffusion_b200 — C ABI of the B200-native (sm_100a) denoising hot path.
+ *
+ * The reference (parlance-zz/dualdiffusion) is pure Python/PyTorch: it has no FFI of its own, and
+ * every entry point below replaces a *PyTorch library call site* of the reference, cited per
+ * function as <file>:<line> relative to /root/reference/src.  The reference-side binding is a
+ * ctypes stub (see INTEGRATION.md and dualdiffusion_b200/_lib.py); the functions are called from
+ * the drop-in module classes in dualdiffusion_b200/modules, never by reference code directly.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; dd_last_error() then returns a
+ *     thread-local, NUL-terminated description (Python shim raises RuntimeError with it);
+ *   - all pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call only
+ *     enqueues work on that stream and never synchronises, so calls are CUDA-graph capturable;
+ *   - activations are NHWC ("channels_last") bf16: [B][H][W][C], C contiguous;
+ *   - model input/output latents keep the reference's NCHW fp32 layout.
+ */
+#ifndef DUALDIFFUSION_B200_H
+#define DUALDIFFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DD_API __attribute__((visibility("default")))
+#else
+#define DD_API
+#endif
+
+/* ---- library ------------------------------------------------------------------------------ */
+DD_API const char* dd_last_error(void);
+DD_API int dd_abi_version(void);
+/* Fills SM count and compute capability of the current device. */
+DD_API int dd_device_info(int* num_sms, int* cc_major, int* cc_minor);
+
+/* ---- weight preparation: MPConv.forward weight path, modules/mp_tools.py:359-364 ----------- */
+/* w      : [O][I_g][taps] weights as stored by the reference (OIHW, fp32 or bf16)
+ * out    : DD_WFMT_BF16_OTI : bf16 [O'][taps][I_g]  (operand layout of dd_mpconv_forward)
+ *          DD_WFMT_F32_OIT  : fp32 [O][I_g][taps]   (same order as the input; dd_conv_in/out)
+ * math   : w_o <- w_o / (1e-4 + ||w_o||_2 / sqrt(fan_in))   if normalize != 0  (training mode)
+ *          w_o <- w_o * gain_host * (*gain_dev) / sqrt(fan_in),  fan_in = I_g * taps
+ * gain_dev may be NULL (== 1).  perm = DD_WPERM_QK de-interleaves the attn_qk output channels:
+ * reference row (head*2*d + 2*c + j) -> row (j*O/2 + head*d + c)  (unet_edm2_b4.py:137-138),
+ * so q and k come out of the GEMM as two contiguous [heads][d] halves.                          */
+#define DD_WFMT_BF16_OTI 0
+#define DD_WFMT_F32_OIT 1
+#define DD_WPERM_NONE 0
+#define DD_WPERM_QK 1
+DD_API int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_format, int O, int I_g, int taps,
+                   const float* gain_dev, float gain_host, int normalize, int perm, int head_dim, void* stream);
+
+/* ---- MPConv forward: F.conv2d in MPConv.forward, modules/mp_tools.py:369 ------------------- */
+/* Stride-1, zero "same" padding, ksize in {1,3}, Cin/groups and Cout/groups multiples of 32.
+ * Fused epilogue (Block.forward, modules/unets/unet_edm2_b4.py:119-131,150-157):
+ *   DD_EPI_NONE       : out = acc
+ *   DD_EPI_SCALE_SILU : out = mp_silu(acc * scale[b][c])                  (:121-122, :150-151)
+ *   DD_EPI_RESIDUAL   : out = clip(alpha*acc + beta*residual[b][h][w][c]) (mp_sum :131,:154; clip :157)
+ * optional second output from the same (pre-rounding) value:
+ *   DD_EPI2_SILU      : out2 = mp_silu(out)                               (next conv_res0 input, :119)
+ *   DD_EPI2_SCALE     : out2 = out * scale2[b][c]                         (attn_qk input, :135-136)   */
+#define DD_EPI_NONE 0
+#define DD_EPI_SCALE_SILU 1
+#define DD_EPI_RESIDUAL 2
+#define DD_EPI2_NONE 0
+#define DD_EPI2_SILU 1
+#define DD_EPI2_SCALE 2
+typedef struct dd_conv_epilogue {
+    int mode;              /* DD_EPI_*  */
+    int mode2;             /* DD_EPI2_* */
+    float alpha, beta;     /* DD_EPI_RESIDUAL */
+    float clip;            /* <= 0: no clip */
+    const void* scale;     /* fp32 [B][Cout] */
+    const void* scale2;    /* fp32 [B][Cout] */
+    const void* residual;  /* bf16 [B][H][W][Cout] */
+    void* out2;            /* bf16 [B][H][W][Cout] */
+} dd_conv_epilogue;
+DD_API int dd_mpconv_forward(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin, int Cout,
+                      int ksize, int groups, const dd_conv_epilogue* epilogue_host, void* stream);
+
+/* Scalar CUDA-core convolution with the same contract as dd_mpconv_forward (no epilogue).
+ * Debug/triangulation aid for the tests only; never called by the product path.                 */
+DD_API int dd_mpconv_forward_naive(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin, int Cout,
+                            int ksize, int groups, void* stream);
+
+/* ---- UNet stem and head: modules/unets/unet_edm2_b4.py:258-271 and :290-291 ---------------- */
+/* x = cat(c_in(sigma)*x_in, ones, ln_freqs) -> conv_in 3x3 (Cin+2 -> Cout), output NHWC bf16.
+ * w_prepped: fp32 [Cout][Cin+2][9] from dd_weight_prep(DD_WFMT_F32_OIT).                         */
+DD_API int dd_conv_in(const float* x_in_nchw, const float* sigma, float sigma_data, const float* ln_freqs_h,
+               const float* w_prepped, void* out_nhwc, int B, int Cin, int H, int W, int Cout, void* stream);
+/* D = c_skip(sigma)*x_in + c_out(sigma)*conv_out(x); w_prepped fp32 [Cout][C][9] includes out_gain.
+ * x_ref (optional, [B][Cout+1][H][W] fp32): D = mp_sum(x_ref[:, :-1], D, t = x_ref[:, -1:])  (:293-294) */
+DD_API int dd_conv_out(const void* x_nhwc, const float* w_prepped, const float* x_in_nchw, const float* sigma,
+                float sigma_data, const float* x_ref_nchw, float* d_out_nchw, int B, int C, int H, int W, int Cout,
+                void* stream);
+
+/* ---- embeddings: unet_edm2_b4.py:232-238, :273-276; MPFourier mp_tools.py:324-330 ---------- */
+/* emb[b] = mp_silu(mp_sum(W_noise @ fourier(ln(sigma_b)/4) / sqrt(cnoise), label_emb[b], t))      */
+DD_API int dd_noise_embedding(const float* sigma, const float* freqs, const float* phases, int cnoise, const void* w_noise,
+                       int w_is_bf16, int normalize, const float* label_emb, float label_balance, float* emb_out,
+                       int B, int cemb, void* stream);
+/* Batched per-block embedding projections (emb_linear / emb_linear_qk / emb_linear_v, :121,:135,:150):
+ *   out_j[b][o] = bias_j + gain_j * sum_i W_j[o][i] * emb[b][(o / (O_j/groups_j)) * I_j + i] / sqrt(I_j)
+ * (+ per-row weight normalisation when normalize != 0).  descs_dev is a DEVICE array.             */
+typedef struct dd_affine_desc {
+    const void* w;       /* [O][I] fp32 or bf16 */
+    const float* gain;   /* device scalar, may be NULL (== 1) */
+    float* out;          /* [B][O] fp32 */
+    int O, I, groups, w_is_bf16;
+    float bias;
+    int normalize;
+} dd_affine_desc;
+DD_API int dd_emb_affine(const dd_affine_desc* descs_dev, int n_descs, int max_O, const float* emb, int B, int cemb,
+                  void* stream);
+
+/* ---- elementwise block glue ---------------------------------------------------------------- */
+/* pixel norm (mp_tools.py:42-49 with dim=1) + mp_silu: x = t/(1e-4+rms_c(t)); s = mp_silu(x)      */
+DD_API int dd_pixnorm_silu(const void* t, void* x_out, void* s_out, long npix, int C, void* stream);
+/* decoder input: xcat = [wa * up(a), wb * b] (mp_cat mp_tools.py:294-301; nearest x2 :79), s = mp_silu(xcat).
+ * b may be NULL (Cb = 0); xcat_out may be NULL when only s is needed; H,W are OUTPUT sizes.        */
+DD_API int dd_cat_silu(const void* a, int Ca, const void* b, int Cb, float wa, float wb, int upsample, void* xcat_out,
+                void* s_out, int B, int H, int W, void* stream);
+/* 2x2 mean pooling (mp_tools.py:77), H,W are INPUT sizes (even).                                  */
+DD_API int dd_avgpool2(const void* x, void* out, int B, int H, int W, int C, void* stream);
+
+/* ---- attention: unet_edm2_b4.py:137-151 ---------------------------------------------------- */
+/* q|k halves [B][N][2C] (after DD_WPERM_QK), v [B][N][C]; per-head cosine normalisation of q,k,v over
+ * head_dim (eps 1e-4), softmax(q k^T / sqrt(head_dim)) v, then out = mp_silu(y * scale_v[b][c]).     */
+DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, void* out, int B, int N, int heads,
+                 int head_dim, void* stream);
+
+/* ---- EDM sampler step glue: pipelines/dual_diffusion_pipeline.py:699-737 -------------------- */
+/* cfg = lerp(D[B:], D[:B], cfg_scale); x_hat = lerp(cfg, sample, t_hat)   (:701, :712)             */
+DD_API int dd_sampler_cfg_lerp(const float* d_2b, const float* sample, float cfg_scale, float t_hat, float* cfg_out,
+                        float* x_hat_out, long n_per_batch_total, void* stream);
+/* cfg2 = lerp(D2[B:], D2[:B], cfg_scale); cfg = use_heun ? lerp(cfg1, cfg2, .5) : cfg1;
+ * sample = lerp(cfg, sample, t) + p * noise   (:717-724, :734-737); noise may be NULL (p = 0).      */
+DD_API int dd_sampler_update(const float* cfg1, const float* d2_2b, float cfg_scale, int use_heun, float t, float p,
+                      const float* noise, float* sample_inout, float* cfg_out, long n_total, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUALDIFFUSION_B200_H */
