@@ -52,14 +52,19 @@ _SIGNATURES = {
     "dd_noise_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_float,
                                    c_void_p, c_int, c_int, c_void_p]),
     "dd_emb_affine": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dd_label_embedding": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                   c_int, c_void_p]),
+    "dd_sigma_logvar": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "dd_mp_fourier": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "dd_axpby": (c_int, [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_long, c_void_p]),
     "dd_pixnorm_silu": (c_int, [c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p]),
     "dd_cat_silu": (c_int, [c_void_p, c_int, c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_int,
                             c_int, c_int, c_void_p]),
     "dd_avgpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_long, c_void_p]),
+    "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
     "dd_sampler_update": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
-                                  c_long, c_void_p]),
+                                  c_int, c_long, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

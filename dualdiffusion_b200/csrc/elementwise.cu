@@ -345,11 +345,87 @@ __global__ void emb_affine_kernel(const dd_affine_desc* __restrict__ descs, cons
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// class-label embedding (UNet.get_embeddings) and loss log-variance head (get_sigma_loss_logvar)
+// ------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void label_embedding_kernel(const float* __restrict__ emb_in, int Bc, int I, const void* __restrict__ w_label,
+                                       const void* __restrict__ w_uncond, const float* __restrict__ mask, int normalize,
+                                       float* __restrict__ out, int cemb) {
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int bm = blockIdx.y;
+    if (o >= cemb) return;
+    const float* e = emb_in + (size_t)(Bc == 1 ? 0 : bm) * I;
+    float acc = 0.f, ee = 0.f, ww = 0.f;
+    for (int i = lane; i < I; i += 32) {
+        const float wv = load_w<kBf16>(w_label, (size_t)o * I + i);
+        const float ev = e[i];
+        acc += wv * ev; ee += ev * ev; ww += wv * wv;
+    }
+    acc = warp_sum(acc); ee = warp_sum(ee); ww = warp_sum(ww);
+    if (lane == 0) {
+        const float rs = rsqrtf((float)I);
+        float c = acc * rs / (kNormEps + sqrtf(ee) * rs);           // normalize(emb_in) then W/sqrt(I)
+        float u = load_w<kBf16>(w_uncond, o);                          // fan_in 1: W * 1
+        if (normalize) {
+            c /= (kNormEps + sqrtf(ww) * rs);
+            u /= (kNormEps + fabsf(u));
+        }
+        const float t = mask[bm];
+        out[(size_t)bm * cemb + o] = (u + t * (c - u)) * rsqrtf((1.f - t) * (1.f - t) + t * t);
+    }
+}
+
+template <bool kBf16>
+__global__ void logvar_kernel(const float* __restrict__ sigma, const float* __restrict__ freqs,
+                              const float* __restrict__ phases, int n, const void* __restrict__ w,
+                              float* __restrict__ out, int count) {
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= count) return;
+    const float c = logf(sigma[idx]) * 0.25f;
+    float acc = 0.f;
+    for (int i = lane; i < n; i += 32)
+        acc += load_w<kBf16>(w, i) * cosf(c * freqs[i] + phases[i]) * 1.41421356237f;
+    acc = warp_sum(acc);
+    if (lane == 0) out[idx] = acc * rsqrtf((float)n);
+}
+
+
+__global__ void mp_fourier_kernel(const float* __restrict__ x, const float* __restrict__ freqs,
+                                  const float* __restrict__ phases, int n, float* __restrict__ out, long total) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % n);
+        out[i] = cosf(x[i / n] * freqs[c] + phases[c]) * 1.41421356237f;
+    }
+}
+
+// out = clip(alpha*a + beta*b)   (mp_sum / lerp on bf16 activations)
+__global__ void axpby_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha, float beta,
+                             float clip, uint4* __restrict__ out, long nvec) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
+        const uint4 qa = __ldg(a + i), qb = __ldg(b + i);
+        const uint32_t ua[4] = {qa.x, qa.y, qa.z, qa.w}, ub[4] = {qb.x, qb.y, qb.z, qb.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 fa = unpack_bf16x2(ua[j]), fb = unpack_bf16x2(ub[j]);
+            const float r0 = fminf(fmaxf(alpha * fa.x + beta * fb.x, -clip), clip);
+            const float r1 = fminf(fmaxf(alpha * fa.y + beta * fb.y, -clip), clip);
+            o[j] = pack_bf16x2(r0, r1);
+        }
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // EDM sampler step (fp32 state)
 // ------------------------------------------------------------------------------------------
 __global__ void sampler_cfg_lerp_kernel(const float4* __restrict__ d, const float4* __restrict__ sample, float cfg,
-                                        float t_hat, float4* __restrict__ cfg_out, float4* __restrict__ xhat, long n4) {
+                                        float t_hat, float4* __restrict__ cfg_out, float4* __restrict__ xhat, int dup,
+                                        long n4) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const float4 c = d[i], u = d[i + n4], s = sample[i];
         float4 o, x;
@@ -358,13 +434,16 @@ __global__ void sampler_cfg_lerp_kernel(const float4* __restrict__ d, const floa
         x.x = o.x + t_hat * (s.x - o.x); x.y = o.y + t_hat * (s.y - o.y);
         x.z = o.z + t_hat * (s.z - o.z); x.w = o.w + t_hat * (s.w - o.w);
         cfg_out[i] = o;
-        if (xhat) xhat[i] = x;
+        if (xhat) {
+            xhat[i] = x;
+            if (dup) xhat[i + n4] = x;
+        }
     }
 }
 
 __global__ void sampler_update_kernel(const float4* __restrict__ cfg1, const float4* __restrict__ d2, float cfg,
                                       int use_heun, float t, float p, const float4* __restrict__ noise,
-                                      float4* __restrict__ sample, float4* __restrict__ cfg_out, long n4) {
+                                      float4* __restrict__ sample, float4* __restrict__ cfg_out, int dup, long n4) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 o = cfg1[i];
         if (use_heun) {
@@ -382,6 +461,7 @@ __global__ void sampler_update_kernel(const float4* __restrict__ cfg1, const flo
             s.x += p * nz.x; s.y += p * nz.y; s.z += p * nz.z; s.w += p * nz.w;
         }
         sample[i] = s;
+        if (dup) sample[i + n4] = s;
         if (cfg_out) cfg_out[i] = o;
     }
 }
@@ -552,21 +632,73 @@ extern "C" int dd_emb_affine(const dd_affine_desc* descs_dev, int n_descs, int m
     return 0;
 }
 
+
+extern "C" int dd_label_embedding(const float* emb_in, int Bc, int I, const void* w_label, const void* w_uncond,
+                                  int w_is_bf16, const float* mask, int Bm, int normalize, float* out, int cemb,
+                                  void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(emb_in && w_label && w_uncond && mask && out, "dd_label_embedding: null pointer");
+    DD_REQUIRE(Bc == 1 || Bc == Bm, "dd_label_embedding: embedding batch %d does not broadcast to mask batch %d", Bc, Bm);
+    const dim3 grid(ceil_div(cemb, 8), Bm);
+    if (w_is_bf16)
+        label_embedding_kernel<true><<<grid, 256, 0, stream>>>(emb_in, Bc, I, w_label, w_uncond, mask, normalize, out, cemb);
+    else
+        label_embedding_kernel<false><<<grid, 256, 0, stream>>>(emb_in, Bc, I, w_label, w_uncond, mask, normalize, out, cemb);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_sigma_logvar(const float* sigma, int count, const float* freqs, const float* phases, int n,
+                               const void* w, int w_is_bf16, float* out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(sigma && freqs && phases && w && out, "dd_sigma_logvar: null pointer");
+    if (count == 0) return 0;
+    if (w_is_bf16) logvar_kernel<true><<<ceil_div(count, 8), 256, 0, stream>>>(sigma, freqs, phases, n, w, out, count);
+    else logvar_kernel<false><<<ceil_div(count, 8), 256, 0, stream>>>(sigma, freqs, phases, n, w, out, count);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+
+extern "C" int dd_mp_fourier(const float* x, int count, const float* freqs, const float* phases, int n, float* out,
+                             void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && freqs && phases && out, "dd_mp_fourier: null pointer");
+    const long total = (long)count * n;
+    if (total == 0) return 0;
+    mp_fourier_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, freqs, phases, n, out, total);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_axpby(const void* a, const void* b, float alpha, float beta, float clip, void* out, long n,
+                        void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(a && b && out, "dd_axpby: null pointer");
+    DD_REQUIRE(n % 8 == 0, "dd_axpby: element count must be a multiple of 8");
+    if (n == 0) return 0;
+    axpby_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b),
+                                                           alpha, beta, clip > 0.f ? clip : INFINITY,
+                                                           static_cast<uint4*>(out), n / 8);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int dd_sampler_cfg_lerp(const float* d_2b, const float* sample, float cfg_scale, float t_hat, float* cfg_out,
-                                   float* x_hat_out, long n, void* stream_) {
+                                   float* x_hat_out, int dup, long n, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(d_2b && sample && cfg_out, "dd_sampler_cfg_lerp: null pointer");
     DD_REQUIRE(n % 4 == 0, "dd_sampler_cfg_lerp: element count must be a multiple of 4");
     if (n == 0) return 0;
     sampler_cfg_lerp_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(
         reinterpret_cast<const float4*>(d_2b), reinterpret_cast<const float4*>(sample), cfg_scale, t_hat,
-        reinterpret_cast<float4*>(cfg_out), reinterpret_cast<float4*>(x_hat_out), n / 4);
+        reinterpret_cast<float4*>(cfg_out), reinterpret_cast<float4*>(x_hat_out), dup, n / 4);
     DD_CHECK_LAUNCH();
     return 0;
 }
 
 extern "C" int dd_sampler_update(const float* cfg1, const float* d2_2b, float cfg_scale, int use_heun, float t, float p,
-                                 const float* noise, float* sample, float* cfg_out, long n, void* stream_) {
+                                 const float* noise, float* sample, float* cfg_out, int dup, long n, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(cfg1 && sample && (!use_heun || d2_2b), "dd_sampler_update: null pointer");
     DD_REQUIRE(n % 4 == 0, "dd_sampler_update: element count must be a multiple of 4");
@@ -574,7 +706,7 @@ extern "C" int dd_sampler_update(const float* cfg1, const float* d2_2b, float cf
     sampler_update_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(
         reinterpret_cast<const float4*>(cfg1), reinterpret_cast<const float4*>(d2_2b), cfg_scale, use_heun, t, p,
         reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(sample), reinterpret_cast<float4*>(cfg_out),
-        n / 4);
+        dup, n / 4);
     DD_CHECK_LAUNCH();
     return 0;
 }

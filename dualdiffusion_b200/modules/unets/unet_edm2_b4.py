@@ -1,0 +1,468 @@
+"""B200-native drop-in for the reference's EDM2 latent-diffusion UNet
+(`modules.unets.unet_edm2_b4.UNet`, /root/reference/src/modules/unets/unet_edm2_b4.py:160-296).
+
+Same constructor (`UNet(config: UNetConfig)`), same state_dict keys and OIHW fp32 parameter shapes (strict
+`load_state_dict` of a reference checkpoint works), same call signature
+`forward(x_in, sigma, format, embeddings, x_ref=None, perturbed_input=None) -> D_x` (fp32, NCHW) and the same
+helper methods (`get_embeddings`, `get_sigma_loss_logvar`, `get_latent_shape`, `normalize_weights`).  Selecting
+it is a one-line change in a model directory's model_index.json:
+    "unet": {"package": "dualdiffusion_b200.modules.unets.unet_edm2_b4", "class": "UNet"}
+
+The forward pass is a fixed schedule of C-ABI kernel launches (see `_Plan`): tcgen05 implicit-GEMM MPConvs with the
+block's elementwise work fused into their epilogues, a tensor-core attention kernel, and a handful of
+vectorised glue kernels; activations live in HBM as NHWC bf16.  In inference the whole schedule is captured
+once per input shape into a CUDA graph and replayed.  There is no PyTorch/CPU fallback: on a machine without
+the CUDA library the constructor works (parameters are plain tensors) but `forward` raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from ... import _lib as L
+from ... import ops
+from ..mp_tools import MPConv, MPFourier, mp_cat_weights
+from .unet import DualDiffusionUNet, DualDiffusionUNetConfig
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class UNetConfig(DualDiffusionUNetConfig):
+    """unet_edm2_b4.py:41-58 (field-for-field, same defaults)."""
+    model_channels: int = 256
+    logvar_channels: int = 128
+    channel_mult: Sequence[int] = (1, 2, 3, 4, 5)
+    channel_mult_noise: Optional[int] = None
+    channel_mult_emb: Optional[int] = None
+    channels_per_head: int = 64
+    num_layers_per_block: int = 2
+    label_balance: float = 0.5
+    concat_balance: float = 0.5
+    res_balance: float = 0.3
+    attn_balance: float = 0.3
+    attn_levels: Sequence[int] = (3, 4)
+    mlp_multiplier: int = 2
+    mlp_groups: int = 8
+
+
+class Block(torch.nn.Module):
+    """Parameter container with the reference Block's names/shapes (unet_edm2_b4.py:60-108).  The arithmetic
+    of Block.forward (:110-158) is scheduled by `_Plan`, not executed module-by-module."""
+
+    def __init__(self, level: int, in_channels: int, out_channels: int, emb_channels: int, flavor: str = "enc",
+                 resample_mode: str = "keep", dropout: float = 0.0, res_balance: float = 0.3,
+                 attn_balance: float = 0.3, clip_act: float = 256, mlp_multiplier: int = 2, mlp_groups: int = 8,
+                 channels_per_head: int = 64, use_attention: bool = False) -> None:
+        super().__init__()
+        self.level = level
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.use_attention = use_attention
+        self.num_heads = out_channels // channels_per_head
+        self.channels_per_head = channels_per_head
+        self.flavor = flavor
+        self.resample_mode = resample_mode
+        self.dropout = dropout
+        self.res_balance = res_balance
+        self.attn_balance = attn_balance
+        self.clip_act = clip_act
+        self.mlp_groups = mlp_groups
+
+        self.conv_res0 = MPConv(out_channels if flavor == "enc" else in_channels, out_channels * mlp_multiplier,
+                                kernel=(3, 3), groups=mlp_groups)
+        self.conv_res1 = MPConv(out_channels * mlp_multiplier, out_channels, kernel=(3, 3), groups=mlp_groups)
+        self.conv_skip = MPConv(in_channels, out_channels, kernel=(1, 1), groups=1)
+        self.emb_gain = torch.nn.Parameter(torch.zeros([]))
+        self.emb_linear = MPConv(emb_channels, out_channels * mlp_multiplier, kernel=(1, 1), groups=mlp_groups)
+        if use_attention:
+            self.emb_gain_qk = torch.nn.Parameter(torch.zeros([]))
+            self.emb_gain_v = torch.nn.Parameter(torch.zeros([]))
+            self.emb_linear_qk = MPConv(emb_channels, out_channels, kernel=(1, 1), groups=1)
+            self.emb_linear_v = MPConv(emb_channels, out_channels, kernel=(1, 1), groups=1)
+            self.attn_qk = MPConv(out_channels, out_channels * 2, kernel=(1, 1))
+            self.attn_v = MPConv(out_channels, out_channels, kernel=(1, 1))
+            self.attn_proj = MPConv(out_channels, out_channels, kernel=(1, 1))
+
+
+def _mp_sum_coeffs(t: float) -> Tuple[float, float]:
+    """mp_sum(a, b, t) = ca*a + cb*b  (mp_tools.py:274-279)."""
+    n = math.sqrt((1 - t) ** 2 + t ** 2)
+    return (1 - t) / n, t / n
+
+
+class _Plan:
+    """Per-device launch schedule state: prepared (scaled / re-laid-out) weights, the embedding-projection
+    descriptor table, and CUDA graphs keyed by input shape."""
+
+    def __init__(self, net: "UNet") -> None:
+        self.net = net
+        self.device = net.device
+        self.prepped: Dict[str, Tensor] = {}
+        self.versions: Dict[str, int] = {}
+        self.training: Optional[bool] = None
+        self.affine: Dict[int, dict] = {}      # batch size -> descs / outputs
+        self.graphs: Dict[tuple, dict] = {}
+        self.ln_freqs: Dict[tuple, Tensor] = {}
+        # scalar gains (emb_gain*, out_gain) gathered into one fp32 device vector: the kernels read them
+        # through float pointers whatever dtype the module's parameters are held in
+        self.gain_params: List[torch.nn.Parameter] = [p for n, p in net.named_parameters() if p.ndim == 0]
+        self.gain_index = {id(p): i for i, p in enumerate(self.gain_params)}
+        self.gains_f32 = torch.zeros(max(1, len(self.gain_params)), device=self.device, dtype=torch.float32)
+        self.gain_version = None
+        self._weight_items = None
+
+    def gain_ptr(self, p: torch.nn.Parameter) -> Tensor:
+        i = self.gain_index[id(p)]
+        return self.gains_f32[i:i + 1]
+
+    def refresh_gains(self) -> None:
+        ver = sum(p._version for p in self.gain_params)
+        if ver != self.gain_version:
+            self.gains_f32.copy_(torch.stack([p.detach().float() for p in self.gain_params]))
+            self.gain_version = ver
+
+    # ---- weight preparation cache: refresh when a parameter's version changes ----
+    def _weights(self) -> List[Tuple[str, torch.nn.Parameter, Optional[torch.nn.Parameter], int, int]]:
+        if self._weight_items is not None:
+            return self._weight_items
+        net = self.net
+        items = []
+        items.append(("enc.conv_in", net.enc["conv_in"].weight, None, L.WFMT_F32_OIT, 0))
+        for prefix, blocks in (("enc", net.enc), ("dec", net.dec)):
+            for name, blk in blocks.items():
+                if not isinstance(blk, Block):
+                    continue
+                p = f"{prefix}.{name}"
+                items.append((p + ".conv_res0", blk.conv_res0.weight, None, L.WFMT_BF16_OTI, 0))
+                items.append((p + ".conv_res1", blk.conv_res1.weight, None, L.WFMT_BF16_OTI, 0))
+                items.append((p + ".conv_skip", blk.conv_skip.weight, None, L.WFMT_BF16_OTI, 0))
+                if blk.use_attention:
+                    items.append((p + ".attn_qk", blk.attn_qk.weight, None, L.WFMT_BF16_OTI, blk.channels_per_head))
+                    items.append((p + ".attn_v", blk.attn_v.weight, None, L.WFMT_BF16_OTI, 0))
+                    items.append((p + ".attn_proj", blk.attn_proj.weight, None, L.WFMT_BF16_OTI, 0))
+        items.append(("conv_out", net.conv_out.weight, net.out_gain, L.WFMT_F32_OIT, 0))
+        self._weight_items = items
+        return items
+
+    def refresh_weights(self) -> None:
+        training = self.net.training
+        stale_all = training != self.training
+        self.refresh_gains()
+        for key, w, gain, fmt, qk_dim in self._weights():
+            ver = w._version + (gain._version if gain is not None else 0)
+            if not stale_all and self.versions.get(key) == ver and key in self.prepped:
+                continue
+            self.prepped[key] = ops.weight_prep(w.detach(), gain=None if gain is None else self.gain_ptr(gain),
+                                                normalize=training, fmt=fmt, qk_head_dim=qk_dim,
+                                                out=self.prepped.get(key))
+            self.versions[key] = ver
+        self.training = training
+
+    # ---- embedding projections: one launch for every block's emb_linear* ----
+    def affine_for(self, B: int) -> dict:
+        st = self.affine.get(B)
+        if st is not None:
+            return st
+        net = self.net
+        entries, outs = [], {}
+        for prefix, blocks in (("enc", net.enc), ("dec", net.dec)):
+            for name, blk in blocks.items():
+                if not isinstance(blk, Block):
+                    continue
+                p = f"{prefix}.{name}"
+
+                def add(tag: str, conv: MPConv, gain: torch.nn.Parameter) -> None:
+                    O, I = conv.weight.shape[0], conv.weight.shape[1]
+                    out = torch.empty((B, O), device=self.device, dtype=torch.float32)
+                    outs[p + tag] = out
+                    entries.append(dict(w=conv.weight.detach().view(O, I), gain=self.gain_ptr(gain), out=out,
+                                        groups=conv.groups, bias=1.0, normalize=False, conv=conv))
+                add(".c", blk.emb_linear, blk.emb_gain)
+                if blk.use_attention:
+                    add(".c_qk", blk.emb_linear_qk, blk.emb_gain_qk)
+                    add(".c_v", blk.emb_linear_v, blk.emb_gain_v)
+        st = dict(entries=entries, outs=outs, descs=None, max_o=0, training=None, ptrs=None)
+        self.affine[B] = st
+        return st
+
+    def affine_descs(self, st: dict) -> Tuple[Tensor, int]:
+        ptrs = tuple(e["conv"].weight.data_ptr() for e in st["entries"])
+        if st["descs"] is None or st["training"] != self.net.training or st["ptrs"] != ptrs:
+            for e in st["entries"]:
+                conv = e["conv"]
+                e["w"] = conv.weight.detach().view(conv.weight.shape[0], conv.weight.shape[1])
+                e["normalize"] = self.net.training
+            st["descs"], st["max_o"] = ops.make_affine_descs(st["entries"], self.device)
+            st["training"] = self.net.training
+            st["ptrs"] = ptrs
+        return st["descs"], st["max_o"]
+
+
+class UNet(DualDiffusionUNet):
+
+    supports_compile = False     # no torch.compile dispatch on this path (CUDA graphs instead)
+
+    def __init__(self, config: UNetConfig) -> None:
+        super().__init__()
+        self.config = config
+        block_kwargs = {"dropout": config.dropout, "mlp_multiplier": config.mlp_multiplier,
+                        "mlp_groups": config.mlp_groups, "res_balance": config.res_balance,
+                        "attn_balance": config.attn_balance, "channels_per_head": config.channels_per_head}
+        cblock = [config.model_channels * x for x in config.channel_mult]
+        cnoise = config.model_channels * config.channel_mult_noise if config.channel_mult_noise is not None else max(cblock)
+        cemb = config.model_channels * config.channel_mult_emb if config.channel_mult_emb is not None else max(cblock)
+        self.num_levels = len(config.channel_mult)
+        self.cemb = cemb
+
+        # embedding + training-uncertainty heads (unet_edm2_b4.py:179-187)
+        self.emb_fourier = MPFourier(cnoise)
+        self.emb_noise = MPConv(cnoise, cemb, kernel=())
+        self.emb_label = MPConv(config.in_channels_emb, cemb, kernel=())
+        self.emb_label_unconditional = MPConv(1, cemb, kernel=())
+        self.logvar_fourier = MPFourier(config.logvar_channels)
+        self.logvar_linear = MPConv(config.logvar_channels, 1, kernel=(), disable_weight_norm=True)
+
+        # encoder (:189-207)
+        self.enc = torch.nn.ModuleDict()
+        cout = config.in_channels + 2
+        for level, channels in enumerate(cblock):
+            attn = level in config.attn_levels
+            if level == 0:
+                cin, cout = cout, channels
+                self.enc["conv_in"] = MPConv(cin, cout, kernel=(3, 3))
+            else:
+                self.enc[f"block{level}_down"] = Block(level, cout, cout, cemb, use_attention=attn, flavor="enc",
+                                                       resample_mode="down", **block_kwargs)
+            for idx in range(config.num_layers_per_block):
+                cin, cout = cout, channels
+                self.enc[f"block{level}_layer{idx}"] = Block(level, cin, cout, cemb, use_attention=attn,
+                                                             flavor="enc", **block_kwargs)
+        # decoder (:209-227)
+        self.dec = torch.nn.ModuleDict()
+        skips = [blk.out_channels for blk in self.enc.values()]
+        for level, channels in reversed(list(enumerate(cblock))):
+            attn = level in config.attn_levels
+            if level == len(cblock) - 1:
+                self.dec[f"block{level}_in0"] = Block(level, cout, cout, cemb, use_attention=True, flavor="dec", **block_kwargs)
+                self.dec[f"block{level}_in1"] = Block(level, cout, cout, cemb, use_attention=True, flavor="dec", **block_kwargs)
+            else:
+                self.dec[f"block{level}_up"] = Block(level, cout, cout, cemb, use_attention=attn, flavor="dec",
+                                                     resample_mode="up", **block_kwargs)
+            for idx in range(config.num_layers_per_block + 1):
+                cin = cout + skips.pop()
+                cout = channels
+                self.dec[f"block{level}_layer{idx}"] = Block(level, cin, cout, cemb, use_attention=attn,
+                                                             flavor="dec", **block_kwargs)
+        self.out_gain = torch.nn.Parameter(torch.zeros([]))
+        self.conv_out = MPConv(cout, config.out_channels, kernel=(3, 3))
+
+        self.use_cuda_graphs = True
+        self._plan: Optional[_Plan] = None
+
+    # ------------------------------------------------------------------------------------------
+    # helpers mirrored from the reference
+    # ------------------------------------------------------------------------------------------
+    def get_latent_shape(self, latent_shape: Union[torch.Size, Tuple[int, int, int, int]]) -> torch.Size:
+        """unet_edm2_b4.py:240-242."""
+        m = 2 ** (self.num_levels - 1)
+        return torch.Size(tuple(latent_shape[0:2]) + ((latent_shape[2] // m) * m, (latent_shape[3] // m) * m))
+
+    def _aux(self) -> dict:
+        """fp32 copies of the Fourier buffers on the module's device (the registered buffers follow
+        `.to(dtype)` like the reference's; the kernels always want fp32)."""
+        dev = torch.device(self.device)
+        aux = getattr(self, "_aux_cache", None)
+        if aux is None or aux["device"] != dev or aux["src"] != (self.emb_fourier.freqs.data_ptr(), self.emb_fourier.freqs._version):
+            aux = {"device": dev, "src": (self.emb_fourier.freqs.data_ptr(), self.emb_fourier.freqs._version)}
+            for name, mod in (("emb", self.emb_fourier), ("logvar", self.logvar_fourier)):
+                aux[name + "_freqs"] = mod.freqs.detach().to(device=dev, dtype=torch.float32).contiguous()
+                aux[name + "_phases"] = mod.phases.detach().to(device=dev, dtype=torch.float32).contiguous()
+            self._aux_cache = aux
+        return aux
+
+    def get_embeddings(self, emb_in: Tensor, conditioning_mask: Tensor) -> Tensor:
+        """unet_edm2_b4.py:232-235 -> (len(mask), cemb) in the module dtype."""
+        dev = torch.device(self.device)
+        e = emb_in.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if e.ndim == 1:
+            e = e.unsqueeze(0)
+        mask = conditioning_mask.detach().to(device=dev, dtype=torch.float32).contiguous().flatten()
+        L.require_cuda(self.emb_label.weight)
+        out = ops.label_embedding(e, self.emb_label.weight.detach().contiguous(),
+                                  self.emb_label_unconditional.weight.detach().contiguous(), mask,
+                                  normalize=self.training)
+        return out.to(self.dtype)
+
+    def get_sigma_loss_logvar(self, sigma: Optional[Tensor] = None) -> Tensor:
+        """unet_edm2_b4.py:237-238 -> (N,1,1,1) fp32."""
+        dev = torch.device(self.device)
+        aux = self._aux()
+        s = sigma.detach().to(device=dev, dtype=torch.float32).contiguous().flatten()
+        L.require_cuda(self.logvar_linear.weight)
+        out = ops.sigma_logvar(s, aux["logvar_freqs"], aux["logvar_phases"],
+                               self.logvar_linear.weight.detach().contiguous())
+        return out.view(-1, 1, 1, 1)
+
+    def _ln_freqs(self, plan: _Plan, format, H: int) -> Tensor:
+        """Mel positional channel, one value per latent row (unet_edm2_b4.py:244-248).  The statistics are taken
+        over the (identical) columns of the reference's (B,1,H,W) tensor, i.e. over the H row values."""
+        key = (id(format) if format is not None else 0, H)
+        t = plan.ln_freqs.get(key)
+        if t is None:
+            if format is not None and hasattr(format, "ms_freq_scale"):
+                f = format.ms_freq_scale.get_unscaled(H + 2)[1:-1].float().cpu()
+            else:   # MS_MDCT_DualFormat defaults: mel scale, 0 Hz .. sample_rate/2 (ms_mdct_dual.py:144-153)
+                hi = 2595.0 * math.log10(1.0 + 16000.0 / 700.0)
+                f = 700.0 * (10.0 ** (torch.linspace(0.0, hi, H + 2) / 2595.0) - 1.0)
+                f = f[1:-1]
+            f = f.log2()
+            f = (f - f.mean()) / f.std()
+            t = f.to(device=plan.device, dtype=torch.float32).contiguous()
+            plan.ln_freqs[key] = t
+        return t
+
+    def _apply(self, fn, *args, **kwargs):
+        # parameters may be re-allocated by .to()/.cuda()/.float(): drop every cached pointer / graph
+        self._plan = None
+        self._aux_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    # ------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------
+    def _get_plan(self) -> _Plan:
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError("dualdiffusion_b200 UNet has no CPU path: move the module to a CUDA device (B200)")
+        if self._plan is None or self._plan.device != dev:
+            self._plan = _Plan(self)
+            self._plan.device = dev
+        return self._plan
+
+    def _run(self, plan: _Plan, x_in: Tensor, net_in: Tensor, sigma: Tensor, embeddings: Tensor,
+             ln_freqs: Tensor, x_ref: Optional[Tensor]) -> Tensor:
+        """The launch schedule of one UNet evaluation (unet_edm2_b4.py:250-296 + Block.forward :110-158)."""
+        cfg = self.config
+        B = x_in.shape[0]
+        W = plan.prepped
+        aux = self._aux()
+        g = cfg.mlp_groups
+
+        emb = ops.noise_embedding(sigma, aux["emb_freqs"], aux["emb_phases"], self.emb_noise.weight.detach(), embeddings,
+                                  cfg.label_balance, normalize=self.training)
+        st = plan.affine_for(B)
+        descs, max_o = plan.affine_descs(st)
+        ops.emb_affine(descs, len(st["entries"]), max_o, emb)
+        cvec = st["outs"]
+
+        x = ops.conv_in(net_in, sigma, cfg.sigma_data, ln_freqs, W["enc.conv_in"])
+        skips = [x]
+        ca_r, cb_r = _mp_sum_coeffs(cfg.res_balance)
+        ca_a, cb_a = _mp_sum_coeffs(cfg.attn_balance)
+
+        def attention_tail(p: str, blk: Block, x2: Tensor, xs: Tensor) -> Tensor:
+            qk = ops.mpconv(xs, W[p + ".attn_qk"], 1)
+            v = ops.mpconv(x2, W[p + ".attn_v"], 1)
+            y = ops.attention(qk, v, cvec[p + ".c_v"], blk.num_heads, blk.channels_per_head)
+            return ops.mpconv(y, W[p + ".attn_proj"], 1, epi=L.EPI_RESIDUAL, alpha=cb_a, beta=ca_a, clip=blk.clip_act,
+                              residual=x2)
+
+        for name, blk in self.enc.items():
+            if not isinstance(blk, Block):
+                continue
+            p = "enc." + name
+            if blk.resample_mode == "down":
+                x = ops.avgpool2(x)
+            t0 = ops.mpconv(x, W[p + ".conv_skip"], 1)
+            xn, s = ops.pixnorm_silu(t0)
+            y0 = ops.mpconv(s, W[p + ".conv_res0"], 3, g, epi=L.EPI_SCALE_SILU, scale=cvec[p + ".c"])
+            if blk.use_attention:
+                x2, xs = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
+                                    residual=xn, epi2=L.EPI2_SCALE, scale2=cvec[p + ".c_qk"])
+                x = attention_tail(p, blk, x2, xs)
+            else:
+                x = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
+                               clip=blk.clip_act, residual=xn)
+            skips.append(x)
+
+        for name, blk in self.dec.items():
+            p = "dec." + name
+            if "layer" in name:
+                skip = skips.pop()
+                wa, wb = mp_cat_weights(x.shape[-1], skip.shape[-1], cfg.concat_balance)
+                xc, s = ops.cat_silu(x, skip, wa, wb, False)
+            elif blk.resample_mode == "up":
+                xc, s = ops.cat_silu(x, None, 1.0, 0.0, True)
+            else:
+                xc = x
+                _, s = ops.cat_silu(x, None, 1.0, 0.0, False, need_cat=False)
+            y0 = ops.mpconv(s, W[p + ".conv_res0"], 3, g, epi=L.EPI_SCALE_SILU, scale=cvec[p + ".c"])
+            y1 = ops.mpconv(y0, W[p + ".conv_res1"], 3, g)
+            if blk.use_attention:
+                x2, xs = ops.mpconv(xc, W[p + ".conv_skip"], 1, epi=L.EPI_RESIDUAL, alpha=ca_r, beta=cb_r, residual=y1,
+                                    epi2=L.EPI2_SCALE, scale2=cvec[p + ".c_qk"])
+                x = attention_tail(p, blk, x2, xs)
+            else:
+                x = ops.mpconv(xc, W[p + ".conv_skip"], 1, epi=L.EPI_RESIDUAL, alpha=ca_r, beta=cb_r,
+                               clip=blk.clip_act, residual=y1)
+
+        return ops.conv_out(x, W["conv_out"], x_in, sigma, cfg.sigma_data, x_ref)
+
+    def forward(self, x_in: Tensor, sigma: Tensor, format=None, embeddings: Optional[Tensor] = None,
+                x_ref: Optional[Tensor] = None, perturbed_input: Optional[Tensor] = None) -> Tensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("dualdiffusion_b200 UNet: backward is not implemented yet (inference only)")
+        if self.training and self.config.dropout != 0:
+            raise NotImplementedError("dualdiffusion_b200 UNet: dropout is not implemented")
+        plan = self._get_plan()
+        dev = plan.device
+        B, _, H, Wd = x_in.shape
+        x32 = x_in.detach().to(device=dev, dtype=torch.float32).contiguous()
+        net_in = x32 if perturbed_input is None else perturbed_input.detach().to(device=dev, dtype=torch.float32).contiguous()
+        sg = sigma.detach().to(device=dev, dtype=torch.float32).flatten().contiguous()
+        if sg.numel() == 1 and B > 1:
+            sg = sg.expand(B).contiguous()
+        if embeddings is None:
+            raise ValueError("embeddings (from get_embeddings) are required")
+        em = embeddings.detach().to(device=dev, dtype=torch.float32).contiguous()
+        xr = None if x_ref is None else x_ref.detach().to(device=dev, dtype=torch.float32).contiguous()
+        lf = self._ln_freqs(plan, format, H)
+
+        with torch.no_grad():
+            plan.refresh_weights()
+            if not self.use_cuda_graphs or self.training:
+                return self._run(plan, x32, net_in, sg, em, lf, xr)
+
+            key = (B, H, Wd, xr is not None, perturbed_input is not None, lf.data_ptr())
+            gs = plan.graphs.get(key)
+            if gs is None:
+                static = dict(x=x32.clone(), n=net_in.clone() if perturbed_input is not None else None, s=sg.clone(),
+                              e=em.clone(), r=None if xr is None else xr.clone())
+                n_static = static["n"] if static["n"] is not None else static["x"]
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):      # warm-up outside capture (lazy attribute setup, allocator)
+                    self._run(plan, static["x"], n_static, static["s"], static["e"], lf, static["r"])
+                torch.cuda.current_stream(dev).wait_stream(side)
+                before = ops.launch_count
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._run(plan, static["x"], n_static, static["s"], static["e"], lf, static["r"])
+                gs = dict(graph=graph, static=static, out=out, launches=ops.launch_count - before,
+                          affine_ptrs=plan.affine_for(B)["ptrs"])
+                plan.graphs[key] = gs
+            st = gs["static"]
+            st["x"].copy_(x32)
+            if st["n"] is not None:
+                st["n"].copy_(net_in)
+            st["s"].copy_(sg)
+            st["e"].copy_(em)
+            if st["r"] is not None:
+                st["r"].copy_(xr)
+            gs["graph"].replay()
+            ops.launch_count += gs["launches"]
+            return gs["out"].clone()

@@ -17,9 +17,15 @@ Tensor = torch.Tensor
 launch_count = 0   # number of C-ABI kernel launches issued (bench.py reports it as gpu_launches)
 
 
-def _count(n: int = 1) -> None:
+trace = None       # set to a list to record (op, detail) per launch (profiling scripts only)
+
+
+def _count(n: int = 1, what: str = "", detail=None) -> None:
     global launch_count
     launch_count += n
+    if trace is not None:
+        import sys
+        trace.append((what or sys._getframe(1).f_code.co_name, detail))
 
 
 def _is_bf16(t: Tensor) -> int:
@@ -66,7 +72,7 @@ def mpconv(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1, *, epi: in
     e = L.ConvEpilogue(epi, epi2, alpha, beta, clip, L.ptr(scale), L.ptr(scale2), L.ptr(residual), L.ptr(out2))
     L.check(L.load().dd_mpconv_forward(L.ptr(x), L.ptr(w_prepped), L.ptr(out), B, H, W, Cin, Cout, ksize, groups,
                                        C.byref(e), L.stream_ptr()))
-    _count()
+    _count(1, "mpconv", (B, H, W, Cin, Cout, ksize, groups, epi, epi2))
     return (out, out2) if epi2 != L.EPI2_NONE else out
 
 
@@ -180,14 +186,49 @@ def attention(qk: Tensor, v: Tensor, scale_v: Tensor, heads: int, head_dim: int 
 
 
 def sampler_cfg_lerp(d_2b: Tensor, sample: Tensor, cfg_scale: float, t_hat: float, cfg_out: Tensor,
-                     x_hat_out: Optional[Tensor]) -> None:
+                     x_hat_out: Optional[Tensor], dup: bool = False) -> None:
+    """`sample` may be the first half of a duplicated [2B] buffer; n is taken from cfg_out."""
     L.check(L.load().dd_sampler_cfg_lerp(L.ptr(d_2b), L.ptr(sample), cfg_scale, t_hat, L.ptr(cfg_out), L.ptr(x_hat_out),
-                                         sample.numel(), L.stream_ptr()))
+                                         int(dup), cfg_out.numel(), L.stream_ptr()))
     _count()
 
 
 def sampler_update(cfg1: Tensor, d2_2b: Optional[Tensor], cfg_scale: float, use_heun: bool, t: float, p: float,
-                   noise: Optional[Tensor], sample: Tensor, cfg_out: Optional[Tensor]) -> None:
+                   noise: Optional[Tensor], sample: Tensor, cfg_out: Optional[Tensor], dup: bool = False) -> None:
     L.check(L.load().dd_sampler_update(L.ptr(cfg1), L.ptr(d2_2b), cfg_scale, int(use_heun), t, p, L.ptr(noise),
-                                       L.ptr(sample), L.ptr(cfg_out), sample.numel(), L.stream_ptr()))
+                                       L.ptr(sample), L.ptr(cfg_out), int(dup), cfg1.numel(), L.stream_ptr()))
     _count()
+
+
+def label_embedding(emb_in: Tensor, w_label: Tensor, w_uncond: Tensor, mask: Tensor, normalize: bool = False) -> Tensor:
+    Bc, I = emb_in.shape
+    Bm = mask.numel()
+    cemb = w_label.shape[0]
+    out = torch.empty((Bm, cemb), device=emb_in.device, dtype=torch.float32)
+    L.check(L.load().dd_label_embedding(L.ptr(emb_in), Bc, I, L.ptr(w_label), L.ptr(w_uncond), _is_bf16(w_label),
+                                        L.ptr(mask), Bm, int(normalize), L.ptr(out), cemb, L.stream_ptr()))
+    _count()
+    return out
+
+
+def sigma_logvar(sigma: Tensor, freqs: Tensor, phases: Tensor, w: Tensor) -> Tensor:
+    out = torch.empty(sigma.numel(), device=sigma.device, dtype=torch.float32)
+    L.check(L.load().dd_sigma_logvar(L.ptr(sigma), sigma.numel(), L.ptr(freqs), L.ptr(phases), freqs.numel(), L.ptr(w),
+                                     _is_bf16(w), L.ptr(out), L.stream_ptr()))
+    _count()
+    return out
+
+
+def axpby(a: Tensor, b: Tensor, alpha: float, beta: float, clip: float = 0.0) -> Tensor:
+    out = torch.empty_like(a)
+    L.check(L.load().dd_axpby(L.ptr(a), L.ptr(b), alpha, beta, clip, L.ptr(out), a.numel(), L.stream_ptr()))
+    _count()
+    return out
+
+
+def mp_fourier(x: Tensor, freqs: Tensor, phases: Tensor) -> Tensor:
+    out = torch.empty((x.numel(), freqs.numel()), device=x.device, dtype=torch.float32)
+    L.check(L.load().dd_mp_fourier(L.ptr(x), x.numel(), L.ptr(freqs), L.ptr(phases), freqs.numel(), L.ptr(out),
+                                   L.stream_ptr()))
+    _count()
+    return out

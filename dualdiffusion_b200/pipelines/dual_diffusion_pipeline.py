@@ -1,0 +1,158 @@
+"""EDM sampler of the drop-in path: `DualDiffusionPipeline.diffusion_decode` with the reference's signature and
+step arithmetic (src/pipelines/dual_diffusion_pipeline.py:48-110 SampleParams, :589-752 diffusion_decode).
+
+Per step (Heun + classifier-free guidance) the reference issues 2 UNet calls at batch 2B plus ~10 eager
+elementwise kernels and 4 host syncs.  Here a step is: UNet graph replay, `dd_sampler_cfg_lerp`, UNet graph
+replay, `dd_sampler_update` — the cond/uncond `.repeat(2,1,1,1)` is folded into the two glue kernels (they
+write both halves of the next UNet input), per-step sigmas come from one pre-uploaded device table, and the
+debug statistics (`.item()` x4 per step, :740-744) are only computed when `collect_debug_info` is set.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Optional, Union
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..sampling.schedule import SamplingSchedule
+
+
+@dataclass
+class SampleParams:
+    """pipeline.py:48-70 (same fields and defaults)."""
+    seed: Optional[int] = None
+    num_steps: int = 100
+    batch_size: int = 1
+    length: Optional[int] = None
+    seamless_loop: bool = False
+    cfg_scale: float = 1.5
+    sigma_max: Optional[float] = None
+    sigma_min: Optional[float] = None
+    sigma_data: Optional[float] = None
+    rho: float = 7.0
+    schedule: Optional[str] = "edm2"
+    prompt: Optional[str] = None
+    use_heun: bool = True
+    input_perturbation: float = 1.0
+    input_perturbation_offset: float = 0.0
+    stereo_fix: float = 0
+    img2img_strength: float = 0.5
+    input_audio: Optional[Union[str, torch.Tensor]] = None
+    input_audio_pre_encoded: bool = False
+    inpainting_mask: Optional[torch.Tensor] = None
+
+    def sanitize(self) -> "SampleParams":
+        self.seed = int(self.seed) if self.seed is not None else None
+        self.length = int(self.length) if self.length is not None else None
+        self.num_steps = int(self.num_steps)
+        self.batch_size = int(self.batch_size)
+        self.stereo_fix = float(self.stereo_fix)
+        return self
+
+
+def step_scalars(i: int, sigma_curr: float, sigma_next: float, params: SampleParams) -> dict:
+    """Host-side per-step scalars of the sampler loop (pipeline.py:680-724): perturbed sigma_next, Heun's
+    sigma_hat / t_hat, the final lerp weight t and the re-noise amplitude p."""
+    old_sigma_next = sigma_next
+    ipo = np.log(sigma_curr) + params.input_perturbation_offset
+    eff = (np.tanh(ipo) / 2 + 0.5) * float(params.input_perturbation)             # :691
+    sigma_next = sigma_next * (1 - (max(min(eff, 1), 0)))                          # :694
+    sigma_hat = max(old_sigma_next, params.sigma_min)                              # :706
+    t_hat = sigma_hat / sigma_curr
+    last = (i + 1) >= params.num_steps
+    t = 0.0 if last else sigma_next / sigma_curr                                   # :723
+    p = 0.0 if last else max(old_sigma_next ** 2 - sigma_next ** 2, 0) ** 0.5      # :735
+    return dict(sigma_next=float(sigma_next), old_sigma_next=float(old_sigma_next), sigma_hat=float(sigma_hat),
+                t_hat=float(t_hat), t=float(t), p=float(p), effective_input_perturbation=float(old_sigma_next - sigma_next))
+
+
+class DualDiffusionPipeline(torch.nn.Module):
+    """Minimal module container exposing the sampler.  Construct with the modules that a model directory's
+    model_index.json would load (`unet`, optionally `format`, ...)."""
+
+    def __init__(self, pipeline_modules: dict) -> None:
+        super().__init__()
+        for name, module in pipeline_modules.items():
+            setattr(self, name, module)
+        self.collect_debug_info = False
+        self.last_debug_info: dict = {}
+
+    @torch.inference_mode()
+    def diffusion_decode(self, params: SampleParams, quiet: bool = False,
+                         audio_embedding: Optional[torch.Tensor] = None, sample_shape: Optional[torch.Size] = None,
+                         x_ref: Optional[torch.Tensor] = None, module=None,
+                         initial_noise: Optional[torch.Tensor] = None,
+                         step_noise: Optional[Any] = None) -> torch.Tensor:
+        """pipeline.py:589-752.  `initial_noise` / `step_noise` (callable i -> tensor) optionally inject the
+        noise draws so that parity tests can feed the oracle's values; by default they come from a device
+        `torch.Generator` seeded with params.seed exactly as in the reference (:605, :637, :736)."""
+        unet = module or getattr(self, "unet")
+        params = SampleParams(**params.__dict__).sanitize()
+        params.seed = params.seed or int(np.random.randint(100000, 999999))
+        params.sigma_max = params.sigma_max or unet.config.sigma_max
+        params.sigma_min = params.sigma_min or unet.config.sigma_min
+        params.sigma_data = params.sigma_data or unet.config.sigma_data
+        if params.seamless_loop:
+            raise NotImplementedError("seamless_loop sampling is not implemented on the B200 path")
+        if audio_embedding is None:
+            raise NotImplementedError("unconditional (no class embedding) sampling is not implemented")
+        if sample_shape is None and x_ref is None:
+            raise ValueError("sample_shape or x_ref is required")
+
+        device = torch.device(unet.device)
+        B = params.batch_size
+        debug_info: dict = {}
+        generator = torch.Generator(device=device).manual_seed(params.seed)
+
+        conditioning_mask = torch.cat((torch.ones(B, dtype=torch.bool), torch.zeros(B, dtype=torch.bool)))
+        emb = unet.get_embeddings(audio_embedding, conditioning_mask.to(device))
+        input_ref = None
+        if x_ref is not None:
+            sample_shape = sample_shape or x_ref.shape
+            input_ref = x_ref.to(device=device, dtype=torch.float32).repeat(2, 1, 1, 1)
+        sample_shape = tuple(sample_shape)
+
+        schedule = SamplingSchedule.get_schedule(params.schedule, params.num_steps, 1, device="cpu",
+                                                 sigma_max=params.sigma_max, sigma_min=params.sigma_min, rho=params.rho)
+        sig = schedule.tolist()
+        debug_info["sigma_schedule"] = sig
+        steps = [step_scalars(i, sig[i], sig[i + 1], params) for i in range(params.num_steps)]
+        # device table of the per-call sigma vectors: [step][0 = sigma_curr | 1 = sigma_hat][2B]
+        table = torch.tensor([[[sig[i]] * (2 * B), [st["t_hat"] * sig[i]] * (2 * B)] for i, st in enumerate(steps)],
+                             dtype=torch.float32).to(device)
+
+        if initial_noise is None:
+            noise = torch.randn(sample_shape, device=device, generator=generator)
+            if params.stereo_fix > 0:
+                raise NotImplementedError("stereo_fix is not implemented on the B200 path")
+        else:
+            noise = initial_noise.to(device=device, dtype=torch.float32)
+        n = noise.numel()
+        sample2 = torch.empty((2 * B,) + sample_shape[1:], device=device, dtype=torch.float32)
+        sample2[:B] = noise * (sig[0] ** 2 + params.sigma_data ** 2) ** 0.5
+        sample2[B:] = sample2[:B]
+        xhat2 = torch.empty_like(sample2)
+        cfg1 = torch.empty(sample_shape, device=device, dtype=torch.float32)
+        cfg_out = torch.empty(sample_shape, device=device, dtype=torch.float32) if self.collect_debug_info else None
+        fmt = getattr(self, "format", None)
+
+        for i, st in enumerate(steps):
+            d1 = unet(sample2, table[i, 0], fmt, emb, input_ref)
+            ops.sampler_cfg_lerp(d1, sample2, params.cfg_scale, st["t_hat"], cfg1,
+                                 xhat2 if params.use_heun else None, dup=True)
+            d2 = unet(xhat2, table[i, 1], fmt, emb, input_ref) if params.use_heun else None
+            nz = None
+            if st["p"] > 0 or (i + 1) < params.num_steps:
+                nz = (step_noise(i).to(device=device, dtype=torch.float32) if step_noise is not None
+                      else torch.randn(sample_shape, generator=generator, device=device, dtype=torch.float32))
+            ops.sampler_update(cfg1, d2, params.cfg_scale, params.use_heun, st["t"], st["p"], nz, sample2, cfg_out,
+                               dup=True)
+            if self.collect_debug_info:   # pipeline.py:740-744 (forces host syncs)
+                debug_info.setdefault("sample_std", []).append(sample2[:B].std().item())
+                debug_info.setdefault("cfg_output_mean", []).append(cfg_out.mean().item())
+                debug_info.setdefault("cfg_output_std", []).append(cfg_out.std().item())
+                debug_info.setdefault("effective_input_perturbation", []).append(st["effective_input_perturbation"])
+        self.last_debug_info = debug_info
+        return sample2[:B].clone()

@@ -119,6 +119,18 @@ typedef struct dd_affine_desc {
 DD_API int dd_emb_affine(const dd_affine_desc* descs_dev, int n_descs, int max_O, const float* emb, int B, int cemb,
                   void* stream);
 
+/* UNet.get_embeddings (:232-235): out[b] = mp_sum(W_u*1, W_l @ normalize(emb_in[b or 0]) / sqrt(I), t = mask[b]);
+ * emb_in fp32 [Bc][I] with Bc in {1, Bm}; mask fp32 [Bm] (1 = conditioned, 0 = unconditional).     */
+DD_API int dd_label_embedding(const float* emb_in, int Bc, int I, const void* w_label, const void* w_uncond,
+                              int w_is_bf16, const float* mask, int Bm, int normalize, float* out, int cemb,
+                              void* stream);
+/* MPFourier.forward, 1-D input (mp_tools.py:324-330): out[i][c] = cos(x_i*freqs_c + phases_c)*sqrt(2)   */
+DD_API int dd_mp_fourier(const float* x, int count, const float* freqs, const float* phases, int n, float* out,
+                         void* stream);
+/* UNet.get_sigma_loss_logvar (:237-238): out[i] = w . fourier(ln(sigma_i)/4) / sqrt(n)             */
+DD_API int dd_sigma_logvar(const float* sigma, int count, const float* freqs, const float* phases, int n,
+                           const void* w, int w_is_bf16, float* out, void* stream);
+
 /* ---- elementwise block glue ---------------------------------------------------------------- */
 /* pixel norm (mp_tools.py:42-49 with dim=1) + mp_silu: x = t/(1e-4+rms_c(t)); s = mp_silu(x)      */
 DD_API int dd_pixnorm_silu(const void* t, void* x_out, void* s_out, long npix, int C, void* stream);
@@ -129,6 +141,9 @@ DD_API int dd_cat_silu(const void* a, int Ca, const void* b, int Cb, float wa, f
 /* 2x2 mean pooling (mp_tools.py:77), H,W are INPUT sizes (even).                                  */
 DD_API int dd_avgpool2(const void* x, void* out, int B, int H, int W, int C, void* stream);
 
+/* out = clip(alpha*a + beta*b) on bf16 activations (mp_sum mp_tools.py:274-279 with float t).        */
+DD_API int dd_axpby(const void* a, const void* b, float alpha, float beta, float clip, void* out, long n, void* stream);
+
 /* ---- attention: unet_edm2_b4.py:137-151 ---------------------------------------------------- */
 /* q|k halves [B][N][2C] (after DD_WPERM_QK), v [B][N][C]; per-head cosine normalisation of q,k,v over
  * head_dim (eps 1e-4), softmax(q k^T / sqrt(head_dim)) v, then out = mp_silu(y * scale_v[b][c]).     */
@@ -136,13 +151,16 @@ DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, voi
                  int head_dim, void* stream);
 
 /* ---- EDM sampler step glue: pipelines/dual_diffusion_pipeline.py:699-737 -------------------- */
-/* cfg = lerp(D[B:], D[:B], cfg_scale); x_hat = lerp(cfg, sample, t_hat)   (:701, :712)             */
+/* n = element count of ONE latent batch (B*C*H*W); d_2b holds [cond ; uncond] = 2n elements.
+ * cfg = lerp(D[B:], D[:B], cfg_scale); x_hat = lerp(cfg, sample, t_hat)   (:701, :712).
+ * dup != 0 writes x_hat twice ([x_hat ; x_hat], the `.repeat(2,1,1,1)` of :712) into a 2n buffer.     */
 DD_API int dd_sampler_cfg_lerp(const float* d_2b, const float* sample, float cfg_scale, float t_hat, float* cfg_out,
-                        float* x_hat_out, long n_per_batch_total, void* stream);
+                               float* x_hat_out, int dup, long n, void* stream);
 /* cfg2 = lerp(D2[B:], D2[:B], cfg_scale); cfg = use_heun ? lerp(cfg1, cfg2, .5) : cfg1;
- * sample = lerp(cfg, sample, t) + p * noise   (:717-724, :734-737); noise may be NULL (p = 0).      */
+ * sample = lerp(cfg, sample, t) + p * noise   (:717-724, :734-737); noise may be NULL (p = 0).
+ * dup != 0: sample_inout is a 2n buffer, read from its first half and written to both halves (:661).   */
 DD_API int dd_sampler_update(const float* cfg1, const float* d2_2b, float cfg_scale, int use_heun, float t, float p,
-                      const float* noise, float* sample_inout, float* cfg_out, long n_total, void* stream);
+                             const float* noise, float* sample_inout, float* cfg_out, int dup, long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,85 @@
+"""Regenerates tests/golden/*.pt from the UNMODIFIED reference, imported on CPU in the build container through
+oracle/ref_shim.py.  Run:  python tests/golden/make_golden.py   (needs /root/reference; never runs on the GPU box).
+
+Golden files hold inputs + reference outputs only.  Model weights are NOT stored: they are re-created from
+`oracle.unet_oracle.synth_state_dict(spec, seed)` (a seeded CPU generator), and a checksum of them is stored so
+a silent RNG change is detected.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim, unet_oracle as uo  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def weight_checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+def build_reference_unet(spec, sd):
+    from modules.unets.unet_edm2_b4 import UNet, UNetConfig
+    cfg = UNetConfig(**{k: getattr(spec, k) for k in UNetConfig.__dataclass_fields__ if hasattr(spec, k)})
+    net = UNet(cfg).eval()
+    net.load_state_dict(sd, strict=True)
+    return net
+
+
+def main():
+    ref_shim.install()
+    from modules.formats.ms_mdct_dual import MS_MDCT_DualFormat, MS_MDCT_DualFormatConfig
+    from pipelines.dual_diffusion_pipeline import DualDiffusionPipeline, SampleParams
+    from sampling.schedule import SamplingSchedule
+    fmt = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig())
+    torch.set_grad_enabled(False)
+
+    # ---- UNet forward, reduced config (every code path) and the default config at BASELINE config 1 ----
+    for tag, spec, shape, sigmas, masks in (
+            ("unet_small", uo.small_spec(), (2, 4, 32, 48), [2.0, 0.3], [True, False]),
+            ("unet_default_c1", uo.default_spec(), (1, 4, 64, 64), [2.0], [True])):
+        sd = uo.synth_state_dict(spec, seed=0)
+        net = build_reference_unet(spec, sd)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(shape, generator=g)
+        sigma = torch.tensor(sigmas)
+        clap = torch.randn(shape[0], spec.in_channels_emb, generator=g)
+        mask = torch.tensor(masks)
+        emb = net.get_embeddings(clap, mask)
+        d = net(x, sigma, fmt, emb)
+        x_ref = torch.rand(shape[0], shape[1] + 1, *shape[2:], generator=g)
+        d_ref = net(x, sigma, fmt, emb, x_ref)
+        logvar = net.get_sigma_loss_logvar(sigma)
+        net.train()
+        d_train = net(x, sigma, fmt, emb)
+        torch.save(dict(x=x, sigma=sigma, clap=clap, mask=mask, emb=emb, d=d, x_ref=x_ref, d_xref=d_ref, logvar=logvar,
+                        d_train=d_train, weight_checksum=weight_checksum(sd)), os.path.join(OUT, tag + ".pt"))
+        print(tag, "std", d.std().item())
+
+    # ---- sampler: reference diffusion_decode on CPU, reduced config, 3 Heun+CFG steps ----
+    spec = uo.small_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    net = build_reference_unet(spec, sd)
+    pipe = DualDiffusionPipeline({"unet": net, "format": fmt})
+    g = torch.Generator().manual_seed(2)
+    clap = torch.randn(1, spec.in_channels_emb, generator=g)
+    cases = {}
+    for name, kw in (("heun3", dict(num_steps=3, use_heun=True)), ("euler4", dict(num_steps=4, use_heun=False, cfg_scale=2.0))):
+        params = SampleParams(seed=1234, batch_size=1, **kw)
+        out = pipe.diffusion_decode(params, quiet=True, audio_embedding=clap, sample_shape=(1, 4, 32, 48), module=net)
+        cases[name] = dict(kwargs=kw, seed=1234, sample=out.clone())
+        print("sampler", name, out.std().item())
+    torch.save(dict(clap=clap, cases=cases, weight_checksum=weight_checksum(sd)), os.path.join(OUT, "sampler_small.pt"))
+
+    # ---- sigma schedules ----
+    sched = {n: SamplingSchedule.get_schedule(n, 10, 1.0, sigma_max=200.0, sigma_min=0.03, rho=7.0)
+             for n in ("edm2", "ln_linear", "linear", "cos", "scale_invariant")}
+    sched["edm2_100"] = SamplingSchedule.get_schedule("edm2", 100, 1.0, sigma_max=200.0, sigma_min=0.03, rho=7.0)
+    torch.save(sched, os.path.join(OUT, "schedules.pt"))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""CPU tests: the oracle restatement (oracle/) against the golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py), and against the live reference when /root/reference is present."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import ref_shim, sampler_oracle, unet_oracle as uo
+
+
+def _checksum(sd):
+    return float(sum(v.double().abs().sum() for v in sd.values()))
+
+
+@pytest.fixture(scope="module")
+def small():
+    spec = uo.small_spec()
+    return spec, uo.synth_state_dict(spec, seed=0)
+
+
+def test_synth_weights_reproducible(small):
+    spec, sd = small
+    g = load_golden("unet_small.pt")
+    assert _checksum(sd) == pytest.approx(g["weight_checksum"], rel=1e-12)
+
+
+def test_block_plan_matches_reference_key_set(small):
+    spec, sd = small
+    shapes = uo.state_dict_shapes(uo.default_spec())
+    assert len(shapes) == 291                      # default UNet has 291 tensors
+    assert shapes["enc.conv_in.weight"] == (256, 6, 3, 3)
+    assert shapes["conv_out.weight"] == (4, 256, 3, 3)
+    assert shapes["emb_label.weight"] == (768, 512)
+
+
+def test_unet_oracle_vs_golden_small(small):
+    spec, sd = small
+    g = load_golden("unet_small.pt")
+    emb = uo.get_embeddings(sd, g["clap"], g["mask"])
+    assert rel_err(emb, g["emb"]) < 1e-6
+    d = uo.unet_forward(sd, spec, g["x"], g["sigma"], emb)
+    assert rel_err(d, g["d"]) < 1e-5
+    d = uo.unet_forward(sd, spec, g["x"], g["sigma"], emb, x_ref=g["x_ref"])
+    assert rel_err(d, g["d_xref"]) < 1e-5
+    d = uo.unet_forward(sd, spec, g["x"], g["sigma"], emb, training=True)
+    assert rel_err(d, g["d_train"]) < 1e-5
+    assert rel_err(uo.sigma_loss_logvar(sd, g["sigma"]), g["logvar"]) < 1e-6
+
+
+def test_unet_oracle_vs_golden_default_config1():
+    """BASELINE config 1: single EDM2 UNet forward, 1x4x64x64 latent, fp32 on CPU."""
+    spec = uo.default_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    g = load_golden("unet_default_c1.pt")
+    assert _checksum(sd) == pytest.approx(g["weight_checksum"], rel=1e-12)
+    emb = uo.get_embeddings(sd, g["clap"], g["mask"])
+    d = uo.unet_forward(sd, spec, g["x"], g["sigma"], emb)
+    assert rel_err(d, g["d"]) < 1e-5
+    # the body must actually contribute (gains are non-zero): D != c_skip * x
+    c_skip = 1.0 / (1.0 + g["sigma"].view(-1, 1, 1, 1) ** 2)
+    assert (d - c_skip * g["x"]).std() > 0.1
+
+
+def test_sampler_oracle_vs_golden(small):
+    spec, sd = small
+    g = load_golden("sampler_small.pt")
+    for name, case in g["cases"].items():
+        out = sampler_oracle.diffusion_decode(sd, spec, g["clap"], (1, 4, 32, 48), seed=case["seed"], **case["kwargs"])
+        assert rel_err(out, case["sample"]) < 1e-4, name
+
+
+def test_schedule_oracle_vs_golden():
+    g = load_golden("schedules.pt")
+    s = sampler_oracle.schedule_edm2(100, 200.0, 0.03, 7.0)
+    assert torch.equal(s, g["edm2_100"])
+    assert s[0].item() == pytest.approx(200.0, rel=1e-6) and s[-1].item() == pytest.approx(0.03, rel=1e-5)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not present")
+def test_unet_oracle_vs_live_reference(small):
+    spec, sd = small
+    ref_shim.install()
+    from modules.unets.unet_edm2_b4 import UNet, UNetConfig
+    from modules.formats.ms_mdct_dual import MS_MDCT_DualFormat, MS_MDCT_DualFormatConfig
+    cfg = UNetConfig(**{k: getattr(spec, k) for k in UNetConfig.__dataclass_fields__ if hasattr(spec, k)})
+    net = UNet(cfg).eval()
+    net.load_state_dict(sd, strict=True)
+    fmt = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig())
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 4, 16, 32, generator=gen)
+    sigma = torch.tensor([7.0])
+    clap = torch.randn(1, spec.in_channels_emb, generator=gen)
+    with torch.no_grad():
+        emb = net.get_embeddings(clap, torch.tensor([True]))
+        ref = net(x, sigma, fmt, emb)
+    got = uo.unet_forward(sd, spec, x, sigma, uo.get_embeddings(sd, clap, torch.tensor([True])))
+    assert rel_err(got, ref) < 1e-5
