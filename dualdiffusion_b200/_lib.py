@@ -40,13 +40,12 @@ _SIGNATURES = {
     "dd_abi_version": (c_int, []),
     "dd_device_info": (c_int, [C.POINTER(c_int)] * 3),
     "dd_weight_prep": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_int, c_int,
-                               c_int, c_void_p]),
+                               c_int, c_int, c_void_p]),
     "dd_mpconv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                   C.POINTER(ConvEpilogue), c_void_p]),
     "dd_mpconv_forward_naive": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p]),
-    "dd_conv_in": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                           c_void_p]),
+    "dd_stem_patches": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_conv_out": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int,
                             c_int, c_int, c_void_p]),
     "dd_noise_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_float,

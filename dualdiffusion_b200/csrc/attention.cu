@@ -1,8 +1,9 @@
 // Small-sequence attention of the EDM2 UNet blocks (N = H*W <= 640 tokens, head_dim 64):
 // reference modules/unets/unet_edm2_b4.py:137-151.
 //
-// Per (batch, head, 64-query tile) CTA: K and V of the head are cosine-normalised (mp_tools.normalize over
-// the head channels, eps 1e-4) while they are staged into shared memory (V transposed), then a
+// Per (batch, head, 128-query tile) CTA: K and V of the head are cosine-normalised (mp_tools.normalize over
+// the head channels, eps 1e-4) while they are staged into shared memory (row-major, V^T fragments come from
+// ldmatrix.trans), then a
 // FlashAttention-style online-softmax loop runs QK^T and PV on the tensor cores (mma.sync m16n8k16 bf16,
 // fp32 accumulate).  The block's `mp_silu(y * (emb_linear_v(emb) + 1))` (:150-151) is the epilogue.
 // Attention is 0.8 % of the UNet FLOPs; the kernel is sized for latency, not peak.
@@ -12,7 +13,8 @@
 namespace {
 
 constexpr int kD = 64;            // head dim
-constexpr int kQTile = 64;        // queries per CTA (4 warps x 16 rows)
+constexpr int kQTile = 128;       // queries per CTA (8 warps x 16 rows)
+constexpr int kAttThreads = 256;
 constexpr int kKStride = kD + 8;  // bf16 elements per K/Q smem row (conflict-free fragment loads)
 constexpr float kNormEps = 1e-4f;
 
@@ -44,37 +46,41 @@ __device__ __forceinline__ void load_norm8(const __nv_bfloat16* src, bool active
     for (int j = 0; j < 8; ++j) f[j] *= inv;
 }
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+__global__ void __launch_bounds__(kAttThreads)
 attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                  const float* __restrict__ scale_v, __nv_bfloat16* __restrict__ out, int N, int heads, int npad) {
     extern __shared__ __align__(16) uint8_t smem_att[];
     const int C = heads * kD;
-    const int vstride = npad + 8;
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);            // [npad][kKStride]
-    __nv_bfloat16* Vt = Ks + (size_t)npad * kKStride;                          // [kD][vstride]
-    __nv_bfloat16* Qs = Vt + (size_t)kD * vstride;                             // [kQTile][kKStride]
+    __nv_bfloat16* Vs = Ks + (size_t)npad * kKStride;                          // [npad][kKStride]
+    __nv_bfloat16* Qs = Vs + (size_t)npad * kKStride;                          // [kQTile][kKStride]
 
     const int q0 = blockIdx.x * kQTile, head = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = tid & 7;          // which 8-channel slice of the head vector this lane loads
-    const int tok_in_pass = tid >> 3; // 16 tokens per pass
+    const int tok_in_pass = tid >> 3; // 32 tokens per pass
 
     const __nv_bfloat16* q_base = qk + (size_t)b * N * 2 * C + head * kD + sub * 8;
     const __nv_bfloat16* k_base = q_base + C;
     const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kD + sub * 8;
 
-    for (int j0 = 0; j0 < npad; j0 += 16) {
+    for (int j0 = 0; j0 < npad; j0 += 32) {
         const int j = j0 + tok_in_pass;
         float f[8];
         load_norm8(k_base + (size_t)j * 2 * C, j < N, f);
-        uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                              pack_bf16x2(f[6], f[7]));
-        *reinterpret_cast<uint4*>(Ks + (size_t)j * kKStride + sub * 8) = pk;
+        *reinterpret_cast<uint4*>(Ks + (size_t)j * kKStride + sub * 8) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         load_norm8(v_base + (size_t)j * C, j < N, f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) Vt[(size_t)(sub * 8 + i) * vstride + j] = __float2bfloat16_rn(f[i]);
+        *reinterpret_cast<uint4*>(Vs + (size_t)j * kKStride + sub * 8) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
     }
-    for (int r0 = 0; r0 < kQTile; r0 += 16) {
+    for (int r0 = 0; r0 < kQTile; r0 += 32) {
         const int r = r0 + tok_in_pass;
         float f[8];
         load_norm8(q_base + (size_t)(q0 + r) * 2 * C, q0 + r < N, f);
@@ -150,15 +156,18 @@ attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __re
             pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
             pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
         }
-        // O += P V
+        // O += P V : V^T fragments via ldmatrix.trans on the row-major [key][d] tile.
+        // lanes 0-7 / 8-15 address keys +0..7 / +8..15 of head-dim block n, lanes 16-31 the same keys of block n+1
 #pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            const __nv_bfloat16* vp = Vt + (size_t)(n * 8 + g) * vstride + kb + 2 * t;
+        for (int kk = 0; kk < 4; ++kk) {
+            const __nv_bfloat16* vrow = Vs + (size_t)(kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kKStride +
+                                        (lane >> 4) * 8;
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp + kk * 16);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + kk * 16 + 8);
-                mma_bf16_16816(o[n], pa[kk], b0, b1);
+            for (int n = 0; n < 8; n += 2) {
+                uint32_t vb[4];
+                ldmatrix_x4_trans(vb, vrow + n * 8);
+                mma_bf16_16816(o[n], pa[kk], vb[0], vb[1]);
+                mma_bf16_16816(o[n + 1], pa[kk], vb[2], vb[3]);
             }
         }
     }
@@ -194,14 +203,14 @@ extern "C" int dd_attention(const void* qk, const void* v, const float* scale_v,
     DD_REQUIRE(head_dim == kD, "dd_attention: head_dim=%d unsupported (64)", head_dim);
     DD_REQUIRE(N > 0 && N <= 640, "dd_attention: N=%d unsupported (1..640)", N);
     const int npad = ceil_div(N, 64) * 64;
-    const size_t smem = ((size_t)npad * kKStride + (size_t)kD * (npad + 8) + (size_t)kQTile * kKStride) * 2;
+    const size_t smem = ((size_t)2 * npad * kKStride + (size_t)kQTile * kKStride) * 2;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         DD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
     const dim3 grid(ceil_div(N, kQTile), heads, B);
-    attention_kernel<<<grid, 128, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+    attention_kernel<<<grid, kAttThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
                                                   static_cast<const __nv_bfloat16*>(v), scale_v,
                                                   static_cast<__nv_bfloat16*>(out), N, heads, npad);
     DD_CHECK_LAUNCH();

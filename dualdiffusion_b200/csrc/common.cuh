@@ -121,10 +121,17 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = globaltimer_ns();
+    // try_wait suspends the thread in hardware for a bounded time; the deadlock guard (2 s of wall time,
+    // then trap so that a protocol bug aborts the launch instead of hanging the GPU) is only consulted
+    // every 64K unsuccessful probes to keep the timer read off the critical path.
+    uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (globaltimer_ns() - t0 > 2000000000ull) __trap();   // 2 s: deadlock, abort the launch
+        if ((++spins & 0xFFFFu) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     }
 }
 
@@ -232,6 +239,18 @@ __host__ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr
     d |= (uint64_t)((row_bytes * 8u) >> 4) << 32;       // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                             // descriptor version 1 (Blackwell)
     d |= layout << 61;
+    return d;
+}
+// Same, 128B-swizzled rows, with an explicit byte stride between consecutive 8-row groups (the swizzle XOR is
+// a function of the absolute shared-memory address, so the start may sit on any 128 B row of a TMA-written
+// tile and the group stride may be any multiple of 128 B -- verified on B200, tools/exp_swizzle.py).
+__host__ __device__ __forceinline__ uint64_t make_kmajor_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
     return d;
 }
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.

@@ -14,7 +14,10 @@
 // out-of-bounds fill) and an n_tile-wide slice of one group's output channels.
 //   warp 0     : TMA producer   (A: 4-D box of activations, B: 2-D box of weights)
 //   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x n_tile x 16)
-//   warps 2..5 : epilogue       (tcgen05.ld -> registers -> fused elementwise -> global)
+//   warps 2..9 : epilogue       (tcgen05.ld -> registers -> fused elementwise -> global); two warps per
+//                TMEM lane quadrant, interleaved over 16-column chunks
+// A pipeline stage carries `sub` (1 or 2) consecutive (tap, k-chunk) operand pairs so that narrow tiles
+// (n_tile <= 64 or 32-channel k-chunks) amortise the mbarrier round trip over more MMA work.
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
 // tile i+1; the kernel is persistent over a static round-robin tile schedule.
 #include "common.cuh"
@@ -22,12 +25,14 @@
 
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kMaxThreads = 320;
 constexpr int kMaxStages = 8;
+constexpr int DD_EPI_HEAD = 3;   // internal: EDM output head (dd_conv_out)
 
 struct ConvParams {
     int B, H, W, Cin, Cout;
@@ -37,10 +42,16 @@ struct ConvParams {
     int tiles_w, tiles_h, tiles_b, m_tiles;
     int n_tile, n_tiles_per_group;
     int kchunks;                    // cin_g / KC
+    int k_iters;                    // taps * kchunks
+    int sub;                        // operand pairs per pipeline stage (1 or 2)
     int num_tiles;
     int stages;
     uint32_t a_bytes, b_bytes;      // bytes landed per stage by the two TMA boxes
     uint32_t tmem_cols;
+    // halo kernel (3x3, weights stationary)
+    int ks_last;                    // 16-channel MMA steps in the last 64-channel chunk
+    int a_stages;
+    uint32_t b_block_bytes;         // n_tile * 128
     // epilogue
     int epi;                        // DD_EPI_*
     int epi2;                       // DD_EPI2_*
@@ -50,6 +61,13 @@ struct ConvParams {
     const __nv_bfloat16* residual;  // [B][H][W][Cout]
     __nv_bfloat16* out;
     __nv_bfloat16* out2;
+    // DD_EPI_HEAD (EDM output preconditioning, fp32 NCHW)
+    int head_cout;
+    float sigma_data;
+    const float* sigma;             // [B]
+    const float* x_in;              // [B][head_cout][H][W]
+    const float* x_ref;             // [B][head_cout+1][H][W] or null
+    float* d_out;                   // [B][head_cout][H][W]
 };
 
 struct TileCoord {
@@ -68,8 +86,120 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
     return t;
 }
 
-template <int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+// fast magnitude-preserving SiLU for the epilogue: x*sigmoid(x) = x*(0.5 + 0.5*tanh(x/2)), one MUFU op.
+// tanh.approx has ~2^-11 relative error, below the bf16 rounding (2^-9) applied to the result.
+__device__ __forceinline__ float mp_silu_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return x * fmaf(0.5f, t, 0.5f) * (1.0f / 0.596f);
+}
+
+__device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float (&v)[16]) {
+    uint4* op = reinterpret_cast<uint4*>(dst);
+    op[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    op[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                       pack_bf16x2(v[14], v[15]));
+}
+
+// Epilogue of one 128 x n_tile accumulator tile for one thread (= one output pixel row of the tile):
+// TMEM -> registers -> fused elementwise (Block.forward glue) -> global.  `taddr` addresses this warp's lane
+// quadrant and the tile's accumulator buffer; with EW == 8 the two warps of a quadrant interleave 16-column chunks.
+template <int EW>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int chunk0, bool valid, int b, int h,
+                                              int w, int ch0) {
+    constexpr int kChunk = EW == 8 ? 16 : 32;   // columns per tcgen05.ld
+    const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+    for (int c0 = chunk0 * kChunk; c0 < p.n_tile; c0 += (EW / 4) * kChunk) {
+              uint32_t r[kChunk];
+              if constexpr (kChunk == 16) {
+                  ptx::tmem_ld_32x16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(r));
+              } else {
+                  if (c0 + 32 <= p.n_tile) {
+                      ptx::tmem_ld_32x32(taddr + c0, reinterpret_cast<uint32_t(&)[32]>(r));
+                  } else {   // n_tile is a multiple of 16 only: ragged last half chunk
+                      ptx::tmem_ld_32x16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(r));
+                  }
+              }
+              ptx::tmem_ld_wait();
+              if (!valid) continue;
+#pragma unroll
+              for (int sub16 = 0; sub16 < kChunk / 16; ++sub16) {
+                const int c = c0 + sub16 * 16;
+                if (c >= p.n_tile) break;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[sub16 * 16 + i]);
+                const int ch = ch0 + c;
+                if (p.epi == DD_EPI_HEAD) {
+                    // D = c_skip*x_in + c_out*F(x) (unet_edm2_b4.py:291), optional x_ref blend (:293-294)
+                    const float sg = __ldg(p.sigma + b), sd2 = p.sigma_data * p.sigma_data;
+                    const float c_skip = sd2 / (sg * sg + sd2), c_out = sg * p.sigma_data * rsqrtf(sg * sg + sd2);
+                    const size_t plane = (size_t)p.H * p.W, hw = (size_t)h * p.W + w;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int co = ch + i;
+                        if (co < p.head_cout) {
+                            const size_t o = ((size_t)b * p.head_cout + co) * plane + hw;
+                            float d = c_skip * __ldg(p.x_in + o) + c_out * v[i];
+                            if (p.x_ref) {
+                                const float rr = __ldg(p.x_ref + ((size_t)b * (p.head_cout + 1) + co) * plane + hw);
+                                const float tt = __ldg(p.x_ref + ((size_t)b * (p.head_cout + 1) + p.head_cout) * plane + hw);
+                                d = (rr + tt * (d - rr)) * rsqrtf((1.f - tt) * (1.f - tt) + tt * tt);
+                            }
+                            p.d_out[o] = d;
+                        }
+                    }
+                    continue;
+                }
+                if (p.epi == DD_EPI_SCALE_SILU) {
+                    const float4* sc = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + ch);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 s = __ldg(sc + i);
+                        v[4 * i + 0] = mp_silu_fast(v[4 * i + 0] * s.x);
+                        v[4 * i + 1] = mp_silu_fast(v[4 * i + 1] * s.y);
+                        v[4 * i + 2] = mp_silu_fast(v[4 * i + 2] * s.z);
+                        v[4 * i + 3] = mp_silu_fast(v[4 * i + 3] * s.w);
+                    }
+                } else if (p.epi == DD_EPI_RESIDUAL) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + ch);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint4 q = __ldg(rp + i);
+                        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = unpack_bf16x2(u[j]);
+                            const float a0 = p.alpha * v[8 * i + 2 * j + 0] + p.beta * f.x;
+                            const float a1 = p.alpha * v[8 * i + 2 * j + 1] + p.beta * f.y;
+                            v[8 * i + 2 * j + 0] = fminf(fmaxf(a0, -p.clip), p.clip);
+                            v[8 * i + 2 * j + 1] = fminf(fmaxf(a1, -p.clip), p.clip);
+                        }
+                    }
+                }
+                store_bf16x16(p.out + pix * p.Cout + ch, v);
+                if (p.epi2 != DD_EPI2_NONE) {
+                    if (p.epi2 == DD_EPI2_SILU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = mp_silu_fast(v[i]);
+                    } else {
+                        const float4* sc = reinterpret_cast<const float4*>(p.scale2 + (size_t)b * p.Cout + ch);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 s = __ldg(sc + i);
+                            v[4 * i + 0] *= s.x; v[4 * i + 1] *= s.y; v[4 * i + 2] *= s.z; v[4 * i + 3] *= s.w;
+                        }
+                    }
+                    store_bf16x16(p.out2 + pix * p.Cout + ch, v);
+                }
+              }
+            }
+}
+
+// EW = number of epilogue warps: 4 (one per TMEM lane quadrant, 32-column chunks) or 8 (two per quadrant,
+// interleaved 16-column chunks; for epilogues with transcendental math).
+template <int KC, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ ConvParams p) {
     constexpr uint32_t kRowBytes = KC * 2;           // one swizzle span per row
@@ -85,9 +215,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B swizzle atom
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t b_buf_bytes = (uint32_t)p.n_tile * kRowBytes;
-    const uint32_t stage_bytes = kABufBytes + b_buf_bytes;
+    const uint32_t pair_bytes = kABufBytes + b_buf_bytes;          // one (A box, B box) operand pair
+    const uint32_t stage_bytes = pair_bytes * (uint32_t)p.sub;
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -99,7 +230,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 4);
+            ptx::mbar_init(&tmem_empty_bar[a], EW);
         }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
@@ -113,8 +244,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    const int k_iters = p.taps * p.kchunks;
-
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
@@ -123,25 +252,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const TileCoord t = decode_tile(p, tile);
                 const int a_c0 = t.g * p.cin_g;
                 const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const int dy = tap / p.kw - p.kh / 2;
-                    const int dx = tap % p.kw - p.kw / 2;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* a_dst = smem + stage * stage_bytes;
+                for (int it0 = 0; it0 < p.k_iters; it0 += p.sub) {
+                    const int cnt = min(p.sub, p.k_iters - it0);
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                    for (int j = 0; j < cnt; ++j) {
+                        const int it = it0 + j;
+                        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                        const int dy = tap / p.kw - p.kh / 2;
+                        const int dx = tap % p.kw - p.kw / 2;
+                        uint8_t* a_dst = smem + stage * stage_bytes + j * pair_bytes;
                         uint8_t* b_dst = a_dst + kABufBytes;
-                        ptx::mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
                         ptx::tma_load_4d(a_dst, &tmA, &full_bar[stage], a_c0 + kc * KC, t.w0 + dx, t.h0 + dy, t.b0);
                         ptx::tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.cin_g + kc * KC, b_row);
-                        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                     }
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        if (lane == 0) {
+        // The whole warp runs the (warp-uniform) control flow so that addresses and descriptors live in
+        // uniform registers; one elected lane issues the tcgen05 instructions.
+        {
             const uint32_t idesc = ptx::make_idesc_bf16(kTileM, p.n_tile);
+            const uint32_t smem_base = ptx::smem_u32(smem);
             uint32_t stage = 0, phase = 0;
             uint32_t local = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
@@ -150,26 +285,36 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
-                for (int it = 0; it < k_iters; ++it) {
+                uint32_t accumulate = 0;
+                for (int it0 = 0; it0 < p.k_iters; it0 += p.sub) {
+                    const int cnt = min(p.sub, p.k_iters - it0);
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tcgen05_fence_after();
-                    const uint32_t a_addr = ptx::smem_u32(smem + stage * stage_bytes);
-                    const uint32_t b_addr = a_addr + kABufBytes;
+                    if (ptx::elect_one()) {
+                        const uint32_t s_addr = smem_base + stage * stage_bytes;
+                        for (int j = 0; j < cnt; ++j) {
+                            const uint64_t a_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes, kRowBytes);
+                            const uint64_t b_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes + kABufBytes, kRowBytes);
 #pragma unroll
-                    for (int ks = 0; ks < KC / 16; ++ks) {
-                        const uint64_t a_desc = ptx::make_kmajor_desc(a_addr + ks * 32, kRowBytes);
-                        const uint64_t b_desc = ptx::make_kmajor_desc(b_addr + ks * 32, kRowBytes);
-                        ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                            for (int ks = 0; ks < KC / 16; ++ks) {      // +32 B per 16-channel step = +2 in 16 B units
+                                ptx::umma_bf16_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        ptx::umma_commit(&empty_bar[stage]);    // frees the smem stage once the MMAs retire
                     }
-                    ptx::umma_commit(&empty_bar[stage]);        // frees the smem stage once the MMAs retire
+                    __syncwarp();
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tmem_full_bar[acc]);          // accumulator complete -> epilogue
+                if (ptx::elect_one()) ptx::umma_commit(&tmem_full_bar[acc]);   // accumulator complete -> epilogue
+                __syncwarp();
             }
         }
     } else {
         // ------------------------------ epilogue ------------------------------
+        const int ew = warp - 2;                    // 0..EW-1
         const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+        const int chunk0 = ew >> 2;                 // EW == 8: this warp takes chunks chunk0, chunk0+2, ...
         const int row = quad * 32 + lane;           // row of the 128-row tile == box-linear pixel index
         const int ww = row % p.wt;
         const int hh = (row / p.wt) % p.ht;
@@ -181,84 +326,214 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t acc_phase = (local >> 1) & 1;
             const int b = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
             const bool valid = (bb < p.bt) && (b < p.B) && (h < p.H) && (w < p.W);
-            const size_t pix = ((size_t)b * p.H + h) * p.W + w;
             const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
 
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)p.n_tile;
 
-            for (int c = 0; c < p.n_tile; c += 32) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32(taddr + c, r);
-                ptx::tmem_ld_wait();
-                if (valid) {
-                    float v[32];
+            epilogue_tile<EW>(p, taddr, chunk0, valid, b, h, w, ch0);
+            // all TMEM reads of this buffer have completed (wait::ld above): hand it back
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+    }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------
+// 3x3 convolution, halo variant (image rows >= 16): the 9 filter taps are shifted *views* of one
+// shared-memory halo tile instead of 9 separate TMA boxes, and the weight panel stays resident.
+//
+// M tile = 8 x 16 output pixels of one image.  Per 64-channel chunk one TMA box of (8+2) x (16+2) pixels
+// x 64 channels (23 KB, 128B-swizzled rows, pixel-major with a pitch of 10 rows per image row) is loaded.
+// For tap (dy,dx) the A operand of UMMA is that same tile read from row dy*10+dx with a stride of 10 rows
+// between 8-row groups -- operand traffic from L2 drops ~6x versus re-loading a box per tap.  The B operand
+// (9 taps x all chunks x n_tile output channels of one group) is loaded once per weight panel; every CTA walks
+// a contiguous range of (panel, m-tile) pairs so that it reloads weights at most once or twice per launch.
+// ---------------------------------------------------------------------------------
+constexpr int kHaloW = 8, kHaloH = 16, kHaloPitch = kHaloW + 2;
+constexpr uint32_t kHaloBytes = (kHaloH + 2) * kHaloPitch * 128;          // 23040 landed bytes
+constexpr uint32_t kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;       // stage stride (23552)
+constexpr int kMaxAStages = 6;
+
+struct HaloTile {
+    int panel, g, n_idx, b, h0, w0;
+};
+
+__device__ __forceinline__ HaloTile decode_halo_tile(const ConvParams& p, int tile) {
+    HaloTile t;
+    t.panel = tile / p.m_tiles;
+    const int m = tile - t.panel * p.m_tiles;
+    t.g = t.panel / p.n_tiles_per_group;
+    t.n_idx = t.panel - t.g * p.n_tiles_per_group;
+    t.w0 = (m % p.tiles_w) * kHaloW;
+    t.h0 = ((m / p.tiles_w) % p.tiles_h) * kHaloH;
+    t.b = m / (p.tiles_w * p.tiles_h);
+    return t;
+}
+
+// Issue the 9 taps x NKS 16-channel steps of one 64-channel chunk.  Descriptor arithmetic is in 16 B units:
+// a tap is a (dy*pitch + dx)-row shift of the halo tile (8 units per 128 B row), a k-step is +2 units.
+template <int NKS>
+__device__ __forceinline__ void halo_issue_taps(uint64_t a_desc0, uint64_t b_desc0, uint32_t b_block16, uint32_t d_tmem,
+                                                uint32_t idesc, uint32_t accumulate) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    const int ch = ch0 + c;
-                    if (p.epi == DD_EPI_SCALE_SILU) {
-                        const float4* sc = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + ch);
+    for (int tap = 0; tap < 9; ++tap) {
+        const uint64_t a_tap = a_desc0 + (uint64_t)(((tap / 3) * kHaloPitch + (tap % 3)) * 8);
+        const uint64_t b_tap = b_desc0 + (uint64_t)tap * b_block16;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 s = __ldg(sc + i);
-                            v[4 * i + 0] = mp_silu_f(v[4 * i + 0] * s.x);
-                            v[4 * i + 1] = mp_silu_f(v[4 * i + 1] * s.y);
-                            v[4 * i + 2] = mp_silu_f(v[4 * i + 2] * s.z);
-                            v[4 * i + 3] = mp_silu_f(v[4 * i + 3] * s.w);
-                        }
-                    } else if (p.epi == DD_EPI_RESIDUAL) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + ch);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 q = __ldg(rp + i);
-                            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = unpack_bf16x2(u[j]);
-                                float a0 = p.alpha * v[8 * i + 2 * j + 0] + p.beta * f.x;
-                                float a1 = p.alpha * v[8 * i + 2 * j + 1] + p.beta * f.y;
-                                v[8 * i + 2 * j + 0] = fminf(fmaxf(a0, -p.clip), p.clip);
-                                v[8 * i + 2 * j + 1] = fminf(fmaxf(a1, -p.clip), p.clip);
-                            }
-                        }
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + ch);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 q;
-                        q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                        q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                        q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                        q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                        op[i] = q;
-                    }
-                    if (p.epi2 != DD_EPI2_NONE) {
-                        if (p.epi2 == DD_EPI2_SILU) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = mp_silu_f(v[i]);
-                        } else {
-                            const float4* sc = reinterpret_cast<const float4*>(p.scale2 + (size_t)b * p.Cout + ch);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float4 s = __ldg(sc + i);
-                                v[4 * i + 0] *= s.x; v[4 * i + 1] *= s.y; v[4 * i + 2] *= s.z; v[4 * i + 3] *= s.w;
-                            }
-                        }
-                        uint4* op2 = reinterpret_cast<uint4*>(p.out2 + pix * p.Cout + ch);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 q;
-                            q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                            q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                            q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                            q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                            op2[i] = q;
-                        }
-                    }
+        for (int ks = 0; ks < NKS; ++ks) {
+            ptx::umma_bf16_ss(d_tmem, a_tap + 2 * ks, b_tap + 2 * ks, idesc, (tap == 0 && ks == 0) ? accumulate : 1u);
+        }
+    }
+}
+
+template <int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t a_full[kMaxAStages];
+    __shared__ __align__(8) uint64_t a_empty[kMaxAStages];
+    __shared__ __align__(8) uint64_t b_full, b_empty;
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_smem = smem;                                              // [kchunks][9] blocks of n_tile x 128 B
+    uint8_t* a_smem = smem + (size_t)p.kchunks * 9 * p.b_block_bytes;    // a_stages x kHaloStride
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int t_begin = (int)((long)blockIdx.x * p.num_tiles / gridDim.x);
+    const int t_end = (int)((long)(blockIdx.x + 1) * p.num_tiles / gridDim.x);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        for (int s = 0; s < p.a_stages; ++s) {
+            ptx::mbar_init(&a_full[s], 1);
+            ptx::mbar_init(&a_empty[s], 1);
+        }
+        ptx::mbar_init(&b_full, 1);
+        ptx::mbar_init(&b_empty, 1);
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(&tmem_full_bar[a], 1);
+            ptx::mbar_init(&tmem_empty_bar[a], EW);
+        }
+        ptx::mbar_fence_init();
+        ptx::fence_proxy_async_smem();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, b_par = 0;
+            int cur_panel = -1;
+            for (int tile = t_begin; tile < t_end; ++tile) {
+                const HaloTile t = decode_halo_tile(p, tile);
+                if (t.panel != cur_panel) {
+                    if (cur_panel >= 0) { ptx::mbar_wait(&b_empty, b_par); b_par ^= 1; }   // old panel fully consumed
+                    ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.kchunks * 9u * p.b_block_bytes);
+                    const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
+                    for (int kc = 0; kc < p.kchunks; ++kc)
+                        for (int tap = 0; tap < 9; ++tap)
+                            ptx::tma_load_2d(b_smem + (size_t)(kc * 9 + tap) * p.b_block_bytes, &tmB, &b_full,
+                                             tap * p.cin_g + kc * 64, b_row);
+                    cur_panel = t.panel;
+                }
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&a_full[stage], kHaloBytes);
+                    ptx::tma_load_4d(a_smem + (size_t)stage * kHaloStride, &tmA, &a_full[stage], t.g * p.cin_g + kc * 64,
+                                     t.w0 - 1, t.h0 - 1, t.b);
+                    if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
                 }
             }
-            // all TMEM reads of this buffer have completed (wait::ld above): hand it back
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        {
+            const uint32_t idesc = ptx::make_idesc_bf16(kTileM, p.n_tile);
+            const uint32_t b_base = ptx::smem_u32(b_smem), a_base = ptx::smem_u32(a_smem);
+            const uint32_t b_block16 = p.b_block_bytes >> 4;
+            uint32_t stage = 0, phase = 0, b_par = 0, local = 0;
+            int cur_panel = -1;
+            for (int tile = t_begin; tile < t_end; ++tile, ++local) {
+                const int panel = tile / p.m_tiles;
+                if (panel != cur_panel) {
+                    ptx::mbar_wait(&b_full, b_par);
+                    b_par ^= 1;
+                    cur_panel = panel;
+                }
+                const uint32_t acc = local & 1;
+                const uint32_t acc_phase = (local >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                ptx::tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
+                uint32_t accumulate = 0;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    ptx::mbar_wait(&a_full[stage], phase);
+                    ptx::tcgen05_fence_after();
+                    if (ptx::elect_one()) {
+                        const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + stage * kHaloStride, kHaloPitch * 128);
+                        const uint64_t b_desc0 = ptx::make_kmajor_desc_sw128(b_base + (uint32_t)(kc * 9) * p.b_block_bytes, 1024);
+                        const int nks = (kc == p.kchunks - 1) ? p.ks_last : 4;
+                        if (nks == 4) halo_issue_taps<4>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
+                        else if (nks == 2) halo_issue_taps<2>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
+                        else if (nks == 1) halo_issue_taps<1>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
+                        else halo_issue_taps<3>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
+                        ptx::umma_commit(&a_empty[stage]);
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
+                }
+                const bool panel_ends = (tile + 1 == t_end) || ((tile + 1) / p.m_tiles != panel);
+                if (ptx::elect_one()) {
+                    ptx::umma_commit(&tmem_full_bar[acc]);
+                    if (panel_ends) ptx::umma_commit(&b_empty);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ------------------------------ epilogue ------------------------------
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int chunk0 = ew >> 2;
+        const int row = quad * 32 + lane;
+        const int hh = row >> 3, ww = row & 7;
+        uint32_t local = 0;
+        for (int tile = t_begin; tile < t_end; ++tile, ++local) {
+            const HaloTile t = decode_halo_tile(p, tile);
+            const uint32_t acc = local & 1;
+            const uint32_t acc_phase = (local >> 1) & 1;
+            const int h = t.h0 + hh, w = t.w0 + ww;
+            const bool valid = (h < p.H) && (w < p.W);
+            const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
+            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+            ptx::tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)p.n_tile;
+            epilogue_tile<EW>(p, taddr, chunk0, valid, t.b, h, w, ch0);
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -310,80 +585,53 @@ void choose_box(int B, int H, int W, int& wt, int& ht, int& bt) {
     }
 }
 
-int choose_n_tile(int cout_g, long m_tiles, int groups, int num_sms) {
-    // candidates: multiples of 32 that divide cout_g, at most 256 wide
-    int best = 32;
-    for (int n = 32; n <= std::min(cout_g, 256); n += 32) {
+// Cost model (cycles) used to pick the output-channel tile: a k-iteration is bound either by operand
+// delivery from L2 (~36 B/cycle/SM measured on B200 with all SMs pulling) or by the tensor pipe
+// (128 x n x 16 MACs = n/2 cycles per UMMA).
+int choose_n_tile(int cout_g, long m_tiles, int groups, int k_iters, int KC, int num_sms) {
+    int best = 16;
+    double best_cost = 1e30;
+    for (int n = 16; n <= std::min(cout_g, 256); n += 16) {
         if (cout_g % n) continue;
-        best = n;
-    }
-    // small problems: prefer narrower tiles until the grid covers the SMs
-    while (best > 32) {
-        const long tiles = m_tiles * groups * (cout_g / best);
-        if (tiles >= num_sms) break;
-        int next = 0;
-        for (int n = best - 32; n >= 32; n -= 32) if (cout_g % n == 0) { next = n; break; }
-        if (!next) break;
-        best = next;
+        const long tiles = m_tiles * groups * (cout_g / n);
+        const long waves = (tiles + num_sms - 1) / num_sms;
+        const double t_l2 = (128.0 + n) * KC * 2.0 / 36.0;
+        const double t_mma = n * KC / 32.0;
+        const double t_iter = std::max(t_l2, t_mma) + 30.0;
+        const double t_epi = 64.0 + n * 6.0;                     // ~ per-tile epilogue (overlapped unless last)
+        const double cost = 2500.0 + waves * (k_iters * t_iter) + t_epi + (waves - 1) * 200.0;
+        if (cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && n > best)) { best_cost = cost; best = n; }
     }
     return best;
 }
 
-}  // namespace
-
-extern "C" int dd_mpconv_forward(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin,
-                                 int Cout, int ksize, int groups, const dd_conv_epilogue* epi, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    DD_REQUIRE(x && w_prepped && out, "dd_mpconv_forward: null pointer");
-    DD_REQUIRE(ksize == 1 || ksize == 3, "dd_mpconv_forward: kernel size %d unsupported (1 or 3)", ksize);
-    DD_REQUIRE(groups >= 1 && Cin % groups == 0 && Cout % groups == 0, "dd_mpconv_forward: bad groups");
-    const int cin_g = Cin / groups, cout_g = Cout / groups;
-    DD_REQUIRE(cin_g % 32 == 0, "dd_mpconv_forward: Cin/groups=%d must be a multiple of 32", cin_g);
-    DD_REQUIRE(cout_g % 32 == 0, "dd_mpconv_forward: Cout/groups=%d must be a multiple of 32", cout_g);
-    DD_REQUIRE(B > 0 && H > 0 && W > 0, "dd_mpconv_forward: empty input");
+int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode_fn();
     DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");
-
-    ConvParams p{};
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-    p.kh = p.kw = ksize; p.taps = ksize * ksize;
+    const int B = p.B, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout;
+    const int cin_g = Cin / groups, cout_g = Cout / groups;
     p.cin_g = cin_g; p.cout_g = cout_g;
     choose_box(B, H, W, p.wt, p.ht, p.bt);
     p.tiles_w = ceil_div(W, p.wt); p.tiles_h = ceil_div(H, p.ht); p.tiles_b = ceil_div(B, p.bt);
     p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
     const int num_sms = dd_num_sms();
-    p.n_tile = choose_n_tile(cout_g, p.m_tiles, groups, num_sms);
-    p.n_tiles_per_group = cout_g / p.n_tile;
     const int KC = (cin_g % 64 == 0) ? 64 : 32;
     p.kchunks = cin_g / KC;
+    p.k_iters = p.taps * p.kchunks;
+    p.n_tile = choose_n_tile(cout_g, p.m_tiles, groups, p.k_iters, KC, num_sms);
+    p.n_tiles_per_group = cout_g / p.n_tile;
     p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
     const uint32_t row_bytes = KC * 2;
     p.a_bytes = (uint32_t)(p.wt * p.ht * p.bt) * row_bytes;
     p.b_bytes = (uint32_t)p.n_tile * row_bytes;
-    const uint32_t stage_bytes = kTileM * row_bytes + p.b_bytes;
+    const uint32_t pair_bytes = kTileM * row_bytes + p.b_bytes;
+    p.sub = (pair_bytes <= 24u * 1024u && p.k_iters >= 2) ? 2 : 1;
+    const uint32_t stage_bytes = pair_bytes * p.sub;
     p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u) / stage_bytes)));
     uint32_t cols = 32;
     while (cols < 2u * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
 
-    if (epi) {
-        p.epi = epi->mode; p.epi2 = epi->mode2;
-        p.alpha = epi->alpha; p.beta = epi->beta;
-        p.clip = epi->clip > 0.f ? epi->clip : INFINITY;
-        p.scale = static_cast<const float*>(epi->scale);
-        p.scale2 = static_cast<const float*>(epi->scale2);
-        p.residual = static_cast<const __nv_bfloat16*>(epi->residual);
-        p.out2 = static_cast<__nv_bfloat16*>(epi->out2);
-        DD_REQUIRE(p.epi != DD_EPI_SCALE_SILU || p.scale, "dd_mpconv_forward: epilogue scale missing");
-        DD_REQUIRE(p.epi != DD_EPI_RESIDUAL || p.residual, "dd_mpconv_forward: epilogue residual missing");
-        DD_REQUIRE(p.epi2 == DD_EPI2_NONE || p.out2, "dd_mpconv_forward: epilogue out2 missing");
-        DD_REQUIRE(p.epi2 != DD_EPI2_SCALE || p.scale2, "dd_mpconv_forward: epilogue scale2 missing");
-    } else {
-        p.epi = DD_EPI_NONE; p.epi2 = DD_EPI2_NONE; p.clip = INFINITY;
-    }
-    p.out = static_cast<__nv_bfloat16*>(out);
-
-    // tensor maps
     CUtensorMap tmA, tmB;
     const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {
@@ -410,23 +658,155 @@ extern "C" int dd_mpconv_forward(const void* x, const void* w_prepped, void* out
 
     const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024;
     const int grid = std::min(p.num_tiles, num_sms);
-    if (KC == 64) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               220 * 1024));
-            attr_done = true;
-        }
-        conv_igemm_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
-    } else {
-        static bool attr_done = false;
-        if (!attr_done) {
-            DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               220 * 1024));
-            attr_done = true;
-        }
-        conv_igemm_kernel<32><<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, p);
-    }
+    int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
+    if (const char* f = getenv("DD_FORCE_EPI_WARPS")) ew = atoi(f) == 8 ? 8 : 4;   // tuning experiments only
+#define DD_LAUNCH_IGEMM(KC_, EW_)                                                                                  \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<KC_, EW_>,                                       \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        conv_igemm_kernel<KC_, EW_><<<grid, 64 + 32 * EW_, smem_bytes, stream>>>(tmA, tmB, p);                     \
+    } while (0)
+    if (KC == 64) { if (ew == 8) DD_LAUNCH_IGEMM(64, 8); else DD_LAUNCH_IGEMM(64, 4); }
+    else          { if (ew == 8) DD_LAUNCH_IGEMM(32, 8); else DD_LAUNCH_IGEMM(32, 4); }
+#undef DD_LAUNCH_IGEMM
     DD_CHECK_LAUNCH();
     return 0;
+}
+
+
+// 3x3 halo variant: used when the image is at least 16 rows tall (levels 0-1 of the 45 s latent).
+int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
+    PFN_encodeTiled encode = get_encode_fn();
+    DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");
+    const int B = p.B, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout;
+    const int cin_g = Cin / groups, cout_g = Cout / groups;
+    p.cin_g = cin_g; p.cout_g = cout_g;
+    p.wt = kHaloW; p.ht = kHaloH; p.bt = 1;
+    p.tiles_w = ceil_div(W, kHaloW); p.tiles_h = ceil_div(H, kHaloH); p.tiles_b = B;
+    p.m_tiles = p.tiles_w * p.tiles_h * B;
+    p.kchunks = ceil_div(cin_g, 64);
+    p.ks_last = (cin_g - 64 * (p.kchunks - 1)) / 16;
+    p.k_iters = p.kchunks;
+    const uint32_t budget = 214u * 1024u;
+    int n_tile = 0;
+    for (int n = 16; n <= std::min(cout_g, 256); n += 16) {
+        if (cout_g % n) continue;
+        if ((uint32_t)p.kchunks * 9u * n * 128u + 2u * kHaloStride <= budget) n_tile = n;
+    }
+    if (n_tile == 0) return -1;     // weight panel does not fit: caller falls back to the per-tap kernel
+    p.n_tile = n_tile;
+    p.n_tiles_per_group = cout_g / n_tile;
+    p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
+    p.b_block_bytes = (uint32_t)n_tile * 128u;
+    const uint32_t b_total = (uint32_t)p.kchunks * 9u * p.b_block_bytes;
+    p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((budget - b_total) / kHaloStride)));
+    uint32_t cols = 32;
+    while (cols < 2u * p.n_tile) cols <<= 1;
+    p.tmem_cols = cols;
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)kHaloPitch, (cuuint32_t)(kHaloH + 2), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: halo tensor map encode failed (CUresult %d)", (int)r);
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)9 * cin_g;
+        cuuint64_t dims[2] = {ktot, (cuuint64_t)Cout};
+        cuuint64_t strides[1] = {ktot * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_prepped), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: weight tensor map encode failed (CUresult %d)", (int)r);
+    }
+    const size_t smem_bytes = (size_t)b_total + (size_t)p.a_stages * kHaloStride + 1024;
+    const int grid = std::min(p.num_tiles, dd_num_sms());
+    const int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
+#define DD_LAUNCH_HALO(EW_)                                                                                        \
+    do {                                                                                                           \
+        static bool attr_done = false;                                                                             \
+        if (!attr_done) {                                                                                          \
+            DD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<EW_>,                                          \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
+            attr_done = true;                                                                                      \
+        }                                                                                                          \
+        conv3x3_halo_kernel<EW_><<<grid, 64 + 32 * EW_, smem_bytes, stream>>>(tmA, tmB, p);                        \
+    } while (0)
+    if (ew == 8) DD_LAUNCH_HALO(8); else DD_LAUNCH_HALO(4);
+#undef DD_LAUNCH_HALO
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_conv(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
+    static const bool no_halo = getenv("DD_DISABLE_HALO") != nullptr;     // tuning experiments only
+    if (p.taps == 9 && p.H >= kHaloH && p.W >= kHaloW && (p.Cin / groups) % 16 == 0 && p.Cin >= 64 && !no_halo) {
+        ConvParams q = p;
+        const int r = launch_halo(q, x, w_prepped, groups, stream);
+        if (r >= 0) return r;
+    }
+    return fill_and_launch(p, x, w_prepped, groups, stream);
+}
+
+}  // namespace
+
+extern "C" int dd_mpconv_forward(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin,
+                                 int Cout, int ksize, int groups, const dd_conv_epilogue* epi, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && w_prepped && out, "dd_mpconv_forward: null pointer");
+    DD_REQUIRE(ksize == 1 || ksize == 3, "dd_mpconv_forward: kernel size %d unsupported (1 or 3)", ksize);
+    DD_REQUIRE(groups >= 1 && Cin % groups == 0 && Cout % groups == 0, "dd_mpconv_forward: bad groups");
+    DD_REQUIRE((Cin / groups) % 32 == 0, "dd_mpconv_forward: Cin/groups=%d must be a multiple of 32", Cin / groups);
+    DD_REQUIRE((Cout / groups) % 16 == 0, "dd_mpconv_forward: Cout/groups=%d must be a multiple of 16", Cout / groups);
+    DD_REQUIRE(B > 0 && H > 0 && W > 0, "dd_mpconv_forward: empty input");
+
+    ConvParams p{};
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+    p.kh = p.kw = ksize; p.taps = ksize * ksize;
+    if (epi) {
+        p.epi = epi->mode; p.epi2 = epi->mode2;
+        p.alpha = epi->alpha; p.beta = epi->beta;
+        p.clip = epi->clip > 0.f ? epi->clip : INFINITY;
+        p.scale = static_cast<const float*>(epi->scale);
+        p.scale2 = static_cast<const float*>(epi->scale2);
+        p.residual = static_cast<const __nv_bfloat16*>(epi->residual);
+        p.out2 = static_cast<__nv_bfloat16*>(epi->out2);
+        DD_REQUIRE(p.epi >= DD_EPI_NONE && p.epi <= DD_EPI_RESIDUAL, "dd_mpconv_forward: bad epilogue mode %d", p.epi);
+        DD_REQUIRE(p.epi != DD_EPI_SCALE_SILU || p.scale, "dd_mpconv_forward: epilogue scale missing");
+        DD_REQUIRE(p.epi != DD_EPI_RESIDUAL || p.residual, "dd_mpconv_forward: epilogue residual missing");
+        DD_REQUIRE(p.epi2 == DD_EPI2_NONE || p.out2, "dd_mpconv_forward: epilogue out2 missing");
+        DD_REQUIRE(p.epi2 != DD_EPI2_SCALE || p.scale2, "dd_mpconv_forward: epilogue scale2 missing");
+    } else {
+        p.epi = DD_EPI_NONE; p.epi2 = DD_EPI2_NONE; p.clip = INFINITY;
+    }
+    p.out = static_cast<__nv_bfloat16*>(out);
+    return launch_conv(p, x, w_prepped, groups, stream);
+}
+
+// UNet head on the tensor cores: 3x3 conv to `Cout` (<= 16) channels whose weights were padded to 16 output
+// rows by dd_weight_prep(pad_rows), fused with the EDM output preconditioning (fp32 NCHW result).
+extern "C" int dd_conv_out(const void* x, const void* w_prepped16, const float* x_in, const float* sigma,
+                           float sigma_data, const float* x_ref, float* d_out, int B, int C, int H, int W, int Cout,
+                           void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && w_prepped16 && x_in && sigma && d_out, "dd_conv_out: null pointer");
+    DD_REQUIRE(Cout >= 1 && Cout <= 16, "dd_conv_out: out_channels=%d unsupported (1..16)", Cout);
+    DD_REQUIRE(C % 32 == 0, "dd_conv_out: C=%d must be a multiple of 32", C);
+    ConvParams p{};
+    p.B = B; p.H = H; p.W = W; p.Cin = C; p.Cout = 16;
+    p.kh = p.kw = 3; p.taps = 9;
+    p.epi = DD_EPI_HEAD; p.epi2 = DD_EPI2_NONE; p.clip = INFINITY;
+    p.head_cout = Cout; p.sigma_data = sigma_data; p.sigma = sigma; p.x_in = x_in; p.x_ref = x_ref; p.d_out = d_out;
+    return launch_conv(p, x, w_prepped16, 1, stream);
 }

@@ -35,7 +35,7 @@ __device__ __forceinline__ float load_w(const void* w, size_t i) {
 template <bool kBf16>
 __global__ void weight_prep_kernel(const void* __restrict__ w, void* __restrict__ out, int out_format, int O, int I_g,
                                    int taps, const float* __restrict__ gain_dev, float gain_host, int normalize,
-                                   int perm, int head_dim) {
+                                   int perm, int head_dim, int row_stride) {
     __shared__ float red[32];
     const int o = blockIdx.x;
     const int fan_in = I_g * taps;
@@ -56,13 +56,13 @@ __global__ void weight_prep_kernel(const void* __restrict__ w, void* __restrict_
         o_dst = (rem & 1) * (O / 2) + head * head_dim + (rem >> 1);
     }
     if (out_format == DD_WFMT_BF16_OTI) {
-        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(out) + (size_t)o_dst * fan_in;
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(out) + (size_t)o_dst * row_stride;
         for (int j = threadIdx.x; j < fan_in; j += blockDim.x) {      // j = tap * I_g + i  (coalesced writes)
             const int tap = j / I_g, i = j - tap * I_g;
             dst[j] = __float2bfloat16_rn(load_w<kBf16>(w, base + (size_t)i * taps + tap) * scale);
         }
     } else {
-        float* dst = static_cast<float*>(out) + (size_t)o_dst * fan_in;
+        float* dst = static_cast<float*>(out) + (size_t)o_dst * row_stride;
         for (int j = threadIdx.x; j < fan_in; j += blockDim.x) dst[j] = load_w<kBf16>(w, base + j) * scale;
     }
 }
@@ -173,110 +173,38 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
-// UNet stem: preconditioning + constant/positional channels + 3x3 conv (CT = Cin+2 input channels)
+// UNet stem: preconditioning + constant/positional channels, written as 3x3 patches ("im2col") so that
+// conv_in runs as a K=64 GEMM on the tensor cores.  patch[pix][tap*CT + c], zero padded to 64 columns.
 // ------------------------------------------------------------------------------------------
-constexpr int kStemPix = 32;
-
-template <int CT>
-__global__ void __launch_bounds__(256)
-conv_in_kernel(const float* __restrict__ x_in, const float* __restrict__ sigma, float sigma_data,
-               const float* __restrict__ ln_freqs, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-               int B, int H, int W, int Cout) {
-    __shared__ float patch[CT][3][kStemPix + 2];
-    const int w0 = blockIdx.x * kStemPix, h = blockIdx.y, b = blockIdx.z;
-    const float sg = sigma[b];
-    const float c_in = rsqrtf(sigma_data * sigma_data + sg * sg);
-    constexpr int kCin = CT - 2;
-    for (int i = threadIdx.x; i < CT * 3 * (kStemPix + 2); i += blockDim.x) {
-        const int px = i % (kStemPix + 2), dy = (i / (kStemPix + 2)) % 3, c = i / (3 * (kStemPix + 2));
-        const int hh = h + dy - 1, ww = w0 + px - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-            if (c < kCin) v = c_in * x_in[(((size_t)b * kCin + c) * H + hh) * W + ww];
-            else if (c == kCin) v = 1.f;
-            else v = ln_freqs[hh];
-        }
-        patch[c][dy][px] = v;
-    }
-    __syncthreads();
-    for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-        float wr[CT * 9];
+__global__ void stem_patches_kernel(const float* __restrict__ x_in, const float* __restrict__ sigma, float sigma_data,
+                                    const float* __restrict__ ln_freqs, uint4* __restrict__ out, int B, int Cin, int H,
+                                    int W) {
+    const int CT = Cin + 2;
+    const long total = (long)B * H * W * 8;       // 8 x (8 bf16) per pixel
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx & 7);
+        const long pix = idx >> 3;
+        const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+        const float sg = __ldg(sigma + b);
+        const float c_in = rsqrtf(sigma_data * sigma_data + sg * sg);
+        float f[8];
 #pragma unroll
-        for (int i = 0; i < CT * 9; ++i) wr[i] = __ldg(w + (size_t)co * CT * 9 + i);
-        for (int px = 0; px < kStemPix; ++px) {
-            if (w0 + px >= W) break;
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < CT; ++c)
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) acc += wr[c * 9 + dy * 3 + dx] * patch[c][dy][px + dx];
-            out[(((size_t)b * H + h) * W + w0 + px) * Cout + co] = __float2bfloat16_rn(acc);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// UNet head: 3x3 conv to a handful of channels + EDM output preconditioning (warp per pixel)
-// ------------------------------------------------------------------------------------------
-template <int COUT>
-__global__ void __launch_bounds__(256)
-conv_out_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ x_in,
-                const float* __restrict__ sigma, float sigma_data, const float* __restrict__ x_ref,
-                float* __restrict__ d_out, int B, int C, int H, int W) {
-    extern __shared__ float wsm[];   // [9][COUT][C]
-    for (int i = threadIdx.x; i < 9 * COUT * C; i += blockDim.x) {
-        const int c = i % C, co = (i / C) % COUT, tap = i / (C * COUT);
-        wsm[i] = w[((size_t)co * C + c) * 9 + tap];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, nvec = C >> 3;
-    const long npix = (long)B * H * W;
-    const int warps_total = gridDim.x * (blockDim.x >> 5);
-    for (long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < npix; pix += warps_total) {
-        const int wq = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
-        float acc[COUT];
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            const int hh = h + tap / 3 - 1, ww = wq + tap % 3 - 1;
-            if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
-            const uint4* src = x + (((long)b * H + hh) * W + ww) * nvec;
-            for (int v = lane; v < nvec; v += 32) {
-                const uint4 q = __ldg(src + v);
-                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(u[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
-#pragma unroll
-                for (int co = 0; co < COUT; ++co) {
-                    const float* wp = wsm + ((size_t)tap * COUT + co) * C + v * 8;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[co] += f[j] * wp[j];
+        for (int j = 0; j < 8; ++j) {
+            const int k = v * 8 + j;
+            float val = 0.f;
+            if (k < 9 * CT) {
+                const int tap = k / CT, c = k - tap * CT;
+                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                    if (c < Cin) val = c_in * __ldg(x_in + (((size_t)b * Cin + c) * H + hh) * W + ww);
+                    else if (c == Cin) val = 1.f;
+                    else val = __ldg(ln_freqs + hh);
                 }
             }
+            f[j] = val;
         }
-#pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[co] = warp_sum(acc[co]);
-        if (lane == 0) {
-            const float sg = sigma[b];
-            const float sd2 = sigma_data * sigma_data;
-            const float c_skip = sd2 / (sg * sg + sd2);
-            const float c_out = sg * sigma_data * rsqrtf(sg * sg + sd2);
-#pragma unroll
-            for (int co = 0; co < COUT; ++co) {
-                const size_t o = (((size_t)b * COUT + co) * H + h) * W + wq;
-                float d = c_skip * x_in[o] + c_out * acc[co];
-                if (x_ref) {   // unet_edm2_b4.py:293-294, tensor-valued mp_sum
-                    const size_t plane = (size_t)H * W;
-                    const float r = x_ref[((size_t)b * (COUT + 1) + co) * plane + (size_t)h * W + wq];
-                    const float t = x_ref[((size_t)b * (COUT + 1) + COUT) * plane + (size_t)h * W + wq];
-                    d = (r + t * (d - r)) * rsqrtf((1.f - t) * (1.f - t) + t * t);
-                }
-                d_out[o] = d;
-            }
-        }
+        out[idx] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
     }
 }
 
@@ -503,18 +431,20 @@ inline int grid_for(long total, int block, int cap_mult = 8) {
 // ------------------------------------------------------------------------------------------
 extern "C" int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_format, int O, int I_g, int taps,
                               const float* gain_dev, float gain_host, int normalize, int perm, int head_dim,
-                              void* stream_) {
+                              int out_row_stride, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(w && out && O > 0 && I_g > 0 && taps > 0, "dd_weight_prep: bad arguments");
     DD_REQUIRE(out_format == DD_WFMT_BF16_OTI || out_format == DD_WFMT_F32_OIT, "dd_weight_prep: bad out_format");
     DD_REQUIRE(perm == DD_WPERM_NONE || (perm == DD_WPERM_QK && head_dim > 0 && O % (2 * head_dim) == 0),
                "dd_weight_prep: bad permutation arguments");
+    const int row_stride = out_row_stride > 0 ? out_row_stride : I_g * taps;
+    DD_REQUIRE(row_stride >= I_g * taps, "dd_weight_prep: out_row_stride smaller than a row");
     if (w_is_bf16)
         weight_prep_kernel<true><<<O, 128, 0, stream>>>(w, out, out_format, O, I_g, taps, gain_dev, gain_host, normalize,
-                                                        perm, head_dim);
+                                                        perm, head_dim, row_stride);
     else
         weight_prep_kernel<false><<<O, 128, 0, stream>>>(w, out, out_format, O, I_g, taps, gain_dev, gain_host,
-                                                         normalize, perm, head_dim);
+                                                         normalize, perm, head_dim, row_stride);
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -558,49 +488,15 @@ extern "C" int dd_avgpool2(const void* x, void* out, int B, int H, int W, int C,
     return 0;
 }
 
-extern "C" int dd_conv_in(const float* x_in, const float* sigma, float sigma_data, const float* ln_freqs,
-                          const float* w, void* out, int B, int Cin, int H, int W, int Cout, void* stream_) {
+extern "C" int dd_stem_patches(const float* x_in, const float* sigma, float sigma_data, const float* ln_freqs,
+                               void* out, int B, int Cin, int H, int W, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    DD_REQUIRE(x_in && sigma && ln_freqs && w && out, "dd_conv_in: null pointer");
-    const dim3 grid(ceil_div(W, kStemPix), H, B);
-#define DD_LAUNCH_STEM(CT)                                                                                       \
-    conv_in_kernel<CT><<<grid, 256, 0, stream>>>(x_in, sigma, sigma_data, ln_freqs, w,                          \
-                                                 static_cast<__nv_bfloat16*>(out), B, H, W, Cout)
-    switch (Cin) {
-        case 1: DD_LAUNCH_STEM(3); break;
-        case 2: DD_LAUNCH_STEM(4); break;
-        case 4: DD_LAUNCH_STEM(6); break;
-        case 8: DD_LAUNCH_STEM(10); break;
-        default: DD_REQUIRE(false, "dd_conv_in: in_channels=%d unsupported (1,2,4,8)", Cin);
-    }
-#undef DD_LAUNCH_STEM
-    DD_CHECK_LAUNCH();
-    return 0;
-}
-
-extern "C" int dd_conv_out(const void* x, const float* w, const float* x_in, const float* sigma, float sigma_data,
-                           const float* x_ref, float* d_out, int B, int C, int H, int W, int Cout, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    DD_REQUIRE(x && w && x_in && sigma && d_out, "dd_conv_out: null pointer");
-    DD_REQUIRE(C % 8 == 0, "dd_conv_out: C must be a multiple of 8");
-    const size_t smem = (size_t)9 * Cout * C * sizeof(float);
-    DD_REQUIRE(smem <= 200 * 1024, "dd_conv_out: weights (%zu B) do not fit in shared memory", smem);
-    const int grid = std::min<long>((long)dd_num_sms() * 2, ((long)B * H * W + 7) / 8);
-#define DD_LAUNCH_HEAD(CO)                                                                                           \
-    do {                                                                                                             \
-        DD_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                           (int)smem));                                                              \
-        conv_out_kernel<CO><<<grid, 256, smem, stream>>>(static_cast<const uint4*>(x), w, x_in, sigma, sigma_data,   \
-                                                         x_ref, d_out, B, C, H, W);                                  \
-    } while (0)
-    switch (Cout) {
-        case 1: DD_LAUNCH_HEAD(1); break;
-        case 2: DD_LAUNCH_HEAD(2); break;
-        case 4: DD_LAUNCH_HEAD(4); break;
-        case 8: DD_LAUNCH_HEAD(8); break;
-        default: DD_REQUIRE(false, "dd_conv_out: out_channels=%d unsupported (1,2,4,8)", Cout);
-    }
-#undef DD_LAUNCH_HEAD
+    DD_REQUIRE(x_in && sigma && ln_freqs && out, "dd_stem_patches: null pointer");
+    DD_REQUIRE(9 * (Cin + 2) <= 64, "dd_stem_patches: in_channels=%d unsupported (9*(Cin+2) must be <= 64)", Cin);
+    const long total = (long)B * H * W * 8;
+    if (total == 0) return 0;
+    stem_patches_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x_in, sigma, sigma_data, ln_freqs,
+                                                                  static_cast<uint4*>(out), B, Cin, H, W);
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -126,25 +126,26 @@ class _Plan:
             self.gain_version = ver
 
     # ---- weight preparation cache: refresh when a parameter's version changes ----
-    def _weights(self) -> List[Tuple[str, torch.nn.Parameter, Optional[torch.nn.Parameter], int, int]]:
+    def _weights(self) -> list:
         if self._weight_items is not None:
             return self._weight_items
         net = self.net
         items = []
-        items.append(("enc.conv_in", net.enc["conv_in"].weight, None, L.WFMT_F32_OIT, 0))
+        # (key, weight, gain, qk_head_dim, pad_rows, row_stride)
+        items.append(("enc.conv_in", net.enc["conv_in"].weight, None, 0, 0, 64))       # K = 9*(Cin+2) padded to 64
         for prefix, blocks in (("enc", net.enc), ("dec", net.dec)):
             for name, blk in blocks.items():
                 if not isinstance(blk, Block):
                     continue
                 p = f"{prefix}.{name}"
-                items.append((p + ".conv_res0", blk.conv_res0.weight, None, L.WFMT_BF16_OTI, 0))
-                items.append((p + ".conv_res1", blk.conv_res1.weight, None, L.WFMT_BF16_OTI, 0))
-                items.append((p + ".conv_skip", blk.conv_skip.weight, None, L.WFMT_BF16_OTI, 0))
+                items.append((p + ".conv_res0", blk.conv_res0.weight, None, 0, 0, 0))
+                items.append((p + ".conv_res1", blk.conv_res1.weight, None, 0, 0, 0))
+                items.append((p + ".conv_skip", blk.conv_skip.weight, None, 0, 0, 0))
                 if blk.use_attention:
-                    items.append((p + ".attn_qk", blk.attn_qk.weight, None, L.WFMT_BF16_OTI, blk.channels_per_head))
-                    items.append((p + ".attn_v", blk.attn_v.weight, None, L.WFMT_BF16_OTI, 0))
-                    items.append((p + ".attn_proj", blk.attn_proj.weight, None, L.WFMT_BF16_OTI, 0))
-        items.append(("conv_out", net.conv_out.weight, net.out_gain, L.WFMT_F32_OIT, 0))
+                    items.append((p + ".attn_qk", blk.attn_qk.weight, None, blk.channels_per_head, 0, 0))
+                    items.append((p + ".attn_v", blk.attn_v.weight, None, 0, 0, 0))
+                    items.append((p + ".attn_proj", blk.attn_proj.weight, None, 0, 0, 0))
+        items.append(("conv_out", net.conv_out.weight, net.out_gain, 0, 16, 0))         # Cout padded to 16 rows
         self._weight_items = items
         return items
 
@@ -152,13 +153,13 @@ class _Plan:
         training = self.net.training
         stale_all = training != self.training
         self.refresh_gains()
-        for key, w, gain, fmt, qk_dim in self._weights():
+        for key, w, gain, qk_dim, pad_rows, row_stride in self._weights():
             ver = w._version + (gain._version if gain is not None else 0)
             if not stale_all and self.versions.get(key) == ver and key in self.prepped:
                 continue
             self.prepped[key] = ops.weight_prep(w.detach(), gain=None if gain is None else self.gain_ptr(gain),
-                                                normalize=training, fmt=fmt, qk_head_dim=qk_dim,
-                                                out=self.prepped.get(key))
+                                                normalize=training, qk_head_dim=qk_dim, pad_rows=pad_rows,
+                                                row_stride=row_stride, out=self.prepped.get(key))
             self.versions[key] = ver
         self.training = training
 
@@ -359,7 +360,8 @@ class UNet(DualDiffusionUNet):
         ops.emb_affine(descs, len(st["entries"]), max_o, emb)
         cvec = st["outs"]
 
-        x = ops.conv_in(net_in, sigma, cfg.sigma_data, ln_freqs, W["enc.conv_in"])
+        patches = ops.stem_patches(net_in, sigma, cfg.sigma_data, ln_freqs)
+        x = ops.mpconv(patches, W["enc.conv_in"], 1)
         skips = [x]
         ca_r, cb_r = _mp_sum_coeffs(cfg.res_balance)
         ca_a, cb_a = _mp_sum_coeffs(cfg.attn_balance)

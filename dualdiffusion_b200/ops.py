@@ -37,7 +37,8 @@ def _is_bf16(t: Tensor) -> int:
 
 
 def weight_prep(w: Tensor, gain: Optional[Tensor] = None, gain_host: float = 1.0, normalize: bool = False,
-                fmt: int = L.WFMT_BF16_OTI, qk_head_dim: int = 0, out: Optional[Tensor] = None) -> Tensor:
+                fmt: int = L.WFMT_BF16_OTI, qk_head_dim: int = 0, out: Optional[Tensor] = None,
+                pad_rows: int = 0, row_stride: int = 0) -> Tensor:
     """MPConv weight path (reference modules/mp_tools.py:359-364) fused into one pass."""
     L.require_cuda(w)
     w = w.contiguous()
@@ -47,13 +48,16 @@ def weight_prep(w: Tensor, gain: Optional[Tensor] = None, gain_host: float = 1.0
     for s in w.shape[2:]:
         taps *= s
     if out is None:
-        if fmt == L.WFMT_BF16_OTI:
+        if pad_rows or row_stride:      # zero-initialised padded buffer [max(O,pad_rows)][row_stride or taps*I_g]
+            out = torch.zeros((max(O, pad_rows), row_stride or taps * I_g), device=w.device,
+                              dtype=torch.bfloat16 if fmt == L.WFMT_BF16_OTI else torch.float32)
+        elif fmt == L.WFMT_BF16_OTI:
             out = torch.empty((O, taps, I_g), device=w.device, dtype=torch.bfloat16)
         else:
             out = torch.empty((O, I_g, taps), device=w.device, dtype=torch.float32)
     perm = L.WPERM_QK if qk_head_dim else L.WPERM_NONE
     L.check(L.load().dd_weight_prep(L.ptr(w), _is_bf16(w), L.ptr(out), fmt, O, I_g, taps, L.ptr(gain), gain_host,
-                                    int(normalize), perm, qk_head_dim, L.stream_ptr()))
+                                    int(normalize), perm, qk_head_dim, row_stride, L.stream_ptr()))
     _count()
     return out
 
@@ -86,25 +90,26 @@ def mpconv_naive(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1) -> T
     return out
 
 
-def conv_in(x_in: Tensor, sigma: Tensor, sigma_data: float, ln_freqs: Tensor, w_f32: Tensor,
-            out: Optional[Tensor] = None) -> Tensor:
+def stem_patches(x_in: Tensor, sigma: Tensor, sigma_data: float, ln_freqs: Tensor,
+                 out: Optional[Tensor] = None) -> Tensor:
+    """Stem input as zero-padded 3x3 patches [B, H, W, 64] (conv_in then runs as a K=64 tensor-core GEMM)."""
     B, Cin, H, W = x_in.shape
-    Cout = w_f32.shape[0]
     if out is None:
-        out = torch.empty((B, H, W, Cout), device=x_in.device, dtype=torch.bfloat16)
-    L.check(L.load().dd_conv_in(L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(ln_freqs), L.ptr(w_f32), L.ptr(out), B, Cin,
-                                H, W, Cout, L.stream_ptr()))
+        out = torch.empty((B, H, W, 64), device=x_in.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_stem_patches(L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(ln_freqs), L.ptr(out), B, Cin, H, W,
+                                     L.stream_ptr()))
     _count()
     return out
 
 
-def conv_out(x: Tensor, w_f32: Tensor, x_in: Tensor, sigma: Tensor, sigma_data: float,
+def conv_out(x: Tensor, w16: Tensor, x_in: Tensor, sigma: Tensor, sigma_data: float,
              x_ref: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """w16: bf16 [16, 9*C] from weight_prep(conv_out.weight, gain=out_gain, pad_rows=16)."""
     B, H, W, Cc = x.shape
-    Cout = w_f32.shape[0]
+    Cout = x_in.shape[1]
     if out is None:
         out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
-    L.check(L.load().dd_conv_out(L.ptr(x), L.ptr(w_f32), L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(x_ref), L.ptr(out),
+    L.check(L.load().dd_conv_out(L.ptr(x), L.ptr(w16), L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(x_ref), L.ptr(out),
                                  B, Cc, H, W, Cout, L.stream_ptr()))
     _count()
     return out

@@ -43,7 +43,7 @@ DD_API int dd_device_info(int* num_sms, int* cc_major, int* cc_minor);
 /* ---- weight preparation: MPConv.forward weight path, modules/mp_tools.py:359-364 ----------- */
 /* w      : [O][I_g][taps] weights as stored by the reference (OIHW, fp32 or bf16)
  * out    : DD_WFMT_BF16_OTI : bf16 [O'][taps][I_g]  (operand layout of dd_mpconv_forward)
- *          DD_WFMT_F32_OIT  : fp32 [O][I_g][taps]   (same order as the input; dd_conv_in/out)
+ *          DD_WFMT_F32_OIT  : fp32 [O][I_g][taps]   (same order as the input; normalize_weights)
  * math   : w_o <- w_o / (1e-4 + ||w_o||_2 / sqrt(fan_in))   if normalize != 0  (training mode)
  *          w_o <- w_o * gain_host * (*gain_dev) / sqrt(fan_in),  fan_in = I_g * taps
  * gain_dev may be NULL (== 1).  perm = DD_WPERM_QK de-interleaves the attn_qk output channels:
@@ -53,8 +53,11 @@ DD_API int dd_device_info(int* num_sms, int* cc_major, int* cc_minor);
 #define DD_WFMT_F32_OIT 1
 #define DD_WPERM_NONE 0
 #define DD_WPERM_QK 1
+/* out_row_stride (elements, 0 = dense I_g*taps) lets rows be written into a wider, zero-initialised buffer
+ * (K padded to 64 for the stem GEMM; Cout padded to 16 rows for the head GEMM).                    */
 DD_API int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_format, int O, int I_g, int taps,
-                   const float* gain_dev, float gain_host, int normalize, int perm, int head_dim, void* stream);
+                          const float* gain_dev, float gain_host, int normalize, int perm, int head_dim,
+                          int out_row_stride, void* stream);
 
 /* ---- MPConv forward: F.conv2d in MPConv.forward, modules/mp_tools.py:369 ------------------- */
 /* Stride-1, zero "same" padding, ksize in {1,3}, Cin/groups and Cout/groups multiples of 32.
@@ -89,16 +92,18 @@ DD_API int dd_mpconv_forward(const void* x, const void* w_prepped, void* out, in
 DD_API int dd_mpconv_forward_naive(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin, int Cout,
                             int ksize, int groups, void* stream);
 
-/* ---- UNet stem and head: modules/unets/unet_edm2_b4.py:258-271 and :290-291 ---------------- */
-/* x = cat(c_in(sigma)*x_in, ones, ln_freqs) -> conv_in 3x3 (Cin+2 -> Cout), output NHWC bf16.
- * w_prepped: fp32 [Cout][Cin+2][9] from dd_weight_prep(DD_WFMT_F32_OIT).                         */
-DD_API int dd_conv_in(const float* x_in_nchw, const float* sigma, float sigma_data, const float* ln_freqs_h,
-               const float* w_prepped, void* out_nhwc, int B, int Cin, int H, int W, int Cout, void* stream);
-/* D = c_skip(sigma)*x_in + c_out(sigma)*conv_out(x); w_prepped fp32 [Cout][C][9] includes out_gain.
- * x_ref (optional, [B][Cout+1][H][W] fp32): D = mp_sum(x_ref[:, :-1], D, t = x_ref[:, -1:])  (:293-294) */
-DD_API int dd_conv_out(const void* x_nhwc, const float* w_prepped, const float* x_in_nchw, const float* sigma,
-                float sigma_data, const float* x_ref_nchw, float* d_out_nchw, int B, int C, int H, int W, int Cout,
-                void* stream);
+/* ---- UNet stem and head: modules/unets/unet_edm2_b4.py:258-271 and :290-294 ---------------- */
+/* Stem input cat(c_in(sigma)*x_in, ones, ln_freqs) (:262-271) written as zero-padded 3x3 patches
+ * out[b][h][w][tap*(Cin+2)+c] (bf16, 64 columns) so that conv_in is dd_mpconv_forward(ksize=1, Cin=64)
+ * with weights from dd_weight_prep(DD_WFMT_BF16_OTI, out_row_stride=64).                            */
+DD_API int dd_stem_patches(const float* x_in_nchw, const float* sigma, float sigma_data, const float* ln_freqs_h,
+                           void* out_patches, int B, int Cin, int H, int W, void* stream);
+/* D = c_skip(sigma)*x_in + c_out(sigma)*conv_out(x) on the tensor cores; w_prepped16: bf16 [16][9][C]
+ * (rows >= Cout zero) from dd_weight_prep(gain = out_gain).  x_ref (optional, [B][Cout+1][H][W] fp32):
+ * D = mp_sum(x_ref[:, :-1], D, t = x_ref[:, -1:])  (:293-294).  Result fp32 NCHW.                     */
+DD_API int dd_conv_out(const void* x_nhwc, const void* w_prepped16, const float* x_in_nchw, const float* sigma,
+                       float sigma_data, const float* x_ref_nchw, float* d_out_nchw, int B, int C, int H, int W,
+                       int Cout, void* stream);
 
 /* ---- embeddings: unet_edm2_b4.py:232-238, :273-276; MPFourier mp_tools.py:324-330 ---------- */
 /* emb[b] = mp_silu(mp_sum(W_noise @ fourier(ln(sigma_b)/4) / sqrt(cnoise), label_emb[b], t))      */

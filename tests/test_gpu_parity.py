@@ -55,6 +55,11 @@ CONV_CASES = [
     (2, 2, 43, 1280, 2560, 3, 8),    # coarsest level of the 45 s latent: cout_g 320 split in two n tiles
     (1, 4, 4, 1280, 1280, 1, 1),     # 16 pixels (config-1 coarsest level)
     (1, 1, 1, 64, 32, 3, 1),         # one pixel: every tap but the centre is padding
+    # >= 16 image rows: 3x3 "halo" kernel (taps as shifted views of one smem tile, stationary weights)
+    (1, 16, 8, 64, 64, 3, 1),        # exactly one 8x16 tile, one chunk
+    (2, 17, 20, 768, 512, 3, 8),     # ragged tile edges; cin_g 96 = 64 + 32 (partial second chunk)
+    (1, 32, 24, 1280, 1024, 3, 8),   # cin_g 160 (3 chunks), weight panel forces n_tile 32, several panels per CTA
+    (1, 16, 344, 512, 256, 3, 8),    # level-1 row of the 45 s latent, cout_g 32
 ]
 
 
@@ -230,7 +235,8 @@ def test_attention_vs_oracle(dev, B, H, W, heads):
 
 
 def test_stem_and_head_vs_oracle(dev):
-    from dualdiffusion_b200 import ops, _lib as L
+    """conv_in (unet_edm2_b4.py:258-271) as stem patches + K=64 GEMM; conv_out + EDM preconditioning (:290-294)."""
+    from dualdiffusion_b200 import ops
     spec = uo.small_spec()
     gen = torch.Generator().manual_seed(23)
     B, H, W = 2, 32, 48
@@ -240,21 +246,28 @@ def test_stem_and_head_vs_oracle(dev):
     lf = uo.ln_freqs_channel(spec, B, H, W)
     c_in = 1 / (1 + sigma ** 2).sqrt()
     xx = torch.cat([c_in.view(-1, 1, 1, 1) * x_in, torch.ones_like(x_in[:, :1]), lf], 1)
-    ref = uo.mp_conv(xx, w)
-    y = ops.conv_in(x_in.to(dev), sigma.to(dev), 1.0, lf[0, 0, :, 0].contiguous().to(dev),
-                    ops.weight_prep(w.to(dev), fmt=L.WFMT_F32_OIT))
-    assert rel_err(to_nchw(y), ref) < BF16_OP
+    patches = ops.stem_patches(x_in.to(dev), sigma.to(dev), 1.0, lf[0, 0, :, 0].contiguous().to(dev))
+    # patch layout: [tap*6 + c], zero padded to 64 columns -- an index map, exact up to the bf16 store
+    ref_p = F.unfold(xx, 3, padding=1).view(B, 6, 9, H, W).permute(0, 3, 4, 2, 1).reshape(B, H, W, 54)
+    assert rel_err(patches[..., :54], ref_p) < BF16_OP
+    got_p = patches.float().cpu()
+    assert torch.equal(got_p[..., 4:54:6], ref_p[..., 4:54:6])              # constant channel incl. zero padding: exact
+    assert torch.equal(got_p[..., 5:54:6], bf16_round(ref_p[..., 5:54:6]))  # positional channel: exact placement
+    assert got_p[..., 54:].abs().max().item() == 0
+    y = ops.mpconv(patches, ops.weight_prep(w.to(dev), row_stride=64), 1)
+    assert rel_err(to_nchw(y), uo.mp_conv(xx, w)) < 2 * BF16_OP
     x = bf16_round(torch.randn(B, 256, H, W, generator=gen))
     w = torch.randn(4, 256, 3, 3, generator=gen)
     gain = torch.tensor(0.5)
     s = sigma.view(-1, 1, 1, 1)
     ref = x_in / (1 + s ** 2) + s / (1 + s ** 2).sqrt() * uo.mp_conv(x, w, gain)
-    wp = ops.weight_prep(w.to(dev), gain=gain.to(dev), fmt=L.WFMT_F32_OIT)
-    d = ops.conv_out(nhwc_bf16(x, dev), wp, x_in.to(dev), sigma.to(dev), 1.0)
-    assert rel_err(d, ref) < 1e-4
+    w16 = ops.weight_prep(w.to(dev), gain=gain.to(dev), pad_rows=16)
+    d = ops.conv_out(nhwc_bf16(x, dev), w16, x_in.to(dev), sigma.to(dev), 1.0)
+    assert d.shape == (B, 4, H, W) and d.dtype == torch.float32
+    assert rel_err(d, ref) < BF16_OP
     x_ref = torch.rand(B, 5, H, W, generator=gen)
-    d = ops.conv_out(nhwc_bf16(x, dev), wp, x_in.to(dev), sigma.to(dev), 1.0, x_ref=x_ref.to(dev))
-    assert rel_err(d, uo.mp_sum(x_ref[:, :-1], ref, x_ref[:, -1:])) < 1e-4
+    d = ops.conv_out(nhwc_bf16(x, dev), w16, x_in.to(dev), sigma.to(dev), 1.0, x_ref=x_ref.to(dev))
+    assert rel_err(d, uo.mp_sum(x_ref[:, :-1], ref, x_ref[:, -1:])) < BF16_OP
 
 
 def test_sampler_glue_vs_oracle(dev):

@@ -113,27 +113,6 @@ elif case == "elementwise":
     print("wprep qk perm", rel(wp, wr))
     wp = ops.weight_prep(w.to(torch.bfloat16), fmt=L.WFMT_F32_OIT)
     print("wprep f32 from bf16", rel(wp, w.to(torch.bfloat16).float().view(256, 128, 1) / math.sqrt(128)))
-elif case == "stem":
-    B, H, W = 2, 32, 48
-    x_in = torch.randn(B, 4, H, W, device=dev); sigma = torch.tensor([2.0, 0.5], device=dev)
-    lf = torch.randn(H, device=dev)
-    w = torch.randn(256, 6, 3, 3, device=dev)
-    wp = ops.weight_prep(w, fmt=L.WFMT_F32_OIT)
-    y = ops.conv_in(x_in, sigma, 1.0, lf, wp)
-    c_in = 1 / (1 + sigma ** 2).sqrt()
-    xx = torch.cat([c_in.view(-1, 1, 1, 1) * x_in, torch.ones_like(x_in[:, :1]), lf.view(1, 1, H, 1).expand(B, 1, H, W)], 1)
-    yr = F.conv2d(xx, w / math.sqrt(54), padding=1).permute(0, 2, 3, 1)
-    print("conv_in", rel(y, yr))
-    x = nhwc(torch.randn(B, 256, H, W, device=dev)); w = torch.randn(4, 256, 3, 3, device=dev); g = torch.tensor(0.5, device=dev)
-    wp = ops.weight_prep(w, gain=g, fmt=L.WFMT_F32_OIT)
-    d = ops.conv_out(x, wp, x_in, sigma, 1.0)
-    yr = F.conv2d(x.float().permute(0, 3, 1, 2), w * 0.5 / math.sqrt(2304), padding=1)
-    s = sigma.view(-1, 1, 1, 1); dr = x_in / (1 + s ** 2) + s / (1 + s ** 2).sqrt() * yr
-    print("conv_out", rel(d, dr))
-    xr = torch.rand(B, 5, H, W, device=dev)
-    d = ops.conv_out(x, wp, x_in, sigma, 1.0, x_ref=xr)
-    t = xr[:, -1:]; dr2 = torch.lerp(xr[:, :-1], dr, t) / ((1 - t) ** 2 + t ** 2).sqrt()
-    print("conv_out x_ref", rel(d, dr2))
 elif case == "emb":
     B, cemb, cn = 3, 768, 256
     sigma = torch.tensor([2.0, 0.05, 150.0], device=dev)
