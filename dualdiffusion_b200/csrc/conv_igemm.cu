@@ -619,6 +619,10 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.kchunks = cin_g / KC;
     p.k_iters = p.taps * p.kchunks;
     p.n_tile = choose_n_tile(cout_g, p.m_tiles, groups, p.k_iters, KC, num_sms);
+    if (const char* f = getenv("DD_FORCE_NTILE")) {            // tuning experiments only
+        const int n = atoi(f);
+        if (n >= 16 && n <= 256 && n % 16 == 0 && cout_g % n == 0) p.n_tile = n;
+    }
     p.n_tiles_per_group = cout_g / p.n_tile;
     p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
     const uint32_t row_bytes = KC * 2;
@@ -658,6 +662,10 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
 
     const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024;
     const int grid = std::min(p.num_tiles, num_sms);
+    if (getenv("DD_DEBUG_CONV"))
+        fprintf(stderr, "[conv] B%d %dx%d %d->%d k%d g%d: box %dx%dx%d m_tiles %d n_tile %d tiles %d k_iters %d KC %d sub %d stages %d\n",
+                B, H, W, Cin, Cout, p.kw, groups, p.wt, p.ht, p.bt, p.m_tiles, p.n_tile, p.num_tiles, p.k_iters, KC, p.sub,
+                p.stages);
     int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
     if (const char* f = getenv("DD_FORCE_EPI_WARPS")) ew = atoi(f) == 8 ? 8 : 4;   // tuning experiments only
 #define DD_LAUNCH_IGEMM(KC_, EW_)                                                                                  \

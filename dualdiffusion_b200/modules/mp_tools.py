@@ -136,8 +136,13 @@ class MPConv(torch.nn.Module):
         gain_t = gain.detach().float() if isinstance(gain, Tensor) else None
         gain_h = 1.0 if isinstance(gain, Tensor) else float(gain)
         normalize = self.training and not self.disable_weight_norm
-        key = (self.weight._version, self.weight.data_ptr(), normalize, gain_h,
-               None if gain_t is None else (gain_t.data_ptr(), gain._version))
+        def ver(t: Tensor) -> int:
+            try:
+                return t._version
+            except RuntimeError:        # inference tensor: immutable
+                return 0
+        key = (ver(self.weight), self.weight.data_ptr(), normalize, gain_h,
+               None if gain_t is None else (gain_t.data_ptr(), ver(gain)))
         if self._prepped is None or key != self._prepped_key:
             self._prepped = ops.weight_prep(self.weight.detach(), gain=gain_t, gain_host=gain_h, normalize=normalize)
             self._prepped_key = key

@@ -88,6 +88,15 @@ class Block(torch.nn.Module):
             self.attn_proj = MPConv(out_channels, out_channels, kernel=(1, 1))
 
 
+def _ver(t: Tensor) -> int:
+    """Parameter version counter; inference tensors (module built under torch.inference_mode) do not track
+    one and cannot be updated by an optimizer, so they count as immutable."""
+    try:
+        return t._version
+    except RuntimeError:
+        return 0
+
+
 def _mp_sum_coeffs(t: float) -> Tuple[float, float]:
     """mp_sum(a, b, t) = ca*a + cb*b  (mp_tools.py:274-279)."""
     n = math.sqrt((1 - t) ** 2 + t ** 2)
@@ -114,13 +123,16 @@ class _Plan:
         self.gains_f32 = torch.zeros(max(1, len(self.gain_params)), device=self.device, dtype=torch.float32)
         self.gain_version = None
         self._weight_items = None
+        # second stream: independent kernels of a block (conv_skip vs the residual branch, attn_v vs attn_qk,
+        # the embedding projections vs the stem) run as parallel branches of the captured graph
+        self.side = torch.cuda.Stream(device=self.device)
 
     def gain_ptr(self, p: torch.nn.Parameter) -> Tensor:
         i = self.gain_index[id(p)]
         return self.gains_f32[i:i + 1]
 
     def refresh_gains(self) -> None:
-        ver = sum(p._version for p in self.gain_params)
+        ver = sum(_ver(p) for p in self.gain_params)
         if ver != self.gain_version:
             self.gains_f32.copy_(torch.stack([p.detach().float() for p in self.gain_params]))
             self.gain_version = ver
@@ -154,7 +166,7 @@ class _Plan:
         stale_all = training != self.training
         self.refresh_gains()
         for key, w, gain, qk_dim, pad_rows, row_stride in self._weights():
-            ver = w._version + (gain._version if gain is not None else 0)
+            ver = _ver(w) + (_ver(gain) if gain is not None else 0)
             if not stale_all and self.versions.get(key) == ver and key in self.prepped:
                 continue
             self.prepped[key] = ops.weight_prep(w.detach(), gain=None if gain is None else self.gain_ptr(gain),
@@ -277,8 +289,8 @@ class UNet(DualDiffusionUNet):
         `.to(dtype)` like the reference's; the kernels always want fp32)."""
         dev = torch.device(self.device)
         aux = getattr(self, "_aux_cache", None)
-        if aux is None or aux["device"] != dev or aux["src"] != (self.emb_fourier.freqs.data_ptr(), self.emb_fourier.freqs._version):
-            aux = {"device": dev, "src": (self.emb_fourier.freqs.data_ptr(), self.emb_fourier.freqs._version)}
+        if aux is None or aux["device"] != dev or aux["src"] != (self.emb_fourier.freqs.data_ptr(), _ver(self.emb_fourier.freqs)):
+            aux = {"device": dev, "src": (self.emb_fourier.freqs.data_ptr(), _ver(self.emb_fourier.freqs))}
             for name, mod in (("emb", self.emb_fourier), ("logvar", self.logvar_fourier)):
                 aux[name + "_freqs"] = mod.freqs.detach().to(device=dev, dtype=torch.float32).contiguous()
                 aux[name + "_phases"] = mod.phases.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -353,22 +365,39 @@ class UNet(DualDiffusionUNet):
         aux = self._aux()
         g = cfg.mlp_groups
 
+        main = torch.cuda.current_stream(plan.device)
+        side = plan.side
+
+        def fork() -> None:
+            side.wait_stream(main)
+
+        def join() -> None:
+            main.wait_stream(side)
+
         emb = ops.noise_embedding(sigma, aux["emb_freqs"], aux["emb_phases"], self.emb_noise.weight.detach(), embeddings,
                                   cfg.label_balance, normalize=self.training)
         st = plan.affine_for(B)
         descs, max_o = plan.affine_descs(st)
-        ops.emb_affine(descs, len(st["entries"]), max_o, emb)
+        fork()
+        with torch.cuda.stream(side):
+            ops.emb_affine(descs, len(st["entries"]), max_o, emb)
         cvec = st["outs"]
 
         patches = ops.stem_patches(net_in, sigma, cfg.sigma_data, ln_freqs)
         x = ops.mpconv(patches, W["enc.conv_in"], 1)
+        join()
         skips = [x]
         ca_r, cb_r = _mp_sum_coeffs(cfg.res_balance)
         ca_a, cb_a = _mp_sum_coeffs(cfg.attn_balance)
 
         def attention_tail(p: str, blk: Block, x2: Tensor, xs: Tensor) -> Tensor:
+            # outputs of side-stream kernels are allocated on the main stream (allocator reuse stays ordered)
+            v = torch.empty_like(x2)
+            fork()
+            with torch.cuda.stream(side):
+                ops.mpconv(x2, W[p + ".attn_v"], 1, out=v)
             qk = ops.mpconv(xs, W[p + ".attn_qk"], 1)
-            v = ops.mpconv(x2, W[p + ".attn_v"], 1)
+            join()
             y = ops.attention(qk, v, cvec[p + ".c_v"], blk.num_heads, blk.channels_per_head)
             return ops.mpconv(y, W[p + ".attn_proj"], 1, epi=L.EPI_RESIDUAL, alpha=cb_a, beta=ca_a, clip=blk.clip_act,
                               residual=x2)
@@ -402,15 +431,21 @@ class UNet(DualDiffusionUNet):
             else:
                 xc = x
                 _, s = ops.cat_silu(x, None, 1.0, 0.0, False, need_cat=False)
+            # conv_skip(x) is independent of the residual branch: run it as a parallel graph branch and let
+            # conv_res1's epilogue do the mp_sum (unet_edm2_b4.py:129-131)
+            t0 = torch.empty(xc.shape[:3] + (blk.out_channels,), device=xc.device, dtype=torch.bfloat16)
+            fork()
+            with torch.cuda.stream(side):
+                ops.mpconv(xc, W[p + ".conv_skip"], 1, out=t0)
             y0 = ops.mpconv(s, W[p + ".conv_res0"], 3, g, epi=L.EPI_SCALE_SILU, scale=cvec[p + ".c"])
-            y1 = ops.mpconv(y0, W[p + ".conv_res1"], 3, g)
+            join()
             if blk.use_attention:
-                x2, xs = ops.mpconv(xc, W[p + ".conv_skip"], 1, epi=L.EPI_RESIDUAL, alpha=ca_r, beta=cb_r, residual=y1,
-                                    epi2=L.EPI2_SCALE, scale2=cvec[p + ".c_qk"])
+                x2, xs = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
+                                    residual=t0, epi2=L.EPI2_SCALE, scale2=cvec[p + ".c_qk"])
                 x = attention_tail(p, blk, x2, xs)
             else:
-                x = ops.mpconv(xc, W[p + ".conv_skip"], 1, epi=L.EPI_RESIDUAL, alpha=ca_r, beta=cb_r,
-                               clip=blk.clip_act, residual=y1)
+                x = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
+                               clip=blk.clip_act, residual=t0)
 
         return ops.conv_out(x, W["conv_out"], x_in, sigma, cfg.sigma_data, x_ref)
 

@@ -18,6 +18,7 @@ launch_count = 0   # number of C-ABI kernel launches issued (bench.py reports it
 
 
 trace = None       # set to a list to record (op, detail) per launch (profiling scripts only)
+timing = None      # set to a list to record (flops, start_event, end_event, detail) per MPConv launch (bench.py)
 
 
 def _count(n: int = 1, what: str = "", detail=None) -> None:
@@ -74,8 +75,15 @@ def mpconv(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1, *, epi: in
     if epi2 != L.EPI2_NONE and out2 is None:
         out2 = torch.empty((B, H, W, Cout), device=x.device, dtype=torch.bfloat16)
     e = L.ConvEpilogue(epi, epi2, alpha, beta, clip, L.ptr(scale), L.ptr(scale2), L.ptr(residual), L.ptr(out2))
+    if timing is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     L.check(L.load().dd_mpconv_forward(L.ptr(x), L.ptr(w_prepped), L.ptr(out), B, H, W, Cin, Cout, ksize, groups,
                                        C.byref(e), L.stream_ptr()))
+    if timing is not None:
+        ev1.record()
+        timing.append((2.0 * B * H * W * Cout * (Cin // groups) * ksize * ksize, ev0, ev1,
+                       (B, H, W, Cin, Cout, ksize, groups)))
     _count(1, "mpconv", (B, H, W, Cin, Cout, ksize, groups, epi, epi2))
     return (out, out2) if epi2 != L.EPI2_NONE else out
 

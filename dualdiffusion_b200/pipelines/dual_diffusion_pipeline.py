@@ -68,6 +68,48 @@ def step_scalars(i: int, sigma_curr: float, sigma_next: float, params: SamplePar
                 t_hat=float(t_hat), t=float(t), p=float(p), effective_input_perturbation=float(old_sigma_next - sigma_next))
 
 
+class EDMSamplerState:
+    """Device-resident state of one `diffusion_decode` run, advanced one sampler step at a time.  A step is the
+    body of the loop at pipeline.py:649-737: UNet (cond|uncond) -> CFG + Heun predictor -> UNet -> corrector,
+    final lerp and re-noise.  `sample2` holds the current sample twice ([cond ; uncond] halves of the UNet batch)."""
+
+    def __init__(self, unet, params: SampleParams, emb: torch.Tensor, sig: list, sample: torch.Tensor,
+                 input_ref: Optional[torch.Tensor], fmt, collect_debug_info: bool = False) -> None:
+        self.unet, self.params, self.emb, self.sig, self.fmt = unet, params, emb, sig, fmt
+        self.input_ref = input_ref
+        device = sample.device
+        B = params.batch_size
+        self.B = B
+        self.steps = [step_scalars(i, sig[i], sig[i + 1], params) for i in range(params.num_steps)]
+        # device table of the per-call sigma vectors: [step][0 = sigma_curr | 1 = sigma_hat][2B]
+        self.table = torch.tensor([[[sig[i]] * (2 * B), [st["t_hat"] * sig[i]] * (2 * B)]
+                                   for i, st in enumerate(self.steps)], dtype=torch.float32).to(device)
+        self.sample2 = torch.empty((2 * B,) + tuple(sample.shape[1:]), device=device, dtype=torch.float32)
+        self.sample2[:B] = sample
+        self.sample2[B:] = sample
+        self.xhat2 = torch.empty_like(self.sample2)
+        self.cfg1 = torch.empty_like(sample)
+        self.cfg_out = torch.empty_like(sample) if collect_debug_info else None
+
+    @property
+    def sample(self) -> torch.Tensor:
+        return self.sample2[:self.B]
+
+    def set_sample(self, sample: torch.Tensor) -> None:
+        """Overwrite the current sample (both UNet-batch halves), e.g. from a pinned host buffer."""
+        self.sample2[:self.B].copy_(sample, non_blocking=True)
+        self.sample2[self.B:].copy_(sample, non_blocking=True)
+
+    def step(self, i: int, noise: Optional[torch.Tensor]) -> None:
+        st, p = self.steps[i], self.params
+        d1 = self.unet(self.sample2, self.table[i, 0], self.fmt, self.emb, self.input_ref)
+        ops.sampler_cfg_lerp(d1, self.sample2, p.cfg_scale, st["t_hat"], self.cfg1,
+                             self.xhat2 if p.use_heun else None, dup=True)
+        d2 = self.unet(self.xhat2, self.table[i, 1], self.fmt, self.emb, self.input_ref) if p.use_heun else None
+        ops.sampler_update(self.cfg1, d2, p.cfg_scale, p.use_heun, st["t"], st["p"] if noise is not None else 0.0,
+                           noise, self.sample2, self.cfg_out, dup=True)
+
+
 class DualDiffusionPipeline(torch.nn.Module):
     """Minimal module container exposing the sampler.  Construct with the modules that a model directory's
     model_index.json would load (`unet`, optionally `format`, ...)."""
@@ -80,14 +122,10 @@ class DualDiffusionPipeline(torch.nn.Module):
         self.last_debug_info: dict = {}
 
     @torch.inference_mode()
-    def diffusion_decode(self, params: SampleParams, quiet: bool = False,
-                         audio_embedding: Optional[torch.Tensor] = None, sample_shape: Optional[torch.Size] = None,
-                         x_ref: Optional[torch.Tensor] = None, module=None,
-                         initial_noise: Optional[torch.Tensor] = None,
-                         step_noise: Optional[Any] = None) -> torch.Tensor:
-        """pipeline.py:589-752.  `initial_noise` / `step_noise` (callable i -> tensor) optionally inject the
-        noise draws so that parity tests can feed the oracle's values; by default they come from a device
-        `torch.Generator` seeded with params.seed exactly as in the reference (:605, :637, :736)."""
+    def prepare_sampler(self, params: SampleParams, audio_embedding: torch.Tensor, sample_shape=None,
+                        x_ref: Optional[torch.Tensor] = None, module=None,
+                        initial_noise: Optional[torch.Tensor] = None):
+        """Everything `diffusion_decode` does before its loop (pipeline.py:598-646).  Returns (state, generator)."""
         unet = module or getattr(self, "unet")
         params = SampleParams(**params.__dict__).sanitize()
         params.seed = params.seed or int(np.random.randint(100000, 999999))
@@ -96,16 +134,15 @@ class DualDiffusionPipeline(torch.nn.Module):
         params.sigma_data = params.sigma_data or unet.config.sigma_data
         if params.seamless_loop:
             raise NotImplementedError("seamless_loop sampling is not implemented on the B200 path")
+        if params.stereo_fix > 0:
+            raise NotImplementedError("stereo_fix is not implemented on the B200 path")
         if audio_embedding is None:
             raise NotImplementedError("unconditional (no class embedding) sampling is not implemented")
         if sample_shape is None and x_ref is None:
             raise ValueError("sample_shape or x_ref is required")
-
         device = torch.device(unet.device)
         B = params.batch_size
-        debug_info: dict = {}
         generator = torch.Generator(device=device).manual_seed(params.seed)
-
         conditioning_mask = torch.cat((torch.ones(B, dtype=torch.bool), torch.zeros(B, dtype=torch.bool)))
         emb = unet.get_embeddings(audio_embedding, conditioning_mask.to(device))
         input_ref = None
@@ -113,46 +150,42 @@ class DualDiffusionPipeline(torch.nn.Module):
             sample_shape = sample_shape or x_ref.shape
             input_ref = x_ref.to(device=device, dtype=torch.float32).repeat(2, 1, 1, 1)
         sample_shape = tuple(sample_shape)
-
         schedule = SamplingSchedule.get_schedule(params.schedule, params.num_steps, 1, device="cpu",
                                                  sigma_max=params.sigma_max, sigma_min=params.sigma_min, rho=params.rho)
         sig = schedule.tolist()
-        debug_info["sigma_schedule"] = sig
-        steps = [step_scalars(i, sig[i], sig[i + 1], params) for i in range(params.num_steps)]
-        # device table of the per-call sigma vectors: [step][0 = sigma_curr | 1 = sigma_hat][2B]
-        table = torch.tensor([[[sig[i]] * (2 * B), [st["t_hat"] * sig[i]] * (2 * B)] for i, st in enumerate(steps)],
-                             dtype=torch.float32).to(device)
-
         if initial_noise is None:
             noise = torch.randn(sample_shape, device=device, generator=generator)
-            if params.stereo_fix > 0:
-                raise NotImplementedError("stereo_fix is not implemented on the B200 path")
         else:
             noise = initial_noise.to(device=device, dtype=torch.float32)
-        n = noise.numel()
-        sample2 = torch.empty((2 * B,) + sample_shape[1:], device=device, dtype=torch.float32)
-        sample2[:B] = noise * (sig[0] ** 2 + params.sigma_data ** 2) ** 0.5
-        sample2[B:] = sample2[:B]
-        xhat2 = torch.empty_like(sample2)
-        cfg1 = torch.empty(sample_shape, device=device, dtype=torch.float32)
-        cfg_out = torch.empty(sample_shape, device=device, dtype=torch.float32) if self.collect_debug_info else None
-        fmt = getattr(self, "format", None)
+        sample = noise * (sig[0] ** 2 + params.sigma_data ** 2) ** 0.5
+        state = EDMSamplerState(unet, params, emb, sig, sample, input_ref, getattr(self, "format", None),
+                                self.collect_debug_info)
+        return state, generator
 
-        for i, st in enumerate(steps):
-            d1 = unet(sample2, table[i, 0], fmt, emb, input_ref)
-            ops.sampler_cfg_lerp(d1, sample2, params.cfg_scale, st["t_hat"], cfg1,
-                                 xhat2 if params.use_heun else None, dup=True)
-            d2 = unet(xhat2, table[i, 1], fmt, emb, input_ref) if params.use_heun else None
+    @torch.inference_mode()
+    def diffusion_decode(self, params: SampleParams, quiet: bool = False,
+                         audio_embedding: Optional[torch.Tensor] = None, sample_shape: Optional[torch.Size] = None,
+                         x_ref: Optional[torch.Tensor] = None, module=None,
+                         initial_noise: Optional[torch.Tensor] = None,
+                         step_noise: Optional[Any] = None) -> torch.Tensor:
+        """pipeline.py:589-752.  `initial_noise` / `step_noise` (callable i -> tensor) optionally inject the
+        noise draws so that parity tests can feed the oracle's values; by default they come from a device
+        `torch.Generator` seeded with params.seed exactly as in the reference (:605, :637, :736)."""
+        state, generator = self.prepare_sampler(params, audio_embedding, sample_shape, x_ref, module, initial_noise)
+        p = state.params
+        debug_info: dict = {"sigma_schedule": state.sig}
+        shape = tuple(state.sample.shape)
+        for i in range(p.num_steps):
             nz = None
-            if st["p"] > 0 or (i + 1) < params.num_steps:
-                nz = (step_noise(i).to(device=device, dtype=torch.float32) if step_noise is not None
-                      else torch.randn(sample_shape, generator=generator, device=device, dtype=torch.float32))
-            ops.sampler_update(cfg1, d2, params.cfg_scale, params.use_heun, st["t"], st["p"], nz, sample2, cfg_out,
-                               dup=True)
+            if (i + 1) < p.num_steps:
+                nz = (step_noise(i).to(device=state.sample2.device, dtype=torch.float32) if step_noise is not None
+                      else torch.randn(shape, generator=generator, device=state.sample2.device, dtype=torch.float32))
+            state.step(i, nz)
             if self.collect_debug_info:   # pipeline.py:740-744 (forces host syncs)
-                debug_info.setdefault("sample_std", []).append(sample2[:B].std().item())
-                debug_info.setdefault("cfg_output_mean", []).append(cfg_out.mean().item())
-                debug_info.setdefault("cfg_output_std", []).append(cfg_out.std().item())
-                debug_info.setdefault("effective_input_perturbation", []).append(st["effective_input_perturbation"])
+                debug_info.setdefault("sample_std", []).append(state.sample.std().item())
+                debug_info.setdefault("cfg_output_mean", []).append(state.cfg_out.mean().item())
+                debug_info.setdefault("cfg_output_std", []).append(state.cfg_out.std().item())
+                debug_info.setdefault("effective_input_perturbation", []).append(
+                    state.steps[i]["effective_input_perturbation"])
         self.last_debug_info = debug_info
-        return sample2[:B].clone()
+        return state.sample.clone()
