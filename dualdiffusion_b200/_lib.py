@@ -61,6 +61,13 @@ _SIGNATURES = {
                             c_int, c_int, c_void_p]),
     "dd_avgpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_stft_mel": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                            c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_int, c_void_p]),
+    "dd_fgla_istft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int,
+                              c_int, c_void_p, c_int, c_void_p]),
+    "dd_fgla_stft_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_void_p, c_float, c_int, c_void_p]),
+    "dd_ola_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
     "dd_sampler_update": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                   c_int, c_long, c_void_p]),

@@ -245,3 +245,41 @@ def mp_fourier(x: Tensor, freqs: Tensor, phases: Tensor) -> Tensor:
                                    L.stream_ptr()))
     _count()
     return out
+
+
+def stft_mel(raw: Tensor, window: Tensor, tw: Tensor, tw_half: Tensor, n_fft: int, hop: int, fb: dict,
+             exponent: float, mean: float, scale: float) -> Tensor:
+    """raw [S, L] fp32 -> [S, n_filters, 1 + L // hop] fp32 (mel-STFT encode)."""
+    S, Ln = raw.shape
+    T = 1 + Ln // hop
+    nf = fb["start"].numel()
+    out = torch.empty((S, nf, T), device=raw.device, dtype=torch.float32)
+    L.check(L.load().dd_stft_mel(L.ptr(raw), S, Ln, L.ptr(window), L.ptr(tw), L.ptr(tw_half), n_fft, hop,
+                                 L.ptr(fb["start"]), L.ptr(fb["count"]), L.ptr(fb["offset"]), L.ptr(fb["weight"]), nf,
+                                 exponent, mean, scale, L.ptr(out), T, L.stream_ptr()))
+    _count()
+    return out
+
+
+def fgla_istft(state: Optional[Tensor], mag_tk: Tensor, stereo: bool, interp_t: float, window: Tensor, tw: Tensor,
+               tw_half: Tensor, n_fft: int, hop: int, ola: Tensor) -> None:
+    S, T, _ = mag_tk.shape
+    L.check(L.load().dd_fgla_istft(L.ptr(state), L.ptr(mag_tk), S, T, int(stereo), interp_t, L.ptr(window), L.ptr(tw),
+                                   L.ptr(tw_half), n_fft, hop, L.ptr(ola), ola.shape[-1], L.stream_ptr()))
+    _count()
+
+
+def fgla_stft_update(ola: Tensor, env: Tensor, state: Tensor, momentum: float, first: bool, window: Tensor, tw: Tensor,
+                     tw_half: Tensor, n_fft: int, hop: int) -> None:
+    S, T, _ = state.shape[:3]
+    L.check(L.load().dd_fgla_stft_update(L.ptr(ola), L.ptr(env), S, T, hop * (T - 1), L.ptr(window), L.ptr(tw),
+                                         L.ptr(tw_half), n_fft, hop, L.ptr(state), momentum, int(first), L.stream_ptr()))
+    _count()
+
+
+def ola_finalize(ola: Tensor, env: Tensor, n_fft: int, length: int) -> Tensor:
+    S = ola.shape[0]
+    out = torch.empty((S, length), device=ola.device, dtype=torch.float32)
+    L.check(L.load().dd_ola_finalize(L.ptr(ola), L.ptr(env), S, ola.shape[-1], n_fft, length, L.ptr(out), L.stream_ptr()))
+    _count()
+    return out

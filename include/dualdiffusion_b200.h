@@ -155,6 +155,37 @@ DD_API int dd_axpby(const void* a, const void* b, float alpha, float beta, float
 DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, void* out, int B, int N, int heads,
                  int head_dim, void* stream);
 
+/* ---- mel-STFT encode / FGLA decode: modules/formats/old/spectrogram.py:176-238 ------------- */
+/* Shared conventions: n_fft = 2 * 2^a * 5^b (6400 and 4096 both qualify), win_length == n_fft, center=True with
+ * reflect padding, one-sided spectra of n_fft/2+1 bins.  `window` fp32 [n_fft]; `twiddles` = exp(-2 pi i m/(n_fft/2)),
+ * m < n_fft/2, and `twiddles_half` = exp(-2 pi i k/n_fft), k <= n_fft/2, as interleaved (re,im) fp32 pairs.
+ *
+ * dd_stft_mel: SpectrogramConverter.audio_to_spectrogram (:176-179) + FrequencyScale.scale
+ * (frequency_scale.py:127-128) + the affine of raw_to_sample (:223-226):
+ *   out[s][f][t] = ((sum_k |STFT(raw_s)[k][t]| * fb[k][f]) ** exponent - mean) * scale
+ * with the triangular filterbank given per filter f as a run of fb_count[f] weights starting at bin fb_start[f]
+ * (weights at fb_weight[fb_offset[f] ...]).  raw [S][len] fp32, out [S][n_filters][n_frames], n_frames = 1+len/hop. */
+DD_API int dd_stft_mel(const float* raw, int n_signals, int len, const float* window, const float* twiddles,
+                       const float* twiddles_half, int n_fft, int hop, const int* fb_start, const int* fb_count,
+                       const int* fb_offset, const float* fb_weight, int n_filters, float exponent, float mean,
+                       float scale, float* out, int n_frames, void* stream);
+/* griffinlim (old/phase_recovery.py:40-129), one iteration = dd_fgla_istft + dd_fgla_stft_update.
+ * State T [S][n_frames][bins] complex64 (frame-major, private layout); magnitudes mag_tk [S][n_frames][bins] fp32.
+ * dd_fgla_istft (:84-95, :121-124): X = T/(|T|+1e-16) * M with M = mag (stereo == 0) or the stereo-coherence blend
+ *   merged + max(interp_t,0)*(mag - merged), merged = (mag_s + mag_{s^1})/2; state == NULL means angles == 1 (:73).
+ *   Writes the windowed overlap-add of all inverse frames into ola [S][ola_len] (zeroed by the call),
+ *   ola_len = n_fft + hop*(n_frames-1); dividing by the window envelope and trimming n_fft/2 is left to the reader.
+ * dd_fgla_stft_update (:97-117): rebuilt = STFT(ola/env trimmed); T <- rebuilt - momentum*T (first != 0: T <- rebuilt).
+ * dd_ola_finalize: out[s][j] = ola[s][n_fft/2 + j] / env[n_fft/2 + j], j < len = hop*(n_frames-1).          */
+DD_API int dd_fgla_istft(const float* state, const float* mag_tk, int n_signals, int n_frames, int stereo,
+                         float interp_t, const float* window, const float* twiddles, const float* twiddles_half,
+                         int n_fft, int hop, float* ola, int ola_len, void* stream);
+DD_API int dd_fgla_stft_update(const float* ola, const float* env, int n_signals, int n_frames, int len,
+                               const float* window, const float* twiddles, const float* twiddles_half, int n_fft,
+                               int hop, float* state, float momentum, int first, void* stream);
+DD_API int dd_ola_finalize(const float* ola, const float* env, int n_signals, int ola_len, int n_fft, int len,
+                           float* out, void* stream);
+
 /* ---- EDM sampler step glue: pipelines/dual_diffusion_pipeline.py:699-737 -------------------- */
 /* n = element count of ONE latent batch (B*C*H*W); d_2b holds [cond ; uncond] = 2n elements.
  * cfg = lerp(D[B:], D[:B], cfg_scale); x_hat = lerp(cfg, sample, t_hat)   (:701, :712).

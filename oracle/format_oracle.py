@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the reference's mel-STFT encode and FGLA (fast Griffin-Lim)
+phase-reconstruction decode: `SpectrogramFormat.raw_to_sample / sample_to_raw`
+(src/modules/formats/old/spectrogram.py:176-238), `FrequencyScale` (src/modules/formats/frequency_scale.py:30-58,
+127-169) and `griffinlim` (src/modules/formats/old/phase_recovery.py:40-129).
+
+The reference delegates the transforms to torch / torchaudio (not vendored): torchaudio.transforms.Spectrogram ==
+torch.stft(center=True, pad_mode="reflect", window, onesided, normalized=False); torch.istft; torch.linalg.lstsq.
+This restatement calls torch.stft / torch.istft for those and writes everything else out explicitly, including the
+in-place aliasing of the momentum update (`tprev` holds the momentum-ADJUSTED spectrum).
+Pinned by tests/golden/format_small.pt (reference output, see tests/golden/make_golden.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class SpectrogramSpec:
+    """old/spectrogram.py:33-74 defaults."""
+    raw_to_sample_scale: float = 2.247
+    sample_mean: float = 1.295
+    abs_exponent: float = 0.25
+    sample_rate: int = 32000
+    step_size_ms: int = 8
+    window_duration_ms: int = 200
+    padded_duration_ms: int = 200
+    window_exponent: float = 32
+    window_periodic: bool = True
+    num_frequencies: int = 256
+    min_frequency: int = 20
+    max_frequency: int = 16000
+    num_fgla_iters: int = 200
+    fgla_momentum: float = 0.99
+    stereo_coherence: float = 0.67
+
+    @property
+    def n_fft(self) -> int:
+        return int(self.padded_duration_ms / 1000.0 * self.sample_rate)
+
+    @property
+    def win_length(self) -> int:
+        return int(self.window_duration_ms / 1000.0 * self.sample_rate)
+
+    @property
+    def hop_length(self) -> int:
+        return int(self.step_size_ms / 1000.0 * self.sample_rate)
+
+    @property
+    def num_stft_bins(self) -> int:
+        return self.n_fft // 2 + 1
+
+
+def window(spec: SpectrogramSpec) -> Tensor:
+    """old/spectrogram.py:99-105 — hann(periodic) ** exponent, fp32."""
+    return torch.hann_window(spec.win_length, periodic=spec.window_periodic) ** spec.window_exponent
+
+
+def mel_filterbank(spec: SpectrogramSpec) -> Tensor:
+    """frequency_scale.py:30-34,45-58,144-169 — HTK mel points, triangular filters, no area norm -> (bins, filters)."""
+    lo = 2595.0 * math.log10(1.0 + spec.min_frequency / 700.0)
+    hi = 2595.0 * math.log10(1.0 + spec.max_frequency / 700.0)
+    f_pts = 700.0 * (10.0 ** (torch.linspace(lo, hi, spec.num_frequencies + 2) / 2595.0) - 1.0)
+    all_freqs = torch.linspace(0, spec.sample_rate / 2, spec.num_stft_bins)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+def stft(x: Tensor, spec: SpectrogramSpec) -> Tensor:
+    shape = x.shape
+    y = torch.stft(x.reshape(-1, shape[-1]), n_fft=spec.n_fft, hop_length=spec.hop_length, win_length=spec.win_length,
+                   window=window(spec), center=True, pad_mode="reflect", normalized=False, onesided=True,
+                   return_complex=True)
+    return y.reshape(shape[:-1] + y.shape[-2:])
+
+
+def raw_to_sample(raw: Tensor, spec: SpectrogramSpec) -> Tensor:
+    """old/spectrogram.py:176-179, 218-226: |STFT| -> mel -> ** 0.25 -> (x - mean) * scale."""
+    mag = stft(raw.float(), spec).abs()
+    mel = torch.matmul(mag.transpose(-1, -2), mel_filterbank(spec)).transpose(-1, -2)      # frequency_scale.py:127-128
+    return (mel ** spec.abs_exponent - spec.sample_mean) * spec.raw_to_sample_scale
+
+
+def unscale(mel_lin: Tensor, spec: SpectrogramSpec) -> Tensor:
+    """frequency_scale.py:130-142 — min-norm least-squares inverse of the filterbank (lstsq gels) + relu."""
+    shape = mel_lin.shape
+    s = mel_lin.reshape(-1, shape[-2], shape[-1])
+    sol = torch.linalg.lstsq(mel_filterbank(spec).transpose(-1, -2)[None], s, driver="gels").solution
+    return torch.relu(sol).view(shape[:-2] + (spec.num_stft_bins, shape[-1]))
+
+
+def griffinlim_step(tprev: Tensor, specgram: Tensor, merged: Optional[Tensor], spec: SpectrogramSpec, i: int,
+                    n_iter: int) -> Tensor:
+    """One iteration of the loop at phase_recovery.py:78-119, as a map on the momentum-adjusted spectrum
+    T_i -> T_{i+1} (`tprev`; None before the first iteration, where angles == 1):
+        A = T/(|T|+1e-16);  rebuilt = STFT(ISTFT(A * M_i));  T' = rebuilt - m/(1+m) * T.
+    `angles.sub_(tprev, alpha=momentum)` (:113) acts in place on `rebuilt`, so the `tprev = rebuilt` of :117 stores
+    the momentum-ADJUSTED spectrum."""
+    momentum = spec.fgla_momentum / (1 + spec.fgla_momentum)                                # :58
+    kw = dict(n_fft=spec.n_fft, hop_length=spec.hop_length, win_length=spec.win_length, window=window(spec))
+    if merged is not None:
+        t = i / n_iter - spec.stereo_coherence                                              # :84-88
+        interp = torch.lerp(merged, specgram, t) if t > 0 else merged
+    else:
+        interp = specgram
+    if tprev is None:
+        angles = torch.full((1,) + tuple(specgram.shape[1:]), 1, dtype=torch.cfloat)        # :73
+    else:
+        angles = tprev / (tprev.abs() + 1e-16)                                              # :115
+    inverse = torch.istft(angles * interp, length=None, **kw)                               # :92-95
+    rebuilt = torch.stft(inverse, center=True, pad_mode="reflect", normalized=False, onesided=True,
+                         return_complex=True, **kw)                                         # :97-108
+    return rebuilt if tprev is None else rebuilt - momentum * tprev                         # :110-113 (tprev_0 == 0)
+
+
+def griffinlim(specgram: Tensor, spec: SpectrogramSpec, n_iter: int, stereo: bool = True) -> Tensor:
+    """phase_recovery.py:40-129 with rand_init=False, length=None."""
+    shape = specgram.shape
+    specgram = specgram.reshape([-1] + list(shape[-2:]))
+    merged = ((specgram[0::2] + specgram[1::2]) / 2).repeat_interleave(2, dim=0) if stereo else None   # :63-64
+    tprev = None
+    for i in range(n_iter):
+        tprev = griffinlim_step(tprev, specgram, merged, spec, i, n_iter)
+    angles = tprev / (tprev.abs() + 1e-16)
+    kw = dict(n_fft=spec.n_fft, hop_length=spec.hop_length, win_length=spec.win_length, window=window(spec))
+    wave = torch.istft(angles * specgram, length=None, **kw)                                # :121-124
+    return wave.reshape(shape[:-2] + wave.shape[-1:])
+
+
+def sample_to_raw(samples: Tensor, spec: SpectrogramSpec, n_fgla_iters: Optional[int] = None) -> Tensor:
+    """old/spectrogram.py:229-238, :181-185."""
+    s = (samples / spec.raw_to_sample_scale + spec.sample_mean).clip(min=0)
+    amplitudes = unscale(s ** (1 / spec.abs_exponent), spec)
+    return griffinlim(amplitudes, spec, n_fgla_iters or spec.num_fgla_iters, stereo=True)

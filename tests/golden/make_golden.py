@@ -74,6 +74,23 @@ def main():
         print("sampler", name, out.std().item())
     torch.save(dict(clap=clap, cases=cases, weight_checksum=weight_checksum(sd)), os.path.join(OUT, "sampler_small.pt"))
 
+    # ---- mel-STFT encode + FGLA decode (old SpectrogramFormat; two config attributes the current base
+    #      config no longer defines are restored) ----
+    from modules.formats.old.spectrogram import SpectrogramFormat, SpectrogramFormatConfig
+    SpectrogramFormatConfig.sample_raw_channels = 2
+    SpectrogramFormatConfig.sample_raw_length = 1440000
+    sfmt = SpectrogramFormat(SpectrogramFormatConfig())
+    g = torch.Generator().manual_seed(3)
+    raw = 0.1 * torch.randn(2, 2, 256 * 95, generator=g)              # 96 frames
+    t = torch.arange(raw.shape[-1]) / 32000.0
+    raw[0, 0] += 0.3 * torch.sin(2 * torch.pi * 440.0 * t)            # a tonal component in one channel
+    raw[0, 1] += 0.2 * torch.sin(2 * torch.pi * 1320.0 * t + 0.5)
+    mel = sfmt.raw_to_sample(raw)
+    decoded = {n: sfmt.sample_to_raw(mel, n_fgla_iters=n, quiet=True) for n in (1, 2, 5, 12)}
+    torch.save(dict(raw=raw, mel=mel, decoded=decoded, shape_1408768=sfmt.get_sample_shape(1, 1408768),
+                    crop_1440000=sfmt.sample_raw_crop_width(1440000)), os.path.join(OUT, "format_small.pt"))
+    print("format", mel.shape, {k: float(v.std()) for k, v in decoded.items()})
+
     # ---- sigma schedules ----
     sched = {n: SamplingSchedule.get_schedule(n, 10, 1.0, sigma_max=200.0, sigma_min=0.03, rho=7.0)
              for n in ("edm2", "ln_linear", "linear", "cos", "scale_invariant")}

@@ -415,3 +415,102 @@ def test_operator_mirror_vs_oracle(dev):
     assert rel_err(conv.weight, uo.normalize(conv.weight.detach().cpu())) < 1e-4
     with pytest.raises(RuntimeError):
         conv.cpu()(x)       # no CPU path
+
+
+# ------------------------------------------------------------------------------------------
+# mel-STFT encode / FGLA decode
+# ------------------------------------------------------------------------------------------
+FP32_SPECTRAL = 1e-3      # north_star: <= 1e-3 relative for fp32 paths (measured ~1e-6 .. 1e-5)
+
+
+def test_stft_mel_vs_golden_reference(dev):
+    from dualdiffusion_b200.modules.formats.spectrogram import SpectrogramFormat, SpectrogramFormatConfig
+    g = load_golden("format_small.pt")
+    fmt = SpectrogramFormat(SpectrogramFormatConfig())
+    mel = fmt.raw_to_sample(g["raw"].to(dev))
+    assert mel.shape == g["mel"].shape and mel.dtype == torch.float32
+    assert rel_err(mel, g["mel"]) < FP32_SPECTRAL
+    assert (mel.cpu() - g["mel"]).abs().max() < 1e-3 * g["mel"].abs().max()
+
+
+def test_stft_mel_edge_cases_vs_oracle(dev):
+    """Shortest legal signal (one hop more than the reflect padding), silence, and a ragged frame block."""
+    from dualdiffusion_b200.modules.formats.spectrogram import SpectrogramFormat, SpectrogramFormatConfig
+    from oracle import format_oracle as fo
+    fmt = SpectrogramFormat(SpectrogramFormatConfig())
+    spec = fo.SpectrogramSpec()
+    gen = torch.Generator().manual_seed(41)
+    for frames in (14, 33, 70):
+        raw = 0.1 * torch.randn(1, 2, 256 * (frames - 1), generator=gen)
+        assert rel_err(fmt.raw_to_sample(raw.to(dev)), fo.raw_to_sample(raw, spec)) < FP32_SPECTRAL
+    silent = torch.zeros(1, 2, 256 * 15)
+    got = fmt.raw_to_sample(silent.to(dev))
+    assert torch.allclose(got.cpu(), fo.raw_to_sample(silent, spec))
+
+
+def test_fgla_single_iteration_vs_oracle(dev):
+    """One Griffin-Lim iteration T_i -> T_{i+1} from an identical starting state (old/phase_recovery.py:78-119):
+    inverse STFT + overlap-add, forward STFT, in-place momentum update, stereo-coherence blend.  Tight tolerance:
+    this is the unit the whole decode is a 200-fold composition of."""
+    from dualdiffusion_b200 import ops
+    from dualdiffusion_b200.modules.formats.spectrogram import SpectrogramFormat, SpectrogramFormatConfig
+    from oracle import format_oracle as fo
+    spec = fo.SpectrogramSpec()
+    fmt = SpectrogramFormat(SpectrogramFormatConfig())
+    c = fmt.config
+    t = fmt._tables(dev)
+    gen = torch.Generator().manual_seed(43)
+    S, T, K = 4, 45, spec.num_stft_bins
+    mag = torch.rand(S, K, T, generator=gen) * torch.linspace(1.0, 0.01, K).view(1, K, 1)       # [S][K][T] (reference layout)
+    merged = ((mag[0::2] + mag[1::2]) / 2).repeat_interleave(2, dim=0)
+    tprev = torch.complex(torch.randn(S, K, T, generator=gen), torch.randn(S, K, T, generator=gen))
+    n_fft, hop = c.padded_length, c.hop_length
+    args = (t["window"], t["tw"], t["tw_half"], n_fft, hop)
+    env = fmt._envelope(t, T, dev)
+    mag_tk = mag.transpose(1, 2).contiguous().to(dev)
+    momentum = c.fgla_momentum / (1 + c.fgla_momentum)
+    for i, n_iter, use_state in ((0, 10, False), (3, 10, True), (9, 10, True)):      # i/n - 0.67: merged only / blended
+        ref = fo.griffinlim_step(tprev if use_state else None, mag, merged, spec, i, n_iter)
+        state = torch.view_as_real(tprev.transpose(1, 2).contiguous()).contiguous().to(dev)
+        ola = torch.empty((S, n_fft + hop * (T - 1)), device=dev)
+        ops.fgla_istft(state if use_state else None, mag_tk, True, i / n_iter - c.stereo_coherence, *args, ola)
+        ops.fgla_stft_update(ola, env, state, momentum, not use_state, *args)
+        got = torch.view_as_complex(state).transpose(1, 2).cpu()
+        assert rel_err(torch.view_as_real(got), torch.view_as_real(ref)) < 1e-4, i
+    # final synthesis (:121-124): un-blended magnitudes
+    kw = dict(n_fft=n_fft, hop_length=hop, win_length=n_fft, window=fo.window(spec))
+    ref = torch.istft(tprev / (tprev.abs() + 1e-16) * mag, length=None, **kw)
+    state = torch.view_as_real(tprev.transpose(1, 2).contiguous()).contiguous().to(dev)
+    ola = torch.empty((S, n_fft + hop * (T - 1)), device=dev)
+    ops.fgla_istft(state, mag_tk, False, 0.0, *args, ola)
+    assert rel_err(ops.ola_finalize(ola, env, n_fft, hop * (T - 1)), ref) < 1e-4
+
+
+def test_fgla_vs_golden_reference(dev):
+    """Whole decode against the reference's output.  Griffin-Lim is a chaotic iteration (phases of near-zero bins are
+    ill-conditioned): fp32 round-off differences between FFT implementations (1e-7) grow to the
+    1e-2 level within a few iterations, so the end-to-end check is energy-relative and loose; the tight check is
+    test_fgla_single_iteration_vs_oracle."""
+    from dualdiffusion_b200.modules.formats.spectrogram import SpectrogramFormat, SpectrogramFormatConfig
+    g = load_golden("format_small.pt")
+    fmt = SpectrogramFormat(SpectrogramFormatConfig())
+    for n, ref in g["decoded"].items():
+        out = fmt.sample_to_raw(g["mel"].to(dev), n_fgla_iters=n)
+        assert out.shape == ref.shape and out.dtype == torch.float32
+        assert rel_err(out, ref) < (5e-2 if n <= 2 else 2.5e-1), (n, rel_err(out, ref))
+        assert abs(float(out.std()) / float(ref.std()) - 1.0) < 5e-2
+
+
+def test_fgla_round_trip_property(dev):
+    """Size-independent property: re-encoding the FGLA output reproduces the mel spectrogram it was decoded from
+    better with more iterations (spectral convergence), and 1 iteration equals plain zero-phase ISTFT -> STFT."""
+    from dualdiffusion_b200.modules.formats.spectrogram import SpectrogramFormat, SpectrogramFormatConfig
+    g = load_golden("format_small.pt")
+    fmt = SpectrogramFormat(SpectrogramFormatConfig())
+    mel = g["mel"].to(dev)
+    errs = []
+    for n in (2, 30):
+        wave = fmt.sample_to_raw(mel, n_fgla_iters=n)
+        lin = lambda m: (m / fmt.config.raw_to_sample_scale + fmt.config.sample_mean).clip(min=0) ** 4
+        errs.append(rel_err(lin(fmt.raw_to_sample(wave))[..., 16:-16], lin(mel)[..., 16:-16]))
+    assert errs[1] < errs[0]

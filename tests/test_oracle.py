@@ -94,3 +94,28 @@ def test_unet_oracle_vs_live_reference(small):
         ref = net(x, sigma, fmt, emb)
     got = uo.unet_forward(sd, spec, x, sigma, uo.get_embeddings(sd, clap, torch.tensor([True])))
     assert rel_err(got, ref) < 1e-5
+
+
+def test_format_oracle_vs_golden():
+    """mel-STFT encode + FGLA decode restatement against the reference's own output (bit-exact: both delegate the
+    transforms to torch.stft / istft / lstsq; everything else must match exactly, incl. the momentum aliasing)."""
+    from oracle import format_oracle as fo
+    g = load_golden("format_small.pt")
+    spec = fo.SpectrogramSpec()
+    mel = fo.raw_to_sample(g["raw"], spec)
+    assert rel_err(mel, g["mel"]) < 1e-6
+    for n, ref in g["decoded"].items():
+        out = fo.sample_to_raw(g["mel"], spec, n)
+        assert out.shape == g["raw"].shape
+        assert rel_err(out, ref) < 1e-5, n
+
+
+def test_format_host_logic_vs_golden():
+    """Shape bookkeeping of the drop-in format (no GPU needed)."""
+    from dualdiffusion_b200.modules.formats.spectrogram import SpectrogramFormat, SpectrogramFormatConfig, mel_filterbank
+    from oracle import format_oracle as fo
+    g = load_golden("format_small.pt")
+    fmt = SpectrogramFormat(SpectrogramFormatConfig())
+    assert tuple(fmt.get_sample_shape(1, 1408768)) == tuple(g["shape_1408768"])
+    assert fmt.sample_raw_crop_width(1440000) == g["crop_1440000"]
+    assert torch.equal(mel_filterbank(fmt.config), fo.mel_filterbank(fo.SpectrogramSpec()))
