@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(kAttThreads)
 attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                  const float* __restrict__ scale_v, __nv_bfloat16* __restrict__ out, int N, int heads, int npad) {
     extern __shared__ __align__(16) uint8_t smem_att[];
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     const int C = heads * kD;
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);            // [npad][kKStride]
     __nv_bfloat16* Vs = Ks + (size_t)npad * kKStride;                          // [npad][kKStride]
@@ -210,9 +212,8 @@ extern "C" int dd_attention(const void* qk, const void* v, const float* scale_v,
         smem_set = smem;
     }
     const dim3 grid(ceil_div(N, kQTile), heads, B);
-    attention_kernel<<<grid, kAttThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
-                                                  static_cast<const __nv_bfloat16*>(v), scale_v,
-                                                  static_cast<__nv_bfloat16*>(out), N, heads, npad);
-    DD_CHECK_LAUNCH();
+    DD_CHECK_CUDA(dd_launch_pdl(attention_kernel, grid, dim3(kAttThreads), smem, stream,
+                                static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v), scale_v,
+                                static_cast<__nv_bfloat16*>(out), N, heads, npad));
     return 0;
 }

@@ -37,6 +37,24 @@ void dd_set_error(const char* fmt, ...);
 
 int dd_num_sms();
 
+// Launch `kernel` with programmatic stream serialization (PDL).  The kernel must call
+// ptx::grid_dependency_wait() before its first access to memory written by earlier kernels.
+template <typename... KArgs, typename... Args>
+inline cudaError_t dd_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------
 // small math helpers
 // ---------------------------------------------------------------------------------
@@ -145,6 +163,12 @@ __device__ __forceinline__ void tcgen05_fence_before() {
 __device__ __forceinline__ void tcgen05_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+
+// ---- programmatic dependent launch (no-ops unless the kernel was launched with the PDL attribute) ----
+// wait: block until every prerequisite grid has completed and its memory is visible.
+// launch_dependents: allow the next kernel in the stream to begin launching (its pre-wait prologue overlaps us).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- TMA ----
 __device__ __forceinline__ void prefetch_tensormap(const void* tmap) {

@@ -52,6 +52,7 @@ struct ConvParams {
     int ks_last;                    // 16-channel MMA steps in the last 64-channel chunk
     int a_stages;
     uint32_t b_block_bytes;         // n_tile * 128
+    uint32_t halo_bytes, halo_stride;   // landed bytes / stage stride of one halo tile
     // epilogue
     int epi;                        // DD_EPI_*
     int epi2;                       // DD_EPI2_*
@@ -243,19 +244,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    ptx::grid_launch_dependents();      // PDL: the next kernel may start its own prologue / weight prefetch now
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
+        // Weights never depend on the preceding kernel: the B boxes of the first pipeline fill are issued before
+        // griddepcontrol.wait, so under programmatic dependent launch they stream in while the previous kernel
+        // drains; activations (A boxes) are only touched after the wait.
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            bool waited = false;
+            int prefetched = 0;                          // stages of the first tile whose B boxes are already in flight
+            {
+                const int tile = blockIdx.x;
+                if (tile < p.num_tiles) {
+                    const TileCoord t = decode_tile(p, tile);
+                    const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
+                    for (int it0 = 0; it0 < p.k_iters && prefetched < p.stages; it0 += p.sub, ++prefetched) {
+                        const int cnt = min(p.sub, p.k_iters - it0);
+                        ptx::mbar_arrive_expect_tx(&full_bar[prefetched], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                        for (int j = 0; j < cnt; ++j) {
+                            const int it = it0 + j;
+                            const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                            ptx::tma_load_2d(smem + prefetched * stage_bytes + j * pair_bytes + kABufBytes, &tmB,
+                                             &full_bar[prefetched], tap * p.cin_g + kc * KC, b_row);
+                        }
+                    }
+                }
+            }
+            ptx::grid_dependency_wait();
+            waited = true;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord t = decode_tile(p, tile);
                 const int a_c0 = t.g * p.cin_g;
                 const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
                 for (int it0 = 0; it0 < p.k_iters; it0 += p.sub) {
                     const int cnt = min(p.sub, p.k_iters - it0);
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                    const bool b_done = prefetched > 0;              // this stage's barrier is armed, B already issued
+                    if (!b_done) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                    } else {
+                        --prefetched;
+                    }
                     for (int j = 0; j < cnt; ++j) {
                         const int it = it0 + j;
                         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
@@ -264,11 +295,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         uint8_t* a_dst = smem + stage * stage_bytes + j * pair_bytes;
                         uint8_t* b_dst = a_dst + kABufBytes;
                         ptx::tma_load_4d(a_dst, &tmA, &full_bar[stage], a_c0 + kc * KC, t.w0 + dx, t.h0 + dy, t.b0);
-                        ptx::tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.cin_g + kc * KC, b_row);
+                        if (!b_done) ptx::tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.cin_g + kc * KC, b_row);
                     }
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
+            (void)waited;
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
@@ -312,6 +344,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else {
         // ------------------------------ epilogue ------------------------------
+        ptx::grid_dependency_wait();                // epilogue reads (residual, scales) / writes depend on prior kernels
         const int ew = warp - 2;                    // 0..EW-1
         const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
         const int chunk0 = ew >> 2;                 // EW == 8: this warp takes chunks chunk0, chunk0+2, ...
@@ -353,16 +386,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // 3x3 convolution, halo variant (image rows >= 16): the 9 filter taps are shifted *views* of one
 // shared-memory halo tile instead of 9 separate TMA boxes, and the weight panel stays resident.
 //
-// M tile = 8 x 16 output pixels of one image.  Per 64-channel chunk one TMA box of (8+2) x (16+2) pixels
-// x 64 channels (23 KB, 128B-swizzled rows, pixel-major with a pitch of 10 rows per image row) is loaded.
-// For tap (dy,dx) the A operand of UMMA is that same tile read from row dy*10+dx with a stride of 10 rows
+// M tile = 16 groups of 8 consecutive pixels: 8 x 16 pixels of one image, or (images of 8..15 rows) 8 x 8
+// pixels of two batch items with the image rows of the two items interleaved.  Per 64-channel chunk one TMA
+// box of (8+2) x bt x (ht+2) pixels x 64 channels (23-26 KB, 128B-swizzled rows, smem order w, b, h) is loaded.
+// For tap (dy,dx) the A operand of UMMA is that same tile read from row dy*bt*10+dx with a stride of 10 rows
 // between 8-row groups -- operand traffic from L2 drops ~6x versus re-loading a box per tap.  The B operand
 // (9 taps x all chunks x n_tile output channels of one group) is loaded once per weight panel; every CTA walks
 // a contiguous range of (panel, m-tile) pairs so that it reloads weights at most once or twice per launch.
 // ---------------------------------------------------------------------------------
-constexpr int kHaloW = 8, kHaloH = 16, kHaloPitch = kHaloW + 2;
-constexpr uint32_t kHaloBytes = (kHaloH + 2) * kHaloPitch * 128;          // 23040 landed bytes
-constexpr uint32_t kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;       // stage stride (23552)
+constexpr int kHaloW = 8, kHaloPitch = kHaloW + 2;
 constexpr int kMaxAStages = 6;
 
 struct HaloTile {
@@ -376,8 +408,8 @@ __device__ __forceinline__ HaloTile decode_halo_tile(const ConvParams& p, int ti
     t.g = t.panel / p.n_tiles_per_group;
     t.n_idx = t.panel - t.g * p.n_tiles_per_group;
     t.w0 = (m % p.tiles_w) * kHaloW;
-    t.h0 = ((m / p.tiles_w) % p.tiles_h) * kHaloH;
-    t.b = m / (p.tiles_w * p.tiles_h);
+    t.h0 = ((m / p.tiles_w) % p.tiles_h) * p.ht;
+    t.b = (m / (p.tiles_w * p.tiles_h)) * p.bt;
     return t;
 }
 
@@ -385,10 +417,10 @@ __device__ __forceinline__ HaloTile decode_halo_tile(const ConvParams& p, int ti
 // a tap is a (dy*pitch + dx)-row shift of the halo tile (8 units per 128 B row), a k-step is +2 units.
 template <int NKS>
 __device__ __forceinline__ void halo_issue_taps(uint64_t a_desc0, uint64_t b_desc0, uint32_t b_block16, uint32_t d_tmem,
-                                                uint32_t idesc, uint32_t accumulate) {
+                                                uint32_t idesc, uint32_t accumulate, int row_pitch) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-        const uint64_t a_tap = a_desc0 + (uint64_t)(((tap / 3) * kHaloPitch + (tap % 3)) * 8);
+        const uint64_t a_tap = a_desc0 + (uint64_t)(((tap / 3) * row_pitch + (tap % 3)) * 8);
         const uint64_t b_tap = b_desc0 + (uint64_t)tap * b_block16;
 #pragma unroll
         for (int ks = 0; ks < NKS; ++ks) {
@@ -442,12 +474,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    ptx::grid_launch_dependents();      // PDL: the next kernel may start its own prologue / weight prefetch now
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, b_par = 0;
             int cur_panel = -1;
+            bool waited = false;
             for (int tile = t_begin; tile < t_end; ++tile) {
                 const HaloTile t = decode_halo_tile(p, tile);
                 if (t.panel != cur_panel) {
@@ -460,11 +494,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                              tap * p.cin_g + kc * 64, b_row);
                     cur_panel = t.panel;
                 }
+                // the weight panel does not depend on the previous kernel; activations do (PDL)
+                if (!waited) { ptx::grid_dependency_wait(); waited = true; }
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&a_empty[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&a_full[stage], kHaloBytes);
-                    ptx::tma_load_4d(a_smem + (size_t)stage * kHaloStride, &tmA, &a_full[stage], t.g * p.cin_g + kc * 64,
-                                     t.w0 - 1, t.h0 - 1, t.b);
+                    ptx::mbar_arrive_expect_tx(&a_full[stage], p.halo_bytes);
+                    ptx::tma_load_4d(a_smem + (size_t)stage * p.halo_stride, &tmA, &a_full[stage], t.g * p.cin_g + kc * 64,
+                                     t.w0 - 1, t.b, t.h0 - 1);      // tensor-map dims are (C, W, B, H)
                     if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -475,6 +511,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t idesc = ptx::make_idesc_bf16(kTileM, p.n_tile);
             const uint32_t b_base = ptx::smem_u32(b_smem), a_base = ptx::smem_u32(a_smem);
             const uint32_t b_block16 = p.b_block_bytes >> 4;
+            const int row_pitch = kHaloPitch * p.bt;     // smem rows between consecutive image rows of one item
             uint32_t stage = 0, phase = 0, b_par = 0, local = 0;
             int cur_panel = -1;
             for (int tile = t_begin; tile < t_end; ++tile, ++local) {
@@ -494,13 +531,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     ptx::mbar_wait(&a_full[stage], phase);
                     ptx::tcgen05_fence_after();
                     if (ptx::elect_one()) {
-                        const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + stage * kHaloStride, kHaloPitch * 128);
+                        const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + stage * p.halo_stride, kHaloPitch * 128);
                         const uint64_t b_desc0 = ptx::make_kmajor_desc_sw128(b_base + (uint32_t)(kc * 9) * p.b_block_bytes, 1024);
                         const int nks = (kc == p.kchunks - 1) ? p.ks_last : 4;
-                        if (nks == 4) halo_issue_taps<4>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
-                        else if (nks == 2) halo_issue_taps<2>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
-                        else if (nks == 1) halo_issue_taps<1>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
-                        else halo_issue_taps<3>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate);
+                        if (nks == 4) halo_issue_taps<4>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
+                        else if (nks == 2) halo_issue_taps<2>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
+                        else if (nks == 1) halo_issue_taps<1>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
+                        else halo_issue_taps<3>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
                         ptx::umma_commit(&a_empty[stage]);
                     }
                     __syncwarp();
@@ -517,23 +554,25 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ------------------------------ epilogue ------------------------------
+        ptx::grid_dependency_wait();
         const int ew = warp - 2;
         const int quad = warp & 3;
         const int chunk0 = ew >> 2;
         const int row = quad * 32 + lane;
-        const int hh = row >> 3, ww = row & 7;
+        const int grp = row >> 3, ww = row & 7;       // group index = h * bt + b
+        const int hh = grp / p.bt, bb = grp - hh * p.bt;
         uint32_t local = 0;
         for (int tile = t_begin; tile < t_end; ++tile, ++local) {
             const HaloTile t = decode_halo_tile(p, tile);
             const uint32_t acc = local & 1;
             const uint32_t acc_phase = (local >> 1) & 1;
-            const int h = t.h0 + hh, w = t.w0 + ww;
-            const bool valid = (h < p.H) && (w < p.W);
+            const int h = t.h0 + hh, w = t.w0 + ww, b = t.b + bb;
+            const bool valid = (hh < p.ht) && (h < p.H) && (w < p.W) && (b < p.B);
             const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)p.n_tile;
-            epilogue_tile<EW>(p, taddr, chunk0, valid, t.b, h, w, ch0);
+            epilogue_tile<EW>(p, taddr, chunk0, valid, b, h, w, ch0);
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -566,6 +605,25 @@ PFN_encodeTiled get_encode_fn() {
         }
     }
     return fn;
+}
+
+// Launch with programmatic stream serialization (PDL): the kernel may begin before its stream predecessor has
+// finished; everything that depends on the predecessor sits behind griddepcontrol.wait inside the kernels.
+template <typename Kernel>
+cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t stream, const CUtensorMap& tmA,
+                       const CUtensorMap& tmB, const ConvParams& p) {
+    static const bool no_pdl = getenv("DD_DISABLE_PDL") != nullptr;      // tuning experiments only
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p);
 }
 
 // Pick the pixel box of an M tile: wt*ht*bt <= 128, minimising the number of tiles.
@@ -676,7 +734,7 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
             attr_done = true;                                                                                      \
         }                                                                                                          \
-        conv_igemm_kernel<KC_, EW_><<<grid, 64 + 32 * EW_, smem_bytes, stream>>>(tmA, tmB, p);                     \
+        DD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<KC_, EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p)); \
     } while (0)
     if (KC == 64) { if (ew == 8) DD_LAUNCH_IGEMM(64, 8); else DD_LAUNCH_IGEMM(64, 4); }
     else          { if (ew == 8) DD_LAUNCH_IGEMM(32, 8); else DD_LAUNCH_IGEMM(32, 4); }
@@ -686,16 +744,23 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
 }
 
 
-// 3x3 halo variant: used when the image is at least 16 rows tall (levels 0-1 of the 45 s latent).
+// 3x3 halo variant: used when the image is at least 8 rows tall (levels 0-2 of the 45 s latent).
 int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode_fn();
     DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");
     const int B = p.B, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout;
     const int cin_g = Cin / groups, cout_g = Cout / groups;
     p.cin_g = cin_g; p.cout_g = cout_g;
-    p.wt = kHaloW; p.ht = kHaloH; p.bt = 1;
-    p.tiles_w = ceil_div(W, kHaloW); p.tiles_h = ceil_div(H, kHaloH); p.tiles_b = B;
-    p.m_tiles = p.tiles_w * p.tiles_h * B;
+    p.wt = kHaloW;
+    p.ht = H >= 16 ? 16 : 8;                       // 16 groups of 8 pixels: 16 rows x 1 item, or 8 rows x 2 items
+    p.bt = std::min(B, 16 / p.ht);
+    p.tiles_w = ceil_div(W, kHaloW); p.tiles_h = ceil_div(H, p.ht); p.tiles_b = ceil_div(B, p.bt);
+    p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    p.halo_bytes = (uint32_t)((p.ht + 2) * p.bt * kHaloPitch) * 128u;
+    // a UMMA always reads 16 groups x 10-row pitch (+ the largest tap shift) from the stage, whether or not the
+    // tile has 16 valid groups: size the stage for that so reads never leave the allocation
+    const uint32_t read_span = (uint32_t)(15 * kHaloPitch + 2 * kHaloPitch * p.bt + 2 + 8) * 128u;
+    p.halo_stride = (std::max(p.halo_bytes, read_span) + 1023u) / 1024u * 1024u;
     p.kchunks = ceil_div(cin_g, 64);
     p.ks_last = (cin_g - 64 * (p.kchunks - 1)) / 16;
     p.k_iters = p.kchunks;
@@ -703,7 +768,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     int n_tile = 0;
     for (int n = 16; n <= std::min(cout_g, 256); n += 16) {
         if (cout_g % n) continue;
-        if ((uint32_t)p.kchunks * 9u * n * 128u + 2u * kHaloStride <= budget) n_tile = n;
+        if ((uint32_t)p.kchunks * 9u * n * 128u + 2u * p.halo_stride <= budget) n_tile = n;
     }
     if (n_tile == 0) return -1;     // weight panel does not fit: caller falls back to the per-tap kernel
     p.n_tile = n_tile;
@@ -711,16 +776,18 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
     p.b_block_bytes = (uint32_t)n_tile * 128u;
     const uint32_t b_total = (uint32_t)p.kchunks * 9u * p.b_block_bytes;
-    p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((budget - b_total) / kHaloStride)));
+    p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((budget - b_total) / p.halo_stride)));
     uint32_t cols = 32;
     while (cols < 2u * p.n_tile) cols <<= 1;
     p.tmem_cols = cols;
 
     CUtensorMap tmA, tmB;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)kHaloPitch, (cuuint32_t)(kHaloH + 2), 1};
+        // dims ordered (C, W, B, H): the box lands in smem as [h][b][w][c], i.e. the image rows of the bt batch
+        // items of a tile are interleaved, which keeps the stride between the tile's 8-pixel groups uniform
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)B, (cuuint64_t)H};
+        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)H * W * Cin * 2, (cuuint64_t)W * Cin * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)kHaloPitch, (cuuint32_t)p.bt, (cuuint32_t)(p.ht + 2)};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -738,7 +805,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: weight tensor map encode failed (CUresult %d)", (int)r);
     }
-    const size_t smem_bytes = (size_t)b_total + (size_t)p.a_stages * kHaloStride + 1024;
+    const size_t smem_bytes = (size_t)b_total + (size_t)p.a_stages * p.halo_stride + 1024;
     const int grid = std::min(p.num_tiles, dd_num_sms());
     const int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
 #define DD_LAUNCH_HALO(EW_)                                                                                        \
@@ -749,7 +816,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
             attr_done = true;                                                                                      \
         }                                                                                                          \
-        conv3x3_halo_kernel<EW_><<<grid, 64 + 32 * EW_, smem_bytes, stream>>>(tmA, tmB, p);                        \
+        DD_CHECK_CUDA(launch_pdl(conv3x3_halo_kernel<EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p));   \
     } while (0)
     if (ew == 8) DD_LAUNCH_HALO(8); else DD_LAUNCH_HALO(4);
 #undef DD_LAUNCH_HALO
@@ -759,7 +826,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
 
 int launch_conv(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     static const bool no_halo = getenv("DD_DISABLE_HALO") != nullptr;     // tuning experiments only
-    if (p.taps == 9 && p.H >= kHaloH && p.W >= kHaloW && (p.Cin / groups) % 16 == 0 && p.Cin >= 64 && !no_halo) {
+    if (p.taps == 9 && p.H >= 8 && p.W >= kHaloW && (p.Cin / groups) % 16 == 0 && p.Cin >= 64 && !no_halo) {
         ConvParams q = p;
         const int r = launch_halo(q, x, w_prepped, groups, stream);
         if (r >= 0) return r;

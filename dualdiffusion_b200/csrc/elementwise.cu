@@ -74,6 +74,8 @@ constexpr int kMaxVecPerLane = 10;    // C <= 10*32*8 = 2560
 
 __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restrict__ x_out, uint4* __restrict__ s_out,
                                     long npix, int C) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     const int lane = threadIdx.x & 31;
     const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pix >= npix) return;
@@ -117,6 +119,8 @@ __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restri
 // ------------------------------------------------------------------------------------------
 __global__ void cat_silu_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb, float wa,
                                 float wb, int up, uint4* __restrict__ xcat, uint4* __restrict__ s, int B, int H, int W) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     const int vt = va + vb;
     const long total = (long)B * H * W * vt;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -151,6 +155,8 @@ __global__ void cat_silu_kernel(const uint4* __restrict__ a, int va, const uint4
 }
 
 __global__ void avgpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nvec) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     const int Ho = H >> 1, Wo = W >> 1;
     const long total = (long)B * Ho * Wo * nvec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -179,6 +185,8 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__
 __global__ void stem_patches_kernel(const float* __restrict__ x_in, const float* __restrict__ sigma, float sigma_data,
                                     const float* __restrict__ ln_freqs, uint4* __restrict__ out, int B, int Cin, int H,
                                     int W) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
     const int CT = Cin + 2;
     const long total = (long)B * H * W * 8;       // 8 x (8 bf16) per pixel
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -455,9 +463,9 @@ extern "C" int dd_pixnorm_silu(const void* t, void* x_out, void* s_out, long npi
     DD_REQUIRE(C % 8 == 0 && C <= kMaxVecPerLane * 256, "dd_pixnorm_silu: C=%d unsupported", C);
     if (npix == 0) return 0;
     const int warps = 8;
-    pixnorm_silu_kernel<<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, stream>>>(
-        static_cast<const uint4*>(t), static_cast<uint4*>(x_out), static_cast<uint4*>(s_out), npix, C);
-    DD_CHECK_LAUNCH();
+    DD_CHECK_CUDA(dd_launch_pdl(pixnorm_silu_kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), 0, stream,
+                                static_cast<const uint4*>(t), static_cast<uint4*>(x_out), static_cast<uint4*>(s_out), npix,
+                                C));
     return 0;
 }
 
@@ -469,11 +477,9 @@ extern "C" int dd_cat_silu(const void* a, int Ca, const void* b, int Cb, float w
     DD_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "dd_cat_silu: upsample needs even output size");
     const long total = (long)B * H * W * ((Ca + Cb) / 8);
     if (total == 0) return 0;
-    cat_silu_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(a), Ca / 8,
-                                                              static_cast<const uint4*>(b), Cb / 8, wa, wb, upsample,
-                                                              static_cast<uint4*>(xcat_out), static_cast<uint4*>(s_out),
-                                                              B, H, W);
-    DD_CHECK_LAUNCH();
+    DD_CHECK_CUDA(dd_launch_pdl(cat_silu_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream,
+                                static_cast<const uint4*>(a), Ca / 8, static_cast<const uint4*>(b), Cb / 8, wa, wb,
+                                upsample, static_cast<uint4*>(xcat_out), static_cast<uint4*>(s_out), B, H, W));
     return 0;
 }
 
@@ -482,9 +488,8 @@ extern "C" int dd_avgpool2(const void* x, void* out, int B, int H, int W, int C,
     DD_REQUIRE(x && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "dd_avgpool2: bad arguments");
     const long total = (long)B * (H / 2) * (W / 2) * (C / 8);
     if (total == 0) return 0;
-    avgpool2_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), B,
-                                                              H, W, C / 8);
-    DD_CHECK_LAUNCH();
+    DD_CHECK_CUDA(dd_launch_pdl(avgpool2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream,
+                                static_cast<const uint4*>(x), static_cast<uint4*>(out), B, H, W, C / 8));
     return 0;
 }
 
@@ -495,9 +500,8 @@ extern "C" int dd_stem_patches(const float* x_in, const float* sigma, float sigm
     DD_REQUIRE(9 * (Cin + 2) <= 64, "dd_stem_patches: in_channels=%d unsupported (9*(Cin+2) must be <= 64)", Cin);
     const long total = (long)B * H * W * 8;
     if (total == 0) return 0;
-    stem_patches_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x_in, sigma, sigma_data, ln_freqs,
-                                                                  static_cast<uint4*>(out), B, Cin, H, W);
-    DD_CHECK_LAUNCH();
+    DD_CHECK_CUDA(dd_launch_pdl(stem_patches_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, x_in, sigma,
+                                sigma_data, ln_freqs, static_cast<uint4*>(out), B, Cin, H, W));
     return 0;
 }
 

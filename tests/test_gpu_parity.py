@@ -60,6 +60,10 @@ CONV_CASES = [
     (2, 17, 20, 768, 512, 3, 8),     # ragged tile edges; cin_g 96 = 64 + 32 (partial second chunk)
     (1, 32, 24, 1280, 1024, 3, 8),   # cin_g 160 (3 chunks), weight panel forces n_tile 32, several panels per CTA
     (1, 16, 344, 512, 256, 3, 8),    # level-1 row of the 45 s latent, cout_g 32
+    # 8..15 image rows: halo tiles hold 8 rows of two batch items, image rows interleaved
+    (2, 8, 172, 512, 1024, 3, 8),    # level 2 of the 45 s latent
+    (3, 8, 20, 128, 64, 3, 2),       # odd batch: the last tile has one item
+    (1, 12, 9, 64, 32, 3, 1),        # single item, 12 rows -> two row tiles, ragged everywhere
 ]
 
 
