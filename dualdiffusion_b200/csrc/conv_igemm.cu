@@ -32,6 +32,7 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kMaxThreads = 320;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAccBufs = 8;
 constexpr int DD_EPI_HEAD = 3;   // internal: EDM output head (dd_conv_out)
 
 struct ConvParams {
@@ -48,6 +49,10 @@ struct ConvParams {
     int stages;
     uint32_t a_bytes, b_bytes;      // bytes landed per stage by the two TMA boxes
     uint32_t tmem_cols;
+    int nacc;                       // independent accumulators per tile (power of two), summed in the epilogue
+    int nbuf;                       // TMEM accumulator buffers (power of two): MMAs run up to nbuf tiles ahead of the epilogue
+    int dbg_taps;                   // experiment: number of taps actually issued (9 = all)
+    int dbg_nostore;                // experiment: skip the epilogue's global stores
     // halo kernel (3x3, weights stationary)
     int ks_last;                    // 16-channel MMA steps in the last 64-channel chunk
     int a_stages;
@@ -105,23 +110,39 @@ __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float (&
 // Epilogue of one 128 x n_tile accumulator tile for one thread (= one output pixel row of the tile):
 // TMEM -> registers -> fused elementwise (Block.forward glue) -> global.  `taddr` addresses this warp's lane
 // quadrant and the tile's accumulator buffer; with EW == 8 the two warps of a quadrant interleave 16-column chunks.
+template <int CH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH], bool half) {
+    if constexpr (CH == 16) {
+        ptx::tmem_ld_32x16(taddr, r);
+    } else {
+        if (!half) ptx::tmem_ld_32x32(taddr, r);
+        else ptx::tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(r));
+    }
+}
+
 template <int EW>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int chunk0, bool valid, int b, int h,
-                                              int w, int ch0) {
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
+                                              int ch0) {
     constexpr int kChunk = EW == 8 ? 16 : 32;   // columns per tcgen05.ld
     const size_t pix = ((size_t)b * p.H + h) * p.W + w;
-    for (int c0 = chunk0 * kChunk; c0 < p.n_tile; c0 += (EW / 4) * kChunk) {
+    uint32_t rn[kChunk];
+    // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
+    tmem_ld_chunk<kChunk>(taddr, rn, kChunk == 32 && 32 > p.n_tile);
+    for (int c0 = 0; c0 < p.n_tile; c0 += kChunk) {
               uint32_t r[kChunk];
-              if constexpr (kChunk == 16) {
-                  ptx::tmem_ld_32x16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(r));
-              } else {
-                  if (c0 + 32 <= p.n_tile) {
-                      ptx::tmem_ld_32x32(taddr + c0, reinterpret_cast<uint32_t(&)[32]>(r));
-                  } else {   // n_tile is a multiple of 16 only: ragged last half chunk
-                      ptx::tmem_ld_32x16(taddr + c0, reinterpret_cast<uint32_t(&)[16]>(r));
-                  }
-              }
               ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < kChunk; ++i) r[i] = rn[i];
+              // (tuning experiment DD_FORCE_NACC) k-steps round-robined over `nacc` accumulators are summed here
+              for (int u = 1; u < p.nacc; ++u) {
+                  uint32_t r2[kChunk];
+                  tmem_ld_chunk<kChunk>(taddr + u * p.n_tile + c0, r2, kChunk == 32 && c0 + 32 > p.n_tile);
+                  ptx::tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < kChunk; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+              }
+              if (c0 + kChunk < p.n_tile)
+                  tmem_ld_chunk<kChunk>(taddr + c0 + kChunk, rn, kChunk == 32 && c0 + 2 * kChunk > p.n_tile);
               if (!valid) continue;
 #pragma unroll
               for (int sub16 = 0; sub16 < kChunk / 16; ++sub16) {
@@ -178,7 +199,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                         }
                     }
                 }
-                store_bf16x16(p.out + pix * p.Cout + ch, v);
+                if (!p.dbg_nostore) store_bf16x16(p.out + pix * p.Cout + ch, v);
                 if (p.epi2 != DD_EPI2_NONE) {
                     if (p.epi2 == DD_EPI2_SILU) {
 #pragma unroll
@@ -209,8 +230,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar[2];
-    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t tmem_full_bar[kMaxAccBufs];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[kMaxAccBufs];
     __shared__ uint32_t tmem_base_slot;
 
     // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 B swizzle atom
@@ -229,9 +250,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::mbar_init(&full_bar[s], 1);
             ptx::mbar_init(&empty_bar[s], 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < p.nbuf; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], EW);
+            ptx::mbar_init(&tmem_empty_bar[a], 4);       // the four warps (lane quadrants) of one epilogue group
         }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
@@ -312,12 +333,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t stage = 0, phase = 0;
             uint32_t local = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
-                const uint32_t acc = local & 1;
-                const uint32_t acc_phase = (local >> 1) & 1;
+                const uint32_t acc = local & (uint32_t)(p.nbuf - 1);
+                const uint32_t acc_phase = (local / (uint32_t)p.nbuf) & 1;
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
-                uint32_t accumulate = 0;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)(p.n_tile * p.nacc);
+                const uint32_t nacc_mask = (uint32_t)p.nacc - 1u;
+                uint32_t q = 0;                                  // running k-step index -> accumulator q % nacc
                 for (int it0 = 0; it0 < p.k_iters; it0 += p.sub) {
                     const int cnt = min(p.sub, p.k_iters - it0);
                     ptx::mbar_wait(&full_bar[stage], phase);
@@ -328,9 +350,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const uint64_t a_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes, kRowBytes);
                             const uint64_t b_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes + kABufBytes, kRowBytes);
 #pragma unroll
-                            for (int ks = 0; ks < KC / 16; ++ks) {      // +32 B per 16-channel step = +2 in 16 B units
-                                ptx::umma_bf16_ss(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc, accumulate);
-                                accumulate = 1;
+                            for (int ks = 0; ks < KC / 16; ++ks, ++q) { // +32 B per 16-channel step = +2 in 16 B units
+                                ptx::umma_bf16_ss(d_tmem + (q & nacc_mask) * (uint32_t)p.n_tile, a_desc + 2 * ks,
+                                                  b_desc + 2 * ks, idesc, q > nacc_mask ? 1u : 0u);
                             }
                         }
                         ptx::umma_commit(&empty_bar[stage]);    // frees the smem stage once the MMAs retire
@@ -345,27 +367,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
         // ------------------------------ epilogue ------------------------------
         ptx::grid_dependency_wait();                // epilogue reads (residual, scales) / writes depend on prior kernels
-        const int ew = warp - 2;                    // 0..EW-1
+        // EW == 8: two groups of four warps (one per TMEM lane quadrant) take alternate tiles
+        const int group = (warp - 2) >> 2, ngroups = EW / 4;
         const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
-        const int chunk0 = ew >> 2;                 // EW == 8: this warp takes chunks chunk0, chunk0+2, ...
         const int row = quad * 32 + lane;           // row of the 128-row tile == box-linear pixel index
         const int ww = row % p.wt;
         const int hh = (row / p.wt) % p.ht;
         const int bb = row / (p.wt * p.ht);
-        uint32_t local = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local) {
+        uint32_t local = group;
+        for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += ngroups * gridDim.x, local += ngroups) {
             const TileCoord t = decode_tile(p, tile);
-            const uint32_t acc = local & 1;
-            const uint32_t acc_phase = (local >> 1) & 1;
+            const uint32_t acc = local & (uint32_t)(p.nbuf - 1);
+            const uint32_t acc_phase = (local / (uint32_t)p.nbuf) & 1;
             const int b = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
             const bool valid = (bb < p.bt) && (b < p.B) && (h < p.H) && (w < p.W);
             const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
 
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)p.n_tile;
-
-            epilogue_tile<EW>(p, taddr, chunk0, valid, b, h, w, ch0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
+            epilogue_tile<EW>(p, taddr, valid, b, h, w, ch0);
             // all TMEM reads of this buffer have completed (wait::ld above): hand it back
             ptx::tcgen05_fence_before();
             __syncwarp();
@@ -417,14 +438,18 @@ __device__ __forceinline__ HaloTile decode_halo_tile(const ConvParams& p, int ti
 // a tap is a (dy*pitch + dx)-row shift of the halo tile (8 units per 128 B row), a k-step is +2 units.
 template <int NKS>
 __device__ __forceinline__ void halo_issue_taps(uint64_t a_desc0, uint64_t b_desc0, uint32_t b_block16, uint32_t d_tmem,
-                                                uint32_t idesc, uint32_t accumulate, int row_pitch) {
+                                                uint32_t idesc, uint32_t q0, uint32_t nacc_mask, uint32_t n_tile,
+                                                int row_pitch, int dbg_taps = 9) {
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
+        if (tap >= dbg_taps) break;
         const uint64_t a_tap = a_desc0 + (uint64_t)(((tap / 3) * row_pitch + (tap % 3)) * 8);
         const uint64_t b_tap = b_desc0 + (uint64_t)tap * b_block16;
 #pragma unroll
         for (int ks = 0; ks < NKS; ++ks) {
-            ptx::umma_bf16_ss(d_tmem, a_tap + 2 * ks, b_tap + 2 * ks, idesc, (tap == 0 && ks == 0) ? accumulate : 1u);
+            const uint32_t q = q0 + tap * NKS + ks;          // running k-step index -> accumulator q % nacc
+            ptx::umma_bf16_ss(d_tmem + (q & nacc_mask) * n_tile, a_tap + 2 * ks, b_tap + 2 * ks, idesc,
+                              q > nacc_mask ? 1u : 0u);
         }
     }
 }
@@ -437,8 +462,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __shared__ __align__(8) uint64_t a_full[kMaxAStages];
     __shared__ __align__(8) uint64_t a_empty[kMaxAStages];
     __shared__ __align__(8) uint64_t b_full, b_empty;
-    __shared__ __align__(8) uint64_t tmem_full_bar[2];
-    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t tmem_full_bar[kMaxAccBufs];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[kMaxAccBufs];
     __shared__ uint32_t tmem_base_slot;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -459,9 +484,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::mbar_init(&b_full, 1);
         ptx::mbar_init(&b_empty, 1);
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < p.nbuf; ++a) {
             ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], EW);
+            ptx::mbar_init(&tmem_empty_bar[a], 4);       // the four warps (lane quadrants) of one epilogue group
         }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
@@ -521,12 +546,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     b_par ^= 1;
                     cur_panel = panel;
                 }
-                const uint32_t acc = local & 1;
-                const uint32_t acc_phase = (local >> 1) & 1;
+                const uint32_t acc = local & (uint32_t)(p.nbuf - 1);
+                const uint32_t acc_phase = (local / (uint32_t)p.nbuf) & 1;
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
-                uint32_t accumulate = 0;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)(p.n_tile * p.nacc);
+                const uint32_t nacc_mask = (uint32_t)p.nacc - 1u;
+                uint32_t q0 = 0;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&a_full[stage], phase);
                     ptx::tcgen05_fence_after();
@@ -534,14 +560,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + stage * p.halo_stride, kHaloPitch * 128);
                         const uint64_t b_desc0 = ptx::make_kmajor_desc_sw128(b_base + (uint32_t)(kc * 9) * p.b_block_bytes, 1024);
                         const int nks = (kc == p.kchunks - 1) ? p.ks_last : 4;
-                        if (nks == 4) halo_issue_taps<4>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
-                        else if (nks == 2) halo_issue_taps<2>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
-                        else if (nks == 1) halo_issue_taps<1>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
-                        else halo_issue_taps<3>(a_desc0, b_desc0, b_block16, d_tmem, idesc, accumulate, row_pitch);
+                        const uint32_t nt = (uint32_t)p.n_tile;
+                        if (nks == 4) halo_issue_taps<4>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
+                        else if (nks == 2) halo_issue_taps<2>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
+                        else if (nks == 1) halo_issue_taps<1>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
+                        else halo_issue_taps<3>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
                         ptx::umma_commit(&a_empty[stage]);
                     }
                     __syncwarp();
-                    accumulate = 1;
+                    q0 += 9u * (uint32_t)((kc == p.kchunks - 1) ? p.ks_last : 4);
                     if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
                 }
                 const bool panel_ends = (tile + 1 == t_end) || ((tile + 1) / p.m_tiles != panel);
@@ -555,24 +582,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ------------------------------ epilogue ------------------------------
         ptx::grid_dependency_wait();
-        const int ew = warp - 2;
+        const int group = (warp - 2) >> 2, ngroups = EW / 4;      // EW == 8: two warp groups take alternate tiles
         const int quad = warp & 3;
-        const int chunk0 = ew >> 2;
         const int row = quad * 32 + lane;
         const int grp = row >> 3, ww = row & 7;       // group index = h * bt + b
         const int hh = grp / p.bt, bb = grp - hh * p.bt;
-        uint32_t local = 0;
-        for (int tile = t_begin; tile < t_end; ++tile, ++local) {
+        uint32_t local = group;
+        for (int tile = t_begin + group; tile < t_end; tile += ngroups, local += ngroups) {
             const HaloTile t = decode_halo_tile(p, tile);
-            const uint32_t acc = local & 1;
-            const uint32_t acc_phase = (local >> 1) & 1;
+            const uint32_t acc = local & (uint32_t)(p.nbuf - 1);
+            const uint32_t acc_phase = (local / (uint32_t)p.nbuf) & 1;
             const int h = t.h0 + hh, w = t.w0 + ww, b = t.b + bb;
             const bool valid = (hh < p.ht) && (h < p.H) && (w < p.W) && (b < p.B);
             const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)p.n_tile;
-            epilogue_tile<EW>(p, taddr, chunk0, valid, b, h, w, ch0);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
+            epilogue_tile<EW>(p, taddr, valid, b, h, w, ch0);
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -663,6 +689,15 @@ int choose_n_tile(int cout_g, long m_tiles, int groups, int k_iters, int KC, int
     return best;
 }
 
+// Dependent UMMAs into one accumulator issue ~100+ cycles apart while a 128 x n x 16 UMMA occupies the tensor pipe
+// for only n cycles (cta_group::1): tiles narrower than 128 columns spread their k-steps over several accumulators.
+int choose_nacc(int n_tile, int k_steps) {
+    static const int forced = getenv("DD_FORCE_NACC") ? atoi(getenv("DD_FORCE_NACC")) : 0;   // tuning experiments
+    int nacc = 1;       // measured: no gain from splitting the accumulation chain (the epilogue was the limiter)
+    if (forced >= 1) { nacc = 1; while (nacc < forced && 2 * (2 * nacc) * n_tile <= 512 && 2 * nacc <= k_steps) nacc *= 2; }
+    return nacc;
+}
+
 int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode_fn();
     DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");
@@ -690,8 +725,11 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.sub = (pair_bytes <= 24u * 1024u && p.k_iters >= 2) ? 2 : 1;
     const uint32_t stage_bytes = pair_bytes * p.sub;
     p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u) / stage_bytes)));
+    p.nacc = choose_nacc(p.n_tile, p.k_iters * (KC / 16));
+    p.nbuf = 2;
+    while (p.nbuf < kMaxAccBufs && 2 * p.nbuf * p.n_tile * p.nacc <= 512) p.nbuf *= 2;
     uint32_t cols = 32;
-    while (cols < 2u * p.n_tile) cols <<= 1;
+    while (cols < (uint32_t)(p.nbuf * p.n_tile * p.nacc)) cols <<= 1;
     p.tmem_cols = cols;
 
     CUtensorMap tmA, tmB;
@@ -777,8 +815,13 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     p.b_block_bytes = (uint32_t)n_tile * 128u;
     const uint32_t b_total = (uint32_t)p.kchunks * 9u * p.b_block_bytes;
     p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((budget - b_total) / p.halo_stride)));
+    p.nacc = choose_nacc(p.n_tile, 9 * (4 * (p.kchunks - 1) + p.ks_last));
+    p.dbg_taps = getenv("DD_DBG_TAPS") ? atoi(getenv("DD_DBG_TAPS")) : 9;
+    p.dbg_nostore = getenv("DD_DBG_NOSTORE") != nullptr;
+    p.nbuf = 2;
+    while (p.nbuf < kMaxAccBufs && 2 * p.nbuf * p.n_tile * p.nacc <= 512) p.nbuf *= 2;
     uint32_t cols = 32;
-    while (cols < 2u * p.n_tile) cols <<= 1;
+    while (cols < (uint32_t)(p.nbuf * p.n_tile * p.nacc)) cols <<= 1;
     p.tmem_cols = cols;
 
     CUtensorMap tmA, tmB;
