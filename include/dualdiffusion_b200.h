@@ -156,7 +156,7 @@ DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, voi
                  int head_dim, void* stream);
 
 /* ---- mel-STFT encode / FGLA decode: modules/formats/old/spectrogram.py:176-238 ------------- */
-/* Shared conventions: n_fft = 2 * 2^a * 5^b (6400 and 4096 both qualify), win_length == n_fft, center=True with
+/* Shared conventions: n_fft in {6400, 4096} (compile-time mixed-radix plans), win_length == n_fft, center=True with
  * reflect padding, one-sided spectra of n_fft/2+1 bins.  `window` fp32 [n_fft]; `twiddles` = exp(-2 pi i m/(n_fft/2)),
  * m < n_fft/2, and `twiddles_half` = exp(-2 pi i k/n_fft), k <= n_fft/2, as interleaved (re,im) fp32 pairs.
  *
