@@ -61,7 +61,7 @@ _SIGNATURES = {
                             c_int, c_int, c_void_p]),
     "dd_avgpool2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "dd_stft_mel": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+    "dd_stft_mel": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_void_p, c_int, c_void_p]),
     "dd_fgla_istft": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int,
                               c_int, c_void_p, c_int, c_void_p]),

@@ -72,24 +72,47 @@ attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __re
     const __nv_bfloat16* k_base = q_base + C;
     const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kD + sub * 8;
 
-    for (int j0 = 0; j0 < npad; j0 += 32) {
-        const int j = j0 + tok_in_pass;
-        float f[8];
-        load_norm8(k_base + (size_t)j * 2 * C, j < N, f);
-        *reinterpret_cast<uint4*>(Ks + (size_t)j * kKStride + sub * 8) =
-            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-        load_norm8(v_base + (size_t)j * C, j < N, f);
-        *reinterpret_cast<uint4*>(Vs + (size_t)j * kKStride + sub * 8) =
-            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-    }
-    for (int r0 = 0; r0 < kQTile; r0 += 32) {
-        const int r = r0 + tok_in_pass;
-        float f[8];
-        load_norm8(q_base + (size_t)(q0 + r) * 2 * C, q0 + r < N, f);
-        uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                              pack_bf16x2(f[6], f[7]));
-        *reinterpret_cast<uint4*>(Qs + (size_t)r * kKStride + sub * 8) = pk;
-    }
+    // Staging is latency-bound if every token's load is followed by its use: issue the loads of kStageBatch
+    // tokens per thread first (one memory round trip per batch), then normalise and store them.
+    constexpr int kStageBatch = 6;
+    auto stage_rows = [&](const __nv_bfloat16* base, size_t token_stride, int first_token, int n_rows, int row_limit,
+                          __nv_bfloat16* dst) {
+        for (int r0 = 0; r0 < n_rows; r0 += 32 * kStageBatch) {
+            uint4 q[kStageBatch];
+#pragma unroll
+            for (int u = 0; u < kStageBatch; ++u) {
+                const int r = r0 + u * 32 + tok_in_pass;
+                q[u] = make_uint4(0, 0, 0, 0);
+                if (r < n_rows && first_token + r < row_limit)
+                    q[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(first_token + r) * token_stride));
+            }
+#pragma unroll
+            for (int u = 0; u < kStageBatch; ++u) {
+                const int r = r0 + u * 32 + tok_in_pass;
+                if (r0 + u * 32 >= n_rows) break;           // warp-uniform: whole batch row beyond the tile
+                const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+                float f[8];
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 t2 = unpack_bf16x2(w[j]);
+                    f[2 * j] = t2.x; f[2 * j + 1] = t2.y;
+                    ss += t2.x * t2.x + t2.y * t2.y;
+                }
+                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+                const float inv = 1.f / (kNormEps + sqrtf(ss) * 0.125f);   // ||x|| / sqrt(64)
+                if (r < n_rows)
+                    *reinterpret_cast<uint4*>(dst + (size_t)r * kKStride + sub * 8) =
+                        make_uint4(pack_bf16x2(f[0] * inv, f[1] * inv), pack_bf16x2(f[2] * inv, f[3] * inv),
+                                   pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
+            }
+        }
+    };
+    stage_rows(k_base, (size_t)2 * C, 0, npad, N, Ks);
+    stage_rows(v_base, (size_t)C, 0, npad, N, Vs);
+    stage_rows(q_base, (size_t)2 * C, q0, kQTile, N, Qs);
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;

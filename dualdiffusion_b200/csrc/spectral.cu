@@ -218,8 +218,9 @@ __device__ __forceinline__ float2* stft_frame(int t, int hop, int len, SrcFn src
 // ------------------------------------------------------------------------------------------
 template <int N>
 __global__ void __launch_bounds__(Plan<N>::kThreads)
-stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict__ window, const float2* __restrict__ tw,
-                const float2* __restrict__ tw_half, int hop, int n_frames,
+stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict__ window,
+                const float* __restrict__ window2, const float* __restrict__ coef1, const float* __restrict__ coef2,
+                const float2* __restrict__ tw, const float2* __restrict__ tw_half, int hop, int n_frames,
                 const int* __restrict__ fb_start, const int* __restrict__ fb_count, const int* __restrict__ fb_offset,
                 const float* __restrict__ fb_weight, int n_filters, float exponent, float mean, float scale,
                 float* __restrict__ out) {
@@ -229,7 +230,8 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
     float2* a = reinterpret_cast<float2*>(smem_fft);
     float2* b = a + buf;
     float2* tws = b + buf;                                        // [n/2] twiddle half table
-    float* tile = reinterpret_cast<float*>(tws + n / 2);          // [n_filters][kEncFrames + 1]
+    float* mag = reinterpret_cast<float*>(tws + n / 2);           // [n + 8] blended magnitudes
+    float* tile = mag + n + 8;                                    // [n_filters][kEncFrames + 1]
     load_twiddles<N>(tws, tw);
     const int s = blockIdx.y;
     const int t0 = blockIdx.x * kEncFrames;
@@ -237,15 +239,25 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
     for (int f = 0; f < kEncFrames; ++f) {
         const int t = t0 + f;
         if (t >= n_frames) break;
+        // |STFT| with the first window (times an optional per-bin coefficient); the live MS_MDCT_DualFormat blends a
+        // second, narrower-window STFT per bin (ms_mdct_dual.py:249-256): mag = |X1|*coef1 + |X2|*coef2
         float2* spec = stft_frame<N>(t, hop, len, [&](int j) { return __ldg(sig + j); }, window, tws, tw_half, a, b);
-        float* mag = reinterpret_cast<float*>(spec == a ? b : a);
-        for (int k = threadIdx.x; k <= n; k += blockDim.x) mag[k] = sqrtf(spec[k].x * spec[k].x + spec[k].y * spec[k].y);
+        for (int k = threadIdx.x; k <= n; k += blockDim.x) {
+            const float m1 = sqrtf(spec[k].x * spec[k].x + spec[k].y * spec[k].y);
+            mag[k] = coef1 ? m1 * __ldg(coef1 + k) : m1;
+        }
         __syncthreads();
+        if (window2) {
+            spec = stft_frame<N>(t, hop, len, [&](int j) { return __ldg(sig + j); }, window2, tws, tw_half, a, b);
+            for (int k = threadIdx.x; k <= n; k += blockDim.x)
+                mag[k] += sqrtf(spec[k].x * spec[k].x + spec[k].y * spec[k].y) * __ldg(coef2 + k);
+            __syncthreads();
+        }
         for (int m = threadIdx.x; m < n_filters; m += blockDim.x) {
             const int st = fb_start[m], cnt = fb_count[m], off = fb_offset[m];
             float acc = 0.f;
             for (int j = 0; j < cnt; ++j) acc += mag[st + j] * __ldg(fb_weight + off + j);
-            const float v = (exponent == 0.25f) ? sqrtf(sqrtf(acc)) : powf(acc, exponent);
+            const float v = (exponent == 0.25f) ? sqrtf(sqrtf(acc)) : (exponent == 1.f ? acc : powf(acc, exponent));
             tile[m * (kEncFrames + 1) + f] = (v - mean) * scale;
         }
         __syncthreads();
@@ -436,7 +448,8 @@ cudaError_t raise_smem_limit(K kernel, size_t smem) {
 
 }  // namespace
 
-extern "C" int dd_stft_mel(const float* raw, int n_signals, int len, const float* window, const float* twiddles,
+extern "C" int dd_stft_mel(const float* raw, int n_signals, int len, const float* window, const float* window2,
+                           const float* coef1, const float* coef2, const float* twiddles,
                            const float* twiddles_half, int n_fft, int hop, const int* fb_start, const int* fb_count,
                            const int* fb_offset, const float* fb_weight, int n_filters, float exponent, float mean,
                            float scale, float* out, int n_frames, void* stream_) {
@@ -444,17 +457,19 @@ extern "C" int dd_stft_mel(const float* raw, int n_signals, int len, const float
     DD_REQUIRE(raw && window && twiddles && twiddles_half && fb_start && fb_count && fb_offset && fb_weight && out,
                "dd_stft_mel: null pointer");
     DD_REQUIRE(supported_n_fft(n_fft), "dd_stft_mel: n_fft=%d unsupported (6400, 4096)", n_fft);
+    DD_REQUIRE(!window2 || coef2, "dd_stft_mel: a second window needs its per-bin coefficients");
     DD_REQUIRE(len > n_fft / 2, "dd_stft_mel: signal shorter than the reflect padding");
     DD_REQUIRE(n_frames == 1 + len / hop, "dd_stft_mel: n_frames must be 1 + len/hop (center=True)");
     if (n_signals == 0) return 0;
-    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)n_filters * (kEncFrames + 1) * sizeof(float);
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)(n_fft / 2 + 8 + n_filters * (kEncFrames + 1)) * sizeof(float);
     const dim3 grid(ceil_div(n_frames, kEncFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);
 #define DD_ENC(N_)                                                                                                 \
     do {                                                                                                           \
         DD_CHECK_CUDA(raise_smem_limit(stft_mel_kernel<N_>, smem));                                                \
-        stft_mel_kernel<N_><<<grid, Plan<N_>::kThreads, smem, stream>>>(raw, len, window, tw, twh, hop, n_frames,  \
+        stft_mel_kernel<N_><<<grid, Plan<N_>::kThreads, smem, stream>>>(raw, len, window, window2, coef1, coef2,   \
+                                                                         tw, twh, hop, n_frames,                    \
                                                                          fb_start, fb_count, fb_offset, fb_weight,  \
                                                                          n_filters, exponent, mean, scale, out);    \
     } while (0)

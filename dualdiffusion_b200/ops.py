@@ -248,13 +248,15 @@ def mp_fourier(x: Tensor, freqs: Tensor, phases: Tensor) -> Tensor:
 
 
 def stft_mel(raw: Tensor, window: Tensor, tw: Tensor, tw_half: Tensor, n_fft: int, hop: int, fb: dict,
-             exponent: float, mean: float, scale: float) -> Tensor:
+             exponent: float, mean: float, scale: float, window2: Optional[Tensor] = None,
+             coef1: Optional[Tensor] = None, coef2: Optional[Tensor] = None) -> Tensor:
     """raw [S, L] fp32 -> [S, n_filters, 1 + L // hop] fp32 (mel-STFT encode)."""
     S, Ln = raw.shape
     T = 1 + Ln // hop
     nf = fb["start"].numel()
     out = torch.empty((S, nf, T), device=raw.device, dtype=torch.float32)
-    L.check(L.load().dd_stft_mel(L.ptr(raw), S, Ln, L.ptr(window), L.ptr(tw), L.ptr(tw_half), n_fft, hop,
+    L.check(L.load().dd_stft_mel(L.ptr(raw), S, Ln, L.ptr(window), L.ptr(window2), L.ptr(coef1), L.ptr(coef2), L.ptr(tw),
+                                 L.ptr(tw_half), n_fft, hop,
                                  L.ptr(fb["start"]), L.ptr(fb["count"]), L.ptr(fb["offset"]), L.ptr(fb["weight"]), nf,
                                  exponent, mean, scale, L.ptr(out), T, L.stream_ptr()))
     _count()

@@ -164,8 +164,13 @@ DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, voi
  * (frequency_scale.py:127-128) + the affine of raw_to_sample (:223-226):
  *   out[s][f][t] = ((sum_k |STFT(raw_s)[k][t]| * fb[k][f]) ** exponent - mean) * scale
  * with the triangular filterbank given per filter f as a run of fb_count[f] weights starting at bin fb_start[f]
- * (weights at fb_weight[fb_offset[f] ...]).  raw [S][len] fp32, out [S][n_filters][n_frames], n_frames = 1+len/hop. */
-DD_API int dd_stft_mel(const float* raw, int n_signals, int len, const float* window, const float* twiddles,
+ * (weights at fb_weight[fb_offset[f] ...]).  raw [S][len] fp32, out [S][n_filters][n_frames], n_frames = 1+len/hop.
+ * Live format MS_MDCT_DualFormat.raw_to_mel_spec (formats/ms_mdct_dual.py:230-257): pass the second (narrower)
+ * window as `window2` and per-bin coefficients; the magnitude fed to the filterbank is then
+ * |STFT_w1|[k]*coef1[k] + |STFT_w2|[k]*coef2[k] (window normalisation, blend weight and 1/mel-density folded into
+ * coef1/coef2).  window2, coef1, coef2 may be NULL (single window, coefficient 1).                              */
+DD_API int dd_stft_mel(const float* raw, int n_signals, int len, const float* window, const float* window2,
+                       const float* coef1, const float* coef2, const float* twiddles,
                        const float* twiddles_half, int n_fft, int hop, const int* fb_start, const int* fb_count,
                        const int* fb_offset, const float* fb_weight, int n_filters, float exponent, float mean,
                        float scale, float* out, int n_frames, void* stream);

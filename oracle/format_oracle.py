@@ -140,3 +140,76 @@ def sample_to_raw(samples: Tensor, spec: SpectrogramSpec, n_fgla_iters: Optional
     s = (samples / spec.raw_to_sample_scale + spec.sample_mean).clip(min=0)
     amplitudes = unscale(s ** (1 / spec.abs_exponent), spec)
     return griffinlim(amplitudes, spec, n_fgla_iters or spec.num_fgla_iters, stereo=True)
+
+
+# --------------------------------------------------------------------------------------
+# live format: MS_MDCT_DualFormat.raw_to_mel_spec (src/modules/formats/ms_mdct_dual.py:230-257)
+# --------------------------------------------------------------------------------------
+@dataclass
+class MSDualSpec:
+    """ms_mdct_dual.py:36-66 defaults (mel-spectrogram side)."""
+    sample_rate: int = 32000
+    raw_to_mel_spec_scale: float = 50
+    raw_to_mel_spec_offset: float = 0
+    ms_abs_exponent: float = 1
+    ms_freq_min: float = 0
+    ms_num_frequencies: int = 256
+    ms_step_size_ms: int = 8
+    ms_window_duration_ms: int = 128
+    ms_padded_duration_ms: int = 128
+    ms_window_exponent_low: float = 17
+    ms_window_exponent_high: Optional[float] = 58
+
+    @property
+    def n_fft(self) -> int:
+        return int(self.ms_padded_duration_ms / 1000.0 * self.sample_rate)
+
+    @property
+    def hop_length(self) -> int:
+        return int(self.ms_step_size_ms / 1000.0 * self.sample_rate)
+
+    @property
+    def num_stft_bins(self) -> int:
+        return self.n_fft // 2 + 1
+
+
+def blackman_harris(n: int) -> Tensor:
+    """utils/mclt.py:69-71."""
+    x = torch.arange(n) / n * 2 * torch.pi
+    return 0.35875 - 0.48829 * torch.cos(x) + 0.14128 * torch.cos(2 * x) - 0.01168 * torch.cos(3 * x)
+
+
+def ms_mel_filterbank(spec: MSDualSpec) -> Tensor:
+    """FrequencyScale(mel, freq_min, sr/2, slaney norm, triangular) — frequency_scale.py:151-169."""
+    lo = 2595.0 * math.log10(1.0 + spec.ms_freq_min / 700.0)
+    hi = 2595.0 * math.log10(1.0 + (spec.sample_rate / 2) / 700.0)
+    f_pts = 700.0 * (10.0 ** (torch.linspace(lo, hi, spec.ms_num_frequencies + 2) / 2595.0) - 1.0)
+    all_freqs = torch.linspace(0, spec.sample_rate / 2, spec.num_stft_bins)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    fb = torch.max(torch.zeros(1), torch.min((-1.0 * slopes[:, :-2]) / f_diff[:-1], slopes[:, 2:] / f_diff[1:]))
+    enorm = 2.0 / (f_pts[2:spec.ms_num_frequencies + 2] - f_pts[:spec.ms_num_frequencies])
+    return fb * enorm.unsqueeze(0)
+
+
+def raw_to_mel_spec(raw: Tensor, spec: MSDualSpec) -> Tensor:
+    """ms_mdct_dual.py:230-257 with ms_freq_min == 0 (no high-pass): two magnitude STFTs (blackman-harris ** 17 / ** 58,
+    torchaudio `normalized="window"`), per-bin blend by (mel_density/max)^2, / mel_density, mel filterbank, affine."""
+    def mag_stft(exponent: float) -> Tensor:
+        w = blackman_harris(spec.n_fft) ** exponent
+        shape = raw.shape
+        y = torch.stft(raw.float().reshape(-1, shape[-1]), n_fft=spec.n_fft, hop_length=spec.hop_length,
+                       win_length=spec.n_fft, window=w, center=True, pad_mode="reflect", normalized=False,
+                       onesided=True, return_complex=True)
+        y = y / w.pow(2.0).sum().sqrt()                                    # normalized="window"
+        return y.abs().reshape(shape[:-1] + y.shape[-2:])
+    hz = torch.linspace(0, spec.sample_rate / 2, spec.num_stft_bins)
+    density = (1127.0 / (700.0 + hz)).view(1, 1, -1, 1)                    # get_mel_density, frequency_scale.py:36-37
+    low = mag_stft(spec.ms_window_exponent_low)
+    if spec.ms_window_exponent_high is not None:
+        bw = ((density / density.amax()) ** 2)
+        blended = low * bw + mag_stft(spec.ms_window_exponent_high) * (1 - bw)   # :252
+    else:
+        blended = low
+    mel = torch.matmul((blended / density).transpose(-1, -2), ms_mel_filterbank(spec)).transpose(-1, -2)
+    return mel ** spec.ms_abs_exponent * spec.raw_to_mel_spec_scale + spec.raw_to_mel_spec_offset   # :256-257

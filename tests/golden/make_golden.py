@@ -91,6 +91,14 @@ def main():
                     crop_1440000=sfmt.sample_raw_crop_width(1440000)), os.path.join(OUT, "format_small.pt"))
     print("format", mel.shape, {k: float(v.std()) for k, v in decoded.items()})
 
+    # ---- live format: MS_MDCT_DualFormat.raw_to_mel_spec (two-window mel-STFT) ----
+    g = torch.Generator().manual_seed(4)
+    raw = 0.1 * torch.randn(2, 2, 256 * 79, generator=g)              # 80 frames
+    raw[1, 0] += 0.25 * torch.sin(2 * torch.pi * 880.0 * torch.arange(raw.shape[-1]) / 32000.0)
+    torch.save(dict(raw=raw, mel=fmt.raw_to_mel_spec(raw), mel_shape_default=fmt.get_mel_spec_shape(3),
+                    crop_default=fmt.get_raw_crop_width(), unscaled_34=fmt.ms_freq_scale.get_unscaled(34)),
+               os.path.join(OUT, "ms_dual_small.pt"))
+
     # ---- sigma schedules ----
     sched = {n: SamplingSchedule.get_schedule(n, 10, 1.0, sigma_max=200.0, sigma_min=0.03, rho=7.0)
              for n in ("edm2", "ln_linear", "linear", "cos", "scale_invariant")}

@@ -518,3 +518,30 @@ def test_fgla_round_trip_property(dev):
         lin = lambda m: (m / fmt.config.raw_to_sample_scale + fmt.config.sample_mean).clip(min=0) ** 4
         errs.append(rel_err(lin(fmt.raw_to_sample(wave))[..., 16:-16], lin(mel)[..., 16:-16]))
     assert errs[1] < errs[0]
+
+
+def test_ms_dual_mel_spec_vs_golden_reference(dev):
+    """Live format: two-window (blackman-harris^17 / ^58, n_fft 4096) mel-STFT, per-bin blend, slaney mel, one launch."""
+    from dualdiffusion_b200.modules.formats.ms_mdct_dual import MS_MDCT_DualFormat, MS_MDCT_DualFormatConfig
+    g = load_golden("ms_dual_small.pt")
+    fmt = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig())
+    mel = fmt.raw_to_mel_spec(g["raw"].to(dev))
+    assert mel.shape == g["mel"].shape and mel.dtype == torch.float32
+    assert rel_err(mel, g["mel"]) < FP32_SPECTRAL
+    # single-window configuration
+    from oracle import format_oracle as fo
+    fmt1 = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig(ms_window_exponent_high=None))
+    ref1 = fo.raw_to_mel_spec(g["raw"], fo.MSDualSpec(ms_window_exponent_high=None))
+    assert rel_err(fmt1.raw_to_mel_spec(g["raw"].to(dev)), ref1) < FP32_SPECTRAL
+
+
+def test_unet_uses_format_frequency_scale(dev):
+    """UNet.forward(…, format, …) reads format.ms_freq_scale.get_unscaled (unet_edm2_b4.py:246)."""
+    from dualdiffusion_b200.modules.formats.ms_mdct_dual import MS_MDCT_DualFormat, MS_MDCT_DualFormatConfig
+    spec = uo.small_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    g = load_golden("unet_small.pt")
+    net = make_unet(spec, sd, dev)
+    emb = net.get_embeddings(g["clap"], g["mask"])
+    d = net(g["x"].to(dev), g["sigma"].to(dev), MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig()), emb)
+    assert rel_err(d, g["d"]) < BF16_NET

@@ -119,3 +119,15 @@ def test_format_host_logic_vs_golden():
     assert tuple(fmt.get_sample_shape(1, 1408768)) == tuple(g["shape_1408768"])
     assert fmt.sample_raw_crop_width(1440000) == g["crop_1440000"]
     assert torch.equal(mel_filterbank(fmt.config), fo.mel_filterbank(fo.SpectrogramSpec()))
+
+
+def test_ms_dual_oracle_and_host_logic_vs_golden():
+    """Live format (MS_MDCT_DualFormat.raw_to_mel_spec): oracle restatement and the drop-in's shape helpers."""
+    from oracle import format_oracle as fo
+    from dualdiffusion_b200.modules.formats.ms_mdct_dual import MS_MDCT_DualFormat, MS_MDCT_DualFormatConfig
+    g = load_golden("ms_dual_small.pt")
+    assert rel_err(fo.raw_to_mel_spec(g["raw"], fo.MSDualSpec()), g["mel"]) < 1e-6
+    fmt = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig())
+    assert tuple(fmt.get_mel_spec_shape(3)) == tuple(g["mel_shape_default"])
+    assert fmt.get_raw_crop_width() == g["crop_default"]
+    assert torch.equal(fmt.ms_freq_scale.get_unscaled(34), g["unscaled_34"])
