@@ -33,7 +33,7 @@ class AffineDesc(C.Structure):
 EPI_NONE, EPI_SCALE_SILU, EPI_RESIDUAL = 0, 1, 2
 EPI2_NONE, EPI2_SILU, EPI2_SCALE = 0, 1, 2
 WFMT_BF16_OTI, WFMT_F32_OIT = 0, 1
-WPERM_NONE, WPERM_QK = 0, 1
+WPERM_NONE, WPERM_QK, WPERM_QKV = 0, 1, 2
 
 _SIGNATURES = {
     "dd_last_error": (C.c_char_p, []),
@@ -68,6 +68,7 @@ _SIGNATURES = {
     "dd_fgla_stft_update": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                     c_void_p, c_float, c_int, c_void_p]),
     "dd_ola_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "dd_attention_axis": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
     "dd_sampler_update": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                   c_int, c_long, c_void_p]),

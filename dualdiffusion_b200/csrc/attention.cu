@@ -52,9 +52,24 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
+// Addressing of one attention problem set.  A "sequence" is indexed by (outer, inner) = (blockIdx.z / n_inner,
+// blockIdx.z % n_inner); token t of it sits at  base + outer*outer_stride + inner*inner_stride + t*tok_stride
+// (element units), head h at + h*64.  Full-image attention: outer = batch item, n_inner = 1.  Axis attention of the
+// legacy ddec UNets (unets/old/unet_edm2_ddec_mdct_b3.py:146-163) folds the reference's
+// permute(0,2,4,1,3) -> reshape(b*z*w, ...) -> SDPA -> reshape -> permute(0,3,1,4,2) into these strides: nothing is
+// physically transposed, tokens along H are simply W*C elements apart in the channels_last_3d tensor.
+struct AttnLayout {
+    long q_tok, q_outer, q_inner;      // q and k share strides (k = q pointer + k_offset)
+    long v_tok, v_outer, v_inner;
+    long o_tok, o_outer, o_inner;
+    int n_inner;
+    int scale_div;                     // sequences per row of scale_v (scale row = blockIdx.z / scale_div)
+};
+
 __global__ void __launch_bounds__(kAttThreads)
-attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
-                 const float* __restrict__ scale_v, __nv_bfloat16* __restrict__ out, int N, int heads, int npad) {
+attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* __restrict__ k_ptr,
+                 const __nv_bfloat16* __restrict__ v_ptr, const float* __restrict__ scale_v,
+                 __nv_bfloat16* __restrict__ out, int N, int heads, int npad, const __grid_constant__ AttnLayout lay) {
     extern __shared__ __align__(16) uint8_t smem_att[];
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
@@ -63,14 +78,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __re
     __nv_bfloat16* Vs = Ks + (size_t)npad * kKStride;                          // [npad][kKStride]
     __nv_bfloat16* Qs = Vs + (size_t)npad * kKStride;                          // [kQTile][kKStride]
 
-    const int q0 = blockIdx.x * kQTile, head = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * kQTile, head = blockIdx.y;
+    const int outer = blockIdx.z / lay.n_inner, inner = blockIdx.z - outer * lay.n_inner;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int sub = tid & 7;          // which 8-channel slice of the head vector this lane loads
     const int tok_in_pass = tid >> 3; // 32 tokens per pass
 
-    const __nv_bfloat16* q_base = qk + (size_t)b * N * 2 * C + head * kD + sub * 8;
-    const __nv_bfloat16* k_base = q_base + C;
-    const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kD + sub * 8;
+    const size_t q_off = (size_t)outer * lay.q_outer + (size_t)inner * lay.q_inner + head * kD + sub * 8;
+    const __nv_bfloat16* q_base = q_ptr + q_off;
+    const __nv_bfloat16* k_base = k_ptr + q_off;
+    const __nv_bfloat16* v_base = v_ptr + (size_t)outer * lay.v_outer + (size_t)inner * lay.v_inner + head * kD + sub * 8;
 
     // Staging is latency-bound if every token's load is followed by its use: issue the loads of kStageBatch
     // tokens per thread first (one memory round trip per batch), then normalise and store them.
@@ -110,9 +127,9 @@ attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __re
             }
         }
     };
-    stage_rows(k_base, (size_t)2 * C, 0, npad, N, Ks);
-    stage_rows(v_base, (size_t)C, 0, npad, N, Vs);
-    stage_rows(q_base, (size_t)2 * C, q0, kQTile, N, Qs);
+    stage_rows(k_base, (size_t)lay.q_tok, 0, npad, N, Ks);
+    stage_rows(v_base, (size_t)lay.v_tok, 0, npad, N, Vs);
+    stage_rows(q_base, (size_t)lay.q_tok, q0, kQTile, N, Qs);
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
@@ -207,16 +224,32 @@ attention_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __re
     for (int r = 0; r < 2; ++r) {
         const int q = q0 + row0 + g + r * 8;
         if (q >= N) continue;
-        __nv_bfloat16* op = out + ((size_t)b * N + q) * C + head * kD;
-        const float* sc = scale_v + (size_t)b * C + head * kD;
+        __nv_bfloat16* op = out + (size_t)outer * lay.o_outer + (size_t)inner * lay.o_inner + (size_t)q * lay.o_tok + head * kD;
+        const float* sc = scale_v ? scale_v + (size_t)(blockIdx.z / lay.scale_div) * C + head * kD : nullptr;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
             const int d = n * 8 + 2 * t;
-            const float y0 = o[n][2 * r + 0] * inv_l[r] * __ldg(sc + d);
-            const float y1 = o[n][2 * r + 1] * inv_l[r] * __ldg(sc + d + 1);
+            const float y0 = o[n][2 * r + 0] * inv_l[r] * (sc ? __ldg(sc + d) : 1.f);
+            const float y1 = o[n][2 * r + 1] * inv_l[r] * (sc ? __ldg(sc + d + 1) : 1.f);
             *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_f(y0), mp_silu_f(y1));
         }
     }
+}
+
+int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const float* scale_v,
+                     __nv_bfloat16* out, int n_seq, int N, int heads, const AttnLayout& lay, cudaStream_t stream) {
+    const int npad = ceil_div(N, 64) * 64;
+    const size_t smem = ((size_t)2 * npad * kKStride + (size_t)kQTile * kKStride) * 2;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        DD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    DD_REQUIRE(n_seq <= 65535, "dd_attention: %d sequences exceed the grid limit", n_seq);
+    const dim3 grid(ceil_div(N, kQTile), heads, n_seq);
+    DD_CHECK_CUDA(dd_launch_pdl(attention_kernel, grid, dim3(kAttThreads), smem, stream, q, k, v, scale_v, out, N, heads,
+                                npad, lay));
+    return 0;
 }
 
 }  // namespace
@@ -227,16 +260,32 @@ extern "C" int dd_attention(const void* qk, const void* v, const float* scale_v,
     DD_REQUIRE(qk && v && scale_v && out, "dd_attention: null pointer");
     DD_REQUIRE(head_dim == kD, "dd_attention: head_dim=%d unsupported (64)", head_dim);
     DD_REQUIRE(N > 0 && N <= 640, "dd_attention: N=%d unsupported (1..640)", N);
-    const int npad = ceil_div(N, 64) * 64;
-    const size_t smem = ((size_t)2 * npad * kKStride + (size_t)kQTile * kKStride) * 2;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        DD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+    const long C = (long)heads * kD;
+    AttnLayout lay{2 * C, (long)N * 2 * C, 0, C, (long)N * C, 0, C, (long)N * C, 0, 1, 1};
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qk);
+    return launch_attention(q, q + C, static_cast<const __nv_bfloat16*>(v), scale_v, static_cast<__nv_bfloat16*>(out), B, N,
+                            heads, lay, stream);
+}
+
+extern "C" int dd_attention_axis(const void* qkv, void* out, int B, int Z, int H, int W, int heads, int head_dim, int axis,
+                                 void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(qkv && out, "dd_attention_axis: null pointer");
+    DD_REQUIRE(head_dim == kD, "dd_attention_axis: head_dim=%d unsupported (64)", head_dim);
+    DD_REQUIRE(axis == 0 || axis == 1, "dd_attention_axis: axis must be 0 (H) or 1 (W)");
+    const long C = (long)heads * kD, C3 = 3 * C;
+    const int N = axis == 0 ? H : W;
+    DD_REQUIRE(N > 0 && N <= 640, "dd_attention_axis: %d tokens unsupported (1..640)", N);
+    AttnLayout lay;
+    int n_seq;
+    if (axis == 0) {      // attend over H; (b, z) outer, w inner -- b3.py:146-148
+        lay = AttnLayout{(long)W * C3, (long)H * W * C3, C3, (long)W * C3, (long)H * W * C3, C3,
+                         (long)W * C, (long)H * W * C, C, W, 1};
+        n_seq = B * Z * W;
+    } else {              // attend over W; (b, z, h) outer
+        lay = AttnLayout{C3, (long)W * C3, 0, C3, (long)W * C3, 0, C, (long)W * C, 0, 1, 1};
+        n_seq = B * Z * H;
     }
-    const dim3 grid(ceil_div(N, kQTile), heads, B);
-    DD_CHECK_CUDA(dd_launch_pdl(attention_kernel, grid, dim3(kAttThreads), smem, stream,
-                                static_cast<const __nv_bfloat16*>(qk), static_cast<const __nv_bfloat16*>(v), scale_v,
-                                static_cast<__nv_bfloat16*>(out), N, heads, npad));
-    return 0;
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+    return launch_attention(q, q + C, q + 2 * C, nullptr, static_cast<__nv_bfloat16*>(out), n_seq, N, heads, lay, stream);
 }

@@ -54,6 +54,9 @@ __global__ void weight_prep_kernel(const void* __restrict__ w, void* __restrict_
     if (perm == DD_WPERM_QK) {
         const int head = o / (2 * head_dim), rem = o % (2 * head_dim);
         o_dst = (rem & 1) * (O / 2) + head * head_dim + (rem >> 1);
+    } else if (perm == DD_WPERM_QKV) {
+        const int head = o / (3 * head_dim), rem = o % (3 * head_dim);
+        o_dst = (rem % 3) * (O / 3) + head * head_dim + rem / 3;
     }
     if (out_format == DD_WFMT_BF16_OTI) {
         __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(out) + (size_t)o_dst * row_stride;
@@ -443,7 +446,8 @@ extern "C" int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_f
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(w && out && O > 0 && I_g > 0 && taps > 0, "dd_weight_prep: bad arguments");
     DD_REQUIRE(out_format == DD_WFMT_BF16_OTI || out_format == DD_WFMT_F32_OIT, "dd_weight_prep: bad out_format");
-    DD_REQUIRE(perm == DD_WPERM_NONE || (perm == DD_WPERM_QK && head_dim > 0 && O % (2 * head_dim) == 0),
+    DD_REQUIRE(perm == DD_WPERM_NONE || (perm == DD_WPERM_QK && head_dim > 0 && O % (2 * head_dim) == 0) ||
+                   (perm == DD_WPERM_QKV && head_dim > 0 && O % (3 * head_dim) == 0),
                "dd_weight_prep: bad permutation arguments");
     const int row_stride = out_row_stride > 0 ? out_row_stride : I_g * taps;
     DD_REQUIRE(row_stride >= I_g * taps, "dd_weight_prep: out_row_stride smaller than a row");

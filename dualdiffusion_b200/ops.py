@@ -39,7 +39,7 @@ def _is_bf16(t: Tensor) -> int:
 
 def weight_prep(w: Tensor, gain: Optional[Tensor] = None, gain_host: float = 1.0, normalize: bool = False,
                 fmt: int = L.WFMT_BF16_OTI, qk_head_dim: int = 0, out: Optional[Tensor] = None,
-                pad_rows: int = 0, row_stride: int = 0) -> Tensor:
+                pad_rows: int = 0, row_stride: int = 0, qkv_head_dim: int = 0) -> Tensor:
     """MPConv weight path (reference modules/mp_tools.py:359-364) fused into one pass."""
     L.require_cuda(w)
     w = w.contiguous()
@@ -56,9 +56,9 @@ def weight_prep(w: Tensor, gain: Optional[Tensor] = None, gain_host: float = 1.0
             out = torch.empty((O, taps, I_g), device=w.device, dtype=torch.bfloat16)
         else:
             out = torch.empty((O, I_g, taps), device=w.device, dtype=torch.float32)
-    perm = L.WPERM_QK if qk_head_dim else L.WPERM_NONE
+    perm = L.WPERM_QK if qk_head_dim else (L.WPERM_QKV if qkv_head_dim else L.WPERM_NONE)
     L.check(L.load().dd_weight_prep(L.ptr(w), _is_bf16(w), L.ptr(out), fmt, O, I_g, taps, L.ptr(gain), gain_host,
-                                    int(normalize), perm, qk_head_dim, row_stride, L.stream_ptr()))
+                                    int(normalize), perm, qk_head_dim or qkv_head_dim, row_stride, L.stream_ptr()))
     _count()
     return out
 
@@ -283,5 +283,14 @@ def ola_finalize(ola: Tensor, env: Tensor, n_fft: int, length: int) -> Tensor:
     S = ola.shape[0]
     out = torch.empty((S, length), device=ola.device, dtype=torch.float32)
     L.check(L.load().dd_ola_finalize(L.ptr(ola), L.ptr(env), S, ola.shape[-1], n_fft, length, L.ptr(out), L.stream_ptr()))
+    _count()
+    return out
+
+
+def attention_axis(qkv: Tensor, heads: int, axis: int, head_dim: int = 64) -> Tensor:
+    """Axis attention on a channels_last_3d tensor [B, Z, H, W, 3C] (q|k|v thirds) -> [B, Z, H, W, C]."""
+    B, Z, H, W, C3 = qkv.shape
+    out = torch.empty((B, Z, H, W, C3 // 3), device=qkv.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_attention_axis(L.ptr(qkv), L.ptr(out), B, Z, H, W, heads, head_dim, axis, L.stream_ptr()))
     _count()
     return out

@@ -53,6 +53,7 @@ DD_API int dd_device_info(int* num_sms, int* cc_major, int* cc_minor);
 #define DD_WFMT_F32_OIT 1
 #define DD_WPERM_NONE 0
 #define DD_WPERM_QK 1
+#define DD_WPERM_QKV 2   /* row (head*3*d + 3*c + j) -> row (j*O/3 + head*d + c)  (old/unet_edm2_ddec_mdct_b3.py:149-150) */
 /* out_row_stride (elements, 0 = dense I_g*taps) lets rows be written into a wider, zero-initialised buffer
  * (K padded to 64 for the stem GEMM; Cout padded to 16 rows for the head GEMM).                    */
 DD_API int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_format, int O, int I_g, int taps,
@@ -154,6 +155,14 @@ DD_API int dd_axpby(const void* a, const void* b, float alpha, float beta, float
  * head_dim (eps 1e-4), softmax(q k^T / sqrt(head_dim)) v, then out = mp_silu(y * scale_v[b][c]).     */
 DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, void* out, int B, int N, int heads,
                  int head_dim, void* stream);
+
+/* Axis ("separable") attention of the legacy ddec UNets, modules/unets/old/unet_edm2_ddec_mdct_b3.py:144-163:
+ * qkv [B][Z][H][W][3C] (channels_last_3d, q|k|v thirds after DD_WPERM_QKV), attention over H (axis 0, sequences
+ * (b,z,w)) or W (axis 1, sequences (b,z,h)); out [B][Z][H][W][C] = mp_silu(attention).  The reference's
+ * permute -> reshape(b*z*w, heads, d, 3, h) -> SDPA -> reshape -> permute round trip is folded into the kernel's
+ * token / sequence strides: no tensor is physically permuted.                                               */
+DD_API int dd_attention_axis(const void* qkv, void* out, int B, int Z, int H, int W, int heads, int head_dim, int axis,
+                             void* stream);
 
 /* ---- mel-STFT encode / FGLA decode: modules/formats/old/spectrogram.py:176-238 ------------- */
 /* Shared conventions: n_fft in {6400, 4096} (compile-time mixed-radix plans), win_length == n_fft, center=True with

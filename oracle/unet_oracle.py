@@ -398,3 +398,21 @@ def small_spec() -> UNetSpec:
     but builds and runs on CPU in well under a second."""
     return UNetSpec(model_channels=256, channel_mult=(1, 2), channel_mult_noise=1, channel_mult_emb=2,
                     num_layers_per_block=1, attn_levels=(1,), in_channels_emb=64, logvar_channels=32)
+
+
+# --------------------------------------------------------------------------------------
+# axis ("separable") attention of the legacy ddec UNets
+# (modules/unets/old/unet_edm2_ddec_mdct_b3.py:144-163) -- the only row/col <-> batch reshape in the reference
+# --------------------------------------------------------------------------------------
+def axis_attention_b3(qkv: Tensor, heads: int) -> Tensor:
+    """qkv (b, 3c, z, h, w) with channel index (head, d, j in {q,k,v}); attention over h with (b, z, w) folded into
+    the batch; returns y (b, c, z, h, w) BEFORE the block's mp_silu / attn_proj.  Statement by statement as :146-160."""
+    b, c3, z, h, w = qkv.shape
+    x = qkv.permute(0, 2, 4, 1, 3)                                        # b z w c h   (:148)
+    x = x.reshape(b * z * w, heads, -1, 3, h)                             # (:149)
+    q, k, v = normalize(x, dim=2).unbind(3)                               # (:150)
+    d = q.shape[2]
+    s = torch.einsum("nhdq,nhdk->nhqk", q.float(), k.float()) / math.sqrt(d)
+    y = torch.einsum("nhqk,nhdk->nhdq", torch.softmax(s, dim=-1), v.float())      # SDPA on transposed views (:152-154)
+    y = y.reshape(b, z, w, c3 // 3, h)                                    # (:157)
+    return y.permute(0, 3, 1, 4, 2)                                       # b c z h w   (:159)

@@ -545,3 +545,61 @@ def test_unet_uses_format_frequency_scale(dev):
     emb = net.get_embeddings(g["clap"], g["mask"])
     d = net(g["x"].to(dev), g["sigma"].to(dev), MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig()), emb)
     assert rel_err(d, g["d"]) < BF16_NET
+
+
+# ------------------------------------------------------------------------------------------
+# axis attention: the row/col <-> batch reshape folded into kernel addressing
+# ------------------------------------------------------------------------------------------
+def _qkv_thirds(qkv_ref_layout, heads):
+    """(b, 3c, z, h, w) with channels (head, d, j) -> (b, z, h, w, 3c) channels_last_3d with q|k|v thirds: the
+    re-ordering DD_WPERM_QKV applies to the rows of attn_qkv's weight."""
+    b, c3, z, h, w = qkv_ref_layout.shape
+    x = qkv_ref_layout.view(b, heads, c3 // (3 * heads), 3, z, h, w).permute(0, 3, 1, 2, 4, 5, 6).reshape(b, c3, z, h, w)
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def test_axis_attention_vs_oracle(dev):
+    from dualdiffusion_b200 import ops
+    gen = torch.Generator().manual_seed(47)
+    b, heads, z, h, w = 2, 2, 2, 24, 5
+    c = heads * 64
+    qkv = bf16_round(torch.randn(b, 3 * c, z, h, w, generator=gen) * 2)
+    ref = uo.mp_silu(uo.axis_attention_b3(qkv, heads))                           # (b, c, z, h, w)
+    got = ops.attention_axis(_qkv_thirds(qkv, heads).to(device=dev, dtype=torch.bfloat16), heads, axis=0)
+    assert got.shape == (b, z, h, w, c)
+    assert rel_err(got.float().cpu().permute(0, 4, 1, 2, 3), ref) < 3 * BF16_OP
+
+
+def test_axis_attention_reshape_indexing_is_bit_exact(dev):
+    """North star: 'bit-exact for the row/col reshape indexing'.  The same attention arithmetic is run twice:
+    (a) as the reference does it -- physically permute to (b*z*w, h, c), attend, permute back (b3.py:148-159) --
+    through dd_attention on the permuted copies, and (b) in place through dd_attention_axis, where the permutes
+    are strides.  The two results must be bit-identical."""
+    from dualdiffusion_b200 import ops
+    gen = torch.Generator().manual_seed(53)
+    for axis, (b, heads, z, h, w) in ((0, (2, 3, 2, 40, 7)), (1, (1, 2, 2, 6, 70))):
+        c = heads * 64
+        qkv = (torch.randn(b, z, h, w, 3 * c, generator=gen) * 2).to(device=dev, dtype=torch.bfloat16)
+        got = ops.attention_axis(qkv, heads, axis=axis)
+        if axis == 0:      # sequences (b, z, w), tokens h
+            seq = qkv.permute(0, 1, 3, 2, 4).reshape(b * z * w, h, 1, 3 * c)
+        else:              # sequences (b, z, h), tokens w
+            seq = qkv.reshape(b * z * h, w, 1, 3 * c)
+        qk = seq[..., :2 * c].contiguous()
+        v = seq[..., 2 * c:].contiguous()
+        ones = torch.ones(seq.shape[0], c, device=dev)
+        y = ops.attention(qk, v, ones, heads)                                   # [n_seq, tokens, 1, c]
+        if axis == 0:
+            y = y.reshape(b, z, w, h, c).permute(0, 1, 3, 2, 4)
+        else:
+            y = y.reshape(b, z, h, w, c)
+        assert torch.equal(got, y.contiguous())
+
+
+def test_qkv_deinterleave_is_bit_exact(dev):
+    from dualdiffusion_b200 import ops
+    heads, d, cin = 2, 64, 32
+    w = (torch.arange(heads * d * 3 * cin, dtype=torch.float32) % 251).view(heads * d * 3, cin, 1, 1, 1)
+    got = ops.weight_prep(w.view(heads * d * 3, cin, 1, 1).to(dev), gain_host=math.sqrt(cin), qkv_head_dim=d)
+    ref = w.view(heads, d, 3, cin).permute(2, 0, 1, 3).reshape(3 * heads * d, 1, cin)
+    assert torch.equal(got.float().cpu(), ref)
