@@ -15,15 +15,22 @@
 
 namespace {
 
-constexpr int kEncFrames = 32;      // frames per CTA in the encoder (one 128 B output row segment per filter)
-constexpr int kOlaFrames = 32;      // frames per CTA in the inverse STFT (overlap-add accumulated in shared memory)
+constexpr int kEncFrames = 32;      // frames per CTA in the FGLA forward STFT
+constexpr int kMelFrames = 16;      // frames per CTA in the encoder (one 64 B output row segment per filter)
+constexpr int kOlaFrames = 64;      // frames per CTA in the inverse STFT (overlap-add ring in shared memory)
 
-// Shared-memory FFT buffers are padded by one element every 8 (index i -> i + i/8): the first Stockham passes
-// scatter with a stride of `radix` elements, which would otherwise be a 16-way bank conflict on 8-byte elements.
-__host__ __device__ constexpr int pad_idx(int i) { return i + (i >> 3); }
+// Shared-memory FFT buffers are XOR-swizzled inside aligned groups of 16 complex values: every Stockham pass
+// reads contiguous runs (conflict-free under any in-group permutation) and scatters with strides 8 / 64 / 320,
+// which the two XOR terms spread over all 16 eight-byte bank pairs (searched offline over the access patterns of
+// both plans; the earlier `i + i/8` padding cost one extra wavefront on every contiguous access -- ncu showed 47%
+// of all shared wavefronts were excess).
+__host__ __device__ constexpr int swz(int i) { return i ^ (((i >> 4) & 15) ^ (((i >> 4) & 4) << 1)); }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float wr, float wi) {
+    return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -50,9 +57,9 @@ __device__ __forceinline__ void butterfly<8>(float2 (&v)[8]) {
     dft4(e0, e1, e2, e3);
     dft4(o0, o1, o2, o3);
     const float h = 0.70710678118654752f;
-    o1 = cmul(o1, make_float2(h, -h));          // w8^1
+    o1 = cmulc(o1, h, -h);                      // w8^1
     o2 = mul_neg_i(o2);                         // w8^2
-    o3 = cmul(o3, make_float2(-h, -h));         // w8^3
+    o3 = cmulc(o3, -h, -h);                     // w8^3
     v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
     v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
     v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
@@ -75,27 +82,42 @@ __device__ __forceinline__ void butterfly<5>(float2 (&v)[5]) {
     v[1] = cadd(r1, q1); v[4] = csub(r1, q1);
     v[2] = cadd(r2, q2); v[3] = csub(r2, q2);
 }
+template <>
+__device__ __forceinline__ void butterfly<10>(float2 (&v)[10]) {
+    // 10 = 5 x 2 in registers: X[k1 + 5 k2] = E[k1] + (-1)^k2 w10^k1 O[k1]
+    float2 e[5] = {v[0], v[2], v[4], v[6], v[8]}, o[5] = {v[1], v[3], v[5], v[7], v[9]};
+    butterfly<5>(e);
+    butterfly<5>(o);
+    o[1] = cmulc(o[1], 0.80901699437494742f, -0.58778525229247313f);
+    o[2] = cmulc(o[2], 0.30901699437494742f, -0.95105651629515357f);
+    o[3] = cmulc(o[3], -0.30901699437494742f, -0.95105651629515357f);
+    o[4] = cmulc(o[4], -0.80901699437494742f, -0.58778525229247313f);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { v[k] = cadd(e[k], o[k]); v[k + 5] = csub(e[k], o[k]); }
+}
 
 // Compile-time FFT plans (complex length N = n_fft/2, T threads per frame).  Everything that depends on the plan
 // -- radices, strides, twiddle steps, loop trip counts -- folds into immediates: the first, runtime-planned version
 // of these kernels spent ~230 instructions per complex element on index arithmetic.
 template <int N> struct Plan;
 template <> struct Plan<3200> {            // n_fft 6400 = 2^8 * 5^2 (reference SpectrogramFormat)
-    static constexpr int kThreads = 320, kStages = 5;
-    static constexpr int radix(int s) { return s == 0 ? 8 : s == 1 ? 8 : s == 2 ? 5 : s == 3 ? 5 : 2; }
+    static constexpr int kThreads = 320, kStages = 4;
+    static constexpr int radix(int s) { return s == 0 ? 8 : s == 1 ? 8 : s == 2 ? 5 : 10; }
 };
 template <> struct Plan<2048> {            // n_fft 4096 (live MS_MDCT_DualFormat windows)
     static constexpr int kThreads = 256, kStages = 4;
     static constexpr int radix(int s) { return s == 0 ? 8 : s == 1 ? 8 : s == 2 ? 8 : 4; }
 };
 
-// One Stockham autosort pass of radix R with NS = product of the previous radices: in -> out (both padded).
-// `tws` is the shared-memory half table exp(-2 pi i m / N), m < N/2 (the other half is its negation): with most
-// of the SM's SRAM carved out as shared memory there is next to no L1 left, and __ldg twiddles came from L2.
+// One Stockham autosort pass of radix R with NS = product of the previous radices: in -> out (both swizzled).
+// `tws` is the shared-memory half table exp(-2 pi i m / N), m < N/2: with most of the SM's SRAM carved out as
+// shared memory there is next to no L1 left, and __ldg twiddles came from L2.  Only w^k and w^2k are loaded
+// (their indices stay below N/2 for R >= 4); the higher powers are products at most two multiplications deep --
+// the strided table reads of w^(rk) were 2- to 8-way bank-conflicted.
 template <int N, int T, int R, int NS>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out,
                                               const float2* __restrict__ tws) {
-    constexpr int NB = N / R, HALF = N / 2, STEP = N / (NS * R);
+    constexpr int NB = N / R, STEP = N / (NS * R);
     constexpr int ITERS = (NB + T - 1) / T;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -104,20 +126,23 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
         const int k = (NS & (NS - 1)) == 0 ? (j & (NS - 1)) : (NS >= NB ? j : (T % NS == 0 ? (int)threadIdx.x % NS : j % NS));
         float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = in[pad_idx(j + r * NB)];
+        for (int r = 0; r < R; ++r) v[r] = in[swz(j + r * NB)];
         if (NS > 1) {
+            float2 w[R];
+            w[1] = tws[k * STEP];
+            if constexpr (R > 2) w[2] = tws[2 * k * STEP];
 #pragma unroll
-            for (int r = 1; r < R; ++r) {
-                const int idx = r * k * STEP;                       // < N
-                float2 w = tws[idx < HALF ? idx : idx - HALF];
-                if (idx >= HALF) { w.x = -w.x; w.y = -w.y; }
-                v[r] = cmul(v[r], w);
+            for (int r = 3; r < R; ++r) {
+                const int a = r == 3 ? 1 : r == 4 ? 2 : r < 9 ? 4 : 8;
+                w[r] = cmul(w[a], w[r - a]);
             }
+#pragma unroll
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], w[r]);
         }
         butterfly<R>(v);
         const int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[pad_idx(j0 + r * NS)] = v[r];
+        for (int r = 0; r < R; ++r) out[swz(j0 + r * NS)] = v[r];
     }
 }
 
@@ -134,7 +159,8 @@ __device__ __forceinline__ float2* fft_stages(float2* src, float2* dst, const fl
     }
 }
 
-// Forward complex FFT of length N on (padded) shared memory.  Returns the buffer holding the result.
+// Forward complex FFT of length N on (swizzled) shared memory.  Returns the buffer holding the result; the last
+// pass is followed by a barrier.
 template <int N>
 __device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const float2* tws) {
     return fft_stages<N, 0, 1>(a, b, tws);
@@ -153,25 +179,25 @@ __device__ __forceinline__ int reflect_index(int j, int len) {
     return j;
 }
 
-// Windowed frame `t` of a (reflect-padded, centred) signal packed as n_fft/2 complex values, then the real-input
-// FFT.  src(j) returns sample j of the un-padded signal.  On return spec[0..n] (n+1 bins) holds the one-sided
-// spectrum; `other` is the second scratch buffer.  Both buffers hold n+1 float2.
+// Windowed frame `t` of a (reflect-padded, centred) signal packed as n_fft/2 complex values into `in`, then the
+// half-length complex FFT.  src(j) returns sample j of the un-padded signal.  Returns the buffer holding Z
+// (swizzled); the caller unpacks the real-input spectrum from it with spectrum_pairs().  No barrier is needed
+// between a caller's use of the previous frame's Z and this call as long as `in` is the buffer NOT holding it.
 template <int N, typename SrcFn>
-__device__ __forceinline__ float2* stft_frame(int t, int hop, int len, SrcFn src,
-                                              const float* __restrict__ window, const float2* tw, const float2* tw_half,
-                                              float2* a, float2* b) {
-    constexpr int n = N;
+__device__ __forceinline__ float2* stft_fft(int t, int hop, int len, SrcFn src, const float* __restrict__ window,
+                                            const float2* tws, float2* in, float2* other) {
+    constexpr int n = N, T = Plan<N>::kThreads;
     const int p0 = t * hop - n;                       // first padded-domain sample of the frame, relative to signal
     const float2* w2 = reinterpret_cast<const float2*>(window);
     // loads are issued in batches of kGather per thread before any use: one memory round trip per batch
     // instead of one per element (the frame loop is latency-bound otherwise -- measured)
     constexpr int kGather = 5;
-    for (int base = threadIdx.x; base < n; base += kGather * blockDim.x) {
+    for (int base = threadIdx.x; base < n; base += kGather * T) {
         float x0[kGather], x1[kGather];
         float2 w[kGather];
 #pragma unroll
         for (int u = 0; u < kGather; ++u) {
-            const int m = base + u * blockDim.x;
+            const int m = base + u * T;
             if (m < n) {
                 x0[u] = src(reflect_index(p0 + 2 * m, len));
                 x1[u] = src(reflect_index(p0 + 2 * m + 1, len));
@@ -180,44 +206,57 @@ __device__ __forceinline__ float2* stft_frame(int t, int hop, int len, SrcFn src
         }
 #pragma unroll
         for (int u = 0; u < kGather; ++u) {
-            const int m = base + u * blockDim.x;
-            if (m < n) a[pad_idx(m)] = make_float2(x0[u] * w[u].x, x1[u] * w[u].y);
+            const int m = base + u * T;
+            if (m < n) in[swz(m)] = make_float2(x0[u] * w[u].x, x1[u] * w[u].y);
         }
     }
     __syncthreads();
-    float2* z = fft_forward<N>(a, b, tw);
-    float2* o = (z == a) ? b : a;
-    // X[k] = (Z[k] + conj(Z[n-k]))/2 - (i/2) e^{-2 pi i k/(2n)} (Z[k] - conj(Z[n-k])),  k = 0..n  (Z[n] == Z[0])
-    // (z is padded, the spectrum o is written densely)
-    constexpr int kPost = 6;
-    for (int base = threadIdx.x; base <= n; base += kPost * blockDim.x) {
+    return fft_forward<N>(in, other, tws);
+}
+
+// Real-input spectrum from the half-length FFT Z, two bins per step:
+//   X[k]   = E + (-i) D w_k,  X[n-k] = conj(E) - i conj(D w_k),   E = (Z[k] + conj(Z[n-k]))/2, D = (Z[k] - conj(Z[n-k]))/2,
+//   w_k = e^{-2 pi i k/(2n)}  (w_{n-k} = -conj(w_k)),  Z[n] == Z[0];  k = 0 yields X[0] and X[n] (DC / Nyquist).
+// pre(k) is fetched for a whole batch before any arithmetic (global operands of the sink, e.g. the previous
+// Griffin-Lim state); sink(k, X[k], pre(k)) consumes each bin -- nothing is staged through shared memory.
+template <int N, typename PreFn, typename SinkFn>
+__device__ __forceinline__ void spectrum_pairs(const float2* z, const float2* __restrict__ tw_half, PreFn pre, SinkFn sink) {
+    constexpr int n = N, T = Plan<N>::kThreads, HALFN = N / 2;
+    constexpr int kPost = 5;
+    using PreT = decltype(pre(0));
+    for (int base = threadIdx.x; base < HALFN; base += kPost * T) {
         float2 wh[kPost];
+        PreT pa[kPost], pb[kPost];
 #pragma unroll
         for (int u = 0; u < kPost; ++u) {
-            const int k = base + u * blockDim.x;
-            if (k <= n) wh[u] = __ldg(tw_half + k);
+            const int k = base + u * T;
+            if (k < HALFN) { wh[u] = __ldg(tw_half + k); pa[u] = pre(k); pb[u] = pre(n - k); }
         }
 #pragma unroll
         for (int u = 0; u < kPost; ++u) {
-            const int k = base + u * blockDim.x;
-            if (k <= n) {
-                const float2 zk = z[pad_idx(k == n ? 0 : k)];
-                const float2 zc = z[pad_idx(k == 0 ? 0 : n - k)];
+            const int k = base + u * T;
+            if (k < HALFN) {
+                const float2 zk = z[swz(k)];
+                const float2 zc = z[swz(k == 0 ? 0 : n - k)];
                 const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
                 const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
-                o[k] = cadd(e, cmul(mul_neg_i(d), wh[u]));
+                const float2 q = cmul(d, wh[u]);
+                sink(k, make_float2(e.x + q.y, e.y - q.x), pa[u]);
+                sink(n - k, make_float2(e.x - q.y, -e.y - q.x), pb[u]);
             }
         }
     }
-    __syncthreads();
-    return o;
+    if (threadIdx.x == 0) {                           // k = n/2 pairs with itself: w = -i, X = conj(Z[n/2])
+        const float2 zk = z[swz(HALFN)];
+        sink(HALFN, make_float2(zk.x, -zk.y), pre(HALFN));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
 // mel-STFT encoder
 // ------------------------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(Plan<N>::kThreads)
+__global__ void __launch_bounds__(Plan<N>::kThreads, 2)
 stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict__ window,
                 const float* __restrict__ window2, const float* __restrict__ coef1, const float* __restrict__ coef2,
                 const float2* __restrict__ tw, const float2* __restrict__ tw_half, int hop, int n_frames,
@@ -226,169 +265,200 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
                 float* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_fft[];
     constexpr int n = N;
-    constexpr int buf = pad_idx(n) + 8;
     float2* a = reinterpret_cast<float2*>(smem_fft);
-    float2* b = a + buf;
-    float2* tws = b + buf;                                        // [n/2] twiddle half table
+    float2* b = a + n;
+    float2* tws = b + n;                                          // [n/2] twiddle half table
     float* mag = reinterpret_cast<float*>(tws + n / 2);           // [n + 8] blended magnitudes
-    float* tile = mag + n + 8;                                    // [n_filters][kEncFrames + 1]
+    float* tile = mag + n + 8;                                    // [n_filters][kMelFrames + 1]
     load_twiddles<N>(tws, tw);
     const int s = blockIdx.y;
-    const int t0 = blockIdx.x * kEncFrames;
+    const int t0 = blockIdx.x * kMelFrames;
     const float* sig = raw + (size_t)s * len;
-    for (int f = 0; f < kEncFrames; ++f) {
+    auto src = [&](int j) { return __ldg(sig + j); };
+    float2* in = a;
+    for (int f = 0; f < kMelFrames; ++f) {
         const int t = t0 + f;
         if (t >= n_frames) break;
         // |STFT| with the first window (times an optional per-bin coefficient); the live MS_MDCT_DualFormat blends a
-        // second, narrower-window STFT per bin (ms_mdct_dual.py:249-256): mag = |X1|*coef1 + |X2|*coef2
-        float2* spec = stft_frame<N>(t, hop, len, [&](int j) { return __ldg(sig + j); }, window, tws, tw_half, a, b);
-        for (int k = threadIdx.x; k <= n; k += blockDim.x) {
-            const float m1 = sqrtf(spec[k].x * spec[k].x + spec[k].y * spec[k].y);
-            mag[k] = coef1 ? m1 * __ldg(coef1 + k) : m1;
+        // second, narrower-window STFT per bin (ms_mdct_dual.py:249-256): mag = |X1|*coef1 + |X2|*coef2.  A bin is
+        // handled by the same thread in both passes, so the accumulation needs no barrier.
+        {
+            float2* other = (in == a) ? b : a;
+            const float2* z = stft_fft<N>(t, hop, len, src, window, tws, in, other);
+            spectrum_pairs<N>(z, tw_half, [&](int k) { return coef1 ? __ldg(coef1 + k) : 1.f; },
+                              [&](int k, float2 x, float c) { mag[k] = sqrtf(x.x * x.x + x.y * x.y) * c; });
+            in = (z == a) ? b : a;
+        }
+        if (window2) {
+            float2* other = (in == a) ? b : a;
+            const float2* z = stft_fft<N>(t, hop, len, src, window2, tws, in, other);
+            spectrum_pairs<N>(z, tw_half, [&](int k) { return __ldg(coef2 + k); },
+                              [&](int k, float2 x, float c) { mag[k] += sqrtf(x.x * x.x + x.y * x.y) * c; });
+            in = (z == a) ? b : a;
         }
         __syncthreads();
-        if (window2) {
-            spec = stft_frame<N>(t, hop, len, [&](int j) { return __ldg(sig + j); }, window2, tws, tw_half, a, b);
-            for (int k = threadIdx.x; k <= n; k += blockDim.x)
-                mag[k] += sqrtf(spec[k].x * spec[k].x + spec[k].y * spec[k].y) * __ldg(coef2 + k);
-            __syncthreads();
-        }
         for (int m = threadIdx.x; m < n_filters; m += blockDim.x) {
             const int st = fb_start[m], cnt = fb_count[m], off = fb_offset[m];
             float acc = 0.f;
             for (int j = 0; j < cnt; ++j) acc += mag[st + j] * __ldg(fb_weight + off + j);
             const float v = (exponent == 0.25f) ? sqrtf(sqrtf(acc)) : (exponent == 1.f ? acc : powf(acc, exponent));
-            tile[m * (kEncFrames + 1) + f] = (v - mean) * scale;
+            tile[m * (kMelFrames + 1) + f] = (v - mean) * scale;
         }
-        __syncthreads();
+        // the next frame's first write to `mag` sits behind its gather + FFT barriers
     }
-    const int nf = min(kEncFrames, n_frames - t0);
-    for (int i = threadIdx.x; i < n_filters * kEncFrames; i += blockDim.x) {
-        const int m = i / kEncFrames, f = i % kEncFrames;
-        if (f < nf) out[((size_t)s * n_filters + m) * n_frames + t0 + f] = tile[m * (kEncFrames + 1) + f];
+    __syncthreads();
+    const int nf = min(kMelFrames, n_frames - t0);
+    for (int i = threadIdx.x; i < n_filters * kMelFrames; i += blockDim.x) {
+        const int m = i / kMelFrames, f = i % kMelFrames;
+        if (f < nf) out[((size_t)s * n_filters + m) * n_frames + t0 + f] = tile[m * (kMelFrames + 1) + f];
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // FGLA phase A: A = T/(|T|+1e-16); X = A * M_k; inverse STFT frame, window, overlap-add
 // ------------------------------------------------------------------------------------------
+struct FglaBin { float2 t; float m, mo; };
+
 template <int N>
-__global__ void __launch_bounds__(Plan<N>::kThreads)
+__global__ void __launch_bounds__(Plan<N>::kThreads, 2)
 fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ mag, int stereo, float interp_t,
                   const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw_half,
                   int hop, int n_frames, float* __restrict__ ola, int ola_len) {
     extern __shared__ __align__(16) uint8_t smem_fft[];
-    constexpr int n = N, bins = N + 1;
-    constexpr int buf = pad_idx(n) + 8;
+    constexpr int n = N, bins = N + 1, T = Plan<N>::kThreads, HALFN = N / 2, RING = 2 * N;
     float2* a = reinterpret_cast<float2*>(smem_fft);
-    float2* b = a + buf;
-    float2* tws = b + buf;                                        // [n/2] twiddle half table
-    float* acc = reinterpret_cast<float*>(tws + n / 2);           // [(kOlaFrames-1)*hop + 2n]
+    float2* b = a + n;
+    float2* tws = b + n;                                          // [n/2] twiddle half table
+    float* ring = reinterpret_cast<float*>(tws + n / 2);          // [2n] overlap-add ring: sample p lives at p % 2n
     load_twiddles<N>(tws, tw);
-    const int span = (kOlaFrames - 1) * hop + 2 * n;
     const int s = blockIdx.y;
     const int t0 = blockIdx.x * kOlaFrames;
-    for (int i = threadIdx.x; i < span; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
+    const int nf = min(kOlaFrames, n_frames - t0);
+    for (int i = threadIdx.x; i < RING; i += T) ring[i] = 0.f;
+    // (ordered before the first accumulation by the barriers of the first frame)
     const float inv_n = 1.f / (float)n;
-    for (int f = 0; f < kOlaFrames; ++f) {
+    float* g = ola + (size_t)s * ola_len + (size_t)t0 * hop;      // global position of this CTA's local sample 0
+
+    // X[k] = angle * magnitude  (phase_recovery.py:84-95)
+    auto load_bin = [&](size_t row, size_t row_other, int k) {
+        FglaBin v;
+        v.m = __ldg(mag + row + k);
+        v.mo = stereo ? __ldg(mag + row_other + k) : 0.f;
+        v.t = state ? __ldg(state + row + k) : make_float2(1.f, 0.f);
+        return v;
+    };
+    auto make_x = [&](const FglaBin& v, int k) {
+        float m = v.m;
+        if (stereo) {
+            const float merged = 0.5f * (m + v.mo);                                // :63-64 (L+R)/2
+            m = interp_t > 0.f ? merged + interp_t * (m - merged) : merged;        // :86-88 lerp(merged, spec, t)
+        }
+        float2 ang = v.t;
+        if (state) {
+            const float inv = 1.f / (sqrtf(ang.x * ang.x + ang.y * ang.y) + 1e-16f);   // :115
+            ang = make_float2(ang.x * inv, ang.y * inv);
+        }
+        float2 x = make_float2(ang.x * m, ang.y * m);
+        if (k == 0 || k == n) x.y = 0.f;        // C2R transforms ignore the imaginary part of DC / Nyquist
+        return x;
+    };
+    // conj(Z[k]) and conj(Z[n-k]) of the packed half-length spectrum Z = E + iO from the bin pair (X[k], X[n-k]):
+    // E = (X[k] + conj(X[n-k]))/2, O = e^{+2 pi i k/(2n)} (X[k] - conj(X[n-k]))/2; Z[n-k] = conj(E) + i conj(O).
+    // The inverse FFT runs through the forward one: IFFT(Z) = conj(FFT(conj(Z))) / n.
+    auto pack_pair = [&](float2 xk, float2 xc, float2 wh, float2& zk, float2& zc) {
+        const float2 e = make_float2(0.5f * (xk.x + xc.x), 0.5f * (xk.y - xc.y));
+        const float2 d = make_float2(0.5f * (xk.x - xc.x), 0.5f * (xk.y + xc.y));
+        const float2 o = cmul(d, make_float2(wh.x, -wh.y));
+        zk = make_float2(e.x - o.y, -(e.y + o.x));
+        zc = make_float2(e.x + o.y, e.y - o.x);
+    };
+
+    float2* in = a;
+    for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
-        if (t >= n_frames) break;
         const size_t row = ((size_t)s * n_frames + t) * bins;
         const size_t row_other = ((size_t)(s ^ 1) * n_frames + t) * bins;
-        // X[k] = angle * magnitude  (phase_recovery.py:84-95); stored in b.  Loads batched kBatch per thread.
-        constexpr int kBatch = 6;
-        for (int base = threadIdx.x; base < bins; base += kBatch * blockDim.x) {
-            float2 tv[kBatch];
-            float m0[kBatch], m1[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int k = base + u * blockDim.x;
-                if (k < bins) {
-                    m0[u] = __ldg(mag + row + k);
-                    m1[u] = stereo ? __ldg(mag + row_other + k) : 0.f;
-                    tv[u] = state ? __ldg(state + row + k) : make_float2(1.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int k = base + u * blockDim.x;
-                if (k < bins) {
-                    float m = m0[u];
-                    if (stereo) {
-                        const float merged = 0.5f * (m + m1[u]);                           // :63-64 (L+R)/2
-                        m = interp_t > 0.f ? merged + interp_t * (m - merged) : merged;    // :86-88 lerp(merged, spec, t)
-                    }
-                    float2 ang = tv[u];
-                    if (state) {
-                        const float inv = 1.f / (sqrtf(ang.x * ang.x + ang.y * ang.y) + 1e-16f);   // :115
-                        ang = make_float2(ang.x * inv, ang.y * inv);
-                    }
-                    float2 x = make_float2(ang.x * m, ang.y * m);
-                    if (k == 0 || k == n) x.y = 0.f;    // C2R transforms ignore the imaginary part of DC / Nyquist
-                    b[k] = x;
-                }
-            }
-        }
-        __syncthreads();
-        // Z[k] = E[k] + i O[k], E = (X[k] + conj(X[n-k]))/2, O = e^{+2 pi i k/(2n)} (X[k] - conj(X[n-k]))/2;
-        // inverse FFT through the forward one: IFFT(Z) = conj(FFT(conj(Z))) / n  ->  a holds conj(Z)
-        for (int base = threadIdx.x; base < n; base += kBatch * blockDim.x) {
+        constexpr int kBatch = 5;
+        for (int base = threadIdx.x; base < HALFN; base += kBatch * T) {
+            FglaBin vk[kBatch], vc[kBatch];
             float2 wh[kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int k = base + u * blockDim.x;
-                if (k < n) wh[u] = __ldg(tw_half + k);
+                const int k = base + u * T;
+                if (k < HALFN) {
+                    vk[u] = load_bin(row, row_other, k);
+                    vc[u] = load_bin(row, row_other, n - k);
+                    wh[u] = __ldg(tw_half + k);
+                }
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int k = base + u * blockDim.x;
-                if (k < n) {
-                    const float2 xk = b[k], xc = b[n - k];
-                    const float2 e = make_float2(0.5f * (xk.x + xc.x), 0.5f * (xk.y - xc.y));
-                    const float2 d = make_float2(0.5f * (xk.x - xc.x), 0.5f * (xk.y + xc.y));
-                    const float2 o = cmul(d, make_float2(wh[u].x, -wh[u].y));
-                    a[pad_idx(k)] = make_float2(e.x - o.y, -(e.y + o.x));               // conj(E + iO)
+                const int k = base + u * T;
+                if (k < HALFN) {
+                    float2 zk, zc;
+                    pack_pair(make_x(vk[u], k), make_x(vc[u], n - k), wh[u], zk, zc);
+                    in[swz(k)] = zk;
+                    if (k > 0) in[swz(n - k)] = zc;
                 }
             }
         }
+        if (threadIdx.x == 0) {                       // k = n/2 pairs with itself
+            const float2 x = make_x(load_bin(row, row_other, HALFN), HALFN);
+            float2 zk, zc;
+            pack_pair(x, x, __ldg(tw_half + HALFN), zk, zc);
+            in[swz(HALFN)] = zk;
+        }
         __syncthreads();
-        const float2* z = fft_forward<N>(a, b, tws);
-        float* dst = acc + f * hop;
-        for (int base = threadIdx.x; base < n; base += kBatch * blockDim.x) {
+        float2* other = (in == a) ? b : a;
+        const float2* z = fft_forward<N>(in, other, tws);
+        in = (z == a) ? b : a;
+        // windowed overlap-add into the ring.  The first `hop` samples of the frame are final for this CTA once
+        // added (later frames start further right): they go straight to global memory and their ring slots,
+        // re-used by the next frame's tail, are cleared.
+        const int ring0 = (f * hop) % RING;
+        for (int base = threadIdx.x; base < n; base += kBatch * T) {
             float2 wv[kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int m = base + u * blockDim.x;
+                const int m = base + u * T;
                 if (m < n) wv[u] = __ldg(reinterpret_cast<const float2*>(window) + m);
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int m = base + u * blockDim.x;
+                const int m = base + u * T;
                 if (m < n) {
-                    const float2 v = z[pad_idx(m)];
-                    float2* d2 = reinterpret_cast<float2*>(dst) + m;
-                    float2 cur = *d2;
+                    const float2 v = z[swz(m)];
+                    int p = ring0 + 2 * m;
+                    if (p >= RING) p -= RING;
+                    float2* slot = reinterpret_cast<float2*>(ring + p);
+                    float2 cur = *slot;
                     cur.x += v.x * inv_n * wv[u].x;
                     cur.y += -v.y * inv_n * wv[u].y;
-                    *d2 = cur;
+                    if (2 * m < hop) {
+                        float* dst = g + (size_t)f * hop + 2 * m;
+                        atomicAdd(dst, cur.x);
+                        atomicAdd(dst + 1, cur.y);
+                        cur = make_float2(0.f, 0.f);
+                    }
+                    *slot = cur;
                 }
             }
         }
-        __syncthreads();
+        // the next frame's accumulation (other threads, same slots) sits behind its packing + FFT barriers
     }
-    // every output sample is touched by at most two CTAs of the same signal, so the float atomics are
-    // order-independent (a+b == b+a) and the result is deterministic
-    float* g = ola + (size_t)s * ola_len + (size_t)t0 * hop;
-    const int valid = min(span, ola_len - t0 * hop);
-    for (int i = threadIdx.x; i < valid; i += blockDim.x) atomicAdd(g + i, acc[i]);
+    __syncthreads();
+    // tail: samples [nf*hop, (nf-1)*hop + 2n) of this CTA.  Every output sample is touched by at most two CTAs of
+    // the same signal (kOlaFrames*hop >= n_fft), so the float atomics are order-independent (0 + a + b == 0 + b + a)
+    // and the result is deterministic.
+    const int tail0 = nf * hop, tail = RING - hop;
+    for (int i = threadIdx.x; i < tail; i += T) atomicAdd(g + tail0 + i, ring[(tail0 + i) % RING]);
 }
 
 // ------------------------------------------------------------------------------------------
 // FGLA phase B: rebuilt = STFT(ISTFT(..)); T <- rebuilt - momentum * T   (phase_recovery.py:97-117)
 // ------------------------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(Plan<N>::kThreads)
+__global__ void __launch_bounds__(Plan<N>::kThreads, 2)
 fgla_stft_update_kernel(const float* __restrict__ ola, const float* __restrict__ env, int ola_len, int len,
                         const float* __restrict__ window, const float2* __restrict__ tw,
                         const float2* __restrict__ tw_half, int hop, int n_frames,
@@ -396,36 +466,25 @@ fgla_stft_update_kernel(const float* __restrict__ ola, const float* __restrict__
     extern __shared__ __align__(16) uint8_t smem_fft[];
     constexpr int n = N, bins = N + 1;
     float2* a = reinterpret_cast<float2*>(smem_fft);
-    float2* b = a + pad_idx(n) + 8;
-    float2* tws = b + pad_idx(n) + 8;
+    float2* b = a + n;
+    float2* tws = b + n;
     load_twiddles<N>(tws, tw);
     const int s = blockIdx.y;
     const float* o = ola + (size_t)s * ola_len + n;       // trim n_fft/2 (center=True)
     const float* e = env + n;
+    auto src = [&](int j) { return __ldg(o + j) / __ldg(e + j); };
+    float2* in = a;
     for (int f = 0; f < kEncFrames; ++f) {
         const int t = blockIdx.x * kEncFrames + f;
         if (t >= n_frames) break;
-        float2* spec = stft_frame<N>(t, hop, len, [&](int j) { return __ldg(o + j) / __ldg(e + j); }, window, tws,
-                                     tw_half, a, b);
+        float2* other = (in == a) ? b : a;
+        const float2* z = stft_fft<N>(t, hop, len, src, window, tws, in, other);
+        in = (z == a) ? b : a;
         float2* row = state + ((size_t)s * n_frames + t) * bins;
-        constexpr int kBatch = 6;
-        for (int base = threadIdx.x; base < bins; base += kBatch * blockDim.x) {
-            float2 pv[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int k = base + u * blockDim.x;
-                pv[u] = (!first && k < bins) ? row[k] : make_float2(0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int k = base + u * blockDim.x;
-                if (k < bins) {
-                    const float2 r = spec[k];
-                    row[k] = make_float2(r.x - momentum * pv[u].x, r.y - momentum * pv[u].y);
-                }
-            }
-        }
-        __syncthreads();
+        spectrum_pairs<N>(z, tw_half, [&](int k) { return first ? make_float2(0.f, 0.f) : row[k]; },
+                          [&](int k, float2 x, float2 prev) {
+                              row[k] = make_float2(x.x - momentum * prev.x, x.y - momentum * prev.y);
+                          });
     }
 }
 
@@ -439,7 +498,7 @@ __global__ void ola_finalize_kernel(const float* __restrict__ ola, const float* 
 }
 
 bool supported_n_fft(int n_fft) { return n_fft == 6400 || n_fft == 4096; }
-size_t fft_smem_bytes(int n) { return ((size_t)2 * (pad_idx(n) + 8) + n / 2) * sizeof(float2); }
+size_t fft_smem_bytes(int n) { return ((size_t)2 * n + n / 2) * sizeof(float2); }
 
 template <typename K>
 cudaError_t raise_smem_limit(K kernel, size_t smem) {
@@ -461,8 +520,8 @@ extern "C" int dd_stft_mel(const float* raw, int n_signals, int len, const float
     DD_REQUIRE(len > n_fft / 2, "dd_stft_mel: signal shorter than the reflect padding");
     DD_REQUIRE(n_frames == 1 + len / hop, "dd_stft_mel: n_frames must be 1 + len/hop (center=True)");
     if (n_signals == 0) return 0;
-    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)(n_fft / 2 + 8 + n_filters * (kEncFrames + 1)) * sizeof(float);
-    const dim3 grid(ceil_div(n_frames, kEncFrames), n_signals);
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)(n_fft / 2 + 8 + n_filters * (kMelFrames + 1)) * sizeof(float);
+    const dim3 grid(ceil_div(n_frames, kMelFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);
 #define DD_ENC(N_)                                                                                                 \
@@ -491,7 +550,8 @@ extern "C" int dd_fgla_istft(const float* state, const float* mag_tk, int n_sign
                kOlaFrames);
     if (n_signals == 0) return 0;
     DD_CHECK_CUDA(cudaMemsetAsync(ola, 0, (size_t)n_signals * ola_len * sizeof(float), stream));
-    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)((kOlaFrames - 1) * hop + n_fft) * sizeof(float);
+    DD_REQUIRE(hop > 0 && hop % 2 == 0 && hop <= n_fft, "dd_fgla_istft: hop must be even and at most n_fft");
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)n_fft * sizeof(float);
     const dim3 grid(ceil_div(n_frames, kOlaFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);

@@ -137,10 +137,7 @@ class MPConv(torch.nn.Module):
         gain_h = 1.0 if isinstance(gain, Tensor) else float(gain)
         normalize = self.training and not self.disable_weight_norm
         def ver(t: Tensor) -> int:
-            try:
-                return t._version
-            except RuntimeError:        # inference tensor: immutable
-                return 0
+            return 0 if t.is_inference() else t._version        # inference tensor: immutable
         key = (ver(self.weight), self.weight.data_ptr(), normalize, gain_h,
                None if gain_t is None else (gain_t.data_ptr(), ver(gain)))
         if self._prepped is None or key != self._prepped_key:

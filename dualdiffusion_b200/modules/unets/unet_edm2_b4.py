@@ -91,10 +91,7 @@ class Block(torch.nn.Module):
 def _ver(t: Tensor) -> int:
     """Parameter version counter; inference tensors (module built under torch.inference_mode) do not track
     one and cannot be updated by an optimizer, so they count as immutable."""
-    try:
-        return t._version
-    except RuntimeError:
-        return 0
+    return 0 if t.is_inference() else t._version      # (the RuntimeError path costs ~7 us per parameter per call)
 
 
 def _mp_sum_coeffs(t: float) -> Tuple[float, float]:
