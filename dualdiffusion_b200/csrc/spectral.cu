@@ -16,15 +16,15 @@
 namespace {
 
 constexpr int kEncFrames = 32;      // frames per CTA in the FGLA forward STFT
-constexpr int kMelFrames = 16;      // frames per CTA in the encoder (one 64 B output row segment per filter)
+constexpr int kMelFrames = 8;       // frames per CTA in the encoder (one 32 B output sector per filter; 2 CTAs/SM fit)
 constexpr int kOlaFrames = 64;      // frames per CTA in the inverse STFT (overlap-add ring in shared memory)
 
-// Shared-memory FFT buffers are XOR-swizzled inside aligned groups of 16 complex values: every Stockham pass
-// reads contiguous runs (conflict-free under any in-group permutation) and scatters with strides 8 / 64 / 320,
-// which the two XOR terms spread over all 16 eight-byte bank pairs (searched offline over the access patterns of
-// both plans; the earlier `i + i/8` padding cost one extra wavefront on every contiguous access -- ncu showed 47%
-// of all shared wavefronts were excess).
-__host__ __device__ constexpr int swz(int i) { return i ^ (((i >> 4) & 15) ^ (((i >> 4) & 4) << 1)); }
+// Only the buffer between the first two Stockham passes is XOR-swizzled (inside aligned groups of 16 complex
+// values): pass 0 scatters with a stride of `radix` elements -- a 16-way conflict on 8-byte elements when stored
+// plainly -- while every read is a contiguous run, conflict-free under any in-group permutation.  Later passes
+// write runs of >= 8 elements and need nothing.  (History: `i + i/8` padding cost an extra wavefront on every
+// contiguous access, 47% of all shared wavefronts in ncu; swizzling every buffer cost ~40 integer ops per point.)
+template <bool S> __device__ __forceinline__ int swz(int i) { return S ? (i ^ ((i >> 4) & 15)) : i; }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -109,7 +109,8 @@ template <> struct Plan<2048> {            // n_fft 4096 (live MS_MDCT_DualForma
     static constexpr int radix(int s) { return s == 0 ? 8 : s == 1 ? 8 : s == 2 ? 8 : 4; }
 };
 
-// One Stockham autosort pass of radix R with NS = product of the previous radices: in -> out (both swizzled).
+// One Stockham autosort pass of radix R with NS = product of the previous radices: in -> out (pass 0 writes, and
+// pass 1 reads, the swizzled layout).
 // `tws` is the shared-memory half table exp(-2 pi i m / N), m < N/2: with most of the SM's SRAM carved out as
 // shared memory there is next to no L1 left, and __ldg twiddles came from L2.  Only w^k and w^2k are loaded
 // (their indices stay below N/2 for R >= 4); the higher powers are products at most two multiplications deep --
@@ -126,7 +127,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
         const int k = (NS & (NS - 1)) == 0 ? (j & (NS - 1)) : (NS >= NB ? j : (T % NS == 0 ? (int)threadIdx.x % NS : j % NS));
         float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = in[swz(j + r * NB)];
+        for (int r = 0; r < R; ++r) v[r] = in[swz<NS == Plan<N>::radix(0)>(j + r * NB)];
         if (NS > 1) {
             float2 w[R];
             w[1] = tws[k * STEP];
@@ -142,7 +143,7 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
         butterfly<R>(v);
         const int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[swz(j0 + r * NS)] = v[r];
+        for (int r = 0; r < R; ++r) out[swz<NS == 1>(j0 + r * NS)] = v[r];
     }
 }
 
@@ -159,7 +160,7 @@ __device__ __forceinline__ float2* fft_stages(float2* src, float2* dst, const fl
     }
 }
 
-// Forward complex FFT of length N on (swizzled) shared memory.  Returns the buffer holding the result; the last
+// Forward complex FFT of length N in shared memory (plain layout in and out).  Returns the buffer holding the result; the last
 // pass is followed by a barrier.
 template <int N>
 __device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const float2* tws) {
@@ -179,39 +180,71 @@ __device__ __forceinline__ int reflect_index(int j, int len) {
     return j;
 }
 
-// Windowed frame `t` of a (reflect-padded, centred) signal packed as n_fft/2 complex values into `in`, then the
-// half-length complex FFT.  src(j) returns sample j of the un-padded signal.  Returns the buffer holding Z
-// (swizzled); the caller unpacks the real-input spectrum from it with spectrum_pairs().  No barrier is needed
-// between a caller's use of the previous frame's Z and this call as long as `in` is the buffer NOT holding it.
-template <int N, typename SrcFn>
-__device__ __forceinline__ float2* stft_fft(int t, int hop, int len, SrcFn src, const float* __restrict__ window,
-                                            const float2* tws, float2* in, float2* other) {
-    constexpr int n = N, T = Plan<N>::kThreads;
-    const int p0 = t * hop - n;                       // first padded-domain sample of the frame, relative to signal
+// The forward STFT kernels keep the last n_fft signal samples of their frame sequence in a shared-memory ring
+// (sample q of the CTA's padded-domain span lives at q % n_fft): consecutive frames overlap by n_fft - hop samples,
+// so only `hop` new samples per frame come from global memory (reflect padding, envelope division) instead of
+// n_fft -- the gather was 31% of all stall samples before.  fetch(q) returns span sample q.
+template <int N, typename FetchFn>
+__device__ __forceinline__ void ring_fill(float* ring, FetchFn fetch) {
+    constexpr int RING = 2 * N, T = Plan<N>::kThreads;
+    constexpr int kU = 5;
+    for (int base = threadIdx.x; base < RING; base += kU * T) {
+        float x[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) if (base + u * T < RING) x[u] = fetch(base + u * T);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) if (base + u * T < RING) ring[base + u * T] = x[u];
+    }
+    __syncthreads();
+}
+
+// Windowed frame f (local index; its samples are ring span [f*hop, f*hop + n_fft)) packed as n_fft/2 complex values
+// into `in`, then the half-length complex FFT.  While the first pass runs, the `hop` samples the NEXT frame adds are
+// fetched (if `more`) and dropped into the ring slots this frame no longer needs.  Returns the buffer holding Z; the
+// caller unpacks the real-input spectrum from it with spectrum_pairs().  No barrier is needed between a caller's use
+// of the previous frame's Z and this call as long as `in` is the buffer NOT holding it.
+template <int N, typename FetchFn>
+__device__ __forceinline__ float2* stft_fft(float* ring, int f, int hop, bool more, FetchFn fetch,
+                                            const float* __restrict__ window, const float2* tws, float2* in, float2* other) {
+    using P = Plan<N>;
+    constexpr int n = N, T = P::kThreads, RING = 2 * N;
+    const int ring0 = (f * hop) % RING;               // even (hop is even): float2-aligned
     const float2* w2 = reinterpret_cast<const float2*>(window);
-    // loads are issued in batches of kGather per thread before any use: one memory round trip per batch
-    // instead of one per element (the frame loop is latency-bound otherwise -- measured)
     constexpr int kGather = 5;
     for (int base = threadIdx.x; base < n; base += kGather * T) {
-        float x0[kGather], x1[kGather];
         float2 w[kGather];
+#pragma unroll
+        for (int u = 0; u < kGather; ++u) if (base + u * T < n) w[u] = __ldg(w2 + base + u * T);
 #pragma unroll
         for (int u = 0; u < kGather; ++u) {
             const int m = base + u * T;
             if (m < n) {
-                x0[u] = src(reflect_index(p0 + 2 * m, len));
-                x1[u] = src(reflect_index(p0 + 2 * m + 1, len));
-                w[u] = __ldg(w2 + m);
+                int p = ring0 + 2 * m;
+                if (p >= RING) p -= RING;
+                const float2 x = *reinterpret_cast<const float2*>(ring + p);
+                in[m] = make_float2(x.x * w[u].x, x.y * w[u].y);
             }
-        }
-#pragma unroll
-        for (int u = 0; u < kGather; ++u) {
-            const int m = base + u * T;
-            if (m < n) in[swz(m)] = make_float2(x0[u] * w[u].x, x1[u] * w[u].y);
         }
     }
     __syncthreads();
-    return fft_forward<N>(in, other, tws);
+    constexpr int kNew = 2;
+    float nx[kNew];
+#pragma unroll
+    for (int u = 0; u < kNew; ++u) {
+        const int i = (int)threadIdx.x + u * T;
+        if (more && i < hop) nx[u] = fetch(f * hop + RING + i);
+    }
+    constexpr int R0 = P::radix(0);
+    stockham_pass<N, T, R0, 1>(in, other, tws);
+#pragma unroll
+    for (int u = 0; u < kNew; ++u) {
+        const int i = (int)threadIdx.x + u * T;
+        if (more && i < hop) { int p = ring0 + i; if (p >= RING) p -= RING; ring[p] = nx[u]; }
+    }
+    if (more)
+        for (int i = (int)threadIdx.x + kNew * T; i < hop; i += T) ring[(ring0 + i) % RING] = fetch(f * hop + RING + i);
+    __syncthreads();
+    return fft_stages<N, 1, R0>(other, in, tws);
 }
 
 // Real-input spectrum from the half-length FFT Z, two bins per step:
@@ -236,8 +269,8 @@ __device__ __forceinline__ void spectrum_pairs(const float2* z, const float2* __
         for (int u = 0; u < kPost; ++u) {
             const int k = base + u * T;
             if (k < HALFN) {
-                const float2 zk = z[swz(k)];
-                const float2 zc = z[swz(k == 0 ? 0 : n - k)];
+                const float2 zk = z[k];
+                const float2 zc = z[k == 0 ? 0 : n - k];
                 const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
                 const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
                 const float2 q = cmul(d, wh[u]);
@@ -247,7 +280,7 @@ __device__ __forceinline__ void spectrum_pairs(const float2* z, const float2* __
         }
     }
     if (threadIdx.x == 0) {                           // k = n/2 pairs with itself: w = -i, X = conj(Z[n/2])
-        const float2 zk = z[swz(HALFN)];
+        const float2 zk = z[HALFN];
         sink(HALFN, make_float2(zk.x, -zk.y), pre(HALFN));
     }
 }
@@ -270,28 +303,30 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
     float2* tws = b + n;                                          // [n/2] twiddle half table
     float* mag = reinterpret_cast<float*>(tws + n / 2);           // [n + 8] blended magnitudes
     float* tile = mag + n + 8;                                    // [n_filters][kMelFrames + 1]
+    float* ring = tile + n_filters * (kMelFrames + 1);            // [2n] signal ring
     load_twiddles<N>(tws, tw);
     const int s = blockIdx.y;
     const int t0 = blockIdx.x * kMelFrames;
+    const int nf = min(kMelFrames, n_frames - t0);
     const float* sig = raw + (size_t)s * len;
-    auto src = [&](int j) { return __ldg(sig + j); };
+    const int p_base = t0 * hop - n;                  // signal index of span sample 0 (center=True reflect padding)
+    auto fetch = [&](int q) { return __ldg(sig + reflect_index(p_base + q, len)); };
+    ring_fill<N>(ring, fetch);
     float2* in = a;
-    for (int f = 0; f < kMelFrames; ++f) {
-        const int t = t0 + f;
-        if (t >= n_frames) break;
+    for (int f = 0; f < nf; ++f) {
         // |STFT| with the first window (times an optional per-bin coefficient); the live MS_MDCT_DualFormat blends a
         // second, narrower-window STFT per bin (ms_mdct_dual.py:249-256): mag = |X1|*coef1 + |X2|*coef2.  A bin is
         // handled by the same thread in both passes, so the accumulation needs no barrier.
         {
             float2* other = (in == a) ? b : a;
-            const float2* z = stft_fft<N>(t, hop, len, src, window, tws, in, other);
+            const float2* z = stft_fft<N>(ring, f, hop, !window2 && f + 1 < nf, fetch, window, tws, in, other);
             spectrum_pairs<N>(z, tw_half, [&](int k) { return coef1 ? __ldg(coef1 + k) : 1.f; },
                               [&](int k, float2 x, float c) { mag[k] = sqrtf(x.x * x.x + x.y * x.y) * c; });
             in = (z == a) ? b : a;
         }
         if (window2) {
             float2* other = (in == a) ? b : a;
-            const float2* z = stft_fft<N>(t, hop, len, src, window2, tws, in, other);
+            const float2* z = stft_fft<N>(ring, f, hop, f + 1 < nf, fetch, window2, tws, in, other);
             spectrum_pairs<N>(z, tw_half, [&](int k) { return __ldg(coef2 + k); },
                               [&](int k, float2 x, float c) { mag[k] += sqrtf(x.x * x.x + x.y * x.y) * c; });
             in = (z == a) ? b : a;
@@ -307,7 +342,6 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
         // the next frame's first write to `mag` sits behind its gather + FFT barriers
     }
     __syncthreads();
-    const int nf = min(kMelFrames, n_frames - t0);
     for (int i = threadIdx.x; i < n_filters * kMelFrames; i += blockDim.x) {
         const int m = i / kMelFrames, f = i % kMelFrames;
         if (f < nf) out[((size_t)s * n_filters + m) * n_frames + t0 + f] = tile[m * (kMelFrames + 1) + f];
@@ -355,7 +389,8 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
         }
         float2 ang = v.t;
         if (state) {
-            const float inv = 1.f / (sqrtf(ang.x * ang.x + ang.y * ang.y) + 1e-16f);   // :115
+            // :115 T / (|T| + 1e-16); the epsilon only matters at |T| ~ 0, where both forms give 0
+            const float inv = rsqrtf(fmaxf(ang.x * ang.x + ang.y * ang.y, 1e-32f));
             ang = make_float2(ang.x * inv, ang.y * inv);
         }
         float2 x = make_float2(ang.x * m, ang.y * m);
@@ -397,8 +432,8 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
                 if (k < HALFN) {
                     float2 zk, zc;
                     pack_pair(make_x(vk[u], k), make_x(vc[u], n - k), wh[u], zk, zc);
-                    in[swz(k)] = zk;
-                    if (k > 0) in[swz(n - k)] = zc;
+                    in[k] = zk;
+                    if (k > 0) in[n - k] = zc;
                 }
             }
         }
@@ -406,7 +441,7 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
             const float2 x = make_x(load_bin(row, row_other, HALFN), HALFN);
             float2 zk, zc;
             pack_pair(x, x, __ldg(tw_half + HALFN), zk, zc);
-            in[swz(HALFN)] = zk;
+            in[HALFN] = zk;
         }
         __syncthreads();
         float2* other = (in == a) ? b : a;
@@ -427,7 +462,7 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
             for (int u = 0; u < kBatch; ++u) {
                 const int m = base + u * T;
                 if (m < n) {
-                    const float2 v = z[swz(m)];
+                    const float2 v = z[m];
                     int p = ring0 + 2 * m;
                     if (p >= RING) p -= RING;
                     float2* slot = reinterpret_cast<float2*>(ring + p);
@@ -468,17 +503,21 @@ fgla_stft_update_kernel(const float* __restrict__ ola, const float* __restrict__
     float2* a = reinterpret_cast<float2*>(smem_fft);
     float2* b = a + n;
     float2* tws = b + n;
+    float* ring = reinterpret_cast<float*>(tws + n / 2);  // [2n] signal ring
     load_twiddles<N>(tws, tw);
     const int s = blockIdx.y;
     const float* o = ola + (size_t)s * ola_len + n;       // trim n_fft/2 (center=True)
     const float* e = env + n;
-    auto src = [&](int j) { return __ldg(o + j) / __ldg(e + j); };
+    const int t0 = blockIdx.x * kEncFrames;
+    const int nf = min(kEncFrames, n_frames - t0);
+    const int p_base = t0 * hop - n;
+    auto fetch = [&](int q) { const int j = reflect_index(p_base + q, len); return __ldg(o + j) / __ldg(e + j); };
+    ring_fill<N>(ring, fetch);
     float2* in = a;
-    for (int f = 0; f < kEncFrames; ++f) {
-        const int t = blockIdx.x * kEncFrames + f;
-        if (t >= n_frames) break;
+    for (int f = 0; f < nf; ++f) {
+        const int t = t0 + f;
         float2* other = (in == a) ? b : a;
-        const float2* z = stft_fft<N>(t, hop, len, src, window, tws, in, other);
+        const float2* z = stft_fft<N>(ring, f, hop, f + 1 < nf, fetch, window, tws, in, other);
         in = (z == a) ? b : a;
         float2* row = state + ((size_t)s * n_frames + t) * bins;
         spectrum_pairs<N>(z, tw_half, [&](int k) { return first ? make_float2(0.f, 0.f) : row[k]; },
@@ -520,7 +559,8 @@ extern "C" int dd_stft_mel(const float* raw, int n_signals, int len, const float
     DD_REQUIRE(len > n_fft / 2, "dd_stft_mel: signal shorter than the reflect padding");
     DD_REQUIRE(n_frames == 1 + len / hop, "dd_stft_mel: n_frames must be 1 + len/hop (center=True)");
     if (n_signals == 0) return 0;
-    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)(n_fft / 2 + 8 + n_filters * (kMelFrames + 1)) * sizeof(float);
+    DD_REQUIRE(hop > 0 && hop % 2 == 0 && hop <= n_fft, "dd_stft_mel: hop must be even and at most n_fft");
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)(n_fft / 2 + 8 + n_filters * (kMelFrames + 1) + n_fft) * sizeof(float);
     const dim3 grid(ceil_div(n_frames, kMelFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);
@@ -576,7 +616,8 @@ extern "C" int dd_fgla_stft_update(const float* ola, const float* env, int n_sig
     DD_REQUIRE(supported_n_fft(n_fft), "dd_fgla_stft_update: n_fft=%d unsupported (6400, 4096)", n_fft);
     DD_REQUIRE(len == hop * (n_frames - 1), "dd_fgla_stft_update: len must be hop*(n_frames-1)");
     if (n_signals == 0) return 0;
-    const size_t smem = fft_smem_bytes(n_fft / 2);
+    DD_REQUIRE(hop > 0 && hop % 2 == 0 && hop <= n_fft, "dd_fgla_stft_update: hop must be even and at most n_fft");
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)n_fft * sizeof(float);
     const dim3 grid(ceil_div(n_frames, kEncFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);
