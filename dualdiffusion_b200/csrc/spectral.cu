@@ -109,16 +109,56 @@ template <> struct Plan<2048> {            // n_fft 4096 (live MS_MDCT_DualForma
     static constexpr int radix(int s) { return s == 0 ? 8 : s == 1 ? 8 : s == 2 ? 8 : 4; }
 };
 
-// One Stockham autosort pass of radix R with NS = product of the previous radices: in -> out (pass 0 writes, and
-// pass 1 reads, the swizzled layout).
-// `tws` is the shared-memory half table exp(-2 pi i m / N), m < N/2: with most of the SM's SRAM carved out as
-// shared memory there is next to no L1 left, and __ldg twiddles came from L2.  Only w^k and w^2k are loaded
-// (their indices stay below N/2 for R >= 4); the higher powers are products at most two multiplications deep --
-// the strided table reads of w^(rk) were 2- to 8-way bank-conflicted.
-template <int N, int T, int R, int NS>
-__device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, float2* __restrict__ out,
-                                              const float2* __restrict__ tws) {
-    constexpr int NB = N / R, STEP = N / (NS * R);
+// Per-thread twiddle registers.  In pass S (NS = product of the earlier radices) a thread's butterflies use
+// w^(r k), k = j % NS, and j = tid + it*T: whenever T % NS == 0 (or the pass has a single iteration) k is the same
+// for every frame AND every iteration, so w^k and w^2k are loaded from the global table once per CTA and stay in
+// registers; the higher powers are products at most two multiplications deep.  (History: a shared-memory table
+// cost 12.8 KB and its strided reads were 2- to 8-way bank-conflicted; __ldg twiddles came from L2 every pass.)
+template <int N> struct TwRegs {
+    using P = Plan<N>;
+    static constexpr int ns(int S) { int v = 1; for (int s = 0; s < S; ++s) v *= P::radix(s); return v; }
+    static constexpr int iters(int S) { return (N / P::radix(S) + P::kThreads - 1) / P::kThreads; }
+    static constexpr int sets(int S) { return S == 0 ? 0 : (P::kThreads % ns(S) == 0 ? 1 : iters(S)); }
+    static constexpr int base(int S) { int v = 0; for (int s = 1; s < S; ++s) v += sets(s); return v; }
+    static constexpr int kSets = base(P::kStages);
+    float2 w1[kSets], w2[kSets];
+};
+
+template <int N, int S>
+__device__ __forceinline__ void tw_init(TwRegs<N>& tw, const float2* __restrict__ table) {
+    using P = Plan<N>;
+    using TW = TwRegs<N>;
+    if constexpr (S < P::kStages) {
+        constexpr int R = P::radix(S), NS = TW::ns(S), STEP = N / (NS * R);
+#pragma unroll
+        for (int it = 0; it < TW::sets(S); ++it) {
+            const int k = ((int)threadIdx.x + it * P::kThreads) % NS;
+            tw.w1[TW::base(S) + it] = __ldg(table + k * STEP);                    // k*STEP < N/R <= N/2
+            tw.w2[TW::base(S) + it] = R > 2 ? __ldg(table + 2 * k * STEP) : make_float2(1.f, 0.f);
+        }
+        tw_init<N, S + 1>(tw, table);
+    }
+}
+
+// Only the buffer between the first two Stockham passes is XOR-swizzled (see swz()).
+template <int S> struct SmemLoad {
+    const float2* buf;
+    __device__ __forceinline__ float2 operator()(int i) const { return buf[swz<S == 1>(i)]; }
+};
+template <int S> struct SmemStore {
+    float2* buf;
+    __device__ __forceinline__ void operator()(int i, float2 v) const { buf[swz<S == 0>(i)] = v; }
+};
+
+// One Stockham autosort pass S of radix R with NS = product of the previous radices.  load(i) yields input element i,
+// store(i, v) consumes output element i: the first pass of a forward STFT reads the windowed signal straight from the
+// sample ring and the last pass of the inverse STFT accumulates straight into the overlap-add ring, which saves one
+// shared-memory round trip and one barrier per frame each.
+template <int N, int S, typename LoadFn, typename StoreFn>
+__device__ __forceinline__ void fft_pass(const TwRegs<N>& tw, LoadFn load, StoreFn store) {
+    using P = Plan<N>;
+    using TW = TwRegs<N>;
+    constexpr int T = P::kThreads, R = P::radix(S), NS = TW::ns(S), NB = N / R;
     constexpr int ITERS = (NB + T - 1) / T;
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
@@ -127,11 +167,13 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
         const int k = (NS & (NS - 1)) == 0 ? (j & (NS - 1)) : (NS >= NB ? j : (T % NS == 0 ? (int)threadIdx.x % NS : j % NS));
         float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = in[swz<NS == Plan<N>::radix(0)>(j + r * NB)];
-        if (NS > 1) {
+        for (int r = 0; r < R; ++r) v[r] = load(j + r * NB);
+        if constexpr (S > 0) {
+            constexpr int kBase = TW::base(S);
+            const int set = kBase + (TW::sets(S) == 1 ? 0 : it);
             float2 w[R];
-            w[1] = tws[k * STEP];
-            if constexpr (R > 2) w[2] = tws[2 * k * STEP];
+            w[1] = tw.w1[set];
+            if constexpr (R > 2) w[2] = tw.w2[set];
 #pragma unroll
             for (int r = 3; r < R; ++r) {
                 const int a = r == 3 ? 1 : r == 4 ? 2 : r < 9 ? 4 : 8;
@@ -143,35 +185,21 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ in, flo
         butterfly<R>(v);
         const int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) out[swz<NS == 1>(j0 + r * NS)] = v[r];
+        for (int r = 0; r < R; ++r) store(j0 + r * NS, v[r]);
     }
 }
 
-template <int N, int S, int NS>
-__device__ __forceinline__ float2* fft_stages(float2* src, float2* dst, const float2* tws) {
-    using P = Plan<N>;
-    if constexpr (S == P::kStages) {
+// Passes S .. kStages-2 between the two shared-memory buffers, a barrier after each.  Returns the buffer holding
+// the input of the last pass.
+template <int N, int S>
+__device__ __forceinline__ float2* fft_middle(const TwRegs<N>& tw, float2* src, float2* dst) {
+    if constexpr (S >= Plan<N>::kStages - 1) {
         return src;
     } else {
-        constexpr int R = P::radix(S);
-        stockham_pass<N, P::kThreads, R, NS>(src, dst, tws);
+        fft_pass<N, S>(tw, SmemLoad<S>{src}, SmemStore<S>{dst});
         __syncthreads();
-        return fft_stages<N, S + 1, NS * R>(dst, src, tws);
+        return fft_middle<N, S + 1>(tw, dst, src);
     }
-}
-
-// Forward complex FFT of length N in shared memory (plain layout in and out).  Returns the buffer holding the result; the last
-// pass is followed by a barrier.
-template <int N>
-__device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const float2* tws) {
-    return fft_stages<N, 0, 1>(a, b, tws);
-}
-
-// Cooperative copy of the half twiddle table into shared memory (once per CTA).
-template <int N>
-__device__ __forceinline__ void load_twiddles(float2* tws, const float2* __restrict__ tw) {
-    for (int i = threadIdx.x; i < N / 2; i += blockDim.x) tws[i] = __ldg(tw + i);
-    __syncthreads();
 }
 
 __device__ __forceinline__ int reflect_index(int j, int len) {
@@ -180,10 +208,19 @@ __device__ __forceinline__ int reflect_index(int j, int len) {
     return j;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Pull `bytes` starting at p (any alignment) into L2, one 128 B line per thread per step.
+template <int T>
+__device__ __forceinline__ void prefetch_span_l2(const void* p, size_t bytes) {
+    const char* c = static_cast<const char*>(p);
+    for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)T * 128) prefetch_l2(c + off);
+}
+
 // The forward STFT kernels keep the last n_fft signal samples of their frame sequence in a shared-memory ring
 // (sample q of the CTA's padded-domain span lives at q % n_fft): consecutive frames overlap by n_fft - hop samples,
 // so only `hop` new samples per frame come from global memory (reflect padding, envelope division) instead of
-// n_fft -- the gather was 31% of all stall samples before.  fetch(q) returns span sample q.
+// n_fft -- that gather was 31% of all stall samples before.  fetch(q) returns span sample q.
 template <int N, typename FetchFn>
 __device__ __forceinline__ void ring_fill(float* ring, FetchFn fetch) {
     constexpr int RING = 2 * N, T = Plan<N>::kThreads;
@@ -195,47 +232,36 @@ __device__ __forceinline__ void ring_fill(float* ring, FetchFn fetch) {
 #pragma unroll
         for (int u = 0; u < kU; ++u) if (base + u * T < RING) ring[base + u * T] = x[u];
     }
-    __syncthreads();
 }
 
-// Windowed frame f (local index; its samples are ring span [f*hop, f*hop + n_fft)) packed as n_fft/2 complex values
-// into `in`, then the half-length complex FFT.  While the first pass runs, the `hop` samples the NEXT frame adds are
-// fetched (if `more`) and dropped into the ring slots this frame no longer needs.  Returns the buffer holding Z; the
-// caller unpacks the real-input spectrum from it with spectrum_pairs().  No barrier is needed between a caller's use
-// of the previous frame's Z and this call as long as `in` is the buffer NOT holding it.
+// Half-length complex FFT of the windowed frame f (local index; its samples are ring span [f*hop, f*hop + n_fft)).
+// The first pass reads ring * window directly (`win` may point to shared or global memory).  While the second pass
+// runs, the `hop` samples the NEXT frame adds are fetched (if `more`) and dropped into the ring slots this frame no
+// longer needs.  Z ends up in `b` (kStages is even), with a barrier behind it; the caller unpacks the real-input
+// spectrum with spectrum_pairs().  The next call may start without a barrier: its first pass writes `a`.
 template <int N, typename FetchFn>
-__device__ __forceinline__ float2* stft_fft(float* ring, int f, int hop, bool more, FetchFn fetch,
-                                            const float* __restrict__ window, const float2* tws, float2* in, float2* other) {
+__device__ __forceinline__ const float2* stft_fft(const TwRegs<N>& tw, float* ring, int f, int hop, bool more, FetchFn fetch,
+                                                  const float2* win, float2* a, float2* b) {
     using P = Plan<N>;
-    constexpr int n = N, T = P::kThreads, RING = 2 * N;
+    static_assert(P::kStages % 2 == 0 && P::kStages >= 4, "buffer rotation below assumes an even number of passes");
+    constexpr int T = P::kThreads, RING = 2 * N;
     const int ring0 = (f * hop) % RING;               // even (hop is even): float2-aligned
-    const float2* w2 = reinterpret_cast<const float2*>(window);
-    constexpr int kGather = 5;
-    for (int base = threadIdx.x; base < n; base += kGather * T) {
-        float2 w[kGather];
-#pragma unroll
-        for (int u = 0; u < kGather; ++u) if (base + u * T < n) w[u] = __ldg(w2 + base + u * T);
-#pragma unroll
-        for (int u = 0; u < kGather; ++u) {
-            const int m = base + u * T;
-            if (m < n) {
-                int p = ring0 + 2 * m;
-                if (p >= RING) p -= RING;
-                const float2 x = *reinterpret_cast<const float2*>(ring + p);
-                in[m] = make_float2(x.x * w[u].x, x.y * w[u].y);
-            }
-        }
-    }
+    fft_pass<N, 0>(tw, [&](int i) {
+        int p = ring0 + 2 * i;
+        if (p >= RING) p -= RING;
+        const float2 x = *reinterpret_cast<const float2*>(ring + p);
+        const float2 w = win[i];
+        return make_float2(x.x * w.x, x.y * w.y);
+    }, SmemStore<0>{a});
     __syncthreads();
     constexpr int kNew = 2;
-    float nx[kNew];
+    decltype(fetch(0)) nx[kNew];
 #pragma unroll
     for (int u = 0; u < kNew; ++u) {
         const int i = (int)threadIdx.x + u * T;
         if (more && i < hop) nx[u] = fetch(f * hop + RING + i);
     }
-    constexpr int R0 = P::radix(0);
-    stockham_pass<N, T, R0, 1>(in, other, tws);
+    fft_pass<N, 1>(tw, SmemLoad<1>{a}, SmemStore<1>{b});
 #pragma unroll
     for (int u = 0; u < kNew; ++u) {
         const int i = (int)threadIdx.x + u * T;
@@ -244,7 +270,11 @@ __device__ __forceinline__ float2* stft_fft(float* ring, int f, int hop, bool mo
     if (more)
         for (int i = (int)threadIdx.x + kNew * T; i < hop; i += T) ring[(ring0 + i) % RING] = fetch(f * hop + RING + i);
     __syncthreads();
-    return fft_stages<N, 1, R0>(other, in, tws);
+    float2* src = fft_middle<N, 2>(tw, b, a);
+    float2* dst = (src == a) ? b : a;
+    fft_pass<N, P::kStages - 1>(tw, SmemLoad<P::kStages - 1>{src}, SmemStore<P::kStages - 1>{dst});
+    __syncthreads();
+    return dst;
 }
 
 // Real-input spectrum from the half-length FFT Z, two bins per step:
@@ -300,11 +330,11 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
     constexpr int n = N;
     float2* a = reinterpret_cast<float2*>(smem_fft);
     float2* b = a + n;
-    float2* tws = b + n;                                          // [n/2] twiddle half table
-    float* mag = reinterpret_cast<float*>(tws + n / 2);           // [n + 8] blended magnitudes
+    float* ring = reinterpret_cast<float*>(b + n);                // [2n] signal ring
+    float* mag = ring + 2 * n;                                    // [n + 8] blended magnitudes
     float* tile = mag + n + 8;                                    // [n_filters][kMelFrames + 1]
-    float* ring = tile + n_filters * (kMelFrames + 1);            // [2n] signal ring
-    load_twiddles<N>(tws, tw);
+    TwRegs<N> twr;
+    tw_init<N, 1>(twr, tw);
     const int s = blockIdx.y;
     const int t0 = blockIdx.x * kMelFrames;
     const int nf = min(kMelFrames, n_frames - t0);
@@ -312,24 +342,23 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
     const int p_base = t0 * hop - n;                  // signal index of span sample 0 (center=True reflect padding)
     auto fetch = [&](int q) { return __ldg(sig + reflect_index(p_base + q, len)); };
     ring_fill<N>(ring, fetch);
-    float2* in = a;
+    __syncthreads();
+    // the windows stay in global memory here (L2-resident; the 8 reads of a butterfly are issued together)
+    const float2* win1 = reinterpret_cast<const float2*>(window);
+    const float2* win2 = reinterpret_cast<const float2*>(window2);
     for (int f = 0; f < nf; ++f) {
         // |STFT| with the first window (times an optional per-bin coefficient); the live MS_MDCT_DualFormat blends a
         // second, narrower-window STFT per bin (ms_mdct_dual.py:249-256): mag = |X1|*coef1 + |X2|*coef2.  A bin is
         // handled by the same thread in both passes, so the accumulation needs no barrier.
         {
-            float2* other = (in == a) ? b : a;
-            const float2* z = stft_fft<N>(ring, f, hop, !window2 && f + 1 < nf, fetch, window, tws, in, other);
+            const float2* z = stft_fft<N>(twr, ring, f, hop, !window2 && f + 1 < nf, fetch, win1, a, b);
             spectrum_pairs<N>(z, tw_half, [&](int k) { return coef1 ? __ldg(coef1 + k) : 1.f; },
                               [&](int k, float2 x, float c) { mag[k] = sqrtf(x.x * x.x + x.y * x.y) * c; });
-            in = (z == a) ? b : a;
         }
         if (window2) {
-            float2* other = (in == a) ? b : a;
-            const float2* z = stft_fft<N>(ring, f, hop, f + 1 < nf, fetch, window2, tws, in, other);
+            const float2* z = stft_fft<N>(twr, ring, f, hop, f + 1 < nf, fetch, win2, a, b);
             spectrum_pairs<N>(z, tw_half, [&](int k) { return __ldg(coef2 + k); },
                               [&](int k, float2 x, float c) { mag[k] += sqrtf(x.x * x.x + x.y * x.y) * c; });
-            in = (z == a) ? b : a;
         }
         __syncthreads();
         for (int m = threadIdx.x; m < n_filters; m += blockDim.x) {
@@ -339,7 +368,7 @@ stft_mel_kernel(const float* __restrict__ raw, int len, const float* __restrict_
             const float v = (exponent == 0.25f) ? sqrtf(sqrtf(acc)) : (exponent == 1.f ? acc : powf(acc, exponent));
             tile[m * (kMelFrames + 1) + f] = (v - mean) * scale;
         }
-        // the next frame's first write to `mag` sits behind its gather + FFT barriers
+        // the next frame's first write to `mag` sits behind its FFT barriers
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n_filters * kMelFrames; i += blockDim.x) {
@@ -359,17 +388,20 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
                   const float* __restrict__ window, const float2* __restrict__ tw, const float2* __restrict__ tw_half,
                   int hop, int n_frames, float* __restrict__ ola, int ola_len) {
     extern __shared__ __align__(16) uint8_t smem_fft[];
-    constexpr int n = N, bins = N + 1, T = Plan<N>::kThreads, HALFN = N / 2, RING = 2 * N;
+    using P = Plan<N>;
+    constexpr int n = N, bins = N + 1, T = P::kThreads, HALFN = N / 2, RING = 2 * N;
     float2* a = reinterpret_cast<float2*>(smem_fft);
     float2* b = a + n;
-    float2* tws = b + n;                                          // [n/2] twiddle half table
-    float* ring = reinterpret_cast<float*>(tws + n / 2);          // [2n] overlap-add ring: sample p lives at p % 2n
-    load_twiddles<N>(tws, tw);
+    float2* win = b + n;                                          // [n] synthesis window (sample pairs)
+    float* ring = reinterpret_cast<float*>(win + n);              // [2n] overlap-add ring: sample p lives at p % 2n
+    TwRegs<N> twr;
+    tw_init<N, 1>(twr, tw);
     const int s = blockIdx.y;
     const int t0 = blockIdx.x * kOlaFrames;
     const int nf = min(kOlaFrames, n_frames - t0);
+    for (int i = threadIdx.x; i < n; i += T) win[i] = __ldg(reinterpret_cast<const float2*>(window) + i);
     for (int i = threadIdx.x; i < RING; i += T) ring[i] = 0.f;
-    // (ordered before the first accumulation by the barriers of the first frame)
+    // (ordered before their first use by the barriers of the first frame)
     const float inv_n = 1.f / (float)n;
     float* g = ola + (size_t)s * ola_len + (size_t)t0 * hop;      // global position of this CTA's local sample 0
 
@@ -407,12 +439,18 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
         zk = make_float2(e.x - o.y, -(e.y + o.x));
         zc = make_float2(e.x + o.y, e.y - o.x);
     };
+    auto prefetch_rows = [&](int t) {            // HBM -> L2 one frame ahead of the loads (nothing re-reads these rows)
+        const size_t row = ((size_t)s * n_frames + t) * bins;
+        if (state) prefetch_span_l2<T>(state + row, bins * sizeof(float2));
+        prefetch_span_l2<T>(mag + row, bins * sizeof(float));
+        if (stereo) prefetch_span_l2<T>(mag + ((size_t)(s ^ 1) * n_frames + t) * bins, bins * sizeof(float));
+    };
 
-    float2* in = a;
     for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
         const size_t row = ((size_t)s * n_frames + t) * bins;
         const size_t row_other = ((size_t)(s ^ 1) * n_frames + t) * bins;
+        if (f + 1 < nf) prefetch_rows(t + 1);
         constexpr int kBatch = 5;
         for (int base = threadIdx.x; base < HALFN; base += kBatch * T) {
             FglaBin vk[kBatch], vc[kBatch];
@@ -432,8 +470,8 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
                 if (k < HALFN) {
                     float2 zk, zc;
                     pack_pair(make_x(vk[u], k), make_x(vc[u], n - k), wh[u], zk, zc);
-                    in[k] = zk;
-                    if (k > 0) in[n - k] = zc;
+                    a[k] = zk;
+                    if (k > 0) a[n - k] = zc;
                 }
             }
         }
@@ -441,45 +479,33 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
             const float2 x = make_x(load_bin(row, row_other, HALFN), HALFN);
             float2 zk, zc;
             pack_pair(x, x, __ldg(tw_half + HALFN), zk, zc);
-            in[HALFN] = zk;
+            a[HALFN] = zk;
         }
         __syncthreads();
-        float2* other = (in == a) ? b : a;
-        const float2* z = fft_forward<N>(in, other, tws);
-        in = (z == a) ? b : a;
-        // windowed overlap-add into the ring.  The first `hop` samples of the frame are final for this CTA once
-        // added (later frames start further right): they go straight to global memory and their ring slots,
-        // re-used by the next frame's tail, are cleared.
+        fft_pass<N, 0>(twr, SmemLoad<0>{a}, SmemStore<0>{b});
+        __syncthreads();
+        float2* src = fft_middle<N, 1>(twr, b, a);
+        // Last pass: windowed overlap-add straight into the ring.  The first `hop` samples of the frame are final
+        // for this CTA once added (later frames start further right): they go straight to global memory and their
+        // ring slots, re-used by the next frame's tail, are cleared.  The next frame's accumulation (other threads,
+        // same slots) sits behind its packing + FFT barriers; so does its first write to `a` / `b`.
         const int ring0 = (f * hop) % RING;
-        for (int base = threadIdx.x; base < n; base += kBatch * T) {
-            float2 wv[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int m = base + u * T;
-                if (m < n) wv[u] = __ldg(reinterpret_cast<const float2*>(window) + m);
+        fft_pass<N, P::kStages - 1>(twr, SmemLoad<P::kStages - 1>{src}, [&](int m, float2 v) {
+            int p = ring0 + 2 * m;
+            if (p >= RING) p -= RING;
+            float2* slot = reinterpret_cast<float2*>(ring + p);
+            const float2 w = win[m];
+            float2 cur = *slot;
+            cur.x += v.x * inv_n * w.x;
+            cur.y += -v.y * inv_n * w.y;
+            if (2 * m < hop) {
+                float* dst = g + (size_t)f * hop + 2 * m;
+                atomicAdd(dst, cur.x);
+                atomicAdd(dst + 1, cur.y);
+                cur = make_float2(0.f, 0.f);
             }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int m = base + u * T;
-                if (m < n) {
-                    const float2 v = z[m];
-                    int p = ring0 + 2 * m;
-                    if (p >= RING) p -= RING;
-                    float2* slot = reinterpret_cast<float2*>(ring + p);
-                    float2 cur = *slot;
-                    cur.x += v.x * inv_n * wv[u].x;
-                    cur.y += -v.y * inv_n * wv[u].y;
-                    if (2 * m < hop) {
-                        float* dst = g + (size_t)f * hop + 2 * m;
-                        atomicAdd(dst, cur.x);
-                        atomicAdd(dst + 1, cur.y);
-                        cur = make_float2(0.f, 0.f);
-                    }
-                    *slot = cur;
-                }
-            }
-        }
-        // the next frame's accumulation (other threads, same slots) sits behind its packing + FFT barriers
+            *slot = cur;
+        });
     }
     __syncthreads();
     // tail: samples [nf*hop, (nf-1)*hop + 2n) of this CTA.  Every output sample is touched by at most two CTAs of
@@ -492,6 +518,7 @@ fgla_istft_kernel(const float2* __restrict__ state, const float* __restrict__ ma
 // ------------------------------------------------------------------------------------------
 // FGLA phase B: rebuilt = STFT(ISTFT(..)); T <- rebuilt - momentum * T   (phase_recovery.py:97-117)
 // ------------------------------------------------------------------------------------------
+
 template <int N>
 __global__ void __launch_bounds__(Plan<N>::kThreads, 2)
 fgla_stft_update_kernel(const float* __restrict__ ola, const float* __restrict__ env, int ola_len, int len,
@@ -499,27 +526,30 @@ fgla_stft_update_kernel(const float* __restrict__ ola, const float* __restrict__
                         const float2* __restrict__ tw_half, int hop, int n_frames,
                         float2* __restrict__ state, float momentum, int first) {
     extern __shared__ __align__(16) uint8_t smem_fft[];
-    constexpr int n = N, bins = N + 1;
+    constexpr int n = N, bins = N + 1, T = Plan<N>::kThreads;
     float2* a = reinterpret_cast<float2*>(smem_fft);
     float2* b = a + n;
-    float2* tws = b + n;
-    float* ring = reinterpret_cast<float*>(tws + n / 2);  // [2n] signal ring
-    load_twiddles<N>(tws, tw);
+    float2* win = b + n;                                  // [n] analysis window (sample pairs)
+    float* ring = reinterpret_cast<float*>(win + n);      // [2n] signal ring
+    TwRegs<N> twr;
+    tw_init<N, 1>(twr, tw);
     const int s = blockIdx.y;
     const float* o = ola + (size_t)s * ola_len + n;       // trim n_fft/2 (center=True)
     const float* e = env + n;
     const int t0 = blockIdx.x * kEncFrames;
     const int nf = min(kEncFrames, n_frames - t0);
     const int p_base = t0 * hop - n;
-    auto fetch = [&](int q) { const int j = reflect_index(p_base + q, len); return __ldg(o + j) / __ldg(e + j); };
-    ring_fill<N>(ring, fetch);
-    float2* in = a;
+    for (int i = threadIdx.x; i < n; i += T) win[i] = __ldg(reinterpret_cast<const float2*>(window) + i);
+    ring_fill<N>(ring, [&](int q) { const int j = reflect_index(p_base + q, len); return __ldg(o + j) / __ldg(e + j); });
+    __syncthreads();
+    // per-frame refill: the division waits until the ring store, so the loads fly during an FFT pass
+    struct Lazy { float num, den; __device__ __forceinline__ operator float() const { return num / den; } };
+    auto fetch = [&](int q) { const int j = reflect_index(p_base + q, len); return Lazy{__ldg(o + j), __ldg(e + j)}; };
     for (int f = 0; f < nf; ++f) {
         const int t = t0 + f;
-        float2* other = (in == a) ? b : a;
-        const float2* z = stft_fft<N>(ring, f, hop, f + 1 < nf, fetch, window, tws, in, other);
-        in = (z == a) ? b : a;
         float2* row = state + ((size_t)s * n_frames + t) * bins;
+        if (!first && f + 1 < nf) prefetch_span_l2<T>(row + bins, bins * sizeof(float2));    // HBM -> L2 a frame ahead
+        const float2* z = stft_fft<N>(twr, ring, f, hop, f + 1 < nf, fetch, win, a, b);
         spectrum_pairs<N>(z, tw_half, [&](int k) { return first ? make_float2(0.f, 0.f) : row[k]; },
                           [&](int k, float2 x, float2 prev) {
                               row[k] = make_float2(x.x - momentum * prev.x, x.y - momentum * prev.y);
@@ -537,7 +567,7 @@ __global__ void ola_finalize_kernel(const float* __restrict__ ola, const float* 
 }
 
 bool supported_n_fft(int n_fft) { return n_fft == 6400 || n_fft == 4096; }
-size_t fft_smem_bytes(int n) { return ((size_t)2 * n + n / 2) * sizeof(float2); }
+size_t fft_smem_bytes(int n) { return (size_t)2 * n * sizeof(float2); }      // the two FFT buffers
 
 template <typename K>
 cudaError_t raise_smem_limit(K kernel, size_t smem) {
@@ -560,7 +590,7 @@ extern "C" int dd_stft_mel(const float* raw, int n_signals, int len, const float
     DD_REQUIRE(n_frames == 1 + len / hop, "dd_stft_mel: n_frames must be 1 + len/hop (center=True)");
     if (n_signals == 0) return 0;
     DD_REQUIRE(hop > 0 && hop % 2 == 0 && hop <= n_fft, "dd_stft_mel: hop must be even and at most n_fft");
-    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)(n_fft / 2 + 8 + n_filters * (kMelFrames + 1) + n_fft) * sizeof(float);
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)(n_fft + n_fft / 2 + 8 + n_filters * (kMelFrames + 1)) * sizeof(float);
     const dim3 grid(ceil_div(n_frames, kMelFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);
@@ -591,7 +621,7 @@ extern "C" int dd_fgla_istft(const float* state, const float* mag_tk, int n_sign
     if (n_signals == 0) return 0;
     DD_CHECK_CUDA(cudaMemsetAsync(ola, 0, (size_t)n_signals * ola_len * sizeof(float), stream));
     DD_REQUIRE(hop > 0 && hop % 2 == 0 && hop <= n_fft, "dd_fgla_istft: hop must be even and at most n_fft");
-    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)n_fft * sizeof(float);
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)2 * n_fft * sizeof(float);      // + window + OLA ring
     const dim3 grid(ceil_div(n_frames, kOlaFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);
@@ -617,7 +647,7 @@ extern "C" int dd_fgla_stft_update(const float* ola, const float* env, int n_sig
     DD_REQUIRE(len == hop * (n_frames - 1), "dd_fgla_stft_update: len must be hop*(n_frames-1)");
     if (n_signals == 0) return 0;
     DD_REQUIRE(hop > 0 && hop % 2 == 0 && hop <= n_fft, "dd_fgla_stft_update: hop must be even and at most n_fft");
-    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)n_fft * sizeof(float);
+    const size_t smem = fft_smem_bytes(n_fft / 2) + (size_t)2 * n_fft * sizeof(float);      // + window + signal ring
     const dim3 grid(ceil_div(n_frames, kEncFrames), n_signals);
     const float2* tw = reinterpret_cast<const float2*>(twiddles);
     const float2* twh = reinterpret_cast<const float2*>(twiddles_half);
