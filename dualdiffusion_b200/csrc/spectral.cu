@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int kEncFrames = 32;      // frames per CTA in the FGLA forward STFT
+constexpr int kEncFrames = 64;      // frames per CTA in the FGLA forward STFT
 constexpr int kMelFrames = 8;       // frames per CTA in the encoder (one 32 B output sector per filter; 2 CTAs/SM fit)
 constexpr int kOlaFrames = 64;      // frames per CTA in the inverse STFT (overlap-add ring in shared memory)
 
@@ -124,6 +124,14 @@ template <int N> struct TwRegs {
     float2 w1[kSets], w2[kSets];
 };
 
+// (asm volatile: a plain __ldg is rematerialisable, and under register pressure the compiler re-issued the global
+// loads inside every pass instead of keeping the values -- visible as long-scoreboard stalls on the twiddle multiply)
+__device__ __forceinline__ float2 ld_pinned(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+
 template <int N, int S>
 __device__ __forceinline__ void tw_init(TwRegs<N>& tw, const float2* __restrict__ table) {
     using P = Plan<N>;
@@ -133,8 +141,8 @@ __device__ __forceinline__ void tw_init(TwRegs<N>& tw, const float2* __restrict_
 #pragma unroll
         for (int it = 0; it < TW::sets(S); ++it) {
             const int k = ((int)threadIdx.x + it * P::kThreads) % NS;
-            tw.w1[TW::base(S) + it] = __ldg(table + k * STEP);                    // k*STEP < N/R <= N/2
-            tw.w2[TW::base(S) + it] = R > 2 ? __ldg(table + 2 * k * STEP) : make_float2(1.f, 0.f);
+            tw.w1[TW::base(S) + it] = ld_pinned(table + k * STEP);                    // k*STEP < N/R <= N/2
+            tw.w2[TW::base(S) + it] = R > 2 ? ld_pinned(table + 2 * k * STEP) : make_float2(1.f, 0.f);
         }
         tw_init<N, S + 1>(tw, table);
     }
