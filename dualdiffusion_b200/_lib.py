@@ -30,8 +30,22 @@ class AffineDesc(C.Structure):
                 ("groups", c_int), ("w_is_bf16", c_int), ("bias", c_float), ("normalize", c_int)]
 
 
+class WbwdDesc(C.Structure):
+    """struct dd_wbwd_desc"""
+    _fields_ = [("w", c_void_p), ("dweff", c_void_p), ("dw", c_void_p), ("gain", c_void_p), ("dgain", c_void_p),
+                ("gain_host", c_float), ("O", c_int), ("I_g", c_int), ("taps", c_int), ("normalize", c_int),
+                ("perm", c_int), ("head_dim", c_int), ("row_stride", c_int), ("accumulate", c_int),
+                ("row_begin", c_int)]
+
+
+class AffineBwdDesc(C.Structure):
+    """struct dd_affine_bwd_desc"""
+    _fields_ = [("w", c_void_p), ("gain", c_void_p), ("dout", c_void_p), ("dweff", c_void_p), ("rowscale", c_void_p),
+                ("O", c_int), ("I", c_int), ("groups", c_int), ("normalize", c_int)]
+
+
 EPI_NONE, EPI_SCALE_SILU, EPI_RESIDUAL = 0, 1, 2
-EPI2_NONE, EPI2_SILU, EPI2_SCALE = 0, 1, 2
+EPI2_NONE, EPI2_SILU, EPI2_SCALE, EPI2_RAW = 0, 1, 2, 3
 WFMT_BF16_OTI, WFMT_F32_OIT = 0, 1
 WPERM_NONE, WPERM_QK, WPERM_QKV = 0, 1, 2
 
@@ -69,6 +83,30 @@ _SIGNATURES = {
                                     c_void_p, c_float, c_int, c_void_p]),
     "dd_ola_finalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "dd_attention_axis": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_attention_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_mpconv_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
+                                c_int, c_void_p]),
+    "dd_weight_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_weight_prep_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "dd_silu_scale_bwd": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_long, c_int,
+                                  c_void_p]),
+    "dd_pixnorm_silu_bwd": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p]),
+    "dd_cat_silu_bwd": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_int,
+                                c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_enc_grad_combine": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int,
+                                    c_void_p]),
+    "dd_attn_in_bwd": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                               c_long, c_int, c_void_p]),
+    "dd_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_int, c_int, c_void_p]),
+    "dd_emb_affine_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dd_noise_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_float,
+                                       c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "dd_label_embedding_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                       c_void_p]),
+    "dd_sigma_logvar_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "dd_head_grad": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                             c_void_p]),
     "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
     "dd_sampler_update": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                   c_int, c_long, c_void_p]),

@@ -69,7 +69,8 @@ struct AttnLayout {
 __global__ void __launch_bounds__(kAttThreads)
 attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* __restrict__ k_ptr,
                  const __nv_bfloat16* __restrict__ v_ptr, const float* __restrict__ scale_v,
-                 __nv_bfloat16* __restrict__ out, int N, int heads, int npad, const __grid_constant__ AttnLayout lay) {
+                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw_out, int N, int heads, int npad,
+                 const __grid_constant__ AttnLayout lay) {
     extern __shared__ __align__(16) uint8_t smem_att[];
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
@@ -224,20 +225,24 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
     for (int r = 0; r < 2; ++r) {
         const int q = q0 + row0 + g + r * 8;
         if (q >= N) continue;
-        __nv_bfloat16* op = out + (size_t)outer * lay.o_outer + (size_t)inner * lay.o_inner + (size_t)q * lay.o_tok + head * kD;
+        const size_t o_off = (size_t)outer * lay.o_outer + (size_t)inner * lay.o_inner + (size_t)q * lay.o_tok + head * kD;
+        __nv_bfloat16* op = out + o_off;
         const float* sc = scale_v ? scale_v + (size_t)(blockIdx.z / lay.scale_div) * C + head * kD : nullptr;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
             const int d = n * 8 + 2 * t;
-            const float y0 = o[n][2 * r + 0] * inv_l[r] * (sc ? __ldg(sc + d) : 1.f);
-            const float y1 = o[n][2 * r + 1] * inv_l[r] * (sc ? __ldg(sc + d + 1) : 1.f);
+            const float a0 = o[n][2 * r + 0] * inv_l[r], a1 = o[n][2 * r + 1] * inv_l[r];
+            if (raw_out) *reinterpret_cast<uint32_t*>(raw_out + o_off + d) = pack_bf16x2(a0, a1);   // train mode
+            const float y0 = a0 * (sc ? __ldg(sc + d) : 1.f);
+            const float y1 = a1 * (sc ? __ldg(sc + d + 1) : 1.f);
             *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_f(y0), mp_silu_f(y1));
         }
     }
 }
 
 int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, const float* scale_v,
-                     __nv_bfloat16* out, int n_seq, int N, int heads, const AttnLayout& lay, cudaStream_t stream) {
+                     __nv_bfloat16* out, __nv_bfloat16* raw_out, int n_seq, int N, int heads, const AttnLayout& lay,
+                     cudaStream_t stream) {
     const int npad = ceil_div(N, 64) * 64;
     const size_t smem = ((size_t)2 * npad * kKStride + (size_t)kQTile * kKStride) * 2;
     static size_t smem_set = 0;
@@ -247,8 +252,8 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     }
     DD_REQUIRE(n_seq <= 65535, "dd_attention: %d sequences exceed the grid limit", n_seq);
     const dim3 grid(ceil_div(N, kQTile), heads, n_seq);
-    DD_CHECK_CUDA(dd_launch_pdl(attention_kernel, grid, dim3(kAttThreads), smem, stream, q, k, v, scale_v, out, N, heads,
-                                npad, lay));
+    DD_CHECK_CUDA(dd_launch_pdl(attention_kernel, grid, dim3(kAttThreads), smem, stream, q, k, v, scale_v, out, raw_out, N,
+                                heads, npad, lay));
     return 0;
 }
 
@@ -263,8 +268,21 @@ extern "C" int dd_attention(const void* qk, const void* v, const float* scale_v,
     const long C = (long)heads * kD;
     AttnLayout lay{2 * C, (long)N * 2 * C, 0, C, (long)N * C, 0, C, (long)N * C, 0, 1, 1};
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qk);
-    return launch_attention(q, q + C, static_cast<const __nv_bfloat16*>(v), scale_v, static_cast<__nv_bfloat16*>(out), B, N,
-                            heads, lay, stream);
+    return launch_attention(q, q + C, static_cast<const __nv_bfloat16*>(v), scale_v, static_cast<__nv_bfloat16*>(out),
+                            nullptr, B, N, heads, lay, stream);
+}
+
+extern "C" int dd_attention_train(const void* qk, const void* v, const float* scale_v, void* out, void* raw_out, int B,
+                                  int N, int heads, int head_dim, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(qk && v && scale_v && out && raw_out, "dd_attention_train: null pointer");
+    DD_REQUIRE(head_dim == kD, "dd_attention_train: head_dim=%d unsupported (64)", head_dim);
+    DD_REQUIRE(N > 0 && N <= 640, "dd_attention_train: N=%d unsupported (1..640)", N);
+    const long C = (long)heads * kD;
+    AttnLayout lay{2 * C, (long)N * 2 * C, 0, C, (long)N * C, 0, C, (long)N * C, 0, 1, 1};
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qk);
+    return launch_attention(q, q + C, static_cast<const __nv_bfloat16*>(v), scale_v, static_cast<__nv_bfloat16*>(out),
+                            static_cast<__nv_bfloat16*>(raw_out), B, N, heads, lay, stream);
 }
 
 extern "C" int dd_attention_axis(const void* qkv, void* out, int B, int Z, int H, int W, int heads, int head_dim, int axis,
@@ -287,5 +305,6 @@ extern "C" int dd_attention_axis(const void* qkv, void* out, int B, int Z, int H
         n_seq = B * Z * H;
     }
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
-    return launch_attention(q, q + C, q + 2 * C, nullptr, static_cast<__nv_bfloat16*>(out), n_seq, N, heads, lay, stream);
+    return launch_attention(q, q + C, q + 2 * C, nullptr, static_cast<__nv_bfloat16*>(out), nullptr, n_seq, N, heads, lay,
+                            stream);
 }

@@ -1,0 +1,936 @@
+// Backward-pass glue of the EDM2 UNet train step (reference: loss.backward() through
+// modules/unets/unet_edm2_b4.py:110-158,250-296 and modules/mp_tools.py:42-49,268-301,357-373, driven by
+// training/trainer.py:1022-1044).  The two GEMM-shaped halves of every MPConv backward run on the tensor
+// cores (dgrad = dd_mpconv_forward on transposed/flipped weights, wgrad = dd_mpconv_wgrad); this file holds
+// everything between them: the weight-normalisation backward, the derivatives of the fused elementwise block
+// glue (pixel-norm, mp_silu, mp_sum, mp_cat, clip, resample), the attention backward and the embedding heads.
+// Activations are NHWC bf16, all arithmetic is fp32.
+#include "common.cuh"
+#include "dualdiffusion_b200.h"
+
+#include <algorithm>
+#include <math.h>
+
+namespace {
+
+constexpr float kNormEps = 1e-4f;   // modules/mp_tools.py:43
+constexpr float kInvSiluGain = 1.0f / 0.596f;
+
+// d/dx mp_silu(x) = sigmoid(x) * (1 + x * (1 - sigmoid(x))) / 0.596
+__device__ __forceinline__ float mp_silu_grad(float x) {
+    const float s = 1.0f / (1.0f + __expf(-x));
+    return s * (1.0f + x * (1.0f - s)) * kInvSiluGain;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(u[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+__device__ __forceinline__ float block_sum_b(float v, float* red) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    __syncthreads();
+    return t;
+}
+
+inline int grid_for_b(long total, int block, int cap_mult = 8) {
+    const long blocks = (total + block - 1) / block;
+    return (int)std::max<long>(1, std::min<long>(blocks, (long)dd_num_sms() * cap_mult));
+}
+
+// ------------------------------------------------------------------------------------------
+// bf16 weight transpose for dgrad: Wp[g*cout_g + co][tap][ci] -> Wd[g*cin_g + ci][taps-1-tap][co]
+// ------------------------------------------------------------------------------------------
+__global__ void weight_transpose_kernel(const __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ wd, int cout_g,
+                                        int cin_g, int taps) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int g = blockIdx.z / taps, tap = blockIdx.z - g * taps;
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int co = co0 + r, ci = ci0 + threadIdx.x;
+        if (co < cout_g && ci < cin_g)
+            tile[r][threadIdx.x] = wp[((size_t)(g * cout_g + co) * taps + tap) * cin_g + ci];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int ci = ci0 + r, co = co0 + threadIdx.x;
+        if (co < cout_g && ci < cin_g)
+            wd[((size_t)(g * cin_g + ci) * taps + (taps - 1 - tap)) * cout_g + co] = tile[threadIdx.x][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight-prep backward (batched over parameters): dL/dW_eff -> dL/dW (+ dL/dgain)
+//   forward (mp_tools.py:359-364): w_hat = w / (eps + ||w|| / sqrt(f))  [training], w_eff = w_hat * gain / sqrt(f)
+// ------------------------------------------------------------------------------------------
+__global__ void weight_prep_bwd_kernel(const dd_wbwd_desc* __restrict__ descs, int n_descs) {
+    __shared__ float red[32];
+    // find the descriptor owning this row (row_begin is an exclusive prefix sum)
+    int lo = 0, hi = n_descs - 1;
+    const int row = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].row_begin <= row) lo = mid; else hi = mid - 1;
+    }
+    const dd_wbwd_desc d = descs[lo];
+    const int o = row - d.row_begin;
+    if (o >= d.O) return;
+    const int f = d.I_g * d.taps;
+    const float rs = rsqrtf((float)f);
+    int o_src = o;
+    if (d.perm == DD_WPERM_QK) {
+        const int head = o / (2 * d.head_dim), rem = o % (2 * d.head_dim);
+        o_src = (rem & 1) * (d.O / 2) + head * d.head_dim + (rem >> 1);
+    }
+    const float* w = d.w + (size_t)o * f;                       // [i][tap]
+    const float* g = d.dweff + (size_t)o_src * d.row_stride;    // [tap][i]
+    float* dw = d.dw + (size_t)o * f;
+    const float gain = d.gain_host * (d.gain ? *d.gain : 1.f);
+
+    float ss = 0.f, gw = 0.f;
+    for (int j = threadIdx.x; j < f; j += blockDim.x) {         // j = i*taps + tap (parameter order)
+        const int i = j / d.taps, tap = j - i * d.taps;
+        const float wv = w[j], gv = g[tap * d.I_g + i];
+        ss += wv * wv;
+        gw += gv * wv;
+    }
+    ss = block_sum_b(ss, red);
+    gw = block_sum_b(gw, red);
+    const float nrm = sqrtf(ss);
+    float a, b;                  // dw = a * G - b * w
+    float dgain;
+    if (d.normalize) {
+        const float n = kNormEps + nrm * rs;
+        a = gain * rs / n;
+        b = nrm > 0.f ? (gain * rs) * gw * rs / (n * n * nrm) : 0.f;
+        dgain = gw * rs / n;
+    } else {
+        a = gain * rs;
+        b = 0.f;
+        dgain = gw * rs;
+    }
+    for (int j = threadIdx.x; j < f; j += blockDim.x) {
+        const int i = j / d.taps, tap = j - i * d.taps;
+        const float v = a * g[tap * d.I_g + i] - b * w[j];
+        dw[j] = d.accumulate ? dw[j] + v : v;
+    }
+    if (d.dgain && threadIdx.x == 0) atomicAdd(d.dgain, dgain * d.gain_host);
+}
+
+// ------------------------------------------------------------------------------------------
+// y = mp_silu(pre * scale[b][c]) backward:  dpre = coef*dy*silu'(u)*scale,  dscale[b][c] += sum_pix coef*dy*silu'(u)*pre
+// ------------------------------------------------------------------------------------------
+constexpr int kStripPix = 64;
+
+__global__ void silu_scale_bwd_kernel(const uint4* __restrict__ dy, float coef, const uint4* __restrict__ pre,
+                                      const float* __restrict__ scale, uint4* __restrict__ dpre,
+                                      float* __restrict__ dscale, long npix, int nvec, long strips) {
+    const int b = blockIdx.y;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < strips * nvec; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % nvec);
+        const long strip = idx / nvec;
+        float sc[8], acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + (size_t)b * nvec * 8 + v * 8 + j); acc[j] = 0.f; }
+        const long p0 = strip * kStripPix, p1 = min(npix, p0 + kStripPix);
+        for (long pix = p0; pix < p1; ++pix) {
+            const size_t off = ((size_t)b * npix + pix) * nvec + v;
+            float g[8], x[8], o[8];
+            unpack8(__ldg(dy + off), g);
+            unpack8(__ldg(pre + off), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = coef * g[j] * mp_silu_grad(x[j] * sc[j]);
+                o[j] = t * sc[j];
+                acc[j] += t * x[j];
+            }
+            dpre[off] = pack8(o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dscale + (size_t)b * nvec * 8 + v * 8 + j, acc[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// encoder: xn = t0/(eps + rms_c(t0)), s = mp_silu(xn).  Given g (grad of the block's mp_sum wrt xn is ca*g) and
+// ds (grad wrt s): dxn = ca*g + ds*silu'(xn);  dt0 = dxn/n - t0 * <dxn,t0> / (n^2 * C * rms)
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxVecPerLaneB = 10;    // C <= 2560
+
+__global__ void pixnorm_silu_bwd_kernel(const uint4* __restrict__ g, float ca, const uint4* __restrict__ ds,
+                                        const uint4* __restrict__ t0, uint4* __restrict__ dt0, long npix, int C) {
+    const int lane = threadIdx.x & 31;
+    const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const int nvec = C >> 3;
+    uint4 rt[kMaxVecPerLaneB];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLaneB; ++k) {
+        const int v = lane + k * 32;
+        if (v < nvec) {
+            rt[k] = __ldg(t0 + pix * nvec + v);
+            float f[8];
+            unpack8(rt[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+        }
+    }
+    ss = warp_sum(ss);
+    const float rms = sqrtf(ss) * rsqrtf((float)C);
+    const float n = kNormEps + rms, inv = 1.f / n;
+    // pass 1: dxn and <dxn, t0>
+    float dot = 0.f;
+    uint4 rd[kMaxVecPerLaneB];       // dxn kept as packed fp32 pairs would double registers: keep bf16-packed dxn
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLaneB; ++k) {
+        const int v = lane + k * 32;
+        if (v < nvec) {
+            float ft[8], fg[8], fs[8], dx[8];
+            unpack8(rt[k], ft);
+            unpack8(__ldg(g + pix * nvec + v), fg);
+            unpack8(__ldg(ds + pix * nvec + v), fs);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                dx[j] = ca * fg[j] + fs[j] * mp_silu_grad(ft[j] * inv);
+                dot += dx[j] * ft[j];
+            }
+            rd[k] = pack8(dx);
+        }
+    }
+    dot = warp_sum(dot);
+    const float kb = rms > 0.f ? dot / (n * n * (float)C * rms) : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLaneB; ++k) {
+        const int v = lane + k * 32;
+        if (v < nvec) {
+            float ft[8], dx[8], o[8];
+            unpack8(rt[k], ft);
+            unpack8(rd[k], dx);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = dx[j] * inv - ft[j] * kb;
+            dt0[pix * nvec + v] = pack8(o);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder input backward: xc = [wa*up(a), wb*b], s = mp_silu(xc).
+//   dxc = c1*d_xc + d_s*silu'(xc);  da = mask(a) * wa * (sum over the 2x2 replicas of dxc[..:Ca]);  db = wb * dxc[Ca:]
+// ------------------------------------------------------------------------------------------
+__global__ void cat_silu_bwd_kernel(const uint4* __restrict__ d_xc, float c1, const uint4* __restrict__ d_s,
+                                    const uint4* __restrict__ xc, const uint4* __restrict__ a_prev, float clip, float wa,
+                                    float wb, int up, uint4* __restrict__ da, uint4* __restrict__ db, int B, int H, int W,
+                                    int va, int vb) {
+    const int vt = va + vb;
+    const int Ha = up ? H >> 1 : H, Wa = up ? W >> 1 : W;
+    const long total_a = (long)B * Ha * Wa * va, total_b = (long)B * H * W * vb;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_a + total_b; idx += (long)gridDim.x * blockDim.x) {
+        if (idx < total_a) {
+            const int v = (int)(idx % va);
+            const long apix = idx / va;
+            float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const int reps = up ? 2 : 1;
+            const int w = (int)(apix % Wa), h = (int)((apix / Wa) % Ha), bb = (int)(apix / ((long)Wa * Ha));
+            for (int dy = 0; dy < reps; ++dy)
+                for (int dx = 0; dx < reps; ++dx) {
+                    const long pix = ((long)bb * H + h * reps + dy) * W + w * reps + dx;
+                    float g1[8], g2[8], x[8];
+                    unpack8(__ldg(d_xc + pix * vt + v), g1);
+                    unpack8(__ldg(d_s + pix * vt + v), g2);
+                    unpack8(__ldg(xc + pix * vt + v), x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += c1 * g1[j] + g2[j] * mp_silu_grad(x[j]);
+                }
+            float o[8];
+            if (a_prev) {
+                float ap[8];
+                unpack8(__ldg(a_prev + idx), ap);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fabsf(ap[j]) < clip ? wa * acc[j] : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = wa * acc[j];
+            }
+            da[idx] = pack8(o);
+        } else {
+            const long k = idx - total_a;
+            const int v = (int)(k % vb);
+            const long pix = k / vb;
+            float g1[8], g2[8], x[8], o[8];
+            unpack8(__ldg(d_xc + pix * vt + va + v), g1);
+            unpack8(__ldg(d_s + pix * vt + va + v), g2);
+            unpack8(__ldg(xc + pix * vt + va + v), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = wb * (c1 * g1[j] + g2[j] * mp_silu_grad(x[j]));
+            db[k] = pack8(o);
+        }
+    }
+}
+
+// encoder chain: gradient of a block output = mask(x_prev) * (avgpool-backward(dx0) or dx0, plus the skip gradient)
+__global__ void enc_grad_combine_kernel(const uint4* __restrict__ dx0, int down, const uint4* __restrict__ dskip,
+                                        const uint4* __restrict__ x_prev, float clip, uint4* __restrict__ out, int B, int H,
+                                        int W, int nvec) {
+    const long total = (long)B * H * W * nvec;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        float a[8], o[8];
+        if (down) {
+            const int v = (int)(idx % nvec);
+            const long pix = idx / nvec;
+            const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+            unpack8(__ldg(dx0 + (((long)b * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * nvec + v), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] *= 0.25f;
+        } else {
+            unpack8(__ldg(dx0 + idx), a);
+        }
+        if (dskip) {
+            float s[8];
+            unpack8(__ldg(dskip + idx), s);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += s[j];
+        }
+        if (x_prev) {
+            float xp[8];
+            unpack8(__ldg(x_prev + idx), xp);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fabsf(xp[j]) < clip ? a[j] : 0.f;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = a[j];
+        }
+        out[idx] = pack8(o);
+    }
+}
+
+// attention input: x2 feeds mp_sum (ca*g3), attn_v (dxv) and attn_qk through xs = x2*c_qk (dxs):
+//   dx2 = ca*g3 + dxv + dxs*c_qk[b][c];   dc_qk[b][c] += sum_pix dxs*x2
+__global__ void attn_in_bwd_kernel(const uint4* __restrict__ g3, float ca, const uint4* __restrict__ dxv,
+                                   const uint4* __restrict__ dxs, const uint4* __restrict__ x2,
+                                   const float* __restrict__ c_qk, uint4* __restrict__ dx2, float* __restrict__ dc_qk,
+                                   long npix, int nvec, long strips) {
+    const int b = blockIdx.y;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < strips * nvec; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % nvec);
+        const long strip = idx / nvec;
+        float sc[8], acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(c_qk + (size_t)b * nvec * 8 + v * 8 + j); acc[j] = 0.f; }
+        const long p0 = strip * kStripPix, p1 = min(npix, p0 + kStripPix);
+        for (long pix = p0; pix < p1; ++pix) {
+            const size_t off = ((size_t)b * npix + pix) * nvec + v;
+            float g[8], dv[8], dsx[8], x[8], o[8];
+            unpack8(__ldg(g3 + off), g);
+            unpack8(__ldg(dxv + off), dv);
+            unpack8(__ldg(dxs + off), dsx);
+            unpack8(__ldg(x2 + off), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] = ca * g[j] + dv[j] + dsx[j] * sc[j];
+                acc[j] += dsx[j] * x[j];
+            }
+            dx2[off] = pack8(o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dc_qk + (size_t)b * nvec * 8 + v * 8 + j, acc[j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention backward (unet_edm2_b4.py:137-148): q,k,v cosine-normalised over the 64 head channels, P = softmax(q k^T/8),
+// a = P v.  Two threads per token row, each owning 32 of the 64 head channels.
+//   kernel A (per query):  L_i = logsumexp_j s_ij,  D_i = <da_i, a_i>,  dq
+//   kernel B (per key)  :  dk, dv   (recomputes s_ij from the staged normalised q rows and L_i)
+// ------------------------------------------------------------------------------------------
+constexpr int kAD = 64, kAHalf = 32;
+constexpr int kARows = 64;         // token rows per CTA (128 threads)
+constexpr int kATile = 32;         // staged rows of the other operand per step
+
+// stage `kATile` rows [r0, r0+kATile) of a head (optionally cosine-normalised) as fp32 into smem[kATile][64]
+__device__ __forceinline__ void stage_rows_f32(const __nv_bfloat16* __restrict__ base, long tok_stride, int r0, int N,
+                                               bool normalize, float* __restrict__ dst) {
+    // 128 threads: 4 threads per row (16 channels each)
+    const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
+    float f[16];
+    float ss = 0.f;
+    const bool ok = r0 + r < N;
+    if (ok) {
+        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)(r0 + r) * tok_stride + part * 16);
+        float a[8], b[8];
+        unpack8(__ldg(src), a);
+        unpack8(__ldg(src + 1), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { f[j] = a[j]; f[8 + j] = b[j]; ss += a[j] * a[j] + b[j] * b[j]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    const float inv = normalize ? 1.f / (kNormEps + sqrtf(ss) * 0.125f) : 1.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[r * kAD + part * 16 + j] = f[j] * inv;
+}
+
+// load this thread's 32-channel half of row `row` (zeros if out of range); returns the sum of squares of the half
+__device__ __forceinline__ float load_half(const __nv_bfloat16* __restrict__ base, long tok_stride, int row, int N, int half,
+                                           float (&f)[kAHalf]) {
+    float ss = 0.f;
+    if (row < N) {
+        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)row * tok_stride + half * kAHalf);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float a[8];
+            unpack8(__ldg(src + q), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { f[q * 8 + j] = a[j]; ss += a[j] * a[j]; }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kAHalf; ++j) f[j] = 0.f;
+    }
+    return ss;
+}
+
+__device__ __forceinline__ void store_half(__nv_bfloat16* __restrict__ base, long tok_stride, int row, int half,
+                                           const float (&f)[kAHalf]) {
+    uint4* dst = reinterpret_cast<uint4*>(base + (size_t)row * tok_stride + half * kAHalf);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = f[q * 8 + j];
+        dst[q] = pack8(a);
+    }
+}
+
+// backward of x_hat = x / (eps + ||x||/8): dx = dxh/n - x * <dxh, x> / (n^2 * ||x|| * 8); `dot` and `ss` are full-row sums
+__device__ __forceinline__ void norm_bwd_half(const float (&x)[kAHalf], float (&dxh)[kAHalf], float ss, float dot) {
+    const float nrm = sqrtf(ss);
+    const float n = kNormEps + nrm * 0.125f;
+    const float a = 1.f / n, b = nrm > 0.f ? dot * 0.125f / (n * n * nrm) : 0.f;
+#pragma unroll
+    for (int j = 0; j < kAHalf; ++j) dxh[j] = dxh[j] * a - x[j] * b;
+}
+
+__global__ void __launch_bounds__(128)
+attention_bwd_q_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
+                       const __nv_bfloat16* __restrict__ a_raw, const __nv_bfloat16* __restrict__ da,
+                       __nv_bfloat16* __restrict__ dqk, float* __restrict__ stats, int N, int heads) {
+    __shared__ __align__(16) float Ks[kATile * kAD];
+    __shared__ __align__(16) float Vs[kATile * kAD];
+    const int C = heads * kAD;
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int row = blockIdx.x * kARows + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    const __nv_bfloat16* q_base = qk + (size_t)b * N * 2 * C + head * kAD;
+    const __nv_bfloat16* k_base = q_base + C;
+    const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kAD;
+    const __nv_bfloat16* a_base = a_raw + (size_t)b * N * C + head * kAD;
+    const __nv_bfloat16* da_base = da + (size_t)b * N * C + head * kAD;
+
+    float q[kAHalf], qn[kAHalf], go[kAHalf], dq[kAHalf];
+    float ssq = load_half(q_base, 2 * C, row, N, half, q);
+    ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
+    const float invq = 1.f / (kNormEps + sqrtf(ssq) * 0.125f);
+    float D = 0.f;
+    {
+        float ao[kAHalf];
+        load_half(a_base, C, row, N, half, ao);
+        load_half(da_base, C, row, N, half, go);
+#pragma unroll
+        for (int j = 0; j < kAHalf; ++j) { qn[j] = q[j] * invq; dq[j] = 0.f; D += ao[j] * go[j]; }
+        D += __shfl_xor_sync(0xffffffffu, D, 1);
+    }
+    // pass 1: logsumexp of the scores
+    float m = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < N; k0 += kATile) {
+        __syncthreads();
+        stage_rows_f32(k_base, 2 * C, k0, N, true, Ks);
+        __syncthreads();
+        const int kn = min(kATile, N - k0);
+        for (int jj = 0; jj < kn; ++jj) {
+            const float4* kr = reinterpret_cast<const float4*>(Ks + jj * kAD + half * kAHalf);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 kk = kr[c];
+                s += qn[4 * c] * kk.x + qn[4 * c + 1] * kk.y + qn[4 * c + 2] * kk.z + qn[4 * c + 3] * kk.w;
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s *= 0.125f;
+            const float mn = fmaxf(m, s);
+            l = l * __expf(m - mn) + __expf(s - mn);
+            m = mn;
+        }
+    }
+    const float L = m + __logf(l);
+    // pass 2: dq
+    for (int k0 = 0; k0 < N; k0 += kATile) {
+        __syncthreads();
+        stage_rows_f32(k_base, 2 * C, k0, N, true, Ks);
+        stage_rows_f32(v_base, C, k0, N, true, Vs);
+        __syncthreads();
+        const int kn = min(kATile, N - k0);
+        for (int jj = 0; jj < kn; ++jj) {
+            const float4* kr = reinterpret_cast<const float4*>(Ks + jj * kAD + half * kAHalf);
+            const float4* vr = reinterpret_cast<const float4*>(Vs + jj * kAD + half * kAHalf);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 kk = kr[c], vv = vr[c];
+                s += qn[4 * c] * kk.x + qn[4 * c + 1] * kk.y + qn[4 * c + 2] * kk.z + qn[4 * c + 3] * kk.w;
+                dp += go[4 * c] * vv.x + go[4 * c + 1] * vv.y + go[4 * c + 2] * vv.z + go[4 * c + 3] * vv.w;
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+            const float p = __expf(s * 0.125f - L);
+            const float dsv = p * (dp - D) * 0.125f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 kk = kr[c];
+                dq[4 * c] += dsv * kk.x; dq[4 * c + 1] += dsv * kk.y; dq[4 * c + 2] += dsv * kk.z; dq[4 * c + 3] += dsv * kk.w;
+            }
+        }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kAHalf; ++j) dot += dq[j] * q[j];
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    norm_bwd_half(q, dq, ssq, dot);
+    if (row < N) {
+        store_half(dqk + (size_t)b * N * 2 * C + head * kAD, 2 * C, row, half, dq);
+        if (half == 0) {
+            float* st = stats + (((size_t)b * heads + head) * N + row) * 2;
+            st[0] = L;
+            st[1] = D;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+attention_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
+                        const __nv_bfloat16* __restrict__ da, const float* __restrict__ stats,
+                        __nv_bfloat16* __restrict__ dqk, __nv_bfloat16* __restrict__ dv_out, int N, int heads) {
+    __shared__ __align__(16) float Qs[kATile * kAD];
+    __shared__ __align__(16) float Gs[kATile * kAD];
+    __shared__ float Ls[kATile], Ds[kATile];
+    const int C = heads * kAD;
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int row = blockIdx.x * kARows + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    const __nv_bfloat16* q_base = qk + (size_t)b * N * 2 * C + head * kAD;
+    const __nv_bfloat16* k_base = q_base + C;
+    const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kAD;
+    const __nv_bfloat16* da_base = da + (size_t)b * N * C + head * kAD;
+    const float* st = stats + ((size_t)b * heads + head) * N * 2;
+
+    float k[kAHalf], kn[kAHalf], vv[kAHalf], vn[kAHalf], dk[kAHalf], dvv[kAHalf];
+    float ssk = load_half(k_base, 2 * C, row, N, half, k);
+    float ssv = load_half(v_base, C, row, N, half, vv);
+    ssk += __shfl_xor_sync(0xffffffffu, ssk, 1);
+    ssv += __shfl_xor_sync(0xffffffffu, ssv, 1);
+    const float invk = 1.f / (kNormEps + sqrtf(ssk) * 0.125f), invv = 1.f / (kNormEps + sqrtf(ssv) * 0.125f);
+#pragma unroll
+    for (int j = 0; j < kAHalf; ++j) { kn[j] = k[j] * invk; vn[j] = vv[j] * invv; dk[j] = 0.f; dvv[j] = 0.f; }
+
+    for (int i0 = 0; i0 < N; i0 += kATile) {
+        __syncthreads();
+        stage_rows_f32(q_base, 2 * C, i0, N, true, Qs);
+        stage_rows_f32(da_base, C, i0, N, false, Gs);
+        if (threadIdx.x < kATile) {
+            const int i = i0 + threadIdx.x;
+            Ls[threadIdx.x] = i < N ? st[2 * i] : 0.f;
+            Ds[threadIdx.x] = i < N ? st[2 * i + 1] : 0.f;
+        }
+        __syncthreads();
+        const int in = min(kATile, N - i0);
+        for (int ii = 0; ii < in; ++ii) {
+            const float4* qr = reinterpret_cast<const float4*>(Qs + ii * kAD + half * kAHalf);
+            const float4* gr = reinterpret_cast<const float4*>(Gs + ii * kAD + half * kAHalf);
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 qq = qr[c], gg = gr[c];
+                s += kn[4 * c] * qq.x + kn[4 * c + 1] * qq.y + kn[4 * c + 2] * qq.z + kn[4 * c + 3] * qq.w;
+                dp += vn[4 * c] * gg.x + vn[4 * c + 1] * gg.y + vn[4 * c + 2] * gg.z + vn[4 * c + 3] * gg.w;
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+            const float p = __expf(s * 0.125f - Ls[ii]);
+            const float dsv = p * (dp - Ds[ii]) * 0.125f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 qq = qr[c], gg = gr[c];
+                dk[4 * c] += dsv * qq.x; dk[4 * c + 1] += dsv * qq.y; dk[4 * c + 2] += dsv * qq.z; dk[4 * c + 3] += dsv * qq.w;
+                dvv[4 * c] += p * gg.x; dvv[4 * c + 1] += p * gg.y; dvv[4 * c + 2] += p * gg.z; dvv[4 * c + 3] += p * gg.w;
+            }
+        }
+    }
+    float dotk = 0.f, dotv = 0.f;
+#pragma unroll
+    for (int j = 0; j < kAHalf; ++j) { dotk += dk[j] * k[j]; dotv += dvv[j] * vv[j]; }
+    dotk += __shfl_xor_sync(0xffffffffu, dotk, 1);
+    dotv += __shfl_xor_sync(0xffffffffu, dotv, 1);
+    norm_bwd_half(k, dk, ssk, dotk);
+    norm_bwd_half(vv, dvv, ssv, dotv);
+    if (row < N) {
+        store_half(dqk + (size_t)b * N * 2 * C + C + head * kAD, 2 * C, row, half, dk);
+        store_half(dv_out + (size_t)b * N * C + head * kAD, C, row, half, dvv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding heads
+// ------------------------------------------------------------------------------------------
+// emb_linear*: c[b][o] = bias + gain * sum_i w_hat[o][i] emb[b][g*I+i] / sqrt(I).  Stage 1 (warp per row): row scale and
+// dW_eff[o][i] = sum_b dc[b][o] emb[b][g*I+i].
+__global__ void emb_affine_bwd_w_kernel(const dd_affine_bwd_desc* __restrict__ descs, const float* __restrict__ emb, int B,
+                                        int cemb) {
+    const dd_affine_bwd_desc d = descs[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= d.O) return;
+    const int g = o / (d.O / d.groups);
+    const float* e0 = emb + (size_t)g * d.I;
+    float ss = 0.f;
+    for (int i = lane; i < d.I; i += 32) { const float wv = d.w[(size_t)o * d.I + i]; ss += wv * wv; }
+    ss = warp_sum(ss);
+    float scale = (d.gain ? *d.gain : 1.f) * rsqrtf((float)d.I);
+    if (d.normalize) scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)d.I));
+    if (lane == 0) d.rowscale[o] = scale;
+    for (int i = lane; i < d.I; i += 32) {
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += d.dout[(size_t)b * d.O + o] * e0[(size_t)b * cemb + i];
+        d.dweff[(size_t)o * d.I + i] = acc;
+    }
+}
+
+// Stage 2: demb[b][g*I+i] += sum_o dc[b][o] * rowscale[o] * w[o][i]   (thread per input column, rows chunked over blockIdx.z)
+__global__ void emb_affine_bwd_x_kernel(const dd_affine_bwd_desc* __restrict__ descs, float* __restrict__ demb, int B,
+                                        int cemb, int row_chunks) {
+    const dd_affine_bwd_desc d = descs[blockIdx.y];
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;       // g*I + i
+    if (col >= d.groups * d.I) return;
+    const int g = col / d.I, i = col - g * d.I;
+    const int rows_g = d.O / d.groups;
+    const int r0 = (int)((long)blockIdx.z * rows_g / row_chunks), r1 = (int)((long)(blockIdx.z + 1) * rows_g / row_chunks);
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int r = r0; r < r1; ++r) {
+            const int o = g * rows_g + r;
+            const float wv = d.w[(size_t)o * d.I + i] * d.rowscale[o];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (b0 + j < B) acc[j] += d.dout[(size_t)(b0 + j) * d.O + o] * wv;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (b0 + j < B) atomicAdd(demb + (size_t)(b0 + j) * cemb + col, acc[j]);
+    }
+}
+
+// emb[b][o] = mp_silu(m), m = (e + t*(l - e))/nt, e = w_eff[o] . fourier(ln(sigma_b)/4)   (unet_edm2_b4.py:273-276)
+__global__ void noise_embedding_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ freqs,
+                                           const float* __restrict__ phases, int cnoise, const float* __restrict__ w,
+                                           int normalize, const float* __restrict__ label, float t,
+                                           const float* __restrict__ demb, float* __restrict__ dweff,
+                                           float* __restrict__ dlabel, int B, int cemb) {
+    extern __shared__ float four[];        // [B][cnoise]
+    for (int k = threadIdx.x; k < B * cnoise; k += blockDim.x) {
+        const int b = k / cnoise, i = k - b * cnoise;
+        four[k] = cosf(logf(sigma[b]) * 0.25f * freqs[i] + phases[i]) * 1.41421356237f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= cemb) return;
+    float ss = 0.f;
+    for (int i = lane; i < cnoise; i += 32) { const float wv = w[(size_t)o * cnoise + i]; ss += wv * wv; }
+    ss = warp_sum(ss);
+    float scale = rsqrtf((float)cnoise);
+    if (normalize) scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)cnoise));
+    const float nt = rsqrtf((1.f - t) * (1.f - t) + t * t);
+    for (int i0 = 0; i0 < cnoise; i0 += 32) dweff[(size_t)o * cnoise + i0 + lane] = 0.f;   // cnoise % 32 == 0 (checked)
+    for (int b = 0; b < B; ++b) {
+        float acc = 0.f;
+        for (int i = lane; i < cnoise; i += 32) acc += w[(size_t)o * cnoise + i] * four[b * cnoise + i];
+        acc = warp_sum(acc);
+        const float e = acc * scale;
+        const float l = label[(size_t)b * cemb + o];
+        const float m = (e + t * (l - e)) * nt;
+        const float dm = demb[(size_t)b * cemb + o] * mp_silu_grad(m);
+        const float de = dm * (1.f - t) * nt;
+        if (lane == 0) dlabel[(size_t)b * cemb + o] = dm * t * nt;
+        for (int i = lane; i < cnoise; i += 32) dweff[(size_t)o * cnoise + i] += de * four[b * cnoise + i];
+    }
+}
+
+// get_embeddings backward (unet_edm2_b4.py:232-235): out[b][o] = (u + t_b (c - u))/n_b, c = w_l_eff[o] . normalize(emb_in[b]),
+// u = w_u_eff[o].  Writes dL/dw_l_eff [cemb][I] and dL/dw_u_eff [cemb].
+__global__ void label_embedding_bwd_kernel(const float* __restrict__ emb_in, int Bc, int I, const float* __restrict__ mask,
+                                           int Bm, const float* __restrict__ dout, float* __restrict__ dweff_label,
+                                           float* __restrict__ dweff_uncond, int cemb) {
+    extern __shared__ float ehat[];        // [Bc][I]
+    __shared__ float red[32];
+    for (int b = 0; b < Bc; ++b) {
+        float ss = 0.f;
+        for (int i = threadIdx.x; i < I; i += blockDim.x) { const float v = emb_in[(size_t)b * I + i]; ss += v * v; }
+        ss = block_sum_b(ss, red);
+        const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)I));
+        for (int i = threadIdx.x; i < I; i += blockDim.x) ehat[b * I + i] = emb_in[(size_t)b * I + i] * inv;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= cemb) return;
+    float du = 0.f;
+    for (int i = lane; i < I; i += 32) {
+        float acc = 0.f;
+        for (int b = 0; b < Bm; ++b) {
+            const float t = mask[b];
+            const float nt = rsqrtf((1.f - t) * (1.f - t) + t * t);
+            acc += dout[(size_t)b * cemb + o] * t * nt * ehat[(Bc == 1 ? 0 : b) * I + i];
+        }
+        dweff_label[(size_t)o * I + i] = acc;
+    }
+    if (lane == 0) {
+        for (int b = 0; b < Bm; ++b) {
+            const float t = mask[b];
+            du += dout[(size_t)b * cemb + o] * (1.f - t) * rsqrtf((1.f - t) * (1.f - t) + t * t);
+        }
+        dweff_uncond[o] = du;
+    }
+}
+
+// get_sigma_loss_logvar backward (:237-238): out[i] = w . fourier(ln(sigma_i)/4) / sqrt(n)
+__global__ void logvar_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ freqs,
+                                  const float* __restrict__ phases, int n, const float* __restrict__ dout, int count,
+                                  float* __restrict__ dw, int accumulate) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float acc = 0.f;
+    for (int i = 0; i < count; ++i) acc += dout[i] * cosf(logf(sigma[i]) * 0.25f * freqs[j] + phases[j]);
+    acc *= 1.41421356237f * rsqrtf((float)n);
+    dw[j] = accumulate ? dw[j] + acc : acc;
+}
+
+// UNet head backward: D = c_skip*x_in + c_out*F (optionally D' = mp_sum(x_ref[:, :-1], D, t = x_ref[:, -1:])), fp32 NCHW.
+// Writes dF as NHWC bf16 with the channel dimension zero-padded to `Cpad` (the dgrad / wgrad kernels' operand).
+__global__ void head_grad_kernel(const float* __restrict__ dD, const float* __restrict__ sigma, float sigma_data,
+                                 const float* __restrict__ x_ref, __nv_bfloat16* __restrict__ dF, int B, int Cout, int H,
+                                 int W, int Cpad) {
+    const long total = (long)B * H * W * Cpad;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % Cpad);
+        const long pix = idx / Cpad;
+        float val = 0.f;
+        if (c < Cout) {
+            const long hw = pix % ((long)H * W);
+            const int b = (int)(pix / ((long)H * W));
+            const float sg = sigma[b];
+            const float c_out = sg * sigma_data * rsqrtf(sg * sg + sigma_data * sigma_data);
+            val = dD[((size_t)b * Cout + c) * H * W + hw] * c_out;
+            if (x_ref) {
+                const float tt = x_ref[((size_t)b * (Cout + 1) + Cout) * H * W + hw];
+                val *= tt * rsqrtf((1.f - tt) * (1.f - tt) + tt * tt);
+            }
+        }
+        dF[idx] = __float2bfloat16_rn(val);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int dd_weight_transpose(const void* w_prepped, void* out, int Cout, int cin_g, int taps, int groups,
+                                   void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(w_prepped && out && Cout > 0 && cin_g > 0 && taps > 0 && groups > 0 && Cout % groups == 0,
+               "dd_weight_transpose: bad arguments");
+    const int cout_g = Cout / groups;
+    DD_REQUIRE((long)groups * taps <= 65535, "dd_weight_transpose: groups*taps exceeds the grid limit");
+    const dim3 grid(ceil_div(cin_g, 32), ceil_div(cout_g, 32), groups * taps);
+    weight_transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(w_prepped),
+                                                             static_cast<__nv_bfloat16*>(out), cout_g, cin_g, taps);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_weight_prep_bwd(const dd_wbwd_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_prep_bwd: bad arguments");
+    weight_prep_bwd_kernel<<<total_rows, 128, 0, stream>>>(descs_dev, n_descs);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_silu_scale_bwd(const void* dy, float coef, const void* pre, const float* scale, void* dpre,
+                                 float* dscale, int B, long npix, int C, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(dy && pre && scale && dpre && dscale, "dd_silu_scale_bwd: null pointer");
+    DD_REQUIRE(C % 8 == 0 && B > 0 && B <= 65535, "dd_silu_scale_bwd: bad shape");
+    if (npix == 0) return 0;
+    const long strips = (npix + kStripPix - 1) / kStripPix;
+    const dim3 grid(grid_for_b(strips * (C / 8), 128), B);
+    silu_scale_bwd_kernel<<<grid, 128, 0, stream>>>(static_cast<const uint4*>(dy), coef, static_cast<const uint4*>(pre),
+                                                    scale, static_cast<uint4*>(dpre), dscale, npix, C / 8, strips);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_pixnorm_silu_bwd(const void* g, float ca, const void* ds, const void* t0, void* dt0, long npix, int C,
+                                   void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(g && ds && t0 && dt0, "dd_pixnorm_silu_bwd: null pointer");
+    DD_REQUIRE(C % 8 == 0 && C <= kMaxVecPerLaneB * 256, "dd_pixnorm_silu_bwd: C=%d unsupported", C);
+    if (npix == 0) return 0;
+    const int warps = 4;
+    pixnorm_silu_bwd_kernel<<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, stream>>>(
+        static_cast<const uint4*>(g), ca, static_cast<const uint4*>(ds), static_cast<const uint4*>(t0),
+        static_cast<uint4*>(dt0), npix, C);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_cat_silu_bwd(const void* d_xc, float c1, const void* d_s, const void* xc, const void* a_prev, float clip,
+                               float wa, float wb, int upsample, void* da, void* db, int B, int H, int W, int Ca, int Cb,
+                               void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(d_xc && d_s && xc && da, "dd_cat_silu_bwd: null pointer");
+    DD_REQUIRE(Ca > 0 && Ca % 8 == 0 && Cb % 8 == 0 && (Cb == 0 || db), "dd_cat_silu_bwd: bad arguments");
+    DD_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "dd_cat_silu_bwd: upsample needs even output size");
+    const long total = (long)B * (upsample ? H / 2 : H) * (upsample ? W / 2 : W) * (Ca / 8) + (long)B * H * W * (Cb / 8);
+    if (total == 0) return 0;
+    cat_silu_bwd_kernel<<<grid_for_b(total, 256), 256, 0, stream>>>(
+        static_cast<const uint4*>(d_xc), c1, static_cast<const uint4*>(d_s), static_cast<const uint4*>(xc),
+        static_cast<const uint4*>(a_prev), clip > 0.f ? clip : INFINITY, wa, wb, upsample, static_cast<uint4*>(da),
+        static_cast<uint4*>(db), B, H, W, Ca / 8, Cb / 8);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_enc_grad_combine(const void* dx0, int down, const void* dskip, const void* x_prev, float clip, void* out,
+                                   int B, int H, int W, int C, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(dx0 && out && C % 8 == 0, "dd_enc_grad_combine: bad arguments");
+    DD_REQUIRE(!down || (H % 2 == 0 && W % 2 == 0), "dd_enc_grad_combine: downsampled block needs even size");
+    const long total = (long)B * H * W * (C / 8);
+    if (total == 0) return 0;
+    enc_grad_combine_kernel<<<grid_for_b(total, 256), 256, 0, stream>>>(
+        static_cast<const uint4*>(dx0), down, static_cast<const uint4*>(dskip), static_cast<const uint4*>(x_prev),
+        clip > 0.f ? clip : INFINITY, static_cast<uint4*>(out), B, H, W, C / 8);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_attn_in_bwd(const void* g3, float ca, const void* dxv, const void* dxs, const void* x2,
+                              const float* c_qk, void* dx2, float* dc_qk, int B, long npix, int C, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(g3 && dxv && dxs && x2 && c_qk && dx2 && dc_qk, "dd_attn_in_bwd: null pointer");
+    DD_REQUIRE(C % 8 == 0 && B > 0 && B <= 65535, "dd_attn_in_bwd: bad shape");
+    if (npix == 0) return 0;
+    const long strips = (npix + kStripPix - 1) / kStripPix;
+    const dim3 grid(grid_for_b(strips * (C / 8), 128), B);
+    attn_in_bwd_kernel<<<grid, 128, 0, stream>>>(static_cast<const uint4*>(g3), ca, static_cast<const uint4*>(dxv),
+                                                 static_cast<const uint4*>(dxs), static_cast<const uint4*>(x2), c_qk,
+                                                 static_cast<uint4*>(dx2), dc_qk, npix, C / 8, strips);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_attention_bwd(const void* qk, const void* v, const void* a_raw, const void* d_a, void* dqk, void* dv,
+                                float* stats_ws, int B, int N, int heads, int head_dim, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(qk && v && a_raw && d_a && dqk && dv && stats_ws, "dd_attention_bwd: null pointer");
+    DD_REQUIRE(head_dim == kAD, "dd_attention_bwd: head_dim=%d unsupported (64)", head_dim);
+    DD_REQUIRE(N > 0 && B > 0 && B <= 65535 && heads <= 65535, "dd_attention_bwd: bad shape");
+    const dim3 grid(ceil_div(N, kARows), heads, B);
+    attention_bwd_q_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+                                                     static_cast<const __nv_bfloat16*>(v),
+                                                     static_cast<const __nv_bfloat16*>(a_raw),
+                                                     static_cast<const __nv_bfloat16*>(d_a),
+                                                     static_cast<__nv_bfloat16*>(dqk), stats_ws, N, heads);
+    DD_CHECK_LAUNCH();
+    attention_bwd_kv_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+                                                      static_cast<const __nv_bfloat16*>(v),
+                                                      static_cast<const __nv_bfloat16*>(d_a), stats_ws,
+                                                      static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), N,
+                                                      heads);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_emb_affine_bwd(const dd_affine_bwd_desc* descs_dev, int n_descs, int max_O, int max_cols,
+                                 const float* emb, float* demb, int B, int cemb, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && emb && demb && n_descs > 0 && max_O > 0 && max_cols > 0, "dd_emb_affine_bwd: bad arguments");
+    emb_affine_bwd_w_kernel<<<dim3(ceil_div(max_O, 8), n_descs), 256, 0, stream>>>(descs_dev, emb, B, cemb);
+    DD_CHECK_LAUNCH();
+    const int row_chunks = 4;
+    emb_affine_bwd_x_kernel<<<dim3(ceil_div(max_cols, 128), n_descs, row_chunks), 128, 0, stream>>>(descs_dev, demb, B,
+                                                                                                     cemb, row_chunks);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_noise_embedding_bwd(const float* sigma, const float* freqs, const float* phases, int cnoise,
+                                      const float* w_noise, int normalize, const float* label_emb, float label_balance,
+                                      const float* demb, float* dweff, float* dlabel, int B, int cemb, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(sigma && freqs && phases && w_noise && label_emb && demb && dweff && dlabel,
+               "dd_noise_embedding_bwd: null pointer");
+    DD_REQUIRE(cnoise % 32 == 0, "dd_noise_embedding_bwd: cnoise=%d must be a multiple of 32", cnoise);
+    const size_t smem = (size_t)B * cnoise * sizeof(float);
+    DD_REQUIRE(smem <= 48 * 1024, "dd_noise_embedding_bwd: batch %d x cnoise %d exceeds shared memory", B, cnoise);
+    noise_embedding_bwd_kernel<<<ceil_div(cemb, 8), 256, smem, stream>>>(sigma, freqs, phases, cnoise, w_noise, normalize,
+                                                                        label_emb, label_balance, demb, dweff, dlabel, B,
+                                                                        cemb);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_label_embedding_bwd(const float* emb_in, int Bc, int I, const float* mask, int Bm, const float* dout,
+                                      float* dweff_label, float* dweff_uncond, int cemb, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(emb_in && mask && dout && dweff_label && dweff_uncond, "dd_label_embedding_bwd: null pointer");
+    DD_REQUIRE(Bc == 1 || Bc == Bm, "dd_label_embedding_bwd: embedding batch %d does not broadcast to mask batch %d", Bc, Bm);
+    const size_t smem = (size_t)Bc * I * sizeof(float);
+    DD_REQUIRE(smem <= 48 * 1024, "dd_label_embedding_bwd: batch %d x dim %d exceeds shared memory", Bc, I);
+    label_embedding_bwd_kernel<<<ceil_div(cemb, 8), 256, smem, stream>>>(emb_in, Bc, I, mask, Bm, dout, dweff_label,
+                                                                        dweff_uncond, cemb);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_sigma_logvar_bwd(const float* sigma, int count, const float* freqs, const float* phases, int n,
+                                   const float* dout, float* dw, int accumulate, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(sigma && freqs && phases && dout && dw, "dd_sigma_logvar_bwd: null pointer");
+    if (n == 0) return 0;
+    logvar_bwd_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(sigma, freqs, phases, n, dout, count, dw, accumulate);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_head_grad(const float* dD, const float* sigma, float sigma_data, const float* x_ref, void* dF, int B,
+                            int Cout, int H, int W, int Cpad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(dD && sigma && dF && Cpad >= Cout && Cpad % 8 == 0, "dd_head_grad: bad arguments");
+    const long total = (long)B * H * W * Cpad;
+    if (total == 0) return 0;
+    head_grad_kernel<<<grid_for_b(total, 256), 256, 0, stream>>>(dD, sigma, sigma_data, x_ref,
+                                                                 static_cast<__nv_bfloat16*>(dF), B, Cout, H, W, Cpad);
+    DD_CHECK_LAUNCH();
+    return 0;
+}

@@ -152,6 +152,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[sub16 * 16 + i]);
                 const int ch = ch0 + c;
+                if (p.epi2 == DD_EPI2_RAW) store_bf16x16(p.out2 + pix * p.Cout + ch, v);   // pre-activation, for backward
                 if (p.epi == DD_EPI_HEAD) {
                     // D = c_skip*x_in + c_out*F(x) (unet_edm2_b4.py:291), optional x_ref blend (:293-294)
                     const float sg = __ldg(p.sigma + b), sd2 = p.sigma_data * p.sigma_data;
@@ -200,7 +201,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                     }
                 }
                 if (!p.dbg_nostore) store_bf16x16(p.out + pix * p.Cout + ch, v);
-                if (p.epi2 != DD_EPI2_NONE) {
+                if (p.epi2 != DD_EPI2_NONE && p.epi2 != DD_EPI2_RAW) {
                     if (p.epi2 == DD_EPI2_SILU) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = mp_silu_fast(v[i]);

@@ -294,3 +294,195 @@ def attention_axis(qkv: Tensor, heads: int, axis: int, head_dim: int = 64) -> Te
     L.check(L.load().dd_attention_axis(L.ptr(qkv), L.ptr(out), B, Z, H, W, heads, head_dim, axis, L.stream_ptr()))
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# backward pass (train step): thin wrappers over the dd_*_bwd / dd_mpconv_wgrad entry points
+# ---------------------------------------------------------------------------------------------------------
+def attention_train(qk: Tensor, v: Tensor, scale_v: Tensor, heads: int, head_dim: int = 64) -> Tuple[Tensor, Tensor]:
+    """Train-mode attention: returns (mp_silu(a * scale_v), a) with a = softmax(qk^T/8) v."""
+    B, H, W, Cc = v.shape
+    out = torch.empty_like(v)
+    raw = torch.empty_like(v)
+    L.check(L.load().dd_attention_train(L.ptr(qk), L.ptr(v), L.ptr(scale_v), L.ptr(out), L.ptr(raw), B, H * W, heads,
+                                        head_dim, L.stream_ptr()))
+    _count()
+    return out, raw
+
+
+def mpconv_wgrad(x: Tensor, dy: Tensor, ksize: int, groups: int = 1, scale: float = 1.0,
+                 out: Optional[Tensor] = None, accumulate: bool = False) -> Tensor:
+    """dW_eff [Cout, taps, Cin/groups] fp32 of an MPConv (tcgen05, MN-major operands)."""
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    if out is None:
+        out = torch.empty((Cout, ksize * ksize, Cin // groups), device=x.device, dtype=torch.float32)
+    if timing is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    L.check(L.load().dd_mpconv_wgrad(L.ptr(x), L.ptr(dy), L.ptr(out), B, H, W, Cin, Cout, ksize, groups, scale,
+                                     int(accumulate), L.stream_ptr()))
+    if timing is not None:
+        ev1.record()
+        timing.append((2.0 * B * H * W * Cout * (Cin // groups) * ksize * ksize, ev0, ev1,
+                       ("wgrad", B, H, W, Cin, Cout, ksize, groups)))
+    _count(1, "mpconv_wgrad", (B, H, W, Cin, Cout, ksize, groups))
+    return out
+
+
+def weight_transpose(w_prepped: Tensor, cout: int, cin_g: int, taps: int, groups: int,
+                     out: Optional[Tensor] = None) -> Tensor:
+    """bf16 [Cout, taps*cin_g] -> [Cin, taps*cout_g] with reversed taps (dgrad operand of dd_mpconv_forward)."""
+    if out is None:
+        out = torch.empty((groups * cin_g, taps, cout // groups), device=w_prepped.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_weight_transpose(L.ptr(w_prepped), L.ptr(out), cout, cin_g, taps, groups, L.stream_ptr()))
+    _count()
+    return out
+
+
+def make_wbwd_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int]:
+    """Pack dd_wbwd_desc records (dicts with w, dweff, dw, gain, dgain, gain_host, O, I_g, taps, normalize, perm,
+    head_dim, row_stride, accumulate) into a device buffer; returns (buffer, total_rows)."""
+    arr = (L.WbwdDesc * len(entries))()
+    rows = 0
+    for i, e in enumerate(entries):
+        arr[i] = L.WbwdDesc(L.ptr(e["w"]), L.ptr(e["dweff"]), L.ptr(e["dw"]), L.ptr(e.get("gain")), L.ptr(e.get("dgain")),
+                            e.get("gain_host", 1.0), e["O"], e["I_g"], e["taps"], int(e.get("normalize", False)),
+                            e.get("perm", 0), e.get("head_dim", 0), e.get("row_stride", 0) or e["I_g"] * e["taps"],
+                            int(e.get("accumulate", False)), rows)
+        rows += e["O"]
+    buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    return buf, rows
+
+
+def weight_prep_bwd(descs: Tensor, n: int, total_rows: int) -> None:
+    L.check(L.load().dd_weight_prep_bwd(L.ptr(descs), n, total_rows, L.stream_ptr()))
+    _count()
+
+
+def silu_scale_bwd(dy: Tensor, coef: float, pre: Tensor, scale: Tensor, dscale: Tensor,
+                   out: Optional[Tensor] = None) -> Tensor:
+    B = dy.shape[0]
+    Cc = dy.shape[-1]
+    npix = dy.numel() // (B * Cc)
+    if out is None:
+        out = torch.empty_like(dy)
+    L.check(L.load().dd_silu_scale_bwd(L.ptr(dy), coef, L.ptr(pre), L.ptr(scale), L.ptr(out), L.ptr(dscale), B, npix, Cc,
+                                       L.stream_ptr()))
+    _count()
+    return out
+
+
+def pixnorm_silu_bwd(g: Tensor, ca: float, ds: Tensor, t0: Tensor) -> Tensor:
+    Cc = t0.shape[-1]
+    out = torch.empty_like(t0)
+    L.check(L.load().dd_pixnorm_silu_bwd(L.ptr(g), ca, L.ptr(ds), L.ptr(t0), L.ptr(out), t0.numel() // Cc, Cc,
+                                         L.stream_ptr()))
+    _count()
+    return out
+
+
+def cat_silu_bwd(d_xc: Tensor, c1: float, d_s: Tensor, xc: Tensor, a_prev: Optional[Tensor], clip: float, wa: float,
+                 wb: float, upsample: bool, Ca: int, Cb: int) -> Tuple[Tensor, Optional[Tensor]]:
+    B, H, W, _ = xc.shape
+    Ha, Wa = (H // 2, W // 2) if upsample else (H, W)
+    da = torch.empty((B, Ha, Wa, Ca), device=xc.device, dtype=torch.bfloat16)
+    db = torch.empty((B, H, W, Cb), device=xc.device, dtype=torch.bfloat16) if Cb else None
+    L.check(L.load().dd_cat_silu_bwd(L.ptr(d_xc), c1, L.ptr(d_s), L.ptr(xc), L.ptr(a_prev), clip, wa, wb, int(upsample),
+                                     L.ptr(da), L.ptr(db), B, H, W, Ca, Cb, L.stream_ptr()))
+    _count()
+    return da, db
+
+
+def enc_grad_combine(dx0: Tensor, down: bool, dskip: Optional[Tensor], x_prev: Optional[Tensor], clip: float,
+                     shape: Tuple[int, int, int, int]) -> Tensor:
+    B, H, W, Cc = shape
+    out = torch.empty(shape, device=dx0.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_enc_grad_combine(L.ptr(dx0), int(down), L.ptr(dskip), L.ptr(x_prev), clip, L.ptr(out), B, H, W, Cc,
+                                         L.stream_ptr()))
+    _count()
+    return out
+
+
+def attn_in_bwd(g3: Tensor, ca: float, dxv: Tensor, dxs: Tensor, x2: Tensor, c_qk: Tensor, dc_qk: Tensor) -> Tensor:
+    B = x2.shape[0]
+    Cc = x2.shape[-1]
+    out = torch.empty_like(x2)
+    L.check(L.load().dd_attn_in_bwd(L.ptr(g3), ca, L.ptr(dxv), L.ptr(dxs), L.ptr(x2), L.ptr(c_qk), L.ptr(out), L.ptr(dc_qk),
+                                    B, x2.numel() // (B * Cc), Cc, L.stream_ptr()))
+    _count()
+    return out
+
+
+def attention_bwd(qk: Tensor, v: Tensor, a_raw: Tensor, d_a: Tensor, heads: int, head_dim: int = 64):
+    B, H, W, Cc = v.shape
+    N = H * W
+    dqk = torch.empty_like(qk)
+    dv = torch.empty_like(v)
+    stats = torch.empty((B, heads, N, 2), device=v.device, dtype=torch.float32)
+    L.check(L.load().dd_attention_bwd(L.ptr(qk), L.ptr(v), L.ptr(a_raw), L.ptr(d_a), L.ptr(dqk), L.ptr(dv), L.ptr(stats), B,
+                                      N, heads, head_dim, L.stream_ptr()))
+    _count(2)
+    return dqk, dv
+
+
+def make_affine_bwd_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int, int]:
+    arr = (L.AffineBwdDesc * len(entries))()
+    max_o = max_cols = 0
+    for i, e in enumerate(entries):
+        w = e["w"]
+        O, I = w.shape[0], w.shape[1]
+        arr[i] = L.AffineBwdDesc(L.ptr(w), L.ptr(e.get("gain")), L.ptr(e["dout"]), L.ptr(e["dweff"]), L.ptr(e["rowscale"]),
+                                 O, I, e.get("groups", 1), int(e.get("normalize", False)))
+        max_o = max(max_o, O)
+        max_cols = max(max_cols, I * e.get("groups", 1))
+    buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    return buf, max_o, max_cols
+
+
+def emb_affine_bwd(descs: Tensor, n: int, max_o: int, max_cols: int, emb: Tensor, demb: Tensor) -> None:
+    B, cemb = emb.shape
+    L.check(L.load().dd_emb_affine_bwd(L.ptr(descs), n, max_o, max_cols, L.ptr(emb), L.ptr(demb), B, cemb, L.stream_ptr()))
+    _count(2)
+
+
+def noise_embedding_bwd(sigma: Tensor, freqs: Tensor, phases: Tensor, w_noise: Tensor, label_emb: Tensor,
+                        label_balance: float, demb: Tensor, normalize: bool) -> Tuple[Tensor, Tensor]:
+    B = sigma.numel()
+    cemb, cnoise = w_noise.shape
+    dweff = torch.empty((cemb, cnoise), device=sigma.device, dtype=torch.float32)
+    dlabel = torch.empty((B, cemb), device=sigma.device, dtype=torch.float32)
+    L.check(L.load().dd_noise_embedding_bwd(L.ptr(sigma), L.ptr(freqs), L.ptr(phases), cnoise, L.ptr(w_noise),
+                                            int(normalize), L.ptr(label_emb), label_balance, L.ptr(demb), L.ptr(dweff),
+                                            L.ptr(dlabel), B, cemb, L.stream_ptr()))
+    _count()
+    return dweff, dlabel
+
+
+def label_embedding_bwd(emb_in: Tensor, mask: Tensor, dout: Tensor) -> Tuple[Tensor, Tensor]:
+    Bc, I = emb_in.shape
+    Bm, cemb = dout.shape
+    dwl = torch.empty((cemb, I), device=dout.device, dtype=torch.float32)
+    dwu = torch.empty((cemb, 1), device=dout.device, dtype=torch.float32)
+    L.check(L.load().dd_label_embedding_bwd(L.ptr(emb_in), Bc, I, L.ptr(mask), Bm, L.ptr(dout), L.ptr(dwl), L.ptr(dwu),
+                                            cemb, L.stream_ptr()))
+    _count()
+    return dwl, dwu
+
+
+def sigma_logvar_bwd(sigma: Tensor, freqs: Tensor, phases: Tensor, dout: Tensor) -> Tensor:
+    n = freqs.numel()
+    dw = torch.empty((1, n), device=sigma.device, dtype=torch.float32)
+    L.check(L.load().dd_sigma_logvar_bwd(L.ptr(sigma), sigma.numel(), L.ptr(freqs), L.ptr(phases), n, L.ptr(dout),
+                                         L.ptr(dw), 0, L.stream_ptr()))
+    _count()
+    return dw
+
+
+def head_grad(dD: Tensor, sigma: Tensor, sigma_data: float, x_ref: Optional[Tensor], cpad: int = 32) -> Tensor:
+    B, Cout, H, W = dD.shape
+    out = torch.empty((B, H, W, cpad), device=dD.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_head_grad(L.ptr(dD), L.ptr(sigma), sigma_data, L.ptr(x_ref), L.ptr(out), B, Cout, H, W, cpad,
+                                  L.stream_ptr()))
+    _count()
+    return out

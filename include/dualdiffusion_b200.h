@@ -68,13 +68,15 @@ DD_API int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_forma
  *   DD_EPI_RESIDUAL   : out = clip(alpha*acc + beta*residual[b][h][w][c]) (mp_sum :131,:154; clip :157)
  * optional second output from the same (pre-rounding) value:
  *   DD_EPI2_SILU      : out2 = mp_silu(out)                               (next conv_res0 input, :119)
- *   DD_EPI2_SCALE     : out2 = out * scale2[b][c]                         (attn_qk input, :135-136)   */
+ *   DD_EPI2_SCALE     : out2 = out * scale2[b][c]                         (attn_qk input, :135-136)
+ *   DD_EPI2_RAW       : out2 = acc                                        (train mode: saved for backward) */
 #define DD_EPI_NONE 0
 #define DD_EPI_SCALE_SILU 1
 #define DD_EPI_RESIDUAL 2
 #define DD_EPI2_NONE 0
 #define DD_EPI2_SILU 1
 #define DD_EPI2_SCALE 2
+#define DD_EPI2_RAW 3    /* out2 = acc (pre-activation, saved for the backward pass of DD_EPI_SCALE_SILU) */
 typedef struct dd_conv_epilogue {
     int mode;              /* DD_EPI_*  */
     int mode2;             /* DD_EPI2_* */
@@ -156,6 +158,11 @@ DD_API int dd_axpby(const void* a, const void* b, float alpha, float beta, float
 DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, void* out, int B, int N, int heads,
                  int head_dim, void* stream);
 
+/* Train-mode variant: additionally writes the pre-activation attention output a = softmax(qk^T/8) v
+ * (bf16 [B][N][C]) that dd_attention_bwd and dd_silu_scale_bwd need.                                     */
+DD_API int dd_attention_train(const void* qk, const void* v, const float* scale_v, void* out, void* raw_out, int B, int N,
+                              int heads, int head_dim, void* stream);
+
 /* Axis ("separable") attention of the legacy ddec UNets, modules/unets/old/unet_edm2_ddec_mdct_b3.py:144-163:
  * qkv [B][Z][H][W][3C] (channels_last_3d, q|k|v thirds after DD_WPERM_QKV), attention over H (axis 0, sequences
  * (b,z,w)) or W (axis 1, sequences (b,z,h)); out [B][Z][H][W][C] = mp_silu(attention).  The reference's
@@ -211,6 +218,85 @@ DD_API int dd_sampler_cfg_lerp(const float* d_2b, const float* sample, float cfg
  * dup != 0: sample_inout is a 2n buffer, read from its first half and written to both halves (:661).   */
 DD_API int dd_sampler_update(const float* cfg1, const float* d2_2b, float cfg_scale, int use_heun, float t, float p,
                              const float* noise, float* sample_inout, float* cfg_out, int dup, long n, void* stream);
+
+/* ==== backward pass of the UNet train step ======================================================
+ * Reference: loss.backward() (training/trainer.py:1022-1044) through UNet.forward
+ * (modules/unets/unet_edm2_b4.py:250-296), Block.forward (:110-158) and MPConv.forward
+ * (modules/mp_tools.py:357-373).  The reference relies on PyTorch autograd (cuDNN dgrad/wgrad, SDPA backward,
+ * eager elementwise backward kernels); each entry point below replaces one of those autograd nodes.
+ * dgrad of an MPConv is dd_mpconv_forward itself on weights re-laid-out by dd_weight_transpose.            */
+
+/* conv2d weight gradient (autograd of F.conv2d, mp_tools.py:369) on the tensor cores:
+ *   dw[co][tap][ci] (fp32, the layout of dd_weight_prep's DD_WFMT_BF16_OTI output) = scale * sum_pix dy[pix][co] * x[pix+tap][ci]
+ * x bf16 [B][H][W][Cin], dy bf16 [B][H][W][Cout]; accumulate != 0 adds into dw.                             */
+DD_API int dd_mpconv_wgrad(const void* x, const void* dy, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
+                           int groups, float scale, int accumulate, void* stream);
+/* bf16 [Cout][taps][cin_g] (dd_weight_prep output) -> bf16 [Cin][taps][cout_g] with the taps reversed: the operand
+ * that turns dd_mpconv_forward(dy, ., Cin<->Cout swapped) into the data gradient of the convolution.      */
+DD_API int dd_weight_transpose(const void* w_prepped, void* out, int Cout, int cin_g, int taps, int groups, void* stream);
+
+/* Backward of dd_weight_prep (mp_tools.py:359-364), batched over parameters: one CTA per weight row.
+ *   dw[o][i][tap] (=|+=) d(w_eff)/d(w) applied to dweff;  *dgain += <dweff, w_hat>/sqrt(fan_in) * gain_host       */
+typedef struct dd_wbwd_desc {
+    const float* w;      /* parameter, fp32 [O][I_g][taps] */
+    const float* dweff;  /* fp32 gradient of the effective weight, element (row, tap*I_g + i), rows permuted like dd_weight_prep */
+    float* dw;           /* fp32 [O][I_g][taps] */
+    const float* gain;   /* device scalar or NULL */
+    float* dgain;        /* device scalar accumulator or NULL */
+    float gain_host;
+    int O, I_g, taps, normalize, perm, head_dim, row_stride, accumulate;
+    int row_begin;       /* exclusive prefix sum of O over the descriptor array */
+} dd_wbwd_desc;
+DD_API int dd_weight_prep_bwd(const dd_wbwd_desc* descs_dev, int n_descs, int total_rows, void* stream);
+
+/* y = mp_silu(pre*scale[b][c]) (conv_res0 epilogue :121-122, attention tail :150-151):
+ *   dpre = coef*dy*silu'(pre*scale)*scale;  dscale[b][c] += sum_pix coef*dy*silu'(pre*scale)*pre.  bf16 [B][npix][C]. */
+DD_API int dd_silu_scale_bwd(const void* dy, float coef, const void* pre, const float* scale, void* dpre, float* dscale,
+                             int B, long npix, int C, void* stream);
+/* encoder pixel-norm + mp_silu (:114-119): dt0 from g (block-output gradient, enters as ca*g through mp_sum) and ds. */
+DD_API int dd_pixnorm_silu_bwd(const void* g, float ca, const void* ds, const void* t0, void* dt0, long npix, int C,
+                               void* stream);
+/* backward of dd_cat_silu: dxc = c1*d_xc + d_s*silu'(xc); da = mask(|a_prev|<clip)*wa*sum_2x2(dxc[:Ca]); db = wb*dxc[Ca:].
+ * H,W are the sizes of xc; a_prev (the tensor that was passed as `a`) may be NULL (no clip mask).              */
+DD_API int dd_cat_silu_bwd(const void* d_xc, float c1, const void* d_s, const void* xc, const void* a_prev, float clip,
+                           float wa, float wb, int upsample, void* da, void* db, int B, int H, int W, int Ca, int Cb,
+                           void* stream);
+/* encoder chain: out = mask(|x_prev|<clip) * ((down ? avg_pool2d backward of dx0 : dx0) + dskip); H,W,C of x_prev.      */
+DD_API int dd_enc_grad_combine(const void* dx0, int down, const void* dskip, const void* x_prev, float clip, void* out,
+                               int B, int H, int W, int C, void* stream);
+/* attention input (:133-136): dx2 = ca*g3 + dxv + dxs*c_qk[b][c]; dc_qk[b][c] += sum_pix dxs*x2.               */
+DD_API int dd_attn_in_bwd(const void* g3, float ca, const void* dxv, const void* dxs, const void* x2, const float* c_qk,
+                          void* dx2, float* dc_qk, int B, long npix, int C, void* stream);
+/* SDPA + cosine-norm backward (:137-148): inputs as dd_attention_train, d_a = gradient of raw_out;
+ * dqk [B][N][2C], dv [B][N][C] bf16; stats_ws fp32 [B][heads][N][2] scratch.                                */
+DD_API int dd_attention_bwd(const void* qk, const void* v, const void* a_raw, const void* d_a, void* dqk, void* dv,
+                            float* stats_ws, int B, int N, int heads, int head_dim, void* stream);
+
+/* emb_linear* backward (batched like dd_emb_affine): dweff_j[o][i] = sum_b dout_j[b][o]*emb[b][g*I+i];
+ * demb[b][g*I+i] += sum_o dout_j[b][o]*w_eff_j[o][i].  rowscale: fp32 [O] scratch.                           */
+typedef struct dd_affine_bwd_desc {
+    const float* w;      /* [O][I] fp32 */
+    const float* gain;   /* device scalar or NULL */
+    const float* dout;   /* [B][O] fp32 */
+    float* dweff;        /* [O][I] fp32 out */
+    float* rowscale;     /* [O] fp32 scratch */
+    int O, I, groups, normalize;
+} dd_affine_bwd_desc;
+DD_API int dd_emb_affine_bwd(const dd_affine_bwd_desc* descs_dev, int n_descs, int max_O, int max_cols, const float* emb,
+                             float* demb, int B, int cemb, void* stream);
+/* backward of dd_noise_embedding: dweff [cemb][cnoise] (emb_noise), dlabel [B][cemb] (gradient of `embeddings`).  */
+DD_API int dd_noise_embedding_bwd(const float* sigma, const float* freqs, const float* phases, int cnoise,
+                                  const float* w_noise, int normalize, const float* label_emb, float label_balance,
+                                  const float* demb, float* dweff, float* dlabel, int B, int cemb, void* stream);
+/* backward of dd_label_embedding: dweff_label [cemb][I], dweff_uncond [cemb].                                  */
+DD_API int dd_label_embedding_bwd(const float* emb_in, int Bc, int I, const float* mask, int Bm, const float* dout,
+                                  float* dweff_label, float* dweff_uncond, int cemb, void* stream);
+/* backward of dd_sigma_logvar: dw[n] (=|+=) sum_i dout[i]*fourier(ln(sigma_i)/4)/sqrt(n).                       */
+DD_API int dd_sigma_logvar_bwd(const float* sigma, int count, const float* freqs, const float* phases, int n,
+                               const float* dout, float* dw, int accumulate, void* stream);
+/* UNet head (:290-294): dF = dD*c_out(sigma) (times the x_ref blend weight), NCHW fp32 -> NHWC bf16 padded to Cpad channels. */
+DD_API int dd_head_grad(const float* dD_nchw, const float* sigma, float sigma_data, const float* x_ref_nchw, void* dF_nhwc,
+                        int B, int Cout, int H, int W, int Cpad, void* stream);
 
 #ifdef __cplusplus
 }
