@@ -201,6 +201,72 @@ def bench_format(device) -> dict:
             "encode_plus_decode": {"value": B / (t_enc + t_dec), "unit": "stereo samples/s"}}
 
 
+def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> dict:
+    """BASELINE.json configs[3]: UNet train step forward + backward (bf16 tensor-core compute, fp32 master parameters and
+    gradients), device batch 4 of the 45 s latent per GPU, gradients all-reduced (mean) over NCCL overlapped with the
+    backward when world > 1.  Loss = unet_trainer.py:259-280.  The optimizer (torch AdamW in the reference) is not part
+    of the path."""
+    import torch.nn.functional as F
+    from oracle import unet_oracle as uo          # seeded synthetic weights only
+    from dualdiffusion_b200.ddp import GradAllReducer
+    from dualdiffusion_b200.modules.unets.unet_edm2_b4 import UNet, UNetConfig
+    from dualdiffusion_b200 import ops
+    spec = uo.default_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    cfg = UNetConfig(**{k: getattr(spec, k) for k in UNetConfig.__dataclass_fields__ if hasattr(spec, k)})
+    net = UNet(cfg)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(device).train()
+    net.grad_sync = GradAllReducer()
+    B = 4
+    g = torch.Generator(device=device).manual_seed(100 + (dist.get_rank() if dist is not None else 0))
+    samples = torch.randn(B, *LATENT[1:], device=device, generator=g)
+    noise = torch.randn(B, *LATENT[1:], device=device, generator=g)
+    sigma = torch.exp(torch.randn(B, device=device, generator=g) * 1.2 - 0.4)
+    clap = torch.randn(B, spec.in_channels_emb, device=device, generator=g)
+    mask = torch.ones(B, device=device, dtype=torch.bool)
+    sig = sigma.view(-1, 1, 1, 1)
+    w = (sig ** 2 + spec.sigma_data ** 2) / (sig * spec.sigma_data) ** 2
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        emb = net.get_embeddings(clap, mask)
+        denoised = net(samples + noise * sig, sigma, None, emb)
+        wl = (F.mse_loss(denoised, samples, reduction="none") * w).mean(dim=(1, 2, 3))
+        logvar = net.get_sigma_loss_logvar(sigma)
+        loss = (wl / logvar.exp() + logvar).mean()
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sps = world * B * steps / (ms * 1e-3)
+    pk = peaks()
+    flop = 3 * FLOP_PER_STEP / 4              # fwd + dgrad + wgrad of one sample-forward (0.489 TFLOP)
+    gn = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in net.parameters() if p.grad is not None)))
+    return {"metric": "UNet train step fwd+bwd samples/sec (device batch 4 x 4x32x688, bf16 compute, fp32 grads)",
+            "value": sps, "unit": "samples/s", "ms_per_step": ms / steps, "n_gpus": world, "global_batch": world * B,
+            "allreduce_bytes_per_step": net.grad_sync.bytes_reduced // max(1, steps + warmup),
+            "gpu_launches_per_step": (ops.launch_count - l0) // steps, "loss": float(loss), "grad_norm": gn,
+            "roofline": {"bound": "tensor", "achieved": flop * sps / world / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": flop * sps / world / 1e12 / pk["tflops"]}}
+
+
 def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -306,6 +372,12 @@ def run_ours(args) -> None:
                                    "share_of_unet_call": tt_all / (ms * 1e-3 / K / 2)},
                     "step": {"achieved": FLOP_PER_STEP * value / world / 1e12, "frac": FLOP_PER_STEP * value / world / 1e12 / pk["tflops"]}}
 
+    train = None
+    if not args.no_train:
+        del net, pipe, state
+        torch.cuda.empty_cache()
+        train = bench_train(device, dist, world)
+
     secondary = None
     if rank == 0 and world == 1 and not args.no_format:
         secondary = bench_format(device)
@@ -320,7 +392,7 @@ def run_ours(args) -> None:
                            "library": os.path.relpath(_lib.lib_path(), ROOT)},
                 "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
-                "secondary": secondary}
+                "train_step": train, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -334,6 +406,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-format", action="store_true", help="skip the mel-STFT/FGLA secondary measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the train-step (fwd+bwd+all-reduce) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

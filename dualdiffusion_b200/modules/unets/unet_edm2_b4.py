@@ -302,6 +302,9 @@ class UNet(DualDiffusionUNet):
             e = e.unsqueeze(0)
         mask = conditioning_mask.detach().to(device=dev, dtype=torch.float32).contiguous().flatten()
         L.require_cuda(self.emb_label.weight)
+        if self._wants_grad():
+            from .unet_train import LabelEmbeddingFunction
+            return LabelEmbeddingFunction.apply(e, mask, self.emb_label.weight, self.emb_label_unconditional.weight)
         out = ops.label_embedding(e, self.emb_label.weight.detach().contiguous(),
                                   self.emb_label_unconditional.weight.detach().contiguous(), mask,
                                   normalize=self.training)
@@ -313,9 +316,23 @@ class UNet(DualDiffusionUNet):
         aux = self._aux()
         s = sigma.detach().to(device=dev, dtype=torch.float32).contiguous().flatten()
         L.require_cuda(self.logvar_linear.weight)
+        if torch.is_grad_enabled() and self.logvar_linear.weight.requires_grad:
+            from .unet_train import SigmaLogvarFunction
+            return SigmaLogvarFunction.apply(s, aux["logvar_freqs"], aux["logvar_phases"],
+                                             self.logvar_linear.weight).view(-1, 1, 1, 1)
         out = ops.sigma_logvar(s, aux["logvar_freqs"], aux["logvar_phases"],
                                self.logvar_linear.weight.detach().contiguous())
         return out.view(-1, 1, 1, 1)
+
+    def _wants_grad(self) -> bool:
+        """True when this call must be differentiable: autograd is recording, the module is in train mode (the
+        reference's train step; weight-norm runs inside the forward) and some parameter requires grad."""
+        if not torch.is_grad_enabled() or not any(p.requires_grad for p in self.parameters()):
+            return False
+        if not self.training:
+            raise NotImplementedError("dualdiffusion_b200 UNet: gradients are only implemented for train() mode "
+                                      "(eval-mode calls belong under torch.no_grad(), as in the reference's validation)")
+        return True
 
     def _ln_freqs(self, plan: _Plan, format, H: int) -> Tensor:
         """Mel positional channel, one value per latent row (unet_edm2_b4.py:244-248).  The statistics are taken
@@ -448,8 +465,6 @@ class UNet(DualDiffusionUNet):
 
     def forward(self, x_in: Tensor, sigma: Tensor, format=None, embeddings: Optional[Tensor] = None,
                 x_ref: Optional[Tensor] = None, perturbed_input: Optional[Tensor] = None) -> Tensor:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("dualdiffusion_b200 UNet: backward is not implemented yet (inference only)")
         if self.training and self.config.dropout != 0:
             raise NotImplementedError("dualdiffusion_b200 UNet: dropout is not implemented")
         plan = self._get_plan()
@@ -465,6 +480,10 @@ class UNet(DualDiffusionUNet):
         em = embeddings.detach().to(device=dev, dtype=torch.float32).contiguous()
         xr = None if x_ref is None else x_ref.detach().to(device=dev, dtype=torch.float32).contiguous()
         lf = self._ln_freqs(plan, format, H)
+
+        if self._wants_grad():      # train step: one autograd node, hand-scheduled forward + backward
+            from .unet_train import UNetFunction, unet_params
+            return UNetFunction.apply(self, x32, net_in, sg, em, lf, xr, embeddings, *unet_params(self, plan))
 
         with torch.no_grad():
             plan.refresh_weights()

@@ -447,10 +447,12 @@ def emb_affine_bwd(descs: Tensor, n: int, max_o: int, max_cols: int, emb: Tensor
 
 
 def noise_embedding_bwd(sigma: Tensor, freqs: Tensor, phases: Tensor, w_noise: Tensor, label_emb: Tensor,
-                        label_balance: float, demb: Tensor, normalize: bool) -> Tuple[Tensor, Tensor]:
+                        label_balance: float, demb: Tensor, normalize: bool,
+                        dweff: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     B = sigma.numel()
     cemb, cnoise = w_noise.shape
-    dweff = torch.empty((cemb, cnoise), device=sigma.device, dtype=torch.float32)
+    if dweff is None:
+        dweff = torch.empty((cemb, cnoise), device=sigma.device, dtype=torch.float32)
     dlabel = torch.empty((B, cemb), device=sigma.device, dtype=torch.float32)
     L.check(L.load().dd_noise_embedding_bwd(L.ptr(sigma), L.ptr(freqs), L.ptr(phases), cnoise, L.ptr(w_noise),
                                             int(normalize), L.ptr(label_emb), label_balance, L.ptr(demb), L.ptr(dweff),

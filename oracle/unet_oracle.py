@@ -401,6 +401,34 @@ def small_spec() -> UNetSpec:
 
 
 # --------------------------------------------------------------------------------------
+# train step (training/module_trainers/unet_trainer.py:236-280): EDM loss with the learned
+# per-noise-level uncertainty, as a function of a reference-layout state_dict
+# --------------------------------------------------------------------------------------
+def train_loss(sd: Dict[str, Tensor], spec: UNetSpec, samples: Tensor, noise: Tensor, sigma: Tensor, clap: Tensor,
+               conditioning_mask: Tensor) -> Tensor:
+    """unet_trainer.py:239,259-280 (input_perturbation = 0, no ref_samples / loss_weight) followed by the
+    `.mean()` of trainer.py:1016.  `noise` is unit-variance; the trainer scales it by sigma (:252).  Weight
+    normalisation runs inside the forward (train mode, mp_tools.py:360-361).  Keeps the (B,1,1,B) broadcast of
+    `batch_weighted_loss / error_logvar.exp() + error_logvar`."""
+    u = mp_conv(torch.ones(1), sd["emb_label_unconditional.weight"], training=True)
+    c = mp_conv(normalize(clap.float()), sd["emb_label.weight"], training=True)
+    emb = mp_sum(u, c, conditioning_mask.unsqueeze(1).float())
+    sig = sigma.float().view(-1, 1, 1, 1)
+    denoised = unet_forward(sd, spec, samples + noise * sig, sigma, emb, training=True)
+    w = (sig ** 2 + spec.sigma_data ** 2) / (sig * spec.sigma_data) ** 2
+    wl = (F.mse_loss(denoised, samples, reduction="none") * w).mean(dim=(1, 2, 3))
+    logvar = sigma_loss_logvar(sd, sigma)
+    return (wl / logvar.exp() + logvar).mean()
+
+
+def grad_probe(name: str, shape) -> Tensor:
+    """Seeded random direction per parameter name: golden files store <grad, probe> and ||grad|| instead of
+    the full gradients (tests/golden/make_golden.py)."""
+    g = torch.Generator().manual_seed(sum(ord(ch) * (i + 1) for i, ch in enumerate(name)) % (2 ** 31))
+    return torch.randn(tuple(shape), generator=g)
+
+
+# --------------------------------------------------------------------------------------
 # axis ("separable") attention of the legacy ddec UNets
 # (modules/unets/old/unet_edm2_ddec_mdct_b3.py:144-163) -- the only row/col <-> batch reshape in the reference
 # --------------------------------------------------------------------------------------

@@ -59,6 +59,35 @@ def main():
                         d_train=d_train, weight_checksum=weight_checksum(sd)), os.path.join(OUT, tag + ".pt"))
         print(tag, "std", d.std().item())
 
+    # ---- train step: gradients of the reference's loss (unet_trainer.py:259-280) through the reference module ----
+    torch.set_grad_enabled(True)
+    spec = uo.small_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    net = build_reference_unet(spec, sd).train()
+    g = torch.Generator().manual_seed(5)
+    samples = torch.randn(2, 4, 32, 48, generator=g)
+    noise = torch.randn(2, 4, 32, 48, generator=g)
+    sigma = torch.tensor([1.5, 0.2])
+    clap = torch.randn(2, spec.in_channels_emb, generator=g)
+    mask = torch.tensor([True, False])
+    emb = net.get_embeddings(clap, mask)
+    sig = sigma.view(-1, 1, 1, 1)
+    denoised = net(samples + noise * sig, sigma, fmt, emb)
+    w = (sig ** 2 + spec.sigma_data ** 2) / (sig * spec.sigma_data) ** 2
+    wl = (torch.nn.functional.mse_loss(denoised, samples, reduction="none") * w).mean(dim=(1, 2, 3))
+    logvar = net.get_sigma_loss_logvar(sigma)
+    loss = (wl / logvar.exp() + logvar).mean()
+    loss.backward()
+    stats = {}
+    for name, p in net.named_parameters():
+        stats[name] = (float(p.grad.norm()), float((p.grad * uo.grad_probe(name, p.shape)).sum()))
+    small = {n: p.grad.clone() for n, p in net.named_parameters() if p.numel() <= 4096}
+    torch.save(dict(samples=samples, noise=noise, sigma=sigma, clap=clap, mask=mask, loss=loss.detach(),
+                    denoised=denoised.detach(), grad_stats=stats, small_grads=small,
+                    weight_checksum=weight_checksum(sd)), os.path.join(OUT, "unet_small_train.pt"))
+    print("train loss", float(loss), "params", len(stats))
+    torch.set_grad_enabled(False)
+
     # ---- sampler: reference diffusion_decode on CPU, reduced config, 3 Heun+CFG steps ----
     spec = uo.small_spec()
     sd = uo.synth_state_dict(spec, seed=0)

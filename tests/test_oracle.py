@@ -131,3 +131,24 @@ def test_ms_dual_oracle_and_host_logic_vs_golden():
     assert tuple(fmt.get_mel_spec_shape(3)) == tuple(g["mel_shape_default"])
     assert fmt.get_raw_crop_width() == g["crop_default"]
     assert torch.equal(fmt.ms_freq_scale.get_unscaled(34), g["unscaled_34"])
+
+
+def test_oracle_train_step_gradients_vs_golden_reference():
+    """Row A12: autograd through the oracle's train loss (unet_trainer.py:259-280 restated) reproduces the
+    reference module's loss and its parameter gradients (norm and seeded projection per tensor, plus every
+    small tensor in full)."""
+    g = load_golden("unet_small_train.pt")
+    spec = uo.small_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    sdg = {k: (v.clone().requires_grad_(True) if "fourier" not in k else v) for k, v in sd.items()}
+    loss = uo.train_loss(sdg, spec, g["samples"], g["noise"], g["sigma"], g["clap"], g["mask"])
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    loss.backward()
+    assert set(g["grad_stats"]) == {k for k in sdg if "fourier" not in k}
+    for name, (n_ref, dot_ref) in g["grad_stats"].items():
+        gr = sdg[name].grad
+        assert abs(float(gr.norm()) - n_ref) <= 1e-4 * n_ref + 1e-9, name
+        dot = float((gr * uo.grad_probe(name, gr.shape)).sum())
+        assert abs(dot - dot_ref) <= 1e-3 * n_ref * 3 + 1e-9, name
+    for name, gref in g["small_grads"].items():
+        assert rel_err(sdg[name].grad, gref) < 1e-4 or (sdg[name].grad - gref).abs().max() < 1e-8, name
