@@ -129,35 +129,68 @@ __global__ void weight_prep_bwd_kernel(const dd_wbwd_desc* __restrict__ descs, i
 // ------------------------------------------------------------------------------------------
 // y = mp_silu(pre * scale[b][c]) backward:  dpre = coef*dy*silu'(u)*scale,  dscale[b][c] += sum_pix coef*dy*silu'(u)*pre
 // ------------------------------------------------------------------------------------------
-constexpr int kStripPix = 64;
+// A block covers a strip of pixels x 32 channel-vectors (256 channels): threadIdx.x walks the channel vectors
+// (coalesced 512 B rows), threadIdx.y the pixels; every thread keeps kPixPerThread independent loads in flight and the
+// per-channel sums meet in shared memory before one atomicAdd per channel and block.
+constexpr int kRedRows = 8;
 
-__global__ void silu_scale_bwd_kernel(const uint4* __restrict__ dy, float coef, const uint4* __restrict__ pre,
-                                      const float* __restrict__ scale, uint4* __restrict__ dpre,
-                                      float* __restrict__ dscale, long npix, int nvec, long strips) {
-    const int b = blockIdx.y;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < strips * nvec; idx += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx % nvec);
-        const long strip = idx / nvec;
-        float sc[8], acc[8];
+__device__ __forceinline__ void strip_reduce_atomic(float (&acc)[8], float* __restrict__ dst, bool vok,
+                                                    float (*red)[32][8]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(scale + (size_t)b * nvec * 8 + v * 8 + j); acc[j] = 0.f; }
-        const long p0 = strip * kStripPix, p1 = min(npix, p0 + kStripPix);
-        for (long pix = p0; pix < p1; ++pix) {
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (threadIdx.y == 0 && vok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = 0.f;
+#pragma unroll
+            for (int r = 0; r < kRedRows; ++r) t += red[r][threadIdx.x][j];
+            atomicAdd(dst + j, t);
+        }
+    }
+}
+
+constexpr int kSsbPixPerThread = 8;
+
+__global__ void __launch_bounds__(256)
+silu_scale_bwd_kernel(const uint4* __restrict__ dy, float coef, const uint4* __restrict__ pre,
+                      const float* __restrict__ scale, uint4* __restrict__ dpre, float* __restrict__ dscale, long npix,
+                      int nvec) {
+    __shared__ float red[kRedRows][32][8];
+    const int b = blockIdx.z;
+    const int v = blockIdx.y * 32 + threadIdx.x;
+    const bool vok = v < nvec;
+    const long p0 = (long)blockIdx.x * (kRedRows * kSsbPixPerThread) + threadIdx.y;
+    float sc[8], acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = vok ? __ldg(scale + (size_t)b * nvec * 8 + v * 8 + j) : 0.f; acc[j] = 0.f; }
+    uint4 qg[kSsbPixPerThread], qx[kSsbPixPerThread];
+#pragma unroll
+    for (int i = 0; i < kSsbPixPerThread; ++i) {
+        const long pix = p0 + (long)i * kRedRows;
+        if (vok && pix < npix) {
             const size_t off = ((size_t)b * npix + pix) * nvec + v;
+            qg[i] = __ldg(dy + off);
+            qx[i] = __ldg(pre + off);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kSsbPixPerThread; ++i) {
+        const long pix = p0 + (long)i * kRedRows;
+        if (vok && pix < npix) {
             float g[8], x[8], o[8];
-            unpack8(__ldg(dy + off), g);
-            unpack8(__ldg(pre + off), x);
+            unpack8(qg[i], g);
+            unpack8(qx[i], x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float t = coef * g[j] * mp_silu_grad(x[j] * sc[j]);
                 o[j] = t * sc[j];
                 acc[j] += t * x[j];
             }
-            dpre[off] = pack8(o);
+            dpre[((size_t)b * npix + pix) * nvec + v] = pack8(o);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(dscale + (size_t)b * nvec * 8 + v * 8 + j, acc[j]);
     }
+    strip_reduce_atomic(acc, dscale + (size_t)b * nvec * 8 + v * 8, vok, red);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -315,35 +348,44 @@ __global__ void enc_grad_combine_kernel(const uint4* __restrict__ dx0, int down,
 
 // attention input: x2 feeds mp_sum (ca*g3), attn_v (dxv) and attn_qk through xs = x2*c_qk (dxs):
 //   dx2 = ca*g3 + dxv + dxs*c_qk[b][c];   dc_qk[b][c] += sum_pix dxs*x2
-__global__ void attn_in_bwd_kernel(const uint4* __restrict__ g3, float ca, const uint4* __restrict__ dxv,
-                                   const uint4* __restrict__ dxs, const uint4* __restrict__ x2,
-                                   const float* __restrict__ c_qk, uint4* __restrict__ dx2, float* __restrict__ dc_qk,
-                                   long npix, int nvec, long strips) {
-    const int b = blockIdx.y;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < strips * nvec; idx += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx % nvec);
-        const long strip = idx / nvec;
-        float sc[8], acc[8];
+constexpr int kAibPixPerThread = 4;
+
+__global__ void __launch_bounds__(256)
+attn_in_bwd_kernel(const uint4* __restrict__ g3, float ca, const uint4* __restrict__ dxv, const uint4* __restrict__ dxs,
+                   const uint4* __restrict__ x2, const float* __restrict__ c_qk, uint4* __restrict__ dx2,
+                   float* __restrict__ dc_qk, long npix, int nvec) {
+    __shared__ float red[kRedRows][32][8];
+    const int b = blockIdx.z;
+    const int v = blockIdx.y * 32 + threadIdx.x;
+    const bool vok = v < nvec;
+    const long p0 = (long)blockIdx.x * (kRedRows * kAibPixPerThread) + threadIdx.y;
+    float sc[8], acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[j] = __ldg(c_qk + (size_t)b * nvec * 8 + v * 8 + j); acc[j] = 0.f; }
-        const long p0 = strip * kStripPix, p1 = min(npix, p0 + kStripPix);
-        for (long pix = p0; pix < p1; ++pix) {
+    for (int j = 0; j < 8; ++j) { sc[j] = vok ? __ldg(c_qk + (size_t)b * nvec * 8 + v * 8 + j) : 0.f; acc[j] = 0.f; }
+    uint4 q0[kAibPixPerThread], q1[kAibPixPerThread], q2[kAibPixPerThread], q3[kAibPixPerThread];
+#pragma unroll
+    for (int i = 0; i < kAibPixPerThread; ++i) {
+        const long pix = p0 + (long)i * kRedRows;
+        if (vok && pix < npix) {
             const size_t off = ((size_t)b * npix + pix) * nvec + v;
+            q0[i] = __ldg(g3 + off); q1[i] = __ldg(dxv + off); q2[i] = __ldg(dxs + off); q3[i] = __ldg(x2 + off);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kAibPixPerThread; ++i) {
+        const long pix = p0 + (long)i * kRedRows;
+        if (vok && pix < npix) {
             float g[8], dv[8], dsx[8], x[8], o[8];
-            unpack8(__ldg(g3 + off), g);
-            unpack8(__ldg(dxv + off), dv);
-            unpack8(__ldg(dxs + off), dsx);
-            unpack8(__ldg(x2 + off), x);
+            unpack8(q0[i], g); unpack8(q1[i], dv); unpack8(q2[i], dsx); unpack8(q3[i], x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 o[j] = ca * g[j] + dv[j] + dsx[j] * sc[j];
                 acc[j] += dsx[j] * x[j];
             }
-            dx2[off] = pack8(o);
+            dx2[((size_t)b * npix + pix) * nvec + v] = pack8(o);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(dc_qk + (size_t)b * nvec * 8 + v * 8 + j, acc[j]);
     }
+    strip_reduce_atomic(acc, dc_qk + (size_t)b * nvec * 8 + v * 8, vok, red);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -781,10 +823,11 @@ extern "C" int dd_silu_scale_bwd(const void* dy, float coef, const void* pre, co
     DD_REQUIRE(dy && pre && scale && dpre && dscale, "dd_silu_scale_bwd: null pointer");
     DD_REQUIRE(C % 8 == 0 && B > 0 && B <= 65535, "dd_silu_scale_bwd: bad shape");
     if (npix == 0) return 0;
-    const long strips = (npix + kStripPix - 1) / kStripPix;
-    const dim3 grid(grid_for_b(strips * (C / 8), 128), B);
-    silu_scale_bwd_kernel<<<grid, 128, 0, stream>>>(static_cast<const uint4*>(dy), coef, static_cast<const uint4*>(pre),
-                                                    scale, static_cast<uint4*>(dpre), dscale, npix, C / 8, strips);
+    const int strip = kRedRows * kSsbPixPerThread;
+    const dim3 grid((unsigned)((npix + strip - 1) / strip), ceil_div(C / 8, 32), B);
+    silu_scale_bwd_kernel<<<grid, dim3(32, kRedRows), 0, stream>>>(static_cast<const uint4*>(dy), coef,
+                                                                   static_cast<const uint4*>(pre), scale,
+                                                                   static_cast<uint4*>(dpre), dscale, npix, C / 8);
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -840,11 +883,13 @@ extern "C" int dd_attn_in_bwd(const void* g3, float ca, const void* dxv, const v
     DD_REQUIRE(g3 && dxv && dxs && x2 && c_qk && dx2 && dc_qk, "dd_attn_in_bwd: null pointer");
     DD_REQUIRE(C % 8 == 0 && B > 0 && B <= 65535, "dd_attn_in_bwd: bad shape");
     if (npix == 0) return 0;
-    const long strips = (npix + kStripPix - 1) / kStripPix;
-    const dim3 grid(grid_for_b(strips * (C / 8), 128), B);
-    attn_in_bwd_kernel<<<grid, 128, 0, stream>>>(static_cast<const uint4*>(g3), ca, static_cast<const uint4*>(dxv),
-                                                 static_cast<const uint4*>(dxs), static_cast<const uint4*>(x2), c_qk,
-                                                 static_cast<uint4*>(dx2), dc_qk, npix, C / 8, strips);
+    const int strip = kRedRows * kAibPixPerThread;
+    const dim3 grid((unsigned)((npix + strip - 1) / strip), ceil_div(C / 8, 32), B);
+    attn_in_bwd_kernel<<<grid, dim3(32, kRedRows), 0, stream>>>(static_cast<const uint4*>(g3), ca,
+                                                                static_cast<const uint4*>(dxv),
+                                                                static_cast<const uint4*>(dxs),
+                                                                static_cast<const uint4*>(x2), c_qk,
+                                                                static_cast<uint4*>(dx2), dc_qk, npix, C / 8);
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -38,26 +38,41 @@ class GradAllReducer:
     def world_size(self) -> int:
         return dist.get_world_size(self.pg) if dist.is_available() and dist.is_initialized() else 1
 
-    def run_backward(self, net, plan, ts, saved, dD) -> torch.Tensor:
-        from .modules.unets.unet_train import train_backward
+    def _all_reduce_mean(self, t: torch.Tensor) -> None:
+        if dist.get_backend(self.pg) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg)
+        else:                                   # gloo (CPU tests of the host logic) has no AVG
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+            t.mul_(1.0 / self.world_size())
+
+    def run_backward(self, net, plan, ts, saved, dD, backward_fn=None) -> torch.Tensor:
+        """Runs the backward schedule with bucket-wise gradient exchange.  `backward_fn` defaults to
+        unet_train.train_backward (tests substitute a host-only stand-in)."""
+        if backward_fn is None:
+            from .modules.unets.unet_train import train_backward as backward_fn
         params = [s for s in ts.slots.values()]
         installed = all(s.param.grad is not None and s.param.grad.data_ptr() == s.grad.data_ptr() for s in params)
-        main = torch.cuda.current_stream(plan.device)
-        if self.stream is None:
-            self.stream = torch.cuda.Stream(device=plan.device)
+        on_gpu = ts.grad_flat.is_cuda
         exchange = self.sync_now and self.world_size() > 1
+        if on_gpu:
+            main = torch.cuda.current_stream(ts.grad_flat.device)
+            if self.stream is None:
+                self.stream = torch.cuda.Stream(device=ts.grad_flat.device)
 
         def bucket_done(i: int) -> None:
             if not exchange:
                 return
             lo, hi = ts.bucket_ranges[i]
-            self.stream.wait_stream(main)
-            with torch.cuda.stream(self.stream):
-                dist.all_reduce(ts.grad_flat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg)
+            if on_gpu:
+                self.stream.wait_stream(main)
+                with torch.cuda.stream(self.stream):
+                    self._all_reduce_mean(ts.grad_flat[lo:hi])
+            else:
+                self._all_reduce_mean(ts.grad_flat[lo:hi])
             self.bytes_reduced += (hi - lo) * 4
 
-        dlabel = train_backward(net, plan, saved, dD, accumulate=installed, bucket_done=bucket_done)
-        if exchange:
+        dlabel = backward_fn(net, plan, saved, dD, accumulate=installed, bucket_done=bucket_done)
+        if exchange and on_gpu:
             main.wait_stream(self.stream)
         if not installed:
             for s in params:
