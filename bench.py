@@ -230,6 +230,10 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> di
 
     def step():
         net.zero_grad(set_to_none=True)
+        # an optimizer step changes every weight: the per-step weight preparation (weight-norm inside the forward,
+        # mp_tools.py:359-364) and the dgrad transposes are part of the train step
+        if net._plan is not None and getattr(net._plan, "train_state", None) is not None:
+            net._plan.train_state._prep_sig = None
         emb = net.get_embeddings(clap, mask)
         denoised = net(samples + noise * sig, sigma, None, emb)
         wl = (F.mse_loss(denoised, samples, reduction="none") * w).mean(dim=(1, 2, 3))

@@ -38,6 +38,19 @@ class WbwdDesc(C.Structure):
                 ("row_begin", c_int)]
 
 
+class WprepDesc(C.Structure):
+    """struct dd_wprep_desc"""
+    _fields_ = [("w", c_void_p), ("out", c_void_p), ("gain", c_void_p), ("gain_host", c_float), ("w_is_bf16", c_int),
+                ("O", c_int), ("I_g", c_int), ("taps", c_int), ("normalize", c_int), ("perm", c_int), ("head_dim", c_int),
+                ("row_stride", c_int), ("row_begin", c_int)]
+
+
+class WtransDesc(C.Structure):
+    """struct dd_wtrans_desc"""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("cout_g", c_int), ("cin_g", c_int), ("taps", c_int),
+                ("groups", c_int), ("tile_begin", c_int)]
+
+
 class AffineBwdDesc(C.Structure):
     """struct dd_affine_bwd_desc"""
     _fields_ = [("w", c_void_p), ("gain", c_void_p), ("dout", c_void_p), ("dweff", c_void_p), ("rowscale", c_void_p),
@@ -88,6 +101,8 @@ _SIGNATURES = {
                                 c_int, c_void_p]),
     "dd_weight_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_weight_prep_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "dd_weight_prep_batched": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "dd_weight_transpose_batched": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dd_silu_scale_bwd": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_long, c_int,
                                   c_void_p]),
     "dd_pixnorm_silu_bwd": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_long, c_int, c_void_p]),

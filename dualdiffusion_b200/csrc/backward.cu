@@ -68,6 +68,78 @@ __global__ void weight_transpose_kernel(const __nv_bfloat16* __restrict__ wp, __
     }
 }
 
+__global__ void weight_transpose_batched_kernel(const dd_wtrans_desc* __restrict__ descs, int n_descs) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    int lo = 0, hi = n_descs - 1;
+    const int t = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+    }
+    const dd_wtrans_desc d = descs[lo];
+    int r = t - d.tile_begin;
+    const int nx = (d.cin_g + 31) / 32, ny = (d.cout_g + 31) / 32;
+    const int bx = r % nx; r /= nx;
+    const int by = r % ny; r /= ny;
+    const int g = r / d.taps, tap = r - g * d.taps;
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(d.src);
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d.dst);
+    const int ci0 = bx * 32, co0 = by * 32;
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int co = co0 + rr, ci = ci0 + threadIdx.x;
+        if (co < d.cout_g && ci < d.cin_g)
+            tile[rr][threadIdx.x] = wp[((size_t)(g * d.cout_g + co) * d.taps + tap) * d.cin_g + ci];
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += blockDim.y) {
+        const int ci = ci0 + rr, co = co0 + threadIdx.x;
+        if (co < d.cout_g && ci < d.cin_g)
+            wd[((size_t)(g * d.cin_g + ci) * d.taps + (d.taps - 1 - tap)) * d.cout_g + co] = tile[threadIdx.x][rr];
+    }
+}
+
+// dd_weight_prep for every parameter of a model in one launch (same arithmetic as weight_prep_kernel, elementwise.cu)
+__global__ void weight_prep_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs) {
+    __shared__ float red[32];
+    int lo = 0, hi = n_descs - 1;
+    const int row = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].row_begin <= row) lo = mid; else hi = mid - 1;
+    }
+    const dd_wprep_desc d = descs[lo];
+    const int o = row - d.row_begin;
+    if (o >= d.O) return;
+    const int fan_in = d.I_g * d.taps;
+    const size_t base = (size_t)o * fan_in;
+    const float* wf = static_cast<const float*>(d.w);
+    const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(d.w);
+    float scale = d.gain_host * (d.gain ? *d.gain : 1.f) * rsqrtf((float)fan_in);
+    if (d.normalize) {
+        float ss = 0.f;
+        for (int i = threadIdx.x; i < fan_in; i += blockDim.x) {
+            const float v = d.w_is_bf16 ? __bfloat162float(wb[base + i]) : wf[base + i];
+            ss += v * v;
+        }
+        ss = block_sum_b(ss, red);
+        scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)fan_in));
+    }
+    int o_dst = o;
+    if (d.perm == DD_WPERM_QK) {
+        const int head = o / (2 * d.head_dim), rem = o % (2 * d.head_dim);
+        o_dst = (rem & 1) * (d.O / 2) + head * d.head_dim + (rem >> 1);
+    } else if (d.perm == DD_WPERM_QKV) {
+        const int head = o / (3 * d.head_dim), rem = o % (3 * d.head_dim);
+        o_dst = (rem % 3) * (d.O / 3) + head * d.head_dim + rem / 3;
+    }
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(d.out) + (size_t)o_dst * d.row_stride;
+    for (int j = threadIdx.x; j < fan_in; j += blockDim.x) {          // j = tap * I_g + i  (coalesced writes)
+        const int tap = j / d.I_g, i = j - tap * d.I_g;
+        const size_t src = base + (size_t)i * d.taps + tap;
+        dst[j] = __float2bfloat16_rn((d.w_is_bf16 ? __bfloat162float(wb[src]) : wf[src]) * scale);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // weight-prep backward (batched over parameters): dL/dW_eff -> dL/dW (+ dL/dgain)
 //   forward (mp_tools.py:359-364): w_hat = w / (eps + ||w|| / sqrt(f))  [training], w_eff = w_hat * gain / sqrt(f)
@@ -805,6 +877,22 @@ extern "C" int dd_weight_transpose(const void* w_prepped, void* out, int Cout, i
     const dim3 grid(ceil_div(cin_g, 32), ceil_div(cout_g, 32), groups * taps);
     weight_transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(w_prepped),
                                                              static_cast<__nv_bfloat16*>(out), cout_g, cin_g, taps);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_weight_prep_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_prep_batched: bad arguments");
+    weight_prep_batched_kernel<<<total_rows, 128, 0, stream>>>(descs_dev, n_descs);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_weight_transpose_batched(const dd_wtrans_desc* descs_dev, int n_descs, int total_tiles, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && n_descs > 0 && total_tiles > 0, "dd_weight_transpose_batched: bad arguments");
+    weight_transpose_batched_kernel<<<total_tiles, dim3(32, 8), 0, stream>>>(descs_dev, n_descs);
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -65,8 +65,10 @@ class TrainState:
                 raise RuntimeError(f"dualdiffusion_b200 UNet training needs fp32 master parameters ({n} is {p.dtype}); "
                                    "the reference trains fp32 parameters under bf16 autocast (trainer.py:114)")
         self.wt: Dict[str, Tensor] = {}          # dgrad operands
-        self.wt_versions: Dict[str, int] = {}
         self.conv_out_w32: Optional[Tensor] = None
+        self._prep_descs = self._trans_descs = self._prep_entries = None
+        self._prep_sig = None
+        self.step_graphs: Dict[tuple, _StepGraphs] = {}
 
         # ---- gradient buckets in backward-completion order ----
         buckets: List[List[_ParamSlot]] = []
@@ -159,26 +161,51 @@ class TrainState:
         # ---- embedding projections backward (batched over blocks) ----
         self.affine_bwd: Dict[int, dict] = {}
 
-    # dgrad operands follow the prepared weights (refresh when those were rewritten)
-    def refresh_transposed(self) -> None:
+    def refresh(self) -> None:
+        """Train-mode weight preparation (mp_tools.py:359-364: normalise, scale by gain/sqrt(fan_in), cast) for every
+        MPConv of the network plus the transposed dgrad operands: two batched launches, re-run whenever a parameter
+        version changed (i.e. after every optimizer step)."""
         from .unet_edm2_b4 import _ver
         plan = self.plan
-        for key, w, gain, qk_dim, pad_rows, row_stride in plan._weights():
-            if key == "enc.conv_in":
-                continue                              # no gradient flows to the network input
-            ver = plan.versions[key]
-            if self.wt_versions.get(key) == ver and key in self.wt:
-                continue
-            O, I_g = w.shape[0], w.shape[1]
-            taps = w.shape[2] * w.shape[3]
-            groups = getattr(w, "conv_groups", 1)
-            if key == "conv_out":
-                self.conv_out_w32 = ops.weight_prep(w.detach(), gain=plan.gain_ptr(gain), normalize=True,
-                                                    pad_rows=_CONV_OUT_PAD, out=self.conv_out_w32)
-                self.wt[key] = ops.weight_transpose(self.conv_out_w32, _CONV_OUT_PAD, I_g, taps, 1, out=self.wt.get(key))
-            else:
-                self.wt[key] = ops.weight_transpose(plan.prepped[key], O, I_g, taps, groups, out=self.wt.get(key))
-            self.wt_versions[key] = ver
+        plan.refresh_gains()
+        items = plan._weights()
+        sig = (sum(_ver(w) for _, w, *_ in items), plan.gain_version)
+        if self._prep_descs is None:
+            dev = plan.device
+            prep, trans = [], []
+            for key, w, gain, qk_dim, pad_rows, row_stride in items:
+                O, I_g = w.shape[0], w.shape[1]
+                taps = w.shape[2] * w.shape[3]
+                groups = getattr(w, "conv_groups", 1)
+                if key == "conv_out":
+                    self.conv_out_w32 = torch.zeros((_CONV_OUT_PAD, taps * I_g), device=dev, dtype=torch.bfloat16)
+                    out = self.conv_out_w32
+                else:
+                    out = plan.prepped.get(key)
+                    if out is None:
+                        out = (torch.zeros((max(O, pad_rows), row_stride or taps * I_g), device=dev, dtype=torch.bfloat16)
+                               if (pad_rows or row_stride) else torch.empty((O, taps, I_g), device=dev, dtype=torch.bfloat16))
+                        plan.prepped[key] = out
+                prep.append(dict(w=w.detach(), out=out, gain=None if gain is None else plan.gain_ptr(gain), O=O, I_g=I_g,
+                                 taps=taps, normalize=True, perm=L.WPERM_QK if qk_dim else L.WPERM_NONE, head_dim=qk_dim,
+                                 row_stride=row_stride))
+                if key == "enc.conv_in":
+                    continue                          # no gradient flows to the network input
+                rows = _CONV_OUT_PAD if key == "conv_out" else O
+                self.wt[key] = torch.empty((groups * I_g, taps, rows // groups), device=dev, dtype=torch.bfloat16)
+                trans.append(dict(src=out, dst=self.wt[key], cout_g=rows // groups, cin_g=I_g, taps=taps, groups=groups))
+            self._prep_entries = (prep, trans)        # keeps every tensor the descriptors point at alive
+            self._prep_descs = ops.make_wprep_descs(prep, dev) + (len(prep),)
+            self._trans_descs = ops.make_wtrans_descs(trans, dev) + (len(trans),)
+        if sig == self._prep_sig and plan.training is True:
+            return
+        buf, rows, n = self._prep_descs
+        ops.weight_prep_batched(buf, n, rows)
+        buf, tiles, n = self._trans_descs
+        ops.weight_transpose_batched(buf, n, tiles)
+        self._prep_sig = sig
+        plan.training = True                          # eval-mode refresh_weights() re-prepares (un-normalised) on mode flip
+        plan.versions.clear()
 
     def affine_bwd_for(self, B: int, st_fwd: dict) -> dict:
         st = self.affine_bwd.get(B)
@@ -299,7 +326,7 @@ def train_forward(net, plan, x_in: Tensor, net_in: Tensor, sigma: Tensor, embedd
 
     saved["x_last"] = x
     saved["n_skips"] = len(net.enc)
-    d = ops.conv_out(x, W["conv_out"], x_in, sigma, cfg.sigma_data, x_ref)
+    d = ops.conv_out(x, get_train_state(net, plan).conv_out_w32, x_in, sigma, cfg.sigma_data, x_ref)
     return d, saved
 
 
@@ -439,6 +466,38 @@ def train_backward(net, plan, saved: dict, dD: Tensor, accumulate: bool = False,
 # ---------------------------------------------------------------------------------------------------------
 # autograd nodes (the boundary: torch sees three opaque differentiable functions)
 # ---------------------------------------------------------------------------------------------------------
+class _StepGraphs:
+    """CUDA graphs of one train-step shape: the forward schedule, and the backward schedule cut into one graph per
+    gradient bucket so the NCCL all-reduce of a finished bucket can be enqueued between two replays.  All graphs of a
+    step share one memory pool and are replayed in capture order (forward, then the backward segments)."""
+
+    def __init__(self) -> None:
+        self.calls = 0                  # the first call of a shape runs eagerly (lazy descriptor tables, allocator)
+        self.pool = None
+        self.static: Optional[dict] = None
+        self.fwd = None
+        self.d: Optional[Tensor] = None
+        self.saved: Optional[dict] = None
+        self.dD: Optional[Tensor] = None
+        self.bwd: Dict[bool, tuple] = {}     # accumulate -> ([(graph, bucket index or None)], dlabel, launches)
+        self.fwd_launches = 0
+        self.busy = False               # a forward whose backward has not run yet owns the saved activations
+
+
+def _capture(fn, pool, device):
+    """Capture fn() into a new graph on a side stream; returns (graph, fn's result)."""
+    g = torch.cuda.CUDAGraph()
+    cur = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        g.capture_begin(pool=pool)
+        out = fn()
+        g.capture_end()
+    cur.wait_stream(side)
+    return g, out
+
+
 class UNetFunction(torch.autograd.Function):
     """D = UNet(x_in, sigma, embeddings[, x_ref, perturbed_input]); differentiable in `embeddings` and the
     parameters.  Parameter order: TrainState.slots order, then the scalar gains (plan.gain_params)."""
@@ -446,27 +505,97 @@ class UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x32, net_in, sg, em, lf, xr, embeddings_in, *params):
         plan = net._get_plan()
-        plan.refresh_weights()
         ts = get_train_state(net, plan)
-        ts.refresh_transposed()
-        d, saved = train_forward(net, plan, x32, net_in, sg, em, lf, xr)
-        ctx.net, ctx.saved = net, saved
+        ts.refresh()
+        ctx.net = net
         ctx.emb_dtype = embeddings_in.dtype
-        return d
+        ctx.graphs = None
+        key = (tuple(x32.shape), xr is not None, net_in is not x32, lf.data_ptr())
+        sg_ = ts.step_graphs.setdefault(key, _StepGraphs()) if net.use_cuda_graphs else None
+        if sg_ is None or sg_.busy or sg_.calls == 0:
+            if sg_ is not None:
+                sg_.calls += 1
+            d, ctx.saved = train_forward(net, plan, x32, net_in, sg, em, lf, xr)
+            return d
+        if sg_.fwd is None:
+            sg_.pool = torch.cuda.graph_pool_handle()
+            sg_.static = dict(x=x32.clone(), n=net_in.clone() if net_in is not x32 else None, s=sg.clone(), e=em.clone(),
+                              r=None if xr is None else xr.clone())
+            st = sg_.static
+            before = ops.launch_count
+            sg_.fwd, (sg_.d, sg_.saved) = _capture(
+                lambda: train_forward(net, plan, st["x"], st["n"] if st["n"] is not None else st["x"], st["s"], st["e"], lf,
+                                      st["r"]), sg_.pool, plan.device)
+            sg_.fwd_launches = ops.launch_count - before
+            ops.launch_count = before                 # captured, not executed: replays are counted below
+        st = sg_.static
+        st["x"].copy_(x32)
+        if st["n"] is not None:
+            st["n"].copy_(net_in)
+        st["s"].copy_(sg)
+        st["e"].copy_(em)
+        if st["r"] is not None:
+            st["r"].copy_(xr)
+        sg_.fwd.replay()
+        ops.launch_count += sg_.fwd_launches
+        sg_.busy = True
+        ctx.graphs = sg_
+        ctx.saved = sg_.saved
+        return sg_.d.clone()
 
     @staticmethod
     def backward(ctx, dD):
-        net, saved = ctx.net, ctx.saved
+        net, saved, sg_ = ctx.net, ctx.saved, ctx.graphs
         ctx.saved = None
         plan = net._get_plan()
         ts = get_train_state(net, plan)
         sync = getattr(net, "grad_sync", None)
         dD = dD.detach().to(torch.float32).contiguous()
+
+        def run(accumulate: bool, bucket_done) -> Tensor:
+            if sg_ is None:
+                return train_backward(net, plan, saved, dD, accumulate, bucket_done)
+            if sg_.dD is None:
+                sg_.dD = torch.empty_like(dD)
+            sg_.dD.copy_(dD)
+            if accumulate not in sg_.bwd:
+                # capture: every bucket boundary closes the current graph and opens the next one
+                segs: list = []
+                before = ops.launch_count
+                cur = torch.cuda.current_stream(plan.device)
+                side = torch.cuda.Stream(device=plan.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    state = {"g": torch.cuda.CUDAGraph()}
+                    state["g"].capture_begin(pool=sg_.pool)
+
+                    def cut(i: int) -> None:
+                        state["g"].capture_end()
+                        segs.append((state["g"], i))
+                        state["g"] = torch.cuda.CUDAGraph()
+                        state["g"].capture_begin(pool=sg_.pool)
+
+                    dl = train_backward(net, plan, saved, sg_.dD, accumulate, cut)
+                    state["g"].capture_end()
+                    segs.append((state["g"], None))
+                cur.wait_stream(side)
+                sg_.bwd[accumulate] = (segs, dl, ops.launch_count - before)
+                ops.launch_count = before
+            segs, dl, n_launch = sg_.bwd[accumulate]
+            ops.launch_count += n_launch
+            for g, i in segs:
+                g.replay()
+                if i is not None and bucket_done is not None:
+                    bucket_done(i)
+            sg_.busy = False
+            return dl.clone()
+
         if sync is not None:
-            dlabel = sync.run_backward(net, plan, ts, saved, dD)
+            dlabel = sync.run_backward(net, plan, ts, saved, dD, backward_fn=lambda n_, p_, s_, d_, accumulate=False,
+                                       bucket_done=None: run(accumulate, bucket_done))
             grads = [None] * (len(ts.slots) + ts.n_gains)
         else:
-            dlabel = train_backward(net, plan, saved, dD)
+            dlabel = run(False, None)
             flat = ts.grad_flat.clone()       # autograd owns what it is handed; grad_flat is reused next step
             grads = [flat[s.grad_off:s.grad_off + s.param.numel()].view_as(s.param) for s in ts.slots.values()]
             grads += [flat[ts.gain_off + i] for i in range(ts.n_gains)]

@@ -340,6 +340,39 @@ def weight_transpose(w_prepped: Tensor, cout: int, cin_g: int, taps: int, groups
     return out
 
 
+def make_wprep_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int]:
+    """Pack dd_wprep_desc records (dicts with w, out, gain, gain_host, O, I_g, taps, normalize, perm, head_dim,
+    row_stride); returns (device buffer, total_rows)."""
+    arr = (L.WprepDesc * len(entries))()
+    rows = 0
+    for i, e in enumerate(entries):
+        arr[i] = L.WprepDesc(L.ptr(e["w"]), L.ptr(e["out"]), L.ptr(e.get("gain")), e.get("gain_host", 1.0), _is_bf16(e["w"]),
+                             e["O"], e["I_g"], e["taps"], int(e.get("normalize", False)), e.get("perm", 0),
+                             e.get("head_dim", 0), e.get("row_stride", 0) or e["I_g"] * e["taps"], rows)
+        rows += e["O"]
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device), rows
+
+
+def weight_prep_batched(descs: Tensor, n: int, total_rows: int) -> None:
+    L.check(L.load().dd_weight_prep_batched(L.ptr(descs), n, total_rows, L.stream_ptr()))
+    _count()
+
+
+def make_wtrans_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int]:
+    """Pack dd_wtrans_desc records (dicts with src, dst, cout_g, cin_g, taps, groups); returns (buffer, total_tiles)."""
+    arr = (L.WtransDesc * len(entries))()
+    tiles = 0
+    for i, e in enumerate(entries):
+        arr[i] = L.WtransDesc(L.ptr(e["src"]), L.ptr(e["dst"]), e["cout_g"], e["cin_g"], e["taps"], e["groups"], tiles)
+        tiles += ((e["cin_g"] + 31) // 32) * ((e["cout_g"] + 31) // 32) * e["groups"] * e["taps"]
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device), tiles
+
+
+def weight_transpose_batched(descs: Tensor, n: int, total_tiles: int) -> None:
+    L.check(L.load().dd_weight_transpose_batched(L.ptr(descs), n, total_tiles, L.stream_ptr()))
+    _count()
+
+
 def make_wbwd_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int]:
     """Pack dd_wbwd_desc records (dicts with w, dweff, dw, gain, dgain, gain_host, O, I_g, taps, normalize, perm,
     head_dim, row_stride, accumulate) into a device buffer; returns (buffer, total_rows)."""

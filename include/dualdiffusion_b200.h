@@ -235,6 +235,28 @@ DD_API int dd_mpconv_wgrad(const void* x, const void* dy, float* dw, int B, int 
  * that turns dd_mpconv_forward(dy, ., Cin<->Cout swapped) into the data gradient of the convolution.      */
 DD_API int dd_weight_transpose(const void* w_prepped, void* out, int Cout, int cin_g, int taps, int groups, void* stream);
 
+/* dd_weight_prep (DD_WFMT_BF16_OTI output) for a whole parameter set in one launch: one CTA per weight row of every
+ * descriptor.  Used by the train step, where every MPConv weight changes every optimizer step (mp_tools.py:359-364 runs
+ * inside each forward there).                                                                                         */
+typedef struct dd_wprep_desc {
+    const void* w;       /* parameter [O][I_g][taps], fp32 or bf16 */
+    void* out;           /* bf16 [O (or more, zero-filled by the caller)][row_stride] */
+    const float* gain;   /* device scalar or NULL */
+    float gain_host;
+    int w_is_bf16, O, I_g, taps, normalize, perm, head_dim, row_stride;
+    int row_begin;       /* exclusive prefix sum of O over the descriptor array */
+} dd_wprep_desc;
+DD_API int dd_weight_prep_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream);
+/* dd_weight_transpose for a whole parameter set in one launch (32x32 tiles; tile_begin = exclusive prefix sum of
+ * ceil(cin_g/32)*ceil(cout_g/32)*groups*taps).                                                                       */
+typedef struct dd_wtrans_desc {
+    const void* src;     /* bf16 [groups*cout_g][taps][cin_g] */
+    void* dst;           /* bf16 [groups*cin_g][taps][cout_g], taps reversed */
+    int cout_g, cin_g, taps, groups;
+    int tile_begin;
+} dd_wtrans_desc;
+DD_API int dd_weight_transpose_batched(const dd_wtrans_desc* descs_dev, int n_descs, int total_tiles, void* stream);
+
 /* Backward of dd_weight_prep (mp_tools.py:359-364), batched over parameters: one CTA per weight row.
  *   dw[o][i][tap] (=|+=) d(w_eff)/d(w) applied to dweff;  *dgain += <dweff, w_hat>/sqrt(fan_in) * gain_host       */
 typedef struct dd_wbwd_desc {

@@ -458,3 +458,66 @@ def test_train_step_is_linear_in_upstream_gradient_and_accumulates(dev):
     for n, p in net.named_parameters():
         if n in g1 and g1[n].norm() > 1e-8 and not n.startswith("emb_label") and not n.startswith("logvar"):
             assert rel_err(p.grad, 2 * g1[n]) < 1e-4, n
+
+
+def test_train_step_cuda_graphs_match_eager_and_batch_shards_add_up(dev):
+    """(1) The captured forward / per-bucket backward graphs reproduce the eager schedule exactly (same kernels, same
+    order; only the atomically-accumulated scale gradients may differ in summation order).  (2) DDP equivalence
+    (SURVEY.md section 8(c)): for a loss that is a sum over items, the gradient of a batch equals the sum of the
+    gradients of its shards."""
+    spec = uo.small_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    gen = torch.Generator().manual_seed(73)
+    x = torch.randn(2, 4, 32, 48, generator=gen).to(dev)
+    sigma = torch.tensor([0.7, 3.0]).to(dev)
+    clap = torch.randn(2, spec.in_channels_emb, generator=gen).to(dev)
+    mask = torch.tensor([True, False]).to(dev)
+    probe = torch.randn(2, 4, 32, 48, generator=gen).to(dev)
+    net = make_train_unet(spec, sd, dev)
+
+    def run(sl, graphs):
+        net.use_cuda_graphs = graphs
+        net.zero_grad(set_to_none=True)
+        emb = net.get_embeddings(clap[sl], mask[sl])
+        d = net(x[sl], sigma[sl], None, emb)
+        (d * probe[sl]).sum().backward()
+        return d.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+
+    full = slice(0, 2)
+    d_e, g_e = run(full, False)
+    for _ in range(3):                       # eager warm-up call, capture + replay, replay
+        d_g, g_g = run(full, True)
+    assert torch.equal(d_g, d_e)
+    for n in g_e:
+        assert rel_err(g_g[n], g_e[n]) < 1e-3 or g_e[n].norm() < 1e-8, n      # fp32 atomics: summation order only
+    _, g0 = run(slice(0, 1), False)
+    _, g1 = run(slice(1, 2), False)
+    for n in g_e:
+        if g_e[n].norm() > 1e-8:
+            assert rel_err(g0[n] + g1[n], g_e[n]) < 2e-2, (n, rel_err(g0[n] + g1[n], g_e[n]))
+
+
+def test_batched_weight_prep_and_transpose_match_single_calls(dev):
+    from dualdiffusion_b200 import ops, _lib as L
+    gen = torch.Generator().manual_seed(79)
+    shapes = [((512, 32, 3, 3), 8, 0, 0), ((256, 6, 3, 3), 1, 0, 64), ((256, 128, 1, 1), 1, 64, 0), ((768, 96, 3, 3), 8, 0, 0)]
+    prep, trans, singles = [], [], []
+    gain = torch.tensor([0.7], device=dev)
+    for shape, groups, qk, rs in shapes:
+        w = torch.randn(shape, generator=gen).to(dev)
+        O, I, taps = shape[0], shape[1], shape[2] * shape[3]
+        out = torch.zeros((O, rs or taps * I), device=dev, dtype=torch.bfloat16)
+        prep.append(dict(w=w, out=out, gain=gain, O=O, I_g=I, taps=taps, normalize=True, perm=L.WPERM_QK if qk else 0,
+                         head_dim=qk, row_stride=rs))
+        ref = ops.weight_prep(w, gain=gain, normalize=True, qk_head_dim=qk, row_stride=rs)
+        singles.append((out, ref))
+        if not rs:
+            dst = torch.empty((groups * I, taps, O // groups), device=dev, dtype=torch.bfloat16)
+            trans.append(dict(src=out, dst=dst, cout_g=O // groups, cin_g=I, taps=taps, groups=groups))
+            singles.append((dst, ops.weight_transpose(ref, O, I, taps, groups)))
+    buf, rows = ops.make_wprep_descs(prep, dev)
+    ops.weight_prep_batched(buf, len(prep), rows)
+    buf2, tiles = ops.make_wtrans_descs(trans, dev)
+    ops.weight_transpose_batched(buf2, len(trans), tiles)
+    for got, ref in singles:
+        assert torch.equal(got.view(-1), ref.view(-1))

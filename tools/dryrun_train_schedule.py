@@ -103,7 +103,7 @@ def noise_embedding_bwd(sigma, fr, ph, w, lab, lb, demb, normalize, dweff=None):
     return dweff, torch.zeros_like(lab)
 
 
-stubs.update(cat_silu=cat_silu, cat_silu_bwd=cat_silu_bwd, noise_embedding_bwd=noise_embedding_bwd)
+stubs.update(weight_prep_batched=lambda b, n, r: None, weight_transpose_batched=lambda b, n, t: None, cat_silu=cat_silu, cat_silu_bwd=cat_silu_bwd, noise_embedding_bwd=noise_embedding_bwd)
 for k, v in stubs.items():
     assert hasattr(ops, k), k
     setattr(ops, k, v)
@@ -122,9 +122,8 @@ def run(spec, shape):
     plan.device = torch.device("cpu")
     net._plan = plan
     net._get_plan = lambda: plan
-    plan.refresh_weights()
     ts = T.get_train_state(net, plan)
-    ts.refresh_transposed()
+    ts.refresh()
     B = shape[0]
     x = torch.randn(shape)
     sg = torch.ones(B)
