@@ -271,6 +271,52 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> di
                          "frac": flop * sps / world / 1e12 / pk["tflops"]}}
 
 
+def bench_dae(device, batch: int = 16, steps: int = 3) -> dict:
+    """BASELINE.json configs[4]: DAE_D3 diffusion-decoder forward, batch 16 latents (16,8,32,688) -> mel-spectrograms
+    (16,2,256,5504), bf16 tensor-core compute, default edm2_ddec_mclt_b1a decoder (random-init weights).  Tensor-bound
+    (7.313 TFLOP per sample)."""
+    from oracle import dae_oracle as do            # seeded synthetic weights only
+    from dualdiffusion_b200.modules.daes.dae_edm2_d3 import DAE_D3, DAE_D3_Config
+    from dualdiffusion_b200 import ops
+    spec = do.DAESpec()
+    sd = do.synth_dae_state_dict(spec, seed=0)
+    net = DAE_D3(DAE_D3_Config(channel_mult_enc=spec.channel_mult_enc))
+    net.load_state_dict(sd, strict=True)
+    net = net.requires_grad_(False).train(False).to(device)
+    g = torch.Generator(device=device).manual_seed(0)
+    lat = torch.randn(batch, 8, LATENT[2], LATENT[3], device=device, generator=g)
+    lat = lat / lat.square().mean(dim=(1, 2, 3), keepdim=True).sqrt()
+    emb = net.get_embeddings(torch.randn(batch, spec.in_channels_emb, device=device, generator=g))
+    # FLOPs from the layer shapes (2 * pixels * 2 stereo sides * Cout * fan_in per MPConv3D)
+    flop = 0.0
+    h, w = LATENT[2], LATENT[3]
+    flop += 2.0 * h * w * 2 * spec.dec_channels[-1] * 5 * 18
+    for name, cin, cout, up in do.dec_block_plan(spec):
+        if up:
+            h, w = 2 * h, 2 * w
+        m = spec.mlp_multiplier
+        flop += 2.0 * h * w * 2 * (cout * m * cin * 18 + cout * cout * m * 18 + (cout * cin if cin != cout else 0))
+    flop += 2.0 * h * w * 2 * spec.dec_channels[0] * 25
+    for _ in range(2):
+        mel = net.decode(lat, emb)
+    torch.cuda.synchronize()
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        mel = net.decode(lat, emb)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pk = peaks()
+    sps = batch / (ms * 1e-3)
+    return {"metric": "DAE_D3 decoder forward samples/sec (batch 16 latents 8x32x688 -> mel 2x256x5504, bf16)",
+            "value": sps, "unit": "samples/s", "ms_per_batch": ms, "batch": batch, "out_shape": list(mel.shape),
+            "gpu_launches_per_batch": (ops.launch_count - l0) // steps, "tflop_per_sample": flop / 1e12,
+            "roofline": {"bound": "tensor", "achieved": flop * sps / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": flop * sps / 1e12 / pk["tflops"]}}
+
+
 def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -382,6 +428,12 @@ def run_ours(args) -> None:
         torch.cuda.empty_cache()
         train = bench_train(device, dist, world)
 
+    dae = None
+    if rank == 0 and world == 1 and not args.no_dae:
+        torch.cuda.empty_cache()
+        dae = bench_dae(device)
+        torch.cuda.empty_cache()
+
     secondary = None
     if rank == 0 and world == 1 and not args.no_format:
         secondary = bench_format(device)
@@ -396,7 +448,7 @@ def run_ours(args) -> None:
                            "library": os.path.relpath(_lib.lib_path(), ROOT)},
                 "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
-                "train_step": train, "secondary": secondary}
+                "train_step": train, "dae_decode": dae, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -410,6 +462,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-format", action="store_true", help="skip the mel-STFT/FGLA secondary measurement")
+    ap.add_argument("--no-dae", action="store_true", help="skip the DAE_D3 decoder (BASELINE config 5) measurement")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step (fwd+bwd+all-reduce) measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,0 +1,250 @@
+// Glue kernels of the DAE_D3 diffusion-autoencoder decoder (reference: /root/reference/src/modules/daes/dae_edm2_d3.py,
+// MPConv3D :43-93, Block.forward :186-238, DAE_D3.decode :356-369).
+//
+// Layout.  The reference keeps stereo as a depth axis Z = 2 of channels_last_3d tensors (B, C, 2, H, W) and convolves
+// with (kz, 3, 3) kernels: reflection padding along W, one-sided reflection along Z, zero padding along H.  Here Z is
+// folded into the channel dimension -- activations are NHWC bf16 [B][H][Wp][2C], channel = z*C + c -- which turns
+//   * a (2,3,3) MPConv3D into a dense 3x3 convolution 2Cin -> 2Cout whose weight is block-circulant in z
+//     (out[z'] = sum_z W[kz = z xor z'] * x[z]: exactly the reference's [x0, x1, x0] one-sided reflection), and
+//   * a (1,k,k) MPConv3D into a 2-group convolution with the weight duplicated,
+// so every MPConv3D runs on the tcgen05 implicit-GEMM kernels of conv_igemm.cu with identical FLOPs.  Reflection
+// along W is physical: tensors carry `pw` halo columns on each side (Wp = W + 2*pw) that hold the mirrored columns; the
+// convolution computes all Wp columns with TMA zero fill beyond them and dd_reflect_fill_w re-mirrors the halo columns
+// of its output.
+#include "common.cuh"
+#include "dualdiffusion_b200.h"
+
+#include <algorithm>
+#include <math.h>
+
+namespace {
+
+inline int grid_for_d(long total, int block, int cap_mult = 16) {
+    const long blocks = (total + block - 1) / block;
+    return (int)std::max<long>(1, std::min<long>(blocks, (long)dd_num_sms() * cap_mult));
+}
+
+__device__ __forceinline__ void unpack8d(const uint4& q, float (&f)[8]) {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(u[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8d(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// reflect a logical column index into [0, W)
+__device__ __forceinline__ int reflect_idx(int w, int W) {
+    if (w < 0) w = -w;
+    if (w >= W) w = 2 * (W - 1) - w;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------
+// MPConv3D weight prep with Z folded into channels (eval mode: scale = gain / sqrt(fan_in), dae_edm2_d3.py:80-81)
+//   kz == 2: out[(z', o)][tap][z*I + i] = scale * w[o][i][z xor z'][tap]      (dense over 2I input channels)
+//   kz == 1: out[(z', o)][tap][i]       = scale * w[o][i][0][tap]             (2 groups, duplicated)
+// ------------------------------------------------------------------------------------------
+template <bool kBf16>
+__global__ void weight_prep_z2_kernel(const void* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I, int kz,
+                                      int taps, const float* __restrict__ gain_dev, float gain_host, int i_stride) {
+    const int r = blockIdx.x;
+    const int zp = r / O, o = r - zp * O;
+    const float scale = gain_host * (gain_dev ? *gain_dev : 1.f) * rsqrtf((float)(I * kz * taps));
+    const int row_len = taps * i_stride;
+    __nv_bfloat16* dst = out + (size_t)r * row_len;
+    const int n_in = kz == 2 ? 2 * I : I;
+    for (int j = threadIdx.x; j < row_len; j += blockDim.x) {
+        const int tap = j / i_stride, c = j - tap * i_stride;
+        float v = 0.f;
+        if (c < n_in) {
+            const int z = c / I, i = c - z * I;
+            const int kzi = kz == 2 ? (z ^ zp) : 0;
+            const size_t src = (((size_t)o * I + i) * kz + kzi) * taps + tap;
+            v = (kBf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(w)[src]) : static_cast<const float*>(w)[src]) * scale;
+        }
+        dst[j] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// halo columns <- mirrored logical columns:  x[.., pw-k] = x[.., pw+k],  x[.., pw+W-1+k] = x[.., pw+W-1-k]
+// ------------------------------------------------------------------------------------------
+__global__ void reflect_fill_w_kernel(uint4* __restrict__ x, long rows, int Wp, int nvec, int pw) {
+    const long total = rows * 2 * pw * nvec;
+    const int W = Wp - 2 * pw;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % nvec);
+        long r = idx / nvec;
+        const int k = (int)(r % (2 * pw));
+        r /= (2 * pw);
+        int dst_col, src_col;
+        if (k < pw) { dst_col = pw - 1 - k; src_col = pw + 1 + k; }
+        else        { const int kk = k - pw; dst_col = pw + W + kk; src_col = pw + W - 2 - kk; }
+        uint4* row = x + r * (long)Wp * nvec;
+        row[(long)dst_col * nvec + v] = row[(long)src_col * nvec + v];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder stem input (DAE_D3.decode :358-359): latents (B, 2L, H, W) fp32 NCHW, channel c8 = c*2 + z
+//   -> [B][H][Wp][Cpad] bf16 with channel z*(L+1) + c, the constant-one channel at c == L, zeros above 2(L+1)
+// ------------------------------------------------------------------------------------------
+__global__ void dae_stem_kernel(const float* __restrict__ lat, __nv_bfloat16* __restrict__ out, int B, int L, int H, int W,
+                                int pw, int Cpad) {
+    const int Wp = W + 2 * pw;
+    const long total = (long)B * H * Wp * Cpad;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(idx % Cpad);
+        long pix = idx / Cpad;
+        const int p = (int)(pix % Wp);
+        pix /= Wp;
+        const int h = (int)(pix % H), b = (int)(pix / H);
+        const int w = reflect_idx(p - pw, W);
+        float v = 0.f;
+        if (ch < 2 * (L + 1)) {
+            const int z = ch / (L + 1), c = ch - z * (L + 1);
+            v = c == L ? 1.f : lat[(((size_t)b * 2 * L + c * 2 + z) * H + h) * W + w];
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// resample_3d "up" (mp_tools.py:92-93: nearest x2 in H and W) on a W-padded tensor + mp_silu
+// ------------------------------------------------------------------------------------------
+__global__ void up2_silu_pad_kernel(const uint4* __restrict__ a, uint4* __restrict__ xc, uint4* __restrict__ s, int B, int Ha,
+                                    int Wa, int pw, int nvec) {
+    const int H = 2 * Ha, W = 2 * Wa, Wp = W + 2 * pw, Wpa = Wa + 2 * pw;
+    const long total = (long)B * H * Wp * nvec;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % nvec);
+        long pix = idx / nvec;
+        const int p = (int)(pix % Wp);
+        pix /= Wp;
+        const int h = (int)(pix % H), b = (int)(pix / H);
+        const int w = reflect_idx(p - pw, W);
+        const uint4 q = __ldg(a + (((long)b * Ha + (h >> 1)) * Wpa + (w >> 1) + pw) * nvec + v);
+        float f[8], o[8];
+        unpack8d(q, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = mp_silu_f(f[j]);
+        xc[idx] = q;
+        s[idx] = pack8d(o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conv_out: MPConv3D (1,5,5), C channels per stereo side -> 1 (DAE_D3.decode :368), direct convolution on CUDA cores
+// (9 GFLOP per 45 s item; the kernel is bound by reading the level-0 activation once).
+//   x [B][H][Wp][2C] bf16 (pw >= 2), w fp32 [C][25] pre-scaled by 1/sqrt(25 C) (dd_weight_prep, DD_WFMT_F32_OIT),
+//   out fp32 [B][2][H][W]
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) conv5x5_out_kernel(const uint4* __restrict__ x, const float* __restrict__ wq,
+                                                          const float* __restrict__ gain, float* __restrict__ out, int B,
+                                                          int H, int W, int pw) {
+    __shared__ float ws[25 * C];
+    const float g = gain ? *gain : 1.f;
+    for (int i = threadIdx.x; i < 25 * C; i += blockDim.x) ws[i] = wq[i] * g;
+    __syncthreads();
+    constexpr int NV = C / 8;                    // uint4 vectors per stereo side
+    const int Wp = W + 2 * pw;
+    const long total = (long)B * H * W;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int w = (int)(idx % W);
+        const int h = (int)((idx / W) % H);
+        const int b = (int)(idx / ((long)W * H));
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int dy = -2; dy <= 2; ++dy) {
+            const int hh = h + dy;
+            if (hh < 0 || hh >= H) continue;                                   // zero padding along H
+            const uint4* row = x + ((long)b * H + hh) * Wp * (2 * NV);
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                const uint4* px = row + (long)(w + pw + dx) * (2 * NV);       // halo columns hold the reflection
+                const float* wt = ws + ((dy + 2) * 5 + (dx + 2));
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    float f0[8], f1[8];
+                    unpack8d(__ldg(px + v), f0);
+                    unpack8d(__ldg(px + NV + v), f1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { acc0 += f0[j] * wt[(v * 8 + j) * 25]; acc1 += f1[j] * wt[(v * 8 + j) * 25]; }
+                }
+            }
+        }
+        out[(((size_t)b * 2 + 0) * H + h) * W + w] = acc0;
+        out[(((size_t)b * 2 + 1) * H + h) * W + w] = acc1;
+    }
+}
+
+}  // namespace
+
+extern "C" int dd_weight_prep_z2(const void* w, int w_is_bf16, void* out, int O, int I, int kz, int taps,
+                                 const float* gain_dev, float gain_host, int i_stride, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(w && out && O > 0 && I > 0 && taps > 0, "dd_weight_prep_z2: bad arguments");
+    DD_REQUIRE(kz == 1 || kz == 2, "dd_weight_prep_z2: kz=%d unsupported (stereo depth 2)", kz);
+    const int n_in = kz == 2 ? 2 * I : I;
+    if (i_stride <= 0) i_stride = n_in;
+    DD_REQUIRE(i_stride >= n_in, "dd_weight_prep_z2: i_stride smaller than the input channel count");
+    if (w_is_bf16)
+        weight_prep_z2_kernel<true><<<2 * O, 128, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), O, I, kz, taps, gain_dev,
+                                                               gain_host, i_stride);
+    else
+        weight_prep_z2_kernel<false><<<2 * O, 128, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), O, I, kz, taps, gain_dev,
+                                                                gain_host, i_stride);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_reflect_fill_w(void* x, int B, int H, int Wp, int C, int pw, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && C % 8 == 0 && pw >= 1 && Wp - 2 * pw >= pw + 1, "dd_reflect_fill_w: bad arguments");
+    const long rows = (long)B * H;
+    const long total = rows * 2 * pw * (C / 8);
+    if (total == 0) return 0;
+    reflect_fill_w_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<uint4*>(x), rows, Wp, C / 8, pw);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_dae_stem(const float* latents, void* out, int B, int L, int H, int W, int pw, int Cpad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(latents && out && L > 0 && 2 * (L + 1) <= Cpad && pw >= 1 && W > pw, "dd_dae_stem: bad arguments");
+    const long total = (long)B * H * (W + 2 * pw) * Cpad;
+    if (total == 0) return 0;
+    dae_stem_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(latents, static_cast<__nv_bfloat16*>(out), B, L, H, W, pw,
+                                                                Cpad);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_up2_silu_pad(const void* a, void* xc, void* s, int B, int Ha, int Wa, int C, int pw, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(a && xc && s && C % 8 == 0 && pw >= 1 && Wa >= 1, "dd_up2_silu_pad: bad arguments");
+    const long total = (long)B * 2 * Ha * (2 * Wa + 2 * pw) * (C / 8);
+    if (total == 0) return 0;
+    up2_silu_pad_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(a), static_cast<uint4*>(xc),
+                                                                    static_cast<uint4*>(s), B, Ha, Wa, pw, C / 8);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_conv5x5_out(const void* x, const float* w25, const float* gain_dev, float* out, int B, int H, int W, int C,
+                              int pw, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && w25 && out && pw >= 2, "dd_conv5x5_out: bad arguments (needs two halo columns)");
+    const long total = (long)B * H * W;
+    if (total == 0) return 0;
+    const int grid = grid_for_d(total, 256);
+    if (C == 32)
+        conv5x5_out_kernel<32><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
+    else if (C == 64)
+        conv5x5_out_kernel<64><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
+    else
+        DD_REQUIRE(false, "dd_conv5x5_out: C=%d unsupported (32 or 64 channels per stereo side)", C);
+    DD_CHECK_LAUNCH();
+    return 0;
+}

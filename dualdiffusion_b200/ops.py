@@ -521,3 +521,56 @@ def head_grad(dD: Tensor, sigma: Tensor, sigma_data: float, x_ref: Optional[Tens
                                   L.stream_ptr()))
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# DAE_D3 decoder glue (stereo depth folded into channels, physical reflection halo along W)
+# ---------------------------------------------------------------------------------------------------------
+def weight_prep_z2(w: Tensor, gain: Optional[Tensor] = None, gain_host: float = 1.0, i_stride: int = 0,
+                   out: Optional[Tensor] = None) -> Tensor:
+    """MPConv3D weight [O, I, kz, kh, kw] -> bf16 [2*O, kh*kw, i_stride or (kz*I)] in the folded-stereo layout."""
+    L.require_cuda(w)
+    w = w.contiguous()
+    O, I, kz = w.shape[0], w.shape[1], w.shape[2]
+    taps = w.shape[3] * w.shape[4]
+    n_in = 2 * I if kz == 2 else I
+    if out is None:
+        out = torch.empty((2 * O, taps, i_stride or n_in), device=w.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_weight_prep_z2(L.ptr(w), _is_bf16(w), L.ptr(out), O, I, kz, taps, L.ptr(gain), gain_host,
+                                       i_stride, L.stream_ptr()))
+    _count()
+    return out
+
+
+def reflect_fill_w(x: Tensor, pw: int) -> Tensor:
+    B, H, Wp, Cc = x.shape
+    L.check(L.load().dd_reflect_fill_w(L.ptr(x), B, H, Wp, Cc, pw, L.stream_ptr()))
+    _count()
+    return x
+
+
+def dae_stem(latents: Tensor, latent_channels: int, pw: int, cpad: int = 32) -> Tensor:
+    B, C2, H, W = latents.shape
+    out = torch.empty((B, H, W + 2 * pw, cpad), device=latents.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_dae_stem(L.ptr(latents), L.ptr(out), B, latent_channels, H, W, pw, cpad, L.stream_ptr()))
+    _count()
+    return out
+
+
+def up2_silu_pad(a: Tensor, pw: int) -> Tuple[Tensor, Tensor]:
+    B, Ha, Wpa, Cc = a.shape
+    Wa = Wpa - 2 * pw
+    xc = torch.empty((B, 2 * Ha, 2 * Wa + 2 * pw, Cc), device=a.device, dtype=torch.bfloat16)
+    s = torch.empty_like(xc)
+    L.check(L.load().dd_up2_silu_pad(L.ptr(a), L.ptr(xc), L.ptr(s), B, Ha, Wa, Cc, pw, L.stream_ptr()))
+    _count()
+    return xc, s
+
+
+def conv5x5_out(x: Tensor, w25: Tensor, gain: Optional[Tensor], pw: int) -> Tensor:
+    B, H, Wp, C2 = x.shape
+    W = Wp - 2 * pw
+    out = torch.empty((B, 2, H, W), device=x.device, dtype=torch.float32)
+    L.check(L.load().dd_conv5x5_out(L.ptr(x), L.ptr(w25), L.ptr(gain), L.ptr(out), B, H, W, C2 // 2, pw, L.stream_ptr()))
+    _count()
+    return out

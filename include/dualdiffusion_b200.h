@@ -320,6 +320,30 @@ DD_API int dd_sigma_logvar_bwd(const float* sigma, int count, const float* freqs
 DD_API int dd_head_grad(const float* dD_nchw, const float* sigma, float sigma_data, const float* x_ref_nchw, void* dF_nhwc,
                         int B, int Cout, int H, int W, int Cpad, void* stream);
 
+/* ==== DAE_D3 diffusion-autoencoder decoder (modules/daes/dae_edm2_d3.py) ==========
+ * Stereo depth Z = 2 of the reference's channels_last_3d tensors is folded into the channel dimension
+ * ([B][H][Wp][2C] bf16, channel = z*C + c) so that every MPConv3D (:43-93) runs on dd_mpconv_forward; reflection
+ * padding along W (:63-66) is physical: tensors carry pw halo columns per side (Wp = W + 2*pw).               */
+
+/* MPConv3D weight path, eval mode (:70-81), into the folded layout.  w: [O][I][kz][taps] fp32 or bf16.
+ *   kz == 2 -> bf16 [2*O][taps][i_stride], element (z'*O+o, tap, z*I+i) = scale*w[o][i][z xor z'][tap]  (dense conv)
+ *   kz == 1 -> bf16 [2*O][taps][i_stride], element (z'*O+o, tap, i)     = scale*w[o][i][0][tap]         (groups = 2)
+ * scale = gain_host * (*gain_dev) / sqrt(I*kz*taps); columns >= the input channel count are zero.               */
+DD_API int dd_weight_prep_z2(const void* w, int w_is_bf16, void* out, int O, int I, int kz, int taps, const float* gain_dev,
+                             float gain_host, int i_stride, void* stream);
+/* ReflectionPad3d along W (:64): x[.., pw-k, :] = x[.., pw+k, :], x[.., pw+W-1+k, :] = x[.., pw+W-1-k, :], k = 1..pw. */
+DD_API int dd_reflect_fill_w(void* x, int B, int H, int Wp, int C, int pw, void* stream);
+/* DAE_D3.decode input (:358-359): latents fp32 NCHW (B, 2L, H, W) -> [B][H][W+2pw][Cpad] bf16, channel z*(L+1)+c with
+ * the constant-one channel at c == L, zero above 2(L+1), halo columns mirrored.                                 */
+DD_API int dd_dae_stem(const float* latents, void* out, int B, int L, int H, int W, int pw, int Cpad, void* stream);
+/* Block.forward head of an "up" block (:188-189,196): xc = resample_3d(a, "up") (nearest x2 in H, W), s = mp_silu(xc);
+ * a [B][Ha][Wa+2pw][C] -> xc, s [B][2Ha][2Wa+2pw][C], halo columns mirrored.                                    */
+DD_API int dd_up2_silu_pad(const void* a, void* xc, void* s, int B, int Ha, int Wa, int C, int pw, void* stream);
+/* conv_out (:368): MPConv3D (1,5,5), C -> 1 per stereo side, times *gain_dev.  x [B][H][W+2pw][2C] bf16 (pw >= 2),
+ * w25 fp32 [C][25] pre-scaled by 1/sqrt(25 C); out fp32 NCHW (B, 2, H, W) = tensor_5d_to_4d of the reference.   */
+DD_API int dd_conv5x5_out(const void* x, const float* w25, const float* gain_dev, float* out, int B, int H, int W, int C,
+                          int pw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,28 @@ def main():
     print("train loss", float(loss), "params", len(stats))
     torch.set_grad_enabled(False)
 
+    # ---- DAE_D3 decoder (dae_edm2_d3.py:356-369), reduced config, two latent sizes (coarsest level 4 and 8 rows) ----
+    from oracle import dae_oracle as do
+    from modules.daes.dae_edm2_d3 import DAE_D3, DAE_D3_Config
+    dspec = do.small_dae_spec()
+    dsd = do.synth_dae_state_dict(dspec, seed=0)
+    dae = DAE_D3(DAE_D3_Config(in_channels_emb=dspec.in_channels_emb, model_channels=dspec.model_channels,
+                               channel_mult_enc=dspec.channel_mult_enc, channel_mult_dec=tuple(dspec.channel_mult_dec),
+                               channel_mult_emb=dspec.channel_mult_emb, num_enc_layers=dspec.num_enc_layers,
+                               num_dec_layers_per_block=dspec.num_dec_layers_per_block,
+                               mlp_multiplier=dspec.mlp_multiplier)).eval()
+    dae.load_state_dict(dsd, strict=True)
+    g = torch.Generator().manual_seed(6)
+    cases = {}
+    for tag, shape in (("h4", (2, 8, 4, 12)), ("h8", (1, 8, 8, 22))):
+        lat = uo.normalize(torch.randn(shape, generator=g))
+        emb_in = torch.randn(shape[0], dspec.in_channels_emb, generator=g)
+        emb = dae.get_embeddings(emb_in)
+        cases[tag] = dict(latents=lat, emb_in=emb_in, emb=emb, mel=dae.decode(lat, emb))
+        print("dae", tag, cases[tag]["mel"].shape, float(cases[tag]["mel"].std()))
+    torch.save(dict(cases=cases, weight_checksum=weight_checksum(dsd), mel_shape=dae.get_mel_spec_shape((3, 8, 32, 688)),
+                    latent_shape=dae.get_latent_shape((3, 2, 256, 5504))), os.path.join(OUT, "dae_small.pt"))
+
     # ---- sampler: reference diffusion_decode on CPU, reduced config, 3 Heun+CFG steps ----
     spec = uo.small_spec()
     sd = uo.synth_state_dict(spec, seed=0)

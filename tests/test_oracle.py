@@ -152,3 +152,19 @@ def test_oracle_train_step_gradients_vs_golden_reference():
         assert abs(dot - dot_ref) <= 1e-3 * n_ref * 3 + 1e-9, name
     for name, gref in g["small_grads"].items():
         assert rel_err(sdg[name].grad, gref) < 1e-4 or (sdg[name].grad - gref).abs().max() < 1e-8, name
+
+
+def test_dae_oracle_decode_vs_golden_reference():
+    """Row A16: the DAE_D3 decoder restatement (oracle/dae_oracle.py) against the reference module's output."""
+    from oracle import dae_oracle as do
+    g = load_golden("dae_small.pt")
+    spec = do.small_dae_spec()
+    sd = do.synth_dae_state_dict(spec, seed=0)
+    assert abs(float(sum(v.double().abs().sum() for v in sd.values())) - g["weight_checksum"]) < 1e-6 * g["weight_checksum"]
+    for tag, c in g["cases"].items():
+        emb = do.dae_get_embeddings(sd, c["emb_in"])
+        assert rel_err(emb, c["emb"]) < 1e-6
+        mel = do.dae_decode(sd, spec, c["latents"], emb)
+        assert mel.shape == c["mel"].shape and rel_err(mel, c["mel"]) < 1e-5, tag
+    r = 2 ** (len(spec.channel_mult_dec) - 1)      # get_mel_spec_shape / get_latent_shape (:323-342)
+    assert tuple(g["mel_shape"]) == (3, 2, 32 * r, 688 * r) and tuple(g["latent_shape"]) == (3, 8, 256 // r, 5504 // r)
