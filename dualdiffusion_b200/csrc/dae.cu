@@ -179,6 +179,86 @@ __global__ void __launch_bounds__(256) conv5x5_out_kernel(const uint4* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// ddec UNet input (unet_edm2_ddec_mclt_b1.py:294-309): per stereo side z the channels are
+//   [ c_in(sigma) * x_in[b][z] ,  x_ref[b][z][h*k + j] for j < k  (the view/permute(0,3,1,2,4) of :294-295) ,  1 ]
+// -> folded [B][F][Wp][Cpad] bf16, channel z*(k+2) + c, zeros above 2(k+2), halo columns mirrored
+// ------------------------------------------------------------------------------------------
+__global__ void ddec_stem_kernel(const float* __restrict__ x_in, const float* __restrict__ x_ref,
+                                 const float* __restrict__ sigma, float sigma_data, __nv_bfloat16* __restrict__ out, int B,
+                                 int Fq, int W, int k, int pw, int Cpad) {
+    const int Wp = W + 2 * pw, ct = k + 2;
+    const long total = (long)B * Fq * Wp * Cpad;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(idx % Cpad);
+        long pix = idx / Cpad;
+        const int p = (int)(pix % Wp);
+        pix /= Wp;
+        const int h = (int)(pix % Fq), b = (int)(pix / Fq);
+        const int w = reflect_idx(p - pw, W);
+        float v = 0.f;
+        if (ch < 2 * ct) {
+            const int z = ch / ct, c = ch - z * ct;
+            if (c == 0) {
+                const float sg = sigma[b];
+                v = x_in[(((size_t)b * 2 + z) * Fq + h) * W + w] * rsqrtf(sigma_data * sigma_data + sg * sg);
+            } else if (c <= k) {
+                v = x_ref[(((size_t)b * 2 + z) * Fq * k + (size_t)h * k + (c - 1)) * W + w];
+            } else {
+                v = 1.f;
+            }
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+// resample_3d "down" (mp_tools.py:85-90: 2x2 mean over H, W) on a W-padded tensor, halo columns of the result mirrored
+__global__ void avgpool2_pad_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int pw,
+                                    int nvec) {
+    const int Ho = H >> 1, Wo = W >> 1, Wp = W + 2 * pw, Wpo = Wo + 2 * pw;
+    const long total = (long)B * Ho * Wpo * nvec;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % nvec);
+        long pix = idx / nvec;
+        const int p = (int)(pix % Wpo);
+        pix /= Wpo;
+        const int h = (int)(pix % Ho), b = (int)(pix / Ho);
+        const int w = reflect_idx(p - pw, Wo);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                float f[8];
+                unpack8d(__ldg(x + (((long)b * H + 2 * h + dy) * Wp + 2 * w + dx + pw) * nvec + v), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+        out[idx] = pack8d(acc);
+    }
+}
+
+// ddec output head (:323-326): D = c_skip*x_in + c_out*F, F = conv_out result (folded: channel z of a Cst-wide pixel)
+__global__ void ddec_head_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict__ x_in,
+                                 const float* __restrict__ sigma, float sigma_data, float* __restrict__ out, int B, int H,
+                                 int W, int pw, int Cst) {
+    const int Wp = W + 2 * pw;
+    const long total = (long)B * 2 * H * W;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int w = (int)(idx % W);
+        long r = idx / W;
+        const int h = (int)(r % H);
+        r /= H;
+        const int z = (int)(r % 2), b = (int)(r / 2);
+        const float sg = sigma[b], sd2 = sigma_data * sigma_data;
+        const float c_skip = sd2 / (sg * sg + sd2), c_out = sg * sigma_data * rsqrtf(sg * sg + sd2);
+        const float fv = __bfloat162float(f[(((size_t)b * H + h) * Wp + w + pw) * Cst + z]);
+        out[idx] = c_skip * x_in[idx] + c_out * fv;
+    }
+}
+
 }  // namespace
 
 extern "C" int dd_weight_prep_z2(const void* w, int w_is_bf16, void* out, int O, int I, int kz, int taps,
@@ -245,6 +325,41 @@ extern "C" int dd_conv5x5_out(const void* x, const float* w25, const float* gain
         conv5x5_out_kernel<64><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
     else
         DD_REQUIRE(false, "dd_conv5x5_out: C=%d unsupported (32 or 64 channels per stereo side)", C);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_ddec_stem(const float* x_in, const float* x_ref, const float* sigma, float sigma_data, void* out, int B,
+                            int F, int W, int k, int pw, int Cpad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x_in && x_ref && sigma && out && k >= 1 && 2 * (k + 2) <= Cpad && pw >= 1 && W > pw, "dd_ddec_stem: bad arguments");
+    const long total = (long)B * F * (W + 2 * pw) * Cpad;
+    if (total == 0) return 0;
+    ddec_stem_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(x_in, x_ref, sigma, sigma_data,
+                                                                 static_cast<__nv_bfloat16*>(out), B, F, W, k, pw, Cpad);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_avgpool2_pad(const void* x, void* out, int B, int H, int W, int C, int pw, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && pw >= 1 && W / 2 > pw, "dd_avgpool2_pad: bad arguments");
+    const long total = (long)B * (H / 2) * (W / 2 + 2 * pw) * (C / 8);
+    if (total == 0) return 0;
+    avgpool2_pad_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), B,
+                                                                    H, W, pw, C / 8);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_ddec_head(const void* f, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
+                            int W, int pw, int Cst, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(f && x_in && sigma && out && Cst >= 2, "dd_ddec_head: bad arguments");
+    const long total = (long)B * 2 * H * W;
+    if (total == 0) return 0;
+    ddec_head_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(f), x_in, sigma, sigma_data,
+                                                                 out, B, H, W, pw, Cst);
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -1,0 +1,323 @@
+"""B200-native drop-in for the reference's diffusion-decoder UNet
+`modules.unets.unet_edm2_ddec_mclt_b1.DDec_MCLT_UNet_B1` (/root/reference/src/modules/unets/unet_edm2_ddec_mclt_b1.py:177-326;
+SURVEY.md section 8 row A17) -- the denoiser that turns a mel-spectrogram-derived PSD (`x_ref`) into the MDCT image.
+
+Same constructor / config dataclass / state_dict keys and shapes (strict `load_state_dict` of a reference checkpoint
+works), same `forward(x_in, sigma, format, embeddings, x_ref, perturbed_input=None) -> D_x` (fp32, (B, 2, F, W)),
+`get_embeddings` (None: in_channels_emb = 0), `get_sigma_loss_logvar`, `get_latent_shape`.  Register it with
+    "ddec": {"package": "dualdiffusion_b200.modules.unets.unet_edm2_ddec_mclt_b1", "class": "DDec_MCLT_UNet_B1"}
+
+The forward is a fixed schedule of C-ABI launches on the folded-stereo / halo-column layout of csrc/dae.cu: (1,3,3)
+MPConv3Ds are 2-group tensor-core convolutions, (2,1,1) / (2,3,3) ones dense with block-circulant weights; per-side
+pixel norm and mp_cat run the 2-D kernels on a [.., 2*Wp, C] view of the same memory.  Captured into a CUDA graph per
+input shape in eval mode.  Inference only (eval mode, no_grad); no attention / dropout / label conditioning (the
+shipped edm2_ddec_mclt_b1a configuration); no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence, Tuple, Union
+
+import torch
+
+from ... import _lib as L
+from ... import ops
+from ..daes.dae_edm2_d3 import MPConv3D, _ver
+from ..mp_tools import MPFourier, mp_cat_weights
+from .unet import DualDiffusionUNet, DualDiffusionUNetConfig
+
+Tensor = torch.Tensor
+_PW = 2
+
+
+@dataclass
+class DDec_MCLT_UNet_B1_Config(DualDiffusionUNetConfig):
+    """unet_edm2_ddec_mclt_b1.py:45-73 (field-for-field, same defaults)."""
+    in_channels: int = 1
+    out_channels: int = 1
+    in_channels_emb: int = 0
+    in_num_freqs: int = 256
+    in_psd_freqs: int = 4096
+    model_channels: int = 32
+    logvar_channels: int = 128
+    channel_mult: Sequence[int] = (1, 2, 3, 4)
+    double_midblock: bool = True
+    midblock_attn: bool = False
+    channel_mult_noise: Optional[int] = 4
+    channel_mult_emb: Optional[int] = 4
+    channels_per_head: int = 64
+    num_layers_per_block: int = 3
+    label_balance: float = 0.5
+    concat_balance: float = 0.5
+    res_balance: float = 0.3
+    attn_balance: float = 0.3
+    attn_levels: Sequence[int] = ()
+    mlp_multiplier: int = 1
+    mlp_groups: int = 1
+    emb_linear_groups: int = 1
+    add_constant_channel: bool = True
+
+
+class Block(torch.nn.Module):
+    """Parameter container with the reference Block's names / shapes (:75-125)."""
+
+    def __init__(self, level: int, in_channels: int, out_channels: int, emb_channels: int, num_freqs: int,
+                 flavor: str = "enc", resample_mode: str = "keep", res_balance: float = 0.3, clip_act: float = 256,
+                 mlp_multiplier: int = 1, use_attention: bool = False) -> None:
+        super().__init__()
+        if use_attention:
+            raise NotImplementedError("DDec_MCLT_UNet_B1: attention blocks are not used by the shipped configuration")
+        self.level, self.num_freqs = level, num_freqs
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.flavor, self.resample_mode = flavor, resample_mode
+        self.res_balance, self.clip_act = res_balance, clip_act
+        self.conv_res0 = MPConv3D(out_channels if flavor == "enc" else in_channels, out_channels * mlp_multiplier,
+                                  kernel=(1, 3, 3))
+        self.conv_res1 = MPConv3D(out_channels * mlp_multiplier, out_channels, kernel=(1, 3, 3))
+        self.conv_skip = MPConv3D(in_channels, out_channels, kernel=(2, 1, 1))
+        self.emb_gain = torch.nn.Parameter(torch.zeros([]))
+        self.emb_linear = MPConv3D(emb_channels, out_channels * mlp_multiplier, kernel=(1, 1, 1))
+
+
+class DDec_MCLT_UNet_B1(DualDiffusionUNet):
+
+    supports_channels_last: Union[bool, str] = "3d"
+    supports_compile = False
+
+    def __init__(self, config: DDec_MCLT_UNet_B1_Config) -> None:
+        super().__init__()
+        self.config = config
+        if (config.in_channels != 1 or config.out_channels != 1 or config.in_channels_emb != 0 or config.mlp_groups != 1
+                or config.emb_linear_groups != 1 or not config.add_constant_channel or config.midblock_attn
+                or len(config.attn_levels) or config.dropout != 0):
+            raise NotImplementedError("DDec_MCLT_UNet_B1: only the shipped edm2_ddec_mclt_b1a configuration family is implemented "
+                                      "(mono-per-side in/out, unconditioned, dense MLPs, no attention, no dropout)")
+        kw = dict(mlp_multiplier=config.mlp_multiplier, res_balance=config.res_balance)
+        cblock = [config.model_channels * x for x in config.channel_mult]
+        cnoise = config.model_channels * config.channel_mult_noise if config.channel_mult_noise is not None else max(cblock)
+        cemb = config.model_channels * config.channel_mult_emb if config.channel_mult_emb is not None else max(cblock)
+        cemb *= config.mlp_multiplier
+        self.num_levels = len(config.channel_mult)
+        assert config.in_psd_freqs % config.in_num_freqs == 0
+        self.psd_freqs_per_freq = config.in_psd_freqs // config.in_num_freqs
+        self.emb_fourier = MPFourier(cnoise)
+        self.emb_noise = MPConv3D(cnoise, cemb, kernel=())
+        self.emb_label = None
+        self.emb_label_unconditional = None
+        self.logvar_fourier = MPFourier(config.logvar_channels)
+        self.logvar_linear = MPConv3D(config.logvar_channels, 1, kernel=(), disable_weight_norm=True)
+
+        self.enc = torch.nn.ModuleDict()
+        cout = config.in_channels + self.psd_freqs_per_freq + 1
+        for level, channels in enumerate(cblock):
+            nf = config.in_num_freqs // 2 ** level
+            if level == 0:
+                cin, cout = cout, channels
+                self.enc["conv_in"] = MPConv3D(cin, cout, kernel=(2, 3, 3))
+            else:
+                self.enc[f"block{level}_down"] = Block(level, cout, cout, cemb, nf, flavor="enc", resample_mode="down", **kw)
+            for idx in range(config.num_layers_per_block):
+                cin, cout = cout, channels
+                self.enc[f"block{level}_layer{idx}"] = Block(level, cin, cout, cemb, nf, flavor="enc", **kw)
+        self.dec = torch.nn.ModuleDict()
+        skips = [(b.out_channels if isinstance(b, Block) else b.out_channels) for b in self.enc.values()]
+        for level, channels in reversed(list(enumerate(cblock))):
+            nf = config.in_num_freqs // 2 ** level
+            if level == len(cblock) - 1:
+                self.dec[f"block{level}_in0"] = Block(level, cout, cout, cemb, nf, flavor="dec", **kw)
+                if config.double_midblock:
+                    self.dec[f"block{level}_in1"] = Block(level, cout, cout, cemb, nf, flavor="dec", **kw)
+            else:
+                self.dec[f"block{level}_up"] = Block(level, cout, cout, cemb, nf, flavor="dec", resample_mode="up", **kw)
+            for idx in range(config.num_layers_per_block + 1):
+                cin = cout + skips.pop()
+                cout = channels
+                self.dec[f"block{level}_layer{idx}"] = Block(level, cin, cout, cemb, nf, flavor="dec", **kw)
+        self.out_gain = torch.nn.Parameter(torch.zeros([]))
+        self.conv_out = MPConv3D(cout, config.out_channels, kernel=(2, 3, 3))
+        self.use_cuda_graphs = True
+        self._prep: Dict[str, Tuple[int, Tensor]] = {}
+        self._graphs: Dict[tuple, dict] = {}
+        self._affine: Dict[int, dict] = {}
+
+    # ---- helpers mirrored from the reference (:263-276) ----
+    def get_embeddings(self, emb_in: Tensor, conditioning_mask: Tensor) -> Optional[Tensor]:
+        return None
+
+    def get_sigma_loss_logvar(self, sigma: Optional[Tensor] = None) -> Tensor:
+        dev = torch.device(self.device)
+        s = sigma.detach().to(device=dev, dtype=torch.float32).contiguous().flatten()
+        L.require_cuda(self.logvar_linear.weight)
+        out = ops.sigma_logvar(s, self.logvar_fourier.freqs.detach().float().contiguous(),
+                               self.logvar_fourier.phases.detach().float().contiguous(),
+                               self.logvar_linear.weight.detach().contiguous())
+        return out.view(-1, 1, 1, 1)
+
+    def get_latent_shape(self, latent_shape) -> tuple:
+        m = 2 ** (self.num_levels - 1)
+        return tuple(latent_shape[0:2]) + ((latent_shape[2] // m) * m, (latent_shape[3] // m) * m)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._prep, self._graphs, self._affine = {}, {}, {}
+        return super()._apply(fn, *args, **kwargs)
+
+    # ---- prepared weights (eval mode), refreshed on parameter version change ----
+    def _z2(self, key: str, conv: MPConv3D, gain: Optional[Tensor] = None, i_stride: int = 0, pad_rows: int = 0) -> Tensor:
+        w = conv.weight
+        ver = _ver(w) + (_ver(gain) if gain is not None else 0)
+        hit = self._prep.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        g = None if gain is None else gain.detach().float().reshape(1)
+        out = None if hit is None else hit[1]
+        if out is None and pad_rows:
+            kz, taps = w.shape[2], w.shape[3] * w.shape[4]
+            n_in = i_stride or (2 * w.shape[1] if kz == 2 else w.shape[1])
+            out = torch.zeros((max(pad_rows, 2 * w.shape[0]), taps, n_in), device=w.device, dtype=torch.bfloat16)
+        out = ops.weight_prep_z2(w.detach(), gain=g, i_stride=i_stride, out=out)
+        self._prep[key] = (ver, out)
+        return out
+
+    def _blocks(self):
+        for prefix, blocks in (("enc", self.enc), ("dec", self.dec)):
+            for name, blk in blocks.items():
+                if isinstance(blk, Block):
+                    yield f"{prefix}.{name}", blk
+
+    def _emb_scales(self, emb: Tensor) -> Dict[str, Tensor]:
+        B = emb.shape[0]
+        st = self._affine.get(B)
+        sig = tuple(_ver(b.emb_linear.weight) + _ver(b.emb_gain) for _, b in self._blocks())
+        if st is None or st["sig"] != sig:
+            dev = emb.device
+            entries, outs = [], {}
+            for name, blk in self._blocks():
+                w = blk.emb_linear.weight.detach().float().flatten(1)
+                w2 = torch.cat([w, w], dim=0).contiguous()                  # rows (z, o): both stereo sides share the scale
+                out = torch.empty((B, w2.shape[0]), device=dev, dtype=torch.float32)
+                outs[name] = out
+                entries.append(dict(w=w2, gain=blk.emb_gain.detach().float().reshape(1), out=out, groups=1, bias=1.0,
+                                    normalize=False))
+            descs, max_o = ops.make_affine_descs(entries, dev)
+            st = dict(sig=sig, entries=entries, outs=outs, descs=descs, max_o=max_o)
+            self._affine[B] = st
+        ops.emb_affine(st["descs"], len(st["entries"]), st["max_o"], emb)
+        return st["outs"]
+
+    def _noise_emb(self, sigma: Tensor) -> Tensor:
+        """emb = emb_noise(emb_fourier(ln(sigma)/4)) (:301-305 with in_channels_emb = 0: no label mix, no mp_silu)."""
+        four = ops.mp_fourier(sigma.log() / 4, self.emb_fourier.freqs.detach().float().contiguous(),
+                              self.emb_fourier.phases.detach().float().contiguous())
+        w = self.emb_noise.weight.detach()
+        st = self._affine.get(("noise", sigma.numel()))
+        if st is None or st["ver"] != _ver(w):
+            out = torch.empty((sigma.numel(), w.shape[0]), device=sigma.device, dtype=torch.float32)
+            descs, max_o = ops.make_affine_descs([dict(w=w, gain=None, out=out, groups=1, bias=0.0, normalize=False)],
+                                                 sigma.device)
+            st = dict(ver=_ver(w), out=out, descs=descs, max_o=max_o)
+            self._affine[("noise", sigma.numel())] = st
+        ops.emb_affine(st["descs"], 1, st["max_o"], four)
+        return st["out"]
+
+    def _run(self, x_in: Tensor, net_in: Tensor, sigma: Tensor, x_ref: Tensor) -> Tensor:
+        """The launch schedule of DDec_MCLT_UNet_B1.forward (:278-326) + Block.forward (:127-175)."""
+        cfg = self.config
+        t = cfg.res_balance
+        n = math.sqrt((1 - t) ** 2 + t ** 2)
+        ca, cb = (1 - t) / n, t / n
+        cvec = self._emb_scales(self._noise_emb(sigma))
+
+        def fold_view(tns: Tensor) -> Tensor:          # [B][H][Wp][2C] -> [B][H][2Wp][C]: one "pixel" per stereo side
+            return tns.view(tns.shape[0], tns.shape[1], tns.shape[2] * 2, tns.shape[3] // 2)
+
+        def residual_branch(p: str, blk: Block, s: Tensor, resid: Tensor) -> Tensor:
+            y0 = ops.mpconv(s, self._z2(p + ".conv_res0", blk.conv_res0), 3, 2, epi=L.EPI_SCALE_SILU, scale=cvec[p])
+            ops.reflect_fill_w(y0, _PW)
+            out = ops.mpconv(y0, self._z2(p + ".conv_res1", blk.conv_res1), 3, 2, epi=L.EPI_RESIDUAL, alpha=cb, beta=ca,
+                             clip=blk.clip_act, residual=resid)
+            return ops.reflect_fill_w(out, _PW)
+
+        x = ops.ddec_stem(net_in, x_ref, sigma, cfg.sigma_data, self.psd_freqs_per_freq, _PW, 64)
+        x = ops.mpconv(x, self._z2("enc.conv_in", self.enc["conv_in"], i_stride=64), 3)
+        ops.reflect_fill_w(x, _PW)
+        skips = [x]
+        for name, blk in self.enc.items():
+            if not isinstance(blk, Block):
+                continue
+            p = "enc." + name
+            if blk.resample_mode == "down":
+                x = ops.avgpool2_pad(x, _PW)
+            t0 = ops.mpconv(x, self._z2(p + ".conv_skip", blk.conv_skip), 1)
+            xn, s = ops.pixnorm_silu(fold_view(t0))                     # pixel norm per stereo side (:133)
+            x = residual_branch(p, blk, s.view(t0.shape), xn.view(t0.shape))
+            skips.append(x)
+        for name, blk in self.dec.items():
+            p = "dec." + name
+            if "layer" in name:
+                skip = skips.pop()
+                wa, wb = mp_cat_weights(x.shape[-1] // 2, skip.shape[-1] // 2, cfg.concat_balance)
+                xc, s = ops.cat_silu(fold_view(x), fold_view(skip), wa, wb, False)
+                shape = (x.shape[0], x.shape[1], x.shape[2], x.shape[3] + skip.shape[3])
+                xc, s = xc.view(shape), s.view(shape)
+            elif blk.resample_mode == "up":
+                xc, s = ops.up2_silu_pad(x, _PW)
+            else:
+                xc = x
+                _, s = ops.cat_silu(x, None, 1.0, 0.0, False, need_cat=False)
+            t0 = ops.mpconv(xc, self._z2(p + ".conv_skip", blk.conv_skip), 1)
+            x = residual_branch(p, blk, s, t0)
+        f = ops.mpconv(x, self._z2("conv_out", self.conv_out, gain=self.out_gain, pad_rows=16), 3)
+        return ops.ddec_head(f, x_in, sigma, cfg.sigma_data, _PW)
+
+    def forward(self, x_in: Tensor, sigma: Tensor, format=None, embeddings: Optional[Tensor] = None,
+                x_ref: Optional[Tensor] = None, perturbed_input: Optional[Tensor] = None) -> Tensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("dualdiffusion_b200 DDec_MCLT_UNet_B1: backward is not implemented (inference only)")
+        if self.training:
+            raise NotImplementedError("dualdiffusion_b200 DDec_MCLT_UNet_B1: train-mode forward is not built")
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError("dualdiffusion_b200 DDec_MCLT_UNet_B1 has no CPU path: move the module to a CUDA device (B200)")
+        if x_ref is None:
+            raise ValueError("x_ref (the PSD reference, (B, 2, in_psd_freqs, W)) is required")
+        cfg = self.config
+        B, C, Fq, W = x_in.shape
+        if C != 2 or Fq != cfg.in_num_freqs or tuple(x_ref.shape) != (B, 2, cfg.in_psd_freqs, W):
+            raise ValueError(f"expected x_in (B, 2, {cfg.in_num_freqs}, W) and x_ref (B, 2, {cfg.in_psd_freqs}, W), got "
+                             f"{tuple(x_in.shape)} and {tuple(x_ref.shape)}")
+        x32 = x_in.detach().to(device=dev, dtype=torch.float32).contiguous()
+        n32 = x32 if perturbed_input is None else perturbed_input.detach().to(device=dev, dtype=torch.float32).contiguous()
+        xr = x_ref.detach().to(device=dev, dtype=torch.float32).contiguous()
+        sg = sigma.detach().to(device=dev, dtype=torch.float32).flatten().contiguous()
+        if sg.numel() == 1 and B > 1:
+            sg = sg.expand(B).contiguous()
+        with torch.no_grad():
+            if not self.use_cuda_graphs:
+                return self._run(x32, n32, sg, xr)
+            sig = tuple(_ver(p) for p in self.parameters())
+            key = (tuple(x32.shape), perturbed_input is not None)
+            gs = self._graphs.get(key)
+            if gs is None or gs["sig"] != sig:
+                st = dict(x=x32.clone(), n=n32.clone() if perturbed_input is not None else None, s=sg.clone(), r=xr.clone())
+                n_st = st["n"] if st["n"] is not None else st["x"]
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):              # warm-up outside capture (weight prep, descriptor tables)
+                    self._run(st["x"], n_st, st["s"], st["r"])
+                torch.cuda.current_stream(dev).wait_stream(side)
+                before = ops.launch_count
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self._run(st["x"], n_st, st["s"], st["r"])
+                gs = dict(sig=sig, graph=graph, static=st, out=out, launches=ops.launch_count - before)
+                self._graphs[key] = gs
+            st = gs["static"]
+            st["x"].copy_(x32)
+            if st["n"] is not None:
+                st["n"].copy_(n32)
+            st["s"].copy_(sg)
+            st["r"].copy_(xr)
+            gs["graph"].replay()
+            ops.launch_count += gs["launches"]
+            return gs["out"].clone()

@@ -574,3 +574,30 @@ def conv5x5_out(x: Tensor, w25: Tensor, gain: Optional[Tensor], pw: int) -> Tens
     L.check(L.load().dd_conv5x5_out(L.ptr(x), L.ptr(w25), L.ptr(gain), L.ptr(out), B, H, W, C2 // 2, pw, L.stream_ptr()))
     _count()
     return out
+
+
+def ddec_stem(x_in: Tensor, x_ref: Tensor, sigma: Tensor, sigma_data: float, k: int, pw: int, cpad: int = 64) -> Tensor:
+    B, _, Fq, W = x_in.shape
+    out = torch.empty((B, Fq, W + 2 * pw, cpad), device=x_in.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_ddec_stem(L.ptr(x_in), L.ptr(x_ref), L.ptr(sigma), sigma_data, L.ptr(out), B, Fq, W, k, pw, cpad,
+                                  L.stream_ptr()))
+    _count()
+    return out
+
+
+def avgpool2_pad(x: Tensor, pw: int) -> Tensor:
+    B, H, Wp, Cc = x.shape
+    W = Wp - 2 * pw
+    out = torch.empty((B, H // 2, W // 2 + 2 * pw, Cc), device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_avgpool2_pad(L.ptr(x), L.ptr(out), B, H, W, Cc, pw, L.stream_ptr()))
+    _count()
+    return out
+
+
+def ddec_head(f: Tensor, x_in: Tensor, sigma: Tensor, sigma_data: float, pw: int) -> Tensor:
+    B, H, Wp, Cst = f.shape
+    out = torch.empty_like(x_in)
+    L.check(L.load().dd_ddec_head(L.ptr(f), L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(out), B, H, Wp - 2 * pw, pw, Cst,
+                                  L.stream_ptr()))
+    _count()
+    return out

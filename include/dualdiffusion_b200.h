@@ -344,6 +344,20 @@ DD_API int dd_up2_silu_pad(const void* a, void* xc, void* s, int B, int Ha, int 
 DD_API int dd_conv5x5_out(const void* x, const float* w25, const float* gain_dev, float* out, int B, int H, int W, int C,
                           int pw, void* stream);
 
+/* ==== diffusion-decoder UNet DDec_MCLT_UNet_B1 (modules/unets/unet_edm2_ddec_mclt_b1.py:278-326),
+ * same folded-stereo / halo-column layout as the DAE decoder above ============================================== */
+
+/* Network input (:294-309): per stereo side [c_in(sigma)*x_in, the k PSD bins of the mel row (x_ref view + permute of
+ * :294-295), 1] -> [B][F][W+2pw][Cpad] bf16, channel z*(k+2)+c.  x_in fp32 (B,2,F,W), x_ref fp32 (B,2,F*k,W).      */
+DD_API int dd_ddec_stem(const float* x_in, const float* x_ref, const float* sigma, float sigma_data, void* out, int B, int F,
+                        int W, int k, int pw, int Cpad, void* stream);
+/* resample_3d "down" (mp_tools.py:85-90) on a W-padded tensor: [B][H][W+2pw][C] -> [B][H/2][W/2+2pw][C].          */
+DD_API int dd_avgpool2_pad(const void* x, void* out, int B, int H, int W, int C, int pw, void* stream);
+/* Output head (:323-326): D = c_skip*x_in + c_out*F with F = channel z of the Cst-wide conv_out result
+ * [B][H][W+2pw][Cst] bf16; x_in, out fp32 (B,2,H,W).                                                              */
+DD_API int dd_ddec_head(const void* f, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
+                        int W, int pw, int Cst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,26 @@ def main():
     torch.save(dict(cases=cases, weight_checksum=weight_checksum(dsd), mel_shape=dae.get_mel_spec_shape((3, 8, 32, 688)),
                     latent_shape=dae.get_latent_shape((3, 2, 256, 5504))), os.path.join(OUT, "dae_small.pt"))
 
+    # ---- diffusion-decoder UNet DDec_MCLT_UNet_B1 (unet_edm2_ddec_mclt_b1.py:278-326), reduced config ----
+    from oracle import ddec_oracle as dd
+    from modules.unets.unet_edm2_ddec_mclt_b1 import DDec_MCLT_UNet_B1, DDec_MCLT_UNet_B1_Config
+    sspec = dd.small_ddec_spec()
+    ssd = dd.synth_ddec_state_dict(sspec, seed=0)
+    ddec = DDec_MCLT_UNet_B1(DDec_MCLT_UNet_B1_Config(
+        in_num_freqs=sspec.in_num_freqs, in_psd_freqs=sspec.in_psd_freqs, model_channels=sspec.model_channels,
+        logvar_channels=sspec.logvar_channels, channel_mult=tuple(sspec.channel_mult), double_midblock=sspec.double_midblock,
+        channel_mult_noise=sspec.channel_mult_noise, channel_mult_emb=sspec.channel_mult_emb,
+        num_layers_per_block=sspec.num_layers_per_block, mlp_multiplier=sspec.mlp_multiplier)).eval()
+    ddec.load_state_dict(ssd, strict=True)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 2, sspec.in_num_freqs, 24, generator=g)
+    x_ref = torch.rand(2, 2, sspec.in_psd_freqs, 24, generator=g)
+    pert = x + 0.1 * torch.randn(x.shape, generator=g)
+    sigma = torch.tensor([0.5, 3.0])
+    torch.save(dict(x=x, x_ref=x_ref, sigma=sigma, perturbed=pert, d=ddec(x, sigma, None, None, x_ref),
+                    d_perturbed=ddec(x, sigma, None, None, x_ref, pert), logvar=ddec.get_sigma_loss_logvar(sigma),
+                    weight_checksum=weight_checksum(ssd)), os.path.join(OUT, "ddec_small.pt"))
+
     # ---- sampler: reference diffusion_decode on CPU, reduced config, 3 Heun+CFG steps ----
     spec = uo.small_spec()
     sd = uo.synth_state_dict(spec, seed=0)

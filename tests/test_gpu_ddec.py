@@ -1,0 +1,119 @@
+"""GPU parity tests (-m gpu) of the diffusion-decoder UNet DDec_MCLT_UNet_B1: the input
+assembly (x_ref PSD view/permute -- an index map, bit-exact), the padded-layout glue kernels, and the assembled forward
+against the reference golden (tests/golden/ddec_small.pt; the reference's own body runs in bf16) and the fp32 oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden, rel_err
+from oracle import ddec_oracle as dd, unet_oracle as uo
+from test_gpu_dae import PW, bf16_round, fold, unfold
+
+pytestmark = pytest.mark.gpu
+BF16_OP, BF16_NET = 4e-3, 3e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_ddec_stem_xref_permute_is_bit_exact(dev):
+    """unet_edm2_ddec_mclt_b1.py:294-309: x_ref.view(B, 2, F, k, W).permute(0, 3, 1, 2, 4) joins c_in*x and the constant
+    channel.  Pure data movement (+ one bf16 rounding): compared bit for bit with the reference's own statement."""
+    from dualdiffusion_b200 import ops
+    gen = torch.Generator().manual_seed(1)
+    B, Fq, k, W = 2, 8, 4, 9
+    x = torch.randn(B, 2, Fq, W, generator=gen)
+    xr = torch.rand(B, 2, Fq * k, W, generator=gen)
+    sigma = torch.tensor([0.5, 3.0])
+    got = ops.ddec_stem(x.to(dev), xr.to(dev), sigma.to(dev), 1.0, k, PW, 64).float().cpu()
+    c_in = 1 / (1 + sigma.view(-1, 1, 1, 1, 1) ** 2).sqrt()
+    xr5 = xr.view(B, 2, Fq, k, W).permute(0, 3, 1, 2, 4).to(torch.bfloat16)
+    x5 = (c_in * x.reshape(B, 1, 2, Fq, W)).to(torch.bfloat16)
+    ref5 = torch.cat((x5, xr5, torch.ones_like(x5[:, :1])), dim=1).float()              # (B, k+2, 2, F, W)
+    ref = fold(ref5, "cpu").float()
+    ct = k + 2
+    for z in range(2):
+        assert torch.equal(got[..., z * ct + 1:(z + 1) * ct], ref[..., z * ct + 1:(z + 1) * ct])     # PSD bins + constant: exact
+        assert rel_err(got[..., z * ct], ref[..., z * ct]) < 4e-3       # c_in*x: rsqrt vs 1/sqrt may differ by one bf16 ulp
+    assert got[..., 2 * (k + 2):].abs().max().item() == 0
+
+
+def test_padded_avgpool_and_per_side_pixel_norm(dev):
+    from dualdiffusion_b200 import ops
+    gen = torch.Generator().manual_seed(2)
+    x5 = bf16_round(torch.randn(2, 32, 2, 8, 12, generator=gen) * 2)
+    y = ops.avgpool2_pad(fold(x5, dev), PW)
+    ref = dd.resample_3d(x5, "down")
+    assert rel_err(unfold(y, 32), ref) < BF16_OP
+    yl = y.float().cpu()
+    assert torch.equal(yl[:, :, PW - 1], yl[:, :, PW + 1]) and torch.equal(yl[:, :, -1], yl[:, :, -PW - 3])
+    xf = fold(x5, dev)
+    xn, s = ops.pixnorm_silu(xf.view(xf.shape[0], xf.shape[1], xf.shape[2] * 2, 32))
+    refn = uo.normalize(x5, dim=1)
+    assert rel_err(unfold(xn.view(xf.shape), 32), refn) < BF16_OP
+    assert rel_err(unfold(s.view(xf.shape), 32), uo.mp_silu(refn)) < BF16_OP
+    # (2,1,1) conv_skip: dense 1x1 on the folded layout with the block-circulant weight
+    w = torch.randn(64, 32, 2, 1, 1, generator=gen)
+    fan = 64.0
+    refc = dd.mp_conv3d(x5, bf16_round(w / fan ** 0.5) * fan ** 0.5)
+    got = ops.mpconv(xf, ops.weight_prep_z2(w.to(dev)), 1)
+    assert rel_err(unfold(got, 64), refc) < BF16_OP
+    # folded mp_cat: per-side channel concat through the [.., 2*Wp, C] view
+    b5 = bf16_round(torch.randn(2, 64, 2, 8, 12, generator=gen))
+    wa, wb = uo.mp_cat_weights(32, 64, 0.5)
+    bf = fold(b5, dev)
+    xc, _ = ops.cat_silu(xf.view(2, 8, -1, 32), bf.view(2, 8, -1, 64), wa, wb, False)
+    refcat = torch.cat([wa * x5, wb * b5], dim=1)
+    assert rel_err(unfold(xc.view(2, 8, xf.shape[2], 192), 96), refcat) < BF16_OP
+
+
+def make_ddec(spec, sd, dev):
+    from dualdiffusion_b200.modules.unets.unet_edm2_ddec_mclt_b1 import DDec_MCLT_UNet_B1, DDec_MCLT_UNet_B1_Config
+    cfg = DDec_MCLT_UNet_B1_Config(in_num_freqs=spec.in_num_freqs, in_psd_freqs=spec.in_psd_freqs,
+                                   model_channels=spec.model_channels, logvar_channels=spec.logvar_channels,
+                                   channel_mult=tuple(spec.channel_mult), double_midblock=spec.double_midblock,
+                                   channel_mult_noise=spec.channel_mult_noise, channel_mult_emb=spec.channel_mult_emb,
+                                   num_layers_per_block=spec.num_layers_per_block, mlp_multiplier=spec.mlp_multiplier)
+    net = DDec_MCLT_UNet_B1(cfg)
+    net.load_state_dict(sd, strict=True)
+    return net.requires_grad_(False).train(False).to(dev)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_ddec_forward_vs_golden_reference_and_oracle(dev, graphs):
+    spec = dd.small_ddec_spec()
+    sd = dd.synth_ddec_state_dict(spec, seed=0)
+    g = load_golden("ddec_small.pt")
+    net = make_ddec(spec, sd, dev)
+    net.use_cuda_graphs = graphs
+    c_skip = 1.0 / (1.0 + g["sigma"].view(-1, 1, 1, 1) ** 2)
+    ref32 = dd.ddec_forward(sd, spec, g["x"], g["sigma"], g["x_ref"], torch.float32)
+    for _ in range(2):
+        d = net(g["x"].to(dev), g["sigma"].to(dev), None, None, g["x_ref"].to(dev))
+    assert d.shape == g["d"].shape and d.dtype == torch.float32
+    assert rel_err(d, ref32) < BF16_NET and rel_err(d, g["d"]) < BF16_NET
+    # the network body alone (D - c_skip*x), which c_skip*x would otherwise mask
+    assert rel_err(d.cpu() - c_skip * g["x"], ref32 - c_skip * g["x"]) < 2 * BF16_NET
+    dp = net(g["x"].to(dev), g["sigma"].to(dev), None, None, g["x_ref"].to(dev), g["perturbed"].to(dev))
+    assert rel_err(dp, g["d_perturbed"]) < BF16_NET
+    assert rel_err(net.get_sigma_loss_logvar(g["sigma"].to(dev)), g["logvar"]) < 1e-5
+    assert net.get_embeddings(None, None) is None
+
+
+def test_ddec_default_config_runs_and_matches_oracle_band(dev):
+    """Default 15 M-parameter ddec (256 mel rows, 4096 PSD bins) at a short width; the fp32 CPU oracle of the full
+    network at this size takes ~10 s."""
+    spec = dd.DDecSpec()
+    sd = dd.synth_ddec_state_dict(spec, seed=0)
+    net = make_ddec(spec, sd, dev)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 2, 256, 32, generator=gen)
+    xr = torch.rand(1, 2, 4096, 32, generator=gen)
+    sigma = torch.tensor([1.5])
+    d = net(x.to(dev), sigma.to(dev), None, None, xr.to(dev))
+    ref = dd.ddec_forward(sd, spec, x, sigma, xr, torch.float32)
+    c_skip = 1.0 / (1.0 + sigma.view(-1, 1, 1, 1) ** 2)
+    assert rel_err(d, ref) < BF16_NET
+    assert rel_err(d.cpu() - c_skip * x, ref - c_skip * x) < 2 * BF16_NET

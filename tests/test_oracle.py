@@ -168,3 +168,18 @@ def test_dae_oracle_decode_vs_golden_reference():
         assert mel.shape == c["mel"].shape and rel_err(mel, c["mel"]) < 1e-5, tag
     r = 2 ** (len(spec.channel_mult_dec) - 1)      # get_mel_spec_shape / get_latent_shape (:323-342)
     assert tuple(g["mel_shape"]) == (3, 2, 32 * r, 688 * r) and tuple(g["latent_shape"]) == (3, 8, 256 // r, 5504 // r)
+
+
+def test_ddec_oracle_vs_golden_reference():
+    """Row A17: the DDec_MCLT_UNet_B1 restatement against the reference module.  With the reference's hard-coded bf16
+    body dtype the restatement is bit-exact; the fp32 statement of the same arithmetic differs by the reference's own
+    bf16 rounding."""
+    from oracle import ddec_oracle as dd
+    g = load_golden("ddec_small.pt")
+    spec = dd.small_ddec_spec()
+    sd = dd.synth_ddec_state_dict(spec, seed=0)
+    d = dd.ddec_forward(sd, spec, g["x"], g["sigma"], g["x_ref"], torch.bfloat16)
+    assert torch.equal(d, g["d"])
+    d32 = dd.ddec_forward(sd, spec, g["x"], g["sigma"], g["x_ref"], torch.float32)
+    assert rel_err(d32, g["d"]) < 1e-2
+    assert rel_err(dd.ddec_sigma_loss_logvar(sd, g["sigma"]), g["logvar"]) < 1e-6
