@@ -317,6 +317,54 @@ def bench_dae(device, batch: int = 16, steps: int = 3) -> dict:
                          "frac": flop * sps / 1e12 / pk["tflops"]}}
 
 
+def bench_ddec(device, batch: int = 4, steps: int = 3) -> dict:
+    """Row A17: one DDec_MCLT_UNet_B1 denoiser forward at the 45 s shape, x_in (B,2,256,5504) + PSD x_ref (B,2,4096,5504),
+    default edm2_ddec_mclt_b1a configuration (random-init weights), bf16 tensor-core compute."""
+    from oracle import ddec_oracle as dd            # seeded synthetic weights + block plan only
+    from dualdiffusion_b200.modules.unets.unet_edm2_ddec_mclt_b1 import DDec_MCLT_UNet_B1, DDec_MCLT_UNet_B1_Config
+    from dualdiffusion_b200 import ops
+    spec = dd.DDecSpec()
+    net = DDec_MCLT_UNet_B1(DDec_MCLT_UNet_B1_Config(mlp_multiplier=spec.mlp_multiplier))
+    net.load_state_dict(dd.synth_ddec_state_dict(spec, seed=0), strict=True)
+    net = net.requires_grad_(False).train(False).to(device)
+    H, W = spec.in_num_freqs, LATENT[3] * 8
+    g = torch.Generator(device=device).manual_seed(0)
+    x = torch.randn(batch, 2, H, W, device=device, generator=g)
+    xr = torch.rand(batch, 2, spec.in_psd_freqs, W, device=device, generator=g)
+    sigma = torch.full((batch,), 1.5, device=device)
+    enc, dec, _ = dd.ddec_block_plan(spec)
+    flop, h, w, m = 0.0, H, W, spec.mlp_multiplier
+    for name, kind, cin, cout, resample, _ in enc + dec:
+        if resample == "down":
+            h, w = h // 2, w // 2
+        if resample == "up":
+            h, w = h * 2, w * 2
+        if kind == "conv":
+            flop += 2.0 * h * w * 2 * cout * cin * 18
+        else:
+            c0 = cout if name.startswith("enc") else cin
+            flop += 2.0 * h * w * 2 * (cout * m * c0 * 9 + cout * cout * m * 9 + cout * cin * 2)
+    flop += 2.0 * H * W * 2 * spec.cblock[0] * 18
+    for _ in range(2):
+        d = net(x, sigma, None, None, xr)
+    torch.cuda.synchronize()
+    l0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        d = net(x, sigma, None, None, xr)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    pk = peaks()
+    sps = batch / (ms * 1e-3)
+    return {"metric": "DDec_MCLT_UNet_B1 forward samples/sec (batch 4, x_in 2x256x5504 + PSD 2x4096x5504, bf16)",
+            "value": sps, "unit": "samples/s", "ms_per_batch": ms, "batch": batch, "out_shape": list(d.shape),
+            "gpu_launches_per_batch": (ops.launch_count - l0) // steps, "tflop_per_sample": flop / 1e12,
+            "roofline": {"bound": "tensor", "achieved": flop * sps / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": flop * sps / 1e12 / pk["tflops"]}}
+
+
 def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -428,10 +476,12 @@ def run_ours(args) -> None:
         torch.cuda.empty_cache()
         train = bench_train(device, dist, world)
 
-    dae = None
+    dae = ddec = None
     if rank == 0 and world == 1 and not args.no_dae:
         torch.cuda.empty_cache()
         dae = bench_dae(device)
+        torch.cuda.empty_cache()
+        ddec = bench_ddec(device)
         torch.cuda.empty_cache()
 
     secondary = None
@@ -448,7 +498,7 @@ def run_ours(args) -> None:
                            "library": os.path.relpath(_lib.lib_path(), ROOT)},
                 "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
-                "train_step": train, "dae_decode": dae, "secondary": secondary}
+                "train_step": train, "dae_decode": dae, "ddec_forward": ddec, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
