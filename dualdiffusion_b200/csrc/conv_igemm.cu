@@ -30,10 +30,24 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kMaxThreads = 320;
+constexpr int kMaxThreads = 448;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccBufs = 8;
 constexpr int DD_EPI_HEAD = 3;   // internal: EDM output head (dd_conv_out)
+
+// Division by a launch constant without the ~40-instruction integer divide (ncu: the per-tile tile decode was half of
+// the epilogue warps' instruction stream): q = (n * ceil(2^44 / d)) >> 44, exact for n * d < 2^44 (tile counts < 2^20).
+struct FastDiv {
+    unsigned long long m;
+    int d;
+};
+__host__ inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = d;
+    f.m = ((1ull << 44) + (unsigned long long)d - 1ull) / (unsigned long long)d;
+    return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return (int)(((unsigned long long)(unsigned)n * f.m) >> 44); }
 
 struct ConvParams {
     int B, H, W, Cin, Cout;
@@ -41,6 +55,7 @@ struct ConvParams {
     int cin_g, cout_g;
     int wt, ht, bt;                 // pixel box of one M tile (wt*ht*bt <= 128)
     int tiles_w, tiles_h, tiles_b, m_tiles;
+    FastDiv fd_m_tiles, fd_npg, fd_tw, fd_th;       // divisions of the per-tile index decode
     int n_tile, n_tiles_per_group;
     int kchunks;                    // cin_g / KC
     int k_iters;                    // taps * kchunks
@@ -82,13 +97,15 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
     TileCoord t;
-    const int m_idx = tile % p.m_tiles;
-    const int rest = tile / p.m_tiles;
-    t.n_idx = rest % p.n_tiles_per_group;
-    t.g = rest / p.n_tiles_per_group;
-    t.w0 = (m_idx % p.tiles_w) * p.wt;
-    t.h0 = ((m_idx / p.tiles_w) % p.tiles_h) * p.ht;
-    t.b0 = (m_idx / (p.tiles_w * p.tiles_h)) * p.bt;
+    const int rest = fdiv(tile, p.fd_m_tiles);
+    const int m_idx = tile - rest * p.m_tiles;
+    t.g = fdiv(rest, p.fd_npg);
+    t.n_idx = rest - t.g * p.n_tiles_per_group;
+    const int r1 = fdiv(m_idx, p.fd_tw);                 // (b, h) tile index
+    t.w0 = (m_idx - r1 * p.tiles_w) * p.wt;
+    const int r2 = fdiv(r1, p.fd_th);                    // b tile index
+    t.h0 = (r1 - r2 * p.tiles_h) * p.ht;
+    t.b0 = r2 * p.bt;
     return t;
 }
 
@@ -123,7 +140,7 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH],
 template <int EW>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
                                               int ch0) {
-    constexpr int kChunk = EW == 8 ? 16 : 32;   // columns per tcgen05.ld
+    constexpr int kChunk = EW >= 8 ? 16 : 32;   // columns per tcgen05.ld
     const size_t pix = ((size_t)b * p.H + h) * p.W + w;
     uint32_t rn[kChunk];
     // software pipeline: the TMEM load of chunk i+1 is in flight while chunk i is converted and stored
@@ -185,6 +202,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                         v[4 * i + 3] = mp_silu_fast(v[4 * i + 3] * s.w);
                     }
                 } else if (p.epi == DD_EPI_RESIDUAL) {
+                    // (requesting these rows two chunks ahead measured no gain: the fused residual epilogue is bound by
+                    // the scattered 32-byte sector traffic itself, not by its latency -- tools/exp_epi.py)
                     const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.Cout + ch);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -338,9 +357,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t acc_phase = (local / (uint32_t)p.nbuf) & 1;
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)(p.n_tile * p.nacc);
-                const uint32_t nacc_mask = (uint32_t)p.nacc - 1u;
-                uint32_t q = 0;                                  // running k-step index -> accumulator q % nacc
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
                 for (int it0 = 0; it0 < p.k_iters; it0 += p.sub) {
                     const int cnt = min(p.sub, p.k_iters - it0);
                     ptx::mbar_wait(&full_bar[stage], phase);
@@ -350,11 +367,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int j = 0; j < cnt; ++j) {
                             const uint64_t a_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes, kRowBytes);
                             const uint64_t b_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes + kABufBytes, kRowBytes);
+                            // only the first UMMA of a tile overwrites the accumulator; +32 B per 16-channel step = +2 units
+                            ptx::umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, (it0 + j) > 0 ? 1u : 0u);
 #pragma unroll
-                            for (int ks = 0; ks < KC / 16; ++ks, ++q) { // +32 B per 16-channel step = +2 in 16 B units
-                                ptx::umma_bf16_ss(d_tmem + (q & nacc_mask) * (uint32_t)p.n_tile, a_desc + 2 * ks,
-                                                  b_desc + 2 * ks, idesc, q > nacc_mask ? 1u : 0u);
-                            }
+                            for (int ks = 1; ks < KC / 16; ++ks)
+                                ptx::umma_bf16_ss_acc(d_tmem, a_desc + 2 * ks, b_desc + 2 * ks, idesc);
                         }
                         ptx::umma_commit(&empty_bar[stage]);    // frees the smem stage once the MMAs retire
                     }
@@ -425,34 +442,47 @@ struct HaloTile {
 
 __device__ __forceinline__ HaloTile decode_halo_tile(const ConvParams& p, int tile) {
     HaloTile t;
-    t.panel = tile / p.m_tiles;
+    t.panel = fdiv(tile, p.fd_m_tiles);
     const int m = tile - t.panel * p.m_tiles;
-    t.g = t.panel / p.n_tiles_per_group;
+    t.g = fdiv(t.panel, p.fd_npg);
     t.n_idx = t.panel - t.g * p.n_tiles_per_group;
-    t.w0 = (m % p.tiles_w) * kHaloW;
-    t.h0 = ((m / p.tiles_w) % p.tiles_h) * p.ht;
-    t.b = (m / (p.tiles_w * p.tiles_h)) * p.bt;
+    const int r1 = fdiv(m, p.fd_tw);
+    t.w0 = (m - r1 * p.tiles_w) * kHaloW;
+    const int r2 = fdiv(r1, p.fd_th);
+    t.h0 = (r1 - r2 * p.tiles_h) * p.ht;
+    t.b = r2 * p.bt;
     return t;
 }
 
 // Issue the 9 taps x NKS 16-channel steps of one 64-channel chunk.  Descriptor arithmetic is in 16 B units:
-// a tap is a (dy*pitch + dx)-row shift of the halo tile (8 units per 128 B row), a k-step is +2 units.
-template <int NKS>
+// a tap is a (dy*RP + dx)-row shift of the halo tile (8 units per 128 B row), a k-step is +2 units.  The issuing
+// warp's instruction stream is the limiter for narrow tiles (ncu: ~10 uniform-datapath instructions per UTCHMMA made a
+// 36-UMMA chunk cost ~3500 cycles against ~1500 of tensor-pipe time), so everything here is an immediate: the row
+// pitch RP is a template parameter, the accumulate flag is constant except for the very first UMMA of a tile, and each
+// descriptor is one 64-bit add away from the chunk's base.
+template <int NKS, int RP>
 __device__ __forceinline__ void halo_issue_taps(uint64_t a_desc0, uint64_t b_desc0, uint32_t b_block16, uint32_t d_tmem,
-                                                uint32_t idesc, uint32_t q0, uint32_t nacc_mask, uint32_t n_tile,
-                                                int row_pitch, int dbg_taps = 9) {
+                                                uint32_t idesc, uint32_t acc_first) {
+    uint64_t b_tap = b_desc0;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-        if (tap >= dbg_taps) break;
-        const uint64_t a_tap = a_desc0 + (uint64_t)(((tap / 3) * row_pitch + (tap % 3)) * 8);
-        const uint64_t b_tap = b_desc0 + (uint64_t)tap * b_block16;
+        const uint64_t a_tap = a_desc0 + (uint64_t)(((tap / 3) * RP + (tap % 3)) * 8);
 #pragma unroll
         for (int ks = 0; ks < NKS; ++ks) {
-            const uint32_t q = q0 + tap * NKS + ks;          // running k-step index -> accumulator q % nacc
-            ptx::umma_bf16_ss(d_tmem + (q & nacc_mask) * n_tile, a_tap + 2 * ks, b_tap + 2 * ks, idesc,
-                              q > nacc_mask ? 1u : 0u);
+            if (tap == 0 && ks == 0) ptx::umma_bf16_ss(d_tmem, a_tap, b_tap, idesc, acc_first);
+            else ptx::umma_bf16_ss_acc(d_tmem, a_tap + 2 * ks, b_tap + 2 * ks, idesc);
         }
+        b_tap += b_block16;
     }
+}
+
+template <int RP>
+__device__ __forceinline__ void halo_issue_chunk(int nks, uint64_t a_desc0, uint64_t b_desc0, uint32_t b_block16,
+                                                 uint32_t d_tmem, uint32_t idesc, uint32_t acc_first) {
+    if (nks == 4) halo_issue_taps<4, RP>(a_desc0, b_desc0, b_block16, d_tmem, idesc, acc_first);
+    else if (nks == 2) halo_issue_taps<2, RP>(a_desc0, b_desc0, b_block16, d_tmem, idesc, acc_first);
+    else if (nks == 1) halo_issue_taps<1, RP>(a_desc0, b_desc0, b_block16, d_tmem, idesc, acc_first);
+    else halo_issue_taps<3, RP>(a_desc0, b_desc0, b_block16, d_tmem, idesc, acc_first);
 }
 
 template <int EW>
@@ -537,11 +567,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t idesc = ptx::make_idesc_bf16(kTileM, p.n_tile);
             const uint32_t b_base = ptx::smem_u32(b_smem), a_base = ptx::smem_u32(a_smem);
             const uint32_t b_block16 = p.b_block_bytes >> 4;
-            const int row_pitch = kHaloPitch * p.bt;     // smem rows between consecutive image rows of one item
             uint32_t stage = 0, phase = 0, b_par = 0, local = 0;
             int cur_panel = -1;
             for (int tile = t_begin; tile < t_end; ++tile, ++local) {
-                const int panel = tile / p.m_tiles;
+                const int panel = fdiv(tile, p.fd_m_tiles);
                 if (panel != cur_panel) {
                     ptx::mbar_wait(&b_full, b_par);
                     b_par ^= 1;
@@ -551,9 +580,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t acc_phase = (local / (uint32_t)p.nbuf) & 1;
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)(p.n_tile * p.nacc);
-                const uint32_t nacc_mask = (uint32_t)p.nacc - 1u;
-                uint32_t q0 = 0;
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&a_full[stage], phase);
                     ptx::tcgen05_fence_after();
@@ -561,18 +588,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + stage * p.halo_stride, kHaloPitch * 128);
                         const uint64_t b_desc0 = ptx::make_kmajor_desc_sw128(b_base + (uint32_t)(kc * 9) * p.b_block_bytes, 1024);
                         const int nks = (kc == p.kchunks - 1) ? p.ks_last : 4;
-                        const uint32_t nt = (uint32_t)p.n_tile;
-                        if (nks == 4) halo_issue_taps<4>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
-                        else if (nks == 2) halo_issue_taps<2>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
-                        else if (nks == 1) halo_issue_taps<1>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
-                        else halo_issue_taps<3>(a_desc0, b_desc0, b_block16, d_tmem, idesc, q0, nacc_mask, nt, row_pitch, p.dbg_taps);
+                        const uint32_t acc_first = kc > 0 ? 1u : 0u;
+                        if (p.bt == 1) halo_issue_chunk<kHaloPitch>(nks, a_desc0, b_desc0, b_block16, d_tmem, idesc, acc_first);
+                        else halo_issue_chunk<2 * kHaloPitch>(nks, a_desc0, b_desc0, b_block16, d_tmem, idesc, acc_first);
                         ptx::umma_commit(&a_empty[stage]);
                     }
                     __syncwarp();
-                    q0 += 9u * (uint32_t)((kc == p.kchunks - 1) ? p.ks_last : 4);
                     if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
                 }
-                const bool panel_ends = (tile + 1 == t_end) || ((tile + 1) / p.m_tiles != panel);
+                const bool panel_ends = (tile + 1 == t_end) || (fdiv(tile + 1, p.fd_m_tiles) != panel);
                 if (ptx::elect_one()) {
                     ptx::umma_commit(&tmem_full_bar[acc]);
                     if (panel_ends) ptx::umma_commit(&b_empty);
@@ -719,6 +743,8 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     }
     p.n_tiles_per_group = cout_g / p.n_tile;
     p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
+    p.fd_m_tiles = make_fastdiv(p.m_tiles); p.fd_npg = make_fastdiv(p.n_tiles_per_group);
+    p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
     const uint32_t row_bytes = KC * 2;
     p.a_bytes = (uint32_t)(p.wt * p.ht * p.bt) * row_bytes;
     p.b_bytes = (uint32_t)p.n_tile * row_bytes;
@@ -726,7 +752,7 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.sub = (pair_bytes <= 24u * 1024u && p.k_iters >= 2) ? 2 : 1;
     const uint32_t stage_bytes = pair_bytes * p.sub;
     p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u) / stage_bytes)));
-    p.nacc = choose_nacc(p.n_tile, p.k_iters * (KC / 16));
+    p.nacc = 1;      // (splitting the accumulation chain over several TMEM accumulators measured no gain)
     p.nbuf = 2;
     while (p.nbuf < kMaxAccBufs && 2 * p.nbuf * p.n_tile * p.nacc <= 512) p.nbuf *= 2;
     uint32_t cols = 32;
@@ -764,7 +790,8 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
                 B, H, W, Cin, Cout, p.kw, groups, p.wt, p.ht, p.bt, p.m_tiles, p.n_tile, p.num_tiles, p.k_iters, KC, p.sub,
                 p.stages);
     int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
-    if (const char* f = getenv("DD_FORCE_EPI_WARPS")) ew = atoi(f) == 8 ? 8 : 4;   // tuning experiments only
+    if (ew == 8 && p.nbuf >= 4) ew = 12;      // fused epilogues are the limiter (tools/exp_epi.py): a third warp group
+    if (const char* f = getenv("DD_FORCE_EPI_WARPS")) { const int v = atoi(f); ew = v == 12 ? 12 : (v == 8 ? 8 : 4); }   // tuning
 #define DD_LAUNCH_IGEMM(KC_, EW_)                                                                                  \
     do {                                                                                                           \
         static bool attr_done = false;                                                                             \
@@ -775,8 +802,8 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
         }                                                                                                          \
         DD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<KC_, EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p)); \
     } while (0)
-    if (KC == 64) { if (ew == 8) DD_LAUNCH_IGEMM(64, 8); else DD_LAUNCH_IGEMM(64, 4); }
-    else          { if (ew == 8) DD_LAUNCH_IGEMM(32, 8); else DD_LAUNCH_IGEMM(32, 4); }
+    if (KC == 64) { if (ew == 12) DD_LAUNCH_IGEMM(64, 12); else if (ew == 8) DD_LAUNCH_IGEMM(64, 8); else DD_LAUNCH_IGEMM(64, 4); }
+    else          { if (ew == 12) DD_LAUNCH_IGEMM(32, 12); else if (ew == 8) DD_LAUNCH_IGEMM(32, 8); else DD_LAUNCH_IGEMM(32, 4); }
 #undef DD_LAUNCH_IGEMM
     DD_CHECK_LAUNCH();
     return 0;
@@ -813,11 +840,13 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     p.n_tile = n_tile;
     p.n_tiles_per_group = cout_g / n_tile;
     p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
+    p.fd_m_tiles = make_fastdiv(p.m_tiles); p.fd_npg = make_fastdiv(p.n_tiles_per_group);
+    p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
     p.b_block_bytes = (uint32_t)n_tile * 128u;
     const uint32_t b_total = (uint32_t)p.kchunks * 9u * p.b_block_bytes;
     p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((budget - b_total) / p.halo_stride)));
-    p.nacc = choose_nacc(p.n_tile, 9 * (4 * (p.kchunks - 1) + p.ks_last));
-    p.dbg_taps = getenv("DD_DBG_TAPS") ? atoi(getenv("DD_DBG_TAPS")) : 9;
+    p.nacc = 1;
+    p.dbg_taps = 9;
     p.dbg_nostore = getenv("DD_DBG_NOSTORE") != nullptr;
     p.nbuf = 2;
     while (p.nbuf < kMaxAccBufs && 2 * p.nbuf * p.n_tile * p.nacc <= 512) p.nbuf *= 2;
@@ -851,7 +880,9 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     }
     const size_t smem_bytes = (size_t)b_total + (size_t)p.a_stages * p.halo_stride + 1024;
     const int grid = std::min(p.num_tiles, dd_num_sms());
-    const int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
+    int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
+    if (ew == 8 && p.nbuf >= 4) ew = 12;      // fused epilogues are the limiter (tools/exp_epi.py): a third warp group
+    if (const char* f = getenv("DD_FORCE_EPI_WARPS")) { const int v = atoi(f); ew = v == 12 ? 12 : (v == 8 ? 8 : 4); }   // tuning
 #define DD_LAUNCH_HALO(EW_)                                                                                        \
     do {                                                                                                           \
         static bool attr_done = false;                                                                             \
@@ -862,7 +893,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
         }                                                                                                          \
         DD_CHECK_CUDA(launch_pdl(conv3x3_halo_kernel<EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p));   \
     } while (0)
-    if (ew == 8) DD_LAUNCH_HALO(8); else DD_LAUNCH_HALO(4);
+    if (ew == 12) DD_LAUNCH_HALO(12); else if (ew == 8) DD_LAUNCH_HALO(8); else DD_LAUNCH_HALO(4);
 #undef DD_LAUNCH_HALO
     DD_CHECK_LAUNCH();
     return 0;
