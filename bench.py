@@ -266,7 +266,7 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> di
     return {"metric": "UNet train step fwd+bwd samples/sec (device batch 4 x 4x32x688, bf16 compute, fp32 grads)",
             "value": sps, "unit": "samples/s", "ms_per_step": ms / steps, "n_gpus": world, "global_batch": world * B,
             "allreduce_bytes_per_step": net.grad_sync.bytes_reduced // max(1, steps + warmup),
-            "gpu_launches_per_step": (ops.launch_count - l0) // steps, "loss": float(loss), "grad_norm": gn,
+            "gpu_launches_per_step": (ops.launch_count - l0) // steps, "loss": float(loss.detach()), "grad_norm": gn,
             "roofline": {"bound": "tensor", "achieved": flop * sps / world / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": flop * sps / world / 1e12 / pk["tflops"]}}
 
@@ -375,6 +375,7 @@ def run_ours(args) -> None:
     device = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not precede the JSON line on stdout
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
