@@ -462,244 +462,314 @@ attn_in_bwd_kernel(const uint4* __restrict__ g3, float ca, const uint4* __restri
 
 // ------------------------------------------------------------------------------------------
 // attention backward (unet_edm2_b4.py:137-148): q,k,v cosine-normalised over the 64 head channels, P = softmax(q k^T/8),
-// a = P v.  Two threads per token row, each owning 32 of the 64 head channels.
-//   kernel A (per query):  L_i = logsumexp_j s_ij,  D_i = <da_i, a_i>,  dq
-//   kernel B (per key)  :  dk, dv   (recomputes s_ij from the staged normalised q rows and L_i)
+// a = P v.  FlashAttention-2 style on the tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate), two kernels:
+//   kernel Q  (per 64-query tile; K^, V^ of the head resident in shared memory):
+//       pass 1: L_i = logsumexp_j s_ij;  D_i = <da_i, a_i>
+//       pass 2: P = exp(s - L), dP = dA V^^T, dS = P o (dP - D)/8, dQ^ += dS K^        -> dq (norm backward), stats (L, D)
+//   kernel KV (per 64-key tile; Q^, dA of the head resident):
+//       S^T = K^ Q^^T, P^T = exp(S^T - L), dP^T = V^ dA^T, dS^T = P^T o (dP^T - D)/8,
+//       dV^ += P^T dA, dK^ += dS^T Q^                                                  -> dk, dv (norm backward)
+// P and dS are rounded to bf16 before their second MMA, q^/k^/v^/dA are bf16 in shared memory (as in the forward).
 // ------------------------------------------------------------------------------------------
-constexpr int kAD = 64, kAHalf = 32;
-constexpr int kARows = 64;         // token rows per CTA (128 threads)
-constexpr int kATile = 32;         // staged rows of the other operand per step
+constexpr int kAD = 64;
+constexpr int kBT = 64;                 // token rows per CTA (4 warps x 16)
+constexpr int kBwdThreads = 128;
+constexpr int kRS = kAD + 8;            // bf16 elements per shared-memory row (conflict-free fragment loads)
+constexpr float kSl2 = 0.125f * 1.44269504089f;   // 1/sqrt(64) * log2(e)
 
-// stage `kATile` rows [r0, r0+kATile) of a head (optionally cosine-normalised) as fp32 into smem[kATile][64]
-__device__ __forceinline__ void stage_rows_f32(const __nv_bfloat16* __restrict__ base, long tok_stride, int r0, int N,
-                                               bool normalize, float* __restrict__ dst) {
-    // 128 threads: 4 threads per row (16 channels each)
-    const int r = threadIdx.x >> 2, part = threadIdx.x & 3;
-    float f[16];
-    float ss = 0.f;
-    const bool ok = r0 + r < N;
-    if (ok) {
-        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)(r0 + r) * tok_stride + part * 16);
-        float a[8], b[8];
-        unpack8(__ldg(src), a);
-        unpack8(__ldg(src + 1), b);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { f[j] = a[j]; f[8 + j] = b[j]; ss += a[j] * a[j] + b[j] * b[j]; }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = 0.f;
-    }
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-    const float inv = normalize ? 1.f / (kNormEps + sqrtf(ss) * 0.125f) : 1.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) dst[r * kAD + part * 16 + j] = f[j] * inv;
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
-// load this thread's 32-channel half of row `row` (zeros if out of range); returns the sum of squares of the half
-__device__ __forceinline__ float load_half(const __nv_bfloat16* __restrict__ base, long tok_stride, int row, int N, int half,
-                                           float (&f)[kAHalf]) {
-    float ss = 0.f;
-    if (row < N) {
-        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)row * tok_stride + half * kAHalf);
+// Stage rows [first, first + n_rows) of one head (64 channels, token stride `tok_stride`) into dst[n_rows][kRS] as bf16,
+// optionally cosine-normalised; rows >= limit are zero.  128 threads: 8 lanes per token, 16 tokens per pass.
+__device__ __forceinline__ void stage_rows_bwd(const __nv_bfloat16* __restrict__ head_base, size_t tok_stride, int first,
+                                               int n_rows, int limit, __nv_bfloat16* __restrict__ dst, bool normalize) {
+    const int sub = threadIdx.x & 7, tok = threadIdx.x >> 3;
+    constexpr int kBatch = 4;
+    for (int r0 = 0; r0 < n_rows; r0 += 16 * kBatch) {
+        uint4 q[kBatch];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float a[8];
-            unpack8(__ldg(src + q), a);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { f[q * 8 + j] = a[j]; ss += a[j] * a[j]; }
+        for (int u = 0; u < kBatch; ++u) {
+            const int r = r0 + u * 16 + tok;
+            q[u] = make_uint4(0, 0, 0, 0);
+            if (r < n_rows && first + r < limit)
+                q[u] = __ldg(reinterpret_cast<const uint4*>(head_base + (size_t)(first + r) * tok_stride + sub * 8));
         }
-    } else {
 #pragma unroll
-        for (int j = 0; j < kAHalf; ++j) f[j] = 0.f;
+        for (int u = 0; u < kBatch; ++u) {
+            const int r = r0 + u * 16 + tok;
+            if (r0 + u * 16 >= n_rows) break;                 // warp-uniform
+            float f[8];
+            unpack8(q[u], f);
+            float inv = 1.f;
+            if (normalize) {
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+                inv = 1.f / (kNormEps + sqrtf(ss) * 0.125f);
+            }
+            if (r < n_rows) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] *= inv;
+                *reinterpret_cast<uint4*>(dst + (size_t)r * kRS + sub * 8) = pack8(f);
+            }
+        }
     }
-    return ss;
 }
 
-__device__ __forceinline__ void store_half(__nv_bfloat16* __restrict__ base, long tok_stride, int row, int half,
-                                           const float (&f)[kAHalf]) {
-    uint4* dst = reinterpret_cast<uint4*>(base + (size_t)row * tok_stride + half * kAHalf);
+// A-operand fragments (16 rows x 64 channels = 4 k-steps) of rows [row0, row0+16) of a [.][kRS] tile
+__device__ __forceinline__ void load_a_frags(const __nv_bfloat16* tile, int row0, int g, int t, uint32_t (&a)[4][4]) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = f[q * 8 + j];
-        dst[q] = pack8(a);
+    for (int kk = 0; kk < 4; ++kk) {
+        const __nv_bfloat16* p0 = tile + (size_t)(row0 + g) * kRS + kk * 16 + 2 * t;
+        const __nv_bfloat16* p1 = p0 + 8 * kRS;
+        a[kk][0] = *reinterpret_cast<const uint32_t*>(p0);
+        a[kk][1] = *reinterpret_cast<const uint32_t*>(p1);
+        a[kk][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
+        a[kk][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
     }
 }
 
-// backward of x_hat = x / (eps + ||x||/8): dx = dxh/n - x * <dxh, x> / (n^2 * ||x|| * 8); `dot` and `ss` are full-row sums
-__device__ __forceinline__ void norm_bwd_half(const float (&x)[kAHalf], float (&dxh)[kAHalf], float ss, float dot) {
-    const float nrm = sqrtf(ss);
-    const float n = kNormEps + nrm * 0.125f;
-    const float a = 1.f / n, b = nrm > 0.f ? dot * 0.125f / (n * n * nrm) : 0.f;
+// acc[16 x 64] = A[16 x 64ch] * M[rows r0..r0+63][64ch]^T   (M row-major, channels contiguous: the "n = row, k = channel" form)
+__device__ __forceinline__ void mma_a_rowsT(float (&acc)[8][4], const uint32_t (&a)[4][4], const __nv_bfloat16* m, int r0,
+                                            int g, int t) {
 #pragma unroll
-    for (int j = 0; j < kAHalf; ++j) dxh[j] = dxh[j] * a - x[j] * b;
+    for (int n = 0; n < 8; ++n) {
+        acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        const __nv_bfloat16* bp = m + (size_t)(r0 + n * 8 + g) * kRS + 2 * t;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+            mma16816(acc[n], a[kk], *reinterpret_cast<const uint32_t*>(bp + kk * 16),
+                     *reinterpret_cast<const uint32_t*>(bp + kk * 16 + 8));
+    }
 }
 
-__global__ void __launch_bounds__(128)
+// out[16 x 64ch] += F[16 x 64 rows] * M[rows r0..r0+63][64ch]   (F given as 4 k-step A fragments; M^T fragments via ldmatrix.trans)
+__device__ __forceinline__ void mma_frag_rows(float (&out)[8][4], const uint32_t (&f)[4][4], const __nv_bfloat16* m, int r0,
+                                              int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        const __nv_bfloat16* row = m + (size_t)(r0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kRS + (lane >> 4) * 8;
+#pragma unroll
+        for (int n = 0; n < 8; n += 2) {
+            uint32_t vb[4];
+            ldsm_x4_trans(vb, row + n * 8);
+            mma16816(out[n], f[kk], vb[0], vb[1]);
+            mma16816(out[n + 1], f[kk], vb[2], vb[3]);
+        }
+    }
+}
+
+// Backward of x^ = x / (eps + ||x||/8) for the two rows (g, g+8) a thread co-owns: x and dx^ in the accumulator layout
+// (cols n*8 + 2t, +1), writes dx (bf16) to dst rows.  Row sums are reduced over the 4 lanes of a quad.
+__device__ __forceinline__ void norm_bwd_store(const __nv_bfloat16* __restrict__ x_base, __nv_bfloat16* __restrict__ dst_base,
+                                               size_t tok_stride_x, size_t tok_stride_dst, int row_a, int N, int t,
+                                               const float (&dxh)[8][4]) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = row_a + r * 8;
+        const bool ok = row < N;
+        float x[16];
+        float ss = 0.f, dot = 0.f;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            float2 v = make_float2(0.f, 0.f);
+            if (ok) v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x_base + (size_t)row * tok_stride_x + n * 8 + 2 * t));
+            x[2 * n] = v.x; x[2 * n + 1] = v.y;
+            ss += v.x * v.x + v.y * v.y;
+            dot += v.x * dxh[n][2 * r] + v.y * dxh[n][2 * r + 1];
+        }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1); dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        const float nrm = sqrtf(ss);
+        const float nn = kNormEps + nrm * 0.125f;
+        const float a = 1.f / nn, b = nrm > 0.f ? dot * 0.125f / (nn * nn * nrm) : 0.f;
+        if (ok) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                *reinterpret_cast<uint32_t*>(dst_base + (size_t)row * tok_stride_dst + n * 8 + 2 * t) =
+                    pack_bf16x2(dxh[n][2 * r] * a - x[2 * n] * b, dxh[n][2 * r + 1] * a - x[2 * n + 1] * b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
 attention_bwd_q_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                        const __nv_bfloat16* __restrict__ a_raw, const __nv_bfloat16* __restrict__ da,
-                       __nv_bfloat16* __restrict__ dqk, float* __restrict__ stats, int N, int heads) {
-    __shared__ __align__(16) float Ks[kATile * kAD];
-    __shared__ __align__(16) float Vs[kATile * kAD];
+                       __nv_bfloat16* __restrict__ dqk, float* __restrict__ stats, int N, int heads, int npad) {
+    extern __shared__ __align__(16) uint8_t smem_bwd[];
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_bwd);        // [npad][kRS]  k^
+    __nv_bfloat16* Vs = Ks + (size_t)npad * kRS;                           // [npad][kRS]  v^
+    __nv_bfloat16* Qs = Vs + (size_t)npad * kRS;                           // [kBT][kRS]   q^ tile
+    __nv_bfloat16* Gs = Qs + (size_t)kBT * kRS;                            // [kBT][kRS]   dA tile
     const int C = heads * kAD;
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int row = blockIdx.x * kARows + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * kBT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const __nv_bfloat16* q_base = qk + (size_t)b * N * 2 * C + head * kAD;
-    const __nv_bfloat16* k_base = q_base + C;
-    const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kAD;
     const __nv_bfloat16* a_base = a_raw + (size_t)b * N * C + head * kAD;
-    const __nv_bfloat16* da_base = da + (size_t)b * N * C + head * kAD;
+    const __nv_bfloat16* g_base = da + (size_t)b * N * C + head * kAD;
+    stage_rows_bwd(q_base + C, 2 * (size_t)C, 0, npad, N, Ks, true);
+    stage_rows_bwd(v + (size_t)b * N * C + head * kAD, (size_t)C, 0, npad, N, Vs, true);
+    stage_rows_bwd(q_base, 2 * (size_t)C, q0, kBT, N, Qs, true);
+    stage_rows_bwd(g_base, (size_t)C, q0, kBT, N, Gs, false);
+    __syncthreads();
 
-    float q[kAHalf], qn[kAHalf], go[kAHalf], dq[kAHalf];
-    float ssq = load_half(q_base, 2 * C, row, N, half, q);
-    ssq += __shfl_xor_sync(0xffffffffu, ssq, 1);
-    const float invq = 1.f / (kNormEps + sqrtf(ssq) * 0.125f);
-    float D = 0.f;
-    {
-        float ao[kAHalf];
-        load_half(a_base, C, row, N, half, ao);
-        load_half(da_base, C, row, N, half, go);
+    const int row0 = warp * 16, row_a = q0 + row0 + g;
+    uint32_t qa[4][4], ga[4][4];
+    load_a_frags(Qs, row0, g, t, qa);
+    load_a_frags(Gs, row0, g, t, ga);
+    // D_i = <da_i, a_i>
+    float D[2] = {0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < kAHalf; ++j) { qn[j] = q[j] * invq; dq[j] = 0.f; D += ao[j] * go[j]; }
-        D += __shfl_xor_sync(0xffffffffu, D, 1);
-    }
-    // pass 1: logsumexp of the scores
-    float m = -INFINITY, l = 0.f;
-    for (int k0 = 0; k0 < N; k0 += kATile) {
-        __syncthreads();
-        stage_rows_f32(k_base, 2 * C, k0, N, true, Ks);
-        __syncthreads();
-        const int kn = min(kATile, N - k0);
-        for (int jj = 0; jj < kn; ++jj) {
-            const float4* kr = reinterpret_cast<const float4*>(Ks + jj * kAD + half * kAHalf);
-            float s = 0.f;
+    for (int r = 0; r < 2; ++r) {
+        const int row = row_a + r * 8;
+        if (row < N) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 kk = kr[c];
-                s += qn[4 * c] * kk.x + qn[4 * c + 1] * kk.y + qn[4 * c + 2] * kk.z + qn[4 * c + 3] * kk.w;
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s *= 0.125f;
-            const float mn = fmaxf(m, s);
-            l = l * __expf(m - mn) + __expf(s - mn);
-            m = mn;
-        }
-    }
-    const float L = m + __logf(l);
-    // pass 2: dq
-    for (int k0 = 0; k0 < N; k0 += kATile) {
-        __syncthreads();
-        stage_rows_f32(k_base, 2 * C, k0, N, true, Ks);
-        stage_rows_f32(v_base, C, k0, N, true, Vs);
-        __syncthreads();
-        const int kn = min(kATile, N - k0);
-        for (int jj = 0; jj < kn; ++jj) {
-            const float4* kr = reinterpret_cast<const float4*>(Ks + jj * kAD + half * kAHalf);
-            const float4* vr = reinterpret_cast<const float4*>(Vs + jj * kAD + half * kAHalf);
-            float s = 0.f, dp = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 kk = kr[c], vv = vr[c];
-                s += qn[4 * c] * kk.x + qn[4 * c + 1] * kk.y + qn[4 * c + 2] * kk.z + qn[4 * c + 3] * kk.w;
-                dp += go[4 * c] * vv.x + go[4 * c + 1] * vv.y + go[4 * c + 2] * vv.z + go[4 * c + 3] * vv.w;
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-            const float p = __expf(s * 0.125f - L);
-            const float dsv = p * (dp - D) * 0.125f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 kk = kr[c];
-                dq[4 * c] += dsv * kk.x; dq[4 * c + 1] += dsv * kk.y; dq[4 * c + 2] += dsv * kk.z; dq[4 * c + 3] += dsv * kk.w;
+            for (int n = 0; n < 8; ++n) {
+                const float2 av = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(a_base + (size_t)row * C + n * 8 + 2 * t));
+                const float2 gv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(g_base + (size_t)row * C + n * 8 + 2 * t));
+                D[r] += av.x * gv.x + av.y * gv.y;
             }
         }
+        D[r] += __shfl_xor_sync(0xffffffffu, D[r], 1);
+        D[r] += __shfl_xor_sync(0xffffffffu, D[r], 2);
     }
-    float dot = 0.f;
+    // pass 1: log-sum-exp of the score rows (log2 domain)
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int kb = 0; kb < npad; kb += 64) {
+        float s[8][4];
+        mma_a_rowsT(s, qa, Ks, kb, g, t);
+        float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int j = 0; j < kAHalf; ++j) dot += dq[j] * q[j];
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    norm_bwd_half(q, dq, ssq, dot);
-    if (row < N) {
-        store_half(dqk + (size_t)b * N * 2 * C + head * kAD, 2 * C, row, half, dq);
-        if (half == 0) {
-            float* st = stats + (((size_t)b * heads + head) * N + row) * 2;
-            st[0] = L;
-            st[1] = D;
+        for (int n = 0; n < 8; ++n) {
+            const int key = kb + n * 8 + 2 * t;
+            if (key >= N) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+            if (key + 1 >= N) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
+            mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);       // finite: every 64-key block holds >= 1 real key
+            l_run[r] *= exp2f((m_run[r] - m_new) * kSl2);
+            m_run[r] = m_new;
+        }
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            l_run[0] += exp2f((s[n][0] - m_run[0]) * kSl2) + exp2f((s[n][1] - m_run[0]) * kSl2);
+            l_run[1] += exp2f((s[n][2] - m_run[1]) * kSl2) + exp2f((s[n][3] - m_run[1]) * kSl2);
+        }
+    }
+    float L2[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+        L2[r] = m_run[r] * kSl2 + log2f(l_run[r]);
+    }
+    // pass 2: dQ^
+    float dq[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+    for (int kb = 0; kb < npad; kb += 64) {
+        float s[8][4], dp[8][4];
+        mma_a_rowsT(s, qa, Ks, kb, g, t);
+        mma_a_rowsT(dp, ga, Vs, kb, g, t);
+        uint32_t dsa[4][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const int key = kb + n * 8 + 2 * t;
+            const bool k0 = key < N, k1 = key + 1 < N;
+            const float p0 = k0 ? exp2f(s[n][0] * kSl2 - L2[0]) : 0.f, p1 = k1 ? exp2f(s[n][1] * kSl2 - L2[0]) : 0.f;
+            const float p2 = k0 ? exp2f(s[n][2] * kSl2 - L2[1]) : 0.f, p3 = k1 ? exp2f(s[n][3] * kSl2 - L2[1]) : 0.f;
+            dsa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0 * (dp[n][0] - D[0]) * 0.125f, p1 * (dp[n][1] - D[0]) * 0.125f);
+            dsa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2 * (dp[n][2] - D[1]) * 0.125f, p3 * (dp[n][3] - D[1]) * 0.125f);
+        }
+        mma_frag_rows(dq, dsa, Ks, kb, lane);
+    }
+    norm_bwd_store(q_base, dqk + (size_t)b * N * 2 * C + head * kAD, 2 * (size_t)C, 2 * (size_t)C, row_a, N, t, dq);
+    if (t == 0) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int row = row_a + r * 8;
+            if (row < N) {
+                float* st = stats + (((size_t)b * heads + head) * N + row) * 2;
+                st[0] = L2[r];
+                st[1] = D[r];
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kBwdThreads)
 attention_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                         const __nv_bfloat16* __restrict__ da, const float* __restrict__ stats,
-                        __nv_bfloat16* __restrict__ dqk, __nv_bfloat16* __restrict__ dv_out, int N, int heads) {
-    __shared__ __align__(16) float Qs[kATile * kAD];
-    __shared__ __align__(16) float Gs[kATile * kAD];
-    __shared__ float Ls[kATile], Ds[kATile];
+                        __nv_bfloat16* __restrict__ dqk, __nv_bfloat16* __restrict__ dv_out, int N, int heads, int npad) {
+    extern __shared__ __align__(16) uint8_t smem_bwd[];
+    __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_bwd);        // [npad][kRS]  q^ (all queries)
+    __nv_bfloat16* Gs = Qs + (size_t)npad * kRS;                           // [npad][kRS]  dA
+    __nv_bfloat16* Kt = Gs + (size_t)npad * kRS;                           // [kBT][kRS]   k^ tile
+    __nv_bfloat16* Vt = Kt + (size_t)kBT * kRS;                            // [kBT][kRS]   v^ tile
+    float* Ls = reinterpret_cast<float*>(Vt + (size_t)kBT * kRS);          // [npad]
+    float* Ds = Ls + npad;                                                 // [npad]
     const int C = heads * kAD;
-    const int head = blockIdx.y, b = blockIdx.z;
-    const int row = blockIdx.x * kARows + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    const int head = blockIdx.y, b = blockIdx.z, k0 = blockIdx.x * kBT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const __nv_bfloat16* q_base = qk + (size_t)b * N * 2 * C + head * kAD;
-    const __nv_bfloat16* k_base = q_base + C;
     const __nv_bfloat16* v_base = v + (size_t)b * N * C + head * kAD;
-    const __nv_bfloat16* da_base = da + (size_t)b * N * C + head * kAD;
     const float* st = stats + ((size_t)b * heads + head) * N * 2;
-
-    float k[kAHalf], kn[kAHalf], vv[kAHalf], vn[kAHalf], dk[kAHalf], dvv[kAHalf];
-    float ssk = load_half(k_base, 2 * C, row, N, half, k);
-    float ssv = load_half(v_base, C, row, N, half, vv);
-    ssk += __shfl_xor_sync(0xffffffffu, ssk, 1);
-    ssv += __shfl_xor_sync(0xffffffffu, ssv, 1);
-    const float invk = 1.f / (kNormEps + sqrtf(ssk) * 0.125f), invv = 1.f / (kNormEps + sqrtf(ssv) * 0.125f);
-#pragma unroll
-    for (int j = 0; j < kAHalf; ++j) { kn[j] = k[j] * invk; vn[j] = vv[j] * invv; dk[j] = 0.f; dvv[j] = 0.f; }
-
-    for (int i0 = 0; i0 < N; i0 += kATile) {
-        __syncthreads();
-        stage_rows_f32(q_base, 2 * C, i0, N, true, Qs);
-        stage_rows_f32(da_base, C, i0, N, false, Gs);
-        if (threadIdx.x < kATile) {
-            const int i = i0 + threadIdx.x;
-            Ls[threadIdx.x] = i < N ? st[2 * i] : 0.f;
-            Ds[threadIdx.x] = i < N ? st[2 * i + 1] : 0.f;
-        }
-        __syncthreads();
-        const int in = min(kATile, N - i0);
-        for (int ii = 0; ii < in; ++ii) {
-            const float4* qr = reinterpret_cast<const float4*>(Qs + ii * kAD + half * kAHalf);
-            const float4* gr = reinterpret_cast<const float4*>(Gs + ii * kAD + half * kAHalf);
-            float s = 0.f, dp = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 qq = qr[c], gg = gr[c];
-                s += kn[4 * c] * qq.x + kn[4 * c + 1] * qq.y + kn[4 * c + 2] * qq.z + kn[4 * c + 3] * qq.w;
-                dp += vn[4 * c] * gg.x + vn[4 * c + 1] * gg.y + vn[4 * c + 2] * gg.z + vn[4 * c + 3] * gg.w;
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            dp += __shfl_xor_sync(0xffffffffu, dp, 1);
-            const float p = __expf(s * 0.125f - Ls[ii]);
-            const float dsv = p * (dp - Ds[ii]) * 0.125f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float4 qq = qr[c], gg = gr[c];
-                dk[4 * c] += dsv * qq.x; dk[4 * c + 1] += dsv * qq.y; dk[4 * c + 2] += dsv * qq.z; dk[4 * c + 3] += dsv * qq.w;
-                dvv[4 * c] += p * gg.x; dvv[4 * c + 1] += p * gg.y; dvv[4 * c + 2] += p * gg.z; dvv[4 * c + 3] += p * gg.w;
-            }
-        }
+    stage_rows_bwd(q_base, 2 * (size_t)C, 0, npad, N, Qs, true);
+    stage_rows_bwd(da + (size_t)b * N * C + head * kAD, (size_t)C, 0, npad, N, Gs, false);
+    stage_rows_bwd(q_base + C, 2 * (size_t)C, k0, kBT, N, Kt, true);
+    stage_rows_bwd(v_base, (size_t)C, k0, kBT, N, Vt, true);
+    for (int i = threadIdx.x; i < npad; i += kBwdThreads) {
+        Ls[i] = i < N ? st[2 * i] : INFINITY;            // padded queries: P = exp2(. - inf) = 0
+        Ds[i] = i < N ? st[2 * i + 1] : 0.f;
     }
-    float dotk = 0.f, dotv = 0.f;
+    __syncthreads();
+
+    const int row0 = warp * 16, row_a = k0 + row0 + g;
+    uint32_t ka[4][4], va[4][4];
+    load_a_frags(Kt, row0, g, t, ka);
+    load_a_frags(Vt, row0, g, t, va);
+    float dk[8][4], dvv[8][4];
 #pragma unroll
-    for (int j = 0; j < kAHalf; ++j) { dotk += dk[j] * k[j]; dotv += dvv[j] * vv[j]; }
-    dotk += __shfl_xor_sync(0xffffffffu, dotk, 1);
-    dotv += __shfl_xor_sync(0xffffffffu, dotv, 1);
-    norm_bwd_half(k, dk, ssk, dotk);
-    norm_bwd_half(vv, dvv, ssv, dotv);
-    if (row < N) {
-        store_half(dqk + (size_t)b * N * 2 * C + C + head * kAD, 2 * C, row, half, dk);
-        store_half(dv_out + (size_t)b * N * C + head * kAD, C, row, half, dvv);
+    for (int n = 0; n < 8; ++n) { dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f; dvv[n][0] = dvv[n][1] = dvv[n][2] = dvv[n][3] = 0.f; }
+    for (int qb = 0; qb < npad; qb += 64) {
+        float s[8][4], dp[8][4];
+        mma_a_rowsT(s, ka, Qs, qb, g, t);             // S^T: rows = keys, cols = queries
+        mma_a_rowsT(dp, va, Gs, qb, g, t);            // dP^T
+        uint32_t pa[4][4], dsa[4][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const int i = qb + n * 8 + 2 * t;
+            const float l0 = Ls[i], l1 = Ls[i + 1], d0 = Ds[i], d1 = Ds[i + 1];
+            const float p0 = exp2f(s[n][0] * kSl2 - l0), p1 = exp2f(s[n][1] * kSl2 - l1);
+            const float p2 = exp2f(s[n][2] * kSl2 - l0), p3 = exp2f(s[n][3] * kSl2 - l1);
+            pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+            pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+            dsa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0 * (dp[n][0] - d0) * 0.125f, p1 * (dp[n][1] - d1) * 0.125f);
+            dsa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2 * (dp[n][2] - d0) * 0.125f, p3 * (dp[n][3] - d1) * 0.125f);
+        }
+        mma_frag_rows(dvv, pa, Gs, qb, lane);         // dV^ += P^T dA
+        mma_frag_rows(dk, dsa, Qs, qb, lane);         // dK^ += dS^T Q^
     }
+    norm_bwd_store(q_base + C, dqk + (size_t)b * N * 2 * C + C + head * kAD, 2 * (size_t)C, 2 * (size_t)C, row_a, N, t, dk);
+    norm_bwd_store(v_base, dv_out + (size_t)b * N * C + head * kAD, (size_t)C, (size_t)C, row_a, N, t, dvv);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -988,18 +1058,27 @@ extern "C" int dd_attention_bwd(const void* qk, const void* v, const void* a_raw
     DD_REQUIRE(qk && v && a_raw && d_a && dqk && dv && stats_ws, "dd_attention_bwd: null pointer");
     DD_REQUIRE(head_dim == kAD, "dd_attention_bwd: head_dim=%d unsupported (64)", head_dim);
     DD_REQUIRE(N > 0 && B > 0 && B <= 65535 && heads <= 65535, "dd_attention_bwd: bad shape");
-    const dim3 grid(ceil_div(N, kARows), heads, B);
-    attention_bwd_q_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qk),
-                                                     static_cast<const __nv_bfloat16*>(v),
-                                                     static_cast<const __nv_bfloat16*>(a_raw),
-                                                     static_cast<const __nv_bfloat16*>(d_a),
-                                                     static_cast<__nv_bfloat16*>(dqk), stats_ws, N, heads);
+    const int npad = ceil_div(N, 64) * 64;
+    const size_t smem = ((size_t)2 * npad * kRS + (size_t)2 * kBT * kRS) * 2 + (size_t)2 * npad * sizeof(float);
+    DD_REQUIRE(smem <= 227 * 1024, "dd_attention_bwd: sequence length %d exceeds the shared-memory resident design", N);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        DD_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DD_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const dim3 grid(ceil_div(N, kBT), heads, B);
+    attention_bwd_q_kernel<<<grid, kBwdThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+                                                                static_cast<const __nv_bfloat16*>(v),
+                                                                static_cast<const __nv_bfloat16*>(a_raw),
+                                                                static_cast<const __nv_bfloat16*>(d_a),
+                                                                static_cast<__nv_bfloat16*>(dqk), stats_ws, N, heads, npad);
     DD_CHECK_LAUNCH();
-    attention_bwd_kv_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qk),
-                                                      static_cast<const __nv_bfloat16*>(v),
-                                                      static_cast<const __nv_bfloat16*>(d_a), stats_ws,
-                                                      static_cast<__nv_bfloat16*>(dqk), static_cast<__nv_bfloat16*>(dv), N,
-                                                      heads);
+    attention_bwd_kv_kernel<<<grid, kBwdThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+                                                                 static_cast<const __nv_bfloat16*>(v),
+                                                                 static_cast<const __nv_bfloat16*>(d_a), stats_ws,
+                                                                 static_cast<__nv_bfloat16*>(dqk),
+                                                                 static_cast<__nv_bfloat16*>(dv), N, heads, npad);
     DD_CHECK_LAUNCH();
     return 0;
 }

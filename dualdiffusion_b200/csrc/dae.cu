@@ -140,40 +140,54 @@ __global__ void up2_silu_pad_kernel(const uint4* __restrict__ a, uint4* __restri
 //   x [B][H][Wp][2C] bf16 (pw >= 2), w fp32 [C][25] pre-scaled by 1/sqrt(25 C) (dd_weight_prep, DD_WFMT_F32_OIT),
 //   out fp32 [B][2][H][W]
 // ------------------------------------------------------------------------------------------
+// Tile of 32 x 8 output pixels per CTA: the (32+4) x (8+4) input pixels x 2C channels are staged once in shared
+// memory (16-byte channel vectors XOR-swizzled by the pixel column so that the 32 lanes of a warp, which read the same
+// channel vector of 32 neighbouring pixels, hit 32 different banks), then every thread accumulates its pixel's 25 taps.
+constexpr int kC5W = 32, kC5H = 8;
+
 template <int C>
-__global__ void __launch_bounds__(256) conv5x5_out_kernel(const uint4* __restrict__ x, const float* __restrict__ wq,
-                                                          const float* __restrict__ gain, float* __restrict__ out, int B,
-                                                          int H, int W, int pw) {
-    __shared__ float ws[25 * C];
-    const float g = gain ? *gain : 1.f;
-    for (int i = threadIdx.x; i < 25 * C; i += blockDim.x) ws[i] = wq[i] * g;
-    __syncthreads();
+__global__ void __launch_bounds__(kC5W * kC5H) conv5x5_out_kernel(const uint4* __restrict__ x, const float* __restrict__ wq,
+                                                                 const float* __restrict__ gain, float* __restrict__ out,
+                                                                 int B, int H, int W, int pw) {
     constexpr int NV = C / 8;                    // uint4 vectors per stereo side
+    constexpr int PV = 2 * NV;                   // vectors per pixel
+    constexpr int TW = kC5W + 4, TH = kC5H + 4;
+    extern __shared__ __align__(16) uint8_t smem_c5[];
+    uint4* tile = reinterpret_cast<uint4*>(smem_c5);                       // [TH][TW][PV], vector index ^ (col & 7)
+    float* ws = reinterpret_cast<float*>(tile + TH * TW * PV);             // [C][25]
+    const float g = gain ? *gain : 1.f;
+    const int tid = threadIdx.y * kC5W + threadIdx.x;
+    for (int i = tid; i < 25 * C; i += kC5W * kC5H) ws[i] = wq[i] * g;
     const int Wp = W + 2 * pw;
-    const long total = (long)B * H * W;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int w = (int)(idx % W);
-        const int h = (int)((idx / W) % H);
-        const int b = (int)(idx / ((long)W * H));
-        float acc0 = 0.f, acc1 = 0.f;
-        for (int dy = -2; dy <= 2; ++dy) {
-            const int hh = h + dy;
-            if (hh < 0 || hh >= H) continue;                                   // zero padding along H
-            const uint4* row = x + ((long)b * H + hh) * Wp * (2 * NV);
+    const int b = blockIdx.z, h0 = blockIdx.y * kC5H, w0 = blockIdx.x * kC5W;
+    for (int i = tid; i < TH * TW * PV; i += kC5W * kC5H) {
+        const int v = i % PV, col = (i / PV) % TW, row = i / (PV * TW);
+        const int hh = h0 + row - 2, pc = w0 + col + pw - 2;               // physical column (halo columns hold the reflection)
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (hh >= 0 && hh < H && pc < Wp) q = __ldg(x + (((long)b * H + hh) * Wp + pc) * PV + v);
+        tile[(row * TW + col) * PV + (v ^ (col & 7))] = q;
+    }
+    __syncthreads();
+    const int w = w0 + threadIdx.x, h = h0 + threadIdx.y;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 1
+    for (int dy = 0; dy < 5; ++dy) {
+#pragma unroll 1
+        for (int dx = 0; dx < 5; ++dx) {
+            const int col = threadIdx.x + dx;
+            const uint4* px = tile + ((threadIdx.y + dy) * TW + col) * PV;
+            const float* wt = ws + dy * 5 + dx;
 #pragma unroll
-            for (int dx = -2; dx <= 2; ++dx) {
-                const uint4* px = row + (long)(w + pw + dx) * (2 * NV);       // halo columns hold the reflection
-                const float* wt = ws + ((dy + 2) * 5 + (dx + 2));
+            for (int v = 0; v < NV; ++v) {
+                float f0[8], f1[8];
+                unpack8d(px[v ^ (col & 7)], f0);
+                unpack8d(px[(NV + v) ^ (col & 7)], f1);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    float f0[8], f1[8];
-                    unpack8d(__ldg(px + v), f0);
-                    unpack8d(__ldg(px + NV + v), f1);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { acc0 += f0[j] * wt[(v * 8 + j) * 25]; acc1 += f1[j] * wt[(v * 8 + j) * 25]; }
-                }
+                for (int j = 0; j < 8; ++j) { acc0 += f0[j] * wt[(v * 8 + j) * 25]; acc1 += f1[j] * wt[(v * 8 + j) * 25]; }
             }
         }
+    }
+    if (w < W && h < H) {
         out[(((size_t)b * 2 + 0) * H + h) * W + w] = acc0;
         out[(((size_t)b * 2 + 1) * H + h) * W + w] = acc1;
     }
@@ -316,15 +330,20 @@ extern "C" int dd_conv5x5_out(const void* x, const float* w25, const float* gain
                               int pw, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(x && w25 && out && pw >= 2, "dd_conv5x5_out: bad arguments (needs two halo columns)");
-    const long total = (long)B * H * W;
-    if (total == 0) return 0;
-    const int grid = grid_for_d(total, 256);
-    if (C == 32)
-        conv5x5_out_kernel<32><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
-    else if (C == 64)
-        conv5x5_out_kernel<64><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
-    else
-        DD_REQUIRE(false, "dd_conv5x5_out: C=%d unsupported (32 or 64 channels per stereo side)", C);
+    if ((long)B * H * W == 0) return 0;
+    DD_REQUIRE(C == 32 || C == 64, "dd_conv5x5_out: C=%d unsupported (32 or 64 channels per stereo side)", C);
+    DD_REQUIRE(B <= 65535 && ceil_div(H, kC5H) <= 65535, "dd_conv5x5_out: grid too large");
+    const dim3 grid(ceil_div(W, kC5W), ceil_div(H, kC5H), B), block(kC5W, kC5H);
+    const size_t smem = (size_t)(kC5W + 4) * (kC5H + 4) * (2 * C / 8) * 16 + (size_t)25 * C * sizeof(float);
+    if (C == 32) {
+        static bool done = false;
+        if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv5x5_out_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
+        conv5x5_out_kernel<32><<<grid, block, smem, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
+    } else {
+        static bool done = false;
+        if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv5x5_out_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
+        conv5x5_out_kernel<64><<<grid, block, smem, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
+    }
     DD_CHECK_LAUNCH();
     return 0;
 }
