@@ -273,6 +273,39 @@ __global__ void ddec_head_kernel(const __nv_bfloat16* __restrict__ f, const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// unet_edm2_q4_ddec input (unet_edm2_q4_ddec.py:268-277): mp_cat(c_in*x_in, x_ref') with
+//   x_ref' = x_ref.view(B, C, F, k, W).permute(0, 3, 1, 2, 4).reshape(B, k*C, F, W)   (channel j*C + c)
+// -> NHWC bf16 [B][F][W][Cpad]: channels [wa*c_in*x (C) | wb*x_ref' (k*C) | 1 (feeds the conv_in bias column) | 0...]
+// ------------------------------------------------------------------------------------------
+__global__ void q4_stem_kernel(const float* __restrict__ x_in, const float* __restrict__ x_ref, const float* __restrict__ sigma,
+                               float sigma_data, float wa, float wb, __nv_bfloat16* __restrict__ out, int B, int C, int Fq,
+                               int W, int k, int Cpad) {
+    const long total = (long)B * Fq * W * Cpad;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(idx % Cpad);
+        long pix = idx / Cpad;
+        const int w = (int)(pix % W);
+        pix /= W;
+        const int h = (int)(pix % Fq), b = (int)(pix / Fq);
+        float v = 0.f;
+        if (ch < C) {
+            const float sg = sigma[b];
+            // the reference rounds c_in*x to bf16 before the concat scale is applied (:274-277)
+            const float xs = __bfloat162float(__float2bfloat16_rn(x_in[(((size_t)b * C + ch) * Fq + h) * W + w] *
+                                                                  rsqrtf(sigma_data * sigma_data + sg * sg)));
+            v = wa * xs;
+        } else if (ch < C + k * C) {
+            const int j = (ch - C) / C, c = (ch - C) - j * C;
+            const float xr = __bfloat162float(__float2bfloat16_rn(x_ref[(((size_t)b * C + c) * Fq * k + (size_t)h * k + j) * W + w]));
+            v = wb * xr;
+        } else if (ch == C + k * C) {
+            v = 1.f;
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
 }  // namespace
 
 extern "C" int dd_weight_prep_z2(const void* w, int w_is_bf16, void* out, int O, int I, int kz, int taps,
@@ -379,6 +412,18 @@ extern "C" int dd_ddec_head(const void* f, const float* x_in, const float* sigma
     if (total == 0) return 0;
     ddec_head_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(f), x_in, sigma, sigma_data,
                                                                  out, B, H, W, pw, Cst);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_q4_stem(const float* x_in, const float* x_ref, const float* sigma, float sigma_data, float wa, float wb,
+                          void* out, int B, int C, int F, int W, int k, int Cpad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x_in && x_ref && sigma && out && k >= 1 && C * (k + 1) + 1 <= Cpad, "dd_q4_stem: bad arguments");
+    const long total = (long)B * F * W * Cpad;
+    if (total == 0) return 0;
+    q4_stem_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(x_in, x_ref, sigma, sigma_data, wa, wb,
+                                                               static_cast<__nv_bfloat16*>(out), B, C, F, W, k, Cpad);
     DD_CHECK_LAUNCH();
     return 0;
 }

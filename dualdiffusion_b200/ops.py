@@ -601,3 +601,13 @@ def ddec_head(f: Tensor, x_in: Tensor, sigma: Tensor, sigma_data: float, pw: int
                                   L.stream_ptr()))
     _count()
     return out
+
+
+def q4_stem(x_in: Tensor, x_ref: Tensor, sigma: Tensor, sigma_data: float, wa: float, wb: float, k: int,
+            cpad: int = 32) -> Tensor:
+    B, Cc, Fq, W = x_in.shape
+    out = torch.empty((B, Fq, W, cpad), device=x_in.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_q4_stem(L.ptr(x_in), L.ptr(x_ref), L.ptr(sigma), sigma_data, wa, wb, L.ptr(out), B, Cc, Fq, W, k,
+                                cpad, L.stream_ptr()))
+    _count()
+    return out

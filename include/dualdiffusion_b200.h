@@ -358,6 +358,12 @@ DD_API int dd_avgpool2_pad(const void* x, void* out, int B, int H, int W, int C,
 DD_API int dd_ddec_head(const void* f, const float* x_in, const float* sigma, float sigma_data, float* out, int B, int H,
                         int W, int pw, int Cst, void* stream);
 
+/* unet_edm2_q4_ddec.UNet input (modules/unets/unet_edm2_q4_ddec.py:268-277): mp_cat(c_in*x_in, permuted PSD x_ref) as
+ * NHWC bf16 [B][F][W][Cpad]: [wa*c_in*x (C) | wb*x_ref[b][c][h*k+j] at channel C + j*C + c | 1 | 0...]; the constant-one
+ * channel carries conv_in's bias through a centre-tap weight column.  x_in fp32 (B,C,F,W), x_ref fp32 (B,C,F*k,W).   */
+DD_API int dd_q4_stem(const float* x_in, const float* x_ref, const float* sigma, float sigma_data, float wa, float wb,
+                      void* out, int B, int C, int F, int W, int k, int Cpad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,23 @@ def main():
                     d_perturbed=ddec(x, sigma, None, None, x_ref, pert), logvar=ddec.get_sigma_loss_logvar(sigma),
                     weight_checksum=weight_checksum(ssd)), os.path.join(OUT, "ddec_small.pt"))
 
+    # ---- 2-D diffusion-decoder UNet unet_edm2_q4_ddec.UNet (:253-303), reduced config ----
+    from modules.unets.unet_edm2_q4_ddec import UNet as Q4UNet, UNet_Config as Q4Config
+    qspec = dd.small_q4_spec()
+    qsd = dd.synth_q4_state_dict(qspec, seed=0)
+    q4 = Q4UNet(Q4Config(in_num_freqs=qspec.in_num_freqs, in_psd_freqs=qspec.in_psd_freqs, model_channels=qspec.model_channels,
+                         logvar_channels=qspec.logvar_channels, channel_mult=tuple(qspec.channel_mult),
+                         double_midblock=qspec.double_midblock, channel_mult_noise=qspec.channel_mult_noise,
+                         channel_mult_emb=qspec.channel_mult_emb, num_layers_per_block=qspec.num_layers_per_block,
+                         mlp_multiplier=qspec.mlp_multiplier)).eval()
+    q4.load_state_dict(qsd, strict=True)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 2, qspec.in_num_freqs, 24, generator=g)
+    x_ref = torch.rand(2, 2, qspec.in_psd_freqs, 24, generator=g)
+    sigma = torch.tensor([0.5, 3.0])
+    torch.save(dict(x=x, x_ref=x_ref, sigma=sigma, d=q4(x, sigma, None, None, x_ref), weight_checksum=weight_checksum(qsd)),
+               os.path.join(OUT, "q4_ddec_small.pt"))
+
     # ---- sampler: reference diffusion_decode on CPU, reduced config, 3 Heun+CFG steps ----
     spec = uo.small_spec()
     sd = uo.synth_state_dict(spec, seed=0)

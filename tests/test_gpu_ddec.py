@@ -117,3 +117,70 @@ def test_ddec_default_config_runs_and_matches_oracle_band(dev):
     c_skip = 1.0 / (1.0 + sigma.view(-1, 1, 1, 1) ** 2)
     assert rel_err(d, ref) < BF16_NET
     assert rel_err(d.cpu() - c_skip * x, ref - c_skip * x) < 2 * BF16_NET
+
+
+# ------------------------------------------------------------------------------------------
+# unet_edm2_q4_ddec.UNet (the 2-D variant of row A17)
+# ------------------------------------------------------------------------------------------
+def test_q4_stem_permute_and_bias_channel_are_exact(dev):
+    """unet_edm2_q4_ddec.py:268-277: x_ref.view(B,C,F,k,W).permute(0,3,1,2,4).reshape(B,k*C,F,W) joined to c_in*x by mp_cat.
+    With unit concat weights the PSD channels are pure data movement (+ one bf16 rounding): bit-exact."""
+    from dualdiffusion_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    B, C, Fq, k, W = 2, 2, 8, 4, 9
+    x = torch.randn(B, C, Fq, W, generator=gen)
+    xr = torch.rand(B, C, Fq * k, W, generator=gen)
+    sigma = torch.tensor([0.5, 3.0])
+    got = ops.q4_stem(x.to(dev), xr.to(dev), sigma.to(dev), 1.0, 1.0, 1.0, k, 32).float().cpu()      # [B][F][W][32]
+    ref = xr.view(B, C, Fq, k, W).permute(0, 3, 1, 2, 4).reshape(B, k * C, Fq, W).to(torch.bfloat16).float()
+    assert torch.equal(got[..., C:C + k * C], ref.permute(0, 2, 3, 1))
+    c_in = 1 / (1 + sigma.view(-1, 1, 1, 1) ** 2).sqrt()
+    assert rel_err(got[..., :C], (c_in * x).to(torch.bfloat16).float().permute(0, 2, 3, 1)) < 4e-3
+    assert torch.equal(got[..., C + k * C], torch.ones(B, Fq, W)) and got[..., C + k * C + 1:].abs().max().item() == 0
+
+
+def make_q4(spec, sd, dev):
+    from dualdiffusion_b200.modules.unets.unet_edm2_q4_ddec import UNet, UNet_Config
+    cfg = UNet_Config(in_num_freqs=spec.in_num_freqs, in_psd_freqs=spec.in_psd_freqs, model_channels=spec.model_channels,
+                      logvar_channels=spec.logvar_channels, channel_mult=tuple(spec.channel_mult),
+                      double_midblock=spec.double_midblock, channel_mult_noise=spec.channel_mult_noise,
+                      channel_mult_emb=spec.channel_mult_emb, num_layers_per_block=spec.num_layers_per_block,
+                      mlp_multiplier=spec.mlp_multiplier)
+    net = UNet(cfg)
+    net.load_state_dict(sd, strict=True)
+    return net.requires_grad_(False).train(False).to(dev)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_q4_ddec_forward_vs_golden_reference_and_oracle(dev, graphs):
+    spec = dd.small_q4_spec()
+    sd = dd.synth_q4_state_dict(spec, seed=0)
+    g = load_golden("q4_ddec_small.pt")
+    net = make_q4(spec, sd, dev)
+    net.use_cuda_graphs = graphs
+    ref32 = dd.q4_forward(sd, spec, g["x"], g["sigma"], g["x_ref"], torch.float32)
+    for _ in range(2):
+        d = net(g["x"].to(dev), g["sigma"].to(dev), None, None, g["x_ref"].to(dev))
+    assert d.shape == g["d"].shape and d.dtype == torch.float32
+    assert rel_err(d, ref32) < BF16_NET and rel_err(d, g["d"]) < BF16_NET
+    c_skip = 1.0 / (1.0 + g["sigma"].view(-1, 1, 1, 1) ** 2)
+    assert rel_err(d.cpu() - c_skip * g["x"], ref32 - c_skip * g["x"]) < 2 * BF16_NET
+    # the conv_in bias matters: dropping it changes the output far beyond the tolerance (the centre-tap column is live)
+    sd0 = dict(sd)
+    sd0["enc.conv_in.bias"] = torch.zeros_like(sd["enc.conv_in.bias"])
+    assert rel_err(dd.q4_forward(sd0, spec, g["x"], g["sigma"], g["x_ref"]) - c_skip * g["x"], ref32 - c_skip * g["x"]) > 4 * BF16_NET
+
+
+def test_q4_ddec_default_config_vs_oracle(dev):
+    spec = dd.Q4Spec()
+    sd = dd.synth_q4_state_dict(spec, seed=0)
+    net = make_q4(spec, sd, dev)
+    gen = torch.Generator().manual_seed(13)
+    x = torch.randn(1, 2, 256, 32, generator=gen)
+    xr = torch.rand(1, 2, 2048, 32, generator=gen)
+    sigma = torch.tensor([1.5])
+    d = net(x.to(dev), sigma.to(dev), None, None, xr.to(dev))
+    ref = dd.q4_forward(sd, spec, x, sigma, xr, torch.float32)
+    c_skip = 1.0 / (1.0 + sigma.view(-1, 1, 1, 1) ** 2)
+    assert rel_err(d, ref) < BF16_NET
+    assert rel_err(d.cpu() - c_skip * x, ref - c_skip * x) < 2 * BF16_NET

@@ -183,3 +183,17 @@ def test_ddec_oracle_vs_golden_reference():
     d32 = dd.ddec_forward(sd, spec, g["x"], g["sigma"], g["x_ref"], torch.float32)
     assert rel_err(d32, g["d"]) < 1e-2
     assert rel_err(dd.ddec_sigma_loss_logvar(sd, g["sigma"]), g["logvar"]) < 1e-6
+
+
+def test_q4_ddec_oracle_vs_golden_reference():
+    """Row A17 (2-D variant): unet_edm2_q4_ddec.UNet restatement against the reference module (bf16 body in the
+    reference; channels_last CPU kernels order the bf16 accumulation differently, hence bf16-level agreement)."""
+    from oracle import ddec_oracle as dd
+    g = load_golden("q4_ddec_small.pt")
+    spec = dd.small_q4_spec()
+    sd = dd.synth_q4_state_dict(spec, seed=0)
+    c_skip = 1.0 / (1.0 + g["sigma"].view(-1, 1, 1, 1) ** 2)
+    for dt, tol in ((torch.bfloat16, 8e-3), (torch.float32, 1e-2)):
+        d = dd.q4_forward(sd, spec, g["x"], g["sigma"], g["x_ref"], dt)
+        assert rel_err(d, g["d"]) < tol
+        assert rel_err(d - c_skip * g["x"], g["d"] - c_skip * g["x"]) < 3 * tol
