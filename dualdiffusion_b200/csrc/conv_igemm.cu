@@ -60,6 +60,7 @@ struct ConvParams {
     int kchunks;                    // cin_g / KC
     int k_iters;                    // taps * kchunks
     int sub;                        // operand pairs per pipeline stage (1 or 2)
+    int ksplit;                     // split-K factor = cluster size (conv_igemm_splitk_kernel), 1 otherwise
     int num_tiles;
     int stages;
     uint32_t a_bytes, b_bytes;      // bytes landed per stage by the two TMA boxes
@@ -137,9 +138,29 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH],
     }
 }
 
+// (split-K) partial accumulators of the other CTAs of the cluster: `peer_stage` is this CTA's shared::cta byte address of
+// the staging area, which has the same offset in every CTA; rank r's copy is reached through mapa / ld.shared::cluster.
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
 template <int EW>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
-                                              int ch0) {
+                                              int ch0, uint32_t peer_stage = 0, int row = 0) {
     constexpr int kChunk = EW >= 8 ? 16 : 32;   // columns per tcgen05.ld
     const size_t pix = ((size_t)b * p.H + h) * p.W + w;
     uint32_t rn[kChunk];
@@ -160,6 +181,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
               }
               if (c0 + kChunk < p.n_tile)
                   tmem_ld_chunk<kChunk>(taddr + c0 + kChunk, rn, kChunk == 32 && c0 + 2 * kChunk > p.n_tile);
+              if (p.ksplit > 1) {           // add the partial sums the other k-ranges left in their shared memory
+                  const uint32_t off = (uint32_t)(((c0 / kChunk) * kTileM + row) * kChunk) * 4u;
+                  for (int pr = 1; pr < p.ksplit; ++pr) {
+                      const uint32_t pa = map_to_cta(peer_stage + off, (uint32_t)pr);
+#pragma unroll
+                      for (int i = 0; i < kChunk / 4; ++i) {
+                          const float4 q = ld_cluster_f4(pa + 16u * i);
+                          r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + q.x);
+                          r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + q.y);
+                          r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + q.z);
+                          r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + q.w);
+                      }
+                  }
+              }
               if (!valid) continue;
 #pragma unroll
               for (int sub16 = 0; sub16 < kChunk / 16; ++sub16) {
@@ -411,6 +446,155 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
     }
+
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------
+// Split-K variant for the small-M layers (levels 3-4 of the UNet: 172-688 pixels).  There the per-tile k-loop is bound
+// by what one SM can pull through TMA (~36 B/clk) while most SMs idle, so a thread-block cluster of `ksplit` CTAs shares
+// one output tile: CTA r accumulates k-iterations [r*K/S, (r+1)*K/S) in its own TMEM, ranks > 0 park their fp32 partial
+// tile in their (now idle) pipeline shared memory, and rank 0 adds them through distributed shared memory
+// (ld.shared::cluster) in front of the normal fused epilogue.  One tile per cluster, four epilogue warps.
+// ---------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(64 + 32 * 4, 1)
+conv_igemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ ConvParams p) {
+    constexpr uint32_t kRowBytes = KC * 2;
+    constexpr uint32_t kABufBytes = kTileM * kRowBytes;
+    constexpr int kChunk = 32;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t b_buf_bytes = (uint32_t)p.n_tile * kRowBytes;
+    const uint32_t pair_bytes = kABufBytes + b_buf_bytes;
+    const uint32_t stage_bytes = pair_bytes * (uint32_t)p.sub;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int krank = (int)cluster_ctarank();
+    const int tile = blockIdx.x / p.ksplit;
+    const int it_begin = (int)((long)krank * p.k_iters / p.ksplit), it_end = (int)((long)(krank + 1) * p.k_iters / p.ksplit);
+    const TileCoord t = decode_tile(p, tile);
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        for (int s = 0; s < p.stages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_init(&tmem_full_bar, 1);
+        ptx::mbar_fence_init();
+        ptx::fence_proxy_async_smem();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&tmem_base_slot, p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tcgen05_fence_before();
+    __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    ptx::grid_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::grid_dependency_wait();
+            uint32_t stage = 0, phase = 0;
+            const int a_c0 = t.g * p.cin_g;
+            const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
+            for (int it0 = it_begin; it0 < it_end; it0 += p.sub) {
+                const int cnt = min(p.sub, it_end - it0);
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                for (int j = 0; j < cnt; ++j) {
+                    const int it = it0 + j;
+                    const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+                    const int dy = tap / p.kw - p.kh / 2;
+                    const int dx = tap % p.kw - p.kw / 2;
+                    uint8_t* a_dst = smem + stage * stage_bytes + j * pair_bytes;
+                    ptx::tma_load_4d(a_dst, &tmA, &full_bar[stage], a_c0 + kc * KC, t.w0 + dx, t.h0 + dy, t.b0);
+                    ptx::tma_load_2d(a_dst + kABufBytes, &tmB, &full_bar[stage], tap * p.cin_g + kc * KC, b_row);
+                }
+                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        const uint32_t idesc = ptx::make_idesc_bf16(kTileM, p.n_tile);
+        const uint32_t smem_base = ptx::smem_u32(smem);
+        uint32_t stage = 0, phase = 0;
+        for (int it0 = it_begin; it0 < it_end; it0 += p.sub) {
+            const int cnt = min(p.sub, it_end - it0);
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tcgen05_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t s_addr = smem_base + stage * stage_bytes;
+                for (int j = 0; j < cnt; ++j) {
+                    const uint64_t a_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes, kRowBytes);
+                    const uint64_t b_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes + kABufBytes, kRowBytes);
+                    ptx::umma_bf16_ss(tmem_base, a_desc, b_desc, idesc, (it0 + j) > it_begin ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 1; ks < KC / 16; ++ks)
+                        ptx::umma_bf16_ss_acc(tmem_base, a_desc + 2 * ks, b_desc + 2 * ks, idesc);
+                }
+                ptx::umma_commit(&empty_bar[stage]);
+            }
+            __syncwarp();
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (ptx::elect_one()) ptx::umma_commit(&tmem_full_bar);
+        __syncwarp();
+    }
+
+    // ---- reduction handshake: every thread of the cluster passes two cluster barriers ----
+    //   B1: ranks > 0 have parked their partial tile in shared memory;  B2: rank 0 has finished reading them
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t stage_area = ptx::smem_u32(smem);              // same offset in every CTA of the cluster
+    if (warp >= 2) {
+        ptx::grid_dependency_wait();
+        ptx::mbar_wait(&tmem_full_bar, 0);                        // this CTA's MMAs are complete: its pipeline smem is idle
+        ptx::tcgen05_fence_after();
+        if (krank > 0) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 0; c0 < p.n_tile; c0 += kChunk) {
+                uint32_t r[kChunk];
+                tmem_ld_chunk<kChunk>(taddr + c0, r, c0 + 32 > p.n_tile);
+                ptx::tmem_ld_wait();
+                float4* dst = reinterpret_cast<float4*>(smem + (size_t)(((c0 / kChunk) * kTileM + row) * kChunk) * 4);
+#pragma unroll
+                for (int i = 0; i < kChunk / 4; ++i)
+                    dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                         __uint_as_float(r[4 * i + 3]));
+            }
+        }
+    }
+    cluster_arrive_release();
+    cluster_wait_acquire();
+    if (warp >= 2 && krank == 0) {
+        const int ww = row % p.wt;
+        const int hh = (row / p.wt) % p.ht;
+        const int bb = row / (p.wt * p.ht);
+        const int b = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
+        const bool valid = (bb < p.bt) && (b < p.B) && (h < p.H) && (w < p.W);
+        const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        epilogue_tile<4>(p, taddr, valid, b, h, w, ch0, stage_area, row);
+    }
+    cluster_arrive_release();
+    cluster_wait_acquire();
 
     ptx::tcgen05_fence_before();
     __syncthreads();
@@ -737,9 +921,39 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.kchunks = cin_g / KC;
     p.k_iters = p.taps * p.kchunks;
     p.n_tile = choose_n_tile(cout_g, p.m_tiles, groups, p.k_iters, KC, num_sms);
-    if (const char* f = getenv("DD_FORCE_NTILE")) {            // tuning experiments only
-        const int n = atoi(f);
-        if (n >= 16 && n <= 256 && n % 16 == 0 && cout_g % n == 0) p.n_tile = n;
+    p.ksplit = 1;
+    {
+        // Small-M layers: consider sharing one tile between the CTAs of a cluster (split-K, conv_igemm_splitk_kernel).
+        // Same cost model as choose_n_tile plus the distributed-shared-memory reduction; clusters are confined to a GPC
+        // (~18 SMs), which limits how many are co-resident.
+        // Measured on B200 (gpurun_out/bench_convs_splitk.json): correct, but 1.2-3x SLOWER than the single-CTA tiles at
+        // these sizes (cluster launch + two cluster barriers + GPC-confined residency outweigh the shorter k-loop), so
+        // the variant is opt-in (DD_ENABLE_SPLITK=1) until the reduction is overlapped; the default path is unchanged.
+        static const bool no_split = getenv("DD_ENABLE_SPLITK") == nullptr;
+        auto cost = [&](int n, int S) {
+            const long ctas = (long)p.m_tiles * groups * (cout_g / n) * S;
+            const long cap = S == 1 ? num_sms : (long)std::max(1, (num_sms / 8) / S) * S * 8;
+            const long waves = (ctas + cap - 1) / cap;
+            const double t_l2 = (128.0 + n) * KC * 2.0 / 36.0, t_mma = n * KC / 32.0;
+            const double t_iter = std::max(t_l2, t_mma) + 30.0;
+            const double red = S == 1 ? 0.0 : 1500.0 + 60.0 * (S - 1) * (n / 16.0);
+            return 2500.0 + waves * (((p.k_iters + S - 1) / S) * t_iter) + 64.0 + n * 6.0 + red + (waves - 1) * 200.0;
+        };
+        const double base = cost(p.n_tile, 1);
+        double best = base * 0.85;                      // only switch for a clear predicted win
+        if (!no_split && (long)p.m_tiles * groups <= 64 && p.epi2 != DD_EPI2_RAW) {
+            for (int n = 16; n <= std::min(cout_g, 256); n += 16) {
+                if (cout_g % n) continue;
+                for (int S = 2; S <= 8 && 2 * S <= p.k_iters; ++S) {
+                    const double c = cost(n, S);
+                    if (c < best) { best = c; p.n_tile = n; p.ksplit = S; }
+                }
+            }
+        }
+        if (const char* f = getenv("DD_FORCE_KSPLIT")) {                          // tuning experiments only
+            const int S = atoi(f);
+            if (S >= 1 && S <= 8 && 2 * S <= p.k_iters) p.ksplit = S;
+        }
     }
     p.n_tiles_per_group = cout_g / p.n_tile;
     p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
@@ -784,6 +998,39 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     }
 
     const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024;
+    if (p.ksplit > 1) {
+        // rank > 0 parks 128 x n_tile fp32 in its pipeline shared memory: must fit
+        const size_t staging = (size_t)((p.n_tile + 31) / 32) * kTileM * 32 * 4;
+        if (staging > (size_t)p.stages * stage_bytes) p.ksplit = 1;
+    }
+    if (p.ksplit > 1) {
+        if (getenv("DD_DEBUG_CONV"))
+            fprintf(stderr, "[conv split-K] B%d %dx%d %d->%d k%d g%d: m_tiles %d n_tile %d tiles %d k_iters %d ksplit %d stages %d\n",
+                    B, H, W, Cin, Cout, p.kw, groups, p.m_tiles, p.n_tile, p.num_tiles, p.k_iters, p.ksplit, p.stages);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(p.num_tiles * p.ksplit);
+        cfg.blockDim = dim3(64 + 32 * 4);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = p.ksplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = getenv("DD_DISABLE_PDL") ? 1 : 2;
+        if (KC == 64) {
+            static bool done = false;
+            if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_splitk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
+            DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_splitk_kernel<64>, tmA, tmB, p));
+        } else {
+            static bool done = false;
+            if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_splitk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
+            DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_splitk_kernel<32>, tmA, tmB, p));
+        }
+        DD_CHECK_LAUNCH();
+        return 0;
+    }
     const int grid = std::min(p.num_tiles, num_sms);
     if (getenv("DD_DEBUG_CONV"))
         fprintf(stderr, "[conv] B%d %dx%d %d->%d k%d g%d: box %dx%dx%d m_tiles %d n_tile %d tiles %d k_iters %d KC %d sub %d stages %d\n",
@@ -846,6 +1093,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     const uint32_t b_total = (uint32_t)p.kchunks * 9u * p.b_block_bytes;
     p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((budget - b_total) / p.halo_stride)));
     p.nacc = 1;
+    p.ksplit = 1;
     p.dbg_taps = 9;
     p.dbg_nostore = getenv("DD_DBG_NOSTORE") != nullptr;
     p.nbuf = 2;
