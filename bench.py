@@ -465,7 +465,12 @@ def run_ours(args) -> None:
             fl_all, tt_all = sum(f for f, _ in allc), sum(t for _, t in allc)
             roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05 implicit-GEMM MPConv, 3x3 grouped, levels 0-2)",
                     "achieved": fl / tt / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": fl / tt / 1e12 / pk["tflops"],
-                    "traffic": None, "launches": len(halo), "avg_launch_us": tt / max(1, len(halo)) * 1e6,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed
+                    # `ncu --set full` capture (2x32x688, 512->256 grouped 3x3: 45.47 MB read + 0.29 MB written back inside
+                    # the capture window; algorithmic 45.1 MB in + 22.5 MB out) -- no DRAM re-reads of the activations
+                    "traffic": 45.76e6, "traffic_source": "profiles/r01_ncu_halo_512to256_full_summary.csv (one launch, "
+                                                          "512->256 layer; algorithmic 67.6 MB incl. the output write-back)",
+                    "launches": len(halo), "avg_launch_us": tt / max(1, len(halo)) * 1e6,
                     "flop_per_launch_avg": fl / max(1, len(halo)), "peak_source": pk["source"] + " (bf16 sustained)",
                     "all_mpconv": {"achieved": fl_all / tt_all / 1e12, "launches": len(allc),
                                    "share_of_unet_call": tt_all / (ms * 1e-3 / K / 2)},
