@@ -2,8 +2,9 @@
 (`modules.formats.ms_mdct_dual.MS_MDCT_DualFormat`, src/modules/formats/ms_mdct_dual.py:36-257):
 `raw_to_mel_spec`, the shape helpers, and `ms_freq_scale.get_unscaled` (the UNet's positional channel reads it,
 unet_edm2_b4.py:246).  The two-window magnitude STFT, per-bin blend, 1/mel-density, slaney mel filterbank and the
-output affine run as ONE kernel launch (`dd_stft_mel` with a second window).  The MDCT / PSD methods of the
-reference class are not on this round's path and raise NotImplementedError.
+output affine run as ONE kernel launch (`dd_stft_mel` with a second window).  The MDCT side (`raw_to_mdct`,
+`raw_to_mdct_psd`, `mdct_to_raw`, `mel_spec_to_mdct_psd`) runs each transform as one fp32 library GEMM
+against a host-built (fp64) matrix with framing / |.| / overlap-add kernels around it (csrc/mdct.cu).
 """
 from __future__ import annotations
 
@@ -197,11 +198,141 @@ class MS_MDCT_DualFormat(DualDiffusionFormat):
                            c.raw_to_mel_spec_scale, window2=t["window2"], coef1=t["coef1"], coef2=t["coef2"])
         return out.view(B, C, c.ms_num_frequencies, out.shape[-1])
 
-    def mel_spec_to_mdct_psd(self, mel_spec: torch.Tensor):
-        raise NotImplementedError("MDCT / PSD side of MS_MDCT_DualFormat is not on this round's path (SURVEY N1)")
+    # ---- MDCT side (ms_mdct_dual.py:259-318; utils/mclt.py:87-130) ----
+    def _mdct_tables(self, device: torch.device) -> dict:
+        """Host-built (fp64) transform matrices.  forward  Mt [2N][2N]: rows 0..N-1 = Re, N..2N-1 = Im of
+        window * pre-shift * DFT * post-shift * 2 sqrt(N) / (2N) * raw_to_mdct_scale / mel_density[k];
+        inverse  St [2N][2N]: rows 0..N-1 multiply Re(x), N..2N-1 multiply Im(x), columns = the 2N samples of a frame,
+        with mel_density / raw_to_mdct_scale, 2 sqrt(N) and mdct_to_raw_scale folded in;
+        P [bins][filters]: min-norm inverse mel filterbank (lstsq(gels), frequency_scale.py:136) times mel_spec_to_mdct_psd_scale."""
+        key = "mdct:" + str(device)
+        t = self._dev_cache.get(key)
+        if t is not None:
+            return t
+        c = self.config
+        if c.mdct_window_func != "kaiser_bessel_derived":
+            raise NotImplementedError(f"mdct_window_func {c.mdct_window_func!r} is not implemented (default: kaiser_bessel_derived)")
+        N = c.mdct_window_len // 2
+        kais = torch.kaiser_window(N + 1, beta=4.0, periodic=False).double()          # utils/mclt.py:44-62
+        cs = torch.cumsum(kais[:-1] ** 2, dim=0)
+        half = torch.sqrt(cs / cs[-1]).numpy()
+        w = np.concatenate([half, half[::-1]])
+        n = np.arange(2 * N, dtype=np.float64)[:, None]
+        k = np.arange(N, dtype=np.float64)[None, :]
+        hz = (np.arange(N) + 0.5) * c.sample_rate / c.mdct_window_len
+        dens = 1127.0 / (700.0 + hz)
+        fwd = (w[:, None] * np.exp(-1j * np.pi * n / (2 * N)) * np.exp(-2j * np.pi * k * n / (2 * N)) / (2 * N)
+               * np.exp(-1j * np.pi * (N + 1) * (k + 0.5) / (2 * N)) * 2 * np.sqrt(N) * (c.raw_to_mdct_scale / dens)[None, :])
+        phi = np.pi * (N + 1) * (k + 0.5) / (2 * N) + 2 * np.pi * k * n / (2 * N) + np.pi * n / (2 * N)
+        gsc = (dens / c.raw_to_mdct_scale)[None, :] * 2 * np.sqrt(N) * c.mdct_to_raw_scale
+        s_re = w[:, None] / (2 * N) * np.cos(phi) * gsc
+        s_im = -w[:, None] / (2 * N) * np.sin(phi) * gsc
+        if c.mdct_psd_num_bins == c.ms_num_stft_bins - 1:
+            fb = self.ms_freq_scale.get_filters()
+        else:
+            fb = FrequencyScale(c.ms_freq_min, c.sample_rate / 2, c.sample_rate, c.mdct_psd_num_bins, c.ms_num_frequencies,
+                                "slaney").get_filters()
+        a64 = fb.double().numpy().T                                                     # (filters, bins)
+        gram = a64 @ a64.T
+        if np.linalg.cond(gram) > 1e12:
+            raise ValueError("mel filterbank is rank deficient: min-norm inverse undefined")
+        pinv = a64.T @ np.linalg.inv(gram) * c.mel_spec_to_mdct_psd_scale
+        to = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(device)
+        t = dict(N=N, fwd=to(np.concatenate([fwd.real.T, fwd.imag.T], 0)), inv=to(np.concatenate([s_re.T, s_im.T], 0)),
+                 pinv=to(pinv))
+        self._dev_cache[key] = t
+        return t
 
-    def raw_to_mdct(self, *args, **kwargs):
-        raise NotImplementedError("MDCT side of MS_MDCT_DualFormat is not on this round's path (SURVEY N1)")
+    @staticmethod
+    def _gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """Plain fp32 library GEMM (cuBLAS) with TF32 off (the reference's format is fp32-only, format.py:40)."""
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            return torch.matmul(a, b)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
 
-    def mdct_to_raw(self, *args, **kwargs):
-        raise NotImplementedError("MDCT side of MS_MDCT_DualFormat is not on this round's path (SURVEY N1)")
+    def _get_mdct_raw_crop_width(self, raw_length: Optional[int] = None) -> int:
+        c = self.config
+        raw_length = raw_length or c.default_raw_length
+        return raw_length // c.mdct_window_len // c.ms_width_alignment * c.ms_width_alignment * c.mdct_window_len + c.mdct_window_len
+
+    def get_mdct_shape(self, bsz: int = 1, raw_length: Optional[int] = None) -> tuple:
+        c = self.config
+        n_bins = c.mdct_window_len // 2
+        return (bsz, c.num_raw_channels * (2 if c.mdct_dual_channel else 1), n_bins,
+                self.get_raw_crop_width(raw_length=raw_length) // n_bins + 1)
+
+    def _check_no_high_pass(self) -> None:
+        c = self.config
+        if c.ms_freq_min > 0 and (self.ms_lowest_filter_freq - c.ms_freq_min) > 0:
+            raise NotImplementedError("ms_freq_min > 0 (full-length FFT high-pass, :190-207) is not implemented")
+
+    def _mclt_rows(self, raw_samples: torch.Tensor) -> torch.Tensor:
+        """(B, C, L) -> [B*C][2N][T]: real rows then imaginary rows of the scaled, density-weighted MCLT."""
+        self._check_no_high_pass()
+        L.require_cuda(raw_samples)
+        t = self._mdct_tables(raw_samples.device)
+        N = t["N"]
+        B, C, n = raw_samples.shape
+        raw = raw_samples.detach().float().contiguous().view(B * C, n)
+        rem = n % N
+        padded = n + 2 * N + (N - rem if rem else 0)
+        T = (padded - 2 * N) // N + 1
+        frames = ops.frame_reflect(raw, 2 * N, N, N, T)                      # [S][T][2N]
+        return self._gemm(t["fwd"], frames.transpose(-1, -2))               # [S][2N][T]
+
+    @torch.no_grad()
+    def raw_to_mdct(self, raw_samples: torch.Tensor, random_phase_augmentation: bool = False) -> torch.Tensor:
+        """ms_mdct_dual.py:283-298 -> (B, C, N, T), or (B, 2C, N, T) = [real | imag] when mdct_dual_channel."""
+        if random_phase_augmentation:
+            raise NotImplementedError("random_phase_augmentation (training-time augmentation) is not implemented")
+        B, C, _ = raw_samples.shape
+        y = self._mclt_rows(raw_samples)
+        N, T = y.shape[1] // 2, y.shape[2]
+        if self.config.mdct_dual_channel:
+            return y.view(B, C, 2, N, T).permute(0, 2, 1, 3, 4).reshape(B, 2 * C, N, T)
+        return y[:, :N].reshape(B, C, N, T)
+
+    @torch.no_grad()
+    def raw_to_mdct_psd(self, raw_samples: torch.Tensor) -> torch.Tensor:
+        """ms_mdct_dual.py:300-306."""
+        B, C, _ = raw_samples.shape
+        y = self._mclt_rows(raw_samples)
+        out = ops.complex_abs(y.contiguous(), 1.0 / math.sqrt(2.0))
+        return out.view(B, C, out.shape[1], out.shape[2])
+
+    @torch.no_grad()
+    def mdct_to_raw(self, mdct: torch.Tensor) -> torch.Tensor:
+        """ms_mdct_dual.py:308-318 -> (B, C, (T-1)*N)."""
+        L.require_cuda(mdct)
+        t = self._mdct_tables(mdct.device)
+        N = t["N"]
+        x = mdct.detach().float()
+        B, Cx, Nb, T = x.shape
+        if Nb != N:
+            raise ValueError(f"expected {N} MDCT bins, got {Nb}")
+        if self.config.mdct_dual_channel:
+            C = Cx // 2
+            x = torch.cat((x[:, :C], x[:, C:]), dim=2)                       # [B][C][2N (re | im)][T]
+            mat = t["inv"]
+        else:
+            C = Cx
+            mat = t["inv"][:N]
+        y = self._gemm(x.reshape(B * C, -1, T).transpose(-1, -2), mat)       # [S][T][2N]
+        return ops.mdct_ola(y.contiguous()).view(B, C, -1)
+
+    @torch.no_grad()
+    def mel_spec_to_mdct_psd(self, mel_spec: torch.Tensor) -> torch.Tensor:
+        """ms_mdct_dual.py:259-270 -> (B, C, mdct_psd_num_bins, T)."""
+        L.require_cuda(mel_spec)
+        c = self.config
+        t = self._mdct_tables(mel_spec.device)
+        lin = ops.mel_linearize(mel_spec.detach().float().contiguous(), c.raw_to_mel_spec_offset, 1.0 / c.ms_abs_exponent)
+        psd = self._gemm(t["pinv"], lin)                                     # [B][C][bins][T]
+        if c.mdct_psd_num_bins == c.ms_num_stft_bins - 1:
+            psd = psd[:, :, :-1, :]
+        if c.mel_spec_to_mdct_psd_offset != 0:
+            psd = psd + c.mel_spec_to_mdct_psd_offset
+        return psd

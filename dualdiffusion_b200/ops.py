@@ -611,3 +611,37 @@ def q4_stem(x_in: Tensor, x_ref: Tensor, sigma: Tensor, sigma_data: float, wa: f
                                 cpad, L.stream_ptr()))
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# MDCT side of the live format (framing / |.| / overlap-add / mel linearisation around a library GEMM)
+# ---------------------------------------------------------------------------------------------------------
+def frame_reflect(raw: Tensor, block_width: int, hop: int, pad_left: int, n_frames: int) -> Tensor:
+    S, Ln = raw.shape
+    out = torch.empty((S, n_frames, block_width), device=raw.device, dtype=torch.float32)
+    L.check(L.load().dd_frame_reflect(L.ptr(raw), L.ptr(out), S, Ln, n_frames, block_width, hop, pad_left, L.stream_ptr()))
+    _count()
+    return out
+
+
+def complex_abs(y: Tensor, scale: float) -> Tensor:
+    S, N2, T = y.shape
+    out = torch.empty((S, N2 // 2, T), device=y.device, dtype=torch.float32)
+    L.check(L.load().dd_complex_abs(L.ptr(y), L.ptr(out), S, N2 // 2, T, scale, L.stream_ptr()))
+    _count()
+    return out
+
+
+def mdct_ola(y: Tensor) -> Tensor:
+    S, T, N2 = y.shape
+    out = torch.empty((S, (T - 1) * (N2 // 2)), device=y.device, dtype=torch.float32)
+    L.check(L.load().dd_mdct_ola(L.ptr(y), L.ptr(out), S, T, N2 // 2, L.stream_ptr()))
+    _count()
+    return out
+
+
+def mel_linearize(mel: Tensor, offset: float, inv_exponent: float) -> Tensor:
+    out = torch.empty_like(mel)
+    L.check(L.load().dd_mel_linearize(L.ptr(mel), L.ptr(out), mel.numel(), offset, inv_exponent, L.stream_ptr()))
+    _count()
+    return out

@@ -364,6 +364,21 @@ DD_API int dd_ddec_head(const void* f, const float* x_in, const float* sigma, fl
 DD_API int dd_q4_stem(const float* x_in, const float* x_ref, const float* sigma, float sigma_data, float wa, float wb,
                       void* out, int B, int C, int F, int W, int k, int Cpad, void* stream);
 
+/* ==== MDCT side of the live format (utils/mclt.py:87-130, modules/formats/ms_mdct_dual.py:259-318).
+ * The MCLT / inverse MCLT of all frames is one fp32 library GEMM against a host-built matrix (window, phase shifts,
+ * 1/mel-density and scales folded in); these kernels do the framing, |.|, overlap-add and mel linearisation around it. */
+
+/* mclt.py:90-95: out[s][t][n] = reflect-padded raw[s][t*hop + n - pad_left]; raw [S][L] fp32, out [S][T][block_width]. */
+DD_API int dd_frame_reflect(const float* raw, float* out, int S, long L, int T, int block_width, int hop, int pad_left,
+                            void* stream);
+/* ms_mdct_dual.py:300-306: |re + i im| * scale; y [S][2N][T] (real rows, then imaginary rows) -> out [S][N][T].       */
+DD_API int dd_complex_abs(const float* y, float* out, int S, int N, int T, float scale, void* stream);
+/* mclt.py:123-130: 50 %-overlap add of the inverse frames y [S][T][2N] with the first / last half block cropped ->
+ * out [S][(T-1)*N].                                                                                                   */
+DD_API int dd_mdct_ola(const float* y, float* out, int S, int T, int N, void* stream);
+/* ms_mdct_dual.py:261-265: out = clip(mel - offset, 0) ** inv_exponent.                                               */
+DD_API int dd_mel_linearize(const float* mel, float* out, long n, float offset, float inv_exponent, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,3 +213,123 @@ def raw_to_mel_spec(raw: Tensor, spec: MSDualSpec) -> Tensor:
         blended = low
     mel = torch.matmul((blended / density).transpose(-1, -2), ms_mel_filterbank(spec)).transpose(-1, -2)
     return mel ** spec.ms_abs_exponent * spec.raw_to_mel_spec_scale + spec.raw_to_mel_spec_offset   # :256-257
+
+
+# --------------------------------------------------------------------------------------
+# live format, MDCT side: utils/mclt.py:87-130 and
+# MS_MDCT_DualFormat.{mel_spec_to_mdct_psd, raw_to_mdct, raw_to_mdct_psd, mdct_to_raw} (ms_mdct_dual.py:259-325)
+# --------------------------------------------------------------------------------------
+@dataclass
+class MDCTSpec:
+    """ms_mdct_dual.py:36-66 defaults (MDCT side)."""
+    sample_rate: int = 32000
+    mdct_window_len: int = 512
+    mdct_psd_num_bins: int = 2048
+    mdct_dual_channel: bool = False
+    raw_to_mdct_scale: float = 12.1
+    mdct_to_raw_scale: float = 2
+    mel_spec_to_mdct_psd_scale: float = 0.18
+    mel_spec_to_mdct_psd_offset: float = 0
+
+    @property
+    def num_bins(self) -> int:
+        return self.mdct_window_len // 2
+
+
+def kbd_window(n: int, beta: float = 4.0) -> Tensor:
+    """WindowFunction.kaiser_bessel_derived (utils/mclt.py:44-62)."""
+    k = torch.kaiser_window(n // 2 + 1, beta=beta, periodic=False)
+    c = torch.cumsum(k[:-1] ** 2, dim=0)
+    half = torch.sqrt(c / c[-1])
+    return torch.cat((half, half.flip(0)), dim=0)
+
+
+def mclt(x: Tensor, block_width: int) -> Tensor:
+    """utils/mclt.py:87-109 with the kaiser-bessel-derived window, exponent 1: (..., L) -> (..., frames, N) complex."""
+    pad_l = pad_r = block_width // 2
+    rem = x.shape[-1] % (block_width // 2)
+    if rem > 0:
+        pad_r += block_width // 2 - rem
+    x = torch.nn.functional.pad(x, (pad_l, pad_r), mode="reflect").unfold(-1, block_width, block_width // 2)
+    n_bins = block_width // 2
+    n = torch.arange(2 * n_bins)
+    k = torch.arange(0.5, n_bins + 0.5)
+    pre = torch.exp(-1j * torch.pi / 2 / n_bins * n)
+    post = torch.exp(-1j * torch.pi / 2 / n_bins * (n_bins + 1) * k)
+    return torch.fft.fft(x * pre * kbd_window(2 * n_bins), norm="forward")[..., :n_bins] * post * (2 * n_bins ** 0.5)
+
+
+def imclt(x: Tensor) -> Tensor:
+    """utils/mclt.py:111-130: (..., frames, N) complex -> (..., (frames-1)*N) complex."""
+    n_bins = x.shape[-1]
+    n = torch.arange(2 * n_bins)
+    k = torch.arange(0.5, n_bins + 0.5)
+    pre = torch.exp(-1j * torch.pi / 2 / n_bins * n)
+    post = torch.exp(-1j * torch.pi / 2 / n_bins * (n_bins + 1) * k)
+    y = (torch.fft.ifft(x / post, norm="backward", n=2 * n_bins) / pre) * kbd_window(2 * n_bins)
+    total = (y.shape[-2] + 1) * y.shape[-1] // 2
+    out = torch.zeros(y.shape[:-2] + (total,), dtype=y.dtype)
+    even = y[..., ::2, :].reshape(*y[..., ::2, :].shape[:-2], -1)
+    odd = y[..., 1::2, :].reshape(*y[..., 1::2, :].shape[:-2], -1)
+    out[..., :even.shape[-1]] = even
+    out[..., n_bins:odd.shape[-1] + n_bins] += odd
+    return out[..., n_bins:-n_bins] * (2 * n_bins ** 0.5)
+
+
+def mdct_mel_density(spec: MDCTSpec) -> Tensor:
+    hz = (torch.arange(spec.num_bins) + 0.5) * spec.sample_rate / spec.mdct_window_len      # ms_mdct_dual.py:177-179
+    return (1127.0 / (700.0 + hz)).view(1, 1, -1, 1)
+
+
+def raw_to_mdct(raw: Tensor, spec: MDCTSpec) -> Tensor:
+    """ms_mdct_dual.py:283-298 (ms_freq_min == 0: no high-pass; no phase augmentation)."""
+    m = mclt(raw.float(), spec.mdct_window_len).permute(0, 1, 3, 2)
+    if spec.mdct_dual_channel:
+        m = torch.cat((m.real, m.imag), dim=1)
+    else:
+        m = m.real
+    return m / mdct_mel_density(spec) * spec.raw_to_mdct_scale
+
+
+def raw_to_mdct_psd(raw: Tensor, spec: MDCTSpec) -> Tensor:
+    """ms_mdct_dual.py:300-306."""
+    m = mclt(raw.float(), spec.mdct_window_len).permute(0, 1, 3, 2)
+    return m.abs() / mdct_mel_density(spec) * spec.raw_to_mdct_scale / 2 ** 0.5
+
+
+def mdct_to_raw(mdct: Tensor, spec: MDCTSpec) -> Tensor:
+    """ms_mdct_dual.py:308-318."""
+    m = mdct * mdct_mel_density(spec) / spec.raw_to_mdct_scale
+    if spec.mdct_dual_channel:
+        m = torch.complex(*m.chunk(2, dim=1))
+    return imclt(m.permute(0, 1, 3, 2).to(torch.complex64)).real * spec.mdct_to_raw_scale
+
+
+def mel_spec_to_mdct_psd(mel_spec: Tensor, ms: MSDualSpec, spec: MDCTSpec) -> Tensor:
+    """ms_mdct_dual.py:259-270: min-norm inverse of the mel filterbank (torch.linalg.lstsq, frequency_scale.py:136) of
+    the linearised mel spectrogram; the PSD has ms.num_stft_bins - 1 bins (last bin cropped) when that equals
+    mdct_psd_num_bins, otherwise its own filterbank with mdct_psd_num_bins STFT bins."""
+    lin = (mel_spec - ms.raw_to_mel_spec_offset).float().clip(min=0) ** (1 / ms.ms_abs_exponent)
+    if spec.mdct_psd_num_bins == ms.num_stft_bins - 1:
+        fb, crop = ms_mel_filterbank(ms), True
+    else:
+        fb, crop = _mel_filterbank_bins(ms, spec.mdct_psd_num_bins), False
+    shape = lin.shape
+    sol = torch.linalg.lstsq(fb.t()[None], lin.reshape(-1, shape[-2], shape[-1]), driver="gels").solution   # :136, driver gels
+    sol = sol.view(shape[:-2] + (fb.shape[0], shape[-1]))
+    if crop:
+        sol = sol[:, :, :-1, :]
+    return sol * spec.mel_spec_to_mdct_psd_scale + spec.mel_spec_to_mdct_psd_offset
+
+
+def _mel_filterbank_bins(spec: MSDualSpec, num_stft_bins: int) -> Tensor:
+    """ms_mel_filterbank with an explicit number of STFT bins (the ms_freq_scale_mdct_psd scale, ms_mdct_dual.py:158-168)."""
+    lo = 2595.0 * math.log10(1.0 + spec.ms_freq_min / 700.0)
+    hi = 2595.0 * math.log10(1.0 + (spec.sample_rate / 2) / 700.0)
+    f_pts = 700.0 * (10.0 ** (torch.linspace(lo, hi, spec.ms_num_frequencies + 2) / 2595.0) - 1.0)
+    all_freqs = torch.linspace(0, spec.sample_rate / 2, num_stft_bins)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    fb = torch.max(torch.zeros(1), torch.min((-1.0 * slopes[:, :-2]) / f_diff[:-1], slopes[:, 2:] / f_diff[1:]))
+    enorm = 2.0 / (f_pts[2:spec.ms_num_frequencies + 2] - f_pts[:spec.ms_num_frequencies])
+    return fb * enorm.unsqueeze(0)

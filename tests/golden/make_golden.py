@@ -187,6 +187,19 @@ def main():
                     crop_default=fmt.get_raw_crop_width(), unscaled_34=fmt.ms_freq_scale.get_unscaled(34)),
                os.path.join(OUT, "ms_dual_small.pt"))
 
+    # ---- live format, MDCT side (ms_mdct_dual.py:259-318): default config and dual-channel / 4096-bin PSD variant ----
+    g = torch.Generator().manual_seed(9)
+    raw = 0.1 * torch.randn(1, 2, 256 * 19 + 100, generator=g)                # ragged length: remainder padding path
+    raw[0, 1] += 0.2 * torch.sin(2 * torch.pi * 1000.0 * torch.arange(raw.shape[-1]) / 32000.0)
+    mdct_cases = {}
+    for tag, kw in (("default", {}), ("dual4096", dict(mdct_dual_channel=True, mdct_psd_num_bins=4096))):
+        f2 = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig(**kw))
+        mdct = f2.raw_to_mdct(raw)
+        mel = f2.raw_to_mel_spec(raw)
+        mdct_cases[tag] = dict(kwargs=kw, mdct=mdct, psd=f2.raw_to_mdct_psd(raw), raw_back=f2.mdct_to_raw(mdct),
+                               mel=mel, mel_psd=f2.mel_spec_to_mdct_psd(mel), mdct_shape=f2.get_mdct_shape(3))
+    torch.save(dict(raw=raw, cases=mdct_cases), os.path.join(OUT, "mdct_small.pt"))
+
     # ---- sigma schedules ----
     sched = {n: SamplingSchedule.get_schedule(n, 10, 1.0, sigma_max=200.0, sigma_min=0.03, rho=7.0)
              for n in ("edm2", "ln_linear", "linear", "cos", "scale_invariant")}

@@ -197,3 +197,15 @@ def test_q4_ddec_oracle_vs_golden_reference():
         d = dd.q4_forward(sd, spec, g["x"], g["sigma"], g["x_ref"], dt)
         assert rel_err(d, g["d"]) < tol
         assert rel_err(d - c_skip * g["x"], g["d"] - c_skip * g["x"]) < 3 * tol
+
+
+def test_mdct_oracle_vs_golden_reference():
+    """MCLT / inverse MCLT / PSD / mel -> PSD restatements against the reference's own outputs."""
+    from oracle import format_oracle as fo
+    g = load_golden("mdct_small.pt")
+    for tag, c in g["cases"].items():
+        spec = fo.MDCTSpec(**c["kwargs"])
+        assert rel_err(fo.raw_to_mdct(g["raw"], spec), c["mdct"]) < 1e-6, tag
+        assert rel_err(fo.raw_to_mdct_psd(g["raw"], spec), c["psd"]) < 1e-6, tag
+        assert rel_err(fo.mdct_to_raw(c["mdct"], spec), c["raw_back"]) < 1e-6, tag
+        assert rel_err(fo.mel_spec_to_mdct_psd(c["mel"], fo.MSDualSpec(), spec), c["mel_psd"]) < 1e-5, tag
