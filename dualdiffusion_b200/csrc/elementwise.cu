@@ -366,7 +366,7 @@ __global__ void sampler_cfg_lerp_kernel(const float4* __restrict__ d, const floa
                                         float t_hat, float4* __restrict__ cfg_out, float4* __restrict__ xhat, int dup,
                                         long n4) {
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
-        const float4 c = d[i], u = d[i + n4], s = sample[i];
+        const float4 c = d[i], u = (dup & 2) ? c : d[i + n4], s = sample[i];      // bit 1: unconditional (no CFG pair)
         float4 o, x;
         o.x = u.x + cfg * (c.x - u.x); o.y = u.y + cfg * (c.y - u.y);
         o.z = u.z + cfg * (c.z - u.z); o.w = u.w + cfg * (c.w - u.w);
@@ -375,7 +375,7 @@ __global__ void sampler_cfg_lerp_kernel(const float4* __restrict__ d, const floa
         cfg_out[i] = o;
         if (xhat) {
             xhat[i] = x;
-            if (dup) xhat[i + n4] = x;
+            if (dup & 1) xhat[i + n4] = x;
         }
     }
 }
@@ -386,7 +386,7 @@ __global__ void sampler_update_kernel(const float4* __restrict__ cfg1, const flo
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 o = cfg1[i];
         if (use_heun) {
-            const float4 c = d2[i], u = d2[i + n4];
+            const float4 c = d2[i], u = (dup & 2) ? c : d2[i + n4];
             o.x = o.x + 0.5f * ((u.x + cfg * (c.x - u.x)) - o.x);
             o.y = o.y + 0.5f * ((u.y + cfg * (c.y - u.y)) - o.y);
             o.z = o.z + 0.5f * ((u.z + cfg * (c.z - u.z)) - o.z);
@@ -400,7 +400,7 @@ __global__ void sampler_update_kernel(const float4* __restrict__ cfg1, const flo
             s.x += p * nz.x; s.y += p * nz.y; s.z += p * nz.z; s.w += p * nz.w;
         }
         sample[i] = s;
-        if (dup) sample[i + n4] = s;
+        if (dup & 1) sample[i + n4] = s;
         if (cfg_out) cfg_out[i] = o;
     }
 }

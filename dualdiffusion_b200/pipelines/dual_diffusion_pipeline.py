@@ -80,13 +80,19 @@ class EDMSamplerState:
         device = sample.device
         B = params.batch_size
         self.B = B
+        # unconditional modules (get_embeddings -> None, e.g. the ddec UNets) run one copy of the batch and no CFG
+        # (pipeline.py:659-664, :703-704, :713-720)
+        self.uncond = emb is None
+        rep = 1 if self.uncond else 2
+        self.flags = 2 if self.uncond else 1          # dd_sampler_* `dup` bits: 0 = duplicate halves, 1 = unconditional
         self.steps = [step_scalars(i, sig[i], sig[i + 1], params) for i in range(params.num_steps)]
-        # device table of the per-call sigma vectors: [step][0 = sigma_curr | 1 = sigma_hat][2B]
-        self.table = torch.tensor([[[sig[i]] * (2 * B), [st["t_hat"] * sig[i]] * (2 * B)]
+        # device table of the per-call sigma vectors: [step][0 = sigma_curr | 1 = sigma_hat][rep * B]
+        self.table = torch.tensor([[[sig[i]] * (rep * B), [st["t_hat"] * sig[i]] * (rep * B)]
                                    for i, st in enumerate(self.steps)], dtype=torch.float32).to(device)
-        self.sample2 = torch.empty((2 * B,) + tuple(sample.shape[1:]), device=device, dtype=torch.float32)
+        self.sample2 = torch.empty((rep * B,) + tuple(sample.shape[1:]), device=device, dtype=torch.float32)
         self.sample2[:B] = sample
-        self.sample2[B:] = sample
+        if not self.uncond:
+            self.sample2[B:] = sample
         self.xhat2 = torch.empty_like(self.sample2)
         self.cfg1 = torch.empty_like(sample)
         self.cfg_out = torch.empty_like(sample) if collect_debug_info else None
@@ -98,16 +104,17 @@ class EDMSamplerState:
     def set_sample(self, sample: torch.Tensor) -> None:
         """Overwrite the current sample (both UNet-batch halves), e.g. from a pinned host buffer."""
         self.sample2[:self.B].copy_(sample, non_blocking=True)
-        self.sample2[self.B:].copy_(sample, non_blocking=True)
+        if not self.uncond:
+            self.sample2[self.B:].copy_(sample, non_blocking=True)
 
     def step(self, i: int, noise: Optional[torch.Tensor]) -> None:
         st, p = self.steps[i], self.params
         d1 = self.unet(self.sample2, self.table[i, 0], self.fmt, self.emb, self.input_ref)
         ops.sampler_cfg_lerp(d1, self.sample2, p.cfg_scale, st["t_hat"], self.cfg1,
-                             self.xhat2 if p.use_heun else None, dup=True)
+                             self.xhat2 if p.use_heun else None, dup=self.flags)
         d2 = self.unet(self.xhat2, self.table[i, 1], self.fmt, self.emb, self.input_ref) if p.use_heun else None
         ops.sampler_update(self.cfg1, d2, p.cfg_scale, p.use_heun, st["t"], st["p"] if noise is not None else 0.0,
-                           noise, self.sample2, self.cfg_out, dup=True)
+                           noise, self.sample2, self.cfg_out, dup=self.flags)
 
 
 class DualDiffusionPipeline(torch.nn.Module):
@@ -136,8 +143,6 @@ class DualDiffusionPipeline(torch.nn.Module):
             raise NotImplementedError("seamless_loop sampling is not implemented on the B200 path")
         if params.stereo_fix > 0:
             raise NotImplementedError("stereo_fix is not implemented on the B200 path")
-        if audio_embedding is None:
-            raise NotImplementedError("unconditional (no class embedding) sampling is not implemented")
         if sample_shape is None and x_ref is None:
             raise ValueError("sample_shape or x_ref is required")
         device = torch.device(unet.device)
@@ -148,7 +153,9 @@ class DualDiffusionPipeline(torch.nn.Module):
         input_ref = None
         if x_ref is not None:
             sample_shape = sample_shape or x_ref.shape
-            input_ref = x_ref.to(device=device, dtype=torch.float32).repeat(2, 1, 1, 1)
+            input_ref = x_ref.to(device=device, dtype=torch.float32)
+            if emb is not None:
+                input_ref = input_ref.repeat(2, 1, 1, 1)                     # pipeline.py:626-629
         sample_shape = tuple(sample_shape)
         schedule = SamplingSchedule.get_schedule(params.schedule, params.num_steps, 1, device="cpu",
                                                  sigma_max=params.sigma_max, sigma_min=params.sigma_min, rho=params.rho)

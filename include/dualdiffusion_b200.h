@@ -210,7 +210,8 @@ DD_API int dd_ola_finalize(const float* ola, const float* env, int n_signals, in
 /* ---- EDM sampler step glue: pipelines/dual_diffusion_pipeline.py:699-737 -------------------- */
 /* n = element count of ONE latent batch (B*C*H*W); d_2b holds [cond ; uncond] = 2n elements.
  * cfg = lerp(D[B:], D[:B], cfg_scale); x_hat = lerp(cfg, sample, t_hat)   (:701, :712).
- * dup != 0 writes x_hat twice ([x_hat ; x_hat], the `.repeat(2,1,1,1)` of :712) into a 2n buffer.     */
+ * dup bit 0 writes x_hat twice ([x_hat ; x_hat], the `.repeat(2,1,1,1)` of :712) into a 2n buffer;
+ * dup bit 1 = unconditional module (unet_class_embeddings is None, :703-704, :719-720): d holds n elements, cfg = D.   */
 DD_API int dd_sampler_cfg_lerp(const float* d_2b, const float* sample, float cfg_scale, float t_hat, float* cfg_out,
                                float* x_hat_out, int dup, long n, void* stream);
 /* cfg2 = lerp(D2[B:], D2[:B], cfg_scale); cfg = use_heun ? lerp(cfg1, cfg2, .5) : cfg1;

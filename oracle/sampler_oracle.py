@@ -66,3 +66,38 @@ def diffusion_decode(sd: Dict[str, Tensor], spec: uo.UNetSpec, audio_embedding: 
                 record["step_noise"].append(nz.clone())
             sample = sample + p * nz
     return sample
+
+
+def diffusion_decode_unconditional(model_fn, sample_shape, *, seed: int, sigma_max: float, sigma_min: float,
+                                   sigma_data: float = 1.0, num_steps: int = 100, rho: float = 7.0, use_heun: bool = True,
+                                   input_perturbation: float = 1.0, input_perturbation_offset: float = 0.0,
+                                   record: Optional[dict] = None) -> Tensor:
+    """pipeline.py:598-752 for a module without class embeddings (`get_embeddings` -> None, e.g. the ddec UNets): one copy
+    of the batch, no classifier-free guidance (:659-664, :703-704, :713-720).  `model_fn(x, sigma[1]) -> D_x`."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sig = schedule_edm2(num_steps, sigma_max, sigma_min, rho).tolist()
+    noise = torch.randn(tuple(sample_shape), generator=gen)
+    if record is not None:
+        record["initial_noise"] = noise.clone()
+        record["step_noise"] = []
+    sample = noise * (sig[0] ** 2 + sigma_data ** 2) ** 0.5
+    for i, (sigma_curr, sigma_next) in enumerate(zip(sig[:-1], sig[1:])):
+        old_sigma_next = sigma_next
+        ipo = np.log(sigma_curr) + input_perturbation_offset
+        eff = (np.tanh(ipo) / 2 + 0.5) * float(input_perturbation)
+        sigma_next *= (1 - (max(min(eff, 1), 0)))
+        cfg = model_fn(sample, torch.tensor([sigma_curr]))
+        if use_heun:
+            sigma_hat = max(old_sigma_next, sigma_min)
+            t_hat = sigma_hat / sigma_curr
+            cfg_h = model_fn(torch.lerp(cfg, sample, t_hat), torch.tensor([t_hat * sigma_curr]))
+            cfg = torch.lerp(cfg, cfg_h, 0.5)
+        t = sigma_next / sigma_curr if (i + 1) < num_steps else 0
+        sample = torch.lerp(cfg, sample, t)
+        if i + 1 < num_steps:
+            p = max(old_sigma_next ** 2 - sigma_next ** 2, 0) ** 0.5
+            nz = torch.randn(sample.shape, generator=gen, dtype=sample.dtype)
+            if record is not None:
+                record["step_noise"].append(nz.clone())
+            sample = sample + p * nz
+    return sample
