@@ -306,6 +306,57 @@ __global__ void q4_stem_kernel(const float* __restrict__ x_in, const float* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// DAE_D3.encode input (dae_edm2_d3.py:344-346 + conv_in (1,5,5), :283): per stereo side the 5x5 patch of [mel, 1]
+// (reflection along W, zeros along H) as 50 values padded to 64 -> [B][H][Wp][128] bf16 (channel z*64 + tap*2 + c);
+// conv_in then runs as a 2-group K = 64 tensor-core GEMM.
+// ------------------------------------------------------------------------------------------
+__global__ void dae_enc_patches_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                       int pw) {
+    const int Wp = W + 2 * pw;
+    const long total = (long)B * H * Wp * 128;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int ch = (int)(idx & 127);
+        long pix = idx >> 7;
+        const int p = (int)(pix % Wp);
+        pix /= Wp;
+        const int h = (int)(pix % H), b = (int)(pix / H);
+        const int z = ch >> 6, k = ch & 63;
+        float v = 0.f;
+        if (k < 50) {
+            const int tap = k >> 1, c = k & 1;
+            const int hh = h + tap / 5 - 2;
+            if (hh >= 0 && hh < H) {
+                const int w = reflect_idx(p - pw, W);
+                const int ww = reflect_idx(w + tap % 5 - 2, W);
+                v = c == 0 ? mel[(((size_t)b * 2 + z) * H + hh) * W + ww] : 1.f;
+            }
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+// DAE_D3.encode tail (:352-354): conv_latents_out result [B][H][Wp][Cst] bf16 (channel z*L + c) -> tensor_5d_to_4d
+// (channel c*2 + z) -> avg_pool2d(ratio) -> fp32 NCHW (B, 2L, H/ratio, W/ratio)
+__global__ void dae_latents_pool_kernel(const __nv_bfloat16* __restrict__ f, float* __restrict__ out, int B, int L, int H,
+                                        int W, int pw, int Cst, int ratio) {
+    const int Ho = H / ratio, Wo = W / ratio, Wp = W + 2 * pw;
+    const long total = (long)B * 2 * L * Ho * Wo;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int wo = (int)(idx % Wo);
+        long r = idx / Wo;
+        const int ho = (int)(r % Ho);
+        r /= Ho;
+        const int c8 = (int)(r % (2 * L)), b = (int)(r / (2 * L));
+        const int c = c8 >> 1, z = c8 & 1;
+        float acc = 0.f;
+        for (int dy = 0; dy < ratio; ++dy)
+            for (int dx = 0; dx < ratio; ++dx)
+                acc += __bfloat162float(f[(((size_t)b * H + ho * ratio + dy) * Wp + wo * ratio + dx + pw) * Cst + z * L + c]);
+        out[idx] = acc / (float)(ratio * ratio);
+    }
+}
+
 }  // namespace
 
 extern "C" int dd_weight_prep_z2(const void* w, int w_is_bf16, void* out, int O, int I, int kz, int taps,
@@ -424,6 +475,29 @@ extern "C" int dd_q4_stem(const float* x_in, const float* x_ref, const float* si
     if (total == 0) return 0;
     q4_stem_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(x_in, x_ref, sigma, sigma_data, wa, wb,
                                                                static_cast<__nv_bfloat16*>(out), B, C, F, W, k, Cpad);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int W, int pw, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(mel && out && pw >= 1 && W > 2 && H > 0, "dd_dae_enc_patches: bad arguments");
+    const long total = (long)B * H * (W + 2 * pw) * 128;
+    if (total == 0) return 0;
+    dae_enc_patches_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(mel, static_cast<__nv_bfloat16*>(out), B, H, W, pw);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_dae_latents_pool(const void* f, float* out, int B, int L, int H, int W, int pw, int Cst, int ratio,
+                                   void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(f && out && L > 0 && 2 * L <= Cst && ratio >= 1 && H % ratio == 0 && W % ratio == 0,
+               "dd_dae_latents_pool: bad arguments");
+    const long total = (long)B * 2 * L * (H / ratio) * (W / ratio);
+    if (total == 0) return 0;
+    dae_latents_pool_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(f), out, B, L, H, W,
+                                                                        pw, Cst, ratio);
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -9,8 +9,9 @@ strict `load_state_dict` of a reference checkpoint works), same `decode(x, embed
 
 `decode` is a fixed schedule of C-ABI launches.  Stereo depth (Z = 2) is folded into the channel dimension and the
 W-axis reflection padding is carried as physical halo columns (csrc/dae.cu), which maps every MPConv3D onto the
-tcgen05 implicit-GEMM convolution kernels; the schedule is captured into a CUDA graph per latent shape.  The encoder
-(`encode` / `forward` / `tiled_encode`, training of the DAE) is not built: those methods raise.  No CPU fallback.
+tcgen05 implicit-GEMM convolution kernels; the decode schedule is captured into a CUDA graph per latent shape.
+`encode` / `tiled_encode` / `forward` run the encoder the same way (eval mode, no gradients; conv_in (1,5,5) as a 2-group
+K = 64 GEMM over 5x5 patches).  Training of the DAE (backward) is not built.  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -191,11 +192,111 @@ class DAE_D3(DualDiffusionDAE):
         r = 2 ** (self.num_levels - 1)
         return (latent_shape[0], 2, latent_shape[2] * r, latent_shape[3] * r)
 
-    def encode(self, x: Tensor, embeddings: Tensor, training: bool = False) -> Tensor:
-        raise NotImplementedError("dualdiffusion_b200 DAE_D3: the encoder is not built (decoder-only drop-in, SURVEY 8 A16)")
+    def _check_inference(self, what: str) -> torch.device:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(f"dualdiffusion_b200 DAE_D3: backward is not implemented ({what} runs under no_grad)")
+        if self.training:
+            raise NotImplementedError(f"dualdiffusion_b200 DAE_D3: train-mode {what} (weight norm inside the forward) is not built")
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError("dualdiffusion_b200 DAE_D3 has no CPU path: move the module to a CUDA device (B200)")
+        return dev
+
+    def _w_enc_in(self) -> Tensor:
+        """conv_in (1,5,5), [mel, 1] -> C: bf16 [2C][64] for the 2-group K = 64 GEMM over dd_dae_enc_patches (column
+        tap*2 + c; the two stereo sides share the weight)."""
+        conv = self.enc["conv_in"]
+        hit = self._prep.get("enc.conv_in")
+        if hit is not None and hit[0] == _ver(conv.weight):
+            return hit[1]
+        w = conv.weight.detach().float()                                     # [C][2][1][5][5]
+        O = w.shape[0]
+        rows = (w.reshape(O, 2, 25).permute(0, 2, 1).reshape(O, 50) / math.sqrt(50.0)).to(torch.bfloat16)
+        out = torch.zeros((2 * O, 1, 64), device=w.device, dtype=torch.bfloat16)
+        out[:O, 0, :50] = rows
+        out[O:, 0, :50] = rows
+        self._prep["enc.conv_in"] = (_ver(conv.weight), out)
+        return out
+
+    def _run_encode(self, mel: Tensor) -> Tensor:
+        """The launch schedule of DAE_D3.encode (:342-354) + Block.forward (:186-238, flavor "enc", no embedding)."""
+        cfg = self.config
+        t = cfg.res_balance
+        n = math.sqrt((1 - t) ** 2 + t ** 2)
+        ca, cb = (1 - t) / n, t / n
+        B = mel.shape[0]
+        x = ops.mpconv(ops.dae_enc_patches(mel, _PW), self._w_enc_in(), 1, 2)
+        ones = self._prep.get(("ones", B))
+        for name, blk in self.enc.items():
+            if not isinstance(blk, Block):
+                continue
+            if ones is None or ones.shape[1] != 2 * blk.conv_res0.weight.shape[0]:
+                ones = torch.ones((B, 2 * blk.conv_res0.weight.shape[0]), device=mel.device, dtype=torch.float32)
+                self._prep[("ones", B)] = ones
+            _, s = ops.cat_silu(x, None, 1.0, 0.0, False, need_cat=False)
+            # emb_channels = 0 for encoder blocks: y = mp_silu(conv_res0(.)) without the embedding scale (:201-202)
+            y0 = ops.mpconv(s, self._z2("enc." + name + ".conv_res0", blk.conv_res0), 3, 2, epi=L.EPI_SCALE_SILU, scale=ones)
+            ops.reflect_fill_w(y0, _PW)
+            x = ops.mpconv(y0, self._z2("enc." + name + ".conv_res1", blk.conv_res1), 3, 2, epi=L.EPI_RESIDUAL, alpha=cb,
+                           beta=ca, clip=blk.clip_act, residual=x)
+            ops.reflect_fill_w(x, _PW)
+        hit = self._prep.get("conv_latents_out")
+        wv = _ver(self.conv_latents_out.weight)
+        if hit is None or hit[0] != wv:
+            w = self.conv_latents_out.weight
+            buf = torch.zeros((16, 9, 2 * w.shape[1]), device=w.device, dtype=torch.bfloat16) if hit is None else hit[1]
+            ops.weight_prep_z2(w.detach(), out=buf)
+            self._prep["conv_latents_out"] = (wv, buf)
+        f = ops.mpconv(x, self._prep["conv_latents_out"][1], 3)
+        return ops.dae_latents_pool(f, cfg.latent_channels, _PW, self.downsample_ratio)
+
+    def encode(self, x: Tensor, embeddings: Optional[Tensor] = None, training: bool = False) -> Tensor:
+        """mel-spectrogram (B, 2, H, W) -> latents (B, 2*latent_channels, H/r, W/r) fp32; normalised unless `training`
+        (:342-354).  Encoder blocks take no embedding (emb_channels = 0, :287)."""
+        dev = self._check_inference("encode")
+        if self.config.channel_mult_enc * self.config.model_channels % 16:
+            raise NotImplementedError("DAE_D3.encode: encoder width must be a multiple of 16")
+        mel = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if mel.ndim != 4 or mel.shape[1] != 2 or mel.shape[2] % self.downsample_ratio or mel.shape[3] % self.downsample_ratio:
+            raise ValueError(f"expected a mel-spectrogram (B, 2, H, W) with H, W multiples of {self.downsample_ratio}, got "
+                             f"{tuple(mel.shape)}")
+        with torch.no_grad():
+            lat = self._run_encode(mel)
+            return lat if training else normalize(lat)
 
     def forward(self, samples: Tensor, dae_embeddings: Tensor, latents_sigma: Optional[Tensor] = None):
-        raise NotImplementedError("dualdiffusion_b200 DAE_D3: training forward (encode + decode) is not built")
+        """:371-379 (inference use: no gradients)."""
+        pre = self.encode(samples, dae_embeddings, training=True)
+        if latents_sigma is not None:
+            pre = pre + latents_sigma * torch.randn_like(pre)
+        latents = normalize(pre)
+        return latents, self.decode(latents, dae_embeddings, training=True), pre
+
+    def tiled_encode(self, x: Tensor, embeddings: Optional[Tensor] = None, max_chunk: int = 6144, overlap: int = 256) -> Tensor:
+        """:381-434.  (The reference passes `normalize_latents=False` to `encode`, a keyword its own signature does not
+        have; the intent -- un-normalised chunk latents, one normalisation at the end -- is what `training=True` does.)"""
+        x_w = x.shape[-1]
+        ds = self.downsample_ratio
+        assert max_chunk % ds == 0 and overlap % ds == 0 and x_w % ds == 0
+        if x_w <= max_chunk:
+            return self.encode(x, embeddings)
+        min_chunk_len = overlap * 3
+        out_overlap = overlap // ds
+        latents = torch.zeros((x.shape[0], self.config.latent_channels * 2, x.shape[-2] // ds, x_w // ds),
+                              device=torch.device(self.device), dtype=torch.float32)
+        for w_start in range(0, x_w, max_chunk - overlap * 2):
+            chunk_start, chunk_end = max(0, w_start), min(x_w, w_start + max_chunk)
+            if chunk_end - chunk_start < min_chunk_len:
+                chunk_start -= min_chunk_len - (chunk_end - chunk_start)
+            chunk = self.encode(x[:, :, :, chunk_start:chunk_end], embeddings, training=True)
+            out_start, out_end = chunk_start // ds, chunk_end // ds
+            first, last = w_start == 0, chunk_end == x_w
+            valid_start = 0 if first else out_overlap
+            valid_end = chunk.shape[3] if last else chunk.shape[3] - out_overlap
+            dest_start = out_start if first else out_start + out_overlap
+            dest_end = out_end if last else out_end - out_overlap
+            latents[:, :, :, dest_start:dest_end] = chunk[:, :, :, valid_start:valid_end]
+        return normalize(latents)
 
     def _apply(self, fn, *args, **kwargs):
         self._prep, self._graphs, self._affine = {}, {}, {}
@@ -277,13 +378,7 @@ class DAE_D3(DualDiffusionDAE):
 
     def decode(self, x: Tensor, embeddings: Tensor, training: bool = False) -> Tensor:
         """latents (B, 2*latent_channels, H, W) -> mel-spectrogram (B, 2, H*r, W*r), module dtype (:356-369)."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("dualdiffusion_b200 DAE_D3: backward is not implemented (decode runs under no_grad)")
-        if self.training:
-            raise NotImplementedError("dualdiffusion_b200 DAE_D3: train-mode decode (weight norm inside the forward) is not built")
-        dev = torch.device(self.device)
-        if dev.type != "cuda":
-            raise RuntimeError("dualdiffusion_b200 DAE_D3 has no CPU path: move the module to a CUDA device (B200)")
+        dev = self._check_inference("decode")
         if embeddings is None:
             raise ValueError("embeddings (from get_embeddings) are required")
         lat = x.detach().to(device=dev, dtype=torch.float32).contiguous()

@@ -645,3 +645,20 @@ def mel_linearize(mel: Tensor, offset: float, inv_exponent: float) -> Tensor:
     L.check(L.load().dd_mel_linearize(L.ptr(mel), L.ptr(out), mel.numel(), offset, inv_exponent, L.stream_ptr()))
     _count()
     return out
+
+
+def dae_enc_patches(mel: Tensor, pw: int) -> Tensor:
+    B, _, H, W = mel.shape
+    out = torch.empty((B, H, W + 2 * pw, 128), device=mel.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_dae_enc_patches(L.ptr(mel), L.ptr(out), B, H, W, pw, L.stream_ptr()))
+    _count()
+    return out
+
+
+def dae_latents_pool(f: Tensor, latent_channels: int, pw: int, ratio: int) -> Tensor:
+    B, H, Wp, Cst = f.shape
+    W = Wp - 2 * pw
+    out = torch.empty((B, 2 * latent_channels, H // ratio, W // ratio), device=f.device, dtype=torch.float32)
+    L.check(L.load().dd_dae_latents_pool(L.ptr(f), L.ptr(out), B, latent_channels, H, W, pw, Cst, ratio, L.stream_ptr()))
+    _count()
+    return out

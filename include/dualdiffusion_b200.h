@@ -380,6 +380,13 @@ DD_API int dd_mdct_ola(const float* y, float* out, int S, int T, int N, void* st
 /* ms_mdct_dual.py:261-265: out = clip(mel - offset, 0) ** inv_exponent.                                               */
 DD_API int dd_mel_linearize(const float* mel, float* out, long n, float offset, float inv_exponent, void* stream);
 
+/* DAE_D3.encode (modules/daes/dae_edm2_d3.py:342-354).  Input assembly for conv_in (1,5,5): per stereo side the 5x5 patch
+ * of [mel, 1] (reflection along W, zeros along H), 50 values padded to 64 -> [B][H][W+2pw][128] bf16; mel fp32 (B,2,H,W). */
+DD_API int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int W, int pw, void* stream);
+/* Tail: conv_latents_out result [B][H][W+2pw][Cst] bf16 (channel z*L+c) -> tensor_5d_to_4d + avg_pool2d(ratio) -> fp32 NCHW
+ * (B, 2L, H/ratio, W/ratio), channel c*2+z.                                                                              */
+DD_API int dd_dae_latents_pool(const void* f, float* out, int B, int L, int H, int W, int pw, int Cst, int ratio, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

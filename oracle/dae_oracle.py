@@ -149,3 +149,22 @@ def synth_dae_state_dict(spec: DAESpec, seed: int = 0, gain: float = 0.5) -> Dic
         else:
             sd[name] = normalize(torch.randn(shape, generator=gen), dim=1)
     return sd
+
+
+def dae_encode(sd: Dict[str, Tensor], spec: DAESpec, mel: Tensor, training: bool = False) -> Tensor:
+    """DAE_D3.encode (:342-354) with Block.forward flavor "enc" (:186-238; encoder blocks have no embedding, no conv_skip,
+    no pixel norm in the shipped configuration): mel (B, 2, H, W) -> latents (B, 2*latent_channels, H/r, W/r)."""
+    b, _, h, w = mel.shape
+    x = mel.float().reshape(b, 1, -1, h, w)                                       # tensor_4d_to_5d(x, 1)
+    x = torch.cat((x, torch.ones_like(x[:, :1])), dim=1)
+    x = mp_conv3d(x, sd["enc.conv_in.weight"])
+    for i in range(spec.num_enc_layers):
+        p = f"enc.block0_layer{i}."
+        y = mp_conv3d(mp_silu(x), sd[p + "conv_res0.weight"])
+        y = mp_silu(y)
+        y = mp_conv3d(y, sd[p + "conv_res1.weight"])
+        x = mp_sum(x, y, spec.res_balance).clip(-256.0, 256.0)
+    lat = mp_conv3d(x, sd["conv_latents_out.weight"])
+    lat = lat.reshape(b, lat.shape[1] * lat.shape[2], lat.shape[3], lat.shape[4])  # tensor_5d_to_4d
+    lat = F.avg_pool2d(lat, 2 ** (len(spec.channel_mult_dec) - 1))
+    return lat if training else normalize(lat)

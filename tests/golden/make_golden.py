@@ -107,7 +107,10 @@ def main():
         emb = dae.get_embeddings(emb_in)
         cases[tag] = dict(latents=lat, emb_in=emb_in, emb=emb, mel=dae.decode(lat, emb))
         print("dae", tag, cases[tag]["mel"].shape, float(cases[tag]["mel"].std()))
-    torch.save(dict(cases=cases, weight_checksum=weight_checksum(dsd), mel_shape=dae.get_mel_spec_shape((3, 8, 32, 688)),
+    mel_in = torch.randn(2, 2, 16, 24, generator=g).abs() * 20                 # encoder (:342-354)
+    enc = dict(mel=mel_in, latents=dae.encode(mel_in, None), pre_norm=dae.encode(mel_in, None, training=True))
+    torch.save(dict(cases=cases, encode=enc, weight_checksum=weight_checksum(dsd),
+                    mel_shape=dae.get_mel_spec_shape((3, 8, 32, 688)),
                     latent_shape=dae.get_latent_shape((3, 2, 256, 5504))), os.path.join(OUT, "dae_small.pt"))
 
     # ---- diffusion-decoder UNet DDec_MCLT_UNet_B1 (unet_edm2_ddec_mclt_b1.py:278-326), reduced config ----

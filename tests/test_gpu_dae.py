@@ -134,8 +134,33 @@ def test_dae_decode_vs_golden_reference(dev, graphs):
         assert rel_err(mel, c["mel"]) < BF16_NET, (tag, rel_err(mel, c["mel"]))
     assert tuple(net.get_mel_spec_shape((3, 8, 32, 688))) == tuple(g["mel_shape"])
     assert tuple(net.get_latent_shape((3, 2, 256, 5504))) == tuple(g["latent_shape"])
-    with pytest.raises(NotImplementedError):
-        net.encode(torch.zeros(1, 2, 16, 16, device=dev), None)
+
+
+def test_dae_encode_vs_golden_reference(dev):
+    """DAE_D3.encode (:342-354): conv_in (1,5,5) as a patch GEMM, 2-group encoder blocks, conv_latents_out, 2x2 pooling,
+    latent normalisation; plus the autoencoder round trip forward() = (latents, reconstruction, pre-norm latents)."""
+    spec = do.small_dae_spec()
+    sd = do.synth_dae_state_dict(spec, seed=0)
+    g = load_golden("dae_small.pt")
+    net = make_dae(spec, sd, dev)
+    e = g["encode"]
+    lat = net.encode(e["mel"].to(dev), None)
+    assert lat.shape == e["latents"].shape and lat.dtype == torch.float32
+    assert rel_err(lat, e["latents"]) < BF16_NET, rel_err(lat, e["latents"])
+    assert rel_err(net.encode(e["mel"].to(dev), None, training=True), e["pre_norm"]) < BF16_NET
+    # stem patches: an index map (+ one bf16 rounding) -- bit-exact against an unfold of the reflect / zero padded input
+    from dualdiffusion_b200 import ops
+    mel = e["mel"]
+    patches = ops.dae_enc_patches(mel.to(dev), PW).float().cpu()                           # [B][H][Wp][128]
+    x = torch.stack((mel, torch.ones_like(mel)), dim=2)                                     # (B, z, c, H, W)
+    xp = F.pad(F.pad(x.flatten(0, 1), (2, 2, 0, 0), mode="reflect"), (0, 0, 2, 2))          # reflect W, zero H
+    un = F.unfold(xp, 5).view(mel.shape[0], 2, 2, 25, mel.shape[2], mel.shape[3])           # (B, z, c, tap, H, W)
+    ref = un.permute(0, 4, 5, 1, 3, 2).reshape(mel.shape[0], mel.shape[2], mel.shape[3], 2, 50).to(torch.bfloat16).float()
+    got = patches[:, :, PW:-PW].reshape(mel.shape[0], mel.shape[2], mel.shape[3], 2, 64)
+    assert torch.equal(got[..., :50], ref) and got[..., 50:].abs().max().item() == 0
+    emb = net.get_embeddings(g["cases"]["h8"]["emb_in"].repeat(2, 1))
+    latents, recon, pre = net(e["mel"].to(dev), emb)
+    assert rel_err(latents, e["latents"]) < BF16_NET and recon.shape == e["mel"].shape and pre.shape == lat.shape
 
 
 def test_dae_decode_default_config_properties(dev):

@@ -166,6 +166,9 @@ def test_dae_oracle_decode_vs_golden_reference():
         assert rel_err(emb, c["emb"]) < 1e-6
         mel = do.dae_decode(sd, spec, c["latents"], emb)
         assert mel.shape == c["mel"].shape and rel_err(mel, c["mel"]) < 1e-5, tag
+    e = g["encode"]
+    assert rel_err(do.dae_encode(sd, spec, e["mel"]), e["latents"]) < 1e-5
+    assert rel_err(do.dae_encode(sd, spec, e["mel"], training=True), e["pre_norm"]) < 1e-5
     r = 2 ** (len(spec.channel_mult_dec) - 1)      # get_mel_spec_shape / get_latent_shape (:323-342)
     assert tuple(g["mel_shape"]) == (3, 2, 32 * r, 688 * r) and tuple(g["latent_shape"]) == (3, 8, 256 // r, 5504 // r)
 
