@@ -102,6 +102,7 @@ _SIGNATURES = {
     "dd_weight_transpose": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_weight_prep_bwd": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dd_weight_prep_batched": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "dd_weight_normalize_batched": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dd_weight_transpose_batched": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "dd_silu_scale_bwd": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_long, c_int,
                                   c_void_p]),

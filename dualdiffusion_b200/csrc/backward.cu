@@ -98,6 +98,28 @@ __global__ void weight_transpose_batched_kernel(const dd_wtrans_desc* __restrict
     }
 }
 
+// normalize_weights() (mp_tools.py:375-378, run by the trainer after every optimizer step, trainer.py:1107-1108) for a
+// whole parameter set in one launch, in place on the fp32 parameters: w <- w / (eps + ||w|| / sqrt(fan_in)) per row.
+__global__ void weight_normalize_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs) {
+    __shared__ float red[32];
+    int lo = 0, hi = n_descs - 1;
+    const int row = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].row_begin <= row) lo = mid; else hi = mid - 1;
+    }
+    const dd_wprep_desc d = descs[lo];
+    const int o = row - d.row_begin;
+    if (o >= d.O) return;
+    const int f = d.I_g * d.taps;
+    float* w = static_cast<float*>(const_cast<void*>(d.w)) + (size_t)o * f;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < f; i += blockDim.x) ss += w[i] * w[i];
+    ss = block_sum_b(ss, red);
+    const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)f));
+    for (int i = threadIdx.x; i < f; i += blockDim.x) w[i] *= inv;
+}
+
 // dd_weight_prep for every parameter of a model in one launch (same arithmetic as weight_prep_kernel, elementwise.cu)
 __global__ void weight_prep_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs) {
     __shared__ float red[32];
@@ -947,6 +969,14 @@ extern "C" int dd_weight_transpose(const void* w_prepped, void* out, int Cout, i
     const dim3 grid(ceil_div(cin_g, 32), ceil_div(cout_g, 32), groups * taps);
     weight_transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(w_prepped),
                                                              static_cast<__nv_bfloat16*>(out), cout_g, cin_g, taps);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_weight_normalize_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_normalize_batched: bad arguments");
+    weight_normalize_batched_kernel<<<total_rows, 128, 0, stream>>>(descs_dev, n_descs);
     DD_CHECK_LAUNCH();
     return 0;
 }

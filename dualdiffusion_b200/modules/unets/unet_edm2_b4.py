@@ -352,8 +352,35 @@ class UNet(DualDiffusionUNet):
             plan.ln_freqs[key] = t
         return t
 
+    @torch.no_grad()
+    def normalize_weights(self) -> None:
+        """module.py:185-191 -> MPConv.normalize_weights (mp_tools.py:375-378), which the trainer runs after every
+        optimizer step (trainer.py:1107-1108).  On a CUDA device with fp32 parameters all ~190 weight tensors are
+        normalised in place by ONE launch (`dd_weight_normalize_batched`) instead of a kernel + copy per parameter."""
+        convs = [m for m in self.modules() if isinstance(m, MPConv) and not m.disable_weight_norm]
+        if (not convs or not all(c.weight.is_cuda and c.weight.dtype == torch.float32 and c.weight.is_contiguous()
+                                 for c in convs)):
+            return super().normalize_weights()
+        st = getattr(self, "_normalize_descs", None)
+        ptrs = tuple(c.weight.data_ptr() for c in convs)
+        if st is None or st[0] != ptrs:
+            entries = []
+            for c in convs:
+                w = c.weight
+                taps = 1
+                for d in w.shape[2:]:
+                    taps *= d
+                entries.append(dict(w=w.detach(), out=w.detach(), O=w.shape[0], I_g=w.shape[1], taps=taps))
+            buf, rows = ops.make_wprep_descs(entries, convs[0].weight.device)
+            st = (ptrs, buf, rows, len(entries))
+            self._normalize_descs = st
+        ops.weight_normalize_batched(st[1], st[3], st[2])
+        for c in convs:
+            torch.autograd.graph.increment_version(c.weight)      # the raw-pointer write must invalidate prepared weights
+
     def _apply(self, fn, *args, **kwargs):
         # parameters may be re-allocated by .to()/.cuda()/.float(): drop every cached pointer / graph
+        self._normalize_descs = None
         self._plan = None
         self._aux_cache = None
         return super()._apply(fn, *args, **kwargs)

@@ -358,6 +358,11 @@ def weight_prep_batched(descs: Tensor, n: int, total_rows: int) -> None:
     _count()
 
 
+def weight_normalize_batched(descs: Tensor, n: int, total_rows: int) -> None:
+    L.check(L.load().dd_weight_normalize_batched(L.ptr(descs), n, total_rows, L.stream_ptr()))
+    _count()
+
+
 def make_wtrans_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int]:
     """Pack dd_wtrans_desc records (dicts with src, dst, cout_g, cin_g, taps, groups); returns (buffer, total_tiles)."""
     arr = (L.WtransDesc * len(entries))()

@@ -248,6 +248,9 @@ typedef struct dd_wprep_desc {
     int row_begin;       /* exclusive prefix sum of O over the descriptor array */
 } dd_wprep_desc;
 DD_API int dd_weight_prep_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream);
+/* normalize_weights() (mp_tools.py:375-378; trainer.py:1107-1108 runs it after every optimizer step) for a whole parameter
+ * set in one launch, IN PLACE on fp32 parameters (descs[].w; .out / gain / perm fields unused).                          */
+DD_API int dd_weight_normalize_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream);
 /* dd_weight_transpose for a whole parameter set in one launch (32x32 tiles; tile_begin = exclusive prefix sum of
  * ceil(cin_g/32)*ceil(cout_g/32)*groups*taps).                                                                       */
 typedef struct dd_wtrans_desc {

@@ -521,3 +521,25 @@ def test_batched_weight_prep_and_transpose_match_single_calls(dev):
     ops.weight_transpose_batched(buf2, len(trans), tiles)
     for got, ref in singles:
         assert torch.equal(got.view(-1), ref.view(-1))
+
+
+def test_batched_normalize_weights_matches_reference_semantics(dev):
+    """UNet.normalize_weights() (module.py:185-191 -> mp_tools.py:375-378) as one in-place launch: equals the oracle's
+    per-parameter normalize and bumps the parameter versions so prepared weights are refreshed."""
+    spec = uo.small_spec()
+    sd = uo.synth_state_dict(spec, seed=0)
+    net = make_train_unet(spec, sd, dev)
+    gen = torch.Generator().manual_seed(83)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.ndim >= 2:
+                p.mul_(1.0 + 0.5 * torch.rand(p.shape[0], *([1] * (p.ndim - 1)), generator=gen).to(dev))
+    before = {n: p.detach().cpu().clone() for n, p in net.named_parameters()}
+    vers = {n: p._version for n, p in net.named_parameters()}
+    net.normalize_weights()
+    for n, p in net.named_parameters():
+        if p.ndim >= 2 and n != "logvar_linear.weight":
+            assert rel_err(p, uo.normalize(before[n])) < 1e-6, n
+            assert p._version > vers[n], n
+        else:
+            assert torch.equal(p.detach().cpu(), before[n]), n
