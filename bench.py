@@ -374,8 +374,12 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dist = None
+    # stdout carries exactly ONE line (the JSON): native libraries write banners to fd 1 (NCCL prints its version there),
+    # so fd 1 is pointed at stderr for the duration of the run and the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version banner must not precede the JSON line on stdout
         import torch.distributed as dist_mod
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
@@ -505,7 +509,8 @@ def run_ours(args) -> None:
                 "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
                 "train_step": train, "dae_decode": dae, "ddec_forward": ddec, "secondary": secondary}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
