@@ -69,6 +69,8 @@ struct ConvParams {
     int nbuf;                       // TMEM accumulator buffers (power of two): MMAs run up to nbuf tiles ahead of the epilogue
     int dbg_taps;                   // experiment: number of taps actually issued (9 = all)
     int dbg_nostore;                // experiment: skip the epilogue's global stores
+    uint32_t stage_off;             // byte offset (from the aligned dynamic smem base) of the epilogue warps' 4 KB staging
+                                    // slabs; 0 = direct (un-staged) epilogue
     // halo kernel (3x3, weights stationary)
     int ks_last;                    // 16-channel MMA steps in the last 64-channel chunk
     int a_stages;
@@ -273,6 +275,155 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
             }
 }
 
+// ---------------------------------------------------------------------------------
+// Shared-memory-staged epilogue.  In the direct epilogue above a thread owns one pixel row of the tile, so every
+// global access of a warp touches 32 different 128 B lines (16 B each): the LSU needs 32 passes per instruction and
+// the fused residual / second-output epilogues become the limiter of the wide layers (tools/exp_epi.py).  Here each
+// epilogue warp owns a private 4 KB slab (32 rows x 128 B, no cross-warp synchronisation): results are written to
+// the slab in the row-per-thread layout and read back so that 8 (4, 2) adjacent lanes cover the 128 (64, 32)
+// contiguous bytes of one pixel before they go to global memory; the residual takes the same route in reverse and is
+// overwritten in place.  With a second output the slab holds 32 channels of each output (chunks 0-3 / 4-7 of a row),
+// otherwise 64 channels.  The 16 B chunk index is XORed with f(row) = (row&1)<<2 | (row>>1)&3, which makes the
+// row-per-thread accesses and the 8- and 4-lanes-per-row accesses bank-conflict free.
+// Arithmetic is identical to epilogue_tile (bit-identical outputs: tools/dev_check_epi_staged.py).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t slab_addr(uint32_t slab, int row, int chunk) {
+    const int f = ((row & 1) << 2) | ((row >> 1) & 3);
+    return slab + (uint32_t)(row * 128 + ((chunk ^ f) << 4));
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
+    return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// `pixv` = this thread's (row's) linear output pixel index, or -1 when the row lies outside the tensor; `slab` = shared
+// address of this warp's 4 KB staging slab.  All 32 lanes must call (shuffles / __syncwarp inside).
+template <int EW>
+__device__ __forceinline__ void epilogue_tile_staged(const ConvParams& p, uint32_t taddr, int pixv, int b, int ch0,
+                                                     uint32_t slab, int lane) {
+    constexpr int kChunk = EW >= 8 ? 16 : 32;   // columns per tcgen05.ld
+    const bool two = p.epi2 != DD_EPI2_NONE;
+    uint32_t rn[kChunk];
+    tmem_ld_chunk<kChunk>(taddr, rn, kChunk == 32 && 32 > p.n_tile);
+    for (int slab0 = 0; slab0 < p.n_tile;) {
+        const int rem = p.n_tile - slab0;
+        const int lpr_log2 = (!two && rem >= 64) ? 3 : (rem >= 32 ? 2 : 1);    // lanes per pixel row: 8 / 4 / 2
+        const int sw = 8 << lpr_log2;                                            // slab width in channels: 64 / 32 / 16
+        const int lpr = 1 << lpr_log2, rstep = 32 >> lpr_log2;
+        const int ck = lane & (lpr - 1), r_in = lane >> lpr_log2;
+        const size_t col = (size_t)(ch0 + slab0 + ck * 8);
+        if (p.epi == DD_EPI_RESIDUAL) {
+            // coalesced residual rows -> slab (all loads in flight before the first shared store)
+            for (int i0 = 0; i0 < lpr; i0 += 4) {
+                uint4 q[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i0 + i < lpr) {
+                        const int px = __shfl_sync(0xffffffffu, pixv, (i0 + i) * rstep + r_in);
+                        q[i] = make_uint4(0u, 0u, 0u, 0u);
+                        if (px >= 0) q[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)px * p.Cout + col));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i0 + i < lpr) st_shared_v4(slab_addr(slab, (i0 + i) * rstep + r_in, ck), q[i]);
+            }
+            __syncwarp();
+        }
+        for (int c0 = slab0; c0 < slab0 + sw; c0 += kChunk) {
+            uint32_t r[kChunk];
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < kChunk; ++i) r[i] = rn[i];
+            if (c0 + kChunk < p.n_tile)
+                tmem_ld_chunk<kChunk>(taddr + c0 + kChunk, rn, kChunk == 32 && c0 + 2 * kChunk > p.n_tile);
+#pragma unroll
+            for (int sub16 = 0; sub16 < kChunk / 16; ++sub16) {
+                const int c = c0 + sub16 * 16;
+                if (c >= slab0 + sw) break;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[sub16 * 16 + i]);
+                const int ch = ch0 + c;
+                const int lc = (c - slab0) >> 3;                     // first of this sub-chunk's two 16 B chunks
+                const uint32_t a0 = slab_addr(slab, lane, lc), a1 = slab_addr(slab, lane, lc + 1);
+                const uint32_t a2 = slab_addr(slab, lane, lc + 4), a3 = slab_addr(slab, lane, lc + 5);
+                if (p.epi2 == DD_EPI2_RAW) {                         // pre-activation, for backward
+                    st_shared_v4(a2, pack_bf16x8(v));
+                    st_shared_v4(a3, pack_bf16x8(v + 8));
+                }
+                if (p.epi == DD_EPI_SCALE_SILU) {
+                    const float4* sc = reinterpret_cast<const float4*>(p.scale + (size_t)b * p.Cout + ch);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 s = __ldg(sc + i);
+                        v[4 * i + 0] = mp_silu_fast(v[4 * i + 0] * s.x);
+                        v[4 * i + 1] = mp_silu_fast(v[4 * i + 1] * s.y);
+                        v[4 * i + 2] = mp_silu_fast(v[4 * i + 2] * s.z);
+                        v[4 * i + 3] = mp_silu_fast(v[4 * i + 3] * s.w);
+                    }
+                } else if (p.epi == DD_EPI_RESIDUAL) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint4 q = ld_shared_v4(i == 0 ? a0 : a1);
+                        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = unpack_bf16x2(u[j]);
+                            const float x0 = p.alpha * v[8 * i + 2 * j + 0] + p.beta * f.x;
+                            const float x1 = p.alpha * v[8 * i + 2 * j + 1] + p.beta * f.y;
+                            v[8 * i + 2 * j + 0] = fminf(fmaxf(x0, -p.clip), p.clip);
+                            v[8 * i + 2 * j + 1] = fminf(fmaxf(x1, -p.clip), p.clip);
+                        }
+                    }
+                }
+                st_shared_v4(a0, pack_bf16x8(v));
+                st_shared_v4(a1, pack_bf16x8(v + 8));
+                if (p.epi2 == DD_EPI2_SILU || p.epi2 == DD_EPI2_SCALE) {
+                    if (p.epi2 == DD_EPI2_SILU) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = mp_silu_fast(v[i]);
+                    } else {
+                        const float4* sc = reinterpret_cast<const float4*>(p.scale2 + (size_t)b * p.Cout + ch);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 s = __ldg(sc + i);
+                            v[4 * i + 0] *= s.x; v[4 * i + 1] *= s.y; v[4 * i + 2] *= s.z; v[4 * i + 3] *= s.w;
+                        }
+                    }
+                    st_shared_v4(a2, pack_bf16x8(v));
+                    st_shared_v4(a3, pack_bf16x8(v + 8));
+                }
+            }
+        }
+        __syncwarp();
+        // slab -> global: `lpr` adjacent lanes write the contiguous bytes of one pixel
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < lpr) {
+                const int rl = i * rstep + r_in;
+                const int px = __shfl_sync(0xffffffffu, pixv, rl);
+                const uint4 o = ld_shared_v4(slab_addr(slab, rl, ck));
+                uint4 o2 = o;
+                if (two) o2 = ld_shared_v4(slab_addr(slab, rl, ck + 4));
+                if (px >= 0) {
+                    *reinterpret_cast<uint4*>(p.out + (size_t)px * p.Cout + col) = o;
+                    if (two) *reinterpret_cast<uint4*>(p.out2 + (size_t)px * p.Cout + col) = o2;
+                }
+            }
+        }
+        __syncwarp();
+        slab0 += sw;
+    }
+}
+
 // EW = number of epilogue warps: 4 (one per TMEM lane quadrant, 32-column chunks) or 8 (two per quadrant,
 // interleaved 16-column chunks; for epilogues with transcendental math).
 template <int KC, int EW>
@@ -439,7 +590,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
-            epilogue_tile<EW>(p, taddr, valid, b, h, w, ch0);
+            if (p.stage_off) {
+                const uint32_t slab = ptx::smem_u32(smem) + p.stage_off + (uint32_t)(warp - 2) * 4096u;
+                epilogue_tile_staged<EW>(p, taddr, valid ? (b * p.H + h) * p.W + w : -1, valid ? b : 0, ch0, slab, lane);
+            } else {
+                epilogue_tile<EW>(p, taddr, valid, b, h, w, ch0);
+            }
             // all TMEM reads of this buffer have completed (wait::ld above): hand it back
             ptx::tcgen05_fence_before();
             __syncwarp();
@@ -807,7 +963,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
-            epilogue_tile<EW>(p, taddr, valid, b, h, w, ch0);
+            if (p.stage_off) {
+                const uint32_t slab = ptx::smem_u32(smem) + p.stage_off + (uint32_t)(warp - 2) * 4096u;
+                epilogue_tile_staged<EW>(p, taddr, valid ? (b * p.H + h) * p.W + w : -1, valid ? b : 0, ch0, slab, lane);
+            } else {
+                epilogue_tile<EW>(p, taddr, valid, b, h, w, ch0);
+            }
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
@@ -907,6 +1068,27 @@ int choose_nacc(int n_tile, int k_steps) {
     return nacc;
 }
 
+// Epilogue warps: 4 for the plain / head epilogues, 8-12 for the fused ones (tools/exp_epi.py).
+int choose_epi_warps(const ConvParams& p) {
+    int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
+    if (ew == 8 && p.nbuf >= 4) ew = 12;      // fused epilogues are the limiter (tools/exp_epi.py): a third warp group
+    if (const char* f = getenv("DD_FORCE_EPI_WARPS")) { const int v = atoi(f); ew = v == 12 ? 12 : (v == 8 ? 8 : 4); }   // tuning
+    while (ew > 4 && ew / 4 > p.nbuf) ew -= 4;      // every epilogue warp group needs its own accumulator buffer
+    return ew;
+}
+
+// Shared-memory-staged epilogue (epilogue_tile_staged).  Measured on B200 against the direct epilogue, bit-identical
+// outputs (tools/dev_check_epi_staged.py, profiles/r01_epi_staged_ab.log): two-output epilogues gain 5-30 % on every
+// BASELINE-size layer (512->1024 3x3 residual + silu copy 123 -> 104 us, 256->512 67 -> 45 us, silu + raw copy 48 -> 35 us);
+// single-output ones are within +-5 % either way (both variants move the same bytes at ~3 TB/s of algorithmic traffic,
+// i.e. coalescing was not what limits them), so they keep the direct path.  DD_EPI_STAGED=0/1 forces one variant (tuning).
+constexpr uint32_t kSlabBytes = 4096;
+bool want_staged_epilogue(const ConvParams& p) {
+    bool on = p.epi2 != DD_EPI2_NONE;
+    if (const char* f = getenv("DD_EPI_STAGED")) on = atoi(f) != 0;
+    return on && p.epi != DD_EPI_HEAD && p.nacc == 1;
+}
+
 int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode_fn();
     DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");
@@ -965,13 +1147,17 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     const uint32_t pair_bytes = kTileM * row_bytes + p.b_bytes;
     p.sub = (pair_bytes <= 24u * 1024u && p.k_iters >= 2) ? 2 : 1;
     const uint32_t stage_bytes = pair_bytes * p.sub;
-    p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u) / stage_bytes)));
     p.nacc = 1;      // (splitting the accumulation chain over several TMEM accumulators measured no gain)
     p.nbuf = 2;
     while (p.nbuf < kMaxAccBufs && 2 * p.nbuf * p.n_tile * p.nacc <= 512) p.nbuf *= 2;
     uint32_t cols = 32;
     while (cols < (uint32_t)(p.nbuf * p.n_tile * p.nacc)) cols <<= 1;
     p.tmem_cols = cols;
+    const int ew = choose_epi_warps(p);
+    const bool staged = want_staged_epilogue(p) && p.ksplit == 1;
+    const uint32_t slabs_bytes = staged ? (uint32_t)ew * kSlabBytes : 0u;
+    p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u - slabs_bytes) / stage_bytes)));
+    p.stage_off = staged ? (uint32_t)p.stages * stage_bytes : 0u;
 
     CUtensorMap tmA, tmB;
     const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -997,7 +1183,7 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
         DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: weight tensor map encode failed (CUresult %d)", (int)r);
     }
 
-    const size_t smem_bytes = (size_t)p.stages * stage_bytes + 1024;
+    const size_t smem_bytes = (size_t)p.stages * stage_bytes + slabs_bytes + 1024;
     if (p.ksplit > 1) {
         // rank > 0 parks 128 x n_tile fp32 in its pipeline shared memory: must fit
         const size_t staging = (size_t)((p.n_tile + 31) / 32) * kTileM * 32 * 4;
@@ -1036,9 +1222,6 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
         fprintf(stderr, "[conv] B%d %dx%d %d->%d k%d g%d: box %dx%dx%d m_tiles %d n_tile %d tiles %d k_iters %d KC %d sub %d stages %d\n",
                 B, H, W, Cin, Cout, p.kw, groups, p.wt, p.ht, p.bt, p.m_tiles, p.n_tile, p.num_tiles, p.k_iters, KC, p.sub,
                 p.stages);
-    int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
-    if (ew == 8 && p.nbuf >= 4) ew = 12;      // fused epilogues are the limiter (tools/exp_epi.py): a third warp group
-    if (const char* f = getenv("DD_FORCE_EPI_WARPS")) { const int v = atoi(f); ew = v == 12 ? 12 : (v == 8 ? 8 : 4); }   // tuning
 #define DD_LAUNCH_IGEMM(KC_, EW_)                                                                                  \
     do {                                                                                                           \
         static bool attr_done = false;                                                                             \
@@ -1077,7 +1260,12 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     p.kchunks = ceil_div(cin_g, 64);
     p.ks_last = (cin_g - 64 * (p.kchunks - 1)) / 16;
     p.k_iters = p.kchunks;
-    const uint32_t budget = 214u * 1024u;
+    p.nacc = 1;
+    const bool staged = want_staged_epilogue(p);
+    // direct epilogue: 214 KB of operands; staged: 224 KB shared between operands and the 4 KB-per-warp slabs (the output
+    // tile width is chosen as if there were 4 epilogue warps, then the warp count is cut back to what still fits)
+    const uint32_t total = staged ? 224u * 1024u : 214u * 1024u;
+    const uint32_t budget = total - (staged ? 4u * kSlabBytes : 0u);
     int n_tile = 0;
     for (int n = 16; n <= std::min(cout_g, 256); n += 16) {
         if (cout_g % n) continue;
@@ -1091,7 +1279,6 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
     p.b_block_bytes = (uint32_t)n_tile * 128u;
     const uint32_t b_total = (uint32_t)p.kchunks * 9u * p.b_block_bytes;
-    p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((budget - b_total) / p.halo_stride)));
     p.nacc = 1;
     p.ksplit = 1;
     p.dbg_taps = 9;
@@ -1101,6 +1288,15 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     uint32_t cols = 32;
     while (cols < (uint32_t)(p.nbuf * p.n_tile * p.nacc)) cols <<= 1;
     p.tmem_cols = cols;
+    int ew = choose_epi_warps(p);
+    if (staged) {
+        // keep at least three halo stages (or as many as four epilogue warps would leave) before adding warp groups
+        const int want_stages = std::min(3, (int)((budget - b_total) / p.halo_stride));
+        while (ew > 4 && b_total + (uint32_t)want_stages * p.halo_stride + (uint32_t)ew * kSlabBytes > total) ew -= 4;
+    }
+    const uint32_t slabs_bytes = staged ? (uint32_t)ew * kSlabBytes : 0u;
+    p.a_stages = std::max(2, std::min<int>(kMaxAStages, (int)((total - slabs_bytes - b_total) / p.halo_stride)));
+    p.stage_off = staged ? b_total + (uint32_t)p.a_stages * p.halo_stride : 0u;
 
     CUtensorMap tmA, tmB;
     {
@@ -1126,17 +1322,14 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: weight tensor map encode failed (CUresult %d)", (int)r);
     }
-    const size_t smem_bytes = (size_t)b_total + (size_t)p.a_stages * p.halo_stride + 1024;
+    const size_t smem_bytes = (size_t)b_total + (size_t)p.a_stages * p.halo_stride + slabs_bytes + 1024;
     const int grid = std::min(p.num_tiles, dd_num_sms());
-    int ew = (p.epi != DD_EPI_NONE && p.epi != DD_EPI_HEAD) ? 8 : 4;
-    if (ew == 8 && p.nbuf >= 4) ew = 12;      // fused epilogues are the limiter (tools/exp_epi.py): a third warp group
-    if (const char* f = getenv("DD_FORCE_EPI_WARPS")) { const int v = atoi(f); ew = v == 12 ? 12 : (v == 8 ? 8 : 4); }   // tuning
 #define DD_LAUNCH_HALO(EW_)                                                                                        \
     do {                                                                                                           \
         static bool attr_done = false;                                                                             \
         if (!attr_done) {                                                                                          \
             DD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<EW_>,                                          \
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));          \
             attr_done = true;                                                                                      \
         }                                                                                                          \
         DD_CHECK_CUDA(launch_pdl(conv3x3_halo_kernel<EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p));   \

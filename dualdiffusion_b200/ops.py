@@ -83,7 +83,7 @@ def mpconv(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1, *, epi: in
     if timing is not None:
         ev1.record()
         timing.append((2.0 * B * H * W * Cout * (Cin // groups) * ksize * ksize, ev0, ev1,
-                       (B, H, W, Cin, Cout, ksize, groups)))
+                       (B, H, W, Cin, Cout, ksize, groups, epi, epi2)))
     _count(1, "mpconv", (B, H, W, Cin, Cout, ksize, groups, epi, epi2))
     return (out, out2) if epi2 != L.EPI2_NONE else out
 

@@ -141,6 +141,39 @@ def test_mpconv_epilogues(dev):
     assert rel_err(to_nchw(y2), uo.mp_silu(ref)) < BF16_OP
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,g", [
+    (2, 7, 13, 96, 64, 1, 1),        # per-tap kernel, ragged pixel box
+    (2, 17, 20, 768, 512, 3, 8),     # halo kernel, ragged tile edges, n_tile 64
+    (1, 16, 40, 64, 80, 3, 1),       # n_tile 80: 64 + 16 channel slabs
+    (3, 8, 20, 128, 64, 3, 2),       # two batch items per halo tile, odd batch
+])
+def test_mpconv_staged_epilogue_is_bit_identical(dev, monkeypatch, B, H, W, Cin, Cout, k, g):
+    """The shared-memory-staged epilogue (default for two-output epilogues) and the direct one (default otherwise)
+    do the same arithmetic: forcing either variant (DD_EPI_STAGED, read by the launcher per call) must give the
+    same bytes for every epilogue mode, including rows / channels neither may touch (poisoned outputs)."""
+    from dualdiffusion_b200 import ops, _lib as L
+    gen = torch.Generator().manual_seed(B * 100 + Cout)
+    x = torch.randn(B, H, W, Cin, generator=gen).to(dev).to(torch.bfloat16)
+    wp = ops.weight_prep(torch.randn(Cout, Cin // g, k, k, generator=gen).to(dev))
+    sc = (torch.randn(B, Cout, generator=gen) * 0.3 + 1).to(dev)
+    res = torch.randn(B, H, W, Cout, generator=gen).to(dev).to(torch.bfloat16)
+    modes = [dict(), dict(epi2=L.EPI2_RAW), dict(epi=L.EPI_SCALE_SILU, scale=sc),
+             dict(epi=L.EPI_SCALE_SILU, scale=sc, epi2=L.EPI2_RAW),
+             dict(epi=L.EPI_RESIDUAL, alpha=0.6, beta=0.8, clip=2.0, residual=res),
+             dict(epi=L.EPI_RESIDUAL, alpha=0.6, beta=0.8, residual=res, epi2=L.EPI2_SILU),
+             dict(epi=L.EPI_RESIDUAL, alpha=0.6, beta=0.8, clip=1.0, residual=res, epi2=L.EPI2_SCALE, scale2=sc)]
+    for kw in modes:
+        got = []
+        for staged in ("0", "1"):
+            monkeypatch.setenv("DD_EPI_STAGED", staged)
+            out = torch.full((B, H, W, Cout), 7.0, device=dev, dtype=torch.bfloat16)
+            out2 = torch.full((B, H, W, Cout), 9.0, device=dev, dtype=torch.bfloat16) if "epi2" in kw else None
+            r = ops.mpconv(x, wp, k, g, out=out, out2=out2, **kw)
+            got.append(r if isinstance(r, tuple) else (r,))
+        for a, b in zip(*got):
+            assert torch.equal(a.view(torch.int16), b.view(torch.int16)), kw.keys()
+
+
 def test_weight_prep_vs_oracle(dev):
     from dualdiffusion_b200 import ops, _lib as L
     gen = torch.Generator().manual_seed(5)
