@@ -69,6 +69,7 @@ struct ConvParams {
     int nbuf;                       // TMEM accumulator buffers (power of two): MMAs run up to nbuf tiles ahead of the epilogue
     int dbg_taps;                   // experiment: number of taps actually issued (9 = all)
     int dbg_nostore;                // experiment: skip the epilogue's global stores
+    int prefetch_res;               // epilogue warps request the next tile's residual rows into L2 a tile ahead
     uint32_t stage_off;             // byte offset (from the aligned dynamic smem base) of the epilogue warps' 4 KB staging
                                     // slabs; 0 = direct (un-staged) epilogue
     // halo kernel (3x3, weights stationary)
@@ -273,6 +274,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
                 }
               }
             }
+}
+
+// The fused residual epilogues are bound by memory-level parallelism, not by bandwidth: a warp has only the 2-4 KB
+// of residual it is about to consume in flight, and with ~1 us of loaded HBM latency 8-12 warps x 2-4 KB per SM is what
+// Little's law gives for the measured ~2.5 TB/s (profiles/r01_ncu_epi_variants_summary.csv: DRAM 40 %, L2 20 %, tensor
+// pipe 24 % busy).  Each epilogue thread therefore asks L2 for the residual row it will need for its NEXT tile while it
+// waits for the current tile's accumulator, turning the later loads into L2 hits.
+__device__ __forceinline__ void prefetch_residual_row(const ConvParams& p, int pixv, int ch0) {
+    if (pixv < 0) return;
+    const char* a = reinterpret_cast<const char*>(p.residual + (size_t)pixv * p.Cout + ch0);
+    for (int off = 0; off < p.n_tile * 2; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + off));
 }
 
 // ---------------------------------------------------------------------------------
@@ -586,6 +598,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int b = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
             const bool valid = (bb < p.bt) && (b < p.B) && (h < p.H) && (w < p.W);
             const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
+            if (p.prefetch_res && tile + ngroups * (int)gridDim.x < p.num_tiles) {
+                const TileCoord tn = decode_tile(p, tile + ngroups * (int)gridDim.x);
+                const int bn = tn.b0 + bb, hn = tn.h0 + hh, wn = tn.w0 + ww;
+                const bool vn = (bb < p.bt) && (bn < p.B) && (hn < p.H) && (wn < p.W);
+                prefetch_residual_row(p, vn ? (bn * p.H + hn) * p.W + wn : -1, tn.g * p.cout_g + tn.n_idx * p.n_tile);
+            }
 
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
@@ -960,6 +978,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int h = t.h0 + hh, w = t.w0 + ww, b = t.b + bb;
             const bool valid = (hh < p.ht) && (h < p.H) && (w < p.W) && (b < p.B);
             const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
+            if (p.prefetch_res && tile + ngroups < t_end) {
+                const HaloTile tn = decode_halo_tile(p, tile + ngroups);
+                const int hn = tn.h0 + hh, wn = tn.w0 + ww, bn = tn.b + bb;
+                const bool vn = (hh < p.ht) && (hn < p.H) && (wn < p.W) && (bn < p.B);
+                prefetch_residual_row(p, vn ? (bn * p.H + hn) * p.W + wn : -1, tn.g * p.cout_g + tn.n_idx * p.n_tile);
+            }
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
@@ -1083,6 +1107,12 @@ int choose_epi_warps(const ConvParams& p) {
 // single-output ones are within +-5 % either way (both variants move the same bytes at ~3 TB/s of algorithmic traffic,
 // i.e. coalescing was not what limits them), so they keep the direct path.  DD_EPI_STAGED=0/1 forces one variant (tuning).
 constexpr uint32_t kSlabBytes = 4096;
+constexpr bool kPrefetchResidualDefault = false;
+int want_residual_prefetch(const ConvParams& p) {
+    bool on = kPrefetchResidualDefault;
+    if (const char* f = getenv("DD_EPI_PREFETCH")) on = atoi(f) != 0;
+    return (on && p.epi == DD_EPI_RESIDUAL) ? 1 : 0;
+}
 bool want_staged_epilogue(const ConvParams& p) {
     bool on = p.epi2 != DD_EPI2_NONE;
     if (const char* f = getenv("DD_EPI_STAGED")) on = atoi(f) != 0;
@@ -1154,6 +1184,7 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     while (cols < (uint32_t)(p.nbuf * p.n_tile * p.nacc)) cols <<= 1;
     p.tmem_cols = cols;
     const int ew = choose_epi_warps(p);
+    p.prefetch_res = want_residual_prefetch(p);
     const bool staged = want_staged_epilogue(p) && p.ksplit == 1;
     const uint32_t slabs_bytes = staged ? (uint32_t)ew * kSlabBytes : 0u;
     p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u - slabs_bytes) / stage_bytes)));
@@ -1261,6 +1292,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     p.ks_last = (cin_g - 64 * (p.kchunks - 1)) / 16;
     p.k_iters = p.kchunks;
     p.nacc = 1;
+    p.prefetch_res = want_residual_prefetch(p);
     const bool staged = want_staged_epilogue(p);
     // direct epilogue: 214 KB of operands; staged: 224 KB shared between operands and the 4 KB-per-warp slabs (the output
     // tile width is chosen as if there were 4 epilogue warps, then the warp count is cut back to what still fits)

@@ -36,12 +36,17 @@ MODES = [
 ]
 
 
-def run(x, wp, k, g, kw, staged, ew):
+def setenv(staged, ew, prefetch=0):
     os.environ["DD_EPI_STAGED"] = "1" if staged else "0"
+    os.environ["DD_EPI_PREFETCH"] = "1" if prefetch else "0"
     if ew:
         os.environ["DD_FORCE_EPI_WARPS"] = str(ew)
     else:
         os.environ.pop("DD_FORCE_EPI_WARPS", None)
+
+
+def run(x, wp, k, g, kw, staged, ew, prefetch=0):
+    setenv(staged, ew, prefetch)
     B, H, W, _ = x.shape
     Cout = wp.shape[0]
     # poison the outputs so rows the kernel must not touch / forgets to write show up
@@ -70,16 +75,20 @@ def main():
                 kw["residual"] = torch.randn(B, H, W, Cout, generator=gen).to(dev).to(torch.bfloat16)
             for ew in ((0,) if big else (0, 4, 8, 12)):
                 ref = run(x, wp, k, g, kw, False, ew)
-                got = run(x, wp, k, g, kw, True, ew)
-                n += 1
-                for i, (a, b) in enumerate(zip(ref, got)):
-                    if not torch.equal(a.view(torch.int16), b.view(torch.int16)):
-                        bad += 1
-                        d = (a.float() - b.float()).abs()
-                        print(f"MISMATCH {(B, H, W, Cin, Cout, k, g)} {name} ew={ew} out{i}: "
-                              f"{int((d > 0).sum())} / {d.numel()} differ, max {float(d.max()):.4g}, "
-                              f"nan {int(torch.isnan(b.float()).sum())}; first (b,h,w,c): "
-                              f"{(d > 0).nonzero()[:6].tolist()}", flush=True)
+                variants = [("staged", run(x, wp, k, g, kw, True, ew))]
+                if "residual" in kw:        # next-tile residual prefetch (no effect on results)
+                    variants.append(("staged+prefetch", run(x, wp, k, g, kw, True, ew, 1)))
+                    variants.append(("direct+prefetch", run(x, wp, k, g, kw, False, ew, 1)))
+                for vname, got in variants:
+                    n += 1
+                    for i, (a, b) in enumerate(zip(ref, got)):
+                        if not torch.equal(a.view(torch.int16), b.view(torch.int16)):
+                            bad += 1
+                            d = (a.float() - b.float()).abs()
+                            print(f"MISMATCH {(B, H, W, Cin, Cout, k, g)} {name} {vname} ew={ew} out{i}: "
+                                  f"{int((d > 0).sum())} / {d.numel()} differ, max {float(d.max()):.4g}, "
+                                  f"nan {int(torch.isnan(b.float()).sum())}; first (b,h,w,c): "
+                                  f"{(d > 0).nonzero()[:6].tolist()}", flush=True)
     print(f"bit-exactness: {n} combinations, {bad} mismatching outputs", flush=True)
 
     shapes = [(2, 32, 688, 512, 256, 3, 8), (2, 32, 688, 256, 512, 3, 8), (2, 32, 688, 512, 1024, 3, 8),
@@ -95,13 +104,12 @@ def main():
                          ("res+silu2", dict(epi=L.EPI_RESIDUAL, alpha=0.5, beta=0.5, residual=res, epi2=L.EPI2_SILU)),
                          ("silu+raw2", dict(epi=L.EPI_SCALE_SILU, scale=sc, epi2=L.EPI2_RAW))):
             line = f"{(B, H, W, Cin, Cout, k, g)} {name:10s}"
-            for staged in (0, 1):
-                for ew in (0, 4, 8, 12):
-                    os.environ["DD_EPI_STAGED"] = str(staged)
-                    if ew:
-                        os.environ["DD_FORCE_EPI_WARPS"] = str(ew)
-                    else:
-                        os.environ.pop("DD_FORCE_EPI_WARPS", None)
+            full = os.environ.get("DD_CHECK_FULL_SWEEP") is not None
+            combos = [(st, ew, 0) for st in (0, 1) for ew in (0, 4, 8, 12)] if full else \
+                     [(st, 0, pf) for st in (0, 1) for pf in ((0, 1) if "residual" in kw else (0,))]
+            for staged, ew, pf in combos:
+                if True:
+                    setenv(staged, ew, pf)
                     out = torch.empty(B, H, W, Cout, device=dev, dtype=torch.bfloat16)
                     out2 = torch.empty_like(out) if kw.get("epi2") else None
                     for _ in range(3):
@@ -113,7 +121,7 @@ def main():
                         ops.mpconv(x, wp, k, g, out=out, out2=out2, **kw)
                     e1.record()
                     torch.cuda.synchronize()
-                    line += f" | s{staged} ew{ew or 'auto'} {e0.elapsed_time(e1) / 20 * 1e3:6.1f}"
+                    line += f" | s{staged} ew{ew or 'auto'} pf{pf} {e0.elapsed_time(e1) / 20 * 1e3:6.1f}"
             print(line, flush=True)
     return 1 if bad else 0
 
