@@ -365,6 +365,80 @@ def bench_ddec(device, batch: int = 4, steps: int = 3) -> dict:
                          "frac": flop * sps / 1e12 / pk["tflops"]}}
 
 
+def bench_optim(device, steps: int = 10, warmup: int = 3) -> dict:
+    """the optimizer-side sweep of one train step over the default UNet's 293 M fp32 parameters --
+    clip_grad_norm_ + AdamW + 2 EMA copies (one feeding back, config/models/default/unet_train.json) + normalize_weights --
+    as dd_grad_norm_clip + dd_optim_step_batched (3 launches).  HBM-bound; algorithmic bytes per parameter: 4 (norm) +
+    20 read + 12 written (p, g, m, v) + 8 per EMA copy = 52.  `unfused_torch` times the reference's own sequence of library
+    calls on the same GPU (clip_grad_norm_, torch AdamW fused=True, _foreach_lerp_ x3, per-tensor normalize + copy_)."""
+    from oracle import unet_oracle as uo
+    from dualdiffusion_b200.modules.unets.unet_edm2_b4 import UNet, UNetConfig
+    from dualdiffusion_b200.modules.mp_tools import MPConv
+    from dualdiffusion_b200.training.optim import FusedAdamW
+    from dualdiffusion_b200 import ops
+    spec = uo.default_spec()
+    cfg = UNetConfig(**{k: getattr(spec, k) for k in UNetConfig.__dataclass_fields__ if hasattr(spec, k)})
+    net = UNet(cfg).to(device).train()
+    params = list(net.parameters())
+    n_params = sum(p.numel() for p in params)
+    g = torch.Generator(device=device).manual_seed(7)
+    for p in params:
+        p.grad = torch.randn(p.shape, device=device, generator=g)
+    emas = [[p.detach().clone() for p in params] for _ in range(2)]
+    betas, fbs = [0.9999, 0.99999], [0.9999, None]
+    opt = FusedAdamW(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0)
+    opt.attach_module(net)
+    opt.attach_emas(emas, betas, fbs)
+
+    def timed(fn):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    def ours():
+        opt.clip_grad_norm_(10.0)
+        opt.step()
+
+    l0 = ops.launch_count
+    ms = timed(ours)
+    launches = (ops.launch_count - l0) // (steps + warmup)
+    bytes_per_param = 4 + 32 + 8 * len(emas)
+    gbs = n_params * bytes_per_param / (ms * 1e-3) / 1e9
+    pk = peaks()
+    out = {"metric": "optimizer-side sweep (clip + AdamW + 2 EMA + normalize_weights) over the default UNet's parameters",
+           "value": 1e3 / ms, "unit": "sweeps/s", "ms": ms, "params": n_params, "gpu_launches_per_step": launches,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                        "bytes_per_param": bytes_per_param}}
+    try:
+        convs = [m for m in net.modules() if isinstance(m, MPConv) and not m.disable_weight_norm]
+        ref_opt = torch.optim.AdamW(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0, fused=True)
+
+        def unfused():
+            with torch.no_grad():
+                torch.nn.utils.clip_grad_norm_(params, 10.0)
+                ref_opt.step()
+                for e, b, fb in zip(emas, betas, fbs):
+                    torch._foreach_lerp_(e, params, 1 - b)
+                    if fb is not None:
+                        torch._foreach_lerp_(params, e, 1 - fb)
+                for c in convs:                                   # mp_tools.py:42-49,375-378 in library calls
+                    w = c.weight
+                    n = torch.linalg.vector_norm(w, dim=list(range(1, w.ndim)), keepdim=True)
+                    w.copy_(w / (1e-4 + n * (n.numel() / w.numel()) ** 0.5))
+        ms_ref = timed(unfused)
+        out["unfused_torch"] = {"ms": ms_ref, "speedup": ms_ref / ms}
+    except Exception as exc:
+        out["unfused_torch"] = {"error": repr(exc)}
+    return out
+
+
 def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -517,6 +591,15 @@ def run_ours(args) -> None:
     if rank == 0 and world == 1 and not args.no_format:
         secondary = bench_format(device)
 
+    optim = None
+    if rank == 0 and world == 1 and not args.no_train:
+        # last on purpose: every other number is already on the host when this leg runs, and it must never cost the line
+        try:
+            torch.cuda.empty_cache()
+            optim = bench_optim(device)
+        except Exception as exc:
+            optim = {"error": repr(exc)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -527,7 +610,8 @@ def run_ours(args) -> None:
                            "library": os.path.relpath(_lib.lib_path(), ROOT)},
                 "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
-                "train_step": train, "dae_decode": dae, "ddec_forward": ddec, "secondary": secondary}
+                "train_step": train, "dae_decode": dae, "ddec_forward": ddec, "secondary": secondary,
+                "optim_step": optim}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:

@@ -57,6 +57,29 @@ class AffineBwdDesc(C.Structure):
                 ("O", c_int), ("I", c_int), ("groups", c_int), ("normalize", c_int)]
 
 
+OPTIM_MAX_EMA = 4
+GNORM_CHUNK = 8192
+
+
+class GnormDesc(C.Structure):
+    """struct dd_gnorm_desc"""
+    _fields_ = [("g", c_void_p), ("numel", C.c_longlong), ("chunk_begin", c_int), ("_pad", c_int)]
+
+
+class OptimDesc(C.Structure):
+    """struct dd_optim_desc"""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("ema", c_void_p * OPTIM_MAX_EMA),
+                ("numel", C.c_longlong), ("rows", c_int), ("row_len", c_int), ("normalize", c_int), ("row_begin", c_int)]
+
+
+class OptimHyper(C.Structure):
+    """struct dd_optim_hyper"""
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("bias_correction1", C.c_double), ("bias_correction2", C.c_double),
+                ("ema_beta", C.c_double * OPTIM_MAX_EMA), ("feedback_beta", C.c_double * OPTIM_MAX_EMA),
+                ("ema_is_f64", c_int * OPTIM_MAX_EMA), ("n_ema", c_int)]
+
+
 EPI_NONE, EPI_SCALE_SILU, EPI_RESIDUAL = 0, 1, 2
 EPI2_NONE, EPI2_SILU, EPI2_SCALE, EPI2_RAW = 0, 1, 2, 3
 WFMT_BF16_OTI, WFMT_F32_OIT = 0, 1
@@ -141,6 +164,8 @@ _SIGNATURES = {
     "dd_dae_enc_patches": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_dae_latents_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
+    "dd_grad_norm_clip": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
+    "dd_optim_step_batched": (c_int, [c_void_p, c_int, c_int, C.POINTER(OptimHyper), c_void_p, c_void_p]),
     "dd_sampler_update": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                   c_int, c_long, c_void_p]),
 }

@@ -1,0 +1,277 @@
+// Optimizer-side sweep of the train step: what the reference trainer does after backward() as
+// 3-4 full passes over the 293 M parameters --
+//   accelerator.clip_grad_norm_        training/trainer.py:1044   (norm of all gradients, then g *= coef)
+//   optimizer.step()  (torch AdamW)    training/trainer.py:461-473,1062
+//   ema_manager.update()               training/ema.py:284-313    (_foreach_lerp_ per EMA, optional feedback lerp)
+//   module.normalize_weights()         training/trainer.py:1107-1108 -> modules/mp_tools.py:375-378
+// -- as two launches: a deterministic two-stage gradient norm that leaves {norm, clip coefficient} on the device, and one
+// batched launch (CTA per weight row, descriptor table) that reads p, g, m, v and the EMA copies once, applies
+// clip * AdamW, the EMA / feedback lerps and the per-row re-normalisation, and writes each of them once.
+// HBM-bound streaming work: 20 B read + 12 B written per parameter, + 8 B per fp32 EMA (16 B per fp64 EMA).
+#include "common.cuh"
+#include "dualdiffusion_b200.h"
+
+namespace {
+
+constexpr float kNormEps = 1e-4f;   // modules/mp_tools.py:43
+constexpr int kNormChunk = DD_GNORM_CHUNK;    // gradient elements per CTA of the norm kernel
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float warp_sum_o(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float block_sum_o(float v, float* red) {
+    v = warp_sum_o(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (lane < nw) ? red[lane] : 0.f;
+    t = warp_sum_o(t);
+    __syncthreads();
+    return t;
+}
+
+// torch.lerp's two-sided formula (ATen/native/Lerp.h): exact at both ends of the weight range
+template <typename T>
+__device__ __forceinline__ T lerp_t(T a, T b, T w) {
+    return (w < T(0.5)) ? a + w * (b - a) : b - (b - a) * (T(1) - w);
+}
+
+template <typename D>
+__device__ __forceinline__ int find_desc(const D* __restrict__ descs, int n_descs, int unit) {
+    int lo = 0, hi = n_descs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].chunk_begin <= unit) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// stage 1: partials[cta] = sum of squares of one 8192-element chunk of one gradient tensor
+__global__ void __launch_bounds__(kThreads) grad_sqnorm_partial_kernel(const dd_gnorm_desc* __restrict__ descs,
+                                                                       int n_descs, float* __restrict__ partials) {
+    __shared__ float red[32];
+    const int di = find_desc(descs, n_descs, (int)blockIdx.x);
+    const dd_gnorm_desc d = descs[di];
+    const long long begin = (long long)(blockIdx.x - d.chunk_begin) * kNormChunk;
+    const long long rem = d.numel - begin;
+    const int n = (int)(rem < (long long)kNormChunk ? rem : (long long)kNormChunk);
+    const float* g = d.g + begin;
+    float ss = 0.f;
+    if (n > 0) {
+        if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+            const float4* g4 = reinterpret_cast<const float4*>(g);
+            const int n4 = n >> 2;
+            for (int i = threadIdx.x; i < n4; i += kThreads) {
+                const float4 x = __ldg(g4 + i);
+                ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+            }
+            for (int i = (n4 << 2) + threadIdx.x; i < n; i += kThreads) ss += g[i] * g[i];
+        } else {
+            for (int i = threadIdx.x; i < n; i += kThreads) ss += g[i] * g[i];
+        }
+    }
+    ss = block_sum_o(ss, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = ss;
+}
+
+// stage 2 (one CTA): fixed-order double accumulation of the partials -> out[0] = ||g||, out[1] = clip coefficient
+// torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1 (NaN propagates, as torch.clamp does)
+__global__ void __launch_bounds__(kThreads) grad_norm_finish_kernel(const float* __restrict__ partials, int n,
+                                                                    float max_norm, float* __restrict__ out) {
+    __shared__ double red[kThreads];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += kThreads) s += (double)partials[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float norm = (float)sqrt(red[0]);
+        float coef = max_norm / (norm + 1e-6f);
+        if (coef > 1.f) coef = 1.f;               // false for NaN: stays NaN
+        if (!(max_norm > 0.f)) coef = 1.f;        // max_norm <= 0: report the norm only
+        out[0] = norm;
+        out[1] = coef;
+    }
+}
+
+struct OptimHyperDev {
+    float decay, w_m, beta2, w_v, eps, step_size, bc2_sqrt;
+    int use_decay, n_ema;
+    float ema_w[DD_OPTIM_MAX_EMA];        // 1 - beta_k
+    double ema_w64[DD_OPTIM_MAX_EMA];     // the same weight for fp64 EMA copies (EMA_Config.use_float64, ema.py:198)
+    float fb_w[DD_OPTIM_MAX_EMA];         // 1 - feedback_beta_k, < 0: no feedback
+    int ema_is_f64[DD_OPTIM_MAX_EMA];
+};
+
+// torch.optim.AdamW, single-tensor formulation (torch/optim/adam.py _single_tensor_adam with decoupled decay):
+//   p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;  p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+__device__ __forceinline__ float adamw_elem(float pi, float gi, float& mi, float& vi, const OptimHyperDev& h) {
+    if (h.use_decay) pi *= h.decay;
+    mi = lerp_t(mi, gi, h.w_m);
+    vi = h.beta2 * vi + h.w_v * gi * gi;
+    const float denom = sqrtf(vi) / h.bc2_sqrt + h.eps;
+    return pi - h.step_size * (mi / denom);
+}
+
+// ema.py:307-313: ema_k = lerp(ema_k, p, 1-beta_k); if feedback: p = lerp(p, ema_k, 1-feedback_beta_k), in config order
+template <typename E>
+__device__ __forceinline__ float ema_elem(float pi, E& ei, E w, float fb_w) {
+    ei = lerp_t(ei, (E)pi, w);
+    if (fb_w >= 0.f) pi = lerp_t(pi, (float)ei, fb_w);
+    return pi;
+}
+
+// One CTA per row of one parameter tensor viewed as [rows][row_len].  Pass 1 updates m, v, p and the EMA copies and
+// accumulates the row's sum of squares; pass 2 (normalize != 0) rescales the row: every thread re-reads exactly the
+// elements it wrote itself, so no fence is needed and the second read is served from L1/L2.
+__global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_optim_desc* __restrict__ descs, int n_descs,
+                                                                      OptimHyperDev h, const float* __restrict__ clip_coef) {
+    __shared__ float red[32];
+    int lo = 0, hi = n_descs - 1;
+    const int unit = blockIdx.x;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].row_begin <= unit) lo = mid; else hi = mid - 1;
+    }
+    const dd_optim_desc d = descs[lo];
+    const int r = unit - d.row_begin;
+    if (r >= d.rows) return;
+    const size_t base = (size_t)r * d.row_len;
+    const long long tail = d.numel - (long long)base;
+    const int f = (int)(tail < (long long)d.row_len ? tail : (long long)d.row_len);
+    float* p = d.p + base;
+    const float* g = d.g + base;
+    float* m = d.m + base;
+    float* v = d.v + base;
+    const float coef = clip_coef ? clip_coef[1] : 1.f;
+
+    // 128-bit path: every stream of this row 16-byte aligned, all EMA copies fp32
+    uintptr_t align = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                      reinterpret_cast<uintptr_t>(v) | (uintptr_t)(f & 3) * 4u;
+    bool any_f64 = false;
+#pragma unroll
+    for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k)
+        if (k < h.n_ema && d.ema[k] != nullptr) {
+            any_f64 |= h.ema_is_f64[k] != 0;
+            align |= reinterpret_cast<uintptr_t>(static_cast<float*>(d.ema[k]) + base);
+        }
+    const bool vec = !any_f64 && (align & 15u) == 0;
+
+    float ss = 0.f;
+    if (vec) {
+        const int f4 = f >> 2;
+        for (int i = threadIdx.x; i < f4; i += kThreads) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+            float4 p4 = reinterpret_cast<float4*>(p)[i];
+            float4 m4 = reinterpret_cast<float4*>(m)[i];
+            float4 v4 = reinterpret_cast<float4*>(v)[i];
+            p4.x = adamw_elem(p4.x, g4.x * coef, m4.x, v4.x, h);
+            p4.y = adamw_elem(p4.y, g4.y * coef, m4.y, v4.y, h);
+            p4.z = adamw_elem(p4.z, g4.z * coef, m4.z, v4.z, h);
+            p4.w = adamw_elem(p4.w, g4.w * coef, m4.w, v4.w, h);
+            reinterpret_cast<float4*>(m)[i] = m4;
+            reinterpret_cast<float4*>(v)[i] = v4;
+#pragma unroll
+            for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k) {
+                if (k < h.n_ema && d.ema[k] != nullptr) {
+                    float4* e = reinterpret_cast<float4*>(static_cast<float*>(d.ema[k]) + base) + i;
+                    float4 e4 = *e;
+                    p4.x = ema_elem(p4.x, e4.x, h.ema_w[k], h.fb_w[k]);
+                    p4.y = ema_elem(p4.y, e4.y, h.ema_w[k], h.fb_w[k]);
+                    p4.z = ema_elem(p4.z, e4.z, h.ema_w[k], h.fb_w[k]);
+                    p4.w = ema_elem(p4.w, e4.w, h.ema_w[k], h.fb_w[k]);
+                    *e = e4;
+                }
+            }
+            reinterpret_cast<float4*>(p)[i] = p4;
+            ss += p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < f; i += kThreads) {
+            float mi = m[i], vi = v[i];
+            float pi = adamw_elem(p[i], g[i] * coef, mi, vi, h);
+            m[i] = mi;
+            v[i] = vi;
+#pragma unroll
+            for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k) {
+                if (k < h.n_ema && d.ema[k] != nullptr) {
+                    if (h.ema_is_f64[k]) {
+                        double* e = static_cast<double*>(d.ema[k]) + base + i;
+                        double ei = *e;
+                        pi = ema_elem(pi, ei, h.ema_w64[k], h.fb_w[k]);
+                        *e = ei;
+                    } else {
+                        float* e = static_cast<float*>(d.ema[k]) + base + i;
+                        float ei = *e;
+                        pi = ema_elem(pi, ei, h.ema_w[k], h.fb_w[k]);
+                        *e = ei;
+                    }
+                }
+            }
+            p[i] = pi;
+            ss += pi * pi;
+        }
+    }
+    if (!d.normalize) return;                 // uniform over the CTA (descriptor field)
+    ss = block_sum_o(ss, red);
+    const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)f));
+    if (vec) {
+        const int f4 = f >> 2;
+        for (int i = threadIdx.x; i < f4; i += kThreads) {
+            float4 p4 = reinterpret_cast<float4*>(p)[i];
+            p4.x *= inv; p4.y *= inv; p4.z *= inv; p4.w *= inv;
+            reinterpret_cast<float4*>(p)[i] = p4;
+        }
+    } else {
+        for (int i = threadIdx.x; i < f; i += kThreads) p[i] *= inv;
+    }
+}
+
+}  // namespace
+
+extern "C" int dd_grad_norm_clip(const dd_gnorm_desc* descs_dev, int n_descs, int total_chunks, float* partials_dev,
+                                 float max_norm, float* out_norm_coef_dev, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && partials_dev && out_norm_coef_dev && n_descs > 0 && total_chunks > 0,
+               "dd_grad_norm_clip: bad arguments");
+    grad_sqnorm_partial_kernel<<<total_chunks, kThreads, 0, stream>>>(descs_dev, n_descs, partials_dev);
+    DD_CHECK_LAUNCH();
+    grad_norm_finish_kernel<<<1, kThreads, 0, stream>>>(partials_dev, total_chunks, max_norm, out_norm_coef_dev);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_optim_step_batched(const dd_optim_desc* descs_dev, int n_descs, int total_rows,
+                                     const dd_optim_hyper* hy, const float* norm_coef_dev, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(descs_dev && hy && n_descs > 0 && total_rows > 0, "dd_optim_step_batched: bad arguments");
+    DD_REQUIRE(hy->n_ema >= 0 && hy->n_ema <= DD_OPTIM_MAX_EMA, "dd_optim_step_batched: n_ema=%d out of range", hy->n_ema);
+    DD_REQUIRE(hy->bias_correction1 > 0.0 && hy->bias_correction2 > 0.0,
+               "dd_optim_step_batched: bias corrections must be positive (step >= 1)");
+    OptimHyperDev h{};
+    h.use_decay = hy->weight_decay != 0.0;
+    h.decay = (float)(1.0 - hy->lr * hy->weight_decay);
+    h.w_m = (float)(1.0 - hy->beta1);
+    h.beta2 = (float)hy->beta2;
+    h.w_v = (float)(1.0 - hy->beta2);
+    h.eps = (float)hy->eps;
+    h.step_size = (float)(hy->lr / hy->bias_correction1);
+    h.bc2_sqrt = (float)sqrt(hy->bias_correction2);
+    h.n_ema = hy->n_ema;
+    for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k) {
+        h.ema_w[k] = (float)(1.0 - hy->ema_beta[k]);
+        h.ema_w64[k] = 1.0 - hy->ema_beta[k];
+        h.fb_w[k] = hy->feedback_beta[k] >= 0.0 ? (float)(1.0 - hy->feedback_beta[k]) : -1.f;
+        h.ema_is_f64[k] = hy->ema_is_f64[k];
+    }
+    optim_step_batched_kernel<<<total_rows, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev);
+    DD_CHECK_LAUNCH();
+    return 0;
+}

@@ -398,6 +398,68 @@ def weight_prep_bwd(descs: Tensor, n: int, total_rows: int) -> None:
     _count()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# optimizer-side sweep: clip_grad_norm_ + AdamW + EMA lerps + normalize_weights in two launches
+# ---------------------------------------------------------------------------------------------------------
+OPTIM_FLAT_ROW = 4096       # row length used for tensors without weight-norm (scalars, gains, un-normalised weights)
+
+
+def pack_gnorm_descs(grads: Sequence[Tensor]):
+    """dd_gnorm_desc records for a list of fp32 gradient tensors; returns (ctypes array, total_chunks).  Host only."""
+    arr = (L.GnormDesc * len(grads))()
+    chunks = 0
+    for i, g in enumerate(grads):
+        n = g.numel()
+        arr[i] = L.GnormDesc(L.ptr(g), n, chunks, 0)
+        chunks += (n + L.GNORM_CHUNK - 1) // L.GNORM_CHUNK
+    return arr, chunks
+
+
+def pack_optim_descs(entries: Sequence[dict]):
+    """dd_optim_desc records (dicts with p, g, m, v, emas (list, <= 4), fan_in (0 = no weight-norm)); returns
+    (ctypes array, total_rows).  A weight-normalised tensor [O, ...] is viewed as O rows of fan_in elements (one CTA
+    per output channel, as mp_tools.normalize does); anything else is cut into rows of OPTIM_FLAT_ROW.  Host only."""
+    arr = (L.OptimDesc * len(entries))()
+    rows_total = 0
+    for i, e in enumerate(entries):
+        n = e["p"].numel()
+        fan_in = int(e.get("fan_in", 0))
+        if fan_in > 0:
+            if n % fan_in != 0:
+                raise ValueError(f"pack_optim_descs: numel {n} is not a multiple of fan_in {fan_in}")
+            rows, row_len, normalize = n // fan_in, fan_in, 1
+        else:
+            rows, row_len, normalize = (n + OPTIM_FLAT_ROW - 1) // OPTIM_FLAT_ROW, OPTIM_FLAT_ROW, 0
+        emas = list(e.get("emas", ()))
+        if len(emas) > L.OPTIM_MAX_EMA:
+            raise ValueError(f"pack_optim_descs: at most {L.OPTIM_MAX_EMA} EMA copies per launch")
+        ema_ptrs = (C.c_void_p * L.OPTIM_MAX_EMA)(*[L.ptr(t) for t in emas] + [None] * (L.OPTIM_MAX_EMA - len(emas)))
+        arr[i] = L.OptimDesc(L.ptr(e["p"]), L.ptr(e["g"]), L.ptr(e["m"]), L.ptr(e["v"]), ema_ptrs, n, rows, row_len,
+                             normalize, rows_total)
+        rows_total += rows
+    return arr, rows_total
+
+
+def descs_to_device(arr, device) -> Tensor:
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+
+
+def grad_norm_clip(descs: Tensor, n: int, total_chunks: int, partials: Tensor, max_norm: float, out: Tensor) -> None:
+    """out[0] = ||g||_2 over every described tensor, out[1] = clip_grad_norm_'s coefficient (2 launches)."""
+    L.require_cuda(descs, partials, out)
+    L.check(L.load().dd_grad_norm_clip(L.ptr(descs), n, total_chunks, L.ptr(partials), float(max_norm), L.ptr(out),
+                                       L.stream_ptr()))
+    _count(2)
+
+
+def optim_step_batched(descs: Tensor, n: int, total_rows: int, hyper: "L.OptimHyper",
+                       norm_coef: Optional[Tensor]) -> None:
+    L.require_cuda(descs, norm_coef)
+    L.check(L.load().dd_optim_step_batched(L.ptr(descs), n, total_rows, C.byref(hyper), L.ptr(norm_coef),
+                                           L.stream_ptr()))
+    _count()
+
+
 def silu_scale_bwd(dy: Tensor, coef: float, pre: Tensor, scale: Tensor, dscale: Tensor,
                    out: Optional[Tensor] = None) -> Tensor:
     B = dy.shape[0]

@@ -390,6 +390,51 @@ DD_API int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int W, 
  * (B, 2L, H/ratio, W/ratio), channel c*2+z.                                                                              */
 DD_API int dd_dae_latents_pool(const void* f, float* out, int B, int L, int H, int W, int pw, int Cst, int ratio, void* stream);
 
+/* ==== Optimizer-side sweep of the train step: clip_grad_norm_ (training/trainer.py:1044), torch AdamW
+ * step (trainer.py:461-473,1062), EMA / feedback-EMA lerps (training/ema.py:284-313) and normalize_weights
+ * (trainer.py:1107-1108, modules/mp_tools.py:375-378) in two launches over a parameter set.                          */
+
+/* Global L2 norm of a list of fp32 gradient tensors and the clip coefficient of torch.nn.utils.clip_grad_norm_:
+ * out[0] = ||g||_2, out[1] = min(1, max_norm / (||g|| + 1e-6)) (1 if max_norm <= 0).  Deterministic: one partial per
+ * 8192-element chunk (partials_dev holds total_chunks floats), summed in fixed order in fp64.                        */
+#define DD_GNORM_CHUNK 8192
+typedef struct dd_gnorm_desc {
+    const float* g;
+    long long numel;
+    int chunk_begin;     /* exclusive prefix sum of ceil(numel / DD_GNORM_CHUNK) over the descriptor array */
+    int _pad;
+} dd_gnorm_desc;
+DD_API int dd_grad_norm_clip(const dd_gnorm_desc* descs_dev, int n_descs, int total_chunks, float* partials_dev,
+                             float max_norm, float* out_norm_coef_dev, void* stream);
+
+/* One launch, one CTA per row: g' = g * coef (coef = norm_coef_dev[1], or 1 if NULL; g itself is not rewritten);
+ * AdamW (decoupled decay) on p, m, v; for k < n_ema in order: ema_k = lerp(ema_k, p, 1 - ema_beta[k]) and, if
+ * feedback_beta[k] >= 0, p = lerp(p, ema_k, 1 - feedback_beta[k]); finally, if normalize, every row of p viewed as
+ * [rows][row_len] is divided by (1e-4 + ||row|| / sqrt(row_len)).  The EMA copies receive the un-normalised post-step
+ * weights, as in the reference's order of calls.  Tensors without weight-norm are cut into rows of any convenient
+ * length with normalize = 0 (the last row may be short: numel bounds it).                                            */
+#define DD_OPTIM_MAX_EMA 4
+typedef struct dd_optim_desc {
+    float* p;            /* parameter, fp32, updated in place */
+    const float* g;      /* gradient, fp32 */
+    float* m;            /* exp_avg */
+    float* v;            /* exp_avg_sq */
+    void* ema[DD_OPTIM_MAX_EMA];   /* EMA copies of p (fp32, or fp64 where dd_optim_hyper.ema_is_f64[k]); NULL = skip */
+    long long numel;
+    int rows, row_len, normalize;
+    int row_begin;       /* exclusive prefix sum of rows over the descriptor array */
+} dd_optim_desc;
+typedef struct dd_optim_hyper {
+    double lr, beta1, beta2, eps, weight_decay;
+    double bias_correction1, bias_correction2;     /* 1 - beta^step, computed by the caller for this step */
+    double ema_beta[DD_OPTIM_MAX_EMA];
+    double feedback_beta[DD_OPTIM_MAX_EMA];        /* < 0: no feedback from this EMA */
+    int ema_is_f64[DD_OPTIM_MAX_EMA];
+    int n_ema;
+} dd_optim_hyper;
+DD_API int dd_optim_step_batched(const dd_optim_desc* descs_dev, int n_descs, int total_rows,
+                                 const dd_optim_hyper* hyper_host, const float* norm_coef_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,150 @@
+"""GPU parity tests of the optimizer-side sweep (dd_grad_norm_clip + dd_optim_step_batched through
+FusedAdamW) against the golden produced by the unmodified reference classes, the CPU oracle on seeded inputs, and
+size-independent properties at a parameter count of the order of the default UNet's.  fp32 arithmetic: tolerance
+1e-5 relative (fused multiply-adds and the reduction order differ from the CPU's), stated per assertion.
+
+The file name sorts last on purpose: these kernels were added after the round's last GPU session."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "optim_small.pt")
+RTOL, ATOL = 1e-5, 1e-7
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _tiny_module():
+    from dualdiffusion_b200.modules.mp_tools import MPConv
+
+    class Tiny(torch.nn.Module):         # mirrors tests/golden/make_golden_optim.py (same registration order)
+        def __init__(self):
+            super().__init__()
+            self.conv_a = MPConv(12, 16, (3, 3), groups=2)
+            self.conv_b = MPConv(16, 10, (1, 1))
+            self.linear = MPConv(40, 7, ())
+            self.free = MPConv(9, 5, (), disable_weight_norm=True)
+            self.gain = torch.nn.Parameter(torch.tensor(0.3))
+            self.vec = torch.nn.Parameter(torch.randn(5000))
+    return Tiny()
+
+
+def test_fused_step_replays_reference_golden():
+    from dualdiffusion_b200.training.optim import FusedAdamW
+    dev = _dev()
+    g = torch.load(GOLD, weights_only=False)
+    net = _tiny_module()
+    names = [n for n, _ in net.named_parameters()]
+    assert names == g["names"]
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            p.copy_(g["init"][n])
+    net = net.to(dev)
+    params = dict(net.named_parameters())
+    cfgs = list(g["emas"].items())
+    emas = [[g["init"][n].to(dev, torch.float64 if c.get("use_float64") else torch.float32).clone() for n in names]
+            for _, c in cfgs]
+    hy = g["hyper"]
+    opt = FusedAdamW(net.parameters(), lr=hy["lr"], betas=hy["betas"], eps=hy["eps"], weight_decay=0.0)
+    opt.attach_module(net)
+    opt.attach_emas(emas, [c["beta"] for _, c in cfgs], [c.get("feedback_beta") for _, c in cfgs])
+    for rec in g["steps"]:
+        opt.param_groups[0]["weight_decay"] = rec["weight_decay"]
+        for n in names:
+            params[n].grad = rec["grads"][n].to(dev)
+        norm = opt.clip_grad_norm_(hy["max_norm"])
+        opt.step()
+        assert abs(norm.item() - float(rec["grad_norm"])) <= 1e-6 * float(rec["grad_norm"])
+        for i, n in enumerate(names):
+            torch.testing.assert_close(params[n].detach().cpu(), rec["params"][n], rtol=RTOL, atol=ATOL, msg=f"param {n}")
+            st = opt.state[params[n]]
+            torch.testing.assert_close(st["exp_avg"].cpu(), rec["exp_avg"][n], rtol=RTOL, atol=1e-9, msg=f"exp_avg {n}")
+            torch.testing.assert_close(st["exp_avg_sq"].cpu(), rec["exp_avg_sq"][n], rtol=RTOL, atol=1e-12)
+            for k, (name, _) in enumerate(cfgs):
+                torch.testing.assert_close(emas[k][i].cpu(), rec["emas"][name][n], rtol=RTOL, atol=ATOL,
+                                           msg=f"ema {name} {n}")
+
+
+@pytest.mark.parametrize("rows,row_len,normalize", [(37, 1440, True), (5, 2560, True), (3, 54, True), (1, 70001, False),
+                                                    (64, 768, False)])
+def test_fused_step_matches_oracle_on_seeded_rows(rows, row_len, normalize):
+    """Both code paths of the kernel (128-bit and scalar, one and several strides per thread) against the CPU oracle."""
+    from dualdiffusion_b200 import ops
+    from dualdiffusion_b200.training.optim import make_hyper
+    from oracle import optim_oracle as oo
+    dev = _dev()
+    gen = torch.Generator().manual_seed(rows * 1000 + row_len)
+    p = torch.randn(rows, row_len, generator=gen)
+    gr = torch.randn(rows, row_len, generator=gen) * 3
+    m = torch.randn(rows, row_len, generator=gen) * 0.1
+    v = torch.rand(rows, row_len, generator=gen) * 0.01
+    e1, e2 = torch.randn(rows, row_len, generator=gen), torch.randn(rows, row_len, generator=gen)
+    ref = dict(p={"w": p.clone()}, g={"w": gr}, m={"w": m.clone()}, v={"w": v.clone()},
+               emas=[{"w": e1.clone()}, {"w": e2.clone()}])
+    oo.train_update(ref["p"], ref["g"], ref["m"], ref["v"], 7, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.02,
+                    max_norm=None, emas=ref["emas"], ema_betas=[0.999, 0.9], feedback_betas=[None, 0.99],
+                    fan_in={"w": row_len if normalize else 0})
+    t = [x.to(dev).contiguous() for x in (p, gr, m, v, e1, e2)]
+    arr, total = ops.pack_optim_descs([dict(p=t[0], g=t[1], m=t[2], v=t[3], emas=[t[4], t[5]],
+                                            fan_in=row_len if normalize else 0)])
+    hyper = make_hyper(3e-3, (0.9, 0.99), 1e-8, 0.02, 7.0, [0.999, 0.9], [None, 0.99], [0, 0])
+    ops.optim_step_batched(ops.descs_to_device(arr, dev), 1, total, hyper, None)
+    torch.testing.assert_close(t[0].cpu(), ref["p"]["w"], rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(t[2].cpu(), ref["m"]["w"], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(t[3].cpu(), ref["v"]["w"], rtol=RTOL, atol=1e-9)
+    torch.testing.assert_close(t[4].cpu(), ref["emas"][0]["w"], rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(t[5].cpu(), ref["emas"][1]["w"], rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(t[1].cpu(), gr, rtol=0, atol=0)          # gradients are never rewritten
+
+
+def test_grad_norm_is_deterministic_and_matches_a_double_sum_at_unet_size():
+    from dualdiffusion_b200 import ops
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(5)
+    grads = [torch.randn(n, device=dev, generator=gen) for n in (293_000_003, 1, 8192, 8193, 7)]
+    arr, chunks = ops.pack_gnorm_descs(grads)
+    descs = ops.descs_to_device(arr, dev)
+    partials = torch.empty(chunks, device=dev)
+    outs = []
+    for _ in range(2):
+        out = torch.empty(2, device=dev)
+        ops.grad_norm_clip(descs, len(grads), chunks, partials, 10.0, out)
+        outs.append(out.cpu())
+    assert torch.equal(outs[0], outs[1])
+    ref = float(torch.sqrt(sum((g.double() ** 2).sum() for g in grads)))
+    assert abs(float(outs[0][0]) - ref) <= 2e-6 * ref
+    assert abs(float(outs[0][1]) - min(1.0, 10.0 / (ref + 1e-6))) <= 2e-6
+
+
+def test_fused_step_properties_at_scale():
+    """~50 M parameters in UNet-like tensors: re-normalised rows have unit RMS, the un-normalised tensor equals torch's
+    own AdamW on the device, the EMA copy is lerp(ema, p_post_step, 1 - beta), the flat tail row is handled."""
+    from dualdiffusion_b200.training.optim import FusedAdamW
+    dev = _dev()
+    gen = torch.Generator(device=dev).manual_seed(9)
+    w = torch.nn.Parameter(torch.randn(8192, 2560, device=dev, generator=gen))       # normalised, 128-bit path
+    q = torch.nn.Parameter(torch.randn(30_000_001, device=dev, generator=gen))       # flat, short scalar tail row
+    for t in (w, q):
+        t.grad = torch.randn(t.shape, device=dev, generator=gen)
+    ema_q0 = torch.randn(q.shape, device=dev, generator=gen)
+    ema = [torch.randn(w.shape, device=dev, generator=gen), ema_q0.clone()]
+    ref_q = torch.nn.Parameter(q.detach().clone())
+    ref_q.grad = q.grad.clone()
+    ref_opt = torch.optim.AdamW([ref_q], lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
+    opt = FusedAdamW([w, q], lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
+    opt._fan_in[id(w)] = 2560
+    opt.attach_emas([ema], [0.999])
+    opt.step()
+    ref_opt.step()
+    torch.testing.assert_close(q.detach(), ref_q.detach(), rtol=RTOL, atol=1e-6)
+    torch.testing.assert_close(ema[1], torch.lerp(ema_q0, ref_q.detach(), 1e-3), rtol=RTOL, atol=1e-6)
+    rms = w.detach().pow(2).mean(dim=1).sqrt()
+    assert float((rms - 1).abs().max()) < 2e-4
+    assert int(opt.state[q]["step"]) == 1 and opt.state[w]["exp_avg"].shape == w.shape
