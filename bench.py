@@ -201,11 +201,12 @@ def bench_format(device) -> dict:
             "encode_plus_decode": {"value": B / (t_enc + t_dec), "unit": "stereo samples/s"}}
 
 
-def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> dict:
+def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3, fused_optimizer: bool = False) -> dict:
     """BASELINE.json configs[3]: UNet train step forward + backward (bf16 tensor-core compute, fp32 master parameters and
     gradients), device batch 4 of the 45 s latent per GPU, gradients all-reduced (mean) over NCCL overlapped with the
-    backward when world > 1.  Loss = unet_trainer.py:259-280.  The optimizer (torch AdamW in the reference) is not part
-    of the path."""
+    backward when world > 1.  Loss = unet_trainer.py:259-280.  With `fused_optimizer` the step also runs the optimizer-side
+    sweep (clip_grad_norm_ + AdamW + 2 EMA copies + normalize_weights through FusedAdamW),
+    i.e. everything trainer.py:1001-1108 does per optimizer step."""
     import torch.nn.functional as F
     from oracle import unet_oracle as uo          # seeded synthetic weights only
     from dualdiffusion_b200.ddp import GradAllReducer
@@ -227,6 +228,13 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> di
     mask = torch.ones(B, device=device, dtype=torch.bool)
     sig = sigma.view(-1, 1, 1, 1)
     w = (sig ** 2 + spec.sigma_data ** 2) / (sig * spec.sigma_data) ** 2
+    opt = None
+    if fused_optimizer:
+        from dualdiffusion_b200.training.optim import FusedAdamW
+        plist = list(net.parameters())
+        opt = FusedAdamW(plist, lr=1e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0)
+        opt.attach_module(net)
+        opt.attach_emas([[p.detach().clone() for p in plist] for _ in range(2)], [0.9999, 0.99999], [0.9999, None])
 
     def step():
         net.zero_grad(set_to_none=True)
@@ -240,6 +248,9 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> di
         logvar = net.get_sigma_loss_logvar(sigma)
         loss = (wl / logvar.exp() + logvar).mean()
         loss.backward()
+        if opt is not None:
+            opt.clip_grad_norm_(10.0)
+            opt.step()
         return loss
 
     for _ in range(warmup):
@@ -263,7 +274,8 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3) -> di
     pk = peaks()
     flop = 3 * FLOP_PER_STEP / 4              # fwd + dgrad + wgrad of one sample-forward (0.489 TFLOP)
     gn = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in net.parameters() if p.grad is not None)))
-    return {"metric": "UNet train step fwd+bwd samples/sec (device batch 4 x 4x32x688, bf16 compute, fp32 grads)",
+    what = "fwd+bwd+clip+AdamW+2 EMA+normalize_weights" if fused_optimizer else "fwd+bwd"
+    return {"metric": f"UNet train step {what} samples/sec (device batch 4 x 4x32x688, bf16 compute, fp32 grads)",
             "value": sps, "unit": "samples/s", "ms_per_step": ms / steps, "n_gpus": world, "global_batch": world * B,
             "allreduce_bytes_per_step": net.grad_sync.bytes_reduced // max(1, steps + warmup),
             "gpu_launches_per_step": (ops.launch_count - l0) // steps, "loss": float(loss.detach()), "grad_norm": gn,
@@ -599,6 +611,11 @@ def run_ours(args) -> None:
             optim = bench_optim(device)
         except Exception as exc:
             optim = {"error": repr(exc)}
+        try:
+            torch.cuda.empty_cache()
+            optim["train_step_with_optimizer"] = bench_train(device, dist, world, fused_optimizer=True)
+        except Exception as exc:
+            optim["train_step_with_optimizer"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
