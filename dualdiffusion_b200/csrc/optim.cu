@@ -10,10 +10,10 @@
 // HBM-bound streaming work: 20 B read + 12 B written per parameter, + 8 B per fp32 EMA (16 B per fp64 EMA).
 #include "common.cuh"
 #include "dualdiffusion_b200.h"
+#include "optim_math.cuh"
 
 namespace {
 
-constexpr float kNormEps = 1e-4f;   // modules/mp_tools.py:43
 constexpr int kNormChunk = DD_GNORM_CHUNK;    // gradient elements per CTA of the norm kernel
 constexpr int kThreads = 256;
 
@@ -32,12 +32,6 @@ __device__ __forceinline__ float block_sum_o(float v, float* red) {
     t = warp_sum_o(t);
     __syncthreads();
     return t;
-}
-
-// torch.lerp's two-sided formula (ATen/native/Lerp.h): exact at both ends of the weight range
-template <typename T>
-__device__ __forceinline__ T lerp_t(T a, T b, T w) {
-    return (w < T(0.5)) ? a + w * (b - a) : b - (b - a) * (T(1) - w);
 }
 
 template <typename D>
@@ -93,39 +87,9 @@ __global__ void __launch_bounds__(kThreads) grad_norm_finish_kernel(const float*
     }
     if (threadIdx.x == 0) {
         const float norm = (float)sqrt(red[0]);
-        float coef = max_norm / (norm + 1e-6f);
-        if (coef > 1.f) coef = 1.f;               // false for NaN: stays NaN
-        if (!(max_norm > 0.f)) coef = 1.f;        // max_norm <= 0: report the norm only
         out[0] = norm;
-        out[1] = coef;
+        out[1] = clip_coef_from_norm(norm, max_norm);
     }
-}
-
-struct OptimHyperDev {
-    float decay, w_m, beta2, w_v, eps, step_size, bc2_sqrt;
-    int use_decay, n_ema;
-    float ema_w[DD_OPTIM_MAX_EMA];        // 1 - beta_k
-    double ema_w64[DD_OPTIM_MAX_EMA];     // the same weight for fp64 EMA copies (EMA_Config.use_float64, ema.py:198)
-    float fb_w[DD_OPTIM_MAX_EMA];         // 1 - feedback_beta_k, < 0: no feedback
-    int ema_is_f64[DD_OPTIM_MAX_EMA];
-};
-
-// torch.optim.AdamW, single-tensor formulation (torch/optim/adam.py _single_tensor_adam with decoupled decay):
-//   p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = b2*v + (1-b2)*g*g;  p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
-__device__ __forceinline__ float adamw_elem(float pi, float gi, float& mi, float& vi, const OptimHyperDev& h) {
-    if (h.use_decay) pi *= h.decay;
-    mi = lerp_t(mi, gi, h.w_m);
-    vi = h.beta2 * vi + h.w_v * gi * gi;
-    const float denom = sqrtf(vi) / h.bc2_sqrt + h.eps;
-    return pi - h.step_size * (mi / denom);
-}
-
-// ema.py:307-313: ema_k = lerp(ema_k, p, 1-beta_k); if feedback: p = lerp(p, ema_k, 1-feedback_beta_k), in config order
-template <typename E>
-__device__ __forceinline__ float ema_elem(float pi, E& ei, E w, float fb_w) {
-    ei = lerp_t(ei, (E)pi, w);
-    if (fb_w >= 0.f) pi = lerp_t(pi, (float)ei, fb_w);
-    return pi;
 }
 
 // One CTA per row of one parameter tensor viewed as [rows][row_len].  Pass 1 updates m, v, p and the EMA copies and
@@ -221,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_o
     }
     if (!d.normalize) return;                 // uniform over the CTA (descriptor field)
     ss = block_sum_o(ss, red);
-    const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)f));
+    const float inv = row_inv_norm(ss, f);
     if (vec) {
         const int f4 = f >> 2;
         for (int i = threadIdx.x; i < f4; i += kThreads) {
@@ -255,22 +219,7 @@ extern "C" int dd_optim_step_batched(const dd_optim_desc* descs_dev, int n_descs
     DD_REQUIRE(hy->n_ema >= 0 && hy->n_ema <= DD_OPTIM_MAX_EMA, "dd_optim_step_batched: n_ema=%d out of range", hy->n_ema);
     DD_REQUIRE(hy->bias_correction1 > 0.0 && hy->bias_correction2 > 0.0,
                "dd_optim_step_batched: bias corrections must be positive (step >= 1)");
-    OptimHyperDev h{};
-    h.use_decay = hy->weight_decay != 0.0;
-    h.decay = (float)(1.0 - hy->lr * hy->weight_decay);
-    h.w_m = (float)(1.0 - hy->beta1);
-    h.beta2 = (float)hy->beta2;
-    h.w_v = (float)(1.0 - hy->beta2);
-    h.eps = (float)hy->eps;
-    h.step_size = (float)(hy->lr / hy->bias_correction1);
-    h.bc2_sqrt = (float)sqrt(hy->bias_correction2);
-    h.n_ema = hy->n_ema;
-    for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k) {
-        h.ema_w[k] = (float)(1.0 - hy->ema_beta[k]);
-        h.ema_w64[k] = 1.0 - hy->ema_beta[k];
-        h.fb_w[k] = hy->feedback_beta[k] >= 0.0 ? (float)(1.0 - hy->feedback_beta[k]) : -1.f;
-        h.ema_is_f64[k] = hy->ema_is_f64[k];
-    }
+    const OptimHyperDev h = make_hyper_dev(*hy);
     optim_step_batched_kernel<<<total_rows, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev);
     DD_CHECK_LAUNCH();
     return 0;

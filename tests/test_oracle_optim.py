@@ -179,3 +179,57 @@ def test_descriptor_table_covers_every_unet_parameter_once(monkeypatch):
         begin += d.rows
     assert begin == rows
     assert all(float(opt.state[p]["step"]) == 1.0 for p in params)
+
+
+@pytest.fixture(scope="module")
+def host_harness(tmp_path_factory):
+    """tests/csrc/optim_host_check.cpp built with g++: the kernels' per-element functions (csrc/optim_math.cuh) and
+    descriptor walk on host memory."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path_factory.mktemp("optim_host") / "liboptim_host_check.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I", os.path.join(root, "include"),
+                    "-I", os.path.join(root, "dualdiffusion_b200", "csrc"), "-x", "c++",
+                    os.path.join(root, "tests", "csrc", "optim_host_check.cpp"), "-o", out], check=True)
+    lib = ctypes.CDLL(out)
+    lib.optim_host_grad_norm.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_void_p]
+    lib.optim_host_grad_norm.restype = None
+    lib.optim_host_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(L.OptimHyper),
+                                    ctypes.c_float]
+    lib.optim_host_step.restype = ctypes.c_int
+    return lib
+
+
+def test_kernel_arithmetic_and_descriptor_walk_replay_reference_golden_on_host(host_harness):
+    """The exact per-element code the CUDA kernels compile (optim_math.cuh), driven by ops.pack_optim_descs /
+    pack_gnorm_descs / make_hyper on host tensors, replays the reference golden: clip, AdamW with and without decay,
+    fp32 + fp64 EMA copies, feedback, weight re-normalisation, flat tensors with a short tail row."""
+    g = _load()
+    names = g["names"]
+    p = {n: g["init"][n].clone().contiguous() for n in names}
+    m = {n: torch.zeros_like(p[n]) for n in names}
+    v = {n: torch.zeros_like(p[n]) for n in names}
+    cfgs = list(g["emas"].values())
+    emas = [{n: g["init"][n].clone().to(torch.float64 if c.get("use_float64") else torch.float32) for n in names}
+            for c in cfgs]
+    hy = g["hyper"]
+    for it, rec in enumerate(g["steps"]):
+        grads = [rec["grads"][n].contiguous() for n in names]
+        garr, _ = ops.pack_gnorm_descs(grads)
+        out2 = (ctypes.c_float * 2)()
+        host_harness.optim_host_grad_norm(garr, len(grads), hy["max_norm"], out2)
+        assert abs(out2[0] - float(rec["grad_norm"])) <= 2e-6 * float(rec["grad_norm"])
+        assert out2[1] == pytest.approx(min(1.0, hy["max_norm"] / (float(rec["grad_norm"]) + 1e-6)), rel=1e-5)
+        arr, rows = ops.pack_optim_descs([dict(p=p[n], g=gr, m=m[n], v=v[n], emas=[e[n] for e in emas],
+                                               fan_in=g["fan_in"][n]) for n, gr in zip(names, grads)])
+        hyper = fo.make_hyper(hy["lr"], hy["betas"], hy["eps"], rec["weight_decay"], float(it + 1),
+                              [c["beta"] for c in cfgs], [c.get("feedback_beta") for c in cfgs],
+                              [int(bool(c.get("use_float64"))) for c in cfgs])
+        assert host_harness.optim_host_step(arr, len(names), rows, ctypes.byref(hyper), out2[1]) == 0
+        for n in names:
+            torch.testing.assert_close(p[n], rec["params"][n], rtol=1e-5, atol=1e-7, msg=f"step {it} param {n}")
+            torch.testing.assert_close(m[n], rec["exp_avg"][n], rtol=1e-5, atol=2e-8, msg=f"step {it} exp_avg {n}")
+            torch.testing.assert_close(v[n], rec["exp_avg_sq"][n], rtol=1e-5, atol=1e-12)
+            for k, name in enumerate(g["emas"]):
+                torch.testing.assert_close(emas[k][n], rec["emas"][name][n], rtol=1e-5, atol=1e-7,
+                                           msg=f"step {it} ema {name} {n}")
