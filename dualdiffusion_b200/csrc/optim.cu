@@ -110,10 +110,13 @@ __global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_o
     const size_t base = (size_t)r * d.row_len;
     const long long tail = d.numel - (long long)base;
     const int f = (int)(tail < (long long)d.row_len ? tail : (long long)d.row_len);
+    // g == NULL: a parameter that received no gradient this step -- torch's AdamW skips it, EMA_Manager.update() and
+    // normalize_weights() still cover it (ema.py:292, mp_tools.py:375-378)
+    const bool has_g = d.g != nullptr;
     float* p = d.p + base;
-    const float* g = d.g + base;
-    float* m = d.m + base;
-    float* v = d.v + base;
+    const float* g = has_g ? d.g + base : nullptr;
+    float* m = has_g ? d.m + base : nullptr;
+    float* v = has_g ? d.v + base : nullptr;
     const float coef = clip_coef ? clip_coef[1] : 1.f;
 
     // 128-bit path: every stream of this row 16-byte aligned, all EMA copies fp32
@@ -132,16 +135,18 @@ __global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_o
     if (vec) {
         const int f4 = f >> 2;
         for (int i = threadIdx.x; i < f4; i += kThreads) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
             float4 p4 = reinterpret_cast<float4*>(p)[i];
-            float4 m4 = reinterpret_cast<float4*>(m)[i];
-            float4 v4 = reinterpret_cast<float4*>(v)[i];
-            p4.x = adamw_elem(p4.x, g4.x * coef, m4.x, v4.x, h);
-            p4.y = adamw_elem(p4.y, g4.y * coef, m4.y, v4.y, h);
-            p4.z = adamw_elem(p4.z, g4.z * coef, m4.z, v4.z, h);
-            p4.w = adamw_elem(p4.w, g4.w * coef, m4.w, v4.w, h);
-            reinterpret_cast<float4*>(m)[i] = m4;
-            reinterpret_cast<float4*>(v)[i] = v4;
+            if (has_g) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
+                float4 m4 = reinterpret_cast<float4*>(m)[i];
+                float4 v4 = reinterpret_cast<float4*>(v)[i];
+                p4.x = adamw_elem(p4.x, g4.x * coef, m4.x, v4.x, h);
+                p4.y = adamw_elem(p4.y, g4.y * coef, m4.y, v4.y, h);
+                p4.z = adamw_elem(p4.z, g4.z * coef, m4.z, v4.z, h);
+                p4.w = adamw_elem(p4.w, g4.w * coef, m4.w, v4.w, h);
+                reinterpret_cast<float4*>(m)[i] = m4;
+                reinterpret_cast<float4*>(v)[i] = v4;
+            }
 #pragma unroll
             for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k) {
                 if (k < h.n_ema && d.ema[k] != nullptr) {
@@ -159,10 +164,13 @@ __global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_o
         }
     } else {
         for (int i = threadIdx.x; i < f; i += kThreads) {
-            float mi = m[i], vi = v[i];
-            float pi = adamw_elem(p[i], g[i] * coef, mi, vi, h);
-            m[i] = mi;
-            v[i] = vi;
+            float pi = p[i];
+            if (has_g) {
+                float mi = m[i], vi = v[i];
+                pi = adamw_elem(pi, g[i] * coef, mi, vi, h);
+                m[i] = mi;
+                v[i] = vi;
+            }
 #pragma unroll
             for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k) {
                 if (k < h.n_ema && d.ema[k] != nullptr) {

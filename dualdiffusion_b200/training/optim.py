@@ -147,9 +147,10 @@ class FusedAdamW(torch.optim.Optimizer):
             by_step: Dict[float, List[Tensor]] = {}
             for p in group["params"]:
                 if p.grad is None:
-                    if self._emas:
-                        raise NotImplementedError("FusedAdamW: a parameter without a gradient cannot take part in the "
-                                                  "fused EMA update")
+                    # torch's AdamW skips it; EMA_Manager.update() / normalize_weights() still cover it (g = NULL)
+                    if self._emas or id(p) in self._fan_in:
+                        _require_f32_cuda(p, "parameter")
+                        by_step.setdefault(-1.0, []).append(p)
                     continue
                 if p.grad.is_sparse:
                     raise RuntimeError("FusedAdamW does not support sparse gradients")
@@ -183,14 +184,20 @@ class FusedAdamW(torch.optim.Optimizer):
         for e, f in zip(emas, is_f64):
             if any(int(t.dtype == torch.float64) != f for t in e):
                 raise RuntimeError("FusedAdamW: one EMA copy mixes fp32 and fp64 tensors")
-        key = (tuple(p.data_ptr() for p in plist), tuple(p.grad.data_ptr() for p in plist),
-               tuple(self.state[p]["exp_avg"].data_ptr() for p in plist),
-               tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in plist),
-               tuple(t.data_ptr() for e in emas for t in e))
-        slot = ("step", gi, len(plist))
+        no_grad = step_t < 0                 # the group of parameters without a gradient: EMA + re-normalisation only
+        if no_grad:
+            step_t = 1.0
+            key = (tuple(p.data_ptr() for p in plist), tuple(t.data_ptr() for e in emas for t in e))
+        else:
+            key = (tuple(p.data_ptr() for p in plist), tuple(p.grad.data_ptr() for p in plist),
+                   tuple(self.state[p]["exp_avg"].data_ptr() for p in plist),
+                   tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in plist),
+                   tuple(t.data_ptr() for e in emas for t in e))
+        slot = ("step", gi, len(plist), no_grad)
         st = self._cache.get(slot)
         if st is None or st[0] != key:
-            entries = [dict(p=p, g=p.grad, m=self.state[p]["exp_avg"], v=self.state[p]["exp_avg_sq"],
+            entries = [dict(p=p, g=None if no_grad else p.grad, m=None if no_grad else self.state[p]["exp_avg"],
+                            v=None if no_grad else self.state[p]["exp_avg_sq"],
                             emas=[e[i] for e in emas], fan_in=self._fan_in.get(id(p), 0))
                        for i, p in enumerate(plist)]
             arr, rows = ops.pack_optim_descs(entries)

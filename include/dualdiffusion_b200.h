@@ -416,7 +416,8 @@ DD_API int dd_grad_norm_clip(const dd_gnorm_desc* descs_dev, int n_descs, int to
 #define DD_OPTIM_MAX_EMA 4
 typedef struct dd_optim_desc {
     float* p;            /* parameter, fp32, updated in place */
-    const float* g;      /* gradient, fp32 */
+    const float* g;      /* gradient, fp32; NULL = no gradient this step: AdamW is skipped (m, v unused), the EMA
+                          * lerps and the re-normalisation still run, as in the reference's separate sweeps */
     float* m;            /* exp_avg */
     float* v;            /* exp_avg_sq */
     void* ema[DD_OPTIM_MAX_EMA];   /* EMA copies of p (fp32, or fp64 where dd_optim_hyper.ema_is_f64[k]); NULL = skip */

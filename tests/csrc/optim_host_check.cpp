@@ -35,10 +35,13 @@ extern "C" int optim_host_step(const dd_optim_desc* descs, int n_descs, int tota
             if (f <= 0) return 2;
             float ss = 0.f;
             for (int i = 0; i < f; ++i) {
-                float mi = d.m[base + i], vi = d.v[base + i];
-                float pi = adamw_elem(d.p[base + i], d.g[base + i] * coef, mi, vi, h);
-                d.m[base + i] = mi;
-                d.v[base + i] = vi;
+                float pi = d.p[base + i];
+                if (d.g != nullptr) {
+                    float mi = d.m[base + i], vi = d.v[base + i];
+                    pi = adamw_elem(pi, d.g[base + i] * coef, mi, vi, h);
+                    d.m[base + i] = mi;
+                    d.v[base + i] = vi;
+                }
                 for (int k = 0; k < DD_OPTIM_MAX_EMA; ++k) {
                     if (k < h.n_ema && d.ema[k] != nullptr) {
                         if (h.ema_is_f64[k]) {

@@ -233,3 +233,19 @@ def test_kernel_arithmetic_and_descriptor_walk_replay_reference_golden_on_host(h
             for k, name in enumerate(g["emas"]):
                 torch.testing.assert_close(emas[k][n], rec["emas"][name][n], rtol=1e-5, atol=1e-7,
                                            msg=f"step {it} ema {name} {n}")
+
+
+def test_parameter_without_gradient_gets_ema_and_renormalisation_only(host_harness):
+    """g == NULL in the descriptor: torch's AdamW skips the parameter, EMA_Manager.update() and normalize_weights()
+    still cover it (ema.py:292 takes every module parameter)."""
+    gen = torch.Generator().manual_seed(3)
+    p = torch.randn(6, 20, generator=gen)
+    e = torch.randn(6, 20, generator=gen)
+    exp_e = torch.lerp(e, p, 1 - 0.99)
+    exp_p = oo.normalize_rows(torch.lerp(p, exp_e, 1 - 0.999))
+    arr, rows = ops.pack_optim_descs([dict(p=p, g=None, m=None, v=None, emas=[e], fan_in=20)])
+    assert not arr[0].g and not arr[0].m and not arr[0].v
+    hyper = fo.make_hyper(1e-2, (0.9, 0.99), 1e-8, 0.1, 1.0, [0.99], [0.999], [0])
+    assert host_harness.optim_host_step(arr, 1, rows, ctypes.byref(hyper), 1.0) == 0
+    torch.testing.assert_close(e, exp_e, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(p, exp_p, rtol=1e-6, atol=1e-7)
