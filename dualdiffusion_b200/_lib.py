@@ -164,6 +164,9 @@ _SIGNATURES = {
     "dd_dae_enc_patches": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_dae_latents_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
+    "dd_roll_pad_w": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_crop_unroll_w": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
+    "dd_stereo_fix_noise": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_long, c_void_p]),
     "dd_grad_norm_clip": (c_int, [c_void_p, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p]),
     "dd_optim_step_batched": (c_int, [c_void_p, c_int, c_int, C.POINTER(OptimHyper), c_void_p, c_void_p]),
     "dd_sampler_update": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,

@@ -239,6 +239,43 @@ def axpby(a: Tensor, b: Tensor, alpha: float, beta: float, clip: float = 0.0) ->
     return out
 
 
+def roll_pad_w(x: Tensor, shift: int, pad: int, copies: int = 1, out: Optional[Tensor] = None) -> Tensor:
+    """torch.roll(x, shift, -1) -> circular pad by `pad` columns per side (-> repeat `copies` times along dim 0);
+    fp32 [..., W] -> [copies * x.shape[0], ..., W + 2 pad] (pipeline.py:651-656)."""
+    L.require_cuda(x)
+    W = x.shape[-1]
+    rows = x.numel() // W
+    if out is None:
+        out = torch.empty((copies * x.shape[0],) + tuple(x.shape[1:-1]) + (W + 2 * pad,), device=x.device,
+                          dtype=torch.float32)
+    L.check(L.load().dd_roll_pad_w(L.ptr(x), L.ptr(out), rows, W, int(shift), int(pad), int(copies), L.stream_ptr()))
+    _count()
+    return out
+
+
+def crop_unroll_w(xp: Tensor, shift: int, pad: int, out: Optional[Tensor] = None) -> Tensor:
+    """torch.roll(xp[..., pad:-pad], -shift, -1) (pipeline.py:729-732); fp32 [..., W + 2 pad] -> [..., W]."""
+    L.require_cuda(xp)
+    W = xp.shape[-1] - 2 * pad
+    rows = xp.numel() // xp.shape[-1]
+    if out is None:
+        out = torch.empty(tuple(xp.shape[:-1]) + (W,), device=xp.device, dtype=torch.float32)
+    L.check(L.load().dd_crop_unroll_w(L.ptr(xp), L.ptr(out), rows, W, int(shift), int(pad), L.stream_ptr()))
+    _count()
+    return out
+
+
+def stereo_fix_noise(noise: Tensor, fresh: Tensor, t: float) -> Tensor:
+    """pipeline.py:638-640: even channels take their odd neighbour's noise, then mp_sum(fresh, noise, t)."""
+    L.require_cuda(noise, fresh)
+    B, Cc = noise.shape[0], noise.shape[1]
+    out = torch.empty_like(noise)
+    L.check(L.load().dd_stereo_fix_noise(L.ptr(noise), L.ptr(fresh), float(t), L.ptr(out), B, Cc,
+                                         noise.numel() // (B * Cc), L.stream_ptr()))
+    _count()
+    return out
+
+
 def mp_fourier(x: Tensor, freqs: Tensor, phases: Tensor) -> Tensor:
     out = torch.empty((x.numel(), freqs.numel()), device=x.device, dtype=torch.float32)
     L.check(L.load().dd_mp_fourier(L.ptr(x), x.numel(), L.ptr(freqs), L.ptr(phases), freqs.numel(), L.ptr(out),

@@ -390,6 +390,17 @@ DD_API int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int W, 
  * (B, 2L, H/ratio, W/ratio), channel c*2+z.                                                                              */
 DD_API int dd_dae_latents_pool(const void* f, float* out, int B, int L, int H, int W, int pw, int Cst, int ratio, void* stream);
 
+/* ---- sampler-loop options (pipelines/dual_diffusion_pipeline.py) ------------------------------------------------ */
+/* seamless_loop, :651-656: out[c][r][j] = x[r][(j - pad - shift) mod W] for j in [0, W + 2 pad) and c in [0, copies):
+ * torch.roll(x, shift, -1) -> cat(x[..., -pad:], x, x[..., :pad]) (-> .repeat(copies, 1, 1, 1)).  x fp32 [rows][W].   */
+DD_API int dd_roll_pad_w(const float* x, float* out, long rows, int W, int shift, int pad, int copies, void* stream);
+/* seamless_loop, :729-732: out[r][i] = xp[r][pad + (i + shift) mod W] = torch.roll(xp[..., pad:-pad], -shift, -1).     */
+DD_API int dd_crop_unroll_w(const float* xp, float* out, long rows, int W, int shift, int pad, void* stream);
+/* stereo_fix, :638-640: noise[:, ::2] = noise[:, 1::2]; out = mp_sum(fresh, noise, t) (mp_tools.py:273-279).
+ * noise, fresh, out fp32 (B, C, hw), C even; out may alias fresh (not noise).                                          */
+DD_API int dd_stereo_fix_noise(const float* noise, const float* fresh, float t, float* out, int B, int C, long hw,
+                               void* stream);
+
 /* ==== Optimizer-side sweep of the train step: clip_grad_norm_ (training/trainer.py:1044), torch AdamW
  * step (trainer.py:461-473,1062), EMA / feedback-EMA lerps (training/ema.py:284-313) and normalize_weights
  * (trainer.py:1107-1108, modules/mp_tools.py:375-378) in two launches over a parameter set.                          */

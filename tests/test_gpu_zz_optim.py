@@ -3,7 +3,9 @@ FusedAdamW) against the golden produced by the unmodified reference classes, the
 size-independent properties at a parameter count of the order of the default UNet's.  fp32 arithmetic: tolerance
 1e-5 relative (fused multiply-adds and the reduction order differ from the CPU's), stated per assertion.
 
-The file name sorts last on purpose: these kernels were added after the round's last GPU session."""
+The file name sorts last on purpose: these kernels were added at the very end of round 1 (the golden replay, the seeded
+row shapes and the gradient-less case ran green on B200, profiles/r01_optim_gpu_tests.log; the two large tests had no
+GPU time left)."""
 import os
 
 import pytest

@@ -1,0 +1,36 @@
+"""Profiling driver for the optimizer-side sweep (run under ncu by tools/r02_first_gpu_session.sh): a few
+clip_grad_norm_ + step() iterations of FusedAdamW over the default UNet's 293 M parameters with two fp32 EMA copies."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import unet_oracle as uo  # noqa: E402  (spec only)
+from dualdiffusion_b200.modules.unets.unet_edm2_b4 import UNet, UNetConfig  # noqa: E402
+from dualdiffusion_b200.training.optim import FusedAdamW  # noqa: E402
+
+
+def main() -> None:
+    dev = torch.device("cuda:0")
+    spec = uo.default_spec()
+    cfg = UNetConfig(**{k: getattr(spec, k) for k in UNetConfig.__dataclass_fields__ if hasattr(spec, k)})
+    net = UNet(cfg).to(dev).train()
+    params = list(net.parameters())
+    g = torch.Generator(device=dev).manual_seed(7)
+    for p in params:
+        p.grad = torch.randn(p.shape, device=dev, generator=g)
+    emas = [[p.detach().clone() for p in params] for _ in range(2)]
+    opt = FusedAdamW(params, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0)
+    opt.attach_module(net)
+    opt.attach_emas(emas, [0.9999, 0.99999], [0.9999, None])
+    for _ in range(4):
+        norm = opt.clip_grad_norm_(10.0)
+        opt.step()
+    torch.cuda.synchronize()
+    print("grad norm", float(norm), "params", sum(p.numel() for p in params))
+
+
+if __name__ == "__main__":
+    main()

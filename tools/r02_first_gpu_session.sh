@@ -1,0 +1,26 @@
+#!/bin/bash
+# First GPU call of round 2: everything that was written at the end of round 1 after the GPU budget ran out
+# (optimizer-side sweep) gets its parity run, its bench numbers and its ncu evidence in ONE gpurun call:
+#
+#   gpurun --timeout 1500 -- 'bash tools/r02_first_gpu_session.sh'
+#
+# Outputs land in gpurun_out/ (copy what is kept into profiles/ as r02_*).
+set -u
+mkdir -p gpurun_out
+echo "=== parity: optimizer sweep" | tee gpurun_out/r02_optim_tests.log
+timeout 600 python -m pytest tests/test_gpu_zz_optim.py -x -q 2>&1 | tail -25 | tee -a gpurun_out/r02_optim_tests.log
+echo "=== compute-sanitizer memcheck over the small optimizer tests" | tee -a gpurun_out/r02_optim_tests.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_zz_optim.py -x -q \
+    -k "golden or seeded or without" 2>&1 | tail -15 | tee -a gpurun_out/r02_optim_tests.log
+echo "=== bench (all legs, optim_step last)"
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1_first.json 2> gpurun_out/r02_bench_n1_first.err
+tail -c 1500 gpurun_out/r02_bench_n1_first.json
+echo "=== ncu: launch list + full capture of dd_optim_step_batched"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"optim_step|grad_sqnorm|grad_norm_finish" \
+    -c 12 --csv --log-file gpurun_out/r02_optim_launches.csv python tools/profile_optim.py > gpurun_out/r02_profile_optim.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:optim_step_batched -s 2 -c 1 \
+    -o gpurun_out/r02_ncu_optim_step python tools/profile_optim.py >> gpurun_out/r02_profile_optim.log 2>&1
+ncu -i gpurun_out/r02_ncu_optim_step.ncu-rep --page raw --csv 2>/dev/null | \
+    grep -E "dram__bytes_(read|write).sum|gpu__time_duration.sum|dram__throughput.avg.pct|sm__warps_active.avg.pct|launch__grid_size|achieved_occupancy" \
+    > gpurun_out/r02_ncu_optim_step_summary.csv
+tail -5 gpurun_out/r02_profile_optim.log
