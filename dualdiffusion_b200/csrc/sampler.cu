@@ -4,6 +4,7 @@
 // PyTorch compute on the product path, not for bandwidth.  Index maps are bit-exact by construction.
 #include "common.cuh"
 #include "dualdiffusion_b200.h"
+#include "sampler_math.cuh"
 
 namespace {
 
@@ -17,9 +18,7 @@ __global__ void roll_pad_w_kernel(const float* __restrict__ x, float* __restrict
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long r = i / Wp;
         const int j = (int)(i - r * Wp);
-        int src = (j - pad - shift) % W;
-        if (src < 0) src += W;
-        const float v = x[r * W + src];
+        const float v = x[r * W + roll_pad_src(j, W, shift, pad)];
         for (int c = 0; c < copies; ++c) out[(long)c * total + i] = v;
     }
 }
@@ -32,7 +31,7 @@ __global__ void crop_unroll_w_kernel(const float* __restrict__ xp, float* __rest
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long r = i / W;
         const int j = (int)(i - r * W);
-        out[i] = xp[r * Wp + pad + (j + shift) % W];
+        out[i] = xp[r * Wp + crop_unroll_src(j, W, shift, pad)];
     }
 }
 
@@ -44,10 +43,8 @@ __global__ void stereo_fix_noise_kernel(const float* __restrict__ noise, const f
         const long bc = i / hw;
         const long pos = i - bc * hw;
         const int c = (int)(bc % C);
-        const float b = noise[(bc - c + (c | 1)) * hw + pos];       // even channels read their odd neighbour
-        const float a = fresh[i];
-        const float l = (t < 0.5f) ? a + t * (b - a) : b - (b - a) * (1.f - t);
-        out[i] = l * inv_norm;
+        const float b = noise[(bc - c + stereo_src_channel(c)) * hw + pos];
+        out[i] = mp_sum_elem(fresh[i], b, t, inv_norm);
     }
 }
 

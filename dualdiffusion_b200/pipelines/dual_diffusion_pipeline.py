@@ -131,7 +131,7 @@ class DualDiffusionPipeline(torch.nn.Module):
     @torch.inference_mode()
     def prepare_sampler(self, params: SampleParams, audio_embedding: torch.Tensor, sample_shape=None,
                         x_ref: Optional[torch.Tensor] = None, module=None,
-                        initial_noise: Optional[torch.Tensor] = None):
+                        initial_noise: Optional[torch.Tensor] = None, stereo_noise: Optional[torch.Tensor] = None):
         """Everything `diffusion_decode` does before its loop (pipeline.py:598-646).  Returns (state, generator)."""
         unet = module or getattr(self, "unet")
         params = SampleParams(**params.__dict__).sanitize()
@@ -139,10 +139,9 @@ class DualDiffusionPipeline(torch.nn.Module):
         params.sigma_max = params.sigma_max or unet.config.sigma_max
         params.sigma_min = params.sigma_min or unet.config.sigma_min
         params.sigma_data = params.sigma_data or unet.config.sigma_data
-        if params.seamless_loop:
-            raise NotImplementedError("seamless_loop sampling is not implemented on the B200 path")
-        if params.stereo_fix > 0:
-            raise NotImplementedError("stereo_fix is not implemented on the B200 path")
+        if params.seamless_loop and x_ref is None:
+            # the reference rolls `input_ref_sample` unconditionally (pipeline.py:655) and fails on None
+            raise ValueError("seamless_loop needs x_ref (pipeline.py:655 rolls input_ref_sample)")
         if sample_shape is None and x_ref is None:
             raise ValueError("sample_shape or x_ref is required")
         device = torch.device(unet.device)
@@ -164,6 +163,11 @@ class DualDiffusionPipeline(torch.nn.Module):
             noise = torch.randn(sample_shape, device=device, generator=generator)
         else:
             noise = initial_noise.to(device=device, dtype=torch.float32)
+        if params.stereo_fix > 0:                                             # pipeline.py:638-640
+            # the reference draws this second noise from the global RNG (`torch.randn_like`, no generator)
+            fresh = (torch.randn_like(noise) if stereo_noise is None
+                     else stereo_noise.to(device=device, dtype=torch.float32))
+            noise = ops.stereo_fix_noise(noise.contiguous(), fresh.contiguous(), params.stereo_fix)
         sample = noise * (sig[0] ** 2 + params.sigma_data ** 2) ** 0.5
         state = EDMSamplerState(unet, params, emb, sig, sample, input_ref, getattr(self, "format", None),
                                 self.collect_debug_info)
@@ -174,24 +178,56 @@ class DualDiffusionPipeline(torch.nn.Module):
                          audio_embedding: Optional[torch.Tensor] = None, sample_shape: Optional[torch.Size] = None,
                          x_ref: Optional[torch.Tensor] = None, module=None,
                          initial_noise: Optional[torch.Tensor] = None,
-                         step_noise: Optional[Any] = None) -> torch.Tensor:
-        """pipeline.py:589-752.  `initial_noise` / `step_noise` (callable i -> tensor) optionally inject the
-        noise draws so that parity tests can feed the oracle's values; by default they come from a device
-        `torch.Generator` seeded with params.seed exactly as in the reference (:605, :637, :736)."""
-        state, generator = self.prepare_sampler(params, audio_embedding, sample_shape, x_ref, module, initial_noise)
+                         step_noise: Optional[Any] = None, stereo_noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pipeline.py:589-752.  `initial_noise` / `step_noise` (callable i -> tensor) / `stereo_noise` optionally inject
+        the noise draws so that parity tests can feed the oracle's values; by default they come from a device
+        `torch.Generator` seeded with params.seed exactly as in the reference (:605, :637, :736) and, for stereo_fix,
+        from the global RNG (:640).
+
+        seamless_loop (:651-656, :729-732): every step runs on the sample rolled by a random shift (numpy generator
+        seeded with params.seed, :606) and circularly padded by 32 columns per side.  The UNet calls, CFG, Heun and the
+        final lerp + re-noise all run in that padded frame (`loop` state: its own CUDA graph at width W + 64); the
+        re-noise commutes with the index map, so the step's noise is rolled / padded the same way and the result is
+        cropped and rolled back -- elementwise identical to the reference's order (crop, roll back, add noise)."""
+        state, generator = self.prepare_sampler(params, audio_embedding, sample_shape, x_ref, module, initial_noise,
+                                                stereo_noise)
         p = state.params
         debug_info: dict = {"sigma_schedule": state.sig}
         shape = tuple(state.sample.shape)
+        device = state.sample2.device
+        loop = None
+        if p.seamless_loop:
+            pad, W = 32, shape[-1]
+            if W < pad:
+                raise ValueError(f"seamless_loop: sample width {W} is smaller than the 32-column loop padding")
+            np_generator = np.random.default_rng(p.seed)                                  # :606
+            rep = 1 if state.uncond else 2
+            ref_src = x_ref.to(device=device, dtype=torch.float32).contiguous()
+            ref_pad = torch.empty((rep * ref_src.shape[0],) + tuple(ref_src.shape[1:-1]) + (W + 2 * pad,),
+                                  device=device, dtype=torch.float32)
+            loop = EDMSamplerState(state.unet, p, state.emb, state.sig,
+                                   torch.zeros(shape[:-1] + (W + 2 * pad,), device=device, dtype=torch.float32),
+                                   ref_pad, state.fmt, self.collect_debug_info)
+            cfg_crop = torch.empty(shape, device=device, dtype=torch.float32) if self.collect_debug_info else None
         for i in range(p.num_steps):
             nz = None
             if (i + 1) < p.num_steps:
-                nz = (step_noise(i).to(device=state.sample2.device, dtype=torch.float32) if step_noise is not None
-                      else torch.randn(shape, generator=generator, device=state.sample2.device, dtype=torch.float32))
-            state.step(i, nz)
+                nz = (step_noise(i).to(device=device, dtype=torch.float32) if step_noise is not None
+                      else torch.randn(shape, generator=generator, device=device, dtype=torch.float32))
+            if loop is None:
+                state.step(i, nz)
+                cfg_dbg = state.cfg_out
+            else:
+                shift = int(np_generator.integers(0, W))                                  # :652
+                ops.roll_pad_w(state.sample, shift, pad, copies=rep, out=loop.sample2)    # :653-654, :661
+                ops.roll_pad_w(ref_src, shift, pad, copies=rep, out=ref_pad)              # :655-656
+                loop.step(i, ops.roll_pad_w(nz.contiguous(), shift, pad) if nz is not None else None)
+                ops.crop_unroll_w(loop.sample, shift, pad, out=state.sample)              # :730
+                cfg_dbg = ops.crop_unroll_w(loop.cfg_out, shift, pad, out=cfg_crop) if self.collect_debug_info else None
             if self.collect_debug_info:   # pipeline.py:740-744 (forces host syncs)
                 debug_info.setdefault("sample_std", []).append(state.sample.std().item())
-                debug_info.setdefault("cfg_output_mean", []).append(state.cfg_out.mean().item())
-                debug_info.setdefault("cfg_output_std", []).append(state.cfg_out.std().item())
+                debug_info.setdefault("cfg_output_mean", []).append(cfg_dbg.mean().item())
+                debug_info.setdefault("cfg_output_std", []).append(cfg_dbg.std().item())
                 debug_info.setdefault("effective_input_perturbation", []).append(
                     state.steps[i]["effective_input_perturbation"])
         self.last_debug_info = debug_info

@@ -26,13 +26,17 @@ def diffusion_decode(sd: Dict[str, Tensor], spec: uo.UNetSpec, audio_embedding: 
                      num_steps: int = 100, batch_size: int = 1, cfg_scale: float = 1.5, rho: float = 7.0,
                      use_heun: bool = True, input_perturbation: float = 1.0, input_perturbation_offset: float = 0.0,
                      sigma_max: Optional[float] = None, sigma_min: Optional[float] = None,
-                     x_ref: Optional[Tensor] = None, record: Optional[dict] = None) -> Tensor:
-    """pipeline.py:598-752 with a CPU torch.Generator (what the reference uses when the module is on CPU)."""
+                     x_ref: Optional[Tensor] = None, record: Optional[dict] = None, seamless_loop: bool = False,
+                     stereo_fix: float = 0.0, stereo_noise: Optional[Tensor] = None) -> Tensor:
+    """pipeline.py:598-752 with a CPU torch.Generator (what the reference uses when the module is on CPU).
+    `seamless_loop` (:651-656, :729-732; needs x_ref, as in the reference) and `stereo_fix` (:638-640; `stereo_noise`
+    stands for the reference's un-seeded `torch.randn_like` draw, taken from the global RNG when None)."""
     sigma_max = sigma_max or spec.sigma_max
     sigma_min = sigma_min or spec.sigma_min
     sigma_data = spec.sigma_data
     B = batch_size
     gen = torch.Generator(device="cpu").manual_seed(seed)
+    np_gen = np.random.default_rng(seed)                                                   # :606
     mask = torch.cat((torch.ones(B, dtype=torch.bool), torch.zeros(B, dtype=torch.bool)))
     emb = uo.get_embeddings(sd, audio_embedding, mask)                                     # :608-609
     ref2 = None if x_ref is None else x_ref.repeat(2, 1, 1, 1)
@@ -41,8 +45,25 @@ def diffusion_decode(sd: Dict[str, Tensor], spec: uo.UNetSpec, audio_embedding: 
     if record is not None:
         record["initial_noise"] = noise.clone()
         record["step_noise"] = []
+        record["loop_shifts"] = []
+    if stereo_fix > 0:                                                                     # :638-640
+        noise = noise.clone()
+        noise[:, ::2] = noise[:, 1::2]
+        fresh = torch.randn_like(noise) if stereo_noise is None else stereo_noise
+        if record is not None:
+            record["stereo_noise"] = fresh.clone()
+        noise = uo.mp_sum(fresh, noise, stereo_fix)
     sample = noise * (sig[0] ** 2 + sigma_data ** 2) ** 0.5                                # :642
     for i, (sigma_curr, sigma_next) in enumerate(zip(sig[:-1], sig[1:])):
+        loop_shift = None
+        if seamless_loop:                                                                  # :651-656
+            loop_shift = int(np_gen.integers(0, sample.shape[-1]))
+            if record is not None:
+                record["loop_shifts"].append(loop_shift)
+            sample = torch.roll(sample, shifts=loop_shift, dims=-1)
+            sample = torch.cat((sample[..., -32:], sample, sample[..., :32]), dim=-1)
+            ref2 = torch.roll(ref2, shifts=loop_shift, dims=-1)
+            ref2 = torch.cat((ref2[..., -32:], ref2, ref2[..., :32]), dim=-1)
         old_sigma_next = sigma_next
         ipo = np.log(sigma_curr) + input_perturbation_offset
         eff = (np.tanh(ipo) / 2 + 0.5) * float(input_perturbation)                        # :691
@@ -59,6 +80,9 @@ def diffusion_decode(sd: Dict[str, Tensor], spec: uo.UNetSpec, audio_embedding: 
             cfg = torch.lerp(cfg, cfg_h, 0.5)                                              # :721
         t = sigma_next / sigma_curr if (i + 1) < num_steps else 0                          # :723
         sample = torch.lerp(cfg, sample, t)
+        if loop_shift is not None:                                                         # :729-732
+            sample = torch.roll(sample[..., 32:-32], shifts=-loop_shift, dims=-1)
+            ref2 = torch.roll(ref2[..., 32:-32], shifts=-loop_shift, dims=-1)
         if i + 1 < num_steps:
             p = max(old_sigma_next ** 2 - sigma_next ** 2, 0) ** 0.5                       # :735
             nz = torch.randn(sample.shape, generator=gen, dtype=sample.dtype)
