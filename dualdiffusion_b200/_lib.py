@@ -164,6 +164,7 @@ _SIGNATURES = {
     "dd_dae_enc_patches": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_dae_latents_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
+    "dd_conv_trace_read": (c_int, [c_void_p, c_int, c_void_p]),
     "dd_roll_pad_w": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_crop_unroll_w": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_void_p]),
     "dd_stereo_fix_noise": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_long, c_void_p]),

@@ -93,6 +93,9 @@ struct ConvParams {
     const float* x_in;              // [B][head_cout][H][W]
     const float* x_ref;             // [B][head_cout+1][H][W] or null
     float* d_out;                   // [B][head_cout][H][W]
+    // role timeline of the halo kernel (DD_CONV_TRACE=1, conv3x3_halo_kernel<EW, true> only; appended last so that the
+    // offsets of every other field -- and with them the default instantiations' code -- stay what they were)
+    unsigned long long* trace;      // [kTraceCtas][kTraceSlots][kTraceTiles] clock64 stamps, or null
 };
 
 struct TileCoord {
@@ -843,7 +846,27 @@ __device__ __forceinline__ void halo_issue_chunk(int nks, uint64_t a_desc0, uint
     else halo_issue_taps<3, RP>(a_desc0, b_desc0, b_block16, d_tmem, idesc, acc_first);
 }
 
-template <int EW>
+// ---- role timeline (diagnostic instantiation only) ----
+// Per-tile clock64 stamps of the three roles of the first kTraceCtas CTAs.  All roles of a CTA run on one SM, so the
+// stamps are directly comparable; tools/trace_halo.py turns them into wait / busy intervals per role and tile.
+constexpr int kTraceCtas = 4, kTraceSlots = 8, kTraceTiles = 64;
+enum TraceSlot { kTrTmaFree = 0,      // producer: stage free (a_empty wait done), about to issue the tile's first box
+                 kTrTmaIssued = 1,    // producer: last box of the tile issued
+                 kTrMmaAcc = 2,       // MMA warp: accumulator buffer free (tmem_empty wait done)
+                 kTrMmaOperands = 3,  // MMA warp: the tile's first halo box has landed (a_full wait done)
+                 kTrMmaIssued = 4,    // MMA warp: last UMMA + commit issued
+                 kTrEpiFull = 5,      // epilogue (quadrant-0 warp of the tile's group): accumulator complete
+                 kTrEpiDone = 6,      // epilogue: tile stored, accumulator released
+                 kTrEpiStart = 7 };   // epilogue: began waiting for this tile
+template <bool TRACE>
+__device__ __forceinline__ void trace_stamp(const ConvParams& p, int slot, uint32_t local) {
+    if constexpr (TRACE) {
+        if (blockIdx.x < (unsigned)kTraceCtas && local < (uint32_t)kTraceTiles && p.trace != nullptr)
+            p.trace[((size_t)blockIdx.x * kTraceSlots + slot) * kTraceTiles + local] = (unsigned long long)clock64();
+    }
+}
+
+template <int EW, bool TRACE = false>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ ConvParams p) {
@@ -897,6 +920,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int cur_panel = -1;
             bool waited = false;
             for (int tile = t_begin; tile < t_end; ++tile) {
+                const uint32_t tr_local = (uint32_t)(tile - t_begin);
                 const HaloTile t = decode_halo_tile(p, tile);
                 if (t.panel != cur_panel) {
                     if (cur_panel >= 0) { ptx::mbar_wait(&b_empty, b_par); b_par ^= 1; }   // old panel fully consumed
@@ -912,11 +936,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (!waited) { ptx::grid_dependency_wait(); waited = true; }
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+                    if (kc == 0) trace_stamp<TRACE>(p, kTrTmaFree, tr_local);
                     ptx::mbar_arrive_expect_tx(&a_full[stage], p.halo_bytes);
                     ptx::tma_load_4d(a_smem + (size_t)stage * p.halo_stride, &tmA, &a_full[stage], t.g * p.cin_g + kc * 64,
                                      t.w0 - 1, t.b, t.h0 - 1);      // tensor-map dims are (C, W, B, H)
                     if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
                 }
+                trace_stamp<TRACE>(p, kTrTmaIssued, tr_local);
             }
         }
     } else if (warp == 1) {
@@ -938,10 +964,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t acc_phase = (local / (uint32_t)p.nbuf) & 1;
                 ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 ptx::tcgen05_fence_after();
+                if (lane == 0) trace_stamp<TRACE>(p, kTrMmaAcc, local);
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.n_tile;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&a_full[stage], phase);
                     ptx::tcgen05_fence_after();
+                    if (kc == 0 && lane == 0) trace_stamp<TRACE>(p, kTrMmaOperands, local);
                     if (ptx::elect_one()) {
                         const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + stage * p.halo_stride, kHaloPitch * 128);
                         const uint64_t b_desc0 = ptx::make_kmajor_desc_sw128(b_base + (uint32_t)(kc * 9) * p.b_block_bytes, 1024);
@@ -960,6 +988,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (panel_ends) ptx::umma_commit(&b_empty);
                 }
                 __syncwarp();
+                if (lane == 0) trace_stamp<TRACE>(p, kTrMmaIssued, local);
             }
         }
     } else {
@@ -984,8 +1013,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const bool vn = (hh < p.ht) && (hn < p.H) && (wn < p.W) && (bn < p.B);
                 prefetch_residual_row(p, vn ? (bn * p.H + hn) * p.W + wn : -1, tn.g * p.cout_g + tn.n_idx * p.n_tile);
             }
+            if (quad == 0 && lane == 0) trace_stamp<TRACE>(p, kTrEpiStart, local);
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
+            if (quad == 0 && lane == 0) trace_stamp<TRACE>(p, kTrEpiFull, local);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
             if (p.stage_off) {
                 const uint32_t slab = ptx::smem_u32(smem) + p.stage_off + (uint32_t)(warp - 2) * 4096u;
@@ -996,6 +1027,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+            if (quad == 0 && lane == 0) trace_stamp<TRACE>(p, kTrEpiDone, local);
         }
     }
 
@@ -1271,6 +1303,18 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
 }
 
 
+// role-timeline buffer of the diagnostic halo instantiation (allocated on first use, never freed)
+constexpr size_t kTraceBytes = (size_t)kTraceCtas * kTraceSlots * kTraceTiles * sizeof(unsigned long long);
+unsigned long long* trace_buffer(bool allocate) {
+    static unsigned long long* buf = nullptr;
+    if (buf == nullptr && allocate && cudaMalloc(&buf, kTraceBytes) != cudaSuccess) buf = nullptr;
+    return buf;
+}
+int* trace_meta() {
+    static int meta[8] = {0};
+    return meta;
+}
+
 // 3x3 halo variant: used when the image is at least 8 rows tall (levels 0-2 of the 45 s latent).
 int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     PFN_encodeTiled encode = get_encode_fn();
@@ -1366,6 +1410,24 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
         }                                                                                                          \
         DD_CHECK_CUDA(launch_pdl(conv3x3_halo_kernel<EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p));   \
     } while (0)
+    static const bool trace_on = getenv("DD_CONV_TRACE") != nullptr;       // diagnostic instantiation, tools/trace_halo.py
+    if (trace_on) {
+        DD_REQUIRE(trace_buffer(true) != nullptr, "dd_mpconv_forward: could not allocate the trace buffer");
+        p.trace = trace_buffer(false);
+        DD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, kTraceBytes, stream));
+#define DD_LAUNCH_HALO_TRACE(EW_)                                                                                  \
+    do {                                                                                                           \
+        DD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<EW_, true>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));              \
+        DD_CHECK_CUDA(launch_pdl(conv3x3_halo_kernel<EW_, true>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p)); \
+    } while (0)
+        if (ew == 12) DD_LAUNCH_HALO_TRACE(12); else if (ew == 8) DD_LAUNCH_HALO_TRACE(8); else DD_LAUNCH_HALO_TRACE(4);
+#undef DD_LAUNCH_HALO_TRACE
+        trace_meta()[0] = p.num_tiles; trace_meta()[1] = grid; trace_meta()[2] = p.n_tile; trace_meta()[3] = p.a_stages;
+        trace_meta()[4] = p.nbuf; trace_meta()[5] = ew; trace_meta()[6] = p.kchunks; trace_meta()[7] = p.stage_off ? 1 : 0;
+        DD_CHECK_LAUNCH();
+        return 0;
+    }
     if (ew == 12) DD_LAUNCH_HALO(12); else if (ew == 8) DD_LAUNCH_HALO(8); else DD_LAUNCH_HALO(4);
 #undef DD_LAUNCH_HALO
     DD_CHECK_LAUNCH();
@@ -1383,6 +1445,18 @@ int launch_conv(ConvParams& p, const void* x, const void* w_prepped, int groups,
 }
 
 }  // namespace
+
+extern "C" int dd_conv_trace_read(unsigned long long* stamps_host, int n_stamps, int* meta_host) {
+    DD_REQUIRE(stamps_host && meta_host, "dd_conv_trace_read: null pointer");
+    DD_REQUIRE(n_stamps == kTraceCtas * kTraceSlots * kTraceTiles, "dd_conv_trace_read: expected %d stamps",
+               kTraceCtas * kTraceSlots * kTraceTiles);
+    DD_REQUIRE(trace_buffer(false) != nullptr, "dd_conv_trace_read: no traced launch yet (set DD_CONV_TRACE=1 before the "
+                                               "library is loaded and run a 3x3 layer of >= 8 rows)");
+    DD_CHECK_CUDA(cudaDeviceSynchronize());
+    DD_CHECK_CUDA(cudaMemcpy(stamps_host, trace_buffer(false), kTraceBytes, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; ++i) meta_host[i] = trace_meta()[i];
+    return 0;
+}
 
 extern "C" int dd_mpconv_forward(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin,
                                  int Cout, int ksize, int groups, const dd_conv_epilogue* epi, void* stream_) {

@@ -390,6 +390,13 @@ DD_API int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int W, 
  * (B, 2L, H/ratio, W/ratio), channel c*2+z.                                                                              */
 DD_API int dd_dae_latents_pool(const void* f, float* out, int B, int L, int H, int W, int pw, int Cst, int ratio, void* stream);
 
+/* Diagnostic (tuning only, not on the product path): with DD_CONV_TRACE=1 in the environment when the library is loaded,
+ * 3x3 layers of >= 8 rows run a traced instantiation of the halo kernel that records, for the first 4 CTAs and their
+ * first 64 tiles, clock64 stamps of the three warp roles (8 slots: producer stage-free / issued, MMA accumulator-free /
+ * operands-landed / issued, epilogue accumulator-complete / done / started waiting).  Copies the last traced launch's
+ * stamps [4][8][64] and meta {num_tiles, grid, n_tile, a_stages, nbuf, epilogue warps, kchunks, staged} to the host.   */
+DD_API int dd_conv_trace_read(unsigned long long* stamps_host, int n_stamps, int* meta_host);
+
 /* ---- sampler-loop options (pipelines/dual_diffusion_pipeline.py) ------------------------------------------------ */
 /* seamless_loop, :651-656: out[c][r][j] = x[r][(j - pad - shift) mod W] for j in [0, W + 2 pad) and c in [0, copies):
  * torch.roll(x, shift, -1) -> cat(x[..., -pad:], x, x[..., :pad]) (-> .repeat(copies, 1, 1, 1)).  x fp32 [rows][W].   */
