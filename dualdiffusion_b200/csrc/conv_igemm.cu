@@ -1342,10 +1342,14 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     // tile width is chosen as if there were 4 epilogue warps, then the warp count is cut back to what still fits)
     const uint32_t total = staged ? 224u * 1024u : 214u * 1024u;
     const uint32_t budget = total - (staged ? 4u * kSlabBytes : 0u);
+    // tuning experiments only (tools/exp_halo_stages.sh): cap the output-channel tile / ask for more halo stages than the
+    // two the default insists on, to trade weight-panel width against activation boxes in flight
+    static const int ntile_cap = getenv("DD_HALO_NTILE_MAX") ? std::max(16, atoi(getenv("DD_HALO_NTILE_MAX"))) : 256;
+    static const uint32_t min_stages = getenv("DD_HALO_MIN_STAGES") ? (uint32_t)std::max(2, atoi(getenv("DD_HALO_MIN_STAGES"))) : 2u;
     int n_tile = 0;
-    for (int n = 16; n <= std::min(cout_g, 256); n += 16) {
+    for (int n = 16; n <= std::min(cout_g, std::min(256, ntile_cap)); n += 16) {
         if (cout_g % n) continue;
-        if ((uint32_t)p.kchunks * 9u * n * 128u + 2u * p.halo_stride <= budget) n_tile = n;
+        if ((uint32_t)p.kchunks * 9u * n * 128u + min_stages * p.halo_stride <= budget) n_tile = n;
     }
     if (n_tile == 0) return -1;     // weight panel does not fit: caller falls back to the per-tap kernel
     p.n_tile = n_tile;

@@ -2,7 +2,7 @@
 # First GPU call of round 2: everything that was written at the end of round 1 after the GPU budget ran out
 # (optimizer-side sweep) gets its parity run, its bench numbers and its ncu evidence in ONE gpurun call:
 #
-#   gpurun --timeout 1500 -- 'bash tools/r02_first_gpu_session.sh'
+#   gpurun --timeout 2400 -- 'bash tools/r02_first_gpu_session.sh'
 #
 # Outputs land in gpurun_out/ (copy what is kept into profiles/ as r02_*).
 set -u
@@ -17,6 +17,12 @@ timeout 600 python -m pytest tests/test_gpu_zz_sampler_options.py -x -q 2>&1 | t
 echo "=== role timeline of the halo conv kernel (per-tile fixed cost, DESIGN.md section 4)"
 DD_CONV_TRACE=1 timeout 300 python tools/trace_halo.py > gpurun_out/r02_trace_halo.log 2>&1
 tail -40 gpurun_out/r02_trace_halo.log
+echo "=== per-layer conv microbenchmarks: default, residual L2 prefetch, more halo stages / narrower weight panels"
+timeout 400 python tools/bench_convs.py r02_base > gpurun_out/r02_bench_convs_base.log 2>&1
+DD_EPI_PREFETCH=1 timeout 400 python tools/bench_convs.py r02_prefetch > gpurun_out/r02_bench_convs_prefetch.log 2>&1
+DD_HALO_MIN_STAGES=4 timeout 400 python tools/bench_convs.py r02_stages4 > gpurun_out/r02_bench_convs_stages4.log 2>&1
+DD_HALO_NTILE_MAX=64 timeout 400 python tools/bench_convs.py r02_ntile64 > gpurun_out/r02_bench_convs_ntile64.log 2>&1
+tail -3 gpurun_out/r02_bench_convs_base.log gpurun_out/r02_bench_convs_prefetch.log gpurun_out/r02_bench_convs_stages4.log gpurun_out/r02_bench_convs_ntile64.log
 echo "=== bench (all legs, optim_step last)"
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1_first.json 2> gpurun_out/r02_bench_n1_first.err
 tail -c 1500 gpurun_out/r02_bench_n1_first.json
