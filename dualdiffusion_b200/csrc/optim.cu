@@ -8,6 +8,7 @@
 // batched launch (CTA per weight row, descriptor table) that reads p, g, m, v and the EMA copies once, applies
 // clip * AdamW, the EMA / feedback lerps and the per-row re-normalisation, and writes each of them once.
 // HBM-bound streaming work: 20 B read + 12 B written per parameter, + 8 B per fp32 EMA (16 B per fp64 EMA).
+#include <stdlib.h>
 #include "common.cuh"
 #include "dualdiffusion_b200.h"
 #include "optim_math.cuh"
@@ -95,14 +96,29 @@ __global__ void __launch_bounds__(kThreads) grad_norm_finish_kernel(const float*
 // One CTA per row of one parameter tensor viewed as [rows][row_len].  Pass 1 updates m, v, p and the EMA copies and
 // accumulates the row's sum of squares; pass 2 (normalize != 0) rescales the row: every thread re-reads exactly the
 // elements it wrote itself, so no fence is needed and the second read is served from L1/L2.
+// SMEM_SEARCH (experiment, DD_OPTIM_SMEM_SEARCH=1): the CTA first copies the row_begin column of the descriptor table to
+// shared memory with one round of parallel loads and searches there, instead of ~log2(n_descs) dependent global loads
+// per CTA before any useful work (about 9 round trips for the UNet's ~290 tensors; a CTA only streams ~70 KB).
+constexpr int kMaxSmemDescs = 2048;
+template <bool SMEM_SEARCH>
 __global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_optim_desc* __restrict__ descs, int n_descs,
                                                                       OptimHyperDev h, const float* __restrict__ clip_coef) {
     __shared__ float red[32];
     int lo = 0, hi = n_descs - 1;
     const int unit = blockIdx.x;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].row_begin <= unit) lo = mid; else hi = mid - 1;
+    if constexpr (SMEM_SEARCH) {
+        __shared__ int s_begin[kMaxSmemDescs];
+        for (int i = threadIdx.x; i < n_descs; i += kThreads) s_begin[i] = descs[i].row_begin;
+        __syncthreads();
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_begin[mid] <= unit) lo = mid; else hi = mid - 1;
+        }
+    } else {
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (descs[mid].row_begin <= unit) lo = mid; else hi = mid - 1;
+        }
     }
     const dd_optim_desc d = descs[lo];
     const int r = unit - d.row_begin;
@@ -228,7 +244,11 @@ extern "C" int dd_optim_step_batched(const dd_optim_desc* descs_dev, int n_descs
     DD_REQUIRE(hy->bias_correction1 > 0.0 && hy->bias_correction2 > 0.0,
                "dd_optim_step_batched: bias corrections must be positive (step >= 1)");
     const OptimHyperDev h = make_hyper_dev(*hy);
-    optim_step_batched_kernel<<<total_rows, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev);
+    static const bool smem_search = getenv("DD_OPTIM_SMEM_SEARCH") != nullptr;      // tuning experiment, default off
+    if (smem_search && n_descs <= kMaxSmemDescs)
+        optim_step_batched_kernel<true><<<total_rows, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev);
+    else
+        optim_step_batched_kernel<false><<<total_rows, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev);
     DD_CHECK_LAUNCH();
     return 0;
 }

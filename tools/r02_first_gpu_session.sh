@@ -26,6 +26,9 @@ tail -3 gpurun_out/r02_bench_convs_base.log gpurun_out/r02_bench_convs_prefetch.
 echo "=== bench (all legs, optim_step last)"
 timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1_first.json 2> gpurun_out/r02_bench_n1_first.err
 tail -c 1500 gpurun_out/r02_bench_n1_first.json
+echo "=== optimizer sweep: descriptor search in global memory (default) vs shared memory"
+timeout 300 python tools/profile_optim.py 2>&1 | tail -1 | tee gpurun_out/r02_optim_ab.log
+DD_OPTIM_SMEM_SEARCH=1 timeout 300 python tools/profile_optim.py 2>&1 | tail -1 | tee -a gpurun_out/r02_optim_ab.log
 echo "=== ncu: launch list + full capture of dd_optim_step_batched"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"optim_step|grad_sqnorm|grad_norm_finish" \
     -c 12 --csv --log-file gpurun_out/r02_optim_launches.csv python tools/profile_optim.py > gpurun_out/r02_profile_optim.log 2>&1
