@@ -78,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see dualdiffusion_b200/lib/build.log")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-Xlinker", "--exclude-libs", "-Xlinker", "ALL"]
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH, *objs, "-Xlinker", "--exclude-libs", "-Xlinker", "ALL"]
     subprocess.run(cmd, check=True)
     with open(STAMP_PATH, "w") as fh:
         fh.write(fp)
