@@ -106,6 +106,27 @@ def test_fused_step_matches_oracle_on_seeded_rows(rows, row_len, normalize):
     torch.testing.assert_close(t[1].cpu(), gr, rtol=0, atol=0)          # gradients are never rewritten
 
 
+def test_parameter_without_gradient_gets_ema_and_renormalisation_only():
+    from dualdiffusion_b200.training.optim import FusedAdamW
+    from oracle import optim_oracle as oo
+    dev = _dev()
+    gen = torch.Generator().manual_seed(3)
+    p0, e0, q0 = torch.randn(6, 20, generator=gen), torch.randn(6, 20, generator=gen), torch.randn(33, generator=gen)
+    p, q = torch.nn.Parameter(p0.to(dev)), torch.nn.Parameter(q0.to(dev))
+    q.grad = torch.ones_like(q)
+    emas = [[e0.to(dev), q0.to(dev).clone()]]
+    opt = FusedAdamW([p, q], lr=1e-2, betas=(0.9, 0.99), weight_decay=0.0)
+    opt._fan_in[id(p)] = 20
+    opt.attach_emas(emas, [0.99], [0.999])
+    opt.step()
+    exp_e = torch.lerp(e0, p0, 1 - 0.99)
+    exp_p = oo.normalize_rows(torch.lerp(p0, exp_e, 1 - 0.999))
+    torch.testing.assert_close(emas[0][0].cpu(), exp_e, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(p.detach().cpu(), exp_p, rtol=RTOL, atol=ATOL)
+    assert len(opt.state[p]) == 0 and float(opt.state[q]["step"]) == 1.0
+    assert not torch.equal(q.detach().cpu(), q0)
+
+
 def test_grad_norm_is_deterministic_and_matches_a_double_sum_at_unet_size():
     from dualdiffusion_b200 import ops
     dev = _dev()
@@ -150,24 +171,3 @@ def test_fused_step_properties_at_scale():
     rms = w.detach().pow(2).mean(dim=1).sqrt()
     assert float((rms - 1).abs().max()) < 2e-4
     assert int(opt.state[q]["step"]) == 1 and opt.state[w]["exp_avg"].shape == w.shape
-
-
-def test_parameter_without_gradient_gets_ema_and_renormalisation_only():
-    from dualdiffusion_b200.training.optim import FusedAdamW
-    from oracle import optim_oracle as oo
-    dev = _dev()
-    gen = torch.Generator().manual_seed(3)
-    p0, e0, q0 = torch.randn(6, 20, generator=gen), torch.randn(6, 20, generator=gen), torch.randn(33, generator=gen)
-    p, q = torch.nn.Parameter(p0.to(dev)), torch.nn.Parameter(q0.to(dev))
-    q.grad = torch.ones_like(q)
-    emas = [[e0.to(dev), q0.to(dev).clone()]]
-    opt = FusedAdamW([p, q], lr=1e-2, betas=(0.9, 0.99), weight_decay=0.0)
-    opt._fan_in[id(p)] = 20
-    opt.attach_emas(emas, [0.99], [0.999])
-    opt.step()
-    exp_e = torch.lerp(e0, p0, 1 - 0.99)
-    exp_p = oo.normalize_rows(torch.lerp(p0, exp_e, 1 - 0.999))
-    torch.testing.assert_close(emas[0][0].cpu(), exp_e, rtol=RTOL, atol=ATOL)
-    torch.testing.assert_close(p.detach().cpu(), exp_p, rtol=RTOL, atol=ATOL)
-    assert len(opt.state[p]) == 0 and float(opt.state[q]["step"]) == 1.0
-    assert not torch.equal(q.detach().cpu(), q0)

@@ -13,7 +13,7 @@ echo "=== compute-sanitizer memcheck over the small optimizer tests" | tee -a gp
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_zz_optim.py -x -q \
     -k "golden or seeded or without" 2>&1 | tail -15 | tee -a gpurun_out/r02_optim_tests.log
 echo "=== parity: sampler options (seamless_loop / stereo_fix)" | tee gpurun_out/r02_sampler_options_tests.log
-timeout 600 python -m pytest tests/test_gpu_zz_sampler_options.py tests/test_gpu_zz_dataset_encode.py -q 2>&1 | tail -25 | tee -a gpurun_out/r02_sampler_options_tests.log
+timeout 600 python -m pytest tests/test_gpu_zzz_sampler_options.py tests/test_gpu_zzz_dataset_encode.py -q 2>&1 | tail -25 | tee -a gpurun_out/r02_sampler_options_tests.log
 echo "=== role timeline of the halo conv kernel (per-tile fixed cost, DESIGN.md section 4)"
 DD_CONV_TRACE=1 timeout 300 python tools/trace_halo.py > gpurun_out/r02_trace_halo.log 2>&1
 tail -40 gpurun_out/r02_trace_halo.log
