@@ -41,7 +41,7 @@ def sources() -> list[str]:
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inl")))
     files.append(os.path.join(ROOT, "include", "dualdiffusion_b200.h"))
     for f in files:
         h.update(f.encode())

@@ -39,7 +39,8 @@ def main() -> None:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     print(f"grad norm {float(norm):.4f} params {n}  sweep {ms:.3f} ms = {n * 52 / ms / 1e6:.0f} GB/s algorithmic "
-          f"(52 B/param; DD_OPTIM_SMEM_SEARCH={os.environ.get('DD_OPTIM_SMEM_SEARCH', '0')})")
+          f"(52 B/param; DD_OPTIM_SMEM_SEARCH={os.environ.get('DD_OPTIM_SMEM_SEARCH', '0')} "
+          f"DD_OPTIM_PERSISTENT={os.environ.get('DD_OPTIM_PERSISTENT', '0')})")
 
 
 if __name__ == "__main__":

@@ -29,6 +29,10 @@ tail -c 1500 gpurun_out/r02_bench_n1_first.json
 echo "=== optimizer sweep: descriptor search in global memory (default) vs shared memory"
 timeout 300 python tools/profile_optim.py 2>&1 | tail -1 | tee gpurun_out/r02_optim_ab.log
 DD_OPTIM_SMEM_SEARCH=1 timeout 300 python tools/profile_optim.py 2>&1 | tail -1 | tee -a gpurun_out/r02_optim_ab.log
+DD_OPTIM_PERSISTENT=1 timeout 300 python tools/profile_optim.py 2>&1 | tail -1 | tee -a gpurun_out/r02_optim_ab.log
+echo "--- parity of the two experimental variants" | tee -a gpurun_out/r02_optim_ab.log
+DD_OPTIM_SMEM_SEARCH=1 timeout 300 python -m pytest tests/test_gpu_zz_optim.py -q -k "golden or seeded or without" 2>&1 | tail -2 | tee -a gpurun_out/r02_optim_ab.log
+DD_OPTIM_PERSISTENT=1 timeout 300 python -m pytest tests/test_gpu_zz_optim.py -q -k "golden or seeded or without" 2>&1 | tail -2 | tee -a gpurun_out/r02_optim_ab.log
 echo "=== ncu: launch list + full capture of dd_optim_step_batched"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"optim_step|grad_sqnorm|grad_norm_finish" \
     -c 12 --csv --log-file gpurun_out/r02_optim_launches.csv python tools/profile_optim.py > gpurun_out/r02_profile_optim.log 2>&1
