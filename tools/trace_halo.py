@@ -43,7 +43,8 @@ def report(t, meta, mhz):
         r = (s[:, :n] - t0).double()
         print(f"-- CTA {cta}: {n} tiles, {us(float(r.max())):.1f} us from first stamp to last")
         period = lambda row: float((r[row, n - 1] - r[row, 2]) / max(1, n - 3))
-        print(f"   period per tile: producer {us(period(1)):.2f} us, MMA {us(period(4)):.2f} us, epilogue {us(period(6)):.2f} us")
+        print(f"   period per tile: producer {us(period(1)):.2f} us, MMA {us(period(4)):.2f} us, epilogue {us(period(6)):.2f} us"
+              f"   ({ew // 4} epilogue group(s) take alternate tiles: a group may spend {ew // 4} periods on one tile)")
         tma_wait = (r[0, 1:n] - r[1, :n - 1]).clamp(min=0)      # stage-free wait after the previous tile's issue
         tma_issue = r[1, :n] - r[0, :n]
         mma_acc_wait = (r[2, 1:n] - r[4, :n - 1]).clamp(min=0)
