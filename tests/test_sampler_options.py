@@ -24,7 +24,7 @@ def test_sampler_oracle_options_vs_reference_golden():
     sd = uo.synth_state_dict(spec, seed=0)
     for name, case in g["cases"].items():
         rec = {}
-        out = sampler_oracle.diffusion_decode(sd, spec, g["clap"], (1, 4, 32, 48), seed=case["seed"],
+        out = sampler_oracle.diffusion_decode(sd, spec, g["clap"], tuple(g["shape"]), seed=case["seed"],
                                               x_ref=g["x_ref"] if case["use_ref"] else None,
                                               stereo_noise=case["stereo_noise"], record=rec, **case["kwargs"])
         assert rel_err(out, case["sample"]) < 1e-4, name
@@ -164,7 +164,8 @@ def test_diffusion_decode_host_logic_replays_reference_goldens(monkeypatch, gold
         x_ref = g["x_ref"] if case.get("use_ref") else None
         params = SampleParams(seed=case["seed"], batch_size=1, **case["kwargs"])
         # a CPU generator seeded like the reference's: the default noise path (no injection) must reproduce the golden
-        out = pipe.diffusion_decode(params, quiet=True, audio_embedding=g["clap"], sample_shape=(1, 4, 32, 48),
+        out = pipe.diffusion_decode(params, quiet=True, audio_embedding=g["clap"],
+                                    sample_shape=tuple(g.get("shape", (1, 4, 32, 48))),
                                     x_ref=x_ref, stereo_noise=case.get("stereo_noise"))
         assert rel_err(out, case["sample"]) < 1e-4, name
         assert len(pipe.last_debug_info["sample_std"]) == case["kwargs"]["num_steps"]
