@@ -45,6 +45,30 @@ class GradAllReducer:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
             t.mul_(1.0 / self.world_size())
 
+    @staticmethod
+    def extra_params(net, plan, ts) -> list:
+        """Trainable parameters of `net` that are neither a slot of the flat gradient buffer nor one of its scalar
+        gains.  Together the three sets must cover every parameter that requires grad (checked here), otherwise a
+        replica would keep a rank-local gradient and the weights diverge silently: everything not covered by the flat
+        buffer is exchanged by reduce_extras at the end of the backward pass."""
+        if net is None:
+            return []
+        covered = {id(s.param) for s in ts.slots.values()} | {id(p) for p in plan.gain_params}
+        return [p for p in net.parameters() if p.requires_grad and id(p) not in covered]
+
+    def reduce_extras(self, extras) -> None:
+        """all-reduce(mean) of the .grad of `extras` as one small flat message on the current stream."""
+        grads = [p.grad for p in extras if p.grad is not None]
+        if not grads or self.world_size() == 1:
+            return
+        flat = torch.cat([g.reshape(-1).to(torch.float32) for g in grads])
+        self._all_reduce_mean(flat)
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        self.bytes_reduced += flat.numel() * 4
+
     def run_backward(self, net, plan, ts, saved, dD, backward_fn=None) -> torch.Tensor:
         """Runs the backward schedule with bucket-wise gradient exchange.  `backward_fn` defaults to
         unet_train.train_backward (tests substitute a host-only stand-in)."""
@@ -74,6 +98,16 @@ class GradAllReducer:
         dlabel = backward_fn(net, plan, saved, dD, accumulate=installed, bucket_done=bucket_done)
         if exchange and on_gpu:
             main.wait_stream(self.stream)
+        if exchange:
+            # Parameters whose gradients do not come out of this node (emb_label / emb_label_unconditional /
+            # logvar_linear: LabelEmbeddingFunction and SigmaLogvarFunction hand theirs to autograd) are exchanged once
+            # the whole backward pass has accumulated them into .grad -- the same point at which torch DDP finalises.
+            extras = self.extra_params(net, plan, ts)
+            if extras:
+                try:
+                    torch.autograd.Variable._execution_engine.queue_callback(lambda: self.reduce_extras(extras))
+                except RuntimeError:            # not inside an autograd backward pass (host-logic tests): caller's job
+                    pass
         if not installed:
             for s in params:
                 if s.param.grad is None:

@@ -112,6 +112,9 @@ def _ver(t: Tensor) -> int:
 
 class DAE_D3(DualDiffusionDAE):
 
+    # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
+    config_class = DAE_D3_Config
+
     supports_channels_last: Union[bool, str] = "3d"
     supports_compile = False
 

@@ -105,6 +105,9 @@ def _window(cfg: MS_MDCT_DualFormatConfig, exponent: float) -> torch.Tensor:
 
 class MS_MDCT_DualFormat(DualDiffusionFormat):
 
+    # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
+    config_class = MS_MDCT_DualFormatConfig
+
     def __init__(self, config: MS_MDCT_DualFormatConfig) -> None:
         super().__init__()
         self.config = config

@@ -87,6 +87,9 @@ def mel_filterbank(cfg: SpectrogramFormatConfig) -> torch.Tensor:
 
 class SpectrogramFormat(DualDiffusionFormat):
 
+    # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
+    config_class = SpectrogramFormatConfig
+
     def __init__(self, config: SpectrogramFormatConfig) -> None:
         super().__init__()
         self.config = config

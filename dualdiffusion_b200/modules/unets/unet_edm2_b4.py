@@ -214,6 +214,9 @@ class _Plan:
 
 class UNet(DualDiffusionUNet):
 
+    # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
+    config_class = UNetConfig
+
     supports_compile = False     # no torch.compile dispatch on this path (CUDA graphs instead)
 
     def __init__(self, config: UNetConfig) -> None:

@@ -82,6 +82,9 @@ class Block(torch.nn.Module):
 
 class DDec_MCLT_UNet_B1(DualDiffusionUNet):
 
+    # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
+    config_class = DDec_MCLT_UNet_B1_Config
+
     supports_channels_last: Union[bool, str] = "3d"
     supports_compile = False
 

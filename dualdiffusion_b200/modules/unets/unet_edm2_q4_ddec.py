@@ -104,6 +104,9 @@ class Block(torch.nn.Module):
 
 class UNet(DualDiffusionUNet):
 
+    # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
+    config_class = UNet_Config
+
     supports_compile = False
 
     def __init__(self, config: UNet_Config) -> None:

@@ -16,7 +16,18 @@ import re
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("DUALDIFFUSION_REFERENCE", "/root/reference")
+def _find_reference() -> str:
+    """/root/reference in the build container; on the GPU box the unmodified src/ tree staged by
+    __graft_entry__.build() under the git-ignored baseline/_ref/."""
+    env = os.environ.get("DUALDIFFUSION_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/src/modules"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def available() -> bool:

@@ -78,6 +78,81 @@ def _worker(rank: int, world: int, port: int, q) -> None:
     dist.destroy_process_group()
 
 
+def _worker_extras(rank: int, world: int, port: int, q) -> None:
+    """A parameter whose gradient reaches .grad through ordinary autograd nodes (the UNet's emb_label /
+    emb_label_unconditional / logvar_linear) must be exchanged too, after the whole backward pass, including the sum
+    accumulated under no_sync()."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    params, gains, ts, plan = _fake_state()
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.slots = torch.nn.ParameterList(params + gains)
+            self.extra = torch.nn.Parameter(torch.ones(5))           # not in the flat gradient buffer
+
+    net = Net()
+    sync = GradAllReducer()
+
+    def fake_backward(net_, plan_, saved, dD, accumulate=False, bucket_done=None):
+        for i, (lo, hi) in enumerate(ts.bucket_ranges):
+            vals = torch.full((hi - lo,), float(rank + 1))
+            if accumulate:
+                ts.grad_flat[lo:hi] += vals
+            else:
+                ts.grad_flat[lo:hi] = vals
+            bucket_done(i)
+        return torch.zeros(1)
+
+    class Node(torch.autograd.Function):                             # stands in for UNetFunction
+        @staticmethod
+        def forward(ctx, x):
+            return x.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            sync.run_backward(net, plan, ts, None, None, backward_fn=fake_backward)
+            return g
+
+    def loss():
+        return (Node.apply(net.extra * float(rank + 1))).sum()       # d/d extra = rank + 1
+
+    loss().backward()
+    ok1 = torch.allclose(net.extra.grad, torch.full((5,), 1.5)) and torch.allclose(ts.grad_flat, torch.full_like(ts.grad_flat, 1.5))
+    net.extra.grad.zero_()
+    for p in params + gains:
+        p.grad.zero_()
+    with sync.no_sync():
+        loss().backward()
+    local = torch.allclose(net.extra.grad, torch.full((5,), float(rank + 1)))
+    loss().backward()
+    ok2 = torch.allclose(net.extra.grad, torch.full((5,), 3.0)) and torch.allclose(ts.grad_flat, torch.full_like(ts.grad_flat, 3.0))
+    every = {id(p) for p in net.parameters() if p.requires_grad}
+    covered = {id(s.param) for s in ts.slots.values()} | {id(p) for p in plan.gain_params} | \
+        {id(p) for p in GradAllReducer.extra_params(net, plan, ts)}
+    q.put((rank, ok1, local, ok2, every == covered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_parameters_outside_the_flat_buffer_are_exchanged():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_extras, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok1, local, ok2, cover in res:
+        assert ok1 and local and ok2 and cover, (rank, ok1, local, ok2, cover)
+
+
 def test_two_rank_bucketed_gradient_allreduce():
     world = 2
     ctx = mp.get_context("spawn")
