@@ -1,5 +1,6 @@
 // Library-level entry points of the C ABI: error reporting and device queries.
 #include "common.cuh"
+#include "conv_dx.cuh"
 #include "dualdiffusion_b200.h"
 
 #include <stdarg.h>
@@ -23,6 +24,18 @@ int dd_num_sms() {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     }
     return sms;
+}
+
+void* dd_tensormap_encode_fn() {
+    static void* fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = sym;
+    }
+    return fn;
 }
 
 extern "C" const char* dd_last_error(void) { return g_error; }

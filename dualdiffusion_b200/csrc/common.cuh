@@ -132,6 +132,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a hardware time slice when the phase is still pending).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a protocol bug must surface as a trap (launch error), never as a hung GPU.
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
@@ -144,10 +158,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     // every 64K unsuccessful probes to keep the timer read off the critical path.
     uint32_t spins = 0;
     uint64_t t0 = 0;
+#ifdef DD_MBAR_DEBUG
+    bool reported = false;
+#endif
     while (!mbar_try_wait(bar, parity)) {
         if ((++spins & 0xFFFFu) == 0) {
             const uint64_t now = globaltimer_ns();
             if (t0 == 0) t0 = now;
+#ifdef DD_MBAR_DEBUG
+            else if (now - t0 > 1000000000ull && !reported) {      // every stuck waiter reports before the first one traps
+                reported = true;
+                printf("mbarrier timeout: block %d warp %d lane %d barrier smem+0x%x parity %u\n", (int)blockIdx.x,
+                       (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31), smem_u32(bar), parity);
+            }
+#endif
             else if (now - t0 > 2000000000ull) __trap();
         }
     }

@@ -21,6 +21,7 @@
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of
 // tile i+1; the kernel is persistent over a static round-robin tile schedule.
 #include "common.cuh"
+#include "conv_dx.cuh"
 #include "dualdiffusion_b200.h"
 
 #include <algorithm>
@@ -849,7 +850,7 @@ __device__ __forceinline__ void halo_issue_chunk(int nks, uint64_t a_desc0, uint
 // ---- role timeline (diagnostic instantiation only) ----
 // Per-tile clock64 stamps of the three roles of the first kTraceCtas CTAs.  All roles of a CTA run on one SM, so the
 // stamps are directly comparable; tools/trace_halo.py turns them into wait / busy intervals per role and tile.
-constexpr int kTraceCtas = 4, kTraceSlots = 8, kTraceTiles = 64;
+constexpr int kTraceCtas = 4, kTraceSlots = 12, kTraceTiles = 64;
 enum TraceSlot { kTrTmaFree = 0,      // producer: stage free (a_empty wait done), about to issue the tile's first box
                  kTrTmaIssued = 1,    // producer: last box of the tile issued
                  kTrMmaAcc = 2,       // MMA warp: accumulator buffer free (tmem_empty wait done)
@@ -1303,17 +1304,10 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
 }
 
 
-// role-timeline buffer of the diagnostic halo instantiation (allocated on first use, never freed)
+// role-timeline buffer of the diagnostic instantiations (allocated on first use, never freed; shared with conv3x3_dx.cu)
 constexpr size_t kTraceBytes = (size_t)kTraceCtas * kTraceSlots * kTraceTiles * sizeof(unsigned long long);
-unsigned long long* trace_buffer(bool allocate) {
-    static unsigned long long* buf = nullptr;
-    if (buf == nullptr && allocate && cudaMalloc(&buf, kTraceBytes) != cudaSuccess) buf = nullptr;
-    return buf;
-}
-int* trace_meta() {
-    static int meta[8] = {0};
-    return meta;
-}
+unsigned long long* trace_buffer(bool allocate) { return dd_conv_trace_buffer(allocate); }
+int* trace_meta() { return dd_conv_trace_meta(); }
 
 // 3x3 halo variant: used when the image is at least 8 rows tall (levels 0-2 of the 45 s latent).
 int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
@@ -1440,6 +1434,16 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
 
 int launch_conv(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     static const bool no_halo = getenv("DD_DISABLE_HALO") != nullptr;     // tuning experiments only
+    if (p.taps == 9 && groups > 1 && p.epi != DD_EPI_HEAD) {
+        // grouped 3x3 layers of the tall levels: tap-stacked kernel (conv3x3_dx.cu); -1 = shape not handled there
+        DxConvArgs a{};
+        a.x = x; a.w = w_prepped; a.out = p.out;
+        a.B = p.B; a.H = p.H; a.W = p.W; a.Cin = p.Cin; a.Cout = p.Cout; a.groups = groups;
+        a.epi = p.epi; a.epi2 = p.epi2; a.alpha = p.alpha; a.beta = p.beta; a.clip = p.clip;
+        a.scale = p.scale; a.scale2 = p.scale2; a.residual = p.residual; a.out2 = p.out2;
+        const int r = dd_launch_conv3x3_dx(a, stream);
+        if (r >= 0) return r;
+    }
     if (p.taps == 9 && p.H >= 8 && p.W >= kHaloW && (p.Cin / groups) % 16 == 0 && p.Cin >= 64 && !no_halo) {
         ConvParams q = p;
         const int r = launch_halo(q, x, w_prepped, groups, stream);
@@ -1449,6 +1453,16 @@ int launch_conv(ConvParams& p, const void* x, const void* w_prepped, int groups,
 }
 
 }  // namespace
+
+unsigned long long* dd_conv_trace_buffer(bool allocate) {
+    static unsigned long long* buf = nullptr;
+    if (buf == nullptr && allocate && cudaMalloc(&buf, kTraceBytes) != cudaSuccess) buf = nullptr;
+    return buf;
+}
+int* dd_conv_trace_meta() {
+    static int meta[8] = {0};
+    return meta;
+}
 
 extern "C" int dd_conv_trace_read(unsigned long long* stamps_host, int n_stamps, int* meta_host) {
     DD_REQUIRE(stamps_host && meta_host, "dd_conv_trace_read: null pointer");

@@ -115,7 +115,9 @@ class DAE_D3(DualDiffusionDAE):
     # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
     config_class = DAE_D3_Config
 
-    supports_channels_last: Union[bool, str] = "3d"
+    # Parameters stay in PyTorch's default (OIHW) layout: the kernels read them through raw pointers and keep their own
+    # NHWC activation / repacked-weight layouts, so the base class must not re-stride them (module.py:118-122).
+    supports_channels_last: Union[bool, str] = False
     supports_compile = False
 
     def __init__(self, config: DAE_D3_Config) -> None:

@@ -214,6 +214,10 @@ class _Plan:
 
 class UNet(DualDiffusionUNet):
 
+    # Parameters stay in PyTorch's default (OIHW) layout: the kernels read them through raw pointers and keep their own
+    # NHWC activation / repacked-weight layouts, so the base class must not re-stride them (module.py:118-122).
+    supports_channels_last: Union[bool, str] = False
+
     # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
     config_class = UNetConfig
 

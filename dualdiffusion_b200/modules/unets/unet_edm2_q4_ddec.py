@@ -17,6 +17,8 @@ import math
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence, Tuple
 
+from typing import Union
+
 import torch
 
 from ... import _lib as L
@@ -103,6 +105,10 @@ class Block(torch.nn.Module):
 
 
 class UNet(DualDiffusionUNet):
+
+    # Parameters stay in PyTorch's default (OIHW) layout: the kernels read them through raw pointers and keep their own
+    # NHWC activation / repacked-weight layouts, so the base class must not re-stride them (module.py:118-122).
+    supports_channels_last: Union[bool, str] = False
 
     # resolved by from_pretrained (module.py:72); explicit because this file's annotations are strings
     config_class = UNet_Config

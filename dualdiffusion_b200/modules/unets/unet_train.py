@@ -169,6 +169,9 @@ class TrainState:
         plan = self.plan
         plan.refresh_gains()
         items = plan._weights()
+        if self._prep_descs is None and not all(w.is_contiguous() for _, w, *_ in items):
+            raise RuntimeError("dualdiffusion_b200 UNet: parameters must be in the default contiguous (OIHW) layout; the "
+                               "kernels read them through raw pointers (supports_channels_last is False for this reason)")
         sig = (sum(_ver(w) for _, w, *_ in items), plan.gain_version)
         if self._prep_descs is None:
             dev = plan.device

@@ -80,14 +80,7 @@ if mode == "gpu":
     ref_pipe = ref_pipe.to(device=dev)
     g = torch.Generator().manual_seed(3)
     clap = torch.randn(1, spec.in_channels_emb, generator=g)
-    # 4. the reference's OWN sampler loop (pipeline.py:589-752) over the drop-in UNet vs over its own UNet, same seed
-    params = RefSampleParams(seed=11, num_steps=4, batch_size=1, cfg_scale=1.5, use_heun=True)
-    shape = (1, spec.in_channels, 32, 48)
-    with torch.no_grad():
-        got = pipe.diffusion_decode(params, audio_embedding=clap.to(dev), sample_shape=shape, quiet=True)
-        want = ref_pipe.diffusion_decode(params, audio_embedding=clap.to(dev), sample_shape=shape, quiet=True)
-    out["decode_rel_err"] = float((got.float() - want.float()).norm() / want.float().norm())
-    # 5. the reference trainer's loss math (unet_trainer.py:259-280) + backward through the drop-in (train mode)
+    # 4. the reference trainer's loss math (unet_trainer.py:259-280) + backward through the drop-in (train mode)
     x = torch.randn(2, spec.in_channels, 32, 48, generator=g).to(dev)
     noise = torch.randn(2, spec.in_channels, 32, 48, generator=g).to(dev)
     sigma = torch.tensor([2.0, 0.4], device=dev)
@@ -111,10 +104,42 @@ if mode == "gpu":
     ga = dict(pipe.unet.named_parameters())
     gb = dict(ref_pipe.unet.named_parameters())
     worst = 0.0
+    per = {}
     for name in ("dec.block0_layer0.conv_res1.weight", "enc.block1_layer0.conv_res0.weight", "emb_noise.weight",
                  "emb_label.weight", "logvar_linear.weight"):
         a, b = ga[name].grad.float(), gb[name].grad.float()
-        worst = max(worst, float((a - b).norm() / (b.norm() + 1e-30)))
+        per[name] = float((a - b).norm() / (b.norm() + 1e-30))
+        out.setdefault("dbg", {})[name] = (float(a.norm()), float(b.norm()), float((a * b).sum() / (a.norm() * b.norm() + 1e-30)))
+        worst = max(worst, per[name])
     out["train_grad_rel_err"] = worst
+    # third opinion: autograd through the CPU oracle on the same inputs
+    sdg = {k: (v.clone().requires_grad_(True) if "fourier" not in k else v) for k, v in sd.items()}
+    xc, nc, sc = x.cpu(), noise.cpu(), sigma.cpu()
+    u_ = uo.mp_conv(torch.ones(1), sdg["emb_label_unconditional.weight"], training=True)
+    c_ = uo.mp_conv(uo.normalize(emb_in.cpu()), sdg["emb_label.weight"], training=True)
+    emb_o = uo.mp_sum(u_, c_, mask.cpu().unsqueeze(1).float())
+    d_o = uo.unet_forward(sdg, spec, xc + nc * sc.view(-1, 1, 1, 1), sc, emb_o, training=True)
+    w_o = (sc ** 2 + spec.sigma_data ** 2) / (sc * spec.sigma_data) ** 2
+    bwl = torch.nn.functional.mse_loss(d_o, xc, reduction="none").mean(dim=(1, 2, 3)) * w_o
+    lv = uo.sigma_loss_logvar(sdg, sc)
+    if lv is not None:
+        lo = (bwl / lv.exp() + lv).mean()
+        lo.backward()
+        name = "dec.block0_layer0.conv_res1.weight"
+        go = sdg[name].grad
+        cos = lambda p_, q_: float((p_ * q_).sum() / (p_.norm() * q_.norm() + 1e-30))
+        out["oracle_vs"] = dict(loss_oracle=float(lo), loss_dropin=float(la), loss_ref_gpu=float(lb),
+                                cos_dropin=cos(go, ga[name].grad.float().cpu()), cos_ref_gpu=cos(go, gb[name].grad.float().cpu()))
+    out["train_grad_rel_err_per_param"] = per
+    for net in (pipe.unet, ref_pipe.unet):
+        net.zero_grad(set_to_none=True)
+        net.requires_grad_(False).train(False)
 
+    # 5. the reference's OWN sampler loop (pipeline.py:589-752) over the drop-in UNet vs over its own UNet, same seed
+    params = RefSampleParams(seed=11, num_steps=4, batch_size=1, cfg_scale=1.5, use_heun=True)
+    shape = (1, spec.in_channels, 32, 48)
+    with torch.no_grad():
+        got = pipe.diffusion_decode(params, audio_embedding=clap.to(dev), sample_shape=shape, quiet=True)
+        want = ref_pipe.diffusion_decode(params, audio_embedding=clap.to(dev), sample_shape=shape, quiet=True)
+    out["decode_rel_err"] = float((got.float() - want.float()).norm() / want.float().norm())
 print(json.dumps(out))

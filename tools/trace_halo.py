@@ -17,7 +17,7 @@ import torch  # noqa: E402
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dualdiffusion_b200 import _lib as L, ops  # noqa: E402
 
-CTAS, SLOTS, TILES = 4, 8, 64
+CTAS, SLOTS, TILES = 4, 12, 64
 NAMES = ["tma_free", "tma_issued", "mma_acc", "mma_operands", "mma_issued", "epi_full", "epi_done", "epi_start"]
 
 
@@ -40,6 +40,10 @@ def report(t, meta, mhz):
         if n < 4:
             continue
         t0 = int(s[:, :n][s[:, :n] > 0].min())
+        if meta[7] == 2 and int((s[1, :n] > 0).sum()) < n:     # two sub-tiles per activation box: producer stamps on even items
+            for row in (0, 1):
+                for i in range(1, n, 2):
+                    s[row, i] = s[row, i - 1]
         r = (s[:, :n] - t0).double()
         print(f"-- CTA {cta}: {n} tiles, {us(float(r.max())):.1f} us from first stamp to last")
         period = lambda row: float((r[row, n - 1] - r[row, 2]) / max(1, n - 3))
@@ -60,6 +64,15 @@ def report(t, meta, mhz):
                         ("epilogue works", epi_work), ("TMA issue -> operands visible", lat)):
             w = v[mid] if v.numel() > 3 else v
             print(f"   {name:38s} mean {us(float(w.mean())):6.2f} us   max {us(float(w.max())):6.2f} us")
+        if int((s[9, :n] > 0).sum()) == n:                      # epilogue phases (conv3x3_dx_kernel only)
+            ph = [("wait for the slab (previous TMA store read)", r[8, :n] - r[5, :n]), ("TMEM loads + shuffle-add + math + staging", r[9, :n] - r[8, :n]),
+                  ("proxy fence + TMA store issue", r[10, :n] - r[9, :n]), ("release accumulator", r[6, :n] - r[10, :n])]
+            for name, v in ph:
+                print(f"      epilogue: {name:45s} mean {us(float(v[mid].mean())):6.2f} us")
+        if int(s[0, 63]) > 0 and int(s[6, 63]) > 0:            # entry / set-up / exit stamps (conv3x3_dx_kernel only)
+            e0, e1, e2 = float(s[0, 63] - t0), float(s[1, 63] - t0), float(s[6, 63] - t0)
+            print(f"   CTA entry at {us(e0):.2f} us, set-up done {us(e1):.2f} us, first UMMAs issued {us(float(r[4, 0])):.2f} us, "
+                  f"last epilogue done {us(float(r[6, :n].max())):.2f} us, exit {us(e2):.2f} us   (CTA lifetime {us(e2 - e0):.2f} us)")
         print("   first tiles (us since first stamp): " + " | ".join(
             f"{i}: tma {us(float(r[1, i])):.1f} mma {us(float(r[4, i])):.1f} epi {us(float(r[6, i])):.1f}" for i in range(min(n, 6))))
 
@@ -70,10 +83,7 @@ def main():
     shapes = [tuple(args[:6]) + ((args[6],) if len(args) > 6 else (0,))] if len(args) >= 6 else [
         (2, 32, 688, 256, 512, 8, 1), (2, 32, 688, 512, 256, 8, 2), (2, 32, 688, 512, 256, 8, 0),
         (2, 16, 344, 512, 1024, 8, 1), (2, 16, 344, 1024, 512, 8, 2)]
-    try:
-        mhz = torch.cuda.clock_rate()              # current SM clock (pynvml); the stamps are SM cycles
-    except Exception:
-        mhz = 1900
+    mhz = 1965                                     # SM clock under load on this pool's B200s (nvidia-smi max); stamps are SM cycles
     for (B, H, W, Cin, Cout, g, epi) in shapes:
         x = torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16)
         wp = ops.weight_prep(torch.randn(Cout, Cin // g, 3, 3, device=dev))
