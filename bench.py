@@ -34,6 +34,8 @@ FLOP_PER_SAMPLE_FWD = 0.489e12       # default UNet forward at
 FLOP_PER_STEP = 4 * FLOP_PER_SAMPLE_FWD
 METRIC = "UNet denoise steps/sec on 45s@32kHz-stereo latents (EDM sampler step: Heun + CFG = 2 UNet calls x batch 2)"
 UNIT = "steps/s"
+# identical in both arms (the driver compares the two `config` objects); arm-specific details go to `config_details`
+CONFIG = {"workload": "EDM sampler step (Heun+CFG), default EDM2 UNet 293M, latent 1x4x32x688 (45 s stereo)"}
 
 
 def peaks() -> dict:
@@ -124,17 +126,77 @@ def cpu_oracle_step_rate(steps: int, warmup: int, budget_s: float) -> dict:
             "sample": f"{n} x {sample}; oracle/unet_oracle.py on {cores} host threads", "seconds": dt}
 
 
+def _reference_unet(device, dtype, memory_format=None):
+    """The UNMODIFIED reference UNet (baseline/_ref/src, staged by __graft_entry__.build) with the same seeded synthetic
+    weights as our arm, through baseline/ref_loader.py (stubs for absent I/O-only imports)."""
+    from baseline import ref_loader
+    ref_loader.install()
+    from oracle import unet_oracle as uo          # seeded synthetic weights only
+    from modules.unets.unet_edm2_b4 import UNet as RefUNet, UNetConfig as RefUNetConfig
+    from modules.formats.ms_mdct_dual import MS_MDCT_DualFormat, MS_MDCT_DualFormatConfig
+    spec = uo.default_spec()
+    cfg = RefUNetConfig(**{k: getattr(spec, k) for k in RefUNetConfig.__dataclass_fields__ if hasattr(spec, k)})
+    net = RefUNet(cfg)
+    net.load_state_dict(uo.synth_state_dict(spec, seed=0), strict=True)
+    net = net.requires_grad_(False).train(False).to(device=device, dtype=dtype, memory_format=memory_format)
+    fmt = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig()).to(device=device)
+    return net, fmt, spec
+
+
+def cpu_reference_step_rate(steps: int, warmup: int, budget_s: float) -> dict:
+    """The reference's own CPU path: its UNet (fp32, all host threads) driven like one sampler step of
+    pipeline.py:649-737 (2 UNet calls at batch 2 + CFG / Heun lerps)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    net, fmt, spec = _reference_unet("cpu", torch.float32)
+    g = torch.Generator().manual_seed(1)
+    x1 = torch.randn(LATENT, generator=g)
+    clap = torch.randn(1, spec.in_channels_emb, generator=g)
+    with torch.no_grad():
+        emb1 = net.get_embeddings(clap, torch.tensor([True]))
+        t0 = time.perf_counter()
+        net(x1, torch.tensor([3.0]), fmt, emb1)
+        t_fwd = time.perf_counter() - t0
+        full_step = 4 * t_fwd * (steps + warmup) <= budget_s
+        if full_step:
+            emb2 = net.get_embeddings(clap, torch.tensor([True, False]))
+            x2 = x1.repeat(2, 1, 1, 1)
+
+            def one():
+                d = net(x2, torch.tensor([3.0, 3.0]), fmt, emb2).float()
+                cfg = d[1:].lerp(d[:1], 1.5)
+                return net(torch.lerp(cfg, x1, 0.9).repeat(2, 1, 1, 1), torch.tensor([2.7, 2.7]), fmt, emb2)
+            sample, per_step = "full sampler steps (2 UNet calls x batch 2, 1x4x32x688, fp32)", 1.0
+        else:
+            def one():
+                return net(x1, torch.tensor([3.0]), fmt, emb1)
+            sample, per_step = "single sample-forwards (1x4x32x688, fp32) = 1/4 sampler step each, scaled x4", 0.25
+        for _ in range(max(0, warmup - 1) if full_step else 0):
+            one()
+        n = max(1, steps if full_step else min(steps, max(1, int(budget_s / max(t_fwd, 1e-3)))))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            one()
+        dt = time.perf_counter() - t0
+    return {"value": per_step * n / dt, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{n} x {sample}; the reference's own modules/unets/unet_edm2_b4.UNet on {cores} host threads",
+            "seconds": dt}
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_oracle_step_rate(args.steps, args.warmup, budget_s=150.0)
+    note = "the unmodified reference UNet (baseline/_ref/src) on the host cores"
+    try:
+        r = cpu_reference_step_rate(args.steps, args.warmup, budget_s=150.0)
+    except Exception as exc:          # reference tree not staged on this box: the validated CPU port stands in
+        note = f"reference tree unavailable ({exc!r}); the CPU oracle port (validated against it, tests/test_oracle.py) is timed"
+        r = cpu_oracle_step_rate(args.steps, args.warmup, budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / r["value"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "EDM sampler step (Heun+CFG), default EDM2 UNet 293M, latent 1x4x32x688 (45 s stereo)",
-                       "note": "reference's own PyTorch code cannot travel to the GPU box; the CPU oracle port "
-                               "(validated against it, tests/test_oracle.py) is timed on the host cores"},
+            "config": CONFIG, "config_details": {"note": note},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -451,6 +513,88 @@ def bench_optim(device, steps: int = 10, warmup: int = 3) -> dict:
     return out
 
 
+def bench_gpu_eager(device, steps: int = 10, warmup: int = 3) -> dict:
+    """SURVEY 8(d) / BASELINE.md section 4: the reference's OWN eager PyTorch path on the same B200 -- its UNet from
+    baseline/_ref/src, bf16 parameters, channels_last, cudnn.benchmark and TF32 on (init_cuda,
+    src/utils/dual_diffusion_utils.py:67-82) -- driven like one sampler step (2 UNet calls at batch 2 + the CFG / Heun
+    lerps of pipeline.py:699-725).  cuDNN / cuBLAS / SDPA library kernels; none of this repository's code runs."""
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    net, fmt, spec = _reference_unet(device, torch.bfloat16, torch.channels_last)
+    g = torch.Generator().manual_seed(1)
+    x1 = torch.randn(LATENT, generator=g).to(device)
+    clap = torch.randn(1, spec.in_channels_emb, generator=g).to(device)
+    out = {"what": "reference UNet (unmodified, eager PyTorch: cuDNN/cuBLAS/SDPA), bf16 + channels_last + cudnn.benchmark + TF32"}
+    with torch.inference_mode():
+        emb2 = net.get_embeddings(clap, torch.tensor([True, False], device=device))
+        s_a, s_b = torch.tensor([3.0, 3.0], device=device), torch.tensor([2.7, 2.7], device=device)
+
+        def one():
+            d = net(x1.repeat(2, 1, 1, 1), s_a, fmt, emb2).float()
+            cfg = d[1:].lerp(d[:1], 1.5)
+            d2 = net(torch.lerp(cfg, x1, 0.9).repeat(2, 1, 1, 1), s_b, fmt, emb2).float()
+            return torch.lerp(cfg, d2[1:].lerp(d2[:1], 1.5), 0.5)
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    out["sampler_step"] = {"value": 1e3 / ms, "unit": UNIT, "ms_per_step": ms}
+    del net
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_gpu_eager_train(device, steps: int = 4, warmup: int = 2) -> dict:
+    """Same for BASELINE config 4 at one GPU: the reference UNet's train step (fwd + bwd) in bf16 (module.half(), i.e.
+    bf16 parameters -- the reference's MPConv casts its weights to the activation dtype itself, mp_tools.py:364, so
+    autocast with fp32 parameters is not how its modules run), channels_last, device batch 4, loss of
+    unet_trainer.py:259-280.  No fp32 master copy is kept here, which only favours the comparator."""
+    import torch.nn.functional as F
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    net, fmt, spec = _reference_unet(device, torch.bfloat16, torch.channels_last)
+    net = net.requires_grad_(True).train()
+    B = 4
+    g = torch.Generator(device=device).manual_seed(100)
+    samples = torch.randn(B, *LATENT[1:], device=device, generator=g)
+    noise = torch.randn(B, *LATENT[1:], device=device, generator=g)
+    sigma = torch.exp(torch.randn(B, device=device, generator=g) * 1.2 - 0.4)
+    clap = torch.randn(B, spec.in_channels_emb, device=device, generator=g)
+    mask = torch.ones(B, device=device, dtype=torch.bool)
+    sig = sigma.view(-1, 1, 1, 1)
+    w = (sig ** 2 + spec.sigma_data ** 2) / (sig * spec.sigma_data) ** 2
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        emb = net.get_embeddings(clap, mask)
+        denoised = net(samples + noise * sig, sigma, fmt, emb)
+        wl = (F.mse_loss(denoised.float(), samples, reduction="none") * w).mean(dim=(1, 2, 3))
+        logvar = net.get_sigma_loss_logvar(sigma).float()
+        loss = (wl / logvar.exp() + logvar).mean()
+        loss.backward()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del net
+    torch.cuda.empty_cache()
+    return {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "device_batch": B}
+
+
 def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -473,7 +617,10 @@ def run_ours(args) -> None:
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_oracle_step_rate(1, 1, budget_s=25.0)
+        try:                                                   # the reference's own CPU path when its tree is staged,
+            cpu_base = cpu_reference_step_rate(1, 1, budget_s=25.0)
+        except Exception:                                      # else the validated CPU port
+            cpu_base = cpu_oracle_step_rate(1, 1, budget_s=25.0)
         cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     K, W = args.steps, max(3, args.warmup)
@@ -511,7 +658,36 @@ def run_ours(args) -> None:
             ms = float(t.item())
         value = world * K / (ms * 1e-3)
 
-        # ---- e2e: the same step through the public API with HOST buffers (pinned), copies inside the timed region
+        # ---- e2e: BASELINE config 2 as a user runs it -- ONE 100-step generate through the public API
+        # (DualDiffusionPipeline.diffusion_decode, the reference's sampler entry point, pipeline.py:589-752) with HOST
+        # tensors in and out: the conditioning embedding is copied in from pinned memory, the finished sample is copied
+        # back, the per-step noise is drawn from the seeded device generator inside the call as in the reference.
+        from dualdiffusion_b200.pipelines.dual_diffusion_pipeline import SampleParams as _SP
+        gen_params = _SP(seed=4321, num_steps=100, batch_size=1, cfg_scale=1.5, use_heun=True)
+        clap_host = torch.randn(1, net.config.in_channels_emb).pin_memory()
+        out_host = torch.empty(LATENT, dtype=torch.float32).pin_memory()
+        pipe.diffusion_decode(gen_params, quiet=True, audio_embedding=clap_host.to(device, non_blocking=True), sample_shape=LATENT)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        n_gen = max(1, min(3, K // 10))
+        t0 = time.perf_counter()
+        for _ in range(n_gen):
+            res = pipe.diffusion_decode(gen_params, quiet=True, audio_embedding=clap_host.to(device, non_blocking=True),
+                                        sample_shape=LATENT)
+            out_host.copy_(res, non_blocking=True)
+            torch.cuda.synchronize()
+        gen_s = (time.perf_counter() - t0) / n_gen
+        if dist is not None:
+            t = torch.tensor([gen_s], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gen_s = float(t.item())
+        e2e_generate = {"value": world * gen_params.num_steps / gen_s, "unit": UNIT, "seconds_per_100_step_generate": gen_s,
+                        "calls_timed": n_gen, "h2d_bytes_per_step": clap_host.numel() * 4 / gen_params.num_steps,
+                        "d2h_bytes_per_step": out_host.numel() * 4 / gen_params.num_steps,
+                        "api": "DualDiffusionPipeline.diffusion_decode(SampleParams(num_steps=100, use_heun=True, cfg_scale=1.5))"}
+
+        # ---- and the single step driven with HOST buffers every step (pinned), copies inside the timed region
         host_in = torch.empty(shape, dtype=torch.float32).pin_memory()
         host_out = torch.empty(shape, dtype=torch.float32).pin_memory()
         host_in.copy_(state.sample.cpu())
@@ -553,13 +729,15 @@ def run_ours(args) -> None:
             allc = [(f, a.elapsed_time(b) * 1e-3) for f, a, b, d in rec]
             fl, tt = sum(f for f, _ in halo), sum(t for _, t in halo)
             fl_all, tt_all = sum(f for f, _ in allc), sum(t for _, t in allc)
-            roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05 implicit-GEMM MPConv, 3x3 grouped, levels 0-2)",
+            roof = {"bound": "tensor", "kernel": "conv3x3_dx_kernel (tcgen05 tap-stacked implicit-GEMM MPConv, 3x3 grouped, levels 0-2)",
                     "achieved": fl / tt / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": fl / tt / 1e12 / pk["tflops"],
                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed
                     # `ncu --set full` capture (2x32x688, 512->256 grouped 3x3: 45.47 MB read + 0.29 MB written back inside
                     # the capture window; algorithmic 45.1 MB in + 22.5 MB out) -- no DRAM re-reads of the activations
-                    "traffic": 45.76e6, "traffic_source": "profiles/r01_ncu_halo_512to256_full_summary.csv (one launch, "
-                                                          "512->256 layer; algorithmic 67.6 MB incl. the output write-back)",
+                    "traffic": 47.25e6, "traffic_source": "profiles/r02_ncu_dx_l0res1_first_version_summary.csv (one launch of the "
+                                                          "2x32x688 512->256 layer: 45.44 MB read + 1.81 MB written back inside "
+                                                          "the capture window; algorithmic 45.1 MB in + 22.5 MB out, the "
+                                                          "output stays in L2)",
                     "launches": len(halo), "avg_launch_us": tt / max(1, len(halo)) * 1e6,
                     "flop_per_launch_avg": fl / max(1, len(halo)), "peak_source": pk["source"] + " (bf16 sustained)",
                     "all_mpconv": {"achieved": fl_all / tt_all / 1e12, "launches": len(allc),
@@ -603,6 +781,18 @@ def run_ours(args) -> None:
     if rank == 0 and world == 1 and not args.no_format:
         secondary = bench_format(device)
 
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager:
+        try:
+            torch.cuda.empty_cache()
+            gpu_eager = bench_gpu_eager(device)
+            gpu_eager["sampler_step"]["ours_over_eager"] = value / gpu_eager["sampler_step"]["value"]
+            if train is not None:
+                gpu_eager["train_step"] = bench_gpu_eager_train(device)
+                gpu_eager["train_step"]["ours_over_eager"] = train["value"] / gpu_eager["train_step"]["value"]
+        except Exception as exc:
+            gpu_eager = {**(gpu_eager or {}), "unavailable": repr(exc)}
+
     optim = None
     if rank == 0 and world == 1 and not args.no_train:
         # last on purpose: every other number is already on the host when this leg runs, and it must never cost the line
@@ -621,13 +811,17 @@ def run_ours(args) -> None:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "EDM sampler step (Heun+CFG), default EDM2 UNet 293M, latent 1x4x32x688 (45 s stereo)",
-                           "sampler_batch": 1, "unet_batch": 2, "parallelism": f"replicas x{world} (sampler is batch-sharded, no collective)",
-                           "l2_policy": "per-step working set (585 MB bf16 weights + activations) exceeds the 126 MB L2; no flush",
-                           "library": os.path.relpath(_lib.lib_path(), ROOT)},
-                "e2e": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+                "config": CONFIG,
+                "config_details": {"sampler_batch": 1, "unet_batch": 2,
+                                   "parallelism": f"replicas x{world} (sampler is batch-sharded, no collective)",
+                                   "l2_policy": "per-step working set (585 MB bf16 weights + activations) exceeds the 126 MB L2; no flush",
+                                   "library": os.path.relpath(_lib.lib_path(), ROOT)},
+                "e2e": e2e_generate,
+                "e2e_per_step_roundtrip": {"value": world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                                           "d2h_bytes_per_step": nbytes,
+                                           "what": "EDMSamplerState.step with the sample copied in from / out to pinned host memory every step"},
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu_base,
-                "train_step": train, "dae_decode": dae, "ddec_forward": ddec, "secondary": secondary,
+                "gpu_eager": gpu_eager, "train_step": train, "dae_decode": dae, "ddec_forward": ddec, "secondary": secondary,
                 "optim_step": optim}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -645,6 +839,7 @@ def main() -> None:
     ap.add_argument("--no-format", action="store_true", help="skip the mel-STFT/FGLA secondary measurement")
     ap.add_argument("--no-dae", action="store_true", help="skip the DAE_D3 decoder (BASELINE config 5) measurement")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step (fwd+bwd+all-reduce) measurement")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the reference's eager PyTorch path on the same GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

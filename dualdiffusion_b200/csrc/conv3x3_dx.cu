@@ -66,6 +66,7 @@ struct DxParams {
     int tiles_w, tiles_h, m_tiles, npg, units;
     FastDiv fd_m, fd_npg, fd_tw, fd_th;
     int a_stages, nbuf, res_stages;
+    int mma_warps, ring;    // UMMA-issuing warps in use (1 or 2) and the activation stages each of them owns
     int ngroups;            // epilogue groups (tiles in the epilogue at once); 16 / ngroups warps share a tile
     uint32_t b_row_bytes, b_dx_bytes, b_blk_bytes, b_sub_bytes;
     uint32_t off_a, off_res, off_slab, res_stride, res_bytes, slab_bytes;
@@ -266,12 +267,16 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, b_par = 0, rs = 0, rph = 0;
+            // Each issuing warp owns its own ring of `ring` activation stages (stage = warp * ring + position): a parity
+            // wait is only sound for a waiter that observes every phase of its barrier in order, and two warps taking
+            // alternate fills of one ring can lap each other (tools/sim_dx_protocol.py reproduces the deadlock).
+            uint32_t rpos = 0, rphase = 0, rpos_other = 0, rphase_other = 0, b_par = 0, rs = 0, rph = 0;    // [turn] / [other warp]
+            int turn = 0;
             bool new_panel = true, first = true;
             for (int u = u_begin; u < u_end; ++u) {
                 if (new_panel) {
                     if (!first) {                                                              // old panel fully consumed
-                        for (int w = 0; w < kMmaWarps; ++w) ptx::mbar_wait(&b_empty[w], b_par);
+                        for (int w = 0; w < p.mma_warps; ++w) ptx::mbar_wait(&b_empty[w], b_par);
                         b_par ^= 1;
                     }
                     ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.nsub * p.b_sub_bytes);
@@ -286,12 +291,18 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (first) { ptx::grid_dependency_wait(); first = false; }      // weights do not depend on the previous kernel
                 const int ci0 = panel_ci0(p, wk.panel);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
-                    ptx::mbar_wait(&a_empty[stage], phase ^ 1);
+                    const uint32_t stage = (uint32_t)(turn * p.ring) + rpos;
+                    ptx::mbar_wait(&a_empty[stage], rphase ^ 1);
                     if (kc == 0) trace_stamp<TRACE>(p, 0, (uint32_t)(u - u_begin) * p.nsub);
                     ptx::mbar_arrive_expect_tx(&a_full[stage], kABytes);
                     ptx::tma_load_4d(smem + p.off_a + (size_t)stage * kABytes, &tmA, &a_full[stage], ci0 + kc * 64, wk.w0 - 1,
                                      wk.h0 - 1, wk.b);
-                    if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
+                    if (++rpos == (uint32_t)p.ring) { rpos = 0; rphase ^= 1; }
+                }
+                if (p.mma_warps == 2) {                   // next unit belongs to the other warp: swap the ring cursors
+                    uint32_t t0 = rpos; rpos = rpos_other; rpos_other = t0;
+                    t0 = rphase; rphase = rphase_other; rphase_other = t0;
+                    turn ^= 1;
                 }
                 trace_stamp<TRACE>(p, 1, (uint32_t)(u - u_begin) * p.nsub);
                 if (has_res) {
@@ -310,6 +321,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ------------------------------ UMMA issuers ------------------------------
         // Both warps walk the whole unit sequence (ring positions advance for every unit) and issue alternate units.
         const int me = warp - 1;
+        const uint32_t ring_base = (uint32_t)(me * p.ring);
         const uint32_t idesc = ptx::make_idesc_bf16(128, ncols);
         const uint32_t b_base = ptx::smem_u32(smem), a_base = ptx::smem_u32(smem + p.off_a);
         const uint32_t b_blk16 = p.b_blk_bytes >> 4;
@@ -320,8 +332,10 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int u = u_begin; u < u_end; ++u) {
             const bool panel_ends = (u + 1 == u_end) || (m + 1 == p.m_tiles);
             // mbarrier waits are parity based: a waiter must observe EVERY phase of a barrier in order, or a phase it skipped
-            // makes the next one look complete.  Each issuing warp therefore waits for every weight panel and (below) for
-            // every activation box, also those of units the other warp issues.
+            // makes the next one look complete.  Each issuing warp therefore waits for every weight panel, also one in
+            // which it happens to issue nothing; activation stages and accumulator buffers are never shared between the
+            // two warps (own ring; nbuf / nsub even).
+            if (me >= p.mma_warps) break;
             if (!have_panel) {
                 ptx::mbar_wait(&b_full, panel_idx & 1);
                 have_panel = true;
@@ -336,7 +350,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     st = stage; ph = phase;
                     uint32_t b_addr = b_base + (uint32_t)s * p.b_sub_bytes;
                     for (int kc = 0; kc < p.kchunks; ++kc, b_addr += 3u * p.b_blk_bytes) {
-                        if (s == 0) ptx::mbar_wait(&a_full[st], ph);
+                        if (s == 0) ptx::mbar_wait(&a_full[ring_base + st], ph);
                         if (kc == 0) {
                             if (!acc_free) ptx::mbar_wait(&acc_empty[bf], bph ^ 1);
                             if (lane == 0) trace_stamp<TRACE>(p, 2, item + s);
@@ -346,7 +360,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         if (ptx::elect_one()) {
                             const uint64_t b_desc0 = b128 ? ptx::make_kmajor_desc_sw128(b_addr, 1024) : ptx::make_kmajor_desc(b_addr, 64);
                             // sub-tile s of a two-group box reads channels [32 s, 32 s + 32) of the box: + 64 B = 4 units
-                            const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + st * kABytes, 1024) +
+                            const uint64_t a_desc0 = ptx::make_kmajor_desc_sw128(a_base + (ring_base + st) * kABytes, 1024) +
                                                      (uint64_t)(p.nsub == 2 ? 4 * s : 0);
                             const int nks = p.nsub == 2 ? 2 : ((kc == p.kchunks - 1) ? p.ks_last : 4);
                             const uint32_t acc_first = kc > 0 ? 1u : 0u;
@@ -354,25 +368,23 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             else if (nks == 2) issue_box<2>(a_desc0, b_desc0, b_blk16, d_tmem, idesc, acc_first);
                             else if (nks == 1) issue_box<1>(a_desc0, b_desc0, b_blk16, d_tmem, idesc, acc_first);
                             else issue_box<3>(a_desc0, b_desc0, b_blk16, d_tmem, idesc, acc_first);
-                            if (s == p.nsub - 1) ptx::umma_commit(&a_empty[st]);      // box consumed by all its sub-tiles
+                            if (s == p.nsub - 1) ptx::umma_commit(&a_empty[ring_base + st]);      // box consumed by all its sub-tiles
                             if (kc == p.kchunks - 1) ptx::umma_commit(&acc_full[bf]);
                         }
                         __syncwarp();
-                        if (++st == (uint32_t)p.a_stages) { st = 0; ph ^= 1; }
+                        if (++st == (uint32_t)p.ring) { st = 0; ph ^= 1; }
                     }
                     if (lane == 0) trace_stamp<TRACE>(p, 4, item + s);
                     if (++bf == (uint32_t)p.nbuf) { bf = 0; bph ^= 1; }
                 }
             }
-            // ring positions advance for every unit, issued here or by the other warp
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-                if (turn != me) ptx::mbar_wait(&a_full[stage], phase);      // observe the other warp's boxes (see above)
-                if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
-            }
+            if (turn == me)                                   // this warp's ring advances with its own units only
+                for (int kc = 0; kc < p.kchunks; ++kc)
+                    if (++stage == (uint32_t)p.ring) { stage = 0; phase ^= 1; }
             for (int s = 0; s < p.nsub; ++s)
                 if (++buf == (uint32_t)p.nbuf) { buf = 0; aph ^= 1; }
             item += (uint32_t)p.nsub;
-            if (++turn == kMmaWarps) turn = 0;
+            if (++turn == p.mma_warps) turn = 0;
             if (panel_ends) {
                 // the weight panel may be overwritten once BOTH warps' UMMAs that read it have completed
                 if (issued_in_panel) { if (ptx::elect_one()) ptx::umma_commit(&b_empty[me]); }
@@ -600,6 +612,8 @@ int dd_launch_conv3x3_dx(const DxConvArgs& a, cudaStream_t stream) {
         break;
     }
     if (!chosen) return -1;
+    p.mma_warps = p.a_stages >= 4 ? kMmaWarps : 1;        // each issuing warp needs a ring of >= 2 activation stages
+    p.ring = p.a_stages / p.mma_warps;
     p.nbuf = chosen == 64 ? 2 : 4;
     p.ngroups = chosen == 64 ? 2 : 4;
     p.npg = cout_g / p.n_co;
@@ -652,7 +666,7 @@ int dd_launch_conv3x3_dx(const DxConvArgs& a, cudaStream_t stream) {
         DD_REQUIRE(p.trace != nullptr, "dd_mpconv_forward: could not allocate the trace buffer");
         DD_CHECK_CUDA(cudaMemsetAsync(p.trace, 0, 4 * 12 * 64 * sizeof(unsigned long long), stream));
         int* meta = dd_conv_trace_meta();
-        meta[0] = p.units * p.nsub; meta[1] = grid; meta[2] = p.n_co; meta[3] = p.a_stages; meta[4] = p.nbuf;
+        meta[0] = p.units * p.nsub; meta[1] = grid; meta[2] = p.n_co; meta[3] = p.ring * p.mma_warps; meta[4] = p.nbuf;
         meta[5] = kEpiWarps; meta[6] = p.kchunks; meta[7] = 2;
         DD_CHECK_CUDA(dd_launch_pdl(conv3x3_dx_kernel<true>, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, tmO, tmO2, tmR, p));
         DD_CHECK_LAUNCH();

@@ -142,8 +142,15 @@ class DualDiffusionPipeline(torch.nn.Module):
         if params.seamless_loop and x_ref is None:
             # the reference rolls `input_ref_sample` unconditionally (pipeline.py:655) and fails on None
             raise ValueError("seamless_loop needs x_ref (pipeline.py:655 rolls input_ref_sample)")
-        if sample_shape is None and x_ref is None:
-            raise ValueError("sample_shape or x_ref is required")
+        if sample_shape is None and x_ref is None:                          # pipeline.py:615-622
+            fmt = getattr(self, "format", None)
+            if fmt is None:
+                raise ValueError("sample_shape, x_ref or a `format` module is required")
+            length = params.length or fmt.config.default_raw_length
+            sample_shape = fmt.get_mel_spec_shape(bsz=params.batch_size, raw_length=length)
+            dae = getattr(self, "dae", None)
+            if dae is not None:
+                sample_shape = dae.get_latent_shape(sample_shape)
         device = torch.device(unet.device)
         B = params.batch_size
         generator = torch.Generator(device=device).manual_seed(params.seed)

@@ -603,6 +603,17 @@ def test_axis_attention_vs_oracle(dev):
     assert rel_err(got.float().cpu().permute(0, 4, 1, 2, 3), ref) < 3 * BF16_OP
 
 
+def test_axis_attention_vs_reference_golden(dev):
+    """Row A9 against the unmodified reference Block's own output (tests/golden/axis_attention_b3.pt, head dim 64 case)."""
+    from dualdiffusion_b200 import ops
+    case = load_golden("axis_attention_b3.pt")["b"]
+    qkv, heads = bf16_round(case["qkv"]), case["heads"]
+    b, c3, z, h, w = qkv.shape
+    got = ops.attention_axis(_qkv_thirds(qkv, heads).to(device=dev, dtype=torch.bfloat16), heads, axis=0)
+    assert got.shape == (b, z, h, w, c3 // 3)
+    assert rel_err(got.float().cpu().permute(0, 4, 1, 2, 3), case["y_silu"]) < 3 * BF16_OP
+
+
 def test_axis_attention_reshape_indexing_is_bit_exact(dev):
     """North star: 'bit-exact for the row/col reshape indexing'.  The same attention arithmetic is run twice:
     (a) as the reference does it -- physically permute to (b*z*w, h, c), attend, permute back (b3.py:148-159) --

@@ -212,3 +212,14 @@ def test_mdct_oracle_vs_golden_reference():
         assert rel_err(fo.raw_to_mdct_psd(g["raw"], spec), c["psd"]) < 1e-6, tag
         assert rel_err(fo.mdct_to_raw(c["mdct"], spec), c["raw_back"]) < 1e-6, tag
         assert rel_err(fo.mel_spec_to_mdct_psd(c["mel"], fo.MSDualSpec(), spec), c["mel_psd"]) < 1e-5, tag
+
+
+def test_axis_attention_oracle_vs_reference_golden():
+    """Row A9: the row/col <-> batch reshape attention of the legacy ddec UNets, pinned against the unmodified reference
+    Block (tests/golden/make_golden_axis_attention.py hooks attn_qkv / attn_proj of
+    src/modules/unets/old/unet_edm2_ddec_mdct_b3.py)."""
+    g = load_golden("axis_attention_b3.pt")
+    for tag, case in g.items():
+        got = uo.mp_silu(uo.axis_attention_b3(case["qkv"], case["heads"]))
+        assert got.shape == case["y_silu"].shape
+        assert rel_err(got, case["y_silu"]) < 1e-5, tag
