@@ -61,7 +61,10 @@ struct ConvParams {
     int kchunks;                    // cin_g / KC
     int k_iters;                    // taps * kchunks
     int sub;                        // operand pairs per pipeline stage (1 or 2)
-    int ksplit;                     // split-K factor = cluster size (conv_igemm_splitk_kernel), 1 otherwise
+    int ksplit;                     // split-K factor (conv_igemm_splitk_kernel), 1 otherwise
+    float* ws;                      // split-K: fp32 partial-sum workspace [tile][128][n_tile] of this launch's slot (all zero
+                                    // between launches: the finishing CTA of a tile clears what it consumed)
+    int* ws_count;                  // split-K: arrivals per tile (reset by the finisher)
     int num_tiles;
     int stages;
     uint32_t a_bytes, b_bytes;      // bytes landed per stage by the two TMA boxes
@@ -145,29 +148,9 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH],
     }
 }
 
-// (split-K) partial accumulators of the other CTAs of the cluster: `peer_stage` is this CTA's shared::cta byte address of
-// the staging area, which has the same offset in every CTA; rank r's copy is reached through mapa / ld.shared::cluster.
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
 template <int EW>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
-                                              int ch0, uint32_t peer_stage = 0, int row = 0) {
+                                              int ch0, float* ws_row = nullptr) {
     constexpr int kChunk = EW >= 8 ? 16 : 32;   // columns per tcgen05.ld
     const size_t pix = ((size_t)b * p.H + h) * p.W + w;
     uint32_t rn[kChunk];
@@ -188,17 +171,15 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
               }
               if (c0 + kChunk < p.n_tile)
                   tmem_ld_chunk<kChunk>(taddr + c0 + kChunk, rn, kChunk == 32 && c0 + 2 * kChunk > p.n_tile);
-              if (p.ksplit > 1) {           // add the partial sums the other k-ranges left in their shared memory
-                  const uint32_t off = (uint32_t)(((c0 / kChunk) * kTileM + row) * kChunk) * 4u;
-                  for (int pr = 1; pr < p.ksplit; ++pr) {
-                      const uint32_t pa = map_to_cta(peer_stage + off, (uint32_t)pr);
+              if (ws_row != nullptr) {      // split-K finisher: the tile's sum over all k-ranges sits in the workspace
+                  float4* wp = reinterpret_cast<float4*>(ws_row + c0);
 #pragma unroll
-                      for (int i = 0; i < kChunk / 4; ++i) {
-                          const float4 q = ld_cluster_f4(pa + 16u * i);
-                          r[4 * i + 0] = __float_as_uint(__uint_as_float(r[4 * i + 0]) + q.x);
-                          r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + q.y);
-                          r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + q.z);
-                          r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + q.w);
+                  for (int i = 0; i < kChunk / 4; ++i) {
+                      if (c0 + 4 * i < p.n_tile) {
+                          const float4 q = __ldcg(wp + i);
+                          __stcg(wp + i, make_float4(0.f, 0.f, 0.f, 0.f));        // leave the workspace clean for the next launch
+                          r[4 * i + 0] = __float_as_uint(q.x); r[4 * i + 1] = __float_as_uint(q.y);
+                          r[4 * i + 2] = __float_as_uint(q.z); r[4 * i + 3] = __float_as_uint(q.w);
                       }
                   }
               }
@@ -636,10 +617,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 // ---------------------------------------------------------------------------------
 // Split-K variant for the small-M layers (levels 3-4 of the UNet: 172-688 pixels).  There the per-tile k-loop is bound
-// by what one SM can pull through TMA (~36 B/clk) while most SMs idle, so a thread-block cluster of `ksplit` CTAs shares
-// one output tile: CTA r accumulates k-iterations [r*K/S, (r+1)*K/S) in its own TMEM, ranks > 0 park their fp32 partial
-// tile in their (now idle) pipeline shared memory, and rank 0 adds them through distributed shared memory
-// (ld.shared::cluster) in front of the normal fused epilogue.  One tile per cluster, four epilogue warps.
+// by what one SM can pull through TMA (~36 B/clk: ~3.8 cycles per 128 B box row) while most SMs idle, so `ksplit` CTAs
+// share one output tile: CTA r accumulates k-iterations [r*K/S, (r+1)*K/S) in its own TMEM and adds its fp32 partial tile
+// to a global workspace (red.global.add.v4.f32, L2-resident); the CTA that arrives last on the tile's counter reads the
+// sums back, runs the normal fused epilogue and clears what it consumed, so the workspace is zero again for the next
+// launch.  (Round 1's cluster / distributed-shared-memory reduction lost to cluster launch cost and GPC-confined residency;
+// this variant needs neither.)  One tile per CTA group, four epilogue warps.
 // ---------------------------------------------------------------------------------
 template <int KC>
 __global__ void __launch_bounds__(64 + 32 * 4, 1)
@@ -660,8 +643,8 @@ conv_igemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t stage_bytes = pair_bytes * (uint32_t)p.sub;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const int krank = (int)cluster_ctarank();
     const int tile = blockIdx.x / p.ksplit;
+    const int krank = blockIdx.x - tile * p.ksplit;
     const int it_begin = (int)((long)krank * p.k_iters / p.ksplit), it_end = (int)((long)(krank + 1) * p.k_iters / p.ksplit);
     const TileCoord t = decode_tile(p, tile);
 
@@ -736,43 +719,49 @@ conv_igemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
     }
 
-    // ---- reduction handshake: every thread of the cluster passes two cluster barriers ----
-    //   B1: ranks > 0 have parked their partial tile in shared memory;  B2: rank 0 has finished reading them
+    // ---- reduction: every k-range adds its partial tile to the workspace; the last arrival finishes the tile ----
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const uint32_t stage_area = ptx::smem_u32(smem);              // same offset in every CTA of the cluster
+    __shared__ int s_last;
     if (warp >= 2) {
         ptx::grid_dependency_wait();
-        ptx::mbar_wait(&tmem_full_bar, 0);                        // this CTA's MMAs are complete: its pipeline smem is idle
+        ptx::mbar_wait(&tmem_full_bar, 0);
         ptx::tcgen05_fence_after();
-        if (krank > 0) {
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-            for (int c0 = 0; c0 < p.n_tile; c0 += kChunk) {
-                uint32_t r[kChunk];
-                tmem_ld_chunk<kChunk>(taddr + c0, r, c0 + 32 > p.n_tile);
-                ptx::tmem_ld_wait();
-                float4* dst = reinterpret_cast<float4*>(smem + (size_t)(((c0 / kChunk) * kTileM + row) * kChunk) * 4);
-#pragma unroll
-                for (int i = 0; i < kChunk / 4; ++i)
-                    dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                                         __uint_as_float(r[4 * i + 3]));
-            }
-        }
-    }
-    cluster_arrive_release();
-    cluster_wait_acquire();
-    if (warp >= 2 && krank == 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
         const int ww = row % p.wt;
         const int hh = (row / p.wt) % p.ht;
         const int bb = row / (p.wt * p.ht);
-        const int b = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
-        const bool valid = (bb < p.bt) && (b < p.B) && (h < p.H) && (w < p.W);
-        const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        epilogue_tile<4>(p, taddr, valid, b, h, w, ch0, stage_area, row);
+        const bool in_box = bb < p.bt;                       // rows past the pixel box hold stale operands: never published
+        float* ws_row = p.ws + ((size_t)tile * kTileM + row) * p.n_tile;
+        for (int c0 = 0; c0 < p.n_tile; c0 += kChunk) {          // tcgen05.ld is warp-collective: every lane takes part
+            uint32_t r[kChunk];
+            tmem_ld_chunk<kChunk>(taddr + c0, r, c0 + 32 > p.n_tile);
+            ptx::tmem_ld_wait();
+            if (in_box) {
+#pragma unroll
+                for (int i = 0; i < kChunk / 4; ++i)
+                    if (c0 + 4 * i < p.n_tile)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ws_row + c0 + 4 * i),
+                                     "f"(__uint_as_float(r[4 * i])), "f"(__uint_as_float(r[4 * i + 1])),
+                                     "f"(__uint_as_float(r[4 * i + 2])), "f"(__uint_as_float(r[4 * i + 3])) : "memory");
+            }
+        }
+        __threadfence();                                      // partial sums visible before the arrival below
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
+        if (threadIdx.x == 64) {
+            const int old = atomicAdd(p.ws_count + tile, 1);
+            s_last = old == p.ksplit - 1;
+            if (s_last) p.ws_count[tile] = 0;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (s_last) {
+            __threadfence();
+            const int b = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
+            const bool valid = in_box && (b < p.B) && (h < p.H) && (w < p.W);
+            const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
+            epilogue_tile<4>(p, taddr, valid, b, h, w, ch0, in_box ? ws_row : nullptr);
+        }
     }
-    cluster_arrive_release();
-    cluster_wait_acquire();
 
     ptx::tcgen05_fence_before();
     __syncthreads();
@@ -1168,28 +1157,28 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.n_tile = choose_n_tile(cout_g, p.m_tiles, groups, p.k_iters, KC, num_sms);
     p.ksplit = 1;
     {
-        // Small-M layers: consider sharing one tile between the CTAs of a cluster (split-K, conv_igemm_splitk_kernel).
-        // Same cost model as choose_n_tile plus the distributed-shared-memory reduction; clusters are confined to a GPC
-        // (~18 SMs), which limits how many are co-resident.
-        // Measured on B200 (gpurun_out/bench_convs_splitk.json): correct, but 1.2-3x SLOWER than the single-CTA tiles at
-        // these sizes (cluster launch + two cluster barriers + GPC-confined residency outweigh the shorter k-loop), so
-        // the variant is opt-in (DD_ENABLE_SPLITK=1) until the reduction is overlapped; the default path is unchanged.
+        // Small-M layers: consider sharing one tile between `S` CTAs (split-K, conv_igemm_splitk_kernel: workspace +
+        // arrival counter).  Same cost model as choose_n_tile plus the reduction round trip; only taken when everything
+        // still runs as one wave.  Measured in-graph on B200 (profiles/r02_splitk_ab.log): correct, but 1.2-1.8x SLOWER
+        // than the single-CTA tiles on every level 3-4 shape it selects (e.g. 2x2x43 1280->1280 1x1: 13.9 vs 8.5 us): the
+        // scattered 16 B red.global traffic and the finisher's L2 round trip cost more than the shorter k-loop saves, so
+        // it stays opt-in (DD_ENABLE_SPLITK=1).
         static const bool no_split = getenv("DD_ENABLE_SPLITK") == nullptr;
         auto cost = [&](int n, int S) {
             const long ctas = (long)p.m_tiles * groups * (cout_g / n) * S;
-            const long cap = S == 1 ? num_sms : (long)std::max(1, (num_sms / 8) / S) * S * 8;
-            const long waves = (ctas + cap - 1) / cap;
+            const long waves = (ctas + num_sms - 1) / num_sms;
             const double t_l2 = (128.0 + n) * KC * 2.0 / 36.0, t_mma = n * KC / 32.0;
             const double t_iter = std::max(t_l2, t_mma) + 30.0;
-            const double red = S == 1 ? 0.0 : 1500.0 + 60.0 * (S - 1) * (n / 16.0);
+            const double red = S == 1 ? 0.0 : 2500.0 + 20.0 * n;
             return 2500.0 + waves * (((p.k_iters + S - 1) / S) * t_iter) + 64.0 + n * 6.0 + red + (waves - 1) * 200.0;
         };
         const double base = cost(p.n_tile, 1);
-        double best = base * 0.85;                      // only switch for a clear predicted win
-        if (!no_split && (long)p.m_tiles * groups <= 64 && p.epi2 != DD_EPI2_RAW) {
-            for (int n = 16; n <= std::min(cout_g, 256); n += 16) {
+        double best = base * 0.8;                       // only switch for a clear predicted win
+        if (!no_split && (long)p.m_tiles * groups <= 64) {
+            for (int n = 32; n <= std::min(cout_g, 256); n += 16) {
                 if (cout_g % n) continue;
-                for (int S = 2; S <= 8 && 2 * S <= p.k_iters; ++S) {
+                for (int S = 2; S <= 8 && 3 * S <= p.k_iters; ++S) {
+                    if ((long)p.m_tiles * groups * (cout_g / n) * S > num_sms) continue;
                     const double c = cost(n, S);
                     if (c < best) { best = c; p.n_tile = n; p.ksplit = S; }
                 }
@@ -1249,34 +1238,43 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
 
     const size_t smem_bytes = (size_t)p.stages * stage_bytes + slabs_bytes + 1024;
     if (p.ksplit > 1) {
-        // rank > 0 parks 128 x n_tile fp32 in its pipeline shared memory: must fit
-        const size_t staging = (size_t)((p.n_tile + 31) / 32) * kTileM * 32 * 4;
-        if (staging > (size_t)p.stages * stage_bytes) p.ksplit = 1;
+        // workspace slot of this launch: 16 slots taken round-robin, so launches that may overlap (parallel branches of the
+        // captured graph, programmatic dependent launch) never share one; every slot is all-zero between launches
+        constexpr size_t kSlotFloats = 2u << 20, kSlotTiles = 1024;
+        constexpr int kSlots = 16;
+        static float* ws_base = nullptr;
+        static int* cnt_base = nullptr;
+        static int next_slot = 0;
+        const size_t need = (size_t)p.num_tiles * kTileM * p.n_tile;
+        if (need > kSlotFloats || (size_t)p.num_tiles > kSlotTiles) p.ksplit = 1;
+        else {
+            if (ws_base == nullptr) {
+                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                cudaStreamIsCapturing(stream, &cap);
+                DD_REQUIRE(cap == cudaStreamCaptureStatusNone, "dd_mpconv_forward: first split-K launch inside a stream capture "
+                                                               "(run the layer once eagerly before capturing)");
+                DD_CHECK_CUDA(cudaMalloc(&ws_base, kSlots * kSlotFloats * sizeof(float)));
+                DD_CHECK_CUDA(cudaMalloc(&cnt_base, kSlots * kSlotTiles * sizeof(int)));
+                DD_CHECK_CUDA(cudaMemset(ws_base, 0, kSlots * kSlotFloats * sizeof(float)));
+                DD_CHECK_CUDA(cudaMemset(cnt_base, 0, kSlots * kSlotTiles * sizeof(int)));
+            }
+            p.ws = ws_base + (size_t)next_slot * kSlotFloats;
+            p.ws_count = cnt_base + (size_t)next_slot * kSlotTiles;
+            next_slot = (next_slot + 1) % kSlots;
+        }
     }
     if (p.ksplit > 1) {
         if (getenv("DD_DEBUG_CONV"))
             fprintf(stderr, "[conv split-K] B%d %dx%d %d->%d k%d g%d: m_tiles %d n_tile %d tiles %d k_iters %d ksplit %d stages %d\n",
                     B, H, W, Cin, Cout, p.kw, groups, p.m_tiles, p.n_tile, p.num_tiles, p.k_iters, p.ksplit, p.stages);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(p.num_tiles * p.ksplit);
-        cfg.blockDim = dim3(64 + 32 * 4);
-        cfg.dynamicSmemBytes = smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = p.ksplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = getenv("DD_DISABLE_PDL") ? 1 : 2;
         if (KC == 64) {
             static bool done = false;
             if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_splitk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
-            DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_splitk_kernel<64>, tmA, tmB, p));
+            DD_CHECK_CUDA(launch_pdl(conv_igemm_splitk_kernel<64>, p.num_tiles * p.ksplit, 64 + 32 * 4, smem_bytes, stream, tmA, tmB, p));
         } else {
             static bool done = false;
             if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_splitk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
-            DD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_splitk_kernel<32>, tmA, tmB, p));
+            DD_CHECK_CUDA(launch_pdl(conv_igemm_splitk_kernel<32>, p.num_tiles * p.ksplit, 64 + 32 * 4, smem_bytes, stream, tmA, tmB, p));
         }
         DD_CHECK_LAUNCH();
         return 0;
