@@ -157,6 +157,8 @@ _SIGNATURES = {
     "dd_ddec_head": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_q4_stem": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_int, c_int, c_int, c_int, c_int,
                            c_int, c_void_p]),
+    "dd_gemm_f32": (c_int, [c_void_p, c_long, c_long, c_long, c_void_p, c_long, c_long, c_long, c_void_p, c_long, c_long, c_long,
+                            c_int, c_int, c_int, c_int, c_int, c_int, c_long, c_float, c_float, c_float, c_int, c_void_p]),
     "dd_frame_reflect": (c_int, [c_void_p, c_void_p, c_int, c_long, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_complex_abs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
     "dd_mdct_ola": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -246,16 +246,6 @@ class MS_MDCT_DualFormat(DualDiffusionFormat):
         self._dev_cache[key] = t
         return t
 
-    @staticmethod
-    def _gemm(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        """Plain fp32 library GEMM (cuBLAS) with TF32 off (the reference's format is fp32-only, format.py:40)."""
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
-        try:
-            return torch.matmul(a, b)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
-
     def _get_mdct_raw_crop_width(self, raw_length: Optional[int] = None) -> int:
         c = self.config
         raw_length = raw_length or c.default_raw_length
@@ -283,8 +273,11 @@ class MS_MDCT_DualFormat(DualDiffusionFormat):
         rem = n % N
         padded = n + 2 * N + (N - rem if rem else 0)
         T = (padded - 2 * N) // N + 1
-        frames = ops.frame_reflect(raw, 2 * N, N, N, T)                      # [S][T][2N]
-        return self._gemm(t["fwd"], frames.transpose(-1, -2))               # [S][2N][T]
+        # y[s][r][t] = sum_k fwd[r][k] * frame[s][t][k]; the frames (hop N, reflect padding N) are gathered from `raw` by the
+        # GEMM's B-operand loads, never materialised
+        y = torch.empty((B * C, 2 * N, T), device=raw.device, dtype=torch.float32)
+        return ops.gemm_f32(t["fwd"], (2 * N, 1, 0), raw, (0, 0, n), y, (T, 1, 2 * N * T), 2 * N, T, 2 * N, B * C,
+                            gather=(N, N, n))
 
     @torch.no_grad()
     def raw_to_mdct(self, raw_samples: torch.Tensor, random_phase_augmentation: bool = False) -> torch.Tensor:
@@ -323,8 +316,11 @@ class MS_MDCT_DualFormat(DualDiffusionFormat):
         else:
             C = Cx
             mat = t["inv"][:N]
-        y = self._gemm(x.reshape(B * C, -1, T).transpose(-1, -2), mat)       # [S][T][2N]
-        return ops.mdct_ola(y.contiguous()).view(B, C, -1)
+        x = x.reshape(B * C, -1, T).contiguous()                              # [S][K][T], K = N or 2N (re | im)
+        K = x.shape[1]
+        y = torch.empty((B * C, T, 2 * N), device=x.device, dtype=torch.float32)
+        ops.gemm_f32(x, (1, T, K * T), mat, (2 * N, 1, 0), y, (2 * N, 1, T * 2 * N), T, 2 * N, K, B * C)   # A = x^T as strides
+        return ops.mdct_ola(y).view(B, C, -1)
 
     @torch.no_grad()
     def mel_spec_to_mdct_psd(self, mel_spec: torch.Tensor) -> torch.Tensor:
@@ -333,7 +329,10 @@ class MS_MDCT_DualFormat(DualDiffusionFormat):
         c = self.config
         t = self._mdct_tables(mel_spec.device)
         lin = ops.mel_linearize(mel_spec.detach().float().contiguous(), c.raw_to_mel_spec_offset, 1.0 / c.ms_abs_exponent)
-        psd = self._gemm(t["pinv"], lin)                                     # [B][C][bins][T]
+        Bm, Cm, F, T = lin.shape
+        nb = t["pinv"].shape[0]
+        psd = torch.empty((Bm, Cm, nb, T), device=lin.device, dtype=torch.float32)
+        ops.gemm_f32(t["pinv"], (F, 1, 0), lin, (T, 1, F * T), psd, (T, 1, nb * T), nb, T, F, Bm * Cm)
         if c.mdct_psd_num_bins == c.ms_num_stft_bins - 1:
             psd = psd[:, :, :-1, :]
         if c.mel_spec_to_mdct_psd_offset != 0:

@@ -194,15 +194,14 @@ class SpectrogramFormat(DualDiffusionFormat):
         B, C, F, T = samples.shape
         S = B * C
         n_fft, hop = c.padded_length, c.hop_length
-        # (x/scale + mean).clip(0) ** (1/abs_exponent), then the min-norm inverse mel as one GEMM -> frame-major
-        mel_lin = (samples.detach().float() / c.raw_to_sample_scale + c.sample_mean).clip(min=0) ** (1 / c.abs_exponent)
-        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
-        try:
-            mag = torch.matmul(mel_lin.view(S, F, T).transpose(1, 2), t["pinv_t"])      # [S][T][bins]
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
-        mag.clamp_(min=0)                                                                 # relu (frequency_scale.py:139)
+        # mag[s][t][bin] = relu(sum_f mel_lin[s][f][t] * pinv_t[f][bin]) with mel_lin = (x/scale + mean).clip(0) ** (1/abs_exponent)
+        # (old/spectrogram.py:229-233, frequency_scale.py:130-142): one launch, the linearisation on the A-operand loads and
+        # the relu on the stores
+        x32 = samples.detach().float().contiguous().view(S, F, T)
+        nbins = t["pinv_t"].shape[1]
+        mag = torch.empty((S, T, nbins), device=samples.device, dtype=torch.float32)
+        ops.gemm_f32(x32, (1, T, F * T), t["pinv_t"], (nbins, 1, 0), mag, (nbins, 1, T * nbins), T, nbins, F, S,
+                     a_transform=(1.0 / c.raw_to_sample_scale, c.sample_mean, 1.0 / c.abs_exponent), relu=True)
         env = self._envelope(t, T, samples.device)
         ola = torch.empty((S, n_fft + hop * (T - 1)), device=samples.device, dtype=torch.float32)
         state = torch.empty((S, T, c.num_stft_bins, 2), device=samples.device, dtype=torch.float32)

@@ -720,6 +720,19 @@ def q4_stem(x_in: Tensor, x_ref: Tensor, sigma: Tensor, sigma_data: float, wa: f
 # ---------------------------------------------------------------------------------------------------------
 # MDCT side of the live format (framing / |.| / overlap-add / mel linearisation around a library GEMM)
 # ---------------------------------------------------------------------------------------------------------
+def gemm_f32(a: Tensor, a_strides, b: Tensor, b_strides, c: Tensor, c_strides, M: int, N: int, K: int, batch: int = 1, *,
+             gather=None, a_transform=None, relu: bool = False) -> Tensor:
+    """C[m][n] = sum_k A[m][k] B[k][n] on fp32 tensors addressed by element strides (m, k, batch) / (k, n, batch) /
+    (m, n, batch).  gather = (hop, pad_left, length): B is the reflect-padded frames of the raw rows in `b`.
+    a_transform = (scale, offset, power): A elements are read as clip(a * scale + offset, 0) ** power."""
+    hop, pad, glen = gather if gather is not None else (0, 0, 0)
+    sc, off, pw = a_transform if a_transform is not None else (1.0, 0.0, 0.0)
+    L.check(L.load().dd_gemm_f32(L.ptr(a), *a_strides, L.ptr(b), *b_strides, L.ptr(c), *c_strides, M, N, K, batch, hop, pad,
+                                 glen, sc, off, pw, int(relu), L.stream_ptr()))
+    _count()
+    return c
+
+
 def frame_reflect(raw: Tensor, block_width: int, hop: int, pad_left: int, n_frames: int) -> Tensor:
     S, Ln = raw.shape
     out = torch.empty((S, n_frames, block_width), device=raw.device, dtype=torch.float32)

@@ -372,6 +372,16 @@ DD_API int dd_q4_stem(const float* x_in, const float* x_ref, const float* sigma,
  * The MCLT / inverse MCLT of all frames is one fp32 library GEMM against a host-built matrix (window, phase shifts,
  * 1/mel-density and scales folded in); these kernels do the framing, |.|, overlap-add and mel linearisation around it. */
 
+/* Batched fp32 GEMM of the audio-format transforms, C[m][n] = sum_k A[m][k] * B[k][n] (fp32 FMA, CUDA cores; the
+ * reference computes these with torch.matmul / torch.fft in fp32: utils/mclt.py:87-130, ms_mdct_dual.py:259-318,
+ * frequency_scale.py:130-142).  Operands are addressed by element strides (A: a_m, a_k; B: b_k, b_n; C: c_m, c_n; plus a
+ * batch stride each).  gather_hop > 0: B is not a matrix but the reflect-padded frames of a raw signal of gather_len
+ * samples per batch item, B[k][n] = raw[reflect(n * gather_hop + k - gather_pad)] (mclt.py:90-95).  a_pow > 0: every A
+ * element is read as clip(a * a_scale + a_offset, 0) ** a_pow (the mel "unscale").  relu != 0: C = max(C, 0).          */
+DD_API int dd_gemm_f32(const float* a, long a_m, long a_k, long a_batch, const float* b, long b_k, long b_n, long b_batch,
+                       float* c, long c_m, long c_n, long c_batch, int M, int N, int K, int batch, int gather_hop,
+                       int gather_pad, long gather_len, float a_scale, float a_offset, float a_pow, int relu, void* stream);
+
 /* mclt.py:90-95: out[s][t][n] = reflect-padded raw[s][t*hop + n - pad_left]; raw [S][L] fp32, out [S][T][block_width]. */
 DD_API int dd_frame_reflect(const float* raw, float* out, int S, long L, int T, int block_width, int hop, int pad_left,
                             void* stream);
