@@ -235,7 +235,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
             if (raw_out) *reinterpret_cast<uint32_t*>(raw_out + o_off + d) = pack_bf16x2(a0, a1);   // train mode
             const float y0 = a0 * (sc ? __ldg(sc + d) : 1.f);
             const float y1 = a1 * (sc ? __ldg(sc + d + 1) : 1.f);
-            *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_f(y0), mp_silu_f(y1));
+            if (out) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_f(y0), mp_silu_f(y1));
         }
     }
 }
@@ -283,6 +283,18 @@ extern "C" int dd_attention_train(const void* qk, const void* v, const float* sc
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qk);
     return launch_attention(q, q + C, static_cast<const __nv_bfloat16*>(v), scale_v, static_cast<__nv_bfloat16*>(out),
                             static_cast<__nv_bfloat16*>(raw_out), B, N, heads, lay, stream);
+}
+
+extern "C" int dd_attention_qkv(const void* qkv, void* out_raw, int B, int N, int heads, int head_dim, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(qkv && out_raw, "dd_attention_qkv: null pointer");
+    DD_REQUIRE(head_dim == kD, "dd_attention_qkv: head_dim=%d unsupported (64)", head_dim);
+    DD_REQUIRE(N > 0 && N <= 640, "dd_attention_qkv: N=%d unsupported (1..640)", N);
+    const long C = (long)heads * kD, C3 = 3 * C;
+    AttnLayout lay{C3, (long)N * C3, 0, C3, (long)N * C3, 0, C, (long)N * C, 0, 1, 1};
+    const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
+    return launch_attention(q, q + C, q + 2 * C, nullptr, nullptr, static_cast<__nv_bfloat16*>(out_raw), B, N, heads, lay,
+                            stream);
 }
 
 extern "C" int dd_attention_axis(const void* qkv, void* out, int B, int Z, int H, int W, int heads, int head_dim, int axis,

@@ -187,14 +187,14 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__
 // ------------------------------------------------------------------------------------------
 __global__ void stem_patches_kernel(const float* __restrict__ x_in, const float* __restrict__ sigma, float sigma_data,
                                     const float* __restrict__ ln_freqs, uint4* __restrict__ out, int B, int Cin, int H,
-                                    int W) {
+                                    int W, int vecs) {
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
     const int CT = Cin + 2;
-    const long total = (long)B * H * W * 8;       // 8 x (8 bf16) per pixel
+    const long total = (long)B * H * W * vecs;    // vecs x (8 bf16) per pixel: 64 or 128 patch columns
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx & 7);
-        const long pix = idx >> 3;
+        const int v = (int)(idx % vecs);
+        const long pix = idx / vecs;
         const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
         const float sg = __ldg(sigma + b);
         const float c_in = rsqrtf(sigma_data * sigma_data + sg * sg);
@@ -497,16 +497,22 @@ extern "C" int dd_avgpool2(const void* x, void* out, int B, int H, int W, int C,
     return 0;
 }
 
-extern "C" int dd_stem_patches(const float* x_in, const float* sigma, float sigma_data, const float* ln_freqs,
-                               void* out, int B, int Cin, int H, int W, void* stream_) {
+extern "C" int dd_stem_patches_cols(const float* x_in, const float* sigma, float sigma_data, const float* ln_freqs,
+                                    void* out, int B, int Cin, int H, int W, int cols, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(x_in && sigma && ln_freqs && out, "dd_stem_patches: null pointer");
-    DD_REQUIRE(9 * (Cin + 2) <= 64, "dd_stem_patches: in_channels=%d unsupported (9*(Cin+2) must be <= 64)", Cin);
-    const long total = (long)B * H * W * 8;
+    DD_REQUIRE(cols == 64 || cols == 128, "dd_stem_patches: patch width %d unsupported (64 or 128)", cols);
+    DD_REQUIRE(9 * (Cin + 2) <= cols, "dd_stem_patches: in_channels=%d unsupported (9*(Cin+2) must be <= %d)", Cin, cols);
+    const long total = (long)B * H * W * (cols / 8);
     if (total == 0) return 0;
     DD_CHECK_CUDA(dd_launch_pdl(stem_patches_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, x_in, sigma,
-                                sigma_data, ln_freqs, static_cast<uint4*>(out), B, Cin, H, W));
+                                sigma_data, ln_freqs, static_cast<uint4*>(out), B, Cin, H, W, cols / 8));
     return 0;
+}
+
+extern "C" int dd_stem_patches(const float* x_in, const float* sigma, float sigma_data, const float* ln_freqs,
+                               void* out, int B, int Cin, int H, int W, void* stream_) {
+    return dd_stem_patches_cols(x_in, sigma, sigma_data, ln_freqs, out, B, Cin, H, W, 64, stream_);
 }
 
 extern "C" int dd_noise_embedding(const float* sigma, const float* freqs, const float* phases, int cnoise,

@@ -56,7 +56,8 @@ class Block(torch.nn.Module):
     def __init__(self, level: int, in_channels: int, out_channels: int, emb_channels: int, flavor: str = "enc",
                  resample_mode: str = "keep", dropout: float = 0.0, res_balance: float = 0.3,
                  attn_balance: float = 0.3, clip_act: float = 256, mlp_multiplier: int = 2, mlp_groups: int = 8,
-                 channels_per_head: int = 64, use_attention: bool = False) -> None:
+                 channels_per_head: int = 64, use_attention: bool = False, fused_qkv: bool = False,
+                 emb_linear_groups: Optional[int] = None) -> None:
         super().__init__()
         self.level = level
         self.in_channels = in_channels
@@ -77,8 +78,15 @@ class Block(torch.nn.Module):
         self.conv_res1 = MPConv(out_channels * mlp_multiplier, out_channels, kernel=(3, 3), groups=mlp_groups)
         self.conv_skip = MPConv(in_channels, out_channels, kernel=(1, 1), groups=1)
         self.emb_gain = torch.nn.Parameter(torch.zeros([]))
-        self.emb_linear = MPConv(emb_channels, out_channels * mlp_multiplier, kernel=(1, 1), groups=mlp_groups)
-        if use_attention:
+        eg = mlp_groups if emb_linear_groups is None else emb_linear_groups      # b4: mlp_groups (:99); b4_2: its own field
+        self.emb_linear = MPConv(emb_channels, out_channels * mlp_multiplier, kernel=(1, 1), groups=eg)
+        self.fused_qkv = fused_qkv
+        if use_attention and fused_qkv:      # unet_edm2_b4_2.py:112-117: one projection, one embedding gain
+            self.attn_qkv = MPConv(out_channels, out_channels * 3, kernel=(1, 1))
+            self.attn_proj = MPConv(out_channels, out_channels, kernel=(1, 1))
+            self.emb_gain_qkv = torch.nn.Parameter(torch.zeros([]))
+            self.emb_linear_qkv = MPConv(emb_channels, out_channels, kernel=(1, 1), groups=eg)
+        elif use_attention:
             self.emb_gain_qk = torch.nn.Parameter(torch.zeros([]))
             self.emb_gain_v = torch.nn.Parameter(torch.zeros([]))
             self.emb_linear_qk = MPConv(emb_channels, out_channels, kernel=(1, 1), groups=1)
@@ -141,7 +149,8 @@ class _Plan:
         net = self.net
         items = []
         # (key, weight, gain, qk_head_dim, pad_rows, row_stride)
-        items.append(("enc.conv_in", net.enc["conv_in"].weight, None, 0, 0, 64))       # K = 9*(Cin+2) padded to 64
+        # K = 9*(Cin+2) padded to the stem's patch width; qk_head_dim < 0 marks a fused q|k|v projection (DD_WPERM_QKV)
+        items.append(("enc.conv_in", net.enc["conv_in"].weight, None, 0, 0, net.stem_cols))
         for prefix, blocks in (("enc", net.enc), ("dec", net.dec)):
             for name, blk in blocks.items():
                 if not isinstance(blk, Block):
@@ -150,7 +159,10 @@ class _Plan:
                 items.append((p + ".conv_res0", blk.conv_res0.weight, None, 0, 0, 0))
                 items.append((p + ".conv_res1", blk.conv_res1.weight, None, 0, 0, 0))
                 items.append((p + ".conv_skip", blk.conv_skip.weight, None, 0, 0, 0))
-                if blk.use_attention:
+                if blk.use_attention and blk.fused_qkv:
+                    items.append((p + ".attn_qkv", blk.attn_qkv.weight, None, -blk.channels_per_head, 0, 0))
+                    items.append((p + ".attn_proj", blk.attn_proj.weight, None, 0, 0, 0))
+                elif blk.use_attention:
                     items.append((p + ".attn_qk", blk.attn_qk.weight, None, blk.channels_per_head, 0, 0))
                     items.append((p + ".attn_v", blk.attn_v.weight, None, 0, 0, 0))
                     items.append((p + ".attn_proj", blk.attn_proj.weight, None, 0, 0, 0))
@@ -167,7 +179,8 @@ class _Plan:
             if not stale_all and self.versions.get(key) == ver and key in self.prepped:
                 continue
             self.prepped[key] = ops.weight_prep(w.detach(), gain=None if gain is None else self.gain_ptr(gain),
-                                                normalize=training, qk_head_dim=qk_dim, pad_rows=pad_rows,
+                                                normalize=training, qk_head_dim=max(qk_dim, 0),
+                                                qkv_head_dim=max(-qk_dim, 0), pad_rows=pad_rows,
                                                 row_stride=row_stride, out=self.prepped.get(key))
             self.versions[key] = ver
         self.training = training
@@ -192,7 +205,9 @@ class _Plan:
                     entries.append(dict(w=conv.weight.detach().view(O, I), gain=self.gain_ptr(gain), out=out,
                                         groups=conv.groups, bias=1.0, normalize=False, conv=conv))
                 add(".c", blk.emb_linear, blk.emb_gain)
-                if blk.use_attention:
+                if blk.use_attention and blk.fused_qkv:
+                    add(".c_qk", blk.emb_linear_qkv, blk.emb_gain_qkv)      # scales the input of the fused projection
+                elif blk.use_attention:
                     add(".c_qk", blk.emb_linear_qk, blk.emb_gain_qk)
                     add(".c_v", blk.emb_linear_v, blk.emb_gain_v)
         st = dict(entries=entries, outs=outs, descs=None, max_o=0, training=None, ptrs=None)
@@ -223,12 +238,20 @@ class UNet(DualDiffusionUNet):
 
     supports_compile = False     # no torch.compile dispatch on this path (CUDA graphs instead)
 
+    # lineage switches (overridden by unet_edm2_b4_2.UNet)
+    fused_qkv = False            # one q|k|v projection with a single embedding gain, no activation on the attention output
+    stem_cols = 64               # patch columns of the stem GEMM: 9 * (in_channels + 2) rounded up to 64 / 128
+
     def __init__(self, config: UNetConfig) -> None:
         super().__init__()
         self.config = config
         block_kwargs = {"dropout": config.dropout, "mlp_multiplier": config.mlp_multiplier,
                         "mlp_groups": config.mlp_groups, "res_balance": config.res_balance,
                         "attn_balance": config.attn_balance, "channels_per_head": config.channels_per_head}
+        if type(self).fused_qkv:
+            block_kwargs.update(fused_qkv=True, emb_linear_groups=config.emb_linear_groups)
+        # c_noise = (ln sigma - offset) / 4 and the bandwidth of the embedding frequencies (unet_edm2_b4_2.py:181, :258-259)
+        self.ln_sigma_offset = float(getattr(config, "mp_fourier_ln_sigma_offset", 0.0))
         cblock = [config.model_channels * x for x in config.channel_mult]
         cnoise = config.model_channels * config.channel_mult_noise if config.channel_mult_noise is not None else max(cblock)
         cemb = config.model_channels * config.channel_mult_emb if config.channel_mult_emb is not None else max(cblock)
@@ -236,7 +259,7 @@ class UNet(DualDiffusionUNet):
         self.cemb = cemb
 
         # embedding + training-uncertainty heads (unet_edm2_b4.py:179-187)
-        self.emb_fourier = MPFourier(cnoise)
+        self.emb_fourier = MPFourier(cnoise, bandwidth=float(getattr(config, "mp_fourier_bandwidth", 1.0)))
         self.emb_noise = MPConv(cnoise, cemb, kernel=())
         self.emb_label = MPConv(config.in_channels_emb, cemb, kernel=())
         self.emb_label_unconditional = MPConv(1, cemb, kernel=())
@@ -322,6 +345,8 @@ class UNet(DualDiffusionUNet):
         dev = torch.device(self.device)
         aux = self._aux()
         s = sigma.detach().to(device=dev, dtype=torch.float32).contiguous().flatten()
+        if self.ln_sigma_offset != 0.0:       # ln(sigma) - offset = ln(sigma * exp(-offset)): the kernels take sigma
+            s = s * math.exp(-self.ln_sigma_offset)
         L.require_cuda(self.logvar_linear.weight)
         if torch.is_grad_enabled() and self.logvar_linear.weight.requires_grad:
             from .unet_train import SigmaLogvarFunction
@@ -336,6 +361,8 @@ class UNet(DualDiffusionUNet):
         reference's train step; weight-norm runs inside the forward) and some parameter requires grad."""
         if not torch.is_grad_enabled() or not any(p.requires_grad for p in self.parameters()):
             return False
+        if type(self).fused_qkv:
+            raise NotImplementedError("dualdiffusion_b200 b4_2 UNet: the train step (backward) is not implemented for this lineage")
         if not self.training:
             raise NotImplementedError("dualdiffusion_b200 UNet: gradients are only implemented for train() mode "
                                       "(eval-mode calls belong under torch.no_grad(), as in the reference's validation)")
@@ -422,7 +449,8 @@ class UNet(DualDiffusionUNet):
         def join() -> None:
             main.wait_stream(side)
 
-        emb = ops.noise_embedding(sigma, aux["emb_freqs"], aux["emb_phases"], self.emb_noise.weight.detach(), embeddings,
+        sg_emb = sigma if self.ln_sigma_offset == 0.0 else sigma * math.exp(-self.ln_sigma_offset)
+        emb = ops.noise_embedding(sg_emb, aux["emb_freqs"], aux["emb_phases"], self.emb_noise.weight.detach(), embeddings,
                                   cfg.label_balance, normalize=self.training)
         st = plan.affine_for(B)
         descs, max_o = plan.affine_descs(st)
@@ -431,7 +459,7 @@ class UNet(DualDiffusionUNet):
             ops.emb_affine(descs, len(st["entries"]), max_o, emb)
         cvec = st["outs"]
 
-        patches = ops.stem_patches(net_in, sigma, cfg.sigma_data, ln_freqs)
+        patches = ops.stem_patches(net_in, sigma, cfg.sigma_data, ln_freqs, cols=type(self).stem_cols)
         x = ops.mpconv(patches, W["enc.conv_in"], 1)
         join()
         skips = [x]
@@ -439,6 +467,11 @@ class UNet(DualDiffusionUNet):
         ca_a, cb_a = _mp_sum_coeffs(cfg.attn_balance)
 
         def attention_tail(p: str, blk: Block, x2: Tensor, xs: Tensor) -> Tensor:
+            if blk.fused_qkv:     # unet_edm2_b4_2.py:146-157: qkv = attn_qkv(x * c); y = attn_proj(SDPA(q, k, v)); mp_sum
+                qkv = ops.mpconv(xs, W[p + ".attn_qkv"], 1)
+                y = ops.attention_qkv(qkv, blk.num_heads, blk.channels_per_head)
+                return ops.mpconv(y, W[p + ".attn_proj"], 1, epi=L.EPI_RESIDUAL, alpha=cb_a, beta=ca_a, clip=blk.clip_act,
+                                  residual=x2)
             # outputs of side-stream kernels are allocated on the main stream (allocator reuse stays ordered)
             v = torch.empty_like(x2)
             fork()

@@ -99,13 +99,13 @@ def mpconv_naive(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1) -> T
 
 
 def stem_patches(x_in: Tensor, sigma: Tensor, sigma_data: float, ln_freqs: Tensor,
-                 out: Optional[Tensor] = None) -> Tensor:
-    """Stem input as zero-padded 3x3 patches [B, H, W, 64] (conv_in then runs as a K=64 tensor-core GEMM)."""
+                 out: Optional[Tensor] = None, cols: int = 64) -> Tensor:
+    """Stem input as zero-padded 3x3 patches [B, H, W, cols] (conv_in then runs as a K=cols tensor-core GEMM)."""
     B, Cin, H, W = x_in.shape
     if out is None:
-        out = torch.empty((B, H, W, 64), device=x_in.device, dtype=torch.bfloat16)
-    L.check(L.load().dd_stem_patches(L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(ln_freqs), L.ptr(out), B, Cin, H, W,
-                                     L.stream_ptr()))
+        out = torch.empty((B, H, W, cols), device=x_in.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_stem_patches_cols(L.ptr(x_in), L.ptr(sigma), sigma_data, L.ptr(ln_freqs), L.ptr(out), B, Cin, H, W,
+                                          cols, L.stream_ptr()))
     _count()
     return out
 
@@ -194,6 +194,15 @@ def attention(qk: Tensor, v: Tensor, scale_v: Tensor, heads: int, head_dim: int 
     out = torch.empty_like(v)
     L.check(L.load().dd_attention(L.ptr(qk), L.ptr(v), L.ptr(scale_v), L.ptr(out), B, H * W, heads, head_dim,
                                   L.stream_ptr()))
+    _count()
+    return out
+
+
+def attention_qkv(qkv: Tensor, heads: int, head_dim: int = 64) -> Tensor:
+    """Fused q|k|v attention of the b4_2 lineage: qkv [B, H, W, 3C] -> raw attention output [B, H, W, C]."""
+    B, H, W, C3 = qkv.shape
+    out = torch.empty((B, H, W, C3 // 3), device=qkv.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_attention_qkv(L.ptr(qkv), L.ptr(out), B, H * W, heads, head_dim, L.stream_ptr()))
     _count()
     return out
 

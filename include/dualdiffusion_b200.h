@@ -101,6 +101,9 @@ DD_API int dd_mpconv_forward_naive(const void* x, const void* w_prepped, void* o
  * with weights from dd_weight_prep(DD_WFMT_BF16_OTI, out_row_stride=64).                            */
 DD_API int dd_stem_patches(const float* x_in_nchw, const float* sigma, float sigma_data, const float* ln_freqs_h,
                            void* out_patches, int B, int Cin, int H, int W, void* stream);
+/* Same with `cols` (64 or 128) patch columns per pixel: 8-channel latents (unet_edm2_b4_2.py: 9 * (8 + 2) = 90 columns). */
+DD_API int dd_stem_patches_cols(const float* x_in_nchw, const float* sigma, float sigma_data, const float* ln_freqs_h,
+                                void* out_patches, int B, int Cin, int H, int W, int cols, void* stream);
 /* D = c_skip(sigma)*x_in + c_out(sigma)*conv_out(x) on the tensor cores; w_prepped16: bf16 [16][9][C]
  * (rows >= Cout zero) from dd_weight_prep(gain = out_gain).  x_ref (optional, [B][Cout+1][H][W] fp32):
  * D = mp_sum(x_ref[:, :-1], D, t = x_ref[:, -1:])  (:293-294).  Result fp32 NCHW.                     */
@@ -157,6 +160,11 @@ DD_API int dd_axpby(const void* a, const void* b, float alpha, float beta, float
  * head_dim (eps 1e-4), softmax(q k^T / sqrt(head_dim)) v, then out = mp_silu(y * scale_v[b][c]).     */
 DD_API int dd_attention(const void* qk, const void* v, const float* scale_v, void* out, int B, int N, int heads,
                  int head_dim, void* stream);
+
+/* Fused-projection variant of the newer lineage (unet_edm2_b4_2.py:146-156): qkv [B][N][3C] holds the q | k | v thirds
+ * (after DD_WPERM_QKV); cosine normalisation of q, k, v and softmax(q k^T / sqrt(head_dim)) v as above, no gain and no
+ * activation on the result: out_raw [B][N][C].                                                                        */
+DD_API int dd_attention_qkv(const void* qkv, void* out_raw, int B, int N, int heads, int head_dim, void* stream);
 
 /* Train-mode variant: additionally writes the pre-activation attention output a = softmax(qk^T/8) v
  * (bf16 [B][N][C]) that dd_attention_bwd and dd_silu_scale_bwd need.                                     */

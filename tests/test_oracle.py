@@ -223,3 +223,17 @@ def test_axis_attention_oracle_vs_reference_golden():
         got = uo.mp_silu(uo.axis_attention_b3(case["qkv"], case["heads"]))
         assert got.shape == case["y_silu"].shape
         assert rel_err(got, case["y_silu"]) < 1e-5, tag
+
+
+def test_b4_2_oracle_vs_reference_golden():
+    """Row N4: the b4_2 lineage restatement against the unmodified reference (tests/golden/make_golden_b4_2.py)."""
+    from oracle import unet_b4_2_oracle as bo
+    g = load_golden("unet_b4_2_small.pt")
+    spec = bo.small_spec()
+    sd = bo.synth_state_dict(spec, seed=0)
+    assert _checksum(sd) == pytest.approx(g["weight_checksum"], rel=1e-12)
+    emb = bo.get_embeddings(sd, g["clap"], g["mask"])
+    assert rel_err(emb, g["emb"]) < 1e-6
+    assert rel_err(bo.unet_forward(sd, spec, g["x"], g["sigma"], emb), g["d"]) < 1e-5
+    assert rel_err(bo.unet_forward(sd, spec, g["x"], g["sigma"], emb, g["x_ref"]), g["d_xref"]) < 1e-5
+    assert rel_err(bo.sigma_loss_logvar(sd, spec, g["sigma"]), g["logvar"]) < 1e-6
