@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------
 // C-ABI error plumbing: every exported function returns 0 on success; on failure the
@@ -51,7 +52,8 @@ inline cudaError_t dd_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("DD_DISABLE_PDL") != nullptr;      // tuning experiments only
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

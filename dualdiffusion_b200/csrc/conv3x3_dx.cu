@@ -266,7 +266,9 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        // Warp-uniform loop, one elected lane issues: a single-lane (`lane == 0`) loop makes the compiler wrap every UTMALDG
+        // in a lane-serialisation loop (R2UR + ELECT + BRA.U.ANY), which costs the producer ~250 cycles per box.
+        {
             // Each issuing warp owns its own ring of `ring` activation stages (stage = warp * ring + position): a parity
             // wait is only sound for a waiter that observes every phase of its barrier in order, and two warps taking
             // alternate fills of one ring can lap each other (tools/sim_dx_protocol.py reproduces the deadlock).
@@ -279,13 +281,18 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         for (int w = 0; w < p.mma_warps; ++w) ptx::mbar_wait(&b_empty[w], b_par);
                         b_par ^= 1;
                     }
-                    ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.nsub * p.b_sub_bytes);
+                    if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.nsub * p.b_sub_bytes);
+                    __syncwarp();
                     for (int s = 0; s < p.nsub; ++s) {
                         const int co0 = panel_co0(p, wk.panel, s);
                         uint8_t* dst = smem + (size_t)s * p.b_sub_bytes;
-                        for (int kc = 0; kc < p.kchunks; ++kc)
-                            for (int tap = 0; tap < 9; ++tap, dst += p.b_dx_bytes)   // tap = dy * 3 + t: block (kc, dy), rows [t][co]
-                                ptx::tma_load_2d(dst, &tmB, &b_full, tap * p.cin_g + kc * 64, co0);
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            int col = kc * 64;
+                            for (int tap = 0; tap < 9; ++tap, dst += p.b_dx_bytes, col += p.cin_g) {   // tap = dy * 3 + t: block (kc, dy), rows [t][co]
+                                if (ptx::elect_one()) ptx::tma_load_2d(dst, &tmB, &b_full, col, co0);
+                                __syncwarp();
+                            }
+                        }
                     }
                 }
                 if (first) { ptx::grid_dependency_wait(); first = false; }      // weights do not depend on the previous kernel
@@ -293,10 +300,13 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     const uint32_t stage = (uint32_t)(turn * p.ring) + rpos;
                     ptx::mbar_wait(&a_empty[stage], rphase ^ 1);
-                    if (kc == 0) trace_stamp<TRACE>(p, 0, (uint32_t)(u - u_begin) * p.nsub);
-                    ptx::mbar_arrive_expect_tx(&a_full[stage], kABytes);
-                    ptx::tma_load_4d(smem + p.off_a + (size_t)stage * kABytes, &tmA, &a_full[stage], ci0 + kc * 64, wk.w0 - 1,
-                                     wk.h0 - 1, wk.b);
+                    if (kc == 0 && lane == 0) trace_stamp<TRACE>(p, 0, (uint32_t)(u - u_begin) * p.nsub);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&a_full[stage], kABytes);
+                        ptx::tma_load_4d(smem + p.off_a + (size_t)stage * kABytes, &tmA, &a_full[stage], ci0 + kc * 64, wk.w0 - 1,
+                                         wk.h0 - 1, wk.b);
+                    }
+                    __syncwarp();
                     if (++rpos == (uint32_t)p.ring) { rpos = 0; rphase ^= 1; }
                 }
                 if (p.mma_warps == 2) {                   // next unit belongs to the other warp: swap the ring cursors
@@ -304,13 +314,16 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     t0 = rphase; rphase = rphase_other; rphase_other = t0;
                     turn ^= 1;
                 }
-                trace_stamp<TRACE>(p, 1, (uint32_t)(u - u_begin) * p.nsub);
+                if (lane == 0) trace_stamp<TRACE>(p, 1, (uint32_t)(u - u_begin) * p.nsub);
                 if (has_res) {
                     for (int s = 0; s < p.nsub; ++s) {
                         ptx::mbar_wait(&res_empty[rs], rph ^ 1);
-                        ptx::mbar_arrive_expect_tx(&res_full[rs], p.res_bytes);
-                        ptx::tma_load_4d(smem + p.off_res + (size_t)rs * p.res_stride, &tmR, &res_full[rs],
-                                         panel_co0(p, wk.panel, s), wk.w0, wk.h0, wk.b);
+                        if (ptx::elect_one()) {
+                            ptx::mbar_arrive_expect_tx(&res_full[rs], p.res_bytes);
+                            ptx::tma_load_4d(smem + p.off_res + (size_t)rs * p.res_stride, &tmR, &res_full[rs],
+                                             panel_co0(p, wk.panel, s), wk.w0, wk.h0, wk.b);
+                        }
+                        __syncwarp();
                         if (++rs == (uint32_t)p.res_stages) { rs = 0; rph ^= 1; }
                     }
                 }
@@ -563,7 +576,8 @@ int dd_launch_conv3x3_dx(const DxConvArgs& a, cudaStream_t stream) {
     static const bool disabled = getenv("DD_DISABLE_DX") != nullptr;          // tuning / A-B experiments only
     if (disabled) return -1;
     const int cin_g = a.Cin / a.groups, cout_g = a.Cout / a.groups;
-    if (a.H < 8 || a.W < 16 || a.Cin < 64 || cin_g % 32 != 0 || cout_g % 32 != 0) return -1;
+    static const int min_h = getenv("DD_DX_MIN_H") ? atoi(getenv("DD_DX_MIN_H")) : 2;      // tuning: images shorter than a tile
+    if (a.H < min_h || a.W < 16 || a.Cin < 64 || cin_g % 32 != 0 || cout_g % 32 != 0) return -1;
     if (a.epi != DD_EPI_NONE && a.epi != DD_EPI_SCALE_SILU && a.epi != DD_EPI_RESIDUAL) return -1;
     PFN_encodeTiled encode = reinterpret_cast<PFN_encodeTiled>(dd_tensormap_encode_fn());
     DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");

@@ -472,59 +472,77 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
+        // The whole warp runs the (warp-uniform) loop and one elected lane issues.  With a single-lane (`lane == 0`) loop
+        // the compiler cannot keep the TMA operands in uniform registers: it wraps every UTMALDG in a lane-serialisation
+        // loop (R2UR + ELECT + BRA.U.ANY, ~250 cycles per box), which made the producer -- not L2 -- the limiter of the
+        // short k-loops of the small levels.  (tap, k-chunk) advance incrementally: no integer division per box.
         // Weights never depend on the preceding kernel: the B boxes of the first pipeline fill are issued before
         // griddepcontrol.wait, so under programmatic dependent launch they stream in while the previous kernel
         // drains; activations (A boxes) are only touched after the wait.
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            bool waited = false;
-            int prefetched = 0;                          // stages of the first tile whose B boxes are already in flight
-            {
-                const int tile = blockIdx.x;
-                if (tile < p.num_tiles) {
-                    const TileCoord t = decode_tile(p, tile);
-                    const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
-                    for (int it0 = 0; it0 < p.k_iters && prefetched < p.stages; it0 += p.sub, ++prefetched) {
-                        const int cnt = min(p.sub, p.k_iters - it0);
-                        ptx::mbar_arrive_expect_tx(&full_bar[prefetched], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
-                        for (int j = 0; j < cnt; ++j) {
-                            const int it = it0 + j;
-                            const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                            ptx::tma_load_2d(smem + prefetched * stage_bytes + j * pair_bytes + kABufBytes, &tmB,
-                                             &full_bar[prefetched], tap * p.cin_g + kc * KC, b_row);
-                        }
-                    }
+        struct KIter {
+            int tap, kc, dy, dx;
+            __device__ __forceinline__ void reset(const ConvParams& q) { tap = 0; kc = 0; dy = -(q.kh / 2); dx = -(q.kw / 2); }
+            __device__ __forceinline__ void next(const ConvParams& q) {
+                if (++kc == q.kchunks) {
+                    kc = 0; ++tap;
+                    if (++dx > q.kw / 2) { dx = -(q.kw / 2); ++dy; }
                 }
             }
-            ptx::grid_dependency_wait();
-            waited = true;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        };
+        uint32_t stage = 0, phase = 0;
+        int prefetched = 0;                          // stages of the first tile whose B boxes are already in flight
+        {
+            const int tile = blockIdx.x;
+            if (tile < p.num_tiles) {
                 const TileCoord t = decode_tile(p, tile);
-                const int a_c0 = t.g * p.cin_g;
                 const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
-                for (int it0 = 0; it0 < p.k_iters; it0 += p.sub) {
+                KIter ki;
+                ki.reset(p);
+                for (int it0 = 0; it0 < p.k_iters && prefetched < p.stages; it0 += p.sub, ++prefetched) {
                     const int cnt = min(p.sub, p.k_iters - it0);
-                    const bool b_done = prefetched > 0;              // this stage's barrier is armed, B already issued
-                    if (!b_done) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
-                    } else {
-                        --prefetched;
-                    }
+                    if (ptx::elect_one())
+                        ptx::mbar_arrive_expect_tx(&full_bar[prefetched], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                    __syncwarp();
                     for (int j = 0; j < cnt; ++j) {
-                        const int it = it0 + j;
-                        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                        const int dy = tap / p.kw - p.kh / 2;
-                        const int dx = tap % p.kw - p.kw / 2;
-                        uint8_t* a_dst = smem + stage * stage_bytes + j * pair_bytes;
-                        uint8_t* b_dst = a_dst + kABufBytes;
-                        ptx::tma_load_4d(a_dst, &tmA, &full_bar[stage], a_c0 + kc * KC, t.w0 + dx, t.h0 + dy, t.b0);
-                        if (!b_done) ptx::tma_load_2d(b_dst, &tmB, &full_bar[stage], tap * p.cin_g + kc * KC, b_row);
+                        if (ptx::elect_one())
+                            ptx::tma_load_2d(smem + prefetched * stage_bytes + j * pair_bytes + kABufBytes, &tmB,
+                                             &full_bar[prefetched], ki.tap * p.cin_g + ki.kc * KC, b_row);
+                        __syncwarp();
+                        ki.next(p);
                     }
-                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
-            (void)waited;
+        }
+        ptx::grid_dependency_wait();
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            const int a_c0 = t.g * p.cin_g;
+            const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
+            KIter ki;
+            ki.reset(p);
+            for (int it0 = 0; it0 < p.k_iters; it0 += p.sub) {
+                const int cnt = min(p.sub, p.k_iters - it0);
+                const bool b_done = prefetched > 0;              // this stage's barrier is armed, B already issued
+                if (!b_done) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (ptx::elect_one())
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                    __syncwarp();
+                } else {
+                    --prefetched;
+                }
+                for (int j = 0; j < cnt; ++j) {
+                    uint8_t* a_dst = smem + stage * stage_bytes + j * pair_bytes;
+                    if (ptx::elect_one()) {
+                        ptx::tma_load_4d(a_dst, &tmA, &full_bar[stage], a_c0 + ki.kc * KC, t.w0 + ki.dx, t.h0 + ki.dy, t.b0);
+                        if (!b_done)
+                            ptx::tma_load_2d(a_dst + kABufBytes, &tmB, &full_bar[stage], ki.tap * p.cin_g + ki.kc * KC, b_row);
+                    }
+                    __syncwarp();
+                    ki.next(p);
+                }
+                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
@@ -905,7 +923,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        // warp-uniform loop, one elected lane issues (see conv_igemm_kernel: a single-lane loop costs a lane-serialisation
+        // loop around every UTMALDG)
+        {
             uint32_t stage = 0, phase = 0, b_par = 0;
             int cur_panel = -1;
             bool waited = false;
@@ -914,25 +934,34 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const HaloTile t = decode_halo_tile(p, tile);
                 if (t.panel != cur_panel) {
                     if (cur_panel >= 0) { ptx::mbar_wait(&b_empty, b_par); b_par ^= 1; }   // old panel fully consumed
-                    ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.kchunks * 9u * p.b_block_bytes);
+                    if (ptx::elect_one())
+                        ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.kchunks * 9u * p.b_block_bytes);
+                    __syncwarp();
                     const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
-                    for (int kc = 0; kc < p.kchunks; ++kc)
-                        for (int tap = 0; tap < 9; ++tap)
-                            ptx::tma_load_2d(b_smem + (size_t)(kc * 9 + tap) * p.b_block_bytes, &tmB, &b_full,
-                                             tap * p.cin_g + kc * 64, b_row);
+                    uint8_t* dst = b_smem;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        int col = kc * 64;
+                        for (int tap = 0; tap < 9; ++tap, col += p.cin_g, dst += p.b_block_bytes) {
+                            if (ptx::elect_one()) ptx::tma_load_2d(dst, &tmB, &b_full, col, b_row);
+                            __syncwarp();
+                        }
+                    }
                     cur_panel = t.panel;
                 }
                 // the weight panel does not depend on the previous kernel; activations do (PDL)
                 if (!waited) { ptx::grid_dependency_wait(); waited = true; }
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     ptx::mbar_wait(&a_empty[stage], phase ^ 1);
-                    if (kc == 0) trace_stamp<TRACE>(p, kTrTmaFree, tr_local);
-                    ptx::mbar_arrive_expect_tx(&a_full[stage], p.halo_bytes);
-                    ptx::tma_load_4d(a_smem + (size_t)stage * p.halo_stride, &tmA, &a_full[stage], t.g * p.cin_g + kc * 64,
-                                     t.w0 - 1, t.b, t.h0 - 1);      // tensor-map dims are (C, W, B, H)
+                    if (kc == 0 && lane == 0) trace_stamp<TRACE>(p, kTrTmaFree, tr_local);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&a_full[stage], p.halo_bytes);
+                        ptx::tma_load_4d(a_smem + (size_t)stage * p.halo_stride, &tmA, &a_full[stage], t.g * p.cin_g + kc * 64,
+                                         t.w0 - 1, t.b, t.h0 - 1);      // tensor-map dims are (C, W, B, H)
+                    }
+                    __syncwarp();
                     if (++stage == (uint32_t)p.a_stages) { stage = 0; phase ^= 1; }
                 }
-                trace_stamp<TRACE>(p, kTrTmaIssued, tr_local);
+                if (lane == 0) trace_stamp<TRACE>(p, kTrTmaIssued, tr_local);
             }
         }
     } else if (warp == 1) {

@@ -121,29 +121,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        // warp-uniform loop, one elected lane issues (a single-lane loop makes the compiler wrap every UTMALDG in a
+        // lane-serialisation loop, ~250 cycles per box); the pixel-tile coordinates advance without divisions
+        {
             uint32_t stage = 0, phase = 0;
+            int tw = 0, th = 0, b = 0;
+            if (p.halo) {
+                tw = pt_begin % p.tiles_w;
+                th = (pt_begin / p.tiles_w) % p.tiles_h;
+                b = pt_begin / (p.tiles_w * p.tiles_h);
+            }
             for (int pt = pt_begin; pt < pt_end; ++pt) {
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)a_boxes * p.a_box_bytes + (uint32_t)cnt * p.x_box_bytes);
                 uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
                 uint8_t* x_dst = a_dst + 2 * p.a_box_bytes;
-                if (p.halo) {
-                    const int tw = pt % p.tiles_w;
-                    const int th = (pt / p.tiles_w) % p.tiles_h;
-                    const int b = pt / (p.tiles_w * p.tiles_h);
-                    for (int a = 0; a < a_boxes; ++a)
-                        ptx::tma_load_4d(a_dst + a * p.a_box_bytes, &tmY, &full_bar[stage], m0 + 64 * a, tw * 8, th * p.ht, b);
-                    for (int c = 0; c < cnt; ++c)
-                        ptx::tma_load_4d(x_dst + c * p.x_box_stride, &tmX, &full_bar[stage], n0 + 64 * c, tw * 8 - 1,
-                                         th * p.ht - 1, b);
-                } else {
-                    const int pix0 = pt * 128;
-                    for (int a = 0; a < a_boxes; ++a)
-                        ptx::tma_load_2d(a_dst + a * p.a_box_bytes, &tmY, &full_bar[stage], m0 + 64 * a, pix0);
-                    for (int c = 0; c < cnt; ++c)
-                        ptx::tma_load_2d(x_dst + c * p.x_box_stride, &tmX, &full_bar[stage], n0 + 64 * c, pix0);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)a_boxes * p.a_box_bytes + (uint32_t)cnt * p.x_box_bytes);
+                    if (p.halo) {
+                        for (int a = 0; a < a_boxes; ++a)
+                            ptx::tma_load_4d(a_dst + a * p.a_box_bytes, &tmY, &full_bar[stage], m0 + 64 * a, tw * 8, th * p.ht, b);
+                        for (int c = 0; c < cnt; ++c)
+                            ptx::tma_load_4d(x_dst + c * p.x_box_stride, &tmX, &full_bar[stage], n0 + 64 * c, tw * 8 - 1,
+                                             th * p.ht - 1, b);
+                    } else {
+                        const int pix0 = pt * 128;
+                        for (int a = 0; a < a_boxes; ++a)
+                            ptx::tma_load_2d(a_dst + a * p.a_box_bytes, &tmY, &full_bar[stage], m0 + 64 * a, pix0);
+                        for (int c = 0; c < cnt; ++c)
+                            ptx::tma_load_2d(x_dst + c * p.x_box_stride, &tmX, &full_bar[stage], n0 + 64 * c, pix0);
+                    }
                 }
+                __syncwarp();
+                if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++b; } }
                 if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
             }
         }

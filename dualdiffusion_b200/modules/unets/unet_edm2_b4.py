@@ -17,6 +17,7 @@ the CUDA library the constructor works (parameters are plain tensors) but `forwa
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -131,6 +132,7 @@ class _Plan:
         # second stream: independent kernels of a block (conv_skip vs the residual branch, attn_v vs attn_qk,
         # the embedding projections vs the stem) run as parallel branches of the captured graph
         self.side = torch.cuda.Stream(device=self.device)
+        self.no_side = os.environ.get("DD_NO_SIDE", "0") == "1"        # tuning: no parallel graph branches
 
     def gain_ptr(self, p: torch.nn.Parameter) -> Tensor:
         i = self.gain_index[id(p)]
@@ -441,13 +443,15 @@ class UNet(DualDiffusionUNet):
         g = cfg.mlp_groups
 
         main = torch.cuda.current_stream(plan.device)
-        side = plan.side
+        side = main if plan.no_side else plan.side
 
         def fork() -> None:
-            side.wait_stream(main)
+            if side is not main:
+                side.wait_stream(main)
 
         def join() -> None:
-            main.wait_stream(side)
+            if side is not main:
+                main.wait_stream(side)
 
         sg_emb = sigma if self.ln_sigma_offset == 0.0 else sigma * math.exp(-self.ln_sigma_offset)
         emb = ops.noise_embedding(sg_emb, aux["emb_freqs"], aux["emb_phases"], self.emb_noise.weight.detach(), embeddings,
@@ -461,17 +465,27 @@ class UNet(DualDiffusionUNet):
 
         patches = ops.stem_patches(net_in, sigma, cfg.sigma_data, ln_freqs, cols=type(self).stem_cols)
         x = ops.mpconv(patches, W["enc.conv_in"], 1)
-        join()
-        skips = [x]
+        emb_pending = True            # the embedding projections are first needed by the first conv_res0 epilogue
         ca_r, cb_r = _mp_sum_coeffs(cfg.res_balance)
         ca_a, cb_a = _mp_sum_coeffs(cfg.attn_balance)
 
-        def attention_tail(p: str, blk: Block, x2: Tensor, xs: Tensor) -> Tensor:
+        dec_list = list(self.dec.items())
+
+        def final_conv(xin: Tensor, w: Tensor, ksize: int, groups: int, ca: float, cb: float, clip: float, residual: Tensor,
+                       want_silu: bool) -> Tuple[Tensor, Optional[Tensor]]:
+            """Last convolution of a block (conv_res1 or attn_proj, mp_sum + clip epilogue); with `want_silu` the epilogue
+            also writes mp_silu(x), the conv_res0 input of a following decoder block that neither concatenates nor
+            up-samples (unet_edm2_b4.py:119)."""
+            if want_silu:
+                return ops.mpconv(xin, w, ksize, groups, epi=L.EPI_RESIDUAL, alpha=cb, beta=ca, clip=clip, residual=residual,
+                                  epi2=L.EPI2_SILU)
+            return ops.mpconv(xin, w, ksize, groups, epi=L.EPI_RESIDUAL, alpha=cb, beta=ca, clip=clip, residual=residual), None
+
+        def attention_tail(p: str, blk: Block, x2: Tensor, xs: Tensor, want_silu: bool) -> Tuple[Tensor, Optional[Tensor]]:
             if blk.fused_qkv:     # unet_edm2_b4_2.py:146-157: qkv = attn_qkv(x * c); y = attn_proj(SDPA(q, k, v)); mp_sum
                 qkv = ops.mpconv(xs, W[p + ".attn_qkv"], 1)
                 y = ops.attention_qkv(qkv, blk.num_heads, blk.channels_per_head)
-                return ops.mpconv(y, W[p + ".attn_proj"], 1, epi=L.EPI_RESIDUAL, alpha=cb_a, beta=ca_a, clip=blk.clip_act,
-                                  residual=x2)
+                return final_conv(y, W[p + ".attn_proj"], 1, 1, ca_a, cb_a, blk.clip_act, x2, want_silu)
             # outputs of side-stream kernels are allocated on the main stream (allocator reuse stays ordered)
             v = torch.empty_like(x2)
             fork()
@@ -480,28 +494,38 @@ class UNet(DualDiffusionUNet):
             qk = ops.mpconv(xs, W[p + ".attn_qk"], 1)
             join()
             y = ops.attention(qk, v, cvec[p + ".c_v"], blk.num_heads, blk.channels_per_head)
-            return ops.mpconv(y, W[p + ".attn_proj"], 1, epi=L.EPI_RESIDUAL, alpha=cb_a, beta=ca_a, clip=blk.clip_act,
-                              residual=x2)
+            return final_conv(y, W[p + ".attn_proj"], 1, 1, ca_a, cb_a, blk.clip_act, x2, want_silu)
 
-        for name, blk in self.enc.items():
-            if not isinstance(blk, Block):
-                continue
+        def block_tail(p: str, blk: Block, y0: Tensor, res: Tensor, want_silu: bool) -> Tuple[Tensor, Optional[Tensor]]:
+            if blk.use_attention:
+                x2, xs = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
+                                    residual=res, epi2=L.EPI2_SCALE, scale2=cvec[p + ".c_qk"])
+                return attention_tail(p, blk, x2, xs, want_silu)
+            return final_conv(y0, W[p + ".conv_res1"], 3, g, ca_r, cb_r, blk.clip_act, res, want_silu)
+
+        def wants_silu(i: int) -> bool:
+            """True when decoder block i exists and takes x as it is (no mp_cat, no up-sampling): the "in" blocks."""
+            return i < len(dec_list) and "layer" not in dec_list[i][0] and dec_list[i][1].resample_mode != "up"
+
+        skips = [x]
+        enc_blocks = [(name, blk) for name, blk in self.enc.items() if isinstance(blk, Block)]
+        s_next: Optional[Tensor] = None
+        for i, (name, blk) in enumerate(enc_blocks):
             p = "enc." + name
             if blk.resample_mode == "down":
                 x = ops.avgpool2(x)
             t0 = ops.mpconv(x, W[p + ".conv_skip"], 1)
             xn, s = ops.pixnorm_silu(t0)
+            if emb_pending:
+                join()
+                emb_pending = False
             y0 = ops.mpconv(s, W[p + ".conv_res0"], 3, g, epi=L.EPI_SCALE_SILU, scale=cvec[p + ".c"])
-            if blk.use_attention:
-                x2, xs = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
-                                    residual=xn, epi2=L.EPI2_SCALE, scale2=cvec[p + ".c_qk"])
-                x = attention_tail(p, blk, x2, xs)
-            else:
-                x = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
-                               clip=blk.clip_act, residual=xn)
+            x, s_next = block_tail(p, blk, y0, xn, i + 1 == len(enc_blocks) and wants_silu(0))
             skips.append(x)
+        if emb_pending:
+            join()
 
-        for name, blk in self.dec.items():
+        for i, (name, blk) in enumerate(dec_list):
             p = "dec." + name
             if "layer" in name:
                 skip = skips.pop()
@@ -509,6 +533,8 @@ class UNet(DualDiffusionUNet):
                 xc, s = ops.cat_silu(x, skip, wa, wb, False)
             elif blk.resample_mode == "up":
                 xc, s = ops.cat_silu(x, None, 1.0, 0.0, True)
+            elif s_next is not None:
+                xc, s = x, s_next                     # written by the previous block's last epilogue
             else:
                 xc = x
                 _, s = ops.cat_silu(x, None, 1.0, 0.0, False, need_cat=False)
@@ -520,13 +546,7 @@ class UNet(DualDiffusionUNet):
                 ops.mpconv(xc, W[p + ".conv_skip"], 1, out=t0)
             y0 = ops.mpconv(s, W[p + ".conv_res0"], 3, g, epi=L.EPI_SCALE_SILU, scale=cvec[p + ".c"])
             join()
-            if blk.use_attention:
-                x2, xs = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
-                                    residual=t0, epi2=L.EPI2_SCALE, scale2=cvec[p + ".c_qk"])
-                x = attention_tail(p, blk, x2, xs)
-            else:
-                x = ops.mpconv(y0, W[p + ".conv_res1"], 3, g, epi=L.EPI_RESIDUAL, alpha=cb_r, beta=ca_r,
-                               clip=blk.clip_act, residual=t0)
+            x, s_next = block_tail(p, blk, y0, t0, wants_silu(i + 1))
 
         return ops.conv_out(x, W["conv_out"], x_in, sigma, cfg.sigma_data, x_ref)
 
