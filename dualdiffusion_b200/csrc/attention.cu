@@ -90,47 +90,52 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
     const __nv_bfloat16* k_base = k_ptr + q_off;
     const __nv_bfloat16* v_base = v_ptr + (size_t)outer * lay.v_outer + (size_t)inner * lay.v_inner + head * kD + sub * 8;
 
-    // Staging is latency-bound if every token's load is followed by its use: issue the loads of kStageBatch
-    // tokens per thread first (one memory round trip per batch), then normalise and store them.
-    constexpr int kStageBatch = 6;
-    auto stage_rows = [&](const __nv_bfloat16* base, size_t token_stride, int first_token, int n_rows, int row_limit,
-                          __nv_bfloat16* dst) {
-        for (int r0 = 0; r0 < n_rows; r0 += 32 * kStageBatch) {
-            uint4 q[kStageBatch];
+    // Staging is latency-bound: every load a thread needs for K, V and Q of up to 384 keys is issued before the first one is
+    // consumed (one memory round trip instead of one per tensor and per 6 tokens), then normalised and stored.
+    constexpr int kPass = 12;          // 32 tokens per pass: 384 keys per chunk
+    auto load_rows = [&](auto& q, const __nv_bfloat16* base, size_t token_stride, int first_token, int r0, int n_rows,
+                         int row_limit) {
 #pragma unroll
-            for (int u = 0; u < kStageBatch; ++u) {
-                const int r = r0 + u * 32 + tok_in_pass;
-                q[u] = make_uint4(0, 0, 0, 0);
-                if (r < n_rows && first_token + r < row_limit)
-                    q[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(first_token + r) * token_stride));
-            }
-#pragma unroll
-            for (int u = 0; u < kStageBatch; ++u) {
-                const int r = r0 + u * 32 + tok_in_pass;
-                if (r0 + u * 32 >= n_rows) break;           // warp-uniform: whole batch row beyond the tile
-                const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-                float f[8];
-                float ss = 0.f;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 t2 = unpack_bf16x2(w[j]);
-                    f[2 * j] = t2.x; f[2 * j + 1] = t2.y;
-                    ss += t2.x * t2.x + t2.y * t2.y;
-                }
-                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-                ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-                const float inv = 1.f / (kNormEps + sqrtf(ss) * 0.125f);   // ||x|| / sqrt(64)
-                if (r < n_rows)
-                    *reinterpret_cast<uint4*>(dst + (size_t)r * kKStride + sub * 8) =
-                        make_uint4(pack_bf16x2(f[0] * inv, f[1] * inv), pack_bf16x2(f[2] * inv, f[3] * inv),
-                                   pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
-            }
+        for (int u = 0; u < (int)(sizeof(q) / sizeof(uint4)); ++u) {
+            const int r = r0 + u * 32 + tok_in_pass;
+            q[u] = make_uint4(0, 0, 0, 0);
+            if (r < n_rows && first_token + r < row_limit)
+                q[u] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(first_token + r) * token_stride));
         }
     };
-    stage_rows(k_base, (size_t)lay.q_tok, 0, npad, N, Ks);
-    stage_rows(v_base, (size_t)lay.v_tok, 0, npad, N, Vs);
-    stage_rows(q_base, (size_t)lay.q_tok, q0, kQTile, N, Qs);
+    auto norm_store_rows = [&](const auto& q, int r0, int n_rows, __nv_bfloat16* dst) {
+#pragma unroll
+        for (int u = 0; u < (int)(sizeof(q) / sizeof(uint4)); ++u) {
+            const int r = r0 + u * 32 + tok_in_pass;
+            if (r0 + u * 32 >= n_rows) break;           // warp-uniform: whole pass beyond the tile
+            const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+            float f[8];
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 t2 = unpack_bf16x2(w[j]);
+                f[2 * j] = t2.x; f[2 * j + 1] = t2.y;
+                ss += t2.x * t2.x + t2.y * t2.y;
+            }
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+            const float inv = 1.f / (kNormEps + sqrtf(ss) * 0.125f);   // ||x|| / sqrt(64)
+            if (r < n_rows)
+                *reinterpret_cast<uint4*>(dst + (size_t)r * kKStride + sub * 8) =
+                    make_uint4(pack_bf16x2(f[0] * inv, f[1] * inv), pack_bf16x2(f[2] * inv, f[3] * inv),
+                               pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
+        }
+    };
+    for (int c0 = 0; c0 < npad; c0 += 32 * kPass) {
+        uint4 kq[kPass], vq[kPass], qq[kQTile / 32];
+        load_rows(kq, k_base, (size_t)lay.q_tok, 0, c0, npad, N);
+        load_rows(vq, v_base, (size_t)lay.v_tok, 0, c0, npad, N);
+        if (c0 == 0) load_rows(qq, q_base, (size_t)lay.q_tok, q0, 0, kQTile, N);
+        norm_store_rows(kq, c0, npad, Ks);
+        norm_store_rows(vq, c0, npad, Vs);
+        if (c0 == 0) norm_store_rows(qq, 0, kQTile, Qs);
+    }
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
@@ -145,6 +150,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
         qa[kk][1] = *reinterpret_cast<const uint32_t*>(p1);
         qa[kk][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
         qa[kk][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
+    }
+
+    // per-channel output scale of this thread's 16 head channels: requested now, consumed in the epilogue
+    float scv[16];
+    {
+        const float* sc = scale_v ? scale_v + (size_t)(blockIdx.z / lay.scale_div) * C + head * kD : nullptr;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            scv[2 * n] = sc ? __ldg(sc + n * 8 + 2 * t) : 1.f;
+            scv[2 * n + 1] = sc ? __ldg(sc + n * 8 + 2 * t + 1) : 1.f;
+        }
     }
 
     const float sl2 = 0.125f * 1.44269504089f;   // 1/sqrt(64) * log2(e)
@@ -227,14 +243,13 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
         if (q >= N) continue;
         const size_t o_off = (size_t)outer * lay.o_outer + (size_t)inner * lay.o_inner + (size_t)q * lay.o_tok + head * kD;
         __nv_bfloat16* op = out + o_off;
-        const float* sc = scale_v ? scale_v + (size_t)(blockIdx.z / lay.scale_div) * C + head * kD : nullptr;
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
             const int d = n * 8 + 2 * t;
             const float a0 = o[n][2 * r + 0] * inv_l[r], a1 = o[n][2 * r + 1] * inv_l[r];
             if (raw_out) *reinterpret_cast<uint32_t*>(raw_out + o_off + d) = pack_bf16x2(a0, a1);   // train mode
-            const float y0 = a0 * (sc ? __ldg(sc + d) : 1.f);
-            const float y1 = a1 * (sc ? __ldg(sc + d + 1) : 1.f);
+            const float y0 = a0 * scv[2 * n];
+            const float y1 = a1 * scv[2 * n + 1];
             if (out) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_f(y0), mp_silu_f(y1));
         }
     }

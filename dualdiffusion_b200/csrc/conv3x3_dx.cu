@@ -232,18 +232,17 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                ptx::smem_u32(a_full), ptx::smem_u32(a_empty), ptx::smem_u32(&b_full), ptx::smem_u32(b_empty), ptx::smem_u32(acc_full),
                ptx::smem_u32(acc_empty), ptx::smem_u32(res_full), ptx::smem_u32(res_empty), u_begin, u_end);
 #endif
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tmA);
-        ptx::prefetch_tensormap(&tmB);
-        ptx::prefetch_tensormap(&tmO);
-        if (p.epi2 != DD_EPI2_NONE) ptx::prefetch_tensormap(&tmO2);
-        if (has_res) ptx::prefetch_tensormap(&tmR);
-        for (int s = 0; s < p.a_stages; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
-        ptx::mbar_init(&b_full, 1);
-        for (int w = 0; w < kMmaWarps; ++w) ptx::mbar_init(&b_empty[w], 1);
+    if (warp == 0) {            // spread over the lanes: the set-up is on every launch's critical path
         const uint32_t group_warps = (uint32_t)(kEpiWarps / p.ngroups);
-        for (int a = 0; a < p.nbuf; ++a) { ptx::mbar_init(&acc_full[a], 1); ptx::mbar_init(&acc_empty[a], group_warps); }
-        for (int r = 0; r < p.res_stages; ++r) { ptx::mbar_init(&res_full[r], 1); ptx::mbar_init(&res_empty[r], group_warps); }
+        if (lane == 0) { ptx::prefetch_tensormap(&tmA); ptx::mbar_init(&b_full, 1); }
+        if (lane == 1) ptx::prefetch_tensormap(&tmB);
+        if (lane == 2) ptx::prefetch_tensormap(&tmO);
+        if (lane == 3 && p.epi2 != DD_EPI2_NONE) ptx::prefetch_tensormap(&tmO2);
+        if (lane == 4 && has_res) ptx::prefetch_tensormap(&tmR);
+        if (lane < kMmaWarps) ptx::mbar_init(&b_empty[lane], 1);
+        if (lane >= 8 && lane - 8 < p.a_stages) { ptx::mbar_init(&a_full[lane - 8], 1); ptx::mbar_init(&a_empty[lane - 8], 1); }
+        if (lane >= 16 && lane - 16 < p.nbuf) { ptx::mbar_init(&acc_full[lane - 16], 1); ptx::mbar_init(&acc_empty[lane - 16], group_warps); }
+        if (lane >= 24 && lane - 24 < p.res_stages) { ptx::mbar_init(&res_full[lane - 24], 1); ptx::mbar_init(&res_empty[lane - 24], group_warps); }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
     }

@@ -446,16 +446,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tmA);
-        ptx::prefetch_tensormap(&tmB);
-        for (int s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
+    if (warp == 0) {            // one barrier pair per lane: the set-up is on every launch's critical path
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&tmA);
+            ptx::prefetch_tensormap(&tmB);
         }
-        for (int a = 0; a < p.nbuf; ++a) {
-            ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 4);       // the four warps (lane quadrants) of one epilogue group
+        if (lane < p.stages) {
+            ptx::mbar_init(&full_bar[lane], 1);
+            ptx::mbar_init(&empty_bar[lane], 1);
+        }
+        if (lane < p.nbuf) {
+            ptx::mbar_init(&tmem_full_bar[lane], 1);
+            ptx::mbar_init(&tmem_empty_bar[lane], 4);    // the four warps (lane quadrants) of one epilogue group
         }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
@@ -895,18 +897,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int t_begin = (int)((long)blockIdx.x * p.num_tiles / gridDim.x);
     const int t_end = (int)((long)(blockIdx.x + 1) * p.num_tiles / gridDim.x);
 
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tmA);
-        ptx::prefetch_tensormap(&tmB);
-        for (int s = 0; s < p.a_stages; ++s) {
-            ptx::mbar_init(&a_full[s], 1);
-            ptx::mbar_init(&a_empty[s], 1);
+    if (warp == 0) {            // one barrier pair per lane: the set-up is on every launch's critical path
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&tmA);
+            ptx::prefetch_tensormap(&tmB);
+            ptx::mbar_init(&b_full, 1);
+            ptx::mbar_init(&b_empty, 1);
         }
-        ptx::mbar_init(&b_full, 1);
-        ptx::mbar_init(&b_empty, 1);
-        for (int a = 0; a < p.nbuf; ++a) {
-            ptx::mbar_init(&tmem_full_bar[a], 1);
-            ptx::mbar_init(&tmem_empty_bar[a], 4);       // the four warps (lane quadrants) of one epilogue group
+        if (lane < p.a_stages) {
+            ptx::mbar_init(&a_full[lane], 1);
+            ptx::mbar_init(&a_empty[lane], 1);
+        }
+        if (lane >= 16 && lane - 16 < p.nbuf) {
+            ptx::mbar_init(&tmem_full_bar[lane - 16], 1);
+            ptx::mbar_init(&tmem_empty_bar[lane - 16], 4);       // the four warps (lane quadrants) of one epilogue group
         }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();

@@ -76,6 +76,26 @@ def indep_conv1():
         ops.mpconv(x, w1, 1)
 
 
+qk86 = torch.randn(2, 2, 43, 2560, generator=g).to(dev, torch.bfloat16)
+v86 = torch.randn(2, 2, 43, 1280, generator=g).to(dev, torch.bfloat16)
+qk344 = torch.randn(2, 4, 86, 2048, generator=g).to(dev, torch.bfloat16)
+v344 = torch.randn(2, 4, 86, 1024, generator=g).to(dev, torch.bfloat16)
+sc20 = torch.ones(2, 1280, device=dev)
+sc16 = torch.ones(2, 1024, device=dev)
+
+
+def chain_attn86():
+    for _ in range(N):
+        ops.attention(qk86, v86, sc20, 20, 64)
+
+
+def chain_attn344():
+    for _ in range(N):
+        ops.attention(qk344, v344, sc16, 16, 64)
+
+
+timed(chain_attn86, "attention 86 tokens x 20 heads x batch 2")
+timed(chain_attn344, "attention 344 tokens x 16 heads x batch 2")
 timed(chain_pixnorm, "pixnorm_silu 172 x 1280, dependent chain")
 timed(chain_avgpool_like, "axpby 172 x 1280, dependent chain")
 timed(chain_conv1, "1x1 conv 1280->1280 at 2x2x43, dependent chain")
