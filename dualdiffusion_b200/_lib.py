@@ -190,9 +190,14 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path):
+    # build() is a no-op when the stamp matches the sources (a stale library after a csrc/ or header edit would
+    # otherwise load silently); without nvcc a library that is already there is used as it is
+    try:
         path = _build.build()
+    except RuntimeError:
+        if not os.path.exists(_build.LIB_PATH):
+            raise
+        path = _build.LIB_PATH
     lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: fail loudly

@@ -44,20 +44,36 @@ def _fingerprint() -> str:
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".inl")))
     files.append(os.path.join(ROOT, "include", "dualdiffusion_b200.h"))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())      # relative: the same tree fingerprints equally wherever it is copied
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
+def _up_to_date(fp: str) -> bool:
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH)):
+        return False
+    with open(STAMP_PATH) as fh:
+        return fh.read().strip() == fp
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile if the sources changed since the library was built.  Safe under torchrun: one process compiles (file lock),
+    the others wait and find the stamp; the library appears atomically."""
+    import fcntl
     os.makedirs(LIB_DIR, exist_ok=True)
     fp = _fingerprint()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP_PATH):
-        with open(STAMP_PATH) as fh:
-            if fh.read().strip() == fp:
-                return LIB_PATH
+    if not force and _up_to_date(fp):
+        return LIB_PATH
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and _up_to_date(fp):          # another process built it while we waited
+            return LIB_PATH
+        return _build_locked(fp, verbose)
+
+
+def _build_locked(fp: str, verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
@@ -78,8 +94,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see dualdiffusion_b200/lib/build.log")
-    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB_PATH, *objs, "-Xlinker", "--exclude-libs", "-Xlinker", "ALL"]
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", tmp, *objs, "-Xlinker", "--exclude-libs", "-Xlinker", "ALL"]
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB_PATH)
     with open(STAMP_PATH, "w") as fh:
         fh.write(fp)
     return LIB_PATH

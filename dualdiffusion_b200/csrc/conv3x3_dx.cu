@@ -285,12 +285,11 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int s = 0; s < p.nsub; ++s) {
                         const int co0 = panel_co0(p, wk.panel, s);
                         uint8_t* dst = smem + (size_t)s * p.b_sub_bytes;
-                        for (int kc = 0; kc < p.kchunks; ++kc) {
-                            int col = kc * 64;
-                            for (int tap = 0; tap < 9; ++tap, dst += p.b_dx_bytes, col += p.cin_g) {   // tap = dy * 3 + t: block (kc, dy), rows [t][co]
-                                if (ptx::elect_one()) ptx::tma_load_2d(dst, &tmB, &b_full, col, co0);
-                                __syncwarp();
-                            }
+                        // one box per 64-channel chunk: (ci, co, tap) = (64, n_co, 9) lands as [tap][co][ci], i.e. the three
+                        // (kc, dy) blocks with rows [t][co] (tap = dy * 3 + t)
+                        for (int kc = 0; kc < p.kchunks; ++kc, dst += 9u * p.b_dx_bytes) {
+                            if (ptx::elect_one()) ptx::tma_load_3d(dst, &tmB, &b_full, kc * 64, co0, 0);
+                            __syncwarp();
                         }
                     }
                 }
@@ -643,12 +642,12 @@ int dd_launch_conv3x3_dx(const DxConvArgs& a, cudaStream_t stream) {
     DD_REQUIRE(encode_nhwc(encode, &tmA, a.x, a.B, a.H, a.W, a.Cin, 64, kTileW, kTileH + 2, CU_TENSOR_MAP_SWIZZLE_128B),
                "dd_mpconv_forward: activation tensor map encode failed");
     {
-        const cuuint64_t ktot = (cuuint64_t)9 * cin_g;
-        cuuint64_t dims[2] = {ktot, (cuuint64_t)a.Cout};
-        cuuint64_t strides[1] = {ktot * 2};
-        cuuint32_t box[2] = {p.b_row_bytes / 2, (cuuint32_t)p.n_co};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a.w), dims, strides, box, estr,
+        // weights [Cout][9][cin_g] viewed as (ci, co, tap): a box (64 | 32 channels, n_co, 9 taps) is one chunk of a panel
+        cuuint64_t dims[3] = {(cuuint64_t)cin_g, (cuuint64_t)a.Cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)9 * cin_g * 2, (cuuint64_t)cin_g * 2};
+        cuuint32_t box[3] = {p.b_row_bytes / 2, (cuuint32_t)p.n_co, 9};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a.w), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE,
                             p.b_row_bytes == 128u ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

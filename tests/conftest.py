@@ -25,7 +25,7 @@ def pytest_collection_modifyitems(config, items):
 
 
 def load_golden(name):
-    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=True)      # goldens are plain tensor / scalar containers: no pickled code
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
