@@ -245,7 +245,30 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane >= 24 && lane - 24 < p.res_stages) { ptx::mbar_init(&res_full[lane - 24], 1); ptx::mbar_init(&res_empty[lane - 24], group_warps); }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
+        __syncwarp();
     }
+    // Every role walks the same unit sequence with incremental counters: no integer division and no tile decode in the
+    // per-tile control path (the issuing warp's bookkeeping between two tiles must stay shorter than the work queued in
+    // the tensor pipe, or the pipe idles -- profiles/r02_trace_dx_v1.log).
+    Walker wk;
+    wk.init(p, u_begin);
+    // The first weight panel needs nothing but its own barrier: it is requested before the CTA-wide set-up (TMEM
+    // allocation, __syncthreads) completes, so that it streams in behind the rest of the prologue.
+    auto issue_panel = [&](int panel) {
+        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.nsub * p.b_sub_bytes);
+        __syncwarp();
+        for (int s = 0; s < p.nsub; ++s) {
+            const int co0 = panel_co0(p, panel, s);
+            uint8_t* dst = smem + (size_t)s * p.b_sub_bytes;
+            // one box per 64-channel chunk: (ci, co, tap) = (64, n_co, 9) lands as [tap][co][ci], i.e. the three
+            // (kc, dy) blocks with rows [t][co] (tap = dy * 3 + t)
+            for (int kc = 0; kc < p.kchunks; ++kc, dst += 9u * p.b_dx_bytes) {
+                if (ptx::elect_one()) ptx::tma_load_3d(dst, &tmB, &b_full, kc * 64, co0, 0);
+                __syncwarp();
+            }
+        }
+    };
+    if (warp == 0 && u_begin < u_end) issue_panel(wk.panel);
     if (warp == 1) {
         ptx::tmem_alloc(&tmem_base_slot, 512);
         ptx::tmem_relinquish();
@@ -256,12 +279,6 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t tmem_base = tmem_base_slot;
     ptx::grid_launch_dependents();
     if (threadIdx.x == 0) trace_stamp<TRACE>(p, 1, 63);          // set-up done (barriers, TMEM)
-
-    // Every role walks the same unit sequence with incremental counters: no integer division and no tile decode in the
-    // per-tile control path (the issuing warp's bookkeeping between two tiles must stay shorter than the work queued in
-    // the tensor pipe, or the pipe idles -- profiles/r02_trace_dx_v1.log).
-    Walker wk;
-    wk.init(p, u_begin);
 
     if (warp == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -275,23 +292,10 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int turn = 0;
             bool new_panel = true, first = true;
             for (int u = u_begin; u < u_end; ++u) {
-                if (new_panel) {
-                    if (!first) {                                                              // old panel fully consumed
-                        for (int w = 0; w < p.mma_warps; ++w) ptx::mbar_wait(&b_empty[w], b_par);
-                        b_par ^= 1;
-                    }
-                    if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.nsub * p.b_sub_bytes);
-                    __syncwarp();
-                    for (int s = 0; s < p.nsub; ++s) {
-                        const int co0 = panel_co0(p, wk.panel, s);
-                        uint8_t* dst = smem + (size_t)s * p.b_sub_bytes;
-                        // one box per 64-channel chunk: (ci, co, tap) = (64, n_co, 9) lands as [tap][co][ci], i.e. the three
-                        // (kc, dy) blocks with rows [t][co] (tap = dy * 3 + t)
-                        for (int kc = 0; kc < p.kchunks; ++kc, dst += 9u * p.b_dx_bytes) {
-                            if (ptx::elect_one()) ptx::tma_load_3d(dst, &tmB, &b_full, kc * 64, co0, 0);
-                            __syncwarp();
-                        }
-                    }
+                if (new_panel && !first) {                    // (the first panel was requested during the set-up)
+                    for (int w = 0; w < p.mma_warps; ++w) ptx::mbar_wait(&b_empty[w], b_par);      // old panel fully consumed
+                    b_par ^= 1;
+                    issue_panel(wk.panel);
                 }
                 if (first) { ptx::grid_dependency_wait(); first = false; }      // weights do not depend on the previous kernel
                 const int ci0 = panel_ci0(p, wk.panel);

@@ -461,6 +461,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
+        __syncwarp();
+    }
+    // Weights never depend on the preceding kernel and need nothing but their own barriers: the B boxes of the first
+    // pipeline fill are requested here, before the CTA-wide set-up (TMEM allocation, __syncthreads) completes and before
+    // griddepcontrol.wait, so they stream in behind the prologue / while the previous kernel drains.
+    struct KIter {
+        int tap, kc, dy, dx;
+        __device__ __forceinline__ void reset(const ConvParams& q) { tap = 0; kc = 0; dy = -(q.kh / 2); dx = -(q.kw / 2); }
+        __device__ __forceinline__ void next(const ConvParams& q) {
+            if (++kc == q.kchunks) {
+                kc = 0; ++tap;
+                if (++dx > q.kw / 2) { dx = -(q.kw / 2); ++dy; }
+            }
+        }
+    };
+    int prefetched = 0;                          // stages of the first tile whose B boxes are already in flight
+    if (warp == 0) {
+        const int tile = blockIdx.x;
+        if (tile < p.num_tiles) {
+            const TileCoord t = decode_tile(p, tile);
+            const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
+            KIter ki;
+            ki.reset(p);
+            for (int it0 = 0; it0 < p.k_iters && prefetched < p.stages; it0 += p.sub, ++prefetched) {
+                const int cnt = min(p.sub, p.k_iters - it0);
+                if (ptx::elect_one())
+                    ptx::mbar_arrive_expect_tx(&full_bar[prefetched], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
+                __syncwarp();
+                for (int j = 0; j < cnt; ++j) {
+                    if (ptx::elect_one())
+                        ptx::tma_load_2d(smem + prefetched * stage_bytes + j * pair_bytes + kABufBytes, &tmB,
+                                         &full_bar[prefetched], ki.tap * p.cin_g + ki.kc * KC, b_row);
+                    __syncwarp();
+                    ki.next(p);
+                }
+            }
+        }
     }
     if (warp == 1) {
         ptx::tmem_alloc(&tmem_base_slot, p.tmem_cols);
@@ -478,43 +515,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // the compiler cannot keep the TMA operands in uniform registers: it wraps every UTMALDG in a lane-serialisation
         // loop (R2UR + ELECT + BRA.U.ANY, ~250 cycles per box), which made the producer -- not L2 -- the limiter of the
         // short k-loops of the small levels.  (tap, k-chunk) advance incrementally: no integer division per box.
-        // Weights never depend on the preceding kernel: the B boxes of the first pipeline fill are issued before
-        // griddepcontrol.wait, so under programmatic dependent launch they stream in while the previous kernel
-        // drains; activations (A boxes) are only touched after the wait.
-        struct KIter {
-            int tap, kc, dy, dx;
-            __device__ __forceinline__ void reset(const ConvParams& q) { tap = 0; kc = 0; dy = -(q.kh / 2); dx = -(q.kw / 2); }
-            __device__ __forceinline__ void next(const ConvParams& q) {
-                if (++kc == q.kchunks) {
-                    kc = 0; ++tap;
-                    if (++dx > q.kw / 2) { dx = -(q.kw / 2); ++dy; }
-                }
-            }
-        };
+        // Activations (A boxes) are only touched after griddepcontrol.wait; the first B boxes are already in flight.
         uint32_t stage = 0, phase = 0;
-        int prefetched = 0;                          // stages of the first tile whose B boxes are already in flight
-        {
-            const int tile = blockIdx.x;
-            if (tile < p.num_tiles) {
-                const TileCoord t = decode_tile(p, tile);
-                const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
-                KIter ki;
-                ki.reset(p);
-                for (int it0 = 0; it0 < p.k_iters && prefetched < p.stages; it0 += p.sub, ++prefetched) {
-                    const int cnt = min(p.sub, p.k_iters - it0);
-                    if (ptx::elect_one())
-                        ptx::mbar_arrive_expect_tx(&full_bar[prefetched], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
-                    __syncwarp();
-                    for (int j = 0; j < cnt; ++j) {
-                        if (ptx::elect_one())
-                            ptx::tma_load_2d(smem + prefetched * stage_bytes + j * pair_bytes + kABufBytes, &tmB,
-                                             &full_bar[prefetched], ki.tap * p.cin_g + ki.kc * KC, b_row);
-                        __syncwarp();
-                        ki.next(p);
-                    }
-                }
-            }
-        }
         ptx::grid_dependency_wait();
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
@@ -914,7 +916,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
+        __syncwarp();
     }
+    // one box per 64-channel chunk of the weight panel: (ci, co, tap) = (64, n_tile, 9) lands as [tap][co][ci]
+    auto issue_panel = [&](const HaloTile& t) {
+        if (ptx::elect_one()) ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.kchunks * 9u * p.b_block_bytes);
+        __syncwarp();
+        const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
+        uint8_t* dst = b_smem;
+        for (int kc = 0; kc < p.kchunks; ++kc, dst += 9u * p.b_block_bytes) {
+            if (ptx::elect_one()) ptx::tma_load_3d(dst, &tmB, &b_full, kc * 64, b_row, 0);
+            __syncwarp();
+        }
+    };
+    // the first panel needs nothing but its own barrier: requested before the CTA-wide set-up completes
+    if (warp == 0 && t_begin < t_end) issue_panel(decode_halo_tile(p, t_begin));
     if (warp == 1) {
         ptx::tmem_alloc(&tmem_base_slot, p.tmem_cols);
         ptx::tmem_relinquish();
@@ -937,18 +953,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t tr_local = (uint32_t)(tile - t_begin);
                 const HaloTile t = decode_halo_tile(p, tile);
                 if (t.panel != cur_panel) {
-                    if (cur_panel >= 0) { ptx::mbar_wait(&b_empty, b_par); b_par ^= 1; }   // old panel fully consumed
-                    if (ptx::elect_one())
-                        ptx::mbar_arrive_expect_tx(&b_full, (uint32_t)p.kchunks * 9u * p.b_block_bytes);
-                    __syncwarp();
-                    const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
-                    uint8_t* dst = b_smem;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        int col = kc * 64;
-                        for (int tap = 0; tap < 9; ++tap, col += p.cin_g, dst += p.b_block_bytes) {
-                            if (ptx::elect_one()) ptx::tma_load_2d(dst, &tmB, &b_full, col, b_row);
-                            __syncwarp();
-                        }
+                    if (cur_panel >= 0) {                      // (the first panel was requested during the set-up)
+                        ptx::mbar_wait(&b_empty, b_par);       // old panel fully consumed
+                        b_par ^= 1;
+                        issue_panel(t);
                     }
                     cur_panel = t.panel;
                 }
@@ -1417,12 +1425,13 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
         DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: halo tensor map encode failed (CUresult %d)", (int)r);
     }
     {
-        const cuuint64_t ktot = (cuuint64_t)9 * cin_g;
-        cuuint64_t dims[2] = {ktot, (cuuint64_t)Cout};
-        cuuint64_t strides[1] = {ktot * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)p.n_tile};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_prepped), dims, strides, box,
+        // weights [Cout][9][cin_g] viewed as (ci, co, tap): one box (64 channels, n_tile, 9 taps) is a whole chunk of the
+        // panel, landing as [tap][co][ci] (one TMA instead of nine per chunk)
+        cuuint64_t dims[3] = {(cuuint64_t)cin_g, (cuuint64_t)Cout, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)9 * cin_g * 2, (cuuint64_t)cin_g * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)p.n_tile, 9};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_prepped), dims, strides, box,
                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: weight tensor map encode failed (CUresult %d)", (int)r);
@@ -1466,7 +1475,7 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
 int launch_conv(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
     static const bool no_halo = getenv("DD_DISABLE_HALO") != nullptr;     // tuning experiments only
     if (p.taps == 9 && groups > 1 && p.epi != DD_EPI_HEAD) {
-        // grouped 3x3 layers of the tall levels: tap-stacked kernel (conv3x3_dx.cu); -1 = shape not handled there
+        // grouped 3x3 layers: tap-stacked kernel (conv3x3_dx.cu); -1 = shape not handled there
         DxConvArgs a{};
         a.x = x; a.w = w_prepped; a.out = p.out;
         a.B = p.B; a.H = p.H; a.W = p.W; a.Cin = p.Cin; a.Cout = p.Cout; a.groups = groups;
