@@ -75,55 +75,44 @@ __global__ void weight_prep_kernel(const void* __restrict__ w, void* __restrict_
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxVecPerLane = 10;    // C <= 10*32*8 = 2560
 
-// One warp per pixel, PPW pixels per warp iteration (grid-stride), VPL 16-byte vectors per lane and pixel: every load of
-// the iteration is in flight before the first reduction (C <= 512: 4 pixels x 2 vectors; wider rows: 1 pixel x 10).
-template <int PPW, int VPL>
 __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restrict__ x_out, uint4* __restrict__ s_out,
                                     long npix, int C) {
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= npix) return;
     const int nvec = C >> 3;
-    const float rs = rsqrtf((float)C);
-    for (long p0 = ((long)blockIdx.x * wpb + (threadIdx.x >> 5)) * PPW; p0 < npix; p0 += (long)gridDim.x * wpb * PPW) {
-        uint4 reg[PPW][VPL];
+    const uint4* src = t + pix * nvec;
+    uint4 reg[kMaxVecPerLane];
+    float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < PPW; ++i)
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+        const int v = lane + k * 32;
+        if (v < nvec) {
+            reg[k] = __ldg(src + v);
+            const uint32_t u[4] = {reg[k].x, reg[k].y, reg[k].z, reg[k].w};
 #pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                const int v = lane + k * 32;
-                reg[i][k] = make_uint4(0u, 0u, 0u, 0u);
-                if (v < nvec && p0 + i < npix) reg[i][k] = __ldg(t + (p0 + i) * nvec + v);
+            for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(u[j]); ss += f.x * f.x + f.y * f.y; }
+        }
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)C));
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+        const int v = lane + k * 32;
+        if (v < nvec) {
+            const uint32_t u[4] = {reg[k].x, reg[k].y, reg[k].z, reg[k].w};
+            uint32_t xo[4], so[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_bf16x2(u[j]);
+                f.x *= inv; f.y *= inv;
+                xo[j] = pack_bf16x2(f.x, f.y);
+                so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
             }
-#pragma unroll
-        for (int i = 0; i < PPW; ++i) {
-            if (p0 + i >= npix) break;                 // warp-uniform
-            float ss = 0.f;
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                const uint32_t u[4] = {reg[i][k].x, reg[i][k].y, reg[i][k].z, reg[i][k].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(u[j]); ss += f.x * f.x + f.y * f.y; }
-            }
-            ss = warp_sum(ss);
-            const float inv = 1.f / (kNormEps + sqrtf(ss) * rs);
-#pragma unroll
-            for (int k = 0; k < VPL; ++k) {
-                const int v = lane + k * 32;
-                if (v < nvec) {
-                    const uint32_t u[4] = {reg[i][k].x, reg[i][k].y, reg[i][k].z, reg[i][k].w};
-                    uint32_t xo[4], so[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float2 f = unpack_bf16x2(u[j]);
-                        f.x *= inv; f.y *= inv;
-                        xo[j] = pack_bf16x2(f.x, f.y);
-                        so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
-                    }
-                    x_out[(p0 + i) * nvec + v] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
-                    s_out[(p0 + i) * nvec + v] = make_uint4(so[0], so[1], so[2], so[3]);
-                }
-            }
+            x_out[pix * nvec + v] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+            s_out[pix * nvec + v] = make_uint4(so[0], so[1], so[2], so[3]);
         }
     }
 }
@@ -131,52 +120,40 @@ __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restri
 // ------------------------------------------------------------------------------------------
 // decoder input: (optional nearest x2 upsample of a) ++ (optional skip b), scaled, plus mp_silu
 // ------------------------------------------------------------------------------------------
-constexpr int kCatVecPerLane = 12;    // Ca + Cb <= 12*32*8 = 3072
-
 __global__ void cat_silu_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb, float wa,
                                 float wb, int up, uint4* __restrict__ xcat, uint4* __restrict__ s, int B, int H, int W) {
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
-    // One warp per output pixel (grid-stride): the pixel decode (divisions) is paid once per pixel, not once per 16-byte
-    // vector, and a warp's accesses are contiguous 512 B runs of the pixel's channel vector.
     const int vt = va + vb;
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int npix = B * H * W;
-    for (int pix = blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += gridDim.x * wpb) {
-        int apix = pix;
-        if (up) {
-            const int w = pix % W, r = pix / W;
-            const int h = r % H, bb = r / H;
-            apix = (bb * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
-        }
-        const uint4* ap = a + (size_t)apix * va;
-        const uint4* bp = b ? b + (size_t)pix * vb - va : nullptr;          // indexed with v >= va
-        const size_t o = (size_t)pix * vt;
-        // all loads of the pixel in flight before the first is consumed (C <= 3072: 12 vectors per lane)
-        uint4 reg[kCatVecPerLane];
-#pragma unroll
-        for (int k = 0; k < kCatVecPerLane; ++k) {
-            const int v = lane + k * 32;
-            if (v < vt) reg[k] = v < va ? __ldg(ap + v) : __ldg(bp + v);
-        }
-#pragma unroll
-        for (int k = 0; k < kCatVecPerLane; ++k) {
-            const int v = lane + k * 32;
-            if (v < vt) {
-                const float sc = v < va ? wa : wb;
-                const uint32_t u[4] = {reg[k].x, reg[k].y, reg[k].z, reg[k].w};
-                uint32_t xo[4], so[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float2 f = unpack_bf16x2(u[j]);
-                    f.x *= sc; f.y *= sc;
-                    xo[j] = pack_bf16x2(f.x, f.y);
-                    so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
-                }
-                if (xcat) xcat[o + v] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
-                s[o + v] = make_uint4(so[0], so[1], so[2], so[3]);
+    const long total = (long)B * H * W * vt;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx % vt);
+        const long pix = idx / vt;
+        uint4 q;
+        float sc;
+        if (v < va) {
+            long apix = pix;
+            if (up) {
+                const int w = (int)(pix % W), h = (int)((pix / W) % H), bb = (int)(pix / ((long)W * H));
+                apix = ((long)bb * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
             }
+            q = __ldg(a + apix * va + v);
+            sc = wa;
+        } else {
+            q = __ldg(b + pix * vb + (v - va));
+            sc = wb;
         }
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+        uint32_t xo[4], so[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf16x2(u[j]);
+            f.x *= sc; f.y *= sc;
+            xo[j] = pack_bf16x2(f.x, f.y);
+            so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
+        }
+        if (xcat) xcat[idx] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
+        s[idx] = make_uint4(so[0], so[1], so[2], so[3]);
     }
 }
 
@@ -489,19 +466,10 @@ extern "C" int dd_pixnorm_silu(const void* t, void* x_out, void* s_out, long npi
     DD_REQUIRE(t && x_out && s_out, "dd_pixnorm_silu: null pointer");
     DD_REQUIRE(C % 8 == 0 && C <= kMaxVecPerLane * 256, "dd_pixnorm_silu: C=%d unsupported", C);
     if (npix == 0) return 0;
-    // small images: 2 warps per CTA so that the pixels spread over more SMs (the kernel is a latency chain there)
-    const int warps = npix >= 4096 ? 8 : 2;
-    if (C <= 512) {
-        const long blocks = (npix + warps * 4 - 1) / (warps * 4);
-        DD_CHECK_CUDA(dd_launch_pdl(pixnorm_silu_kernel<4, 2>, dim3((unsigned)std::min<long>(blocks, dd_num_sms() * 16l)),
-                                    dim3(warps * 32), 0, stream, static_cast<const uint4*>(t), static_cast<uint4*>(x_out),
-                                    static_cast<uint4*>(s_out), npix, C));
-    } else {
-        const long blocks = (npix + warps - 1) / warps;
-        DD_CHECK_CUDA(dd_launch_pdl(pixnorm_silu_kernel<1, kMaxVecPerLane>, dim3((unsigned)std::min<long>(blocks, dd_num_sms() * 16l)),
-                                    dim3(warps * 32), 0, stream, static_cast<const uint4*>(t), static_cast<uint4*>(x_out),
-                                    static_cast<uint4*>(s_out), npix, C));
-    }
+    const int warps = 8;
+    DD_CHECK_CUDA(dd_launch_pdl(pixnorm_silu_kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), 0, stream,
+                                static_cast<const uint4*>(t), static_cast<uint4*>(x_out), static_cast<uint4*>(s_out), npix,
+                                C));
     return 0;
 }
 
@@ -511,11 +479,9 @@ extern "C" int dd_cat_silu(const void* a, int Ca, const void* b, int Cb, float w
     DD_REQUIRE(a && s_out && Ca > 0 && Ca % 8 == 0 && Cb % 8 == 0, "dd_cat_silu: bad arguments");
     DD_REQUIRE(Cb == 0 || b, "dd_cat_silu: skip pointer missing");
     DD_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "dd_cat_silu: upsample needs even output size");
-    const long npix = (long)B * H * W;
-    if (npix == 0) return 0;
-    DD_REQUIRE(npix * ((Ca + Cb) / 8) < (1l << 31), "dd_cat_silu: tensor too large");
-    DD_REQUIRE(Ca + Cb <= kCatVecPerLane * 256, "dd_cat_silu: %d channels unsupported (<= %d)", Ca + Cb, kCatVecPerLane * 256);
-    DD_CHECK_CUDA(dd_launch_pdl(cat_silu_kernel, dim3(grid_for(npix * 32, 256)), dim3(256), 0, stream,
+    const long total = (long)B * H * W * ((Ca + Cb) / 8);
+    if (total == 0) return 0;
+    DD_CHECK_CUDA(dd_launch_pdl(cat_silu_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream,
                                 static_cast<const uint4*>(a), Ca / 8, static_cast<const uint4*>(b), Cb / 8, wa, wb,
                                 upsample, static_cast<uint4*>(xcat_out), static_cast<uint4*>(s_out), B, H, W));
     return 0;
