@@ -754,7 +754,7 @@ def run_ours(args) -> None:
             torch.cuda.synchronize()
             rec, ops.timing = ops.timing, None
             net.use_cuda_graphs = True
-            is_dx = lambda d: d[5] == 3 and d[6] > 1 and d[1] >= 8          # grouped 3x3, >= 8 image rows: conv3x3_dx_kernel
+            is_dx = lambda d: d[5] == 3 and d[6] > 1                        # every grouped 3x3 layer runs on conv3x3_dx_kernel
             eager = [(f, a.elapsed_time(b) * 1e-3, d) for f, a, b, d in rec]
             allc = [(f, t) for f, t, d in eager]
             fl_all, tt_all = sum(f for f, _ in allc), sum(t for _, t in allc)
@@ -814,16 +814,17 @@ def run_ours(args) -> None:
                 per_layer.append({"shape": list(d), "launches_per_unet_call": cnt, "us": t * 1e6, "tflops": f / t / 1e12})
             torch.cuda.empty_cache()
             tt_dx_eager = sum(t for f, t, d in eager if is_dx(d))
-            roof = {"bound": "tensor", "kernel": "conv3x3_dx_kernel (tcgen05 tap-stacked implicit-GEMM MPConv, 3x3 grouped, levels 0-2)",
+            roof = {"bound": "tensor", "kernel": "conv3x3_dx_kernel (tcgen05 tap-stacked implicit-GEMM MPConv, every grouped 3x3 layer of the UNet, levels 0-4)",
                     "achieved": fl / tt / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": fl / tt / 1e12 / pk["tflops"],
                     "how": "per distinct layer: CUDA events around replays of a CUDA graph of that layer's launches cycling "
                            "through >= 320 MB of input / output buffer sets (L2-cold inputs); weighted by launches per UNet call",
                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from the committed
                     # `ncu --set full` capture: no DRAM re-reads of the activations
-                    "traffic": 47.25e6, "traffic_source": "profiles/r02_ncu_dx_l0res1_first_version_summary.csv (one launch of the "
-                                                          "2x32x688 512->256 layer: 45.44 MB read + 1.81 MB written back inside "
-                                                          "the capture window; algorithmic 45.1 MB in + 22.5 MB out, the "
-                                                          "output stays in L2)",
+                    "traffic": 75.76e6, "traffic_source": "profiles/r02_ncu_dx_l0_summary.csv (ncu --set full, second launch: the "
+                                                          "2x32x688 512->256 residual layer, 70.77 MB read + 4.99 MB written "
+                                                          "inside the capture window; algorithmic 45.1 MB in + 22.5 MB residual "
+                                                          "+ 22.5 MB out = 90.2 MB: the output and part of the residual stay in "
+                                                          "the 126 MB L2, no DRAM re-reads)",
                     "launches": n_dx, "avg_launch_us": tt / max(1, n_dx) * 1e6,
                     "flop_per_launch_avg": fl / max(1, n_dx), "peak_source": pk["source"] + " (bf16 sustained)",
                     "share_of_unet_call": tt / (ms * 1e-3 / K / 2),

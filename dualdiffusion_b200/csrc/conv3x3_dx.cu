@@ -419,8 +419,10 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const bool two = p.epi2 != DD_EPI2_NONE;
         const uint32_t rb = (uint32_t)p.n_co * 2u;   // bytes per pixel row of a residual tile
         constexpr uint32_t kSlabRow = kEpiCh * 2;    // staging rows: 32 channels = 64 B (SWIZZLE_64B)
-        const uint32_t slab = ptx::smem_u32(smem) + p.off_slab + (uint32_t)e * p.slab_bytes * (two ? 2u : 1u);
-        const uint32_t slab2 = slab + p.slab_bytes;
+        // one 2 KB staging slab per warp; a second output goes through the same slab once the first one's TMA store has
+        // read it (its 32 channels wait in registers): doubling the slabs cost the kernel two activation stages and with
+        // them the second UMMA-issuing warp
+        const uint32_t slab = ptx::smem_u32(smem) + p.off_slab + (uint32_t)e * p.slab_bytes;
         const int srow = min(max(lane - 1, 0), kOutW - 1);       // staging row of this lane (lanes 0 / 31 are halo)
         const bool out_lane = lane >= 1 && lane <= kOutW;
         const int rrow = quad * kOutW + srow;
@@ -444,6 +446,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ptx::tcgen05_fence_after();
                 if (tracer && lane == 0) trace_stamp<TRACE>(p, 5, item);
                 if (has_res) ptx::mbar_wait(&res_full[my_rs], my_rph);
+                const bool raw_first = p.epi2 == DD_EPI2_RAW;      // pass 1 stages the accumulator itself, pass 2 the activation
                 if (h < p.H) {
                     if (store_pending) {                    // the previous tile's TMA store must be done reading the slab
                         if (lane == 0) bulk_wait_read0();
@@ -460,7 +463,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         ptx::tmem_ld_32x16(taddr + 2 * p.n_co + c0, d2);
                         const int ch = co0 + c0;
                         float4 sc[4];
-                        if (p.epi == DD_EPI_SCALE_SILU) {    // per-channel emb gain: in flight while the TMEM loads complete
+                        if (p.epi == DD_EPI_SCALE_SILU && !raw_first) {    // per-channel emb gain: in flight while the TMEM loads complete
                             const float4* sp = reinterpret_cast<const float4*>(p.scale + (size_t)wk.b * p.Cout + ch);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) sc[i] = __ldg(sp + i);
@@ -476,11 +479,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             v[i] = add2(add2(make_float2(__uint_as_float(d1[2 * i]), __uint_as_float(d1[2 * i + 1])), left), right);
                         }
                         const int lc = c0 >> 3;              // first of this chunk's two 16 B pieces within the staging row
-                        if (p.epi2 == DD_EPI2_RAW && out_lane) {
-                            st_shared_v4(slab2 + swz_off(srow, lc, kSlabRow), pack_bf16x8(v));
-                            st_shared_v4(slab2 + swz_off(srow, lc + 1, kSlabRow), pack_bf16x8(v + 4));
-                        }
-                        if (p.epi == DD_EPI_SCALE_SILU) {
+                        if (p.epi == DD_EPI_SCALE_SILU && !raw_first) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 v[2 * i] = mp_silu2(mul2(v[2 * i], make_float2(sc[i].x, sc[i].y)));
@@ -503,35 +502,14 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             st_shared_v4(slab + swz_off(srow, lc, kSlabRow), pack_bf16x8(v));
                             st_shared_v4(slab + swz_off(srow, lc + 1, kSlabRow), pack_bf16x8(v + 4));
                         }
-                        if (p.epi2 == DD_EPI2_SILU || p.epi2 == DD_EPI2_SCALE) {
-                            if (p.epi2 == DD_EPI2_SILU) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = mp_silu2(v[i]);
-                            } else {
-                                const float4* sp = reinterpret_cast<const float4*>(p.scale2 + (size_t)wk.b * p.Cout + ch);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float4 q = __ldg(sp + i);
-                                    v[2 * i] = mul2(v[2 * i], make_float2(q.x, q.y));
-                                    v[2 * i + 1] = mul2(v[2 * i + 1], make_float2(q.z, q.w));
-                                }
-                            }
-                            if (out_lane) {
-                                st_shared_v4(slab2 + swz_off(srow, lc, kSlabRow), pack_bf16x8(v));
-                                st_shared_v4(slab2 + swz_off(srow, lc + 1, kSlabRow), pack_bf16x8(v + 4));
-                            }
-                        }
                     }
                     if (tracer && lane == 0) trace_stamp<TRACE>(p, 9, item);       // arithmetic + staging done
                     ptx::fence_proxy_async_smem();          // generic-proxy slab writes -> visible to the TMA store
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&tmO, slab, co0, wk.w0, h, wk.b);
-                        if (two) tma_store_4d(&tmO2, slab2, co0, wk.w0, h, wk.b);
+                        tma_store_4d(raw_first ? &tmO2 : &tmO, slab, co0, wk.w0, h, wk.b);
                         bulk_commit();
                     }
-                    if (tracer && lane == 0) trace_stamp<TRACE>(p, 10, item);      // store issued
-                    store_pending = true;
                 }
                 // all TMEM / residual reads of this warp are complete (wait::ld, ld.shared above): hand the buffers back
                 ptx::tcgen05_fence_before();
@@ -539,6 +517,47 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 if (lane == 0) {
                     ptx::mbar_arrive(&acc_empty[my_buf]);
                     if (has_res) ptx::mbar_arrive(&res_empty[my_rs]);
+                }
+                if (h < p.H) {
+                    if (two) {
+                        // Second output, derived from the first as it sits (bf16) in the slab once its TMA store has read it:
+                        // mp_silu(out) | out * scale2 | (raw first) the activation mp_silu(acc * scale).  The reference
+                        // applies these to bf16 tensors too (conv2d / mp_sum outputs under autocast), and neither extra
+                        // staging memory nor registers held across the tile are needed.
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+                        if (out_lane) {
+                            const float* scp = raw_first ? p.scale : p.scale2;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t addr = slab + swz_off(srow, i, kSlabRow);
+                                const uint4 q = ld_shared_v4(addr);
+                                const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+                                float2 x[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) x[j] = unpack_bf16x2(w4[j]);
+                                if (p.epi2 != DD_EPI2_SILU && (p.epi2 == DD_EPI2_SCALE || p.epi == DD_EPI_SCALE_SILU)) {
+                                    const float4* sp = reinterpret_cast<const float4*>(scp + (size_t)wk.b * p.Cout + co0 + 8 * i);
+                                    const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+                                    x[0] = mul2(x[0], make_float2(s0.x, s0.y)); x[1] = mul2(x[1], make_float2(s0.z, s0.w));
+                                    x[2] = mul2(x[2], make_float2(s1.x, s1.y)); x[3] = mul2(x[3], make_float2(s1.z, s1.w));
+                                }
+                                if (p.epi2 == DD_EPI2_SILU || (raw_first && p.epi == DD_EPI_SCALE_SILU)) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) x[j] = mp_silu2(x[j]);
+                                }
+                                st_shared_v4(addr, pack_bf16x8(x));
+                            }
+                        }
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(raw_first ? &tmO : &tmO2, slab, co0, wk.w0, h, wk.b);
+                            bulk_commit();
+                        }
+                    }
+                    if (tracer && lane == 0) trace_stamp<TRACE>(p, 10, item);      // store(s) issued
+                    store_pending = true;
                 }
                 if (tracer && lane == 0) trace_stamp<TRACE>(p, 6, item);
             }
@@ -581,6 +600,7 @@ int dd_launch_conv3x3_dx(const DxConvArgs& a, cudaStream_t stream) {
     static const int min_h = getenv("DD_DX_MIN_H") ? atoi(getenv("DD_DX_MIN_H")) : 2;      // tuning: images shorter than a tile
     if (a.H < min_h || a.W < 16 || a.Cin < 64 || cin_g % 32 != 0 || cout_g % 32 != 0) return -1;
     if (a.epi != DD_EPI_NONE && a.epi != DD_EPI_SCALE_SILU && a.epi != DD_EPI_RESIDUAL) return -1;
+    if (a.epi2 == DD_EPI2_RAW && a.epi == DD_EPI_RESIDUAL) return -1;      // (the raw-first second pass has no residual tile left)
     PFN_encodeTiled encode = reinterpret_cast<PFN_encodeTiled>(dd_tensormap_encode_fn());
     DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");
 
@@ -607,7 +627,7 @@ int dd_launch_conv3x3_dx(const DxConvArgs& a, cudaStream_t stream) {
         if (n_co == 64 && p.nsub == 2 && kMmaWarps > 1) continue;
         const uint32_t b_total = (uint32_t)p.nsub * p.kchunks * 9u * n_co * p.b_row_bytes;
         const uint32_t slab = 32u * kEpiCh * 2u;        // per epilogue warp and output: 32 rows x 32 channels
-        const uint32_t slabs = (uint32_t)kEpiWarps * slab * (two ? 2u : 1u);
+        const uint32_t slabs = (uint32_t)kEpiWarps * slab;            // (a second output shares the slab)
         const uint32_t res_stride = (((uint32_t)(kTileH * kOutW * n_co * 2) + 1023u) / 1024u) * 1024u;
         const int res_stages = has_res ? (n_co == 64 ? 2 : 4) : 0;      // == epilogue groups: a group always meets the same stage
         const uint32_t fixed = b_total + slabs + res_stages * res_stride + 1024u;
@@ -664,7 +684,7 @@ int dd_launch_conv3x3_dx(const DxConvArgs& a, cudaStream_t stream) {
     DD_REQUIRE(encode_nhwc(encode, &tmR, has_res ? a.residual : a.out, a.B, a.H, a.W, a.Cout, p.n_co, kOutW, kTileH, res_swz),
                "dd_mpconv_forward: residual tensor map encode failed");
 
-    const size_t smem_bytes = (size_t)p.off_slab + (size_t)kEpiWarps * p.slab_bytes * (two ? 2 : 1) + 1024;
+    const size_t smem_bytes = (size_t)p.off_slab + (size_t)kEpiWarps * p.slab_bytes + 1024;
     static bool attr_done = false;
     if (!attr_done) {
         DD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_dx_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
