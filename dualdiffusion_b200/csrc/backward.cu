@@ -52,6 +52,8 @@ inline int grid_for_b(long total, int block, int cap_mult = 8) {
 // ------------------------------------------------------------------------------------------
 __global__ void weight_transpose_kernel(const __nv_bfloat16* __restrict__ wp, __nv_bfloat16* __restrict__ wd, int cout_g,
                                         int cin_g, int taps) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ __nv_bfloat16 tile[32][33];
     const int g = blockIdx.z / taps, tap = blockIdx.z - g * taps;
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -69,6 +71,8 @@ __global__ void weight_transpose_kernel(const __nv_bfloat16* __restrict__ wp, __
 }
 
 __global__ void weight_transpose_batched_kernel(const dd_wtrans_desc* __restrict__ descs, int n_descs) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ __nv_bfloat16 tile[32][33];
     int lo = 0, hi = n_descs - 1;
     const int t = blockIdx.x;
@@ -101,6 +105,8 @@ __global__ void weight_transpose_batched_kernel(const dd_wtrans_desc* __restrict
 // normalize_weights() (mp_tools.py:375-378, run by the trainer after every optimizer step, trainer.py:1107-1108) for a
 // whole parameter set in one launch, in place on the fp32 parameters: w <- w / (eps + ||w|| / sqrt(fan_in)) per row.
 __global__ void weight_normalize_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[32];
     int lo = 0, hi = n_descs - 1;
     const int row = blockIdx.x;
@@ -122,6 +128,8 @@ __global__ void weight_normalize_batched_kernel(const dd_wprep_desc* __restrict_
 
 // dd_weight_prep for every parameter of a model in one launch (same arithmetic as weight_prep_kernel, elementwise.cu)
 __global__ void weight_prep_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[32];
     int lo = 0, hi = n_descs - 1;
     const int row = blockIdx.x;
@@ -167,6 +175,8 @@ __global__ void weight_prep_batched_kernel(const dd_wprep_desc* __restrict__ des
 //   forward (mp_tools.py:359-364): w_hat = w / (eps + ||w|| / sqrt(f))  [training], w_eff = w_hat * gain / sqrt(f)
 // ------------------------------------------------------------------------------------------
 __global__ void weight_prep_bwd_kernel(const dd_wbwd_desc* __restrict__ descs, int n_descs) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[32];
     // find the descriptor owning this row (row_begin is an exclusive prefix sum)
     int lo = 0, hi = n_descs - 1;
@@ -250,6 +260,8 @@ __global__ void __launch_bounds__(256)
 silu_scale_bwd_kernel(const uint4* __restrict__ dy, float coef, const uint4* __restrict__ pre,
                       const float* __restrict__ scale, uint4* __restrict__ dpre, float* __restrict__ dscale, long npix,
                       int nvec) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[kRedRows][32][8];
     const int b = blockIdx.z;
     const int v = blockIdx.y * 32 + threadIdx.x;
@@ -295,6 +307,8 @@ constexpr int kMaxVecPerLaneB = 10;    // C <= 2560
 
 __global__ void pixnorm_silu_bwd_kernel(const uint4* __restrict__ g, float ca, const uint4* __restrict__ ds,
                                         const uint4* __restrict__ t0, uint4* __restrict__ dt0, long npix, int C) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int lane = threadIdx.x & 31;
     const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pix >= npix) return;
@@ -358,6 +372,8 @@ __global__ void cat_silu_bwd_kernel(const uint4* __restrict__ d_xc, float c1, co
                                     const uint4* __restrict__ xc, const uint4* __restrict__ a_prev, float clip, float wa,
                                     float wb, int up, uint4* __restrict__ da, uint4* __restrict__ db, int B, int H, int W,
                                     int va, int vb) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int vt = va + vb;
     const int Ha = up ? H >> 1 : H, Wa = up ? W >> 1 : W;
     const long total_a = (long)B * Ha * Wa * va, total_b = (long)B * H * W * vb;
@@ -408,6 +424,8 @@ __global__ void cat_silu_bwd_kernel(const uint4* __restrict__ d_xc, float c1, co
 __global__ void enc_grad_combine_kernel(const uint4* __restrict__ dx0, int down, const uint4* __restrict__ dskip,
                                         const uint4* __restrict__ x_prev, float clip, uint4* __restrict__ out, int B, int H,
                                         int W, int nvec) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const long total = (long)B * H * W * nvec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         float a[8], o[8];
@@ -448,6 +466,8 @@ __global__ void __launch_bounds__(256)
 attn_in_bwd_kernel(const uint4* __restrict__ g3, float ca, const uint4* __restrict__ dxv, const uint4* __restrict__ dxs,
                    const uint4* __restrict__ x2, const float* __restrict__ c_qk, uint4* __restrict__ dx2,
                    float* __restrict__ dc_qk, long npix, int nvec) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[kRedRows][32][8];
     const int b = blockIdx.z;
     const int v = blockIdx.y * 32 + threadIdx.x;
@@ -631,6 +651,8 @@ __global__ void __launch_bounds__(kBwdThreads)
 attention_bwd_q_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                        const __nv_bfloat16* __restrict__ a_raw, const __nv_bfloat16* __restrict__ da,
                        __nv_bfloat16* __restrict__ dqk, float* __restrict__ stats, int N, int heads, int npad) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     extern __shared__ __align__(16) uint8_t smem_bwd[];
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_bwd);        // [npad][kRS]  k^
     __nv_bfloat16* Vs = Ks + (size_t)npad * kRS;                           // [npad][kRS]  v^
@@ -741,6 +763,8 @@ __global__ void __launch_bounds__(kBwdThreads)
 attention_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16* __restrict__ v,
                         const __nv_bfloat16* __restrict__ da, const float* __restrict__ stats,
                         __nv_bfloat16* __restrict__ dqk, __nv_bfloat16* __restrict__ dv_out, int N, int heads, int npad) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     extern __shared__ __align__(16) uint8_t smem_bwd[];
     __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem_bwd);        // [npad][kRS]  q^ (all queries)
     __nv_bfloat16* Gs = Qs + (size_t)npad * kRS;                           // [npad][kRS]  dA
@@ -801,6 +825,8 @@ attention_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat1
 // dW_eff[o][i] = sum_b dc[b][o] emb[b][g*I+i].
 __global__ void emb_affine_bwd_w_kernel(const dd_affine_bwd_desc* __restrict__ descs, const float* __restrict__ emb, int B,
                                         int cemb) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const dd_affine_bwd_desc d = descs[blockIdx.y];
     const int lane = threadIdx.x & 31;
     const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -823,6 +849,8 @@ __global__ void emb_affine_bwd_w_kernel(const dd_affine_bwd_desc* __restrict__ d
 // Stage 2: demb[b][g*I+i] += sum_o dc[b][o] * rowscale[o] * w[o][i]   (thread per input column, rows chunked over blockIdx.z)
 __global__ void emb_affine_bwd_x_kernel(const dd_affine_bwd_desc* __restrict__ descs, float* __restrict__ demb, int B,
                                         int cemb, int row_chunks) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const dd_affine_bwd_desc d = descs[blockIdx.y];
     const int col = blockIdx.x * blockDim.x + threadIdx.x;       // g*I + i
     if (col >= d.groups * d.I) return;
@@ -850,6 +878,8 @@ __global__ void noise_embedding_bwd_kernel(const float* __restrict__ sigma, cons
                                            int normalize, const float* __restrict__ label, float t,
                                            const float* __restrict__ demb, float* __restrict__ dweff,
                                            float* __restrict__ dlabel, int B, int cemb) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     extern __shared__ float four[];        // [B][cnoise]
     for (int k = threadIdx.x; k < B * cnoise; k += blockDim.x) {
         const int b = k / cnoise, i = k - b * cnoise;
@@ -885,6 +915,8 @@ __global__ void noise_embedding_bwd_kernel(const float* __restrict__ sigma, cons
 __global__ void label_embedding_bwd_kernel(const float* __restrict__ emb_in, int Bc, int I, const float* __restrict__ mask,
                                            int Bm, const float* __restrict__ dout, float* __restrict__ dweff_label,
                                            float* __restrict__ dweff_uncond, int cemb) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     extern __shared__ float ehat[];        // [Bc][I]
     __shared__ float red[32];
     for (int b = 0; b < Bc; ++b) {
@@ -921,6 +953,8 @@ __global__ void label_embedding_bwd_kernel(const float* __restrict__ emb_in, int
 __global__ void logvar_bwd_kernel(const float* __restrict__ sigma, const float* __restrict__ freqs,
                                   const float* __restrict__ phases, int n, const float* __restrict__ dout, int count,
                                   float* __restrict__ dw, int accumulate) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     float acc = 0.f;
@@ -934,6 +968,8 @@ __global__ void logvar_bwd_kernel(const float* __restrict__ sigma, const float* 
 __global__ void head_grad_kernel(const float* __restrict__ dD, const float* __restrict__ sigma, float sigma_data,
                                  const float* __restrict__ x_ref, __nv_bfloat16* __restrict__ dF, int B, int Cout, int H,
                                  int W, int Cpad) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const long total = (long)B * H * W * Cpad;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % Cpad);
@@ -967,8 +1003,8 @@ extern "C" int dd_weight_transpose(const void* w_prepped, void* out, int Cout, i
     const int cout_g = Cout / groups;
     DD_REQUIRE((long)groups * taps <= 65535, "dd_weight_transpose: groups*taps exceeds the grid limit");
     const dim3 grid(ceil_div(cin_g, 32), ceil_div(cout_g, 32), groups * taps);
-    weight_transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(w_prepped),
-                                                             static_cast<__nv_bfloat16*>(out), cout_g, cin_g, taps);
+    DD_CHECK_CUDA(dd_launch_pdl(weight_transpose_kernel, dim3(grid), dim3(dim3(32, 8)), 0, stream, static_cast<const __nv_bfloat16*>(w_prepped),
+                                                             static_cast<__nv_bfloat16*>(out), cout_g, cin_g, taps));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -976,7 +1012,7 @@ extern "C" int dd_weight_transpose(const void* w_prepped, void* out, int Cout, i
 extern "C" int dd_weight_normalize_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_normalize_batched: bad arguments");
-    weight_normalize_batched_kernel<<<total_rows, 128, 0, stream>>>(descs_dev, n_descs);
+    DD_CHECK_CUDA(dd_launch_pdl(weight_normalize_batched_kernel, dim3(total_rows), dim3(128), 0, stream, descs_dev, n_descs));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -984,7 +1020,7 @@ extern "C" int dd_weight_normalize_batched(const dd_wprep_desc* descs_dev, int n
 extern "C" int dd_weight_prep_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_prep_batched: bad arguments");
-    weight_prep_batched_kernel<<<total_rows, 128, 0, stream>>>(descs_dev, n_descs);
+    DD_CHECK_CUDA(dd_launch_pdl(weight_prep_batched_kernel, dim3(total_rows), dim3(128), 0, stream, descs_dev, n_descs));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -992,7 +1028,7 @@ extern "C" int dd_weight_prep_batched(const dd_wprep_desc* descs_dev, int n_desc
 extern "C" int dd_weight_transpose_batched(const dd_wtrans_desc* descs_dev, int n_descs, int total_tiles, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && n_descs > 0 && total_tiles > 0, "dd_weight_transpose_batched: bad arguments");
-    weight_transpose_batched_kernel<<<total_tiles, dim3(32, 8), 0, stream>>>(descs_dev, n_descs);
+    DD_CHECK_CUDA(dd_launch_pdl(weight_transpose_batched_kernel, dim3(total_tiles), dim3(dim3(32, 8)), 0, stream, descs_dev, n_descs));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1000,7 +1036,7 @@ extern "C" int dd_weight_transpose_batched(const dd_wtrans_desc* descs_dev, int 
 extern "C" int dd_weight_prep_bwd(const dd_wbwd_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_prep_bwd: bad arguments");
-    weight_prep_bwd_kernel<<<total_rows, 128, 0, stream>>>(descs_dev, n_descs);
+    DD_CHECK_CUDA(dd_launch_pdl(weight_prep_bwd_kernel, dim3(total_rows), dim3(128), 0, stream, descs_dev, n_descs));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1013,9 +1049,9 @@ extern "C" int dd_silu_scale_bwd(const void* dy, float coef, const void* pre, co
     if (npix == 0) return 0;
     const int strip = kRedRows * kSsbPixPerThread;
     const dim3 grid((unsigned)((npix + strip - 1) / strip), ceil_div(C / 8, 32), B);
-    silu_scale_bwd_kernel<<<grid, dim3(32, kRedRows), 0, stream>>>(static_cast<const uint4*>(dy), coef,
+    DD_CHECK_CUDA(dd_launch_pdl(silu_scale_bwd_kernel, dim3(grid), dim3(dim3(32, kRedRows)), 0, stream, static_cast<const uint4*>(dy), coef,
                                                                    static_cast<const uint4*>(pre), scale,
-                                                                   static_cast<uint4*>(dpre), dscale, npix, C / 8);
+                                                                   static_cast<uint4*>(dpre), dscale, npix, C / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1027,9 +1063,9 @@ extern "C" int dd_pixnorm_silu_bwd(const void* g, float ca, const void* ds, cons
     DD_REQUIRE(C % 8 == 0 && C <= kMaxVecPerLaneB * 256, "dd_pixnorm_silu_bwd: C=%d unsupported", C);
     if (npix == 0) return 0;
     const int warps = 4;
-    pixnorm_silu_bwd_kernel<<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, stream>>>(
+    DD_CHECK_CUDA(dd_launch_pdl(pixnorm_silu_bwd_kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), 0, stream, 
         static_cast<const uint4*>(g), ca, static_cast<const uint4*>(ds), static_cast<const uint4*>(t0),
-        static_cast<uint4*>(dt0), npix, C);
+        static_cast<uint4*>(dt0), npix, C));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1043,10 +1079,10 @@ extern "C" int dd_cat_silu_bwd(const void* d_xc, float c1, const void* d_s, cons
     DD_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "dd_cat_silu_bwd: upsample needs even output size");
     const long total = (long)B * (upsample ? H / 2 : H) * (upsample ? W / 2 : W) * (Ca / 8) + (long)B * H * W * (Cb / 8);
     if (total == 0) return 0;
-    cat_silu_bwd_kernel<<<grid_for_b(total, 256), 256, 0, stream>>>(
+    DD_CHECK_CUDA(dd_launch_pdl(cat_silu_bwd_kernel, dim3(grid_for_b(total, 256)), dim3(256), 0, stream, 
         static_cast<const uint4*>(d_xc), c1, static_cast<const uint4*>(d_s), static_cast<const uint4*>(xc),
         static_cast<const uint4*>(a_prev), clip > 0.f ? clip : INFINITY, wa, wb, upsample, static_cast<uint4*>(da),
-        static_cast<uint4*>(db), B, H, W, Ca / 8, Cb / 8);
+        static_cast<uint4*>(db), B, H, W, Ca / 8, Cb / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1058,9 +1094,9 @@ extern "C" int dd_enc_grad_combine(const void* dx0, int down, const void* dskip,
     DD_REQUIRE(!down || (H % 2 == 0 && W % 2 == 0), "dd_enc_grad_combine: downsampled block needs even size");
     const long total = (long)B * H * W * (C / 8);
     if (total == 0) return 0;
-    enc_grad_combine_kernel<<<grid_for_b(total, 256), 256, 0, stream>>>(
+    DD_CHECK_CUDA(dd_launch_pdl(enc_grad_combine_kernel, dim3(grid_for_b(total, 256)), dim3(256), 0, stream, 
         static_cast<const uint4*>(dx0), down, static_cast<const uint4*>(dskip), static_cast<const uint4*>(x_prev),
-        clip > 0.f ? clip : INFINITY, static_cast<uint4*>(out), B, H, W, C / 8);
+        clip > 0.f ? clip : INFINITY, static_cast<uint4*>(out), B, H, W, C / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1073,11 +1109,11 @@ extern "C" int dd_attn_in_bwd(const void* g3, float ca, const void* dxv, const v
     if (npix == 0) return 0;
     const int strip = kRedRows * kAibPixPerThread;
     const dim3 grid((unsigned)((npix + strip - 1) / strip), ceil_div(C / 8, 32), B);
-    attn_in_bwd_kernel<<<grid, dim3(32, kRedRows), 0, stream>>>(static_cast<const uint4*>(g3), ca,
+    DD_CHECK_CUDA(dd_launch_pdl(attn_in_bwd_kernel, dim3(grid), dim3(dim3(32, kRedRows)), 0, stream, static_cast<const uint4*>(g3), ca,
                                                                 static_cast<const uint4*>(dxv),
                                                                 static_cast<const uint4*>(dxs),
                                                                 static_cast<const uint4*>(x2), c_qk,
-                                                                static_cast<uint4*>(dx2), dc_qk, npix, C / 8);
+                                                                static_cast<uint4*>(dx2), dc_qk, npix, C / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1098,17 +1134,17 @@ extern "C" int dd_attention_bwd(const void* qk, const void* v, const void* a_raw
         smem_set = smem;
     }
     const dim3 grid(ceil_div(N, kBT), heads, B);
-    attention_bwd_q_kernel<<<grid, kBwdThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+    DD_CHECK_CUDA(dd_launch_pdl(attention_bwd_q_kernel, dim3(grid), dim3(kBwdThreads), smem, stream, static_cast<const __nv_bfloat16*>(qk),
                                                                 static_cast<const __nv_bfloat16*>(v),
                                                                 static_cast<const __nv_bfloat16*>(a_raw),
                                                                 static_cast<const __nv_bfloat16*>(d_a),
-                                                                static_cast<__nv_bfloat16*>(dqk), stats_ws, N, heads, npad);
+                                                                static_cast<__nv_bfloat16*>(dqk), stats_ws, N, heads, npad));
     DD_CHECK_LAUNCH();
-    attention_bwd_kv_kernel<<<grid, kBwdThreads, smem, stream>>>(static_cast<const __nv_bfloat16*>(qk),
+    DD_CHECK_CUDA(dd_launch_pdl(attention_bwd_kv_kernel, dim3(grid), dim3(kBwdThreads), smem, stream, static_cast<const __nv_bfloat16*>(qk),
                                                                  static_cast<const __nv_bfloat16*>(v),
                                                                  static_cast<const __nv_bfloat16*>(d_a), stats_ws,
                                                                  static_cast<__nv_bfloat16*>(dqk),
-                                                                 static_cast<__nv_bfloat16*>(dv), N, heads, npad);
+                                                                 static_cast<__nv_bfloat16*>(dv), N, heads, npad));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1117,11 +1153,11 @@ extern "C" int dd_emb_affine_bwd(const dd_affine_bwd_desc* descs_dev, int n_desc
                                  const float* emb, float* demb, int B, int cemb, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && emb && demb && n_descs > 0 && max_O > 0 && max_cols > 0, "dd_emb_affine_bwd: bad arguments");
-    emb_affine_bwd_w_kernel<<<dim3(ceil_div(max_O, 8), n_descs), 256, 0, stream>>>(descs_dev, emb, B, cemb);
+    DD_CHECK_CUDA(dd_launch_pdl(emb_affine_bwd_w_kernel, dim3(dim3(ceil_div(max_O, 8), n_descs)), dim3(256), 0, stream, descs_dev, emb, B, cemb));
     DD_CHECK_LAUNCH();
     const int row_chunks = 4;
-    emb_affine_bwd_x_kernel<<<dim3(ceil_div(max_cols, 128), n_descs, row_chunks), 128, 0, stream>>>(descs_dev, demb, B,
-                                                                                                     cemb, row_chunks);
+    DD_CHECK_CUDA(dd_launch_pdl(emb_affine_bwd_x_kernel, dim3(dim3(ceil_div(max_cols, 128), n_descs, row_chunks)), dim3(128), 0, stream, descs_dev, demb, B,
+                                                                                                     cemb, row_chunks));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1135,9 +1171,9 @@ extern "C" int dd_noise_embedding_bwd(const float* sigma, const float* freqs, co
     DD_REQUIRE(cnoise % 32 == 0, "dd_noise_embedding_bwd: cnoise=%d must be a multiple of 32", cnoise);
     const size_t smem = (size_t)B * cnoise * sizeof(float);
     DD_REQUIRE(smem <= 48 * 1024, "dd_noise_embedding_bwd: batch %d x cnoise %d exceeds shared memory", B, cnoise);
-    noise_embedding_bwd_kernel<<<ceil_div(cemb, 8), 256, smem, stream>>>(sigma, freqs, phases, cnoise, w_noise, normalize,
+    DD_CHECK_CUDA(dd_launch_pdl(noise_embedding_bwd_kernel, dim3(ceil_div(cemb, 8)), dim3(256), smem, stream, sigma, freqs, phases, cnoise, w_noise, normalize,
                                                                         label_emb, label_balance, demb, dweff, dlabel, B,
-                                                                        cemb);
+                                                                        cemb));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1149,8 +1185,8 @@ extern "C" int dd_label_embedding_bwd(const float* emb_in, int Bc, int I, const 
     DD_REQUIRE(Bc == 1 || Bc == Bm, "dd_label_embedding_bwd: embedding batch %d does not broadcast to mask batch %d", Bc, Bm);
     const size_t smem = (size_t)Bc * I * sizeof(float);
     DD_REQUIRE(smem <= 48 * 1024, "dd_label_embedding_bwd: batch %d x dim %d exceeds shared memory", Bc, I);
-    label_embedding_bwd_kernel<<<ceil_div(cemb, 8), 256, smem, stream>>>(emb_in, Bc, I, mask, Bm, dout, dweff_label,
-                                                                        dweff_uncond, cemb);
+    DD_CHECK_CUDA(dd_launch_pdl(label_embedding_bwd_kernel, dim3(ceil_div(cemb, 8)), dim3(256), smem, stream, emb_in, Bc, I, mask, Bm, dout, dweff_label,
+                                                                        dweff_uncond, cemb));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1160,7 +1196,7 @@ extern "C" int dd_sigma_logvar_bwd(const float* sigma, int count, const float* f
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(sigma && freqs && phases && dout && dw, "dd_sigma_logvar_bwd: null pointer");
     if (n == 0) return 0;
-    logvar_bwd_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(sigma, freqs, phases, n, dout, count, dw, accumulate);
+    DD_CHECK_CUDA(dd_launch_pdl(logvar_bwd_kernel, dim3(ceil_div(n, 128)), dim3(128), 0, stream, sigma, freqs, phases, n, dout, count, dw, accumulate));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -1171,8 +1207,8 @@ extern "C" int dd_head_grad(const float* dD, const float* sigma, float sigma_dat
     DD_REQUIRE(dD && sigma && dF && Cpad >= Cout && Cpad % 8 == 0, "dd_head_grad: bad arguments");
     const long total = (long)B * H * W * Cpad;
     if (total == 0) return 0;
-    head_grad_kernel<<<grid_for_b(total, 256), 256, 0, stream>>>(dD, sigma, sigma_data, x_ref,
-                                                                 static_cast<__nv_bfloat16*>(dF), B, Cout, H, W, Cpad);
+    DD_CHECK_CUDA(dd_launch_pdl(head_grad_kernel, dim3(grid_for_b(total, 256)), dim3(256), 0, stream, dD, sigma, sigma_data, x_ref,
+                                                                 static_cast<__nv_bfloat16*>(dF), B, Cout, H, W, Cpad));
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -69,6 +69,8 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
                   const __grid_constant__ WgradParams p) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kWgStages];
     __shared__ __align__(8) uint64_t empty_bar[kWgStages];
@@ -367,7 +369,7 @@ extern "C" int dd_mpconv_wgrad(const void* x, const void* dy, float* dw, int B, 
                         "stages %d stage_bytes %u grid %d red %d\n",
                 B, H, W, Cin, Cout, ksize, groups, p.halo, p.ht, p.pix_tiles, p.ksteps, p.m_tiles, p.J, p.nch, p.splits,
                 p.stages, p.stage_bytes, grid, p.use_red);
-    conv_wgrad_kernel<<<grid, kWgThreads, smem_bytes, stream>>>(tmY, tmX, p);
+    DD_CHECK_CUDA(dd_launch_pdl(conv_wgrad_kernel, dim3(grid), dim3(kWgThreads), smem_bytes, stream, tmY, tmX, p));
     DD_CHECK_LAUNCH();
     return 0;
 }

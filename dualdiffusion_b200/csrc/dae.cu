@@ -48,6 +48,8 @@ __device__ __forceinline__ int reflect_idx(int w, int W) {
 template <bool kBf16>
 __global__ void weight_prep_z2_kernel(const void* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I, int kz,
                                       int taps, const float* __restrict__ gain_dev, float gain_host, int i_stride) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int r = blockIdx.x;
     const int zp = r / O, o = r - zp * O;
     const float scale = gain_host * (gain_dev ? *gain_dev : 1.f) * rsqrtf((float)(I * kz * taps));
@@ -71,6 +73,8 @@ __global__ void weight_prep_z2_kernel(const void* __restrict__ w, __nv_bfloat16*
 // halo columns <- mirrored logical columns:  x[.., pw-k] = x[.., pw+k],  x[.., pw+W-1+k] = x[.., pw+W-1-k]
 // ------------------------------------------------------------------------------------------
 __global__ void reflect_fill_w_kernel(uint4* __restrict__ x, long rows, int Wp, int nvec, int pw) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const long total = rows * 2 * pw * nvec;
     const int W = Wp - 2 * pw;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -92,6 +96,8 @@ __global__ void reflect_fill_w_kernel(uint4* __restrict__ x, long rows, int Wp, 
 // ------------------------------------------------------------------------------------------
 __global__ void dae_stem_kernel(const float* __restrict__ lat, __nv_bfloat16* __restrict__ out, int B, int L, int H, int W,
                                 int pw, int Cpad) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Wp = W + 2 * pw;
     const long total = (long)B * H * Wp * Cpad;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -115,6 +121,8 @@ __global__ void dae_stem_kernel(const float* __restrict__ lat, __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------
 __global__ void up2_silu_pad_kernel(const uint4* __restrict__ a, uint4* __restrict__ xc, uint4* __restrict__ s, int B, int Ha,
                                     int Wa, int pw, int nvec) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int H = 2 * Ha, W = 2 * Wa, Wp = W + 2 * pw, Wpa = Wa + 2 * pw;
     const long total = (long)B * H * Wp * nvec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -149,6 +157,8 @@ template <int C>
 __global__ void __launch_bounds__(kC5W * kC5H) conv5x5_out_kernel(const uint4* __restrict__ x, const float* __restrict__ wq,
                                                                  const float* __restrict__ gain, float* __restrict__ out,
                                                                  int B, int H, int W, int pw) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     constexpr int NV = C / 8;                    // uint4 vectors per stereo side
     constexpr int PV = 2 * NV;                   // vectors per pixel
     constexpr int TW = kC5W + 4, TH = kC5H + 4;
@@ -201,6 +211,8 @@ __global__ void __launch_bounds__(kC5W * kC5H) conv5x5_out_kernel(const uint4* _
 __global__ void ddec_stem_kernel(const float* __restrict__ x_in, const float* __restrict__ x_ref,
                                  const float* __restrict__ sigma, float sigma_data, __nv_bfloat16* __restrict__ out, int B,
                                  int Fq, int W, int k, int pw, int Cpad) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Wp = W + 2 * pw, ct = k + 2;
     const long total = (long)B * Fq * Wp * Cpad;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -229,6 +241,8 @@ __global__ void ddec_stem_kernel(const float* __restrict__ x_in, const float* __
 // resample_3d "down" (mp_tools.py:85-90: 2x2 mean over H, W) on a W-padded tensor, halo columns of the result mirrored
 __global__ void avgpool2_pad_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int pw,
                                     int nvec) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Ho = H >> 1, Wo = W >> 1, Wp = W + 2 * pw, Wpo = Wo + 2 * pw;
     const long total = (long)B * Ho * Wpo * nvec;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -258,6 +272,8 @@ __global__ void avgpool2_pad_kernel(const uint4* __restrict__ x, uint4* __restri
 __global__ void ddec_head_kernel(const __nv_bfloat16* __restrict__ f, const float* __restrict__ x_in,
                                  const float* __restrict__ sigma, float sigma_data, float* __restrict__ out, int B, int H,
                                  int W, int pw, int Cst) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Wp = W + 2 * pw;
     const long total = (long)B * 2 * H * W;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -281,6 +297,8 @@ __global__ void ddec_head_kernel(const __nv_bfloat16* __restrict__ f, const floa
 __global__ void q4_stem_kernel(const float* __restrict__ x_in, const float* __restrict__ x_ref, const float* __restrict__ sigma,
                                float sigma_data, float wa, float wb, __nv_bfloat16* __restrict__ out, int B, int C, int Fq,
                                int W, int k, int Cpad) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const long total = (long)B * Fq * W * Cpad;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int ch = (int)(idx % Cpad);
@@ -313,6 +331,8 @@ __global__ void q4_stem_kernel(const float* __restrict__ x_in, const float* __re
 // ------------------------------------------------------------------------------------------
 __global__ void dae_enc_patches_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                                        int pw) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Wp = W + 2 * pw;
     const long total = (long)B * H * Wp * 128;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -340,6 +360,8 @@ __global__ void dae_enc_patches_kernel(const float* __restrict__ mel, __nv_bfloa
 // (channel c*2 + z) -> avg_pool2d(ratio) -> fp32 NCHW (B, 2L, H/ratio, W/ratio)
 __global__ void dae_latents_pool_kernel(const __nv_bfloat16* __restrict__ f, float* __restrict__ out, int B, int L, int H,
                                         int W, int pw, int Cst, int ratio) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Ho = H / ratio, Wo = W / ratio, Wp = W + 2 * pw;
     const long total = (long)B * 2 * L * Ho * Wo;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -368,11 +390,11 @@ extern "C" int dd_weight_prep_z2(const void* w, int w_is_bf16, void* out, int O,
     if (i_stride <= 0) i_stride = n_in;
     DD_REQUIRE(i_stride >= n_in, "dd_weight_prep_z2: i_stride smaller than the input channel count");
     if (w_is_bf16)
-        weight_prep_z2_kernel<true><<<2 * O, 128, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), O, I, kz, taps, gain_dev,
-                                                               gain_host, i_stride);
+        DD_CHECK_CUDA(dd_launch_pdl(weight_prep_z2_kernel<true>, dim3(2 * O), dim3(128), 0, stream, w, static_cast<__nv_bfloat16*>(out), O, I, kz, taps, gain_dev,
+                                                               gain_host, i_stride));
     else
-        weight_prep_z2_kernel<false><<<2 * O, 128, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), O, I, kz, taps, gain_dev,
-                                                                gain_host, i_stride);
+        DD_CHECK_CUDA(dd_launch_pdl(weight_prep_z2_kernel<false>, dim3(2 * O), dim3(128), 0, stream, w, static_cast<__nv_bfloat16*>(out), O, I, kz, taps, gain_dev,
+                                                                gain_host, i_stride));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -383,7 +405,7 @@ extern "C" int dd_reflect_fill_w(void* x, int B, int H, int Wp, int C, int pw, v
     const long rows = (long)B * H;
     const long total = rows * 2 * pw * (C / 8);
     if (total == 0) return 0;
-    reflect_fill_w_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<uint4*>(x), rows, Wp, C / 8, pw);
+    DD_CHECK_CUDA(dd_launch_pdl(reflect_fill_w_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<uint4*>(x), rows, Wp, C / 8, pw));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -393,8 +415,8 @@ extern "C" int dd_dae_stem(const float* latents, void* out, int B, int L, int H,
     DD_REQUIRE(latents && out && L > 0 && 2 * (L + 1) <= Cpad && pw >= 1 && W > pw, "dd_dae_stem: bad arguments");
     const long total = (long)B * H * (W + 2 * pw) * Cpad;
     if (total == 0) return 0;
-    dae_stem_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(latents, static_cast<__nv_bfloat16*>(out), B, L, H, W, pw,
-                                                                Cpad);
+    DD_CHECK_CUDA(dd_launch_pdl(dae_stem_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, latents, static_cast<__nv_bfloat16*>(out), B, L, H, W, pw,
+                                                                Cpad));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -404,8 +426,8 @@ extern "C" int dd_up2_silu_pad(const void* a, void* xc, void* s, int B, int Ha, 
     DD_REQUIRE(a && xc && s && C % 8 == 0 && pw >= 1 && Wa >= 1, "dd_up2_silu_pad: bad arguments");
     const long total = (long)B * 2 * Ha * (2 * Wa + 2 * pw) * (C / 8);
     if (total == 0) return 0;
-    up2_silu_pad_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(a), static_cast<uint4*>(xc),
-                                                                    static_cast<uint4*>(s), B, Ha, Wa, pw, C / 8);
+    DD_CHECK_CUDA(dd_launch_pdl(up2_silu_pad_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<const uint4*>(a), static_cast<uint4*>(xc),
+                                                                    static_cast<uint4*>(s), B, Ha, Wa, pw, C / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -422,11 +444,11 @@ extern "C" int dd_conv5x5_out(const void* x, const float* w25, const float* gain
     if (C == 32) {
         static bool done = false;
         if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv5x5_out_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-        conv5x5_out_kernel<32><<<grid, block, smem, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
+        DD_CHECK_CUDA(dd_launch_pdl(conv5x5_out_kernel<32>, dim3(grid), dim3(block), smem, stream, static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw));
     } else {
         static bool done = false;
         if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv5x5_out_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done = true; }
-        conv5x5_out_kernel<64><<<grid, block, smem, stream>>>(static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw);
+        DD_CHECK_CUDA(dd_launch_pdl(conv5x5_out_kernel<64>, dim3(grid), dim3(block), smem, stream, static_cast<const uint4*>(x), w25, gain_dev, out, B, H, W, pw));
     }
     DD_CHECK_LAUNCH();
     return 0;
@@ -438,8 +460,8 @@ extern "C" int dd_ddec_stem(const float* x_in, const float* x_ref, const float* 
     DD_REQUIRE(x_in && x_ref && sigma && out && k >= 1 && 2 * (k + 2) <= Cpad && pw >= 1 && W > pw, "dd_ddec_stem: bad arguments");
     const long total = (long)B * F * (W + 2 * pw) * Cpad;
     if (total == 0) return 0;
-    ddec_stem_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(x_in, x_ref, sigma, sigma_data,
-                                                                 static_cast<__nv_bfloat16*>(out), B, F, W, k, pw, Cpad);
+    DD_CHECK_CUDA(dd_launch_pdl(ddec_stem_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, x_in, x_ref, sigma, sigma_data,
+                                                                 static_cast<__nv_bfloat16*>(out), B, F, W, k, pw, Cpad));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -449,8 +471,8 @@ extern "C" int dd_avgpool2_pad(const void* x, void* out, int B, int H, int W, in
     DD_REQUIRE(x && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && pw >= 1 && W / 2 > pw, "dd_avgpool2_pad: bad arguments");
     const long total = (long)B * (H / 2) * (W / 2 + 2 * pw) * (C / 8);
     if (total == 0) return 0;
-    avgpool2_pad_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), B,
-                                                                    H, W, pw, C / 8);
+    DD_CHECK_CUDA(dd_launch_pdl(avgpool2_pad_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<const uint4*>(x), static_cast<uint4*>(out), B,
+                                                                    H, W, pw, C / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -461,8 +483,8 @@ extern "C" int dd_ddec_head(const void* f, const float* x_in, const float* sigma
     DD_REQUIRE(f && x_in && sigma && out && Cst >= 2, "dd_ddec_head: bad arguments");
     const long total = (long)B * 2 * H * W;
     if (total == 0) return 0;
-    ddec_head_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(f), x_in, sigma, sigma_data,
-                                                                 out, B, H, W, pw, Cst);
+    DD_CHECK_CUDA(dd_launch_pdl(ddec_head_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(f), x_in, sigma, sigma_data,
+                                                                 out, B, H, W, pw, Cst));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -473,8 +495,8 @@ extern "C" int dd_q4_stem(const float* x_in, const float* x_ref, const float* si
     DD_REQUIRE(x_in && x_ref && sigma && out && k >= 1 && C * (k + 1) + 1 <= Cpad, "dd_q4_stem: bad arguments");
     const long total = (long)B * F * W * Cpad;
     if (total == 0) return 0;
-    q4_stem_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(x_in, x_ref, sigma, sigma_data, wa, wb,
-                                                               static_cast<__nv_bfloat16*>(out), B, C, F, W, k, Cpad);
+    DD_CHECK_CUDA(dd_launch_pdl(q4_stem_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, x_in, x_ref, sigma, sigma_data, wa, wb,
+                                                               static_cast<__nv_bfloat16*>(out), B, C, F, W, k, Cpad));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -484,7 +506,7 @@ extern "C" int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int
     DD_REQUIRE(mel && out && pw >= 1 && W > 2 && H > 0, "dd_dae_enc_patches: bad arguments");
     const long total = (long)B * H * (W + 2 * pw) * 128;
     if (total == 0) return 0;
-    dae_enc_patches_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(mel, static_cast<__nv_bfloat16*>(out), B, H, W, pw);
+    DD_CHECK_CUDA(dd_launch_pdl(dae_enc_patches_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, mel, static_cast<__nv_bfloat16*>(out), B, H, W, pw));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -496,8 +518,8 @@ extern "C" int dd_dae_latents_pool(const void* f, float* out, int B, int L, int 
                "dd_dae_latents_pool: bad arguments");
     const long total = (long)B * 2 * L * (H / ratio) * (W / ratio);
     if (total == 0) return 0;
-    dae_latents_pool_kernel<<<grid_for_d(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(f), out, B, L, H, W,
-                                                                        pw, Cst, ratio);
+    DD_CHECK_CUDA(dd_launch_pdl(dae_latents_pool_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(f), out, B, L, H, W,
+                                                                        pw, Cst, ratio));
     DD_CHECK_LAUNCH();
     return 0;
 }

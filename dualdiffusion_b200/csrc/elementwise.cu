@@ -36,6 +36,8 @@ template <bool kBf16>
 __global__ void weight_prep_kernel(const void* __restrict__ w, void* __restrict__ out, int out_format, int O, int I_g,
                                    int taps, const float* __restrict__ gain_dev, float gain_host, int normalize,
                                    int perm, int head_dim, int row_stride) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[32];
     const int o = blockIdx.x;
     const int fan_in = I_g * taps;
@@ -227,6 +229,8 @@ __global__ void noise_embedding_kernel(const float* __restrict__ sigma, const fl
                                        const float* __restrict__ phases, int cnoise, const void* __restrict__ w,
                                        int normalize, const float* __restrict__ label, float t, float* __restrict__ out,
                                        int cemb) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     extern __shared__ float four[];
     const int b = blockIdx.y;
     const float c_noise = logf(sigma[b]) * 0.25f;
@@ -256,6 +260,8 @@ __global__ void noise_embedding_kernel(const float* __restrict__ sigma, const fl
 
 __global__ void emb_affine_kernel(const dd_affine_desc* __restrict__ descs, const float* __restrict__ emb, int B,
                                   int cemb) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const dd_affine_desc d = descs[blockIdx.y];
     const int lane = threadIdx.x & 31;
     const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -292,6 +298,8 @@ template <bool kBf16>
 __global__ void label_embedding_kernel(const float* __restrict__ emb_in, int Bc, int I, const void* __restrict__ w_label,
                                        const void* __restrict__ w_uncond, const float* __restrict__ mask, int normalize,
                                        float* __restrict__ out, int cemb) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int lane = threadIdx.x & 31;
     const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int bm = blockIdx.y;
@@ -335,6 +343,8 @@ __global__ void logvar_kernel(const float* __restrict__ sigma, const float* __re
 
 __global__ void mp_fourier_kernel(const float* __restrict__ x, const float* __restrict__ freqs,
                                   const float* __restrict__ phases, int n, float* __restrict__ out, long total) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int c = (int)(i % n);
         out[i] = cosf(x[i / n] * freqs[c] + phases[c]) * 1.41421356237f;
@@ -344,6 +354,8 @@ __global__ void mp_fourier_kernel(const float* __restrict__ x, const float* __re
 // out = clip(alpha*a + beta*b)   (mp_sum / lerp on bf16 activations)
 __global__ void axpby_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, float alpha, float beta,
                              float clip, uint4* __restrict__ out, long nvec) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long)gridDim.x * blockDim.x) {
         const uint4 qa = __ldg(a + i), qb = __ldg(b + i);
         const uint32_t ua[4] = {qa.x, qa.y, qa.z, qa.w}, ub[4] = {qb.x, qb.y, qb.z, qb.w};
@@ -365,6 +377,8 @@ __global__ void axpby_kernel(const uint4* __restrict__ a, const uint4* __restric
 __global__ void sampler_cfg_lerp_kernel(const float4* __restrict__ d, const float4* __restrict__ sample, float cfg,
                                         float t_hat, float4* __restrict__ cfg_out, float4* __restrict__ xhat, int dup,
                                         long n4) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         const float4 c = d[i], u = (dup & 2) ? c : d[i + n4], s = sample[i];      // bit 1: unconditional (no CFG pair)
         float4 o, x;
@@ -383,6 +397,8 @@ __global__ void sampler_cfg_lerp_kernel(const float4* __restrict__ d, const floa
 __global__ void sampler_update_kernel(const float4* __restrict__ cfg1, const float4* __restrict__ d2, float cfg,
                                       int use_heun, float t, float p, const float4* __restrict__ noise,
                                       float4* __restrict__ sample, float4* __restrict__ cfg_out, int dup, long n4) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 o = cfg1[i];
         if (use_heun) {
@@ -411,6 +427,8 @@ __global__ void sampler_update_kernel(const float4* __restrict__ cfg1, const flo
 __global__ void conv_naive_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                   __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cin, int Cout, int ks,
                                   int groups) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int cin_g = Cin / groups, cout_g = Cout / groups;
     const long total = (long)B * H * W * Cout;
     for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -452,11 +470,11 @@ extern "C" int dd_weight_prep(const void* w, int w_is_bf16, void* out, int out_f
     const int row_stride = out_row_stride > 0 ? out_row_stride : I_g * taps;
     DD_REQUIRE(row_stride >= I_g * taps, "dd_weight_prep: out_row_stride smaller than a row");
     if (w_is_bf16)
-        weight_prep_kernel<true><<<O, 128, 0, stream>>>(w, out, out_format, O, I_g, taps, gain_dev, gain_host, normalize,
-                                                        perm, head_dim, row_stride);
+        DD_CHECK_CUDA(dd_launch_pdl(weight_prep_kernel<true>, dim3(O), dim3(128), 0, stream, w, out, out_format, O, I_g, taps, gain_dev, gain_host, normalize,
+                                                        perm, head_dim, row_stride));
     else
-        weight_prep_kernel<false><<<O, 128, 0, stream>>>(w, out, out_format, O, I_g, taps, gain_dev, gain_host,
-                                                         normalize, perm, head_dim, row_stride);
+        DD_CHECK_CUDA(dd_launch_pdl(weight_prep_kernel<false>, dim3(O), dim3(128), 0, stream, w, out, out_format, O, I_g, taps, gain_dev, gain_host,
+                                                         normalize, perm, head_dim, row_stride));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -523,11 +541,11 @@ extern "C" int dd_noise_embedding(const float* sigma, const float* freqs, const 
     const dim3 grid(ceil_div(cemb, 8), B);
     const size_t smem = (size_t)cnoise * sizeof(float);
     if (w_is_bf16)
-        noise_embedding_kernel<true><<<grid, 256, smem, stream>>>(sigma, freqs, phases, cnoise, w_noise, normalize,
-                                                                  label_emb, label_balance, emb_out, cemb);
+        DD_CHECK_CUDA(dd_launch_pdl(noise_embedding_kernel<true>, dim3(grid), dim3(256), smem, stream, sigma, freqs, phases, cnoise, w_noise, normalize,
+                                                                  label_emb, label_balance, emb_out, cemb));
     else
-        noise_embedding_kernel<false><<<grid, 256, smem, stream>>>(sigma, freqs, phases, cnoise, w_noise, normalize,
-                                                                   label_emb, label_balance, emb_out, cemb);
+        DD_CHECK_CUDA(dd_launch_pdl(noise_embedding_kernel<false>, dim3(grid), dim3(256), smem, stream, sigma, freqs, phases, cnoise, w_noise, normalize,
+                                                                   label_emb, label_balance, emb_out, cemb));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -537,7 +555,7 @@ extern "C" int dd_emb_affine(const dd_affine_desc* descs_dev, int n_descs, int m
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && emb && n_descs > 0 && max_O > 0, "dd_emb_affine: bad arguments");
     const dim3 grid(ceil_div(max_O, 8), n_descs);
-    emb_affine_kernel<<<grid, 256, 0, stream>>>(descs_dev, emb, B, cemb);
+    DD_CHECK_CUDA(dd_launch_pdl(emb_affine_kernel, dim3(grid), dim3(256), 0, stream, descs_dev, emb, B, cemb));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -551,9 +569,9 @@ extern "C" int dd_label_embedding(const float* emb_in, int Bc, int I, const void
     DD_REQUIRE(Bc == 1 || Bc == Bm, "dd_label_embedding: embedding batch %d does not broadcast to mask batch %d", Bc, Bm);
     const dim3 grid(ceil_div(cemb, 8), Bm);
     if (w_is_bf16)
-        label_embedding_kernel<true><<<grid, 256, 0, stream>>>(emb_in, Bc, I, w_label, w_uncond, mask, normalize, out, cemb);
+        DD_CHECK_CUDA(dd_launch_pdl(label_embedding_kernel<true>, dim3(grid), dim3(256), 0, stream, emb_in, Bc, I, w_label, w_uncond, mask, normalize, out, cemb));
     else
-        label_embedding_kernel<false><<<grid, 256, 0, stream>>>(emb_in, Bc, I, w_label, w_uncond, mask, normalize, out, cemb);
+        DD_CHECK_CUDA(dd_launch_pdl(label_embedding_kernel<false>, dim3(grid), dim3(256), 0, stream, emb_in, Bc, I, w_label, w_uncond, mask, normalize, out, cemb));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -576,7 +594,7 @@ extern "C" int dd_mp_fourier(const float* x, int count, const float* freqs, cons
     DD_REQUIRE(x && freqs && phases && out, "dd_mp_fourier: null pointer");
     const long total = (long)count * n;
     if (total == 0) return 0;
-    mp_fourier_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, freqs, phases, n, out, total);
+    DD_CHECK_CUDA(dd_launch_pdl(mp_fourier_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, x, freqs, phases, n, out, total));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -587,9 +605,9 @@ extern "C" int dd_axpby(const void* a, const void* b, float alpha, float beta, f
     DD_REQUIRE(a && b && out, "dd_axpby: null pointer");
     DD_REQUIRE(n % 8 == 0, "dd_axpby: element count must be a multiple of 8");
     if (n == 0) return 0;
-    axpby_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const uint4*>(a), static_cast<const uint4*>(b),
+    DD_CHECK_CUDA(dd_launch_pdl(axpby_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, stream, static_cast<const uint4*>(a), static_cast<const uint4*>(b),
                                                            alpha, beta, clip > 0.f ? clip : INFINITY,
-                                                           static_cast<uint4*>(out), n / 8);
+                                                           static_cast<uint4*>(out), n / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -600,9 +618,9 @@ extern "C" int dd_sampler_cfg_lerp(const float* d_2b, const float* sample, float
     DD_REQUIRE(d_2b && sample && cfg_out, "dd_sampler_cfg_lerp: null pointer");
     DD_REQUIRE(n % 4 == 0, "dd_sampler_cfg_lerp: element count must be a multiple of 4");
     if (n == 0) return 0;
-    sampler_cfg_lerp_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(
+    DD_CHECK_CUDA(dd_launch_pdl(sampler_cfg_lerp_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, stream, 
         reinterpret_cast<const float4*>(d_2b), reinterpret_cast<const float4*>(sample), cfg_scale, t_hat,
-        reinterpret_cast<float4*>(cfg_out), reinterpret_cast<float4*>(x_hat_out), dup, n / 4);
+        reinterpret_cast<float4*>(cfg_out), reinterpret_cast<float4*>(x_hat_out), dup, n / 4));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -613,10 +631,10 @@ extern "C" int dd_sampler_update(const float* cfg1, const float* d2_2b, float cf
     DD_REQUIRE(cfg1 && sample && (!use_heun || d2_2b), "dd_sampler_update: null pointer");
     DD_REQUIRE(n % 4 == 0, "dd_sampler_update: element count must be a multiple of 4");
     if (n == 0) return 0;
-    sampler_update_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(
+    DD_CHECK_CUDA(dd_launch_pdl(sampler_update_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, stream, 
         reinterpret_cast<const float4*>(cfg1), reinterpret_cast<const float4*>(d2_2b), cfg_scale, use_heun, t, p,
         reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(sample), reinterpret_cast<float4*>(cfg_out),
-        dup, n / 4);
+        dup, n / 4));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -627,9 +645,9 @@ extern "C" int dd_mpconv_forward_naive(const void* x, const void* w, void* out, 
     DD_REQUIRE(x && w && out, "dd_mpconv_forward_naive: null pointer");
     const long total = (long)B * H * W * Cout;
     if (total == 0) return 0;
-    conv_naive_kernel<<<grid_for(total, 256, 32), 256, 0, stream>>>(
+    DD_CHECK_CUDA(dd_launch_pdl(conv_naive_kernel, dim3(grid_for(total, 256, 32)), dim3(256), 0, stream, 
         static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(out), B,
-        H, W, Cin, Cout, ksize, groups);
+        H, W, Cin, Cout, ksize, groups));
     DD_CHECK_LAUNCH();
     return 0;
 }

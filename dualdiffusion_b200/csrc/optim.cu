@@ -48,6 +48,8 @@ __device__ __forceinline__ int find_desc(const D* __restrict__ descs, int n_desc
 // stage 1: partials[cta] = sum of squares of one 8192-element chunk of one gradient tensor
 __global__ void __launch_bounds__(kThreads) grad_sqnorm_partial_kernel(const dd_gnorm_desc* __restrict__ descs,
                                                                        int n_descs, float* __restrict__ partials) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[32];
     const int di = find_desc(descs, n_descs, (int)blockIdx.x);
     const dd_gnorm_desc d = descs[di];
@@ -77,6 +79,8 @@ __global__ void __launch_bounds__(kThreads) grad_sqnorm_partial_kernel(const dd_
 // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1 (NaN propagates, as torch.clamp does)
 __global__ void __launch_bounds__(kThreads) grad_norm_finish_kernel(const float* __restrict__ partials, int n,
                                                                     float max_norm, float* __restrict__ out) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ double red[kThreads];
     double s = 0.0;
     for (int i = threadIdx.x; i < n; i += kThreads) s += (double)partials[i];
@@ -103,6 +107,8 @@ constexpr int kMaxSmemDescs = 2048;
 template <bool SMEM_SEARCH>
 __global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_optim_desc* __restrict__ descs, int n_descs,
                                                                       OptimHyperDev h, const float* __restrict__ clip_coef) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[32];
     int lo = 0, hi = n_descs - 1;
     const int unit = blockIdx.x;
@@ -130,6 +136,8 @@ __global__ void __launch_bounds__(kThreads) optim_step_batched_kernel(const dd_o
 __global__ void __launch_bounds__(kThreads) optim_step_persistent_kernel(const dd_optim_desc* __restrict__ descs, int n_descs,
                                                                          OptimHyperDev h, const float* __restrict__ clip_coef,
                                                                          int total_rows) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     __shared__ float red[32];
     __shared__ int s_begin[kMaxSmemDescs];
     for (int i = threadIdx.x; i < n_descs; i += kThreads) s_begin[i] = descs[i].row_begin;
@@ -153,9 +161,9 @@ extern "C" int dd_grad_norm_clip(const dd_gnorm_desc* descs_dev, int n_descs, in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && partials_dev && out_norm_coef_dev && n_descs > 0 && total_chunks > 0,
                "dd_grad_norm_clip: bad arguments");
-    grad_sqnorm_partial_kernel<<<total_chunks, kThreads, 0, stream>>>(descs_dev, n_descs, partials_dev);
+    DD_CHECK_CUDA(dd_launch_pdl(grad_sqnorm_partial_kernel, dim3(total_chunks), dim3(kThreads), 0, stream, descs_dev, n_descs, partials_dev));
     DD_CHECK_LAUNCH();
-    grad_norm_finish_kernel<<<1, kThreads, 0, stream>>>(partials_dev, total_chunks, max_norm, out_norm_coef_dev);
+    DD_CHECK_CUDA(dd_launch_pdl(grad_norm_finish_kernel, dim3(1), dim3(kThreads), 0, stream, partials_dev, total_chunks, max_norm, out_norm_coef_dev));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -172,11 +180,11 @@ extern "C" int dd_optim_step_batched(const dd_optim_desc* descs_dev, int n_descs
     static const bool persistent = getenv("DD_OPTIM_PERSISTENT") != nullptr;
     if (persistent && n_descs <= kMaxSmemDescs) {
         const int grid = total_rows < dd_num_sms() * 3 ? total_rows : dd_num_sms() * 3;
-        optim_step_persistent_kernel<<<grid, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev, total_rows);
+        DD_CHECK_CUDA(dd_launch_pdl(optim_step_persistent_kernel, dim3(grid), dim3(kThreads), 0, stream, descs_dev, n_descs, h, norm_coef_dev, total_rows));
     } else if (smem_search && n_descs <= kMaxSmemDescs)
-        optim_step_batched_kernel<true><<<total_rows, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev);
+        DD_CHECK_CUDA(dd_launch_pdl(optim_step_batched_kernel<true>, dim3(total_rows), dim3(kThreads), 0, stream, descs_dev, n_descs, h, norm_coef_dev));
     else
-        optim_step_batched_kernel<false><<<total_rows, kThreads, 0, stream>>>(descs_dev, n_descs, h, norm_coef_dev);
+        DD_CHECK_CUDA(dd_launch_pdl(optim_step_batched_kernel<false>, dim3(total_rows), dim3(kThreads), 0, stream, descs_dev, n_descs, h, norm_coef_dev));
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -13,6 +13,8 @@ namespace {
 // (`.repeat(2,1,1,1)` of :661 / :628).
 __global__ void roll_pad_w_kernel(const float* __restrict__ x, float* __restrict__ out, long rows, int W, int shift,
                                   int pad, int copies) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Wp = W + 2 * pad;
     const long total = rows * Wp;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -26,6 +28,8 @@ __global__ void roll_pad_w_kernel(const float* __restrict__ x, float* __restrict
 // out[r][i] = xp[r][pad + (i + shift) mod W]:  torch.roll(xp[..., pad:-pad], -shift, -1)  (:730-732)
 __global__ void crop_unroll_w_kernel(const float* __restrict__ xp, float* __restrict__ out, long rows, int W, int shift,
                                      int pad) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     const int Wp = W + 2 * pad;
     const long total = rows * W;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -39,6 +43,8 @@ __global__ void crop_unroll_w_kernel(const float* __restrict__ xp, float* __rest
 // (mp_tools.py:273-279, torch.lerp's two-sided formula).  noise, fresh, out: fp32 (B, C, hw), C even.
 __global__ void stereo_fix_noise_kernel(const float* __restrict__ noise, const float* __restrict__ fresh, float t,
                                         float inv_norm, float* __restrict__ out, int C, long hw, long total) {
+    ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
+    ptx::grid_dependency_wait();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const long bc = i / hw;
         const long pos = i - bc * hw;
@@ -61,7 +67,7 @@ extern "C" int dd_roll_pad_w(const float* x, float* out, long rows, int W, int s
     DD_REQUIRE(rows > 0 && W > 0 && pad >= 0 && pad <= W && copies >= 1, "dd_roll_pad_w: bad sizes (rows=%ld W=%d pad=%d)",
                rows, W, pad);
     DD_REQUIRE(shift >= 0 && shift < W, "dd_roll_pad_w: shift=%d must lie in [0, W)", shift);
-    roll_pad_w_kernel<<<grid_for_s(rows * (W + 2 * pad), 256), 256, 0, stream>>>(x, out, rows, W, shift, pad, copies);
+    DD_CHECK_CUDA(dd_launch_pdl(roll_pad_w_kernel, dim3(grid_for_s(rows * (W + 2 * pad), 256)), dim3(256), 0, stream, x, out, rows, W, shift, pad, copies));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -71,7 +77,7 @@ extern "C" int dd_crop_unroll_w(const float* xp, float* out, long rows, int W, i
     DD_REQUIRE(xp && out, "dd_crop_unroll_w: null pointer");
     DD_REQUIRE(rows > 0 && W > 0 && pad >= 0 && pad <= W, "dd_crop_unroll_w: bad sizes (rows=%ld W=%d pad=%d)", rows, W, pad);
     DD_REQUIRE(shift >= 0 && shift < W, "dd_crop_unroll_w: shift=%d must lie in [0, W)", shift);
-    crop_unroll_w_kernel<<<grid_for_s(rows * W, 256), 256, 0, stream>>>(xp, out, rows, W, shift, pad);
+    DD_CHECK_CUDA(dd_launch_pdl(crop_unroll_w_kernel, dim3(grid_for_s(rows * W, 256)), dim3(256), 0, stream, xp, out, rows, W, shift, pad));
     DD_CHECK_LAUNCH();
     return 0;
 }
@@ -84,8 +90,8 @@ extern "C" int dd_stereo_fix_noise(const float* noise, const float* fresh, float
     DD_REQUIRE(C % 2 == 0, "dd_stereo_fix_noise: the channel count must be even (noise[:, ::2] = noise[:, 1::2])");
     const double norm = sqrt((1.0 - (double)t) * (1.0 - (double)t) + (double)t * (double)t);
     const long total = (long)B * C * hw;
-    stereo_fix_noise_kernel<<<grid_for_s(total, 256), 256, 0, stream>>>(noise, fresh, t, (float)(1.0 / norm), out, C, hw,
-                                                                        total);
+    DD_CHECK_CUDA(dd_launch_pdl(stereo_fix_noise_kernel, dim3(grid_for_s(total, 256)), dim3(256), 0, stream, noise, fresh, t, (float)(1.0 / norm), out, C, hw,
+                                                                        total));
     DD_CHECK_LAUNCH();
     return 0;
 }
