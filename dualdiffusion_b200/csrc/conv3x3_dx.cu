@@ -246,6 +246,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::mbar_fence_init();
         ptx::fence_proxy_async_smem();
         __syncwarp();
+        if (lane == 0) trace_stamp<TRACE>(p, 2, 63);          // barriers initialised
     }
     // Every role walks the same unit sequence with incremental counters: no integer division and no tile decode in the
     // per-tile control path (the issuing warp's bookkeeping between two tiles must stay shorter than the work queued in
@@ -269,9 +270,12 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     };
     if (warp == 0 && u_begin < u_end) issue_panel(wk.panel);
+    if (threadIdx.x == 0) trace_stamp<TRACE>(p, 3, 63);          // first weight panel requested
     if (warp == 1) {
+        if (lane == 0) trace_stamp<TRACE>(p, 4, 63);          // TMEM allocation starts
         ptx::tmem_alloc(&tmem_base_slot, 512);
         ptx::tmem_relinquish();
+        if (lane == 0) trace_stamp<TRACE>(p, 5, 63);          // TMEM allocated
     }
     ptx::tcgen05_fence_before();
     __syncthreads();
@@ -297,7 +301,11 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     b_par ^= 1;
                     issue_panel(wk.panel);
                 }
-                if (first) { ptx::grid_dependency_wait(); first = false; }      // weights do not depend on the previous kernel
+                if (first) {                                  // weights do not depend on the previous kernel
+                    ptx::grid_dependency_wait();
+                    first = false;
+                    if (lane == 0) trace_stamp<TRACE>(p, 7, 63);      // previous grid complete
+                }
                 const int ci0 = panel_ci0(p, wk.panel);
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     const uint32_t stage = (uint32_t)(turn * p.ring) + rpos;

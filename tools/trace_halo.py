@@ -36,7 +36,7 @@ def report(t, meta, mhz):
     us = lambda c: c / mhz          # cycles -> microseconds at the SM clock
     for cta in range(CTAS):
         s = t[cta]
-        n = int((s[4] > 0).sum())
+        n = int((s[4, :62] > 0).sum())            # (items 62 / 63 carry per-CTA stamps, never tiles)
         if n < 4:
             continue
         t0 = int(s[:, :n][s[:, :n] > 0].min())
@@ -73,6 +73,10 @@ def report(t, meta, mhz):
             e0, e1, e2 = float(s[0, 63] - t0), float(s[1, 63] - t0), float(s[6, 63] - t0)
             print(f"   CTA entry at {us(e0):.2f} us, set-up done {us(e1):.2f} us, first UMMAs issued {us(float(r[4, 0])):.2f} us, "
                   f"last epilogue done {us(float(r[6, :n].max())):.2f} us, exit {us(e2):.2f} us   (CTA lifetime {us(e2 - e0):.2f} us)")
+            if int(s[5, 63]) > 0:                              # finer set-up stamps
+                f = lambda slot: us(float(s[slot, 63] - t0))
+                print(f"   set-up: barriers initialised {f(2):.2f}, first weight panel requested {f(3):.2f}, TMEM alloc "
+                      f"{f(4):.2f} -> {f(5):.2f}, previous grid complete (griddepcontrol.wait) {f(7):.2f}")
         print("   first tiles (us since first stamp): " + " | ".join(
             f"{i}: tma {us(float(r[1, i])):.1f} mma {us(float(r[4, i])):.1f} epi {us(float(r[6, i])):.1f}" for i in range(min(n, 6))))
 
