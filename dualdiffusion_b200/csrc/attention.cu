@@ -1,4 +1,5 @@
-// Small-sequence attention of the EDM2 UNet blocks (N = H*W <= 640 tokens, head_dim 64):
+// Attention of the EDM2 UNet blocks (N = H*W tokens, head_dim 64; sized for the small sequences of the latent: K / V of
+// up to 640 tokens stay resident in shared memory, longer sequences stream through in 512-key chunks):
 // reference modules/unets/unet_edm2_b4.py:137-151.
 //
 // Per (batch, head, 128-query tile) CTA: K and V of the head are cosine-normalised (mp_tools.normalize over
@@ -8,6 +9,7 @@
 // fp32 accumulate).  The block's `mp_silu(y * (emb_linear_v(emb) + 1))` (:150-151) is the epilogue.
 // Attention is 0.8 % of the UNet FLOPs; the kernel is sized for latency, not peak.
 #include "common.cuh"
+#include <type_traits>
 #include "dualdiffusion_b200.h"
 
 namespace {
@@ -69,15 +71,17 @@ struct AttnLayout {
 __global__ void __launch_bounds__(kAttThreads)
 attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* __restrict__ k_ptr,
                  const __nv_bfloat16* __restrict__ v_ptr, const float* __restrict__ scale_v,
-                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw_out, int N, int heads, int npad,
+                 __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ raw_out, int N, int heads, int npad, int kcap,
                  const __grid_constant__ AttnLayout lay) {
     extern __shared__ __align__(16) uint8_t smem_att[];
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
     const int C = heads * kD;
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);            // [npad][kKStride]
-    __nv_bfloat16* Vs = Ks + (size_t)npad * kKStride;                          // [npad][kKStride]
-    __nv_bfloat16* Qs = Vs + (size_t)npad * kKStride;                          // [kQTile][kKStride]
+    // K / V are resident `kcap` keys at a time (the whole sequence when it fits: N <= 640); longer sequences stream
+    // through the same buffers chunk by chunk while the online softmax carries on
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem_att);            // [kcap][kKStride]
+    __nv_bfloat16* Vs = Ks + (size_t)kcap * kKStride;                          // [kcap][kKStride]
+    __nv_bfloat16* Qs = Vs + (size_t)kcap * kKStride;                          // [kQTile][kKStride]
 
     const int q0 = blockIdx.x * kQTile, head = blockIdx.y;
     const int outer = blockIdx.z / lay.n_inner, inner = blockIdx.z - outer * lay.n_inner;
@@ -127,21 +131,26 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
                                pack_bf16x2(f[4] * inv, f[5] * inv), pack_bf16x2(f[6] * inv, f[7] * inv));
         }
     };
-    for (int c0 = 0; c0 < npad; c0 += 32 * kPass) {
-        uint4 kq[kPass], vq[kPass], qq[kQTile / 32];
-        load_rows(kq, k_base, (size_t)lay.q_tok, 0, c0, npad, N);
-        load_rows(vq, v_base, (size_t)lay.v_tok, 0, c0, npad, N);
-        if (c0 == 0) load_rows(qq, q_base, (size_t)lay.q_tok, q0, 0, kQTile, N);
-        norm_store_rows(kq, c0, npad, Ks);
-        norm_store_rows(vq, c0, npad, Vs);
-        if (c0 == 0) norm_store_rows(qq, 0, kQTile, Qs);
-    }
+    // One chunk of keys (and, with the first chunk, the query tile) into shared memory, PASS x 32 rows per batch of loads.
+    auto stage_chunk = [&](auto pass_tag, int cbase, int cn, bool with_q) {
+        constexpr int PASS = decltype(pass_tag)::value;
+        for (int c0 = 0; c0 < cn; c0 += 32 * PASS) {
+            uint4 kq[PASS], vq[PASS], qq[kQTile / 32];
+            load_rows(kq, k_base, (size_t)lay.q_tok, cbase, c0, cn, N);
+            load_rows(vq, v_base, (size_t)lay.v_tok, cbase, c0, cn, N);
+            if (with_q && c0 == 0) load_rows(qq, q_base, (size_t)lay.q_tok, q0, 0, kQTile, N);
+            norm_store_rows(kq, c0, cn, Ks);
+            norm_store_rows(vq, c0, cn, Vs);
+            if (with_q && c0 == 0) norm_store_rows(qq, 0, kQTile, Qs);
+        }
+    };
+    // first (usually only) chunk: staged before the accumulators exist, so its 28 vectors per thread cost no spills
+    stage_chunk(std::integral_constant<int, kPass>{}, 0, min(kcap, npad), true);
     __syncthreads();
 
     const int g = lane >> 2, t = lane & 3;
     const int row0 = warp * 16;
-    // Q fragments for the 4 k-steps over head_dim
-    uint32_t qa[4][4];
+    uint32_t qa[4][4];                           // Q fragments for the 4 k-steps over head_dim
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
         const __nv_bfloat16* p0 = Qs + (size_t)(row0 + g) * kKStride + kk * 16 + 2 * t;
@@ -151,7 +160,6 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
         qa[kk][2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
         qa[kk][3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
     }
-
     // per-channel output scale of this thread's 16 head channels: requested now, consumed in the epilogue
     float scv[16];
     {
@@ -162,14 +170,21 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
             scv[2 * n + 1] = sc ? __ldg(sc + n * 8 + 2 * t + 1) : 1.f;
         }
     }
-
     const float sl2 = 0.125f * 1.44269504089f;   // 1/sqrt(64) * log2(e)
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     float o[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
 
-    for (int kb = 0; kb < npad; kb += 64) {
+    for (int cbase = 0; cbase < npad; cbase += kcap) {
+    const int cn = min(kcap, npad - cbase);          // keys of this chunk (a multiple of 64)
+    if (cbase > 0) {                                 // sequences beyond 640 tokens: next 512 keys through the same buffers
+        __syncthreads();                             // every warp is done with the previous chunk
+        stage_chunk(std::integral_constant<int, 2>{}, cbase, cn, false);
+        __syncthreads();
+    }
+
+    for (int kb = 0; kb < cn; kb += 64) {
         float s[8][4];
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
@@ -186,7 +201,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const int key = kb + n * 8 + 2 * t;
+            const int key = cbase + kb + n * 8 + 2 * t;
             if (key >= N) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
             if (key + 1 >= N) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
             mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
@@ -231,6 +246,8 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
         }
     }
 
+    }      // key chunks
+
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
@@ -259,7 +276,8 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
                      __nv_bfloat16* out, __nv_bfloat16* raw_out, int n_seq, int N, int heads, const AttnLayout& lay,
                      cudaStream_t stream) {
     const int npad = ceil_div(N, 64) * 64;
-    const size_t smem = ((size_t)2 * npad * kKStride + (size_t)kQTile * kKStride) * 2;
+    const int kcap = npad <= 640 ? npad : 512;           // resident keys: whole sequence, or 512-key chunks
+    const size_t smem = ((size_t)2 * kcap * kKStride + (size_t)kQTile * kKStride) * 2;
     static size_t smem_set = 0;
     if (smem > smem_set) {
         DD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -268,7 +286,7 @@ int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_
     DD_REQUIRE(n_seq <= 65535, "dd_attention: %d sequences exceed the grid limit", n_seq);
     const dim3 grid(ceil_div(N, kQTile), heads, n_seq);
     DD_CHECK_CUDA(dd_launch_pdl(attention_kernel, grid, dim3(kAttThreads), smem, stream, q, k, v, scale_v, out, raw_out, N,
-                                heads, npad, lay));
+                                heads, npad, kcap, lay));
     return 0;
 }
 
@@ -279,7 +297,7 @@ extern "C" int dd_attention(const void* qk, const void* v, const float* scale_v,
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(qk && v && scale_v && out, "dd_attention: null pointer");
     DD_REQUIRE(head_dim == kD, "dd_attention: head_dim=%d unsupported (64)", head_dim);
-    DD_REQUIRE(N > 0 && N <= 640, "dd_attention: N=%d unsupported (1..640)", N);
+    DD_REQUIRE(N > 0 && N <= 65536, "dd_attention: N=%d unsupported (1..65536)", N);
     const long C = (long)heads * kD;
     AttnLayout lay{2 * C, (long)N * 2 * C, 0, C, (long)N * C, 0, C, (long)N * C, 0, 1, 1};
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qk);
@@ -292,7 +310,7 @@ extern "C" int dd_attention_train(const void* qk, const void* v, const float* sc
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(qk && v && scale_v && out && raw_out, "dd_attention_train: null pointer");
     DD_REQUIRE(head_dim == kD, "dd_attention_train: head_dim=%d unsupported (64)", head_dim);
-    DD_REQUIRE(N > 0 && N <= 640, "dd_attention_train: N=%d unsupported (1..640)", N);
+    DD_REQUIRE(N > 0 && N <= 640, "dd_attention_train: N=%d unsupported (1..640: the backward kernels keep the whole sequence resident)", N);
     const long C = (long)heads * kD;
     AttnLayout lay{2 * C, (long)N * 2 * C, 0, C, (long)N * C, 0, C, (long)N * C, 0, 1, 1};
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qk);
@@ -304,7 +322,7 @@ extern "C" int dd_attention_qkv(const void* qkv, void* out_raw, int B, int N, in
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(qkv && out_raw, "dd_attention_qkv: null pointer");
     DD_REQUIRE(head_dim == kD, "dd_attention_qkv: head_dim=%d unsupported (64)", head_dim);
-    DD_REQUIRE(N > 0 && N <= 640, "dd_attention_qkv: N=%d unsupported (1..640)", N);
+    DD_REQUIRE(N > 0 && N <= 65536, "dd_attention_qkv: N=%d unsupported (1..65536)", N);
     const long C = (long)heads * kD, C3 = 3 * C;
     AttnLayout lay{C3, (long)N * C3, 0, C3, (long)N * C3, 0, C, (long)N * C, 0, 1, 1};
     const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(qkv);
@@ -320,7 +338,7 @@ extern "C" int dd_attention_axis(const void* qkv, void* out, int B, int Z, int H
     DD_REQUIRE(axis == 0 || axis == 1, "dd_attention_axis: axis must be 0 (H) or 1 (W)");
     const long C = (long)heads * kD, C3 = 3 * C;
     const int N = axis == 0 ? H : W;
-    DD_REQUIRE(N > 0 && N <= 640, "dd_attention_axis: %d tokens unsupported (1..640)", N);
+    DD_REQUIRE(N > 0 && N <= 65536, "dd_attention_axis: %d tokens unsupported (1..65536)", N);
     AttnLayout lay;
     int n_seq;
     if (axis == 0) {      // attend over H; (b, z) outer, w inner -- b3.py:146-148

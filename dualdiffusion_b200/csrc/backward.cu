@@ -536,7 +536,7 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* smem
 __device__ __forceinline__ void stage_rows_bwd(const __nv_bfloat16* __restrict__ head_base, size_t tok_stride, int first,
                                                int n_rows, int limit, __nv_bfloat16* __restrict__ dst, bool normalize) {
     const int sub = threadIdx.x & 7, tok = threadIdx.x >> 3;
-    constexpr int kBatch = 4;
+    constexpr int kBatch = 12;          // loads in flight per thread: staging is a chain of memory round trips otherwise
     for (int r0 = 0; r0 < n_rows; r0 += 16 * kBatch) {
         uint4 q[kBatch];
 #pragma unroll
@@ -1152,13 +1152,18 @@ extern "C" int dd_attention_bwd(const void* qk, const void* v, const void* a_raw
 extern "C" int dd_emb_affine_bwd(const dd_affine_bwd_desc* descs_dev, int n_descs, int max_O, int max_cols,
                                  const float* emb, float* demb, int B, int cemb, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    DD_REQUIRE(descs_dev && emb && demb && n_descs > 0 && max_O > 0 && max_cols > 0, "dd_emb_affine_bwd: bad arguments");
-    DD_CHECK_CUDA(dd_launch_pdl(emb_affine_bwd_w_kernel, dim3(dim3(ceil_div(max_O, 8), n_descs)), dim3(256), 0, stream, descs_dev, emb, B, cemb));
-    DD_CHECK_LAUNCH();
-    const int row_chunks = 4;
-    DD_CHECK_CUDA(dd_launch_pdl(emb_affine_bwd_x_kernel, dim3(dim3(ceil_div(max_cols, 128), n_descs, row_chunks)), dim3(128), 0, stream, descs_dev, demb, B,
-                                                                                                     cemb, row_chunks));
-    DD_CHECK_LAUNCH();
+    DD_REQUIRE(descs_dev && (emb || demb) && n_descs > 0 && max_O > 0 && max_cols > 0, "dd_emb_affine_bwd: bad arguments");
+    if (emb) {          // stage 1: weight gradients + row scales of these descriptors
+        DD_CHECK_CUDA(dd_launch_pdl(emb_affine_bwd_w_kernel, dim3(ceil_div(max_O, 8), n_descs), dim3(256), 0, stream, descs_dev, emb, B,
+                                    cemb));
+        DD_CHECK_LAUNCH();
+    }
+    if (demb) {         // stage 2: gradient of the embedding vector (needs stage 1 of every descriptor it is given)
+        const int row_chunks = 4;
+        DD_CHECK_CUDA(dd_launch_pdl(emb_affine_bwd_x_kernel, dim3(ceil_div(max_cols, 128), n_descs, row_chunks), dim3(128), 0, stream,
+                                    descs_dev, demb, B, cemb, row_chunks));
+        DD_CHECK_LAUNCH();
+    }
     return 0;
 }
 

@@ -61,10 +61,6 @@ struct ConvParams {
     int kchunks;                    // cin_g / KC
     int k_iters;                    // taps * kchunks
     int sub;                        // operand pairs per pipeline stage (1 or 2)
-    int ksplit;                     // split-K factor (conv_igemm_splitk_kernel), 1 otherwise
-    float* ws;                      // split-K: fp32 partial-sum workspace [tile][128][n_tile] of this launch's slot (all zero
-                                    // between launches: the finishing CTA of a tile clears what it consumed)
-    int* ws_count;                  // split-K: arrivals per tile (reset by the finisher)
     int num_tiles;
     int stages;
     uint32_t a_bytes, b_bytes;      // bytes landed per stage by the two TMA boxes
@@ -150,7 +146,7 @@ __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH],
 
 template <int EW>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
-                                              int ch0, float* ws_row = nullptr) {
+                                              int ch0) {
     constexpr int kChunk = EW >= 8 ? 16 : 32;   // columns per tcgen05.ld
     const size_t pix = ((size_t)b * p.H + h) * p.W + w;
     uint32_t rn[kChunk];
@@ -171,18 +167,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
               }
               if (c0 + kChunk < p.n_tile)
                   tmem_ld_chunk<kChunk>(taddr + c0 + kChunk, rn, kChunk == 32 && c0 + 2 * kChunk > p.n_tile);
-              if (ws_row != nullptr) {      // split-K finisher: the tile's sum over all k-ranges sits in the workspace
-                  float4* wp = reinterpret_cast<float4*>(ws_row + c0);
-#pragma unroll
-                  for (int i = 0; i < kChunk / 4; ++i) {
-                      if (c0 + 4 * i < p.n_tile) {
-                          const float4 q = __ldcg(wp + i);
-                          __stcg(wp + i, make_float4(0.f, 0.f, 0.f, 0.f));        // leave the workspace clean for the next launch
-                          r[4 * i + 0] = __float_as_uint(q.x); r[4 * i + 1] = __float_as_uint(q.y);
-                          r[4 * i + 2] = __float_as_uint(q.z); r[4 * i + 3] = __float_as_uint(q.w);
-                      }
-                  }
-              }
               if (!valid) continue;
 #pragma unroll
               for (int sub16 = 0; sub16 < kChunk / 16; ++sub16) {
@@ -638,163 +622,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
 
 // ---------------------------------------------------------------------------------
-// Split-K variant for the small-M layers (levels 3-4 of the UNet: 172-688 pixels).  There the per-tile k-loop is bound
-// by what one SM can pull through TMA (~36 B/clk: ~3.8 cycles per 128 B box row) while most SMs idle, so `ksplit` CTAs
-// share one output tile: CTA r accumulates k-iterations [r*K/S, (r+1)*K/S) in its own TMEM and adds its fp32 partial tile
-// to a global workspace (red.global.add.v4.f32, L2-resident); the CTA that arrives last on the tile's counter reads the
-// sums back, runs the normal fused epilogue and clears what it consumed, so the workspace is zero again for the next
-// launch.  (Round 1's cluster / distributed-shared-memory reduction lost to cluster launch cost and GPC-confined residency;
-// this variant needs neither.)  One tile per CTA group, four epilogue warps.
-// ---------------------------------------------------------------------------------
-template <int KC>
-__global__ void __launch_bounds__(64 + 32 * 4, 1)
-conv_igemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ ConvParams p) {
-    constexpr uint32_t kRowBytes = KC * 2;
-    constexpr uint32_t kABufBytes = kTileM * kRowBytes;
-    constexpr int kChunk = 32;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar;
-    __shared__ uint32_t tmem_base_slot;
-
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const uint32_t b_buf_bytes = (uint32_t)p.n_tile * kRowBytes;
-    const uint32_t pair_bytes = kABufBytes + b_buf_bytes;
-    const uint32_t stage_bytes = pair_bytes * (uint32_t)p.sub;
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x / p.ksplit;
-    const int krank = blockIdx.x - tile * p.ksplit;
-    const int it_begin = (int)((long)krank * p.k_iters / p.ksplit), it_end = (int)((long)(krank + 1) * p.k_iters / p.ksplit);
-    const TileCoord t = decode_tile(p, tile);
-
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tensormap(&tmA);
-        ptx::prefetch_tensormap(&tmB);
-        for (int s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
-        }
-        ptx::mbar_init(&tmem_full_bar, 1);
-        ptx::mbar_fence_init();
-        ptx::fence_proxy_async_smem();
-    }
-    if (warp == 1) {
-        ptx::tmem_alloc(&tmem_base_slot, p.tmem_cols);
-        ptx::tmem_relinquish();
-    }
-    ptx::tcgen05_fence_before();
-    __syncthreads();
-    ptx::tcgen05_fence_after();
-    const uint32_t tmem_base = tmem_base_slot;
-    ptx::grid_launch_dependents();
-
-    if (warp == 0) {
-        if (lane == 0) {
-            ptx::grid_dependency_wait();
-            uint32_t stage = 0, phase = 0;
-            const int a_c0 = t.g * p.cin_g;
-            const int b_row = t.g * p.cout_g + t.n_idx * p.n_tile;
-            for (int it0 = it_begin; it0 < it_end; it0 += p.sub) {
-                const int cnt = min(p.sub, it_end - it0);
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)cnt * (p.a_bytes + p.b_bytes));
-                for (int j = 0; j < cnt; ++j) {
-                    const int it = it0 + j;
-                    const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-                    const int dy = tap / p.kw - p.kh / 2;
-                    const int dx = tap % p.kw - p.kw / 2;
-                    uint8_t* a_dst = smem + stage * stage_bytes + j * pair_bytes;
-                    ptx::tma_load_4d(a_dst, &tmA, &full_bar[stage], a_c0 + kc * KC, t.w0 + dx, t.h0 + dy, t.b0);
-                    ptx::tma_load_2d(a_dst + kABufBytes, &tmB, &full_bar[stage], tap * p.cin_g + kc * KC, b_row);
-                }
-                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        const uint32_t idesc = ptx::make_idesc_bf16(kTileM, p.n_tile);
-        const uint32_t smem_base = ptx::smem_u32(smem);
-        uint32_t stage = 0, phase = 0;
-        for (int it0 = it_begin; it0 < it_end; it0 += p.sub) {
-            const int cnt = min(p.sub, it_end - it0);
-            ptx::mbar_wait(&full_bar[stage], phase);
-            ptx::tcgen05_fence_after();
-            if (ptx::elect_one()) {
-                const uint32_t s_addr = smem_base + stage * stage_bytes;
-                for (int j = 0; j < cnt; ++j) {
-                    const uint64_t a_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes, kRowBytes);
-                    const uint64_t b_desc = ptx::make_kmajor_desc(s_addr + j * pair_bytes + kABufBytes, kRowBytes);
-                    ptx::umma_bf16_ss(tmem_base, a_desc, b_desc, idesc, (it0 + j) > it_begin ? 1u : 0u);
-#pragma unroll
-                    for (int ks = 1; ks < KC / 16; ++ks)
-                        ptx::umma_bf16_ss_acc(tmem_base, a_desc + 2 * ks, b_desc + 2 * ks, idesc);
-                }
-                ptx::umma_commit(&empty_bar[stage]);
-            }
-            __syncwarp();
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-        }
-        if (ptx::elect_one()) ptx::umma_commit(&tmem_full_bar);
-        __syncwarp();
-    }
-
-    // ---- reduction: every k-range adds its partial tile to the workspace; the last arrival finishes the tile ----
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    __shared__ int s_last;
-    if (warp >= 2) {
-        ptx::grid_dependency_wait();
-        ptx::mbar_wait(&tmem_full_bar, 0);
-        ptx::tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const int ww = row % p.wt;
-        const int hh = (row / p.wt) % p.ht;
-        const int bb = row / (p.wt * p.ht);
-        const bool in_box = bb < p.bt;                       // rows past the pixel box hold stale operands: never published
-        float* ws_row = p.ws + ((size_t)tile * kTileM + row) * p.n_tile;
-        for (int c0 = 0; c0 < p.n_tile; c0 += kChunk) {          // tcgen05.ld is warp-collective: every lane takes part
-            uint32_t r[kChunk];
-            tmem_ld_chunk<kChunk>(taddr + c0, r, c0 + 32 > p.n_tile);
-            ptx::tmem_ld_wait();
-            if (in_box) {
-#pragma unroll
-                for (int i = 0; i < kChunk / 4; ++i)
-                    if (c0 + 4 * i < p.n_tile)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ws_row + c0 + 4 * i),
-                                     "f"(__uint_as_float(r[4 * i])), "f"(__uint_as_float(r[4 * i + 1])),
-                                     "f"(__uint_as_float(r[4 * i + 2])), "f"(__uint_as_float(r[4 * i + 3])) : "memory");
-            }
-        }
-        __threadfence();                                      // partial sums visible before the arrival below
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
-        if (threadIdx.x == 64) {
-            const int old = atomicAdd(p.ws_count + tile, 1);
-            s_last = old == p.ksplit - 1;
-            if (s_last) p.ws_count[tile] = 0;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (s_last) {
-            __threadfence();
-            const int b = t.b0 + bb, h = t.h0 + hh, w = t.w0 + ww;
-            const bool valid = in_box && (b < p.B) && (h < p.H) && (w < p.W);
-            const int ch0 = t.g * p.cout_g + t.n_idx * p.n_tile;
-            epilogue_tile<4>(p, taddr, valid, b, h, w, ch0, in_box ? ws_row : nullptr);
-        }
-    }
-
-    ptx::tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        ptx::tcgen05_fence_after();
-        ptx::tmem_dealloc(tmem_base, p.tmem_cols);
-    }
-}
-
-
-// ---------------------------------------------------------------------------------
 // 3x3 convolution, halo variant (image rows >= 16): the 9 filter taps are shifted *views* of one
 // shared-memory halo tile instead of 9 separate TMA boxes, and the weight panel stays resident.
 //
@@ -1196,40 +1023,6 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.kchunks = cin_g / KC;
     p.k_iters = p.taps * p.kchunks;
     p.n_tile = choose_n_tile(cout_g, p.m_tiles, groups, p.k_iters, KC, num_sms);
-    p.ksplit = 1;
-    {
-        // Small-M layers: consider sharing one tile between `S` CTAs (split-K, conv_igemm_splitk_kernel: workspace +
-        // arrival counter).  Same cost model as choose_n_tile plus the reduction round trip; only taken when everything
-        // still runs as one wave.  Measured in-graph on B200 (profiles/r02_splitk_ab.log): correct, but 1.2-1.8x SLOWER
-        // than the single-CTA tiles on every level 3-4 shape it selects (e.g. 2x2x43 1280->1280 1x1: 13.9 vs 8.5 us): the
-        // scattered 16 B red.global traffic and the finisher's L2 round trip cost more than the shorter k-loop saves, so
-        // it stays opt-in (DD_ENABLE_SPLITK=1).
-        static const bool no_split = getenv("DD_ENABLE_SPLITK") == nullptr;
-        auto cost = [&](int n, int S) {
-            const long ctas = (long)p.m_tiles * groups * (cout_g / n) * S;
-            const long waves = (ctas + num_sms - 1) / num_sms;
-            const double t_l2 = (128.0 + n) * KC * 2.0 / 36.0, t_mma = n * KC / 32.0;
-            const double t_iter = std::max(t_l2, t_mma) + 30.0;
-            const double red = S == 1 ? 0.0 : 2500.0 + 20.0 * n;
-            return 2500.0 + waves * (((p.k_iters + S - 1) / S) * t_iter) + 64.0 + n * 6.0 + red + (waves - 1) * 200.0;
-        };
-        const double base = cost(p.n_tile, 1);
-        double best = base * 0.8;                       // only switch for a clear predicted win
-        if (!no_split && (long)p.m_tiles * groups <= 64) {
-            for (int n = 32; n <= std::min(cout_g, 256); n += 16) {
-                if (cout_g % n) continue;
-                for (int S = 2; S <= 8 && 3 * S <= p.k_iters; ++S) {
-                    if ((long)p.m_tiles * groups * (cout_g / n) * S > num_sms) continue;
-                    const double c = cost(n, S);
-                    if (c < best) { best = c; p.n_tile = n; p.ksplit = S; }
-                }
-            }
-        }
-        if (const char* f = getenv("DD_FORCE_KSPLIT")) {                          // tuning experiments only
-            const int S = atoi(f);
-            if (S >= 1 && S <= 8 && 2 * S <= p.k_iters) p.ksplit = S;
-        }
-    }
     p.n_tiles_per_group = cout_g / p.n_tile;
     p.num_tiles = p.m_tiles * groups * p.n_tiles_per_group;
     p.fd_m_tiles = make_fastdiv(p.m_tiles); p.fd_npg = make_fastdiv(p.n_tiles_per_group);
@@ -1248,7 +1041,7 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.tmem_cols = cols;
     const int ew = choose_epi_warps(p);
     p.prefetch_res = want_residual_prefetch(p);
-    const bool staged = want_staged_epilogue(p) && p.ksplit == 1;
+    const bool staged = want_staged_epilogue(p);
     const uint32_t slabs_bytes = staged ? (uint32_t)ew * kSlabBytes : 0u;
     p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u - slabs_bytes) / stage_bytes)));
     p.stage_off = staged ? (uint32_t)p.stages * stage_bytes : 0u;
@@ -1278,48 +1071,6 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     }
 
     const size_t smem_bytes = (size_t)p.stages * stage_bytes + slabs_bytes + 1024;
-    if (p.ksplit > 1) {
-        // workspace slot of this launch: 16 slots taken round-robin, so launches that may overlap (parallel branches of the
-        // captured graph, programmatic dependent launch) never share one; every slot is all-zero between launches
-        constexpr size_t kSlotFloats = 2u << 20, kSlotTiles = 1024;
-        constexpr int kSlots = 16;
-        static float* ws_base = nullptr;
-        static int* cnt_base = nullptr;
-        static int next_slot = 0;
-        const size_t need = (size_t)p.num_tiles * kTileM * p.n_tile;
-        if (need > kSlotFloats || (size_t)p.num_tiles > kSlotTiles) p.ksplit = 1;
-        else {
-            if (ws_base == nullptr) {
-                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-                cudaStreamIsCapturing(stream, &cap);
-                DD_REQUIRE(cap == cudaStreamCaptureStatusNone, "dd_mpconv_forward: first split-K launch inside a stream capture "
-                                                               "(run the layer once eagerly before capturing)");
-                DD_CHECK_CUDA(cudaMalloc(&ws_base, kSlots * kSlotFloats * sizeof(float)));
-                DD_CHECK_CUDA(cudaMalloc(&cnt_base, kSlots * kSlotTiles * sizeof(int)));
-                DD_CHECK_CUDA(cudaMemset(ws_base, 0, kSlots * kSlotFloats * sizeof(float)));
-                DD_CHECK_CUDA(cudaMemset(cnt_base, 0, kSlots * kSlotTiles * sizeof(int)));
-            }
-            p.ws = ws_base + (size_t)next_slot * kSlotFloats;
-            p.ws_count = cnt_base + (size_t)next_slot * kSlotTiles;
-            next_slot = (next_slot + 1) % kSlots;
-        }
-    }
-    if (p.ksplit > 1) {
-        if (getenv("DD_DEBUG_CONV"))
-            fprintf(stderr, "[conv split-K] B%d %dx%d %d->%d k%d g%d: m_tiles %d n_tile %d tiles %d k_iters %d ksplit %d stages %d\n",
-                    B, H, W, Cin, Cout, p.kw, groups, p.m_tiles, p.n_tile, p.num_tiles, p.k_iters, p.ksplit, p.stages);
-        if (KC == 64) {
-            static bool done = false;
-            if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_splitk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
-            DD_CHECK_CUDA(launch_pdl(conv_igemm_splitk_kernel<64>, p.num_tiles * p.ksplit, 64 + 32 * 4, smem_bytes, stream, tmA, tmB, p));
-        } else {
-            static bool done = false;
-            if (!done) { DD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_splitk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); done = true; }
-            DD_CHECK_CUDA(launch_pdl(conv_igemm_splitk_kernel<32>, p.num_tiles * p.ksplit, 64 + 32 * 4, smem_bytes, stream, tmA, tmB, p));
-        }
-        DD_CHECK_LAUNCH();
-        return 0;
-    }
     const int grid = std::min(p.num_tiles, num_sms);
     if (getenv("DD_DEBUG_CONV"))
         fprintf(stderr, "[conv] B%d %dx%d %d->%d k%d g%d: box %dx%dx%d m_tiles %d n_tile %d tiles %d k_iters %d KC %d sub %d stages %d\n",
@@ -1393,7 +1144,6 @@ int launch_halo(ConvParams& p, const void* x, const void* w_prepped, int groups,
     p.b_block_bytes = (uint32_t)n_tile * 128u;
     const uint32_t b_total = (uint32_t)p.kchunks * 9u * p.b_block_bytes;
     p.nacc = 1;
-    p.ksplit = 1;
     p.dbg_taps = 9;
     p.dbg_nostore = getenv("DD_DBG_NOSTORE") != nullptr;
     p.nbuf = 2;

@@ -75,14 +75,20 @@ class TrainState:
         slots: Dict[str, _ParamSlot] = {}
 
         def conv_slots(p: str, blk) -> List[_ParamSlot]:
+            """Every weight of one block: its convolutions and its embedding projections.  The latter's gradients are
+            complete as soon as the block's backward has run, so they travel in the block's bucket; left to the tail
+            bucket their ~200 MB were all-reduced after the backward had ended, fully exposed."""
             out = [_ParamSlot(p + ".conv_res0.weight", blk.conv_res0.weight),
                    _ParamSlot(p + ".conv_res1.weight", blk.conv_res1.weight),
-                   _ParamSlot(p + ".conv_skip.weight", blk.conv_skip.weight)]
+                   _ParamSlot(p + ".conv_skip.weight", blk.conv_skip.weight),
+                   _ParamSlot(p + ".emb_linear.weight", blk.emb_linear.weight, gain=blk.emb_gain)]
             if blk.use_attention:
                 out += [_ParamSlot(p + ".attn_qk.weight", blk.attn_qk.weight, perm=L.WPERM_QK,
                                    head_dim=blk.channels_per_head),
                         _ParamSlot(p + ".attn_v.weight", blk.attn_v.weight),
-                        _ParamSlot(p + ".attn_proj.weight", blk.attn_proj.weight)]
+                        _ParamSlot(p + ".attn_proj.weight", blk.attn_proj.weight),
+                        _ParamSlot(p + ".emb_linear_qk.weight", blk.emb_linear_qk.weight, gain=blk.emb_gain_qk),
+                        _ParamSlot(p + ".emb_linear_v.weight", blk.emb_linear_v.weight, gain=blk.emb_gain_v)]
             return out
 
         cur: List[_ParamSlot] = [_ParamSlot("conv_out.weight", net.conv_out.weight, rows_eff=_CONV_OUT_PAD,
@@ -99,19 +105,13 @@ class TrainState:
                 if cur_bytes >= target:
                     buckets.append(cur)
                     cur, cur_bytes = [], 0
-        # tail bucket: stem + every embedding-side parameter (complete only after the whole backward)
+        # tail bucket: the first encoder blocks (whatever did not fill a bucket), the stem and the noise embedding
         cur.append(_ParamSlot("enc.conv_in.weight", net.enc["conv_in"].weight, row_stride=64))
         self.block_order: List[Tuple[str, object]] = []
         for prefix, blocks in (("enc", net.enc), ("dec", net.dec)):
             for name, blk in blocks.items():
-                if not isinstance(blk, Block):
-                    continue
-                p = f"{prefix}.{name}"
-                self.block_order.append((p, blk))
-                cur.append(_ParamSlot(p + ".emb_linear.weight", blk.emb_linear.weight, gain=blk.emb_gain))
-                if blk.use_attention:
-                    cur.append(_ParamSlot(p + ".emb_linear_qk.weight", blk.emb_linear_qk.weight, gain=blk.emb_gain_qk))
-                    cur.append(_ParamSlot(p + ".emb_linear_v.weight", blk.emb_linear_v.weight, gain=blk.emb_gain_v))
+                if isinstance(blk, Block):
+                    self.block_order.append((f"{prefix}.{name}", blk))
         cur.append(_ParamSlot("emb_noise.weight", net.emb_noise.weight))
         buckets.append(cur)
         self.buckets = buckets
@@ -234,8 +234,19 @@ class TrainState:
                                 rowscale=rowscale[off:off + O], groups=conv.groups, normalize=True))
             off += O
         descs, max_o, max_cols = ops.make_affine_bwd_descs(entries, dev)
+        # descriptors of the blocks of each gradient bucket: a contiguous range of the (forward-ordered) table, because a
+        # bucket is a contiguous run of the backward order and the last encoder blocks precede the first decoder blocks
+        bucket_of = {s.name: i for i, b in enumerate(self.buckets) for s in b}
+        ranges: List[Optional[Tuple[int, int]]] = [None] * len(self.buckets)
+        for j, key in enumerate(keys):
+            pfx, tag = key.rsplit(".", 1)
+            i = bucket_of[pfx + {"c": ".emb_linear.weight", "c_qk": ".emb_linear_qk.weight", "c_v": ".emb_linear_v.weight"}[tag]]
+            lo, n = ranges[i] if ranges[i] is not None else (j, 0)
+            if lo + n != j:
+                raise RuntimeError("embedding descriptors of a gradient bucket are not contiguous")
+            ranges[i] = (lo, n + 1)
         st = dict(fwd=st_fwd, dc_flat=dc_flat, douts=douts, descs=descs, n=len(entries), max_o=max_o, max_cols=max_cols,
-                  rowscale=rowscale, entries=entries)
+                  rowscale=rowscale, entries=entries, ranges=ranges)
         self.affine_bwd[B] = st
         return st
 
@@ -376,6 +387,9 @@ def train_backward(net, plan, saved: dict, dD: Tensor, accumulate: bool = False,
             i = slot_bucket[n]
             pending[i] -= 1
             if pending[i] == 0:
+                if ab["ranges"][i] is not None:            # weight gradients of the bucket's embedding projections
+                    lo, cnt_e = ab["ranges"][i]
+                    ops.emb_affine_bwd(ab["descs"], cnt_e, ab["max_o"], ab["max_cols"], saved["emb"], None, first=lo)
                 buf, cnt, rows = ts.wbwd[i][accumulate]
                 ops.weight_prep_bwd(buf, cnt, rows)
                 if bucket_done is not None:
@@ -395,13 +409,14 @@ def train_backward(net, plan, saved: dict, dD: Tensor, accumulate: bool = False,
             dxv = ops.mpconv(dv, WT[p + ".attn_v"], 1)
             wgrad(p + ".attn_v", sv["x2"], dv, 1)
             gout = ops.attn_in_bwd(gout, ca_a, dxv, dxs, sv["x2"], cvec[p + ".c_qk"], dcv[p + ".c_qk"])
-            done += [p + ".attn_proj.weight", p + ".attn_qk.weight", p + ".attn_v.weight"]
+            done += [p + ".attn_proj.weight", p + ".attn_qk.weight", p + ".attn_v.weight",
+                     p + ".emb_linear_qk.weight", p + ".emb_linear_v.weight"]     # their dc rows are complete
         dy0 = ops.mpconv(gout, WT[p + ".conv_res1"], 3, g8)
         wgrad(p + ".conv_res1", sv["y0"], gout, 3, g8, cb_r)
         dpre = ops.silu_scale_bwd(dy0, cb_r, sv["pre"], cvec[p + ".c"], dcv[p + ".c"])
         ds = ops.mpconv(dpre, WT[p + ".conv_res0"], 3, g8)
         wgrad(p + ".conv_res0", sv["s"], dpre, 3, g8)
-        done += [p + ".conv_res1.weight", p + ".conv_res0.weight"]
+        done += [p + ".conv_res1.weight", p + ".conv_res0.weight", p + ".emb_linear.weight"]
         sv["_done"] = done
         return gout, ds
 
@@ -457,7 +472,7 @@ def train_backward(net, plan, saved: dict, dD: Tensor, accumulate: bool = False,
     # ---- embedding side ----
     emb = saved["emb"]
     demb = torch.zeros_like(emb)
-    ops.emb_affine_bwd(ab["descs"], ab["n"], ab["max_o"], ab["max_cols"], emb, demb)
+    ops.emb_affine_bwd(ab["descs"], ab["n"], ab["max_o"], ab["max_cols"], None, demb)      # stage 2: every row scale exists by now
     aux = net._aux()
     s_noise = slots["emb_noise.weight"]
     _, dlabel = ops.noise_embedding_bwd(saved["sigma"], aux["emb_freqs"], aux["emb_phases"], net.emb_noise.weight.detach(),

@@ -586,10 +586,17 @@ def make_affine_bwd_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int,
     return buf, max_o, max_cols
 
 
-def emb_affine_bwd(descs: Tensor, n: int, max_o: int, max_cols: int, emb: Tensor, demb: Tensor) -> None:
-    B, cemb = emb.shape
-    L.check(L.load().dd_emb_affine_bwd(L.ptr(descs), n, max_o, max_cols, L.ptr(emb), L.ptr(demb), B, cemb, L.stream_ptr()))
-    _count(2)
+def emb_affine_bwd(descs: Tensor, n: int, max_o: int, max_cols: int, emb: Optional[Tensor], demb: Optional[Tensor],
+                   first: int = 0, B: int = 0, cemb: int = 0) -> None:
+    """Stage 1 (emb given: weight gradients) and / or stage 2 (demb given: embedding gradient) over descriptors
+    [first, first + n) of the table."""
+    if emb is not None:
+        B, cemb = emb.shape
+    elif demb is not None:
+        B, cemb = demb.shape
+    base = descs.data_ptr() + first * C.sizeof(L.AffineBwdDesc)
+    L.check(L.load().dd_emb_affine_bwd(base, n, max_o, max_cols, L.ptr(emb), L.ptr(demb), B, cemb, L.stream_ptr()))
+    _count((emb is not None) + (demb is not None))
 
 
 def noise_embedding_bwd(sigma: Tensor, freqs: Tensor, phases: Tensor, w_noise: Tensor, label_emb: Tensor,

@@ -306,8 +306,11 @@ DD_API int dd_attn_in_bwd(const void* g3, float ca, const void* dxv, const void*
 DD_API int dd_attention_bwd(const void* qk, const void* v, const void* a_raw, const void* d_a, void* dqk, void* dv,
                             float* stats_ws, int B, int N, int heads, int head_dim, void* stream);
 
-/* emb_linear* backward (batched like dd_emb_affine): dweff_j[o][i] = sum_b dout_j[b][o]*emb[b][g*I+i];
- * demb[b][g*I+i] += sum_o dout_j[b][o]*w_eff_j[o][i].  rowscale: fp32 [O] scratch.                           */
+/* emb_linear* backward (batched like dd_emb_affine), two stages over a descriptor array:
+ *   stage 1 (emb != NULL):  dweff_j[o][i] = sum_b dout_j[b][o]*emb[b][g*I+i]  and the row scales (rowscale: fp32 [O] scratch);
+ *   stage 2 (demb != NULL): demb[b][g*I+i] += sum_o dout_j[b][o]*w_eff_j[o][i]   (needs stage 1 of the same descriptors).
+ * Either pointer may be NULL to run one stage only: the train step runs stage 1 per gradient bucket (a block's embedding
+ * weights travel with the block's bucket) and stage 2 once at the end.                                                  */
 typedef struct dd_affine_bwd_desc {
     const float* w;      /* [O][I] fp32 */
     const float* gain;   /* device scalar or NULL */

@@ -255,9 +255,12 @@ def test_embeddings_vs_oracle(dev):
     assert rel_err(f, uo.mp_fourier(sigma.log() / 4, sd["emb_fourier.freqs"], sd["emb_fourier.phases"])) < FP32
 
 
-@pytest.mark.parametrize("B,H,W,heads", [(2, 4, 86, 16), (2, 2, 43, 20), (1, 8, 8, 12), (1, 4, 4, 2), (1, 1, 1, 1)])
+@pytest.mark.parametrize("B,H,W,heads", [(2, 4, 86, 16), (2, 2, 43, 20), (1, 8, 8, 12), (1, 4, 4, 2), (1, 1, 1, 1),
+                                         (1, 20, 30, 2), (1, 8, 94, 2), (1, 16, 94, 1)])
 def test_attention_vs_oracle(dev, B, H, W, heads):
-    """Sequence lengths of the 45 s latent (344, 86), of config 1 (64, 16) and the degenerate N=1."""
+    """Sequence lengths of the 45 s latent (344, 86), of config 1 (64, 16), the degenerate N=1, the largest resident
+    sequence class (600 <= 640 tokens) and sequences streamed through shared memory in 512-key chunks (752, 1504 tokens:
+    the seamless-loop frame of samples longer than 45 s)."""
     from dualdiffusion_b200 import ops
     gen = torch.Generator().manual_seed(19 + H * W)
     C = heads * 64

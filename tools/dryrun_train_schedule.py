@@ -78,7 +78,7 @@ stubs = dict(
     enc_grad_combine=lambda dx0, down, dskip, x_prev, clip, shape: E(*shape) if (dskip is None or tuple(dskip.shape) == tuple(shape)) and tuple(dx0.shape) == ((shape[0], shape[1] // 2, shape[2] // 2, shape[3]) if down else tuple(shape)) else 1 / 0,
     attn_in_bwd=lambda g3, ca, dxv, dxs, x2, cqk, dc: torch.zeros_like(x2) if g3.shape == dxv.shape == dxs.shape == x2.shape else 1 / 0,
     attention_bwd=lambda qk, v, a, da, heads, hd=64: (torch.zeros_like(qk), torch.zeros_like(v)),
-    emb_affine_bwd=lambda *a: None,
+    emb_affine_bwd=lambda *a, **k: None,
     head_grad=lambda dD, s, sd, xr, cpad=32: E(dD.shape[0], dD.shape[2], dD.shape[3], cpad),
 )
 

@@ -1,0 +1,14 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+echo "== reference arm"; (time python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err); tail -c 400 gpurun_out/r02_bench_reference_arm.json; echo
+echo "== full bench"; (time python bench.py > gpurun_out/r02_bench_n1_final.json 2> gpurun_out/r02_bench_n1_final.err); python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_n1_final.json'))
+print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['levels_0_2'], d['clocks'])
+for k in ['train_step','dae_decode','ddec_forward']: print(k, d[k]['value'], d[k].get('roofline',{}).get('frac'))
+print('gpu_eager', d['gpu_eager']['sampler_step'], d['gpu_eager'].get('train_step'))
+print('cpu', d['cpu_baseline'])
+print('optim', d['optim_step']['ms'], d['optim_step']['train_step_with_optimizer']['value'])
+print('secondary', json.dumps(d['secondary'])[:600])
+"
+echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
