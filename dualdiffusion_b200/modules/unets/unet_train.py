@@ -387,7 +387,8 @@ def train_backward(net, plan, saved: dict, dD: Tensor, accumulate: bool = False,
             i = slot_bucket[n]
             pending[i] -= 1
             if pending[i] == 0:
-                if ab["ranges"][i] is not None:            # weight gradients of the bucket's embedding projections
+                if ab["ranges"][i] is not None and i != len(ts.buckets) - 1:      # weight gradients of the bucket's embedding
+                    # projections (the tail bucket's ran before the embedding-vector gradient below, which needs them)
                     lo, cnt_e = ab["ranges"][i]
                     ops.emb_affine_bwd(ab["descs"], cnt_e, ab["max_o"], ab["max_cols"], saved["emb"], None, first=lo)
                 buf, cnt, rows = ts.wbwd[i][accumulate]
@@ -472,7 +473,10 @@ def train_backward(net, plan, saved: dict, dD: Tensor, accumulate: bool = False,
     # ---- embedding side ----
     emb = saved["emb"]
     demb = torch.zeros_like(emb)
-    ops.emb_affine_bwd(ab["descs"], ab["n"], ab["max_o"], ab["max_cols"], None, demb)      # stage 2: every row scale exists by now
+    if ab["ranges"][-1] is not None:            # stage 1 of the blocks left in the tail bucket (the first encoder blocks)
+        lo, cnt_e = ab["ranges"][-1]
+        ops.emb_affine_bwd(ab["descs"], cnt_e, ab["max_o"], ab["max_cols"], emb, None, first=lo)
+    ops.emb_affine_bwd(ab["descs"], ab["n"], ab["max_o"], ab["max_cols"], None, demb)      # stage 2: every row scale exists now
     aux = net._aux()
     s_noise = slots["emb_noise.weight"]
     _, dlabel = ops.noise_embedding_bwd(saved["sigma"], aux["emb_freqs"], aux["emb_phases"], net.emb_noise.weight.detach(),
