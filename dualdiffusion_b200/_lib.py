@@ -35,7 +35,7 @@ class WbwdDesc(C.Structure):
     _fields_ = [("w", c_void_p), ("dweff", c_void_p), ("dw", c_void_p), ("gain", c_void_p), ("dgain", c_void_p),
                 ("gain_host", c_float), ("O", c_int), ("I_g", c_int), ("taps", c_int), ("normalize", c_int),
                 ("perm", c_int), ("head_dim", c_int), ("row_stride", c_int), ("accumulate", c_int),
-                ("row_begin", c_int)]
+                ("row_begin", c_int), ("t_cout_g", c_int)]
 
 
 class WprepDesc(C.Structure):

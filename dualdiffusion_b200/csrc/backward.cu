@@ -196,14 +196,23 @@ __global__ void weight_prep_bwd_kernel(const dd_wbwd_desc* __restrict__ descs, i
         o_src = (rem & 1) * (d.O / 2) + head * d.head_dim + (rem >> 1);
     }
     const float* w = d.w + (size_t)o * f;                       // [i][tap]
-    const float* g = d.dweff + (size_t)o_src * d.row_stride;    // [tap][i]
     float* dw = d.dw + (size_t)o * f;
     const float gain = d.gain_host * (d.gain ? *d.gain : 1.f);
+    // dL/dW_eff of (row o, tap, i): [o][tap][i], or for an operand-swapped wgrad [group*I_g + i][taps-1-tap][o % cout_g]
+    const float* g = d.dweff + (size_t)o_src * d.row_stride;
+    size_t s_i = 1, s_tap = (size_t)d.I_g;
+    if (d.t_cout_g > 0) {
+        const int grp = o / d.t_cout_g;
+        const size_t row_t = (size_t)d.taps * d.t_cout_g;
+        g = d.dweff + (size_t)grp * d.I_g * row_t + (size_t)(d.taps - 1) * d.t_cout_g + (o - grp * d.t_cout_g);
+        s_i = row_t;
+        s_tap = (size_t)0 - (size_t)d.t_cout_g;                 // (unsigned wrap: taps run backwards)
+    }
 
     float ss = 0.f, gw = 0.f;
     for (int j = threadIdx.x; j < f; j += blockDim.x) {         // j = i*taps + tap (parameter order)
         const int i = j / d.taps, tap = j - i * d.taps;
-        const float wv = w[j], gv = g[tap * d.I_g + i];
+        const float wv = w[j], gv = g[tap * s_tap + i * s_i];
         ss += wv * wv;
         gw += gv * wv;
     }
@@ -224,7 +233,7 @@ __global__ void weight_prep_bwd_kernel(const dd_wbwd_desc* __restrict__ descs, i
     }
     for (int j = threadIdx.x; j < f; j += blockDim.x) {
         const int i = j / d.taps, tap = j - i * d.taps;
-        const float v = a * g[tap * d.I_g + i] - b * w[j];
+        const float v = a * g[tap * s_tap + i * s_i] - b * w[j];
         dw[j] = d.accumulate ? dw[j] + v : v;
     }
     if (d.dgain && threadIdx.x == 0) atomicAdd(d.dgain, dgain * d.gain_host);

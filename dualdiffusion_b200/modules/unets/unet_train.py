@@ -38,9 +38,17 @@ def _mp_sum_coeffs(t: float) -> Tuple[float, float]:
 class _ParamSlot:
     """One trainable tensor: where its effective-weight gradient and its parameter gradient live."""
     __slots__ = ("name", "param", "O", "I_g", "taps", "row_stride", "rows_eff", "normalize", "perm", "head_dim",
-                 "gain", "eff_off", "grad_off", "dweff", "grad")
+                 "gain", "eff_off", "grad_off", "dweff", "grad", "t_cout_g")
 
     def __init__(self, name, param, *, row_stride=0, rows_eff=0, perm=0, head_dim=0, gain=None, normalize=True):
+        # Grouped layers with more input than output channels per group (conv_res1: I_g = 2 * cout_g): the weight
+        # gradient is computed with the operands exchanged (M = input channels), so that a 128-row MMA tile straddles
+        # half as many groups of the block diagonal (twice the useful work per issued MMA); the gradient then lands
+        # transposed and tap-reversed, [groups*I_g][taps][cout_g], which dd_weight_prep_bwd reads through t_cout_g.
+        groups = getattr(param, "conv_groups", 1)
+        cout_g = param.shape[0] // groups
+        self.t_cout_g = cout_g if (groups > 1 and param.ndim == 4 and param.shape[1] > cout_g and cout_g < 128
+                                   and cout_g % 32 == 0) else 0
         self.name, self.param = name, param
         self.O, self.I_g = param.shape[0], param.shape[1]
         taps = 1
@@ -94,7 +102,8 @@ class TrainState:
         cur: List[_ParamSlot] = [_ParamSlot("conv_out.weight", net.conv_out.weight, rows_eff=_CONV_OUT_PAD,
                                             gain=net.out_gain)]
         cur_bytes = 0
-        target = 96 << 20       # ~96 MB of fp32 gradients per bucket: large enough to run NCCL at bandwidth
+        target = 64 << 20       # >= 64 MB of fp32 gradients per bucket: still at NVLink bandwidth, and the buckets that
+                                # finish last (whose all-reduce is what stays exposed) are smaller
         for prefix, blocks in (("dec", net.dec), ("enc", net.enc)):
             for name, blk in reversed(list(blocks.items())):
                 if not isinstance(blk, Block):
@@ -153,7 +162,8 @@ class TrainState:
                                         gain=None if gi is None else plan.gains_f32[gi:gi + 1],
                                         dgain=None if gi is None else self.dgains[gi:gi + 1], gain_host=1.0,
                                         O=s.O, I_g=s.I_g, taps=s.taps, normalize=s.normalize, perm=s.perm,
-                                        head_dim=s.head_dim, row_stride=s.row_stride, accumulate=acc))
+                                        head_dim=s.head_dim, row_stride=s.row_stride, accumulate=acc,
+                                        t_cout_g=s.t_cout_g))
                 buf, rows = ops.make_wbwd_descs(entries, dev)
                 variants[acc] = (buf, len(entries), rows)
             self.wbwd.append(variants)
@@ -369,7 +379,10 @@ def train_backward(net, plan, saved: dict, dD: Tensor, accumulate: bool = False,
 
     def wgrad(key: str, x: Tensor, dy: Tensor, k: int, groups: int = 1, scale: float = 1.0) -> None:
         s = slots[key + ".weight"]
-        ops.mpconv_wgrad(x, dy, k, groups, scale, out=s.dweff)
+        if s.t_cout_g:      # operands exchanged: [Cin][taps][cout_g], taps reversed (see _ParamSlot)
+            ops.mpconv_wgrad(dy, x, k, groups, scale, out=s.dweff.view(groups * s.I_g, s.taps * s.t_cout_g))
+        else:
+            ops.mpconv_wgrad(x, dy, k, groups, scale, out=s.dweff)
 
     slot_bucket = {}
     for i, b in enumerate(ts.buckets):

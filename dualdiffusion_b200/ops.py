@@ -426,14 +426,14 @@ def weight_transpose_batched(descs: Tensor, n: int, total_tiles: int) -> None:
 
 def make_wbwd_descs(entries: Sequence[dict], device) -> Tuple[Tensor, int]:
     """Pack dd_wbwd_desc records (dicts with w, dweff, dw, gain, dgain, gain_host, O, I_g, taps, normalize, perm,
-    head_dim, row_stride, accumulate) into a device buffer; returns (buffer, total_rows)."""
+    head_dim, row_stride, accumulate, t_cout_g) into a device buffer; returns (buffer, total_rows)."""
     arr = (L.WbwdDesc * len(entries))()
     rows = 0
     for i, e in enumerate(entries):
         arr[i] = L.WbwdDesc(L.ptr(e["w"]), L.ptr(e["dweff"]), L.ptr(e["dw"]), L.ptr(e.get("gain")), L.ptr(e.get("dgain")),
                             e.get("gain_host", 1.0), e["O"], e["I_g"], e["taps"], int(e.get("normalize", False)),
                             e.get("perm", 0), e.get("head_dim", 0), e.get("row_stride", 0) or e["I_g"] * e["taps"],
-                            int(e.get("accumulate", False)), rows)
+                            int(e.get("accumulate", False)), rows, int(e.get("t_cout_g", 0)))
         rows += e["O"]
     buf = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
     return buf, rows

@@ -280,6 +280,10 @@ typedef struct dd_wbwd_desc {
     float gain_host;
     int O, I_g, taps, normalize, perm, head_dim, row_stride, accumulate;
     int row_begin;       /* exclusive prefix sum of O over the descriptor array */
+    int t_cout_g;        /* 0: dweff as above.  > 0 (= O / groups): dweff holds the transposed, tap-reversed gradient
+                          * [groups*I_g][taps][t_cout_g] that dd_mpconv_wgrad produces when called with x and dy exchanged
+                          * (M = input channels): used for grouped layers with I_g > O/groups, where the 128-row MMA tile
+                          * then straddles half as many groups of the block diagonal */
 } dd_wbwd_desc;
 DD_API int dd_weight_prep_bwd(const dd_wbwd_desc* descs_dev, int n_descs, int total_rows, void* stream);
 
