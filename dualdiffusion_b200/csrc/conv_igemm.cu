@@ -245,6 +245,37 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
             }
 }
 
+// Plain epilogue (DD_EPI_NONE, one output): accumulator -> bf16 -> global and nothing else.  The general epilogue_tile
+// re-tests its modes and re-derives its addresses for every 16 columns: 147 instructions per 32 columns, a third of them
+// register copies of its software pipeline (ncu source page, profiles/r02_ncu_igemm_l0_summary.csv: 71 % of the kernel's
+// instructions on the level-0 1x1 layer), which made the epilogue warps the limiter of the 1x1 convolutions.  Here two
+// 32-column loads are in flight per iteration and a 32-column group costs ~40 instructions.
+__device__ __forceinline__ void store_bf16x16_u(__nv_bfloat16* dst, const uint32_t* r) {
+    uint4* op = reinterpret_cast<uint4*>(dst);
+    op[0] = make_uint4(pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3])),
+                       pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7])));
+    op[1] = make_uint4(pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9])), pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11])),
+                       pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])), pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15])));
+}
+__device__ __forceinline__ void epilogue_tile_plain(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
+                                                    int ch0) {
+    __nv_bfloat16* dst = p.out + (((size_t)b * p.H + h) * p.W + w) * p.Cout + ch0;
+    const int n = p.n_tile;                       // a multiple of 16
+    for (int c0 = 0; c0 < n; c0 += 64) {
+        uint32_t r0[32], r1[32];
+        const int rem = n - c0;                   // >= 16
+        tmem_ld_chunk<32>(taddr + c0, r0, rem < 32);
+        if (rem > 32) tmem_ld_chunk<32>(taddr + c0 + 32, r1, rem < 64);
+        ptx::tmem_ld_wait();
+        if (valid) {
+            store_bf16x16_u(dst + c0, r0);
+            if (rem >= 32) store_bf16x16_u(dst + c0 + 16, r0 + 16);
+            if (rem > 32) store_bf16x16_u(dst + c0 + 32, r1);
+            if (rem >= 64) store_bf16x16_u(dst + c0 + 48, r1 + 16);
+        }
+    }
+}
+
 // The fused residual epilogues are bound by memory-level parallelism, not by bandwidth: a warp has only the 2-4 KB
 // of residual it is about to consume in flight, and with ~1 us of loaded HBM latency 8-12 warps x 2-4 KB per SM is what
 // Little's law gives for the measured ~2.5 TB/s (profiles/r01_ncu_epi_variants_summary.csv: DRAM 40 %, L2 20 %, tensor
@@ -578,6 +609,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int group = (warp - 2) >> 2, ngroups = EW / 4;
         const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;           // row of the 128-row tile == box-linear pixel index
+        const bool plain = EW == 4 && p.epi == DD_EPI_NONE && p.epi2 == DD_EPI2_NONE && p.nacc == 1 && !p.dbg_nostore &&
+                           p.stage_off == 0;
         const int ww = row % p.wt;
         const int hh = (row / p.wt) % p.ht;
         const int bb = row / (p.wt * p.ht);
@@ -599,7 +632,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
-            if (p.stage_off) {
+            if (plain) {
+                epilogue_tile_plain(p, taddr, valid, b, h, w, ch0);
+            } else if (p.stage_off) {
                 const uint32_t slab = ptx::smem_u32(smem) + p.stage_off + (uint32_t)(warp - 2) * 4096u;
                 epilogue_tile_staged<EW>(p, taddr, valid ? (b * p.H + h) * p.W + w : -1, valid ? b : 0, ch0, slab, lane);
             } else {
