@@ -245,35 +245,84 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
             }
 }
 
-// Plain epilogue (DD_EPI_NONE, one output): accumulator -> bf16 -> global and nothing else.  The general epilogue_tile
-// re-tests its modes and re-derives its addresses for every 16 columns: 147 instructions per 32 columns, a third of them
-// register copies of its software pipeline (ncu source page, profiles/r02_ncu_igemm_l0_summary.csv: 71 % of the kernel's
-// instructions on the level-0 1x1 layer), which made the epilogue warps the limiter of the 1x1 convolutions.  Here two
-// 32-column loads are in flight per iteration and a 32-column group costs ~40 instructions.
-__device__ __forceinline__ void store_bf16x16_u(__nv_bfloat16* dst, const uint32_t* r) {
-    uint4* op = reinterpret_cast<uint4*>(dst);
-    op[0] = make_uint4(pack_bf16x2(__uint_as_float(r[0]), __uint_as_float(r[1])), pack_bf16x2(__uint_as_float(r[2]), __uint_as_float(r[3])),
-                       pack_bf16x2(__uint_as_float(r[4]), __uint_as_float(r[5])), pack_bf16x2(__uint_as_float(r[6]), __uint_as_float(r[7])));
-    op[1] = make_uint4(pack_bf16x2(__uint_as_float(r[8]), __uint_as_float(r[9])), pack_bf16x2(__uint_as_float(r[10]), __uint_as_float(r[11])),
-                       pack_bf16x2(__uint_as_float(r[12]), __uint_as_float(r[13])), pack_bf16x2(__uint_as_float(r[14]), __uint_as_float(r[15])));
-}
-__device__ __forceinline__ void epilogue_tile_plain(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
-                                                    int ch0) {
-    __nv_bfloat16* dst = p.out + (((size_t)b * p.H + h) * p.W + w) * p.Cout + ch0;
-    const int n = p.n_tile;                       // a multiple of 16
-    for (int c0 = 0; c0 < n; c0 += 64) {
-        uint32_t r0[32], r1[32];
-        const int rem = n - c0;                   // >= 16
-        tmem_ld_chunk<32>(taddr + c0, r0, rem < 32);
-        if (rem > 32) tmem_ld_chunk<32>(taddr + c0 + 32, r1, rem < 64);
-        ptx::tmem_ld_wait();
-        if (valid) {
-            store_bf16x16_u(dst + c0, r0);
-            if (rem >= 32) store_bf16x16_u(dst + c0 + 16, r0 + 16);
-            if (rem > 32) store_bf16x16_u(dst + c0 + 32, r1);
-            if (rem >= 64) store_bf16x16_u(dst + c0 + 48, r1 + 16);
+// Lean single-output epilogues, one per mode (compile-time): accumulator -> fused glue -> bf16 -> global and nothing else.
+// The general epilogue_tile re-tests its modes and re-derives its addresses for every 16 columns: 147 instructions per 32
+// columns, a third of them register copies of its software pipeline (ncu source page of the level-0 1x1 layer: 71 % of the
+// kernel's instruction stream), which made the epilogue warps the limiter.  Here two 16-column loads are in flight per
+// iteration, the row's addresses are formed once, and a 32-column group costs ~40 instructions plus the mode's arithmetic.
+template <int MODE>
+__device__ __forceinline__ void lean_group16(const ConvParams& p, const uint32_t (&r)[16], __nv_bfloat16* dst,
+                                             const float* sc, const __nv_bfloat16* res) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+    if constexpr (MODE == DD_EPI_SCALE_SILU) {
+        const float4* s4 = reinterpret_cast<const float4*>(sc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 q = __ldg(s4 + i);
+            v[4 * i + 0] = mp_silu_fast(v[4 * i + 0] * q.x);
+            v[4 * i + 1] = mp_silu_fast(v[4 * i + 1] * q.y);
+            v[4 * i + 2] = mp_silu_fast(v[4 * i + 2] * q.z);
+            v[4 * i + 3] = mp_silu_fast(v[4 * i + 3] * q.w);
+        }
+    } else if constexpr (MODE == DD_EPI_RESIDUAL) {
+        const uint4* rp = reinterpret_cast<const uint4*>(res);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const uint4 q = __ldg(rp + i);
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(u[j]);
+                const float a0 = p.alpha * v[8 * i + 2 * j + 0] + p.beta * f.x;
+                const float a1 = p.alpha * v[8 * i + 2 * j + 1] + p.beta * f.y;
+                v[8 * i + 2 * j + 0] = fminf(fmaxf(a0, -p.clip), p.clip);
+                v[8 * i + 2 * j + 1] = fminf(fmaxf(a1, -p.clip), p.clip);
+            }
         }
     }
+    store_bf16x16(dst, v);
+}
+template <int MODE, bool PAIR>       // PAIR: two 16-column loads in flight (the 4-warp kernels have the registers for it)
+__device__ __forceinline__ void epilogue_tile_lean(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
+                                                   int ch0) {
+    const size_t pix = ((size_t)b * p.H + h) * p.W + w;
+    __nv_bfloat16* dst = p.out + pix * p.Cout + ch0;
+    const float* sc = MODE == DD_EPI_SCALE_SILU ? p.scale + (size_t)b * p.Cout + ch0 : nullptr;
+    const __nv_bfloat16* res = MODE == DD_EPI_RESIDUAL ? p.residual + pix * p.Cout + ch0 : nullptr;
+    const int n = p.n_tile;                       // a multiple of 16
+    if constexpr (PAIR) {
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            uint32_t r0[16], r1[16];
+            const bool two = c0 + 16 < n;
+            ptx::tmem_ld_32x16(taddr + c0, r0);
+            if (two) ptx::tmem_ld_32x16(taddr + c0 + 16, r1);
+            ptx::tmem_ld_wait();
+            if (valid) {
+                lean_group16<MODE>(p, r0, dst + c0, sc + c0, res + c0);
+                if (two) lean_group16<MODE>(p, r1, dst + c0 + 16, sc + c0 + 16, res + c0 + 16);
+            }
+        }
+    } else {
+        for (int c0 = 0; c0 < n; c0 += 16) {
+            uint32_t r0[16];
+            ptx::tmem_ld_32x16(taddr + c0, r0);
+            ptx::tmem_ld_wait();
+            if (valid) lean_group16<MODE>(p, r0, dst + c0, sc + c0, res + c0);
+        }
+    }
+}
+// mode dispatch, once per tile; false = not a lean case (second output, head, experiments): the caller takes the general path
+template <int EW>
+__device__ __forceinline__ bool epilogue_tile_lean_any(const ConvParams& p, uint32_t taddr, bool valid, int b, int h, int w,
+                                                       int ch0) {
+    if (p.epi2 != DD_EPI2_NONE || p.nacc != 1 || p.dbg_nostore || p.stage_off != 0) return false;
+    if (p.epi == DD_EPI_NONE) epilogue_tile_lean<DD_EPI_NONE, EW == 4>(p, taddr, valid, b, h, w, ch0);
+    else if (p.epi == DD_EPI_SCALE_SILU) epilogue_tile_lean<DD_EPI_SCALE_SILU, EW == 4>(p, taddr, valid, b, h, w, ch0);
+    else if (p.epi == DD_EPI_RESIDUAL) epilogue_tile_lean<DD_EPI_RESIDUAL, EW == 4>(p, taddr, valid, b, h, w, ch0);
+    else return false;
+    return true;
 }
 
 // The fused residual epilogues are bound by memory-level parallelism, not by bandwidth: a warp has only the 2-4 KB
@@ -609,8 +658,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int group = (warp - 2) >> 2, ngroups = EW / 4;
         const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;           // row of the 128-row tile == box-linear pixel index
-        const bool plain = EW == 4 && p.epi == DD_EPI_NONE && p.epi2 == DD_EPI2_NONE && p.nacc == 1 && !p.dbg_nostore &&
-                           p.stage_off == 0;
         const int ww = row % p.wt;
         const int hh = (row / p.wt) % p.ht;
         const int bb = row / (p.wt * p.ht);
@@ -632,8 +679,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
-            if (plain) {
-                epilogue_tile_plain(p, taddr, valid, b, h, w, ch0);
+            if (epilogue_tile_lean_any<EW>(p, taddr, valid, b, h, w, ch0)) {
             } else if (p.stage_off) {
                 const uint32_t slab = ptx::smem_u32(smem) + p.stage_off + (uint32_t)(warp - 2) * 4096u;
                 epilogue_tile_staged<EW>(p, taddr, valid ? (b * p.H + h) * p.W + w : -1, valid ? b : 0, ch0, slab, lane);
@@ -911,7 +957,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::tcgen05_fence_after();
             if (quad == 0 && lane == 0) trace_stamp<TRACE>(p, kTrEpiFull, local);
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)(p.n_tile * p.nacc);
-            if (p.stage_off) {
+            if (epilogue_tile_lean_any<EW>(p, taddr, valid, b, h, w, ch0)) {
+            } else if (p.stage_off) {
                 const uint32_t slab = ptx::smem_u32(smem) + p.stage_off + (uint32_t)(warp - 2) * 4096u;
                 epilogue_tile_staged<EW>(p, taddr, valid ? (b * p.H + h) * p.W + w : -1, valid ? b : 0, ch0, slab, lane);
             } else {
