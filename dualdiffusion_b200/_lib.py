@@ -215,13 +215,25 @@ def check(status: int) -> None:
         raise RuntimeError(f"dualdiffusion_b200 C-ABI call failed ({status}): {msg}")
 
 
+_last_device: Optional[torch.device] = None      # device of the tensor most recently passed through ptr()
+
+
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    global _last_device
     if t is None:
         return None
+    if t.is_cuda:
+        _last_device = t.device
     return t.data_ptr()
 
 
 def stream_ptr() -> int:
+    """Current stream of the current device.  Every wrapper passes its tensors through ptr() before it asks for the
+    stream (argument order), and the C ABI never switches devices: tensors on another device than the current one would
+    be launched into the wrong context, so that case fails here, loudly."""
+    if _last_device is not None and _last_device.index is not None and _last_device.index != torch.cuda.current_device():
+        raise RuntimeError(f"dualdiffusion_b200: tensors live on {_last_device} but the current CUDA device is "
+                           f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device(...) / set_device")
     return torch.cuda.current_stream().cuda_stream
 
 
