@@ -81,7 +81,8 @@ class GradAllReducer:
         if on_gpu:
             main = torch.cuda.current_stream(ts.grad_flat.device)
             if self.stream is None:
-                self.stream = torch.cuda.Stream(device=ts.grad_flat.device)
+                # high priority: the all-reduce kernels of a finished bucket should not queue behind the backward's grids
+                self.stream = torch.cuda.Stream(device=ts.grad_flat.device, priority=-1)
 
         def bucket_done(i: int) -> None:
             if not exchange:
