@@ -289,7 +289,8 @@ def bench_format(device) -> dict:
             "encode_plus_decode": {"value": B / (t_enc + t_dec), "unit": "stereo samples/s"}}
 
 
-def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3, fused_optimizer: bool = False) -> dict:
+def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3, fused_optimizer: bool = False,
+                micro_steps: int = 1) -> dict:
     """BASELINE.json configs[3]: UNet train step forward + backward (bf16 tensor-core compute, fp32 master parameters and
     gradients), device batch 4 of the 45 s latent per GPU, gradients all-reduced (mean) over NCCL overlapped with the
     backward when world > 1.  Loss = unet_trainer.py:259-280.  With `fused_optimizer` the step also runs the optimizer-side
@@ -324,18 +325,23 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3, fused
         opt.attach_module(net)
         opt.attach_emas([[p.detach().clone() for p in plist] for _ in range(2)], [0.9999, 0.99999], [0.9999, None])
 
+    import contextlib
+
     def step():
         net.zero_grad(set_to_none=True)
         # an optimizer step changes every weight: the per-step weight preparation (weight-norm inside the forward,
         # mp_tools.py:359-364) and the dgrad transposes are part of the train step
         if net._plan is not None and getattr(net._plan, "train_state", None) is not None:
             net._plan.train_state._prep_sig = None
-        emb = net.get_embeddings(clap, mask)
-        denoised = net(samples + noise * sig, sigma, None, emb)
-        wl = (F.mse_loss(denoised, samples, reduction="none") * w).mean(dim=(1, 2, 3))
-        logvar = net.get_sigma_loss_logvar(sigma)
-        loss = (wl / logvar.exp() + logvar).mean()
-        loss.backward()
+        for m in range(micro_steps):       # gradient accumulation (trainer.py:1022-1044): exchange on the last micro-step only
+            ctx = net.grad_sync.no_sync() if m + 1 < micro_steps else contextlib.nullcontext()
+            with ctx:
+                emb = net.get_embeddings(clap, mask)
+                denoised = net(samples + noise * sig, sigma, None, emb)
+                wl = (F.mse_loss(denoised, samples, reduction="none") * w).mean(dim=(1, 2, 3))
+                logvar = net.get_sigma_loss_logvar(sigma)
+                loss = (wl / logvar.exp() + logvar).mean() / micro_steps
+                loss.backward()
         if opt is not None:
             opt.clip_grad_norm_(10.0)
             opt.step()
@@ -358,13 +364,16 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3, fused
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    sps = world * B * steps / (ms * 1e-3)
+    sps = world * B * micro_steps * steps / (ms * 1e-3)
     pk = peaks()
     flop = 3 * FLOP_PER_STEP / 4              # fwd + dgrad + wgrad of one sample-forward (0.489 TFLOP)
     gn = float(torch.sqrt(sum((p.grad.float() ** 2).sum() for p in net.parameters() if p.grad is not None)))
     what = "fwd+bwd+clip+AdamW+2 EMA+normalize_weights" if fused_optimizer else "fwd+bwd"
+    if micro_steps > 1:
+        what += f", {micro_steps} accumulation micro-steps per optimizer step"
     return {"metric": f"UNet train step {what} samples/sec (device batch 4 x 4x32x688, bf16 compute, fp32 grads)",
-            "value": sps, "unit": "samples/s", "ms_per_step": ms / steps, "n_gpus": world, "global_batch": world * B,
+            "value": sps, "unit": "samples/s", "ms_per_step": ms / steps, "n_gpus": world,
+            "global_batch": world * B * micro_steps,
             "allreduce_bytes_per_step": net.grad_sync.bytes_reduced // max(1, steps + warmup),
             "gpu_launches_per_step": (ops.launch_count - l0) // steps, "loss": float(loss.detach()), "grad_norm": gn,
             "roofline": {"bound": "tensor", "achieved": flop * sps / world / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
@@ -868,6 +877,21 @@ def run_ours(args) -> None:
         del net, pipe, state
         torch.cuda.empty_cache()
         train = bench_train(device, dist, world)
+        # The complete optimizer step (clip + AdamW + 2 EMA + normalize_weights through FusedAdamW) at EVERY N: the sweep is
+        # replicated and deterministic, so it adds no exchange.  At N = 1 also the survey's strong-scaling base: global batch
+        # 32 on one GPU as 8 accumulation micro-steps (no_sync) per optimizer step.
+        try:
+            torch.cuda.empty_cache()
+            train["with_optimizer"] = bench_train(device, dist, world, steps=4, fused_optimizer=True)
+        except Exception as exc:           # must never cost the bench line
+            train["with_optimizer"] = {"error": repr(exc)}
+        if world == 1:
+            try:
+                torch.cuda.empty_cache()
+                train["global_batch_32_on_one_gpu"] = bench_train(device, dist, world, steps=2, warmup=1,
+                                                                  fused_optimizer=True, micro_steps=8)
+            except Exception as exc:
+                train["global_batch_32_on_one_gpu"] = {"error": repr(exc)}
 
     dae = ddec = None
     if rank == 0 and world == 1 and not args.no_dae:
@@ -901,11 +925,7 @@ def run_ours(args) -> None:
             optim = bench_optim(device)
         except Exception as exc:
             optim = {"error": repr(exc)}
-        try:
-            torch.cuda.empty_cache()
-            optim["train_step_with_optimizer"] = bench_train(device, dist, world, fused_optimizer=True)
-        except Exception as exc:
-            optim["train_step_with_optimizer"] = {"error": repr(exc)}
+        optim["train_step_with_optimizer"] = (train or {}).get("with_optimizer")      # measured with the train legs above
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
