@@ -1,8 +1,10 @@
 """Module base of the drop-in classes.
 
-Mirrors the contract of the reference's `DualDiffusionModule` (src/modules/module.py:42-191): config
-dataclass <-> `<name>.json`, `<name>.safetensors` weights with strict key matching, dtype / device /
-memory_format tracking, `normalize_weights()`.  When the reference itself is loaded in the process (its
+Mirrors the part of the reference's `DualDiffusionModule` contract (src/modules/module.py:42-191) that the hot path
+needs: loading (config dataclass <- `<name>.json`, `<name>.safetensors` weights with strict key matching), dtype /
+device / memory_format tracking and `normalize_weights()`.  The control-plane methods (save_pretrained, load_ema,
+blend_weights) are not restated: under the reference they come from its own base class.
+When the reference itself is loaded in the process (its
 `modules.module` is in sys.modules because its pipeline / trainer imported us through model_index.json),
 the classes here *are* subclasses of the reference bases, so `isinstance(x, DualDiffusionModule)` checks in
 src/pipelines/dual_diffusion_pipeline.py:131-133 pass.  Stand-alone (GPU box, no reference) the local
@@ -15,7 +17,7 @@ import json
 import os
 import sys
 from abc import ABC
-from dataclasses import asdict, dataclass, fields, is_dataclass
+from dataclasses import dataclass, fields
 from typing import Optional, Type, Union
 
 import torch
@@ -69,21 +71,6 @@ else:
             module.module_path = module_path
             return module.to(dtype=torch_dtype, device=device)
 
-        @torch.no_grad()
-        def save_pretrained(self, module_path: str, subfolder: Optional[str] = None,
-                            save_config_only: bool = False) -> None:
-            if subfolder is not None:
-                module_path = os.path.join(module_path, subfolder)
-            os.makedirs(module_path, exist_ok=True)
-            name = os.path.basename(module_path)
-            cfg = asdict(self.config) if is_dataclass(self.config) else dict(self.config.__dict__)
-            with open(os.path.join(module_path, f"{name}.json"), "w") as fh:
-                json.dump(cfg, fh, indent=2)
-            if type(self).has_trainable_parameters and not save_config_only:
-                from safetensors.torch import save_file
-                save_file({k: v.contiguous() for k, v in self.state_dict().items()},
-                          os.path.join(module_path, f"{name}.safetensors"))
-
         # ---- dtype / device tracking: module.py:104-143 ----
         def to(self, device=None, dtype=None, memory_format=None, **kwargs) -> "DualDiffusionModule":
             if device is not None:
@@ -117,22 +104,6 @@ else:
             # module.py:145-149 wraps forward in torch.compile; the B200 path is hand-written kernels +
             # CUDA graphs, so this is a deliberate no-op (supports_compile = False).
             return None
-
-        @torch.no_grad()
-        def load_ema(self, ema_path: str, phema_path: Optional[str] = None) -> None:
-            from safetensors.torch import load_file
-            if not os.path.isfile(ema_path):
-                raise FileNotFoundError(f"Error: Could not find ema file '{ema_path}'")
-            self.load_state_dict(load_file(ema_path))
-            self.normalize_weights()
-
-        @torch.no_grad()
-        def blend_weights(self, other: "DualDiffusionModule", t: float = 0.5) -> None:
-            for (n, p), (on, op) in zip(self.named_parameters(), other.named_parameters()):
-                if p.data.shape != op.data.shape:
-                    raise ValueError(f"Cannot blend parameters with different shapes: {n} {p.data.shape} != {on} {op.data.shape}")
-                p.data.lerp_(op.data, t)
-            self.normalize_weights()
 
         @torch.no_grad()
         def normalize_weights(self) -> None:
