@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+from dualdiffusion_b200.replicas import max_over_ranks  # noqa: E402
+
 LATENT = (1, 4, 32, 688)             # 45 s @ 32 kHz stereo -> mel (2,256,5504) -> 8x-downsampled 4-channel latent
 FLOP_PER_SAMPLE_FWD = 0.489e12       # default UNet forward at (4,32,688)
 FLOP_PER_STEP = 4 * FLOP_PER_SAMPLE_FWD
@@ -360,10 +362,7 @@ def bench_train(device, dist, world: int, steps: int = 6, warmup: int = 3, fused
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms, dist, device)      # job time = slowest rank
     sps = world * B * micro_steps * steps / (ms * 1e-3)
     pk = peaks()
     flop = 3 * FLOP_PER_STEP / 4              # fwd + dgrad + wgrad of one sample-forward (0.489 TFLOP)
@@ -686,11 +685,9 @@ def run_ours(args) -> None:
         torch.cuda.synchronize()
         launches = ops.launch_count - launches0
         ms = e0.elapsed_time(e1)
+        ms = max_over_ranks(ms, dist, device)          # job time = slowest rank
         if dist is not None:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.barrier()
-            ms = float(t.item())
         value = world * K / (ms * 1e-3)
 
         # ---- e2e: BASELINE config 2 as a user runs it -- ONE 100-step generate through the public API
@@ -713,10 +710,7 @@ def run_ours(args) -> None:
             out_host.copy_(res, non_blocking=True)
             torch.cuda.synchronize()
         gen_s = (time.perf_counter() - t0) / n_gen
-        if dist is not None:
-            t = torch.tensor([gen_s], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            gen_s = float(t.item())
+        gen_s = max_over_ranks(gen_s, dist, device)      # job time = slowest rank
         e2e_generate = {"value": world * gen_params.num_steps / gen_s, "unit": UNIT, "seconds_per_100_step_generate": gen_s,
                         "calls_timed": n_gen, "h2d_bytes_per_step": clap_host.numel() * 4 / gen_params.num_steps,
                         "d2h_bytes_per_step": out_host.numel() * 4 / gen_params.num_steps,
@@ -738,10 +732,7 @@ def run_ours(args) -> None:
             torch.cuda.synchronize()
             host_in, host_out = host_out, host_in
         e2e_s = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([e2e_s], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s = max_over_ranks(e2e_s, dist, device)      # job time = slowest rank
         if rank == 0:
             sampler.stop_flag.set()
             sampler.join(timeout=2)
