@@ -93,6 +93,7 @@ _SIGNATURES = {
                                c_int, c_int, c_void_p]),
     "dd_mpconv_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                   C.POINTER(ConvEpilogue), c_void_p]),
+    "dd_mpconv_forward_cat": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_mpconv_forward_naive": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_void_p]),
     "dd_stem_patches": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -61,6 +61,7 @@ struct ConvParams {
     int kchunks;                    // cin_g / KC
     int k_iters;                    // taps * kchunks
     int sub;                        // operand pairs per pipeline stage (1 or 2)
+    int a_split;                    // > 0: input channels [a_split, Cin) are read from a second activation tensor
     int num_tiles;
     int stages;
     uint32_t a_bytes, b_bytes;      // bytes landed per stage by the two TMA boxes
@@ -489,8 +490,8 @@ __device__ __forceinline__ void epilogue_tile_staged(const ConvParams& p, uint32
 // interleaved 16-column chunks; for epilogues with transcendental math).
 template <int KC, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvParams p) {
     constexpr uint32_t kRowBytes = KC * 2;           // one swizzle span per row
     constexpr uint32_t kABufBytes = kTileM * kRowBytes;
 
@@ -515,6 +516,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::prefetch_tensormap(&tmA);
             ptx::prefetch_tensormap(&tmB);
         }
+        if (lane == 1 && p.a_split > 0) ptx::prefetch_tensormap(&tmA2);
         if (lane < p.stages) {
             ptx::mbar_init(&full_bar[lane], 1);
             ptx::mbar_init(&empty_bar[lane], 1);
@@ -602,7 +604,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int j = 0; j < cnt; ++j) {
                     uint8_t* a_dst = smem + stage * stage_bytes + j * pair_bytes;
                     if (ptx::elect_one()) {
-                        ptx::tma_load_4d(a_dst, &tmA, &full_bar[stage], a_c0 + ki.kc * KC, t.w0 + ki.dx, t.h0 + ki.dy, t.b0);
+                        // (dd_mpconv_forward_cat: input channels >= a_split come from the second tensor -- the conv reads the
+                        // two operands of an mp_cat without the concatenation ever being written)
+                        const int c = a_c0 + ki.kc * KC;
+                        const bool second = p.a_split > 0 && c >= p.a_split;
+                        ptx::tma_load_4d(a_dst, second ? &tmA2 : &tmA, &full_bar[stage], second ? c - p.a_split : c, t.w0 + ki.dx,
+                                         t.h0 + ki.dy, t.b0);
                         if (!b_done)
                             ptx::tma_load_2d(a_dst + kABufBytes, &tmB, &full_bar[stage], ki.tap * p.cin_g + ki.kc * KC, b_row);
                     }
@@ -1001,9 +1008,8 @@ PFN_encodeTiled get_encode_fn() {
 
 // Launch with programmatic stream serialization (PDL): the kernel may begin before its stream predecessor has
 // finished; everything that depends on the predecessor sits behind griddepcontrol.wait inside the kernels.
-template <typename Kernel>
-cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t stream, const CUtensorMap& tmA,
-                       const CUtensorMap& tmB, const ConvParams& p) {
+template <typename Kernel, typename... Args>
+cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStream_t stream, const Args&... args) {
     static const bool no_pdl = getenv("DD_DISABLE_PDL") != nullptr;      // tuning experiments only
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1015,7 +1021,7 @@ cudaError_t launch_pdl(Kernel kernel, int grid, int block, size_t smem, cudaStre
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p);
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 // Pick the pixel box of an M tile: wt*ht*bt <= 128, minimising the number of tiles.
@@ -1091,7 +1097,8 @@ bool want_staged_epilogue(const ConvParams& p) {
     return on && p.epi != DD_EPI_HEAD && p.nacc == 1;
 }
 
-int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream) {
+int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int groups, cudaStream_t stream,
+                    const void* x2 = nullptr, int c1 = 0) {
     PFN_encodeTiled encode = get_encode_fn();
     DD_REQUIRE(encode != nullptr, "dd_mpconv_forward: cuTensorMapEncodeTiled unavailable (driver too old?)");
     const int B = p.B, H = p.H, W = p.W, Cin = p.Cin, Cout = p.Cout;
@@ -1128,17 +1135,24 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
     p.stages = std::max(2, std::min<int>(kMaxStages, (int)((200u * 1024u - slabs_bytes) / stage_bytes)));
     p.stage_off = staged ? (uint32_t)p.stages * stage_bytes : 0u;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmA2, tmB;
     const CUtensorMapSwizzle swz = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    p.a_split = x2 ? c1 : 0;
+    DD_REQUIRE(x2 == nullptr || (groups == 1 && c1 > 0 && c1 < Cin && c1 % KC == 0),
+               "dd_mpconv_forward_cat: the first operand's %d channels must be a multiple of the %d-channel K chunk", c1, KC);
+    auto encode_act = [&](CUtensorMap* tm, const void* ptr, int C) {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
         cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)p.wt, (cuuint32_t)p.ht, (cuuint32_t)p.bt};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    {
+        CUresult r = encode_act(&tmA, x, x2 ? c1 : Cin);
         DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: activation tensor map encode failed (CUresult %d)", (int)r);
+        r = encode_act(&tmA2, x2 ? x2 : x, x2 ? Cin - c1 : Cin);
+        DD_REQUIRE(r == CUDA_SUCCESS, "dd_mpconv_forward: second activation tensor map encode failed (CUresult %d)", (int)r);
     }
     {
         const cuuint64_t ktot = (cuuint64_t)p.taps * cin_g;
@@ -1166,7 +1180,7 @@ int fill_and_launch(ConvParams& p, const void* x, const void* w_prepped, int gro
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));          \
             attr_done = true;                                                                                      \
         }                                                                                                          \
-        DD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<KC_, EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmB, p)); \
+        DD_CHECK_CUDA(launch_pdl(conv_igemm_kernel<KC_, EW_>, grid, 64 + 32 * EW_, smem_bytes, stream, tmA, tmA2, tmB, p)); \
     } while (0)
     if (KC == 64) { if (ew == 12) DD_LAUNCH_IGEMM(64, 12); else if (ew == 8) DD_LAUNCH_IGEMM(64, 8); else DD_LAUNCH_IGEMM(64, 4); }
     else          { if (ew == 12) DD_LAUNCH_IGEMM(32, 12); else if (ew == 8) DD_LAUNCH_IGEMM(32, 8); else DD_LAUNCH_IGEMM(32, 4); }
@@ -1379,6 +1393,23 @@ extern "C" int dd_mpconv_forward(const void* x, const void* w_prepped, void* out
     }
     p.out = static_cast<__nv_bfloat16*>(out);
     return launch_conv(p, x, w_prepped, groups, stream);
+}
+
+// 1x1 MPConv over the channel concatenation [x1 | x2] without materialising it (decoder conv_skip after mp_cat,
+// unet_edm2_b4.py:295-296 + :129): the K loop switches tensor maps at channel C1.  The mp_cat weights wa / wb belong in the
+// prepared weight's columns.
+extern "C" int dd_mpconv_forward_cat(const void* x1, int C1, const void* x2, int C2, const void* w_prepped, void* out, int B,
+                                     int H, int W, int Cout, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x1 && x2 && w_prepped && out, "dd_mpconv_forward_cat: null pointer");
+    DD_REQUIRE(C1 > 0 && C2 > 0 && (C1 + C2) % 32 == 0 && Cout % 16 == 0, "dd_mpconv_forward_cat: bad channel counts");
+    DD_REQUIRE(B > 0 && H > 0 && W > 0, "dd_mpconv_forward_cat: empty input");
+    ConvParams p{};
+    p.B = B; p.H = H; p.W = W; p.Cin = C1 + C2; p.Cout = Cout;
+    p.kh = p.kw = 1; p.taps = 1;
+    p.epi = DD_EPI_NONE; p.epi2 = DD_EPI2_NONE; p.clip = INFINITY;
+    p.out = static_cast<__nv_bfloat16*>(out);
+    return fill_and_launch(p, x1, w_prepped, 1, stream, x2, C1);
 }
 
 // UNet head on the tensor cores: 3x3 conv to `Cout` (<= 16) channels whose weights were padded to 16 output

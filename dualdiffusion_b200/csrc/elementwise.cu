@@ -122,27 +122,33 @@ __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restri
 // ------------------------------------------------------------------------------------------
 // decoder input: (optional nearest x2 upsample of a) ++ (optional skip b), scaled, plus mp_silu
 // ------------------------------------------------------------------------------------------
+// I = index type: 32-bit whenever the tensor has fewer than 2^31 vectors (64-bit div / mod by a run-time value is a ~100
+// instruction sequence, and this kernel does up to five per 16-byte vector: with `long` it was bound by them, not by HBM)
+template <typename I>
 __global__ void cat_silu_kernel(const uint4* __restrict__ a, int va, const uint4* __restrict__ b, int vb, float wa,
                                 float wb, int up, uint4* __restrict__ xcat, uint4* __restrict__ s, int B, int H, int W) {
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
-    const int vt = va + vb;
-    const long total = (long)B * H * W * vt;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx % vt);
-        const long pix = idx / vt;
+    const I vt = (I)(va + vb);
+    const I total = (I)B * (I)H * (I)W * vt;
+    for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+        const I pix = idx / vt;
+        const int v = (int)(idx - pix * vt);
         uint4 q;
         float sc;
         if (v < va) {
-            long apix = pix;
+            I apix = pix;
             if (up) {
-                const int w = (int)(pix % W), h = (int)((pix / W) % H), bb = (int)(pix / ((long)W * H));
-                apix = ((long)bb * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1);
+                const I r = pix / (I)W;
+                const int w = (int)(pix - r * (I)W);
+                const I bb = r / (I)H;
+                const int h = (int)(r - bb * (I)H);
+                apix = (bb * (I)(H >> 1) + (I)(h >> 1)) * (I)(W >> 1) + (I)(w >> 1);
             }
-            q = __ldg(a + apix * va + v);
+            q = __ldg(a + (size_t)apix * va + v);
             sc = wa;
         } else {
-            q = __ldg(b + pix * vb + (v - va));
+            q = __ldg(b + (size_t)pix * vb + (v - va));
             sc = wb;
         }
         const uint32_t u[4] = {q.x, q.y, q.z, q.w};
@@ -499,9 +505,14 @@ extern "C" int dd_cat_silu(const void* a, int Ca, const void* b, int Cb, float w
     DD_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "dd_cat_silu: upsample needs even output size");
     const long total = (long)B * H * W * ((Ca + Cb) / 8);
     if (total == 0) return 0;
-    DD_CHECK_CUDA(dd_launch_pdl(cat_silu_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream,
-                                static_cast<const uint4*>(a), Ca / 8, static_cast<const uint4*>(b), Cb / 8, wa, wb,
-                                upsample, static_cast<uint4*>(xcat_out), static_cast<uint4*>(s_out), B, H, W));
+    if (total < (1l << 31) - (long)grid_for(total, 256) * 256)
+        DD_CHECK_CUDA(dd_launch_pdl(cat_silu_kernel<unsigned>, dim3(grid_for(total, 256)), dim3(256), 0, stream,
+                                    static_cast<const uint4*>(a), Ca / 8, static_cast<const uint4*>(b), Cb / 8, wa, wb,
+                                    upsample, static_cast<uint4*>(xcat_out), static_cast<uint4*>(s_out), B, H, W));
+    else
+        DD_CHECK_CUDA(dd_launch_pdl(cat_silu_kernel<long>, dim3(grid_for(total, 256)), dim3(256), 0, stream,
+                                    static_cast<const uint4*>(a), Ca / 8, static_cast<const uint4*>(b), Cb / 8, wa, wb,
+                                    upsample, static_cast<uint4*>(xcat_out), static_cast<uint4*>(s_out), B, H, W));
     return 0;
 }
 

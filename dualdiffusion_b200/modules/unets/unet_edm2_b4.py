@@ -185,6 +185,29 @@ class _Plan:
                                                 qkv_head_dim=max(-qk_dim, 0), pad_rows=pad_rows,
                                                 row_stride=row_stride, out=self.prepped.get(key))
             self.versions[key] = ver
+        # Decoder "layer" blocks (inference): conv_skip reads the two operands of mp_cat directly (dd_mpconv_forward_cat), so
+        # the concatenation is never written; the mp_cat weights (mp_tools.py:294-301) are folded into the weight's columns.
+        # (Train mode normalises the weight rows inside the preparation, which does not commute with a column scale.)
+        if not training:
+            net = self.net
+            skips = [b.out_channels for b in net.enc.values()]      # conv_in and every encoder block, in order
+            for name, blk in net.dec.items():
+                if "layer" in name:
+                    C2 = skips.pop()
+                    C1 = blk.in_channels - C2
+                    kc = 64 if (C1 + C2) % 64 == 0 else 32          # K chunk of the kernel: the split must fall on a chunk edge
+                    if C1 % kc != 0:
+                        continue
+                    key = f"dec.{name}.conv_skip.cat"
+                    w = blk.conv_skip.weight
+                    ver = _ver(w)
+                    if stale_all or self.versions.get(key) != ver or key not in self.prepped:
+                        wa, wb = mp_cat_weights(C1, C2, net.config.concat_balance)
+                        src = w.detach().float().clone()
+                        src[:, :C1] *= wa
+                        src[:, C1:] *= wb
+                        self.prepped[key] = ops.weight_prep(src, normalize=False, out=self.prepped.get(key))
+                        self.versions[key] = ver
         self.training = training
 
     # ---- embedding projections: one launch for every block's emb_linear* ----
@@ -527,10 +550,15 @@ class UNet(DualDiffusionUNet):
 
         for i, (name, blk) in enumerate(dec_list):
             p = "dec." + name
+            cat_pair = None
             if "layer" in name:
                 skip = skips.pop()
                 wa, wb = mp_cat_weights(x.shape[-1], skip.shape[-1], cfg.concat_balance)
-                xc, s = ops.cat_silu(x, skip, wa, wb, False)
+                if not self.training and (p + ".conv_skip.cat") in W:      # inference: only mp_silu(mp_cat(x, skip)) is written
+                    cat_pair = (x, skip)
+                    xc, s = ops.cat_silu(x, skip, wa, wb, False, need_cat=False)
+                else:
+                    xc, s = ops.cat_silu(x, skip, wa, wb, False)
             elif blk.resample_mode == "up":
                 xc, s = ops.cat_silu(x, None, 1.0, 0.0, True)
             elif s_next is not None:
@@ -540,10 +568,13 @@ class UNet(DualDiffusionUNet):
                 _, s = ops.cat_silu(x, None, 1.0, 0.0, False, need_cat=False)
             # conv_skip(x) is independent of the residual branch: run it as a parallel graph branch and let
             # conv_res1's epilogue do the mp_sum (unet_edm2_b4.py:129-131)
-            t0 = torch.empty(xc.shape[:3] + (blk.out_channels,), device=xc.device, dtype=torch.bfloat16)
+            t0 = torch.empty(s.shape[:3] + (blk.out_channels,), device=s.device, dtype=torch.bfloat16)
             fork()
             with torch.cuda.stream(side):
-                ops.mpconv(xc, W[p + ".conv_skip"], 1, out=t0)
+                if cat_pair is not None:
+                    ops.mpconv_cat(cat_pair[0], cat_pair[1], W[p + ".conv_skip.cat"], out=t0)
+                else:
+                    ops.mpconv(xc, W[p + ".conv_skip"], 1, out=t0)
             y0 = ops.mpconv(s, W[p + ".conv_res0"], 3, g, epi=L.EPI_SCALE_SILU, scale=cvec[p + ".c"])
             join()
             x, s_next = block_tail(p, blk, y0, t0, wants_silu(i + 1))

@@ -88,6 +88,19 @@ def mpconv(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1, *, epi: in
     return (out, out2) if epi2 != L.EPI2_NONE else out
 
 
+def mpconv_cat(x1: Tensor, x2: Tensor, w_prepped: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """1x1 MPConv over [x1 | x2] without materialising the concatenation (mp_cat weights folded into w_prepped)."""
+    B, H, W, C1 = x1.shape
+    C2 = x2.shape[-1]
+    Cout = w_prepped.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), device=x1.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_mpconv_forward_cat(L.ptr(x1), C1, L.ptr(x2), C2, L.ptr(w_prepped), L.ptr(out), B, H, W, Cout,
+                                           L.stream_ptr()))
+    _count(1, "mpconv_cat", (B, H, W, C1 + C2, Cout, 1, 1, 0, 0))
+    return out
+
+
 def mpconv_naive(x: Tensor, w_prepped: Tensor, ksize: int, groups: int = 1) -> Tensor:
     B, H, W, Cin = x.shape
     Cout = w_prepped.shape[0]

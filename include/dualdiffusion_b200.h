@@ -90,6 +90,12 @@ typedef struct dd_conv_epilogue {
 DD_API int dd_mpconv_forward(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin, int Cout,
                       int ksize, int groups, const dd_conv_epilogue* epilogue_host, void* stream);
 
+/* 1x1 MPConv over the channel concatenation [x1 | x2] (bf16 NHWC, C1 and C2 channels) without writing the concatenation:
+ * conv_skip of a decoder block after mp_cat (unet_edm2_b4.py:295-296, :129).  w_prepped: bf16 [Cout][C1 + C2] with the mp_cat
+ * weights folded into its columns; C1 a multiple of 64 (32 when C1 + C2 is not a multiple of 64).  No epilogue.        */
+DD_API int dd_mpconv_forward_cat(const void* x1, int C1, const void* x2, int C2, const void* w_prepped, void* out, int B,
+                                 int H, int W, int Cout, void* stream);
+
 /* Scalar CUDA-core convolution with the same contract as dd_mpconv_forward (no epilogue).
  * Debug/triangulation aid for the tests only; never called by the product path.                 */
 DD_API int dd_mpconv_forward_naive(const void* x, const void* w_prepped, void* out, int B, int H, int W, int Cin, int Cout,

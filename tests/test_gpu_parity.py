@@ -141,6 +141,18 @@ def test_mpconv_epilogues(dev):
     assert rel_err(to_nchw(y2), uo.mp_silu(ref)) < BF16_OP
 
 
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout", [(2, 8, 20, 256, 128, 256), (1, 4, 86, 1280, 1024, 1024), (2, 5, 9, 64, 32, 48)])
+def test_mpconv_cat_reads_both_operands_bit_identically(dev, B, H, W, C1, C2, Cout):
+    """dd_mpconv_forward_cat == dd_mpconv_forward on the materialised concatenation (same K order, same accumulators)."""
+    from dualdiffusion_b200 import ops
+    gen = torch.Generator().manual_seed(23)
+    x1 = nhwc_bf16(torch.randn(B, C1, H, W, generator=gen), dev)
+    x2 = nhwc_bf16(torch.randn(B, C2, H, W, generator=gen), dev)
+    wp = ops.weight_prep(torch.randn(Cout, C1 + C2, 1, 1, generator=gen).to(dev))
+    ref = ops.mpconv(torch.cat([x1, x2], dim=-1).contiguous(), wp, 1)
+    assert torch.equal(ops.mpconv_cat(x1, x2, wp), ref)
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,g", [
     (2, 7, 13, 96, 64, 1, 1),        # per-tap kernel, ragged pixel box
     (2, 17, 20, 768, 512, 3, 8),     # halo kernel, ragged tile edges, n_tile 64
