@@ -65,6 +65,13 @@ __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b -
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // magnitude-preserving SiLU (reference mp_tools.py:268): silu(x) / 0.596
 __device__ __forceinline__ float mp_silu_f(float x) { return silu_f(x) * (1.0f / 0.596f); }
+// The same for results that are rounded to bf16 anyway: x*sigmoid(x) = x*(0.5 + 0.5*tanh(x/2)) with one MUFU (tanh.approx,
+// ~2^-11 error, below the 2^-9 of the bf16 rounding that follows) instead of an exp and an IEEE division.
+__device__ __forceinline__ float mp_silu_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return x * fmaf(0.5f, t, 0.5f) * (1.0f / 0.596f);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -123,11 +123,6 @@ struct Walker {
     }
 };
 
-__device__ __forceinline__ float mp_silu_fast(float x) {      // x * sigmoid(x) / 0.596 with one MUFU (tanh.approx)
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-    return x * fmaf(0.5f, t, 0.5f) * (1.0f / 0.596f);
-}
 // Packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): half the issue slots of the epilogue arithmetic.
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     float2 r;

@@ -117,13 +117,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
     return t;
 }
 
-// fast magnitude-preserving SiLU for the epilogue: x*sigmoid(x) = x*(0.5 + 0.5*tanh(x/2)), one MUFU op.
-// tanh.approx has ~2^-11 relative error, below the bf16 rounding (2^-9) applied to the result.
-__device__ __forceinline__ float mp_silu_fast(float x) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
-    return x * fmaf(0.5f, t, 0.5f) * (1.0f / 0.596f);
-}
 
 __device__ __forceinline__ void store_bf16x16(__nv_bfloat16* dst, const float (&v)[16]) {
     uint4* op = reinterpret_cast<uint4*>(dst);

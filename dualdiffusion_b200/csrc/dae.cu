@@ -119,24 +119,28 @@ __global__ void dae_stem_kernel(const float* __restrict__ lat, __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------
 // resample_3d "up" (mp_tools.py:92-93: nearest x2 in H and W) on a W-padded tensor + mp_silu
 // ------------------------------------------------------------------------------------------
+// I = index type (32-bit whenever the output has fewer than 2^31 vectors: 64-bit div / mod by run-time values costs more
+// instructions than the rest of the body)
+template <typename I>
 __global__ void up2_silu_pad_kernel(const uint4* __restrict__ a, uint4* __restrict__ xc, uint4* __restrict__ s, int B, int Ha,
                                     int Wa, int pw, int nvec) {
     ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
     ptx::grid_dependency_wait();
     const int H = 2 * Ha, W = 2 * Wa, Wp = W + 2 * pw, Wpa = Wa + 2 * pw;
-    const long total = (long)B * H * Wp * nvec;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx % nvec);
-        long pix = idx / nvec;
-        const int p = (int)(pix % Wp);
-        pix /= Wp;
-        const int h = (int)(pix % H), b = (int)(pix / H);
+    const I total = (I)B * (I)H * (I)Wp * (I)nvec;
+    for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+        I pix = idx / (I)nvec;
+        const int v = (int)(idx - pix * (I)nvec);
+        const I r = pix / (I)Wp;
+        const int p = (int)(pix - r * (I)Wp);
+        const I b = r / (I)H;
+        const int h = (int)(r - b * (I)H);
         const int w = reflect_idx(p - pw, W);
-        const uint4 q = __ldg(a + (((long)b * Ha + (h >> 1)) * Wpa + (w >> 1) + pw) * nvec + v);
+        const uint4 q = __ldg(a + (((size_t)b * Ha + (h >> 1)) * Wpa + (w >> 1) + pw) * nvec + v);
         float f[8], o[8];
         unpack8d(q, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = mp_silu_f(f[j]);
+        for (int j = 0; j < 8; ++j) o[j] = mp_silu_fast(f[j]);
         xc[idx] = q;
         s[idx] = pack8d(o);
     }
@@ -426,8 +430,10 @@ extern "C" int dd_up2_silu_pad(const void* a, void* xc, void* s, int B, int Ha, 
     DD_REQUIRE(a && xc && s && C % 8 == 0 && pw >= 1 && Wa >= 1, "dd_up2_silu_pad: bad arguments");
     const long total = (long)B * 2 * Ha * (2 * Wa + 2 * pw) * (C / 8);
     if (total == 0) return 0;
-    DD_CHECK_CUDA(dd_launch_pdl(up2_silu_pad_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<const uint4*>(a), static_cast<uint4*>(xc),
-                                                                    static_cast<uint4*>(s), B, Ha, Wa, pw, C / 8));
+    const int grid = grid_for_d(total, 256);
+    const bool narrow = total < (1L << 31) - (long)grid * 256;      // idx + stride must not wrap
+    DD_CHECK_CUDA(dd_launch_pdl(narrow ? up2_silu_pad_kernel<unsigned> : up2_silu_pad_kernel<long>, dim3(grid), dim3(256), 0, stream,
+                                static_cast<const uint4*>(a), static_cast<uint4*>(xc), static_cast<uint4*>(s), B, Ha, Wa, pw, C / 8));
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -111,7 +111,7 @@ __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restri
                 float2 f = unpack_bf16x2(u[j]);
                 f.x *= inv; f.y *= inv;
                 xo[j] = pack_bf16x2(f.x, f.y);
-                so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
+                so[j] = pack_bf16x2(mp_silu_fast(f.x), mp_silu_fast(f.y));
             }
             x_out[pix * nvec + v] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
             s_out[pix * nvec + v] = make_uint4(so[0], so[1], so[2], so[3]);
@@ -158,7 +158,7 @@ __global__ void cat_silu_kernel(const uint4* __restrict__ a, int va, const uint4
             float2 f = unpack_bf16x2(u[j]);
             f.x *= sc; f.y *= sc;
             xo[j] = pack_bf16x2(f.x, f.y);
-            so[j] = pack_bf16x2(mp_silu_f(f.x), mp_silu_f(f.y));
+            so[j] = pack_bf16x2(mp_silu_fast(f.x), mp_silu_fast(f.y));
         }
         if (xcat) xcat[idx] = make_uint4(xo[0], xo[1], xo[2], xo[3]);
         s[idx] = make_uint4(so[0], so[1], so[2], so[3]);
