@@ -213,7 +213,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);     // finite: every 64-key block holds >= 1 real key
-            corr[r] = exp2f((m_run[r] - m_new) * sl2);
+            corr[r] = fast_exp2((m_run[r] - m_new) * sl2);
             m_run[r] = m_new;
             l_run[r] *= corr[r];
         }
@@ -221,10 +221,11 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
         for (int n = 0; n < 8; ++n) { o[n][0] *= corr[0]; o[n][1] *= corr[0]; o[n][2] *= corr[1]; o[n][3] *= corr[1]; }
         // probabilities -> bf16 A fragments
         uint32_t pa[4][4];
+        const float nm0 = -m_run[0] * sl2, nm1 = -m_run[1] * sl2;      // one FFMA + one MUFU per score
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            const float p0 = exp2f((s[n][0] - m_run[0]) * sl2), p1 = exp2f((s[n][1] - m_run[0]) * sl2);
-            const float p2 = exp2f((s[n][2] - m_run[1]) * sl2), p3 = exp2f((s[n][3] - m_run[1]) * sl2);
+            const float p0 = fast_exp2(fmaf(s[n][0], sl2, nm0)), p1 = fast_exp2(fmaf(s[n][1], sl2, nm0));
+            const float p2 = fast_exp2(fmaf(s[n][2], sl2, nm1)), p3 = fast_exp2(fmaf(s[n][3], sl2, nm1));
             l_run[0] += p0 + p1;
             l_run[1] += p2 + p3;
             pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
@@ -267,7 +268,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q_ptr, const __nv_bfloat16* _
             if (raw_out) *reinterpret_cast<uint32_t*>(raw_out + o_off + d) = pack_bf16x2(a0, a1);   // train mode
             const float y0 = a0 * scv[2 * n];
             const float y1 = a1 * scv[2 * n + 1];
-            if (out) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_f(y0), mp_silu_f(y1));
+            if (out) *reinterpret_cast<uint32_t*>(op + d) = pack_bf16x2(mp_silu_fast(y0), mp_silu_fast(y1));
         }
     }
 }

@@ -17,9 +17,13 @@ constexpr float kNormEps = 1e-4f;   // modules/mp_tools.py:43
 constexpr float kInvSiluGain = 1.0f / 0.596f;
 
 // d/dx mp_silu(x) = sigmoid(x) * (1 + x * (1 - sigmoid(x))) / 0.596
+// sigmoid(x) = 0.5 + 0.5 tanh(x/2): one MUFU (tanh.approx, ~2^-11) instead of an exp and an IEEE division -- the result
+// multiplies a bf16 gradient and is rounded to bf16, and the glue kernels that call this were issue-bound on the latter
 __device__ __forceinline__ float mp_silu_grad(float x) {
-    const float s = 1.0f / (1.0f + __expf(-x));
-    return s * (1.0f + x * (1.0f - s)) * kInvSiluGain;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    const float s = fmaf(0.5f, t, 0.5f);
+    return s * fmaf(x, 1.0f - s, 1.0f) * kInvSiluGain;
 }
 
 __device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
@@ -377,6 +381,8 @@ __global__ void pixnorm_silu_bwd_kernel(const uint4* __restrict__ g, float ca, c
 // decoder input backward: xc = [wa*up(a), wb*b], s = mp_silu(xc).
 //   dxc = c1*d_xc + d_s*silu'(xc);  da = mask(a) * wa * (sum over the 2x2 replicas of dxc[..:Ca]);  db = wb * dxc[Ca:]
 // ------------------------------------------------------------------------------------------
+// I = index type (unsigned when the tensors have fewer than 2^31 vectors: 64-bit div / mod is a long instruction sequence)
+template <typename I>
 __global__ void cat_silu_bwd_kernel(const uint4* __restrict__ d_xc, float c1, const uint4* __restrict__ d_s,
                                     const uint4* __restrict__ xc, const uint4* __restrict__ a_prev, float clip, float wa,
                                     float wb, int up, uint4* __restrict__ da, uint4* __restrict__ db, int B, int H, int W,
@@ -385,17 +391,20 @@ __global__ void cat_silu_bwd_kernel(const uint4* __restrict__ d_xc, float c1, co
     ptx::grid_dependency_wait();
     const int vt = va + vb;
     const int Ha = up ? H >> 1 : H, Wa = up ? W >> 1 : W;
-    const long total_a = (long)B * Ha * Wa * va, total_b = (long)B * H * W * vb;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_a + total_b; idx += (long)gridDim.x * blockDim.x) {
+    const I total_a = (I)B * (I)Ha * (I)Wa * (I)va, total_b = (I)B * (I)H * (I)W * (I)vb;
+    for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total_a + total_b; idx += (I)gridDim.x * blockDim.x) {
         if (idx < total_a) {
-            const int v = (int)(idx % va);
-            const long apix = idx / va;
+            const I apix = idx / (I)va;
+            const int v = (int)(idx - apix * (I)va);
             float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const int reps = up ? 2 : 1;
-            const int w = (int)(apix % Wa), h = (int)((apix / Wa) % Ha), bb = (int)(apix / ((long)Wa * Ha));
+            const I row = apix / (I)Wa;
+            const int w = (int)(apix - row * (I)Wa);
+            const I bb = row / (I)Ha;
+            const int h = (int)(row - bb * (I)Ha);
             for (int dy = 0; dy < reps; ++dy)
                 for (int dx = 0; dx < reps; ++dx) {
-                    const long pix = ((long)bb * H + h * reps + dy) * W + w * reps + dx;
+                    const size_t pix = ((size_t)bb * H + h * reps + dy) * W + w * reps + dx;
                     float g1[8], g2[8], x[8];
                     unpack8(__ldg(d_xc + pix * vt + v), g1);
                     unpack8(__ldg(d_s + pix * vt + v), g2);
@@ -415,9 +424,9 @@ __global__ void cat_silu_bwd_kernel(const uint4* __restrict__ d_xc, float c1, co
             }
             da[idx] = pack8(o);
         } else {
-            const long k = idx - total_a;
-            const int v = (int)(k % vb);
-            const long pix = k / vb;
+            const I k = idx - total_a;
+            const size_t pix = k / (I)vb;
+            const int v = (int)(k - (I)pix * (I)vb);
             float g1[8], g2[8], x[8], o[8];
             unpack8(__ldg(d_xc + pix * vt + va + v), g1);
             unpack8(__ldg(d_s + pix * vt + va + v), g2);
@@ -430,19 +439,23 @@ __global__ void cat_silu_bwd_kernel(const uint4* __restrict__ d_xc, float c1, co
 }
 
 // encoder chain: gradient of a block output = mask(x_prev) * (avgpool-backward(dx0) or dx0, plus the skip gradient)
+template <typename I>
 __global__ void enc_grad_combine_kernel(const uint4* __restrict__ dx0, int down, const uint4* __restrict__ dskip,
                                         const uint4* __restrict__ x_prev, float clip, uint4* __restrict__ out, int B, int H,
                                         int W, int nvec) {
     ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
     ptx::grid_dependency_wait();
-    const long total = (long)B * H * W * nvec;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const I total = (I)B * (I)H * (I)W * (I)nvec;
+    for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
         float a[8], o[8];
         if (down) {
-            const int v = (int)(idx % nvec);
-            const long pix = idx / nvec;
-            const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
-            unpack8(__ldg(dx0 + (((long)b * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * nvec + v), a);
+            const I pix = idx / (I)nvec;
+            const int v = (int)(idx - pix * (I)nvec);
+            const I row = pix / (I)W;
+            const int w = (int)(pix - row * (I)W);
+            const I b = row / (I)H;
+            const int h = (int)(row - b * (I)H);
+            unpack8(__ldg(dx0 + (((size_t)b * (H >> 1) + (h >> 1)) * (W >> 1) + (w >> 1)) * nvec + v), a);
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] *= 0.25f;
         } else {
@@ -718,13 +731,13 @@ attention_bwd_q_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
             const float m_new = fmaxf(m_run[r], mx[r]);       // finite: every 64-key block holds >= 1 real key
-            l_run[r] *= exp2f((m_run[r] - m_new) * kSl2);
+            l_run[r] *= fast_exp2((m_run[r] - m_new) * kSl2);
             m_run[r] = m_new;
         }
 #pragma unroll
         for (int n = 0; n < 8; ++n) {
-            l_run[0] += exp2f((s[n][0] - m_run[0]) * kSl2) + exp2f((s[n][1] - m_run[0]) * kSl2);
-            l_run[1] += exp2f((s[n][2] - m_run[1]) * kSl2) + exp2f((s[n][3] - m_run[1]) * kSl2);
+            l_run[0] += fast_exp2((s[n][0] - m_run[0]) * kSl2) + fast_exp2((s[n][1] - m_run[0]) * kSl2);
+            l_run[1] += fast_exp2((s[n][2] - m_run[1]) * kSl2) + fast_exp2((s[n][3] - m_run[1]) * kSl2);
         }
     }
     float L2[2];
@@ -747,8 +760,8 @@ attention_bwd_q_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat16
         for (int n = 0; n < 8; ++n) {
             const int key = kb + n * 8 + 2 * t;
             const bool k0 = key < N, k1 = key + 1 < N;
-            const float p0 = k0 ? exp2f(s[n][0] * kSl2 - L2[0]) : 0.f, p1 = k1 ? exp2f(s[n][1] * kSl2 - L2[0]) : 0.f;
-            const float p2 = k0 ? exp2f(s[n][2] * kSl2 - L2[1]) : 0.f, p3 = k1 ? exp2f(s[n][3] * kSl2 - L2[1]) : 0.f;
+            const float p0 = k0 ? fast_exp2(s[n][0] * kSl2 - L2[0]) : 0.f, p1 = k1 ? fast_exp2(s[n][1] * kSl2 - L2[0]) : 0.f;
+            const float p2 = k0 ? fast_exp2(s[n][2] * kSl2 - L2[1]) : 0.f, p3 = k1 ? fast_exp2(s[n][3] * kSl2 - L2[1]) : 0.f;
             dsa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0 * (dp[n][0] - D[0]) * 0.125f, p1 * (dp[n][1] - D[0]) * 0.125f);
             dsa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2 * (dp[n][2] - D[1]) * 0.125f, p3 * (dp[n][3] - D[1]) * 0.125f);
         }
@@ -813,8 +826,8 @@ attention_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qk, const __nv_bfloat1
         for (int n = 0; n < 8; ++n) {
             const int i = qb + n * 8 + 2 * t;
             const float l0 = Ls[i], l1 = Ls[i + 1], d0 = Ds[i], d1 = Ds[i + 1];
-            const float p0 = exp2f(s[n][0] * kSl2 - l0), p1 = exp2f(s[n][1] * kSl2 - l1);
-            const float p2 = exp2f(s[n][2] * kSl2 - l0), p3 = exp2f(s[n][3] * kSl2 - l1);
+            const float p0 = fast_exp2(s[n][0] * kSl2 - l0), p1 = fast_exp2(s[n][1] * kSl2 - l1);
+            const float p2 = fast_exp2(s[n][2] * kSl2 - l0), p3 = fast_exp2(s[n][3] * kSl2 - l1);
             pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);
             pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p2, p3);
             dsa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0 * (dp[n][0] - d0) * 0.125f, p1 * (dp[n][1] - d1) * 0.125f);
@@ -1088,7 +1101,9 @@ extern "C" int dd_cat_silu_bwd(const void* d_xc, float c1, const void* d_s, cons
     DD_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "dd_cat_silu_bwd: upsample needs even output size");
     const long total = (long)B * (upsample ? H / 2 : H) * (upsample ? W / 2 : W) * (Ca / 8) + (long)B * H * W * (Cb / 8);
     if (total == 0) return 0;
-    DD_CHECK_CUDA(dd_launch_pdl(cat_silu_bwd_kernel, dim3(grid_for_b(total, 256)), dim3(256), 0, stream, 
+    const int grid = grid_for_b(total, 256);
+    const bool narrow = total < (1L << 31) - (long)grid * 256;      // idx + stride must not wrap
+    DD_CHECK_CUDA(dd_launch_pdl(narrow ? cat_silu_bwd_kernel<unsigned> : cat_silu_bwd_kernel<long>, dim3(grid), dim3(256), 0, stream,
         static_cast<const uint4*>(d_xc), c1, static_cast<const uint4*>(d_s), static_cast<const uint4*>(xc),
         static_cast<const uint4*>(a_prev), clip > 0.f ? clip : INFINITY, wa, wb, upsample, static_cast<uint4*>(da),
         static_cast<uint4*>(db), B, H, W, Ca / 8, Cb / 8));
@@ -1103,7 +1118,9 @@ extern "C" int dd_enc_grad_combine(const void* dx0, int down, const void* dskip,
     DD_REQUIRE(!down || (H % 2 == 0 && W % 2 == 0), "dd_enc_grad_combine: downsampled block needs even size");
     const long total = (long)B * H * W * (C / 8);
     if (total == 0) return 0;
-    DD_CHECK_CUDA(dd_launch_pdl(enc_grad_combine_kernel, dim3(grid_for_b(total, 256)), dim3(256), 0, stream, 
+    const int grid = grid_for_b(total, 256);
+    const bool narrow = total < (1L << 31) - (long)grid * 256;      // idx + stride must not wrap
+    DD_CHECK_CUDA(dd_launch_pdl(narrow ? enc_grad_combine_kernel<unsigned> : enc_grad_combine_kernel<long>, dim3(grid), dim3(256), 0, stream,
         static_cast<const uint4*>(dx0), down, static_cast<const uint4*>(dskip), static_cast<const uint4*>(x_prev),
         clip > 0.f ? clip : INFINITY, static_cast<uint4*>(out), B, H, W, C / 8));
     DD_CHECK_LAUNCH();

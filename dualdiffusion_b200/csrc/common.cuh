@@ -73,6 +73,14 @@ __device__ __forceinline__ float mp_silu_fast(float x) {
     return x * fmaf(0.5f, t, 0.5f) * (1.0f / 0.596f);
 }
 
+// 2^x as one MUFU (exp2f without fast-math wraps the MUFU in a range test and two predicated multiplies for denormal
+// results, which a softmax flushes anyway)
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

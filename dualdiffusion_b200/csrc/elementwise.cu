@@ -165,21 +165,25 @@ __global__ void cat_silu_kernel(const uint4* __restrict__ a, int va, const uint4
     }
 }
 
+template <typename I>
 __global__ void avgpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int nvec) {
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
     const int Ho = H >> 1, Wo = W >> 1;
-    const long total = (long)B * Ho * Wo * nvec;
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx % nvec);
-        const long pix = idx / nvec;
-        const int w = (int)(pix % Wo), h = (int)((pix / Wo) % Ho), b = (int)(pix / ((long)Wo * Ho));
+    const I total = (I)B * (I)Ho * (I)Wo * (I)nvec;
+    for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+        const I pix = idx / (I)nvec;
+        const int v = (int)(idx - pix * (I)nvec);
+        const I row = pix / (I)Wo;
+        const int w = (int)(pix - row * (I)Wo);
+        const I b = row / (I)Ho;
+        const int h = (int)(row - b * (I)Ho);
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
-                const uint4 q = __ldg(x + (((long)b * H + 2 * h + dy) * W + 2 * w + dx) * nvec + v);
+                const uint4 q = __ldg(x + (((size_t)b * H + 2 * h + dy) * W + 2 * w + dx) * nvec + v);
                 const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { const float2 f = unpack_bf16x2(u[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
@@ -193,17 +197,21 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__
 // UNet stem: preconditioning + constant/positional channels, written as 3x3 patches ("im2col") so that
 // conv_in runs as a K=64 GEMM on the tensor cores.  patch[pix][tap*CT + c], zero padded to 64 columns.
 // ------------------------------------------------------------------------------------------
+template <typename I>
 __global__ void stem_patches_kernel(const float* __restrict__ x_in, const float* __restrict__ sigma, float sigma_data,
                                     const float* __restrict__ ln_freqs, uint4* __restrict__ out, int B, int Cin, int H,
                                     int W, int vecs) {
     ptx::grid_launch_dependents();
     ptx::grid_dependency_wait();
     const int CT = Cin + 2;
-    const long total = (long)B * H * W * vecs;    // vecs x (8 bf16) per pixel: 64 or 128 patch columns
-    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx % vecs);
-        const long pix = idx / vecs;
-        const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
+    const I total = (I)B * (I)H * (I)W * (I)vecs;    // vecs x (8 bf16) per pixel: 64 or 128 patch columns
+    for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+        const I pix = idx / (I)vecs;
+        const int v = (int)(idx - pix * (I)vecs);
+        const I row = pix / (I)W;
+        const int w = (int)(pix - row * (I)W);
+        const int b = (int)(row / (I)H);
+        const int h = (int)(row - (I)b * (I)H);
         const float sg = __ldg(sigma + b);
         const float c_in = rsqrtf(sigma_data * sigma_data + sg * sg);
         float f[8];
@@ -521,7 +529,8 @@ extern "C" int dd_avgpool2(const void* x, void* out, int B, int H, int W, int C,
     DD_REQUIRE(x && out && C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "dd_avgpool2: bad arguments");
     const long total = (long)B * (H / 2) * (W / 2) * (C / 8);
     if (total == 0) return 0;
-    DD_CHECK_CUDA(dd_launch_pdl(avgpool2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream,
+    const bool narrow = total < (1l << 31) - (long)grid_for(total, 256) * 256;      // idx + stride must not wrap
+    DD_CHECK_CUDA(dd_launch_pdl(narrow ? avgpool2_kernel<unsigned> : avgpool2_kernel<long>, dim3(grid_for(total, 256)), dim3(256), 0, stream,
                                 static_cast<const uint4*>(x), static_cast<uint4*>(out), B, H, W, C / 8));
     return 0;
 }
@@ -534,7 +543,8 @@ extern "C" int dd_stem_patches_cols(const float* x_in, const float* sigma, float
     DD_REQUIRE(9 * (Cin + 2) <= cols, "dd_stem_patches: in_channels=%d unsupported (9*(Cin+2) must be <= %d)", Cin, cols);
     const long total = (long)B * H * W * (cols / 8);
     if (total == 0) return 0;
-    DD_CHECK_CUDA(dd_launch_pdl(stem_patches_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, x_in, sigma,
+    const bool narrow = total < (1l << 31) - (long)grid_for(total, 256) * 256;
+    DD_CHECK_CUDA(dd_launch_pdl(narrow ? stem_patches_kernel<unsigned> : stem_patches_kernel<long>, dim3(grid_for(total, 256)), dim3(256), 0, stream, x_in, sigma,
                                 sigma_data, ln_freqs, static_cast<uint4*>(out), B, Cin, H, W, cols / 8));
     return 0;
 }

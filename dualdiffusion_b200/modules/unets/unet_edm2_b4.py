@@ -129,6 +129,7 @@ class _Plan:
         self.gains_f32 = torch.zeros(max(1, len(self.gain_params)), device=self.device, dtype=torch.float32)
         self.gain_version = None
         self._weight_items = None
+        self._emb_items = None
         # second stream: independent kernels of a block (conv_skip vs the residual branch, attn_v vs attn_qk,
         # the embedding projections vs the stem) run as parallel branches of the captured graph
         self.side = torch.cuda.Stream(device=self.device)
@@ -172,6 +173,23 @@ class _Plan:
         self._weight_items = items
         return items
 
+    def _emb_convs(self) -> list:
+        if self._emb_items is None:
+            items = []
+            for prefix, blocks in (("enc", self.net.enc), ("dec", self.net.dec)):
+                for name, blk in blocks.items():
+                    if not isinstance(blk, Block):
+                        continue
+                    p = f"{prefix}.{name}"
+                    items.append((p + ".c.bf16", blk.emb_linear))
+                    if blk.use_attention and blk.fused_qkv:
+                        items.append((p + ".c_qk.bf16", blk.emb_linear_qkv))
+                    elif blk.use_attention:
+                        items.append((p + ".c_qk.bf16", blk.emb_linear_qk))
+                        items.append((p + ".c_v.bf16", blk.emb_linear_v))
+            self._emb_items = items
+        return self._emb_items
+
     def refresh_weights(self) -> None:
         training = self.net.training
         stale_all = training != self.training
@@ -185,6 +203,21 @@ class _Plan:
                                                 qkv_head_dim=max(-qk_dim, 0), pad_rows=pad_rows,
                                                 row_stride=row_stride, out=self.prepped.get(key))
             self.versions[key] = ver
+        # Embedding projections (inference): the one launch that computes every block's emb_linear* streams all of their
+        # weights (a quarter of the UNet's parameters) for a handful of rows of emb, so it is bound by reading them: keep a
+        # bf16 copy (what the reference's autocast forward multiplies with, mp_tools.py:364) instead of the fp32 masters.
+        if not training:
+            for key, conv in self._emb_convs():
+                w = conv.weight
+                if w.dtype == torch.bfloat16:
+                    continue
+                ver = _ver(w)
+                if stale_all or self.versions.get(key) != ver or key not in self.prepped:
+                    buf = self.prepped.get(key)
+                    if buf is None:
+                        buf = self.prepped[key] = torch.empty((w.shape[0], w.shape[1]), device=self.device, dtype=torch.bfloat16)
+                    buf.copy_(w.detach().view(w.shape[0], w.shape[1]))
+                    self.versions[key] = ver
         # Decoder "layer" blocks (inference): conv_skip reads the two operands of mp_cat directly (dd_mpconv_forward_cat), so
         # the concatenation is never written; the mp_cat weights (mp_tools.py:294-301) are folded into the weight's columns.
         # (Train mode normalises the weight rows inside the preparation, which does not commute with a column scale.)
@@ -228,7 +261,7 @@ class _Plan:
                     out = torch.empty((B, O), device=self.device, dtype=torch.float32)
                     outs[p + tag] = out
                     entries.append(dict(w=conv.weight.detach().view(O, I), gain=self.gain_ptr(gain), out=out,
-                                        groups=conv.groups, bias=1.0, normalize=False, conv=conv))
+                                        groups=conv.groups, bias=1.0, normalize=False, conv=conv, key=p + tag + ".bf16"))
                 add(".c", blk.emb_linear, blk.emb_gain)
                 if blk.use_attention and blk.fused_qkv:
                     add(".c_qk", blk.emb_linear_qkv, blk.emb_gain_qkv)      # scales the input of the fused projection
@@ -245,6 +278,8 @@ class _Plan:
             for e in st["entries"]:
                 conv = e["conv"]
                 e["w"] = conv.weight.detach().view(conv.weight.shape[0], conv.weight.shape[1])
+                if not self.net.training and e["key"] in self.prepped:      # refresh_weights keeps the bf16 copy current
+                    e["w"] = self.prepped[e["key"]]
                 e["normalize"] = self.net.training
             st["descs"], st["max_o"] = ops.make_affine_descs(st["entries"], self.device)
             st["training"] = self.net.training
