@@ -272,6 +272,65 @@ __global__ void noise_embedding_kernel(const float* __restrict__ sigma, const fl
     }
 }
 
+// One warp per output row.  The launch streams every emb_linear* weight of the UNet (a quarter of its parameters) for a few
+// rows of emb, so it is bound by reading them: 16-byte loads (8 bf16 / 2 x 4 fp32 per lane and trip) whenever the rows allow.
+template <bool kBf16>
+__device__ __forceinline__ void load_w8(const void* w, size_t i, float (&f)[8]) {      // i % 8 == 0, 16-byte aligned
+    if constexpr (kBf16) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(w) + i));
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 t = unpack_bf16x2(u[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+    } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(w) + i));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(w) + i) + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void emb_affine_row(const dd_affine_desc& d, const float* __restrict__ e0, int o, int lane, int B,
+                                               int cemb, float gain) {
+    const bool vec = d.I % 8 == 0 && (reinterpret_cast<uintptr_t>(d.w) & 15u) == 0 &&
+                     (reinterpret_cast<uintptr_t>(e0) & 15u) == 0 && cemb % 4 == 0;
+    for (int b0 = 0; b0 < B; b0 += 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float ss = 0.f;
+        if (vec) {
+            for (int i = lane * 8; i < d.I; i += 256) {
+                float wv[8];
+                load_w8<kBf16>(d.w, (size_t)o * d.I + i, wv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) ss += wv[k] * wv[k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (b0 + j < B) {
+                        const float4* e = reinterpret_cast<const float4*>(e0 + (size_t)(b0 + j) * cemb + i);
+                        const float4 ea = __ldg(e), eb = __ldg(e + 1);
+                        acc[j] += wv[0] * ea.x + wv[1] * ea.y + wv[2] * ea.z + wv[3] * ea.w + wv[4] * eb.x + wv[5] * eb.y +
+                                  wv[6] * eb.z + wv[7] * eb.w;
+                    }
+            }
+        } else {
+            for (int i = lane; i < d.I; i += 32) {
+                const float wv = load_w<kBf16>(d.w, (size_t)o * d.I + i);
+                ss += wv * wv;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (b0 + j < B) acc[j] += wv * e0[(size_t)(b0 + j) * cemb + i];
+            }
+        }
+        ss = warp_sum(ss);
+        float scale = gain * rsqrtf((float)d.I);
+        if (d.normalize) scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)d.I));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = warp_sum(acc[j]);
+            if (lane == 0 && b0 + j < B) d.out[(size_t)(b0 + j) * d.O + o] = d.bias + a * scale;
+        }
+    }
+}
+
 __global__ void emb_affine_kernel(const dd_affine_desc* __restrict__ descs, const float* __restrict__ emb, int B,
                                   int cemb) {
     ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
@@ -283,25 +342,8 @@ __global__ void emb_affine_kernel(const dd_affine_desc* __restrict__ descs, cons
     const int g = o / (d.O / d.groups);
     const float* e0 = emb + (size_t)g * d.I;
     const float gain = d.gain ? *d.gain : 1.f;
-    for (int b0 = 0; b0 < B; b0 += 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        float ss = 0.f;
-        for (int i = lane; i < d.I; i += 32) {
-            const float wv = d.w_is_bf16 ? load_w<true>(d.w, (size_t)o * d.I + i) : load_w<false>(d.w, (size_t)o * d.I + i);
-            ss += wv * wv;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (b0 + j < B) acc[j] += wv * e0[(size_t)(b0 + j) * cemb + i];
-        }
-        ss = warp_sum(ss);
-        float scale = gain * rsqrtf((float)d.I);
-        if (d.normalize) scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)d.I));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float a = warp_sum(acc[j]);
-            if (lane == 0 && b0 + j < B) d.out[(size_t)(b0 + j) * d.O + o] = d.bias + a * scale;
-        }
-    }
+    if (d.w_is_bf16) emb_affine_row<true>(d, e0, o, lane, B, cemb, gain);
+    else emb_affine_row<false>(d, e0, o, lane, B, cemb, gain);
 }
 
 
