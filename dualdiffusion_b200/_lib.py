@@ -168,6 +168,10 @@ _SIGNATURES = {
     "dd_mel_linearize": (c_int, [c_void_p, c_void_p, c_long, c_float, c_float, c_void_p]),
     "dd_dae_enc_patches": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_dae_latents_pool": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_pack_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_unpack_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_patches5x5": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "dd_conv5x5_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dd_sampler_cfg_lerp": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_long, c_void_p]),
     "dd_conv_trace_read": (c_int, [c_void_p, c_int, c_void_p]),
     "dd_roll_pad_w": (c_int, [c_void_p, c_void_p, c_long, c_int, c_int, c_int, c_int, c_void_p]),

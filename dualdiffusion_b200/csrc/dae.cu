@@ -383,6 +383,141 @@ __global__ void dae_latents_pool_kernel(const __nv_bfloat16* __restrict__ f, flo
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// dae_edm2_q4.DAE (modules/daes/dae_edm2_q4.py): the plain 2-D sibling of DAE_D3 -- stereo is a channel pair, every
+// convolution a zero-padded MPConv (mp_tools.py:357-373).  Only the ends of the network need kernels of their own.
+// ------------------------------------------------------------------------------------------
+// fp32 NCHW (B, C, H, W) -> bf16 NHWC [B][H][W][Cpad]; channel `ones_channel` (>= C, or < 0 for none) is the constant 1
+// that carries a convolution bias (centre-tap weight column), the other padding channels are zero.
+__global__ void pack_nhwc_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int C, int H, int W, int nvec,
+                                 int ones_channel) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
+    const unsigned total = (unsigned)B * H * W * nvec;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned pix = idx / (unsigned)nvec;
+        const int v = (int)(idx - pix * (unsigned)nvec);
+        const unsigned b = pix / (unsigned)(H * W);
+        const unsigned hw = pix - b * (unsigned)(H * W);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = v * 8 + j;
+            f[j] = c < C ? __ldg(x + ((size_t)b * C + c) * H * W + hw) : (c == ones_channel ? 1.f : 0.f);
+        }
+        out[idx] = pack8d(f);
+    }
+}
+
+// bf16 NHWC [B][H][W][Cpad] -> fp32 NCHW (B, C, H, W), the first C channels.
+__global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int B, int C, int H, int W,
+                                   int Cpad) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
+    const unsigned total = (unsigned)B * C * H * W;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned hw = idx % (unsigned)(H * W);
+        const unsigned bc = idx / (unsigned)(H * W);
+        const unsigned b = bc / (unsigned)C, c = bc - b * (unsigned)C;
+        out[idx] = __bfloat162float(x[((size_t)b * H * W + hw) * Cpad + c]);
+    }
+}
+
+// conv_in (5,5) of a C-channel fp32 image (C = 2) as a K = cols GEMM: patch[pix][tap*C + c], tap = ky*5 + kx, zeros outside
+// the image, column 25*C the constant 1 (the bias column), zero above.
+__global__ void patches5x5_kernel(const float* __restrict__ x, uint4* __restrict__ out, int B, int C, int H, int W, int vecs) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
+    const unsigned total = (unsigned)B * H * W * vecs;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned pix = idx / (unsigned)vecs;
+        const int v = (int)(idx - pix * (unsigned)vecs);
+        const unsigned row = pix / (unsigned)W;
+        const int w = (int)(pix - row * (unsigned)W);
+        const int b = (int)(row / (unsigned)H);
+        const int h = (int)(row - (unsigned)b * (unsigned)H);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = v * 8 + j;
+            float val = 0.f;
+            if (k < 25 * C) {
+                const int tap = k / C, c = k - tap * C;
+                const int hh = h + tap / 5 - 2, ww = w + tap % 5 - 2;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + (((size_t)b * C + c) * H + hh) * W + ww);
+            } else if (k == 25 * C) {
+                val = 1.f;
+            }
+            f[j] = val;
+        }
+        out[idx] = pack8d(f);
+    }
+}
+
+// conv_out (5,5), C -> Cout <= 4 dense, zero padding, times *gain_dev: direct convolution on CUDA cores (the layer is
+// bound by reading the level-0 activation once; 25 C Cout MACs per pixel).  A warp owns 32 consecutive pixels of a row:
+// lanes split the channels (two per lane and trip), every pixel's sum is reduced across the warp and kept by the lane of
+// that pixel, so that the fp32 NCHW result is written with coalesced stores.
+//   x [B][H][W][C] bf16, w fp32 [Cout][25][C] pre-scaled by 1/sqrt(25 C), out fp32 (B, Cout, H, W)
+constexpr int kC5dWarps = 8;
+constexpr int kC5dMaxOut = 4;
+template <int Cout>
+__global__ void __launch_bounds__(kC5dWarps * 32)
+conv5x5_dense_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wq, const float* __restrict__ gain_dev,
+                     float* __restrict__ out, int B, int H, int W, int C) {
+    ptx::grid_launch_dependents();
+    ptx::grid_dependency_wait();
+    extern __shared__ float ws[];      // [Cout][25][C]
+    for (int i = threadIdx.x; i < Cout * 25 * C; i += blockDim.x) ws[i] = wq[i];
+    __syncthreads();
+    const float gain = gain_dev ? *gain_dev : 1.f;
+    const int lane = threadIdx.x & 31;
+    const int strips_w = (W + 31) / 32;
+    const unsigned total = (unsigned)B * H * strips_w;
+    for (unsigned sidx = blockIdx.x * kC5dWarps + (threadIdx.x >> 5); sidx < total; sidx += gridDim.x * kC5dWarps) {
+        const unsigned row = sidx / (unsigned)strips_w;
+        const int w0 = (int)(sidx - row * (unsigned)strips_w) * 32;
+        const int b = (int)(row / (unsigned)H);
+        const int h = (int)(row - (unsigned)b * (unsigned)H);
+        float res[Cout];
+#pragma unroll
+        for (int o = 0; o < Cout; ++o) res[o] = 0.f;
+        const int npix = min(32, W - w0);
+        for (int p = 0; p < npix; ++p) {
+            float acc[Cout];
+#pragma unroll
+            for (int o = 0; o < Cout; ++o) acc[o] = 0.f;
+            for (int ky = 0; ky < 5; ++ky) {
+                const int hh = h + ky - 2;
+                if (hh < 0 || hh >= H) continue;
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int ww = w0 + p + kx - 2;
+                    if (ww < 0 || ww >= W) continue;
+                    const __nv_bfloat16* xp = x + (((size_t)b * H + hh) * W + ww) * C;
+                    const float* wt = ws + (ky * 5 + kx) * C;
+                    for (int c = lane * 2; c < C; c += 64) {
+                        const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(xp + c)));
+#pragma unroll
+                        for (int o = 0; o < Cout; ++o) {
+                            const float2 wv = *reinterpret_cast<const float2*>(wt + (size_t)o * 25 * C + c);
+                            acc[o] = fmaf(f.x, wv.x, fmaf(f.y, wv.y, acc[o]));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < Cout; ++o) {
+                const float t = warp_sum(acc[o]);
+                if (lane == p) res[o] = t;
+            }
+        }
+        if (lane < npix) {
+#pragma unroll
+            for (int o = 0; o < Cout; ++o) out[(((size_t)b * Cout + o) * H + h) * W + w0 + lane] = res[o] * gain;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int dd_weight_prep_z2(const void* w, int w_is_bf16, void* out, int O, int I, int kz, int taps,
@@ -526,6 +661,67 @@ extern "C" int dd_dae_latents_pool(const void* f, float* out, int B, int L, int 
     if (total == 0) return 0;
     DD_CHECK_CUDA(dd_launch_pdl(dae_latents_pool_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(f), out, B, L, H, W,
                                                                         pw, Cst, ratio));
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_pack_nhwc(const float* x, void* out, int B, int C, int H, int W, int Cpad, int ones_channel, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && out && C > 0 && Cpad >= C && Cpad % 8 == 0 && ones_channel < Cpad && (ones_channel < 0 || ones_channel >= C),
+               "dd_pack_nhwc: bad arguments");
+    const long total = (long)B * H * W * (Cpad / 8);
+    if (total == 0) return 0;
+    DD_REQUIRE(total < (1L << 31) - (1L << 24), "dd_pack_nhwc: tensor too large");
+    DD_CHECK_CUDA(dd_launch_pdl(pack_nhwc_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, x, static_cast<uint4*>(out), B, C, H, W,
+                                Cpad / 8, ones_channel));
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_unpack_nchw(const void* x, float* out, int B, int C, int H, int W, int Cpad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && out && C > 0 && Cpad >= C, "dd_unpack_nchw: bad arguments");
+    const long total = (long)B * C * H * W;
+    if (total == 0) return 0;
+    DD_REQUIRE(total < (1L << 31) - (1L << 24), "dd_unpack_nchw: tensor too large");
+    DD_CHECK_CUDA(dd_launch_pdl(unpack_nchw_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(x), out, B, C,
+                                H, W, Cpad));
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_patches5x5(const float* x, void* out, int B, int C, int H, int W, int cols, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && out && C > 0, "dd_patches5x5: bad arguments");
+    DD_REQUIRE(cols == 64 || cols == 128, "dd_patches5x5: patch width %d unsupported (64 or 128)", cols);
+    DD_REQUIRE(25 * C + 1 <= cols, "dd_patches5x5: in_channels=%d unsupported (25*C + 1 must be <= %d)", C, cols);
+    const long total = (long)B * H * W * (cols / 8);
+    if (total == 0) return 0;
+    DD_REQUIRE(total < (1L << 31) - (1L << 24), "dd_patches5x5: tensor too large");
+    DD_CHECK_CUDA(dd_launch_pdl(patches5x5_kernel, dim3(grid_for_d(total, 256)), dim3(256), 0, stream, x, static_cast<uint4*>(out), B, C, H, W,
+                                cols / 8));
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_conv5x5_dense(const void* x, const float* w, const float* gain_dev, float* out, int B, int H, int W, int C,
+                                int Cout, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(x && w && out, "dd_conv5x5_dense: null pointer");
+    DD_REQUIRE(C > 0 && C % 2 == 0 && Cout >= 1 && Cout <= kC5dMaxOut, "dd_conv5x5_dense: C=%d Cout=%d unsupported", C, Cout);
+    const size_t smem = (size_t)Cout * 25 * C * sizeof(float);
+    static_assert(kC5dMaxOut == 4, "dispatch below");
+    DD_REQUIRE(smem <= 200 * 1024, "dd_conv5x5_dense: weights (%zu bytes) do not fit in shared memory", smem);
+    const long strips = (long)B * H * ((W + 31) / 32);
+    if (strips == 0) return 0;
+    DD_REQUIRE(strips < (1L << 31) - (1L << 24), "dd_conv5x5_dense: tensor too large");
+    auto kernel = Cout == 1 ? conv5x5_dense_kernel<1> : Cout == 2 ? conv5x5_dense_kernel<2> : Cout == 3 ? conv5x5_dense_kernel<3>
+                                                                                                       : conv5x5_dense_kernel<4>;
+    if (smem > 48 * 1024) DD_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const long want = (strips + kC5dWarps - 1) / kC5dWarps;
+    const int grid = (int)(want < (long)dd_num_sms() * 8 ? want : (long)dd_num_sms() * 8);
+    DD_CHECK_CUDA(dd_launch_pdl(kernel, dim3(grid), dim3(kC5dWarps * 32), smem, stream, static_cast<const __nv_bfloat16*>(x), w, gain_dev, out, B, H,
+                                W, C));
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -808,3 +808,41 @@ def dae_latents_pool(f: Tensor, latent_channels: int, pw: int, ratio: int) -> Te
     L.check(L.load().dd_dae_latents_pool(L.ptr(f), L.ptr(out), B, latent_channels, H, W, pw, Cst, ratio, L.stream_ptr()))
     _count()
     return out
+
+
+# ---- dae_edm2_q4.DAE ends (csrc/dae.cu) ----
+def pack_nhwc(x: Tensor, cpad: int, ones_channel: int = -1) -> Tensor:
+    """fp32 NCHW -> bf16 NHWC padded to `cpad` channels; `ones_channel` carries a convolution bias (dd_pack_nhwc)."""
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, cpad), device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_pack_nhwc(L.ptr(x), L.ptr(out), B, C, H, W, cpad, ones_channel, L.stream_ptr()))
+    _count()
+    return out
+
+
+def unpack_nchw(x: Tensor, channels: int) -> Tensor:
+    """bf16 NHWC -> fp32 NCHW, the first `channels` channels (dd_unpack_nchw)."""
+    B, H, W, Cpad = x.shape
+    out = torch.empty((B, channels, H, W), device=x.device, dtype=torch.float32)
+    L.check(L.load().dd_unpack_nchw(L.ptr(x), L.ptr(out), B, channels, H, W, Cpad, L.stream_ptr()))
+    _count()
+    return out
+
+
+def patches5x5(x: Tensor, cols: int = 64) -> Tensor:
+    """Zero-padded 5x5 patches of an fp32 NCHW image plus the bias column, as the K = cols operand of conv_in (dd_patches5x5)."""
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, cols), device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().dd_patches5x5(L.ptr(x), L.ptr(out), B, C, H, W, cols, L.stream_ptr()))
+    _count()
+    return out
+
+
+def conv5x5_dense(x: Tensor, w: Tensor, gain: Optional[Tensor]) -> Tensor:
+    """conv_out (5,5) C -> Cout <= 4 on bf16 NHWC, fp32 NCHW result; w fp32 [Cout][25][C] pre-scaled (dd_conv5x5_dense)."""
+    B, H, W, C = x.shape
+    cout = w.shape[0]
+    out = torch.empty((B, cout, H, W), device=x.device, dtype=torch.float32)
+    L.check(L.load().dd_conv5x5_dense(L.ptr(x), L.ptr(w), L.ptr(gain), L.ptr(out), B, H, W, C, cout, L.stream_ptr()))
+    _count()
+    return out

@@ -421,6 +421,21 @@ DD_API int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int W, 
  * (B, 2L, H/ratio, W/ratio), channel c*2+z.                                                                              */
 DD_API int dd_dae_latents_pool(const void* f, float* out, int B, int L, int H, int W, int pw, int Cst, int ratio, void* stream);
 
+/* dae_edm2_q4.DAE (modules/daes/dae_edm2_q4.py:170-300): 2-D zero-padded MPConv network; the blocks run on
+ * dd_mpconv_forward / dd_pixnorm_silu / dd_avgpool2 / dd_cat_silu, these four entry points are its two ends.
+ * conv_latents_in input (:292): fp32 NCHW (B, C, H, W) -> bf16 NHWC [B][H][W][Cpad]; channel `ones_channel` (>= C, or < 0
+ * for none) is the constant 1 that multiplies the bias column of the prepared weight (mp_tools.py:370-371).          */
+DD_API int dd_pack_nhwc(const float* x, void* out, int B, int C, int H, int W, int Cpad, int ones_channel, void* stream);
+/* conv_latents_out result (:281): bf16 NHWC [B][H][W][Cpad] -> fp32 NCHW (B, C, H, W), the first C channels.        */
+DD_API int dd_unpack_nchw(const void* x, float* out, int B, int C, int H, int W, int Cpad, void* stream);
+/* conv_in (5,5) with bias (:232) as a K = cols GEMM: x fp32 (B, C, H, W) -> bf16 [B][H][W][cols], column tap*C + c the
+ * zero-padded 5x5 patch (tap = ky*5 + kx), column 25*C the constant 1, zero above; cols 64 or 128.                   */
+DD_API int dd_patches5x5(const float* x, void* out, int B, int C, int H, int W, int cols, void* stream);
+/* conv_out (5,5), C -> Cout <= 4 dense, zero padding, times *gain_dev (:299): x bf16 [B][H][W][C], w fp32 [Cout][25][C]
+ * pre-scaled by 1/sqrt(25 C), out fp32 (B, Cout, H, W).                                                              */
+DD_API int dd_conv5x5_dense(const void* x, const float* w, const float* gain_dev, float* out, int B, int H, int W, int C,
+                            int Cout, void* stream);
+
 /* Diagnostic (tuning only, not on the product path): with DD_CONV_TRACE=1 in the environment when the library is loaded,
  * 3x3 layers of >= 8 rows run a traced instantiation of the halo kernel that records, for the first 4 CTAs and their
  * first 64 tiles, clock64 stamps of the three warp roles (8 slots: producer stage-free / issued, MMA accumulator-free /

@@ -202,6 +202,37 @@ def test_q4_ddec_oracle_vs_golden_reference():
         assert rel_err(d - c_skip * g["x"], g["d"] - c_skip * g["x"]) < 3 * tol
 
 
+def test_dae_q4_oracle_matches_reference_golden():
+    """dae_edm2_q4.DAE restatement (encode and decode, with and without add_pixel_norm) against the
+    unmodified reference module run in fp32 on CPU (tests/golden/make_golden_dae_q4.py)."""
+    from oracle import dae_q4_oracle as qo
+    g = load_golden("dae_q4_small.pt")
+    for tag, case in g.items():
+        spec = qo.small_dae_q4_spec()
+        spec.add_pixel_norm = tag == "pixel_norm"
+        sd = qo.synth_dae_q4_state_dict(spec, seed=0)
+        assert abs(float(sum(v.double().abs().sum() for v in sd.values())) - case["weight_checksum"]) < 1e-6 * case["weight_checksum"]
+        assert rel_err(qo.dae_q4_encode(sd, spec, case["mel"]), case["latents"]) < 1e-5, tag
+        assert rel_err(qo.dae_q4_decode(sd, spec, case["lat_in"]), case["decoded"]) < 1e-5, tag
+
+
+def test_dae_q4_module_state_dict_matches_reference_layout():
+    """The product module's parameters / buffers carry the reference's names and shapes (the golden's weights, which the
+    unmodified reference loaded with strict=True, load here with strict=True too) and it refuses to run without CUDA."""
+    from oracle import dae_q4_oracle as qo
+    from dualdiffusion_b200.modules.daes.dae_edm2_q4 import DAE, DAE_Config
+    spec = qo.small_dae_q4_spec()
+    sd = qo.synth_dae_q4_state_dict(spec, seed=0)
+    dae = DAE(DAE_Config(model_channels=spec.model_channels, channel_mult_enc=tuple(spec.channel_mult_enc),
+                         channel_mult_dec=tuple(spec.channel_mult_dec), num_enc_layers_per_block=spec.num_enc_layers_per_block,
+                         num_dec_layers_per_block=spec.num_dec_layers_per_block)).eval()
+    dae.load_state_dict(sd, strict=True)
+    assert {k: tuple(v.shape) for k, v in dae.state_dict().items()} == qo.dae_q4_state_dict_shapes(spec)
+    assert tuple(dae.get_latent_shape((2, 2, 32, 72))) == load_golden("dae_q4_small.pt")["plain"]["latent_shape"]
+    with torch.no_grad(), pytest.raises(RuntimeError):
+        dae.decode(torch.zeros(1, spec.latent_channels, 4, 4), None)
+
+
 def test_mdct_oracle_vs_golden_reference():
     """MCLT / inverse MCLT / PSD / mel -> PSD restatements against the reference's own outputs."""
     from oracle import format_oracle as fo
