@@ -67,6 +67,36 @@ __global__ void mel_linearize_kernel(const float* __restrict__ mel, float* __res
     }
 }
 
+// ms_mdct_dual_2.py:203-216: out = ((sum_i mel_i[s][f][t] * ww[f][i]) ** exponent + offset) * inv_scale over the n_win
+// per-window mel spectrograms mels [n_win][S][F][T] (each already filtered: the blend is per mel filter, after the bank).
+__global__ void mel_blend_kernel(const float* __restrict__ mels, const float* __restrict__ ww, int n_win, long S, int F, int T,
+                                 float exponent, float offset, float inv_scale, float* __restrict__ out) {
+    const long total = S * F * T;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int f = (int)((idx / T) % F);
+        float acc = 0.f;
+        for (int i = 0; i < n_win; ++i) acc += mels[(long)i * total + idx] * __ldg(ww + f * n_win + i);
+        out[idx] = (powf(acc, exponent) + offset) * inv_scale;
+    }
+}
+
+// ms_mdct_dual_2.py:275-289 on coefficient rows y [S][2N][T] (rows 0..N-1 real, N..2N-1 imaginary, unscaled MCLT):
+//   |z| -> phase = clip(re / max(|z|, 1e-20), -1, 1) * phase_mul;  psd = ((|z| * inv_density[k]) ** exponent + offset) * inv_scale
+__global__ void mdct_phase_psd_kernel(const float* __restrict__ y, const float* __restrict__ inv_density, int S, int N, int T,
+                                      float exponent, float offset, float inv_scale, float phase_mul, float* __restrict__ phase,
+                                      float* __restrict__ psd) {
+    const long total = (long)S * N * T;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long rt = idx % ((long)N * T);
+        const long s = idx / ((long)N * T);
+        const int k = (int)(rt / T);
+        const float re = y[s * 2 * N * T + rt], im = y[s * 2 * N * T + (long)N * T + rt];
+        const float mag = sqrtf(re * re + im * im);
+        phase[idx] = fminf(fmaxf(re / fmaxf(mag, 1e-20f), -1.f), 1.f) * phase_mul;
+        psd[idx] = (powf(mag * __ldg(inv_density + k), exponent) + offset) * inv_scale;
+    }
+}
+
 }  // namespace
 
 extern "C" int dd_frame_reflect(const float* raw, float* out, int S, long L, int T, int block_width, int hop, int pad_left,
@@ -102,6 +132,25 @@ extern "C" int dd_mel_linearize(const float* mel, float* out, long n, float offs
     DD_REQUIRE(mel && out && n >= 0, "dd_mel_linearize: bad arguments");
     if (n == 0) return 0;
     mel_linearize_kernel<<<grid_for_m(n, 256), 256, 0, stream>>>(mel, out, n, offset, inv_exponent);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_mel_blend(const float* mels, const float* ww, int n_win, int S, int F, int T, float exponent, float offset,
+                            float inv_scale, float* out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(mels && ww && out && n_win >= 1 && S > 0 && F > 0 && T > 0, "dd_mel_blend: bad arguments");
+    mel_blend_kernel<<<grid_for_m((long)S * F * T, 256), 256, 0, stream>>>(mels, ww, n_win, S, F, T, exponent, offset, inv_scale, out);
+    DD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dd_mdct_phase_psd(const float* y, const float* inv_density, int S, int N, int T, float exponent, float offset,
+                                 float inv_scale, float phase_mul, float* phase, float* psd, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DD_REQUIRE(y && inv_density && phase && psd && S > 0 && N > 0 && T > 0, "dd_mdct_phase_psd: bad arguments");
+    mdct_phase_psd_kernel<<<grid_for_m((long)S * N * T, 256), 256, 0, stream>>>(y, inv_density, S, N, T, exponent, offset, inv_scale,
+                                                                             phase_mul, phase, psd);
     DD_CHECK_LAUNCH();
     return 0;
 }

@@ -308,12 +308,13 @@ def mp_fourier(x: Tensor, freqs: Tensor, phases: Tensor) -> Tensor:
 
 def stft_mel(raw: Tensor, window: Tensor, tw: Tensor, tw_half: Tensor, n_fft: int, hop: int, fb: dict,
              exponent: float, mean: float, scale: float, window2: Optional[Tensor] = None,
-             coef1: Optional[Tensor] = None, coef2: Optional[Tensor] = None) -> Tensor:
+             coef1: Optional[Tensor] = None, coef2: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
     """raw [S, L] fp32 -> [S, n_filters, 1 + L // hop] fp32 (mel-STFT encode)."""
     S, Ln = raw.shape
     T = 1 + Ln // hop
     nf = fb["start"].numel()
-    out = torch.empty((S, nf, T), device=raw.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((S, nf, T), device=raw.device, dtype=torch.float32)
     L.check(L.load().dd_stft_mel(L.ptr(raw), S, Ln, L.ptr(window), L.ptr(window2), L.ptr(coef1), L.ptr(coef2), L.ptr(tw),
                                  L.ptr(tw_half), n_fft, hop,
                                  L.ptr(fb["start"]), L.ptr(fb["count"]), L.ptr(fb["offset"]), L.ptr(fb["weight"]), nf,
@@ -846,3 +847,25 @@ def conv5x5_dense(x: Tensor, w: Tensor, gain: Optional[Tensor]) -> Tensor:
     L.check(L.load().dd_conv5x5_dense(L.ptr(x), L.ptr(w), L.ptr(gain), L.ptr(out), B, H, W, C, cout, L.stream_ptr()))
     _count()
     return out
+
+
+# ---- MS_MDCT_DualFormat, second lineage (csrc/mdct.cu) ----
+def mel_blend(mels: Tensor, ww: Tensor, exponent: float, offset: float, inv_scale: float) -> Tensor:
+    """mels [n_win][S][F][T], ww [F][n_win] -> ((sum_i mels[i] * ww[:, i]) ** exponent + offset) * inv_scale (dd_mel_blend)."""
+    n_win, S, F, T = mels.shape
+    out = torch.empty((S, F, T), device=mels.device, dtype=torch.float32)
+    L.check(L.load().dd_mel_blend(L.ptr(mels), L.ptr(ww), n_win, S, F, T, exponent, offset, inv_scale, L.ptr(out), L.stream_ptr()))
+    _count()
+    return out
+
+
+def mdct_phase_psd(y: Tensor, inv_density: Tensor, exponent: float, offset: float, inv_scale: float,
+                   phase_mul: float) -> Tuple[Tensor, Tensor]:
+    """MCLT rows y [S][2N][T] -> (phase, psd) [S][N][T] (dd_mdct_phase_psd)."""
+    S, N2, T = y.shape
+    phase = torch.empty((S, N2 // 2, T), device=y.device, dtype=torch.float32)
+    psd = torch.empty_like(phase)
+    L.check(L.load().dd_mdct_phase_psd(L.ptr(y), L.ptr(inv_density), S, N2 // 2, T, exponent, offset, inv_scale, phase_mul,
+                                       L.ptr(phase), L.ptr(psd), L.stream_ptr()))
+    _count()
+    return phase, psd

@@ -414,6 +414,16 @@ DD_API int dd_mdct_ola(const float* y, float* out, int S, int T, int N, void* st
 /* ms_mdct_dual.py:261-265: out = clip(mel - offset, 0) ** inv_exponent.                                               */
 DD_API int dd_mel_linearize(const float* mel, float* out, long n, float offset, float inv_exponent, void* stream);
 
+/* MS_MDCT_DualFormat, second lineage (modules/formats/ms_mdct_dual_2.py).  raw_to_mel_spec (:198-216): the three per-window
+ * mel spectrograms (dd_stft_mel, one window each) are blended per mel filter and compressed:
+ *   out[s][f][t] = ((sum_i mels[i][s][f][t] * ww[f][i]) ** exponent + offset) * inv_scale,  mels [n_win][S][F][T].       */
+DD_API int dd_mel_blend(const float* mels, const float* ww, int n_win, int S, int F, int T, float exponent, float offset,
+                        float inv_scale, float* out, void* stream);
+/* raw_to_mdct_phase_psd (:275-289) on the unscaled MCLT rows y [S][2N][T] (real rows, then imaginary rows):
+ *   phase = clip(re / max(|z|, 1e-20), -1, 1) * phase_mul,  psd = ((|z| * inv_density[k]) ** exponent + offset) * inv_scale. */
+DD_API int dd_mdct_phase_psd(const float* y, const float* inv_density, int S, int N, int T, float exponent, float offset,
+                             float inv_scale, float phase_mul, float* phase, float* psd, void* stream);
+
 /* DAE_D3.encode (modules/daes/dae_edm2_d3.py:342-354).  Input assembly for conv_in (1,5,5): per stereo side the 5x5 patch
  * of [mel, 1] (reflection along W, zeros along H), 50 values padded to 64 -> [B][H][W+2pw][128] bf16; mel fp32 (B,2,H,W). */
 DD_API int dd_dae_enc_patches(const float* mel, void* out, int B, int H, int W, int pw, void* stream);

@@ -333,3 +333,175 @@ def _mel_filterbank_bins(spec: MSDualSpec, num_stft_bins: int) -> Tensor:
     fb = torch.max(torch.zeros(1), torch.min((-1.0 * slopes[:, :-2]) / f_diff[:-1], slopes[:, 2:] / f_diff[1:]))
     enorm = 2.0 / (f_pts[2:spec.ms_num_frequencies + 2] - f_pts[:spec.ms_num_frequencies])
     return fb * enorm.unsqueeze(0)
+
+
+# ======================================================================================================================
+# MS_MDCT_DualFormat, second lineage (src/modules/formats/ms_mdct_dual_2.py): three Hann-power windows of
+# one 4096-sample STFT blended per mel filter, and the MDCT of utils/mdct (sin window, hop = win/2, reflect padding).
+# Pinned by tests/golden/ms_dual2_small.pt (reference output, tests/golden/make_golden_ms_dual2.py).
+# ======================================================================================================================
+@dataclass
+class MSDual2Spec:
+    """ms_mdct_dual_2.py:34-91 defaults."""
+    sample_rate: int = 32000
+    raw_to_mdct_scale: float = 0.00395184212251821011433253029603
+    mdct_psd_scale: float = 0.07179056842448940381561506832112
+    mdct_psd_offset: float = -0.1806843343919556
+    mdct_psd_exponent: float = 0.25
+    mdct_phase_scale: float = 1
+    mdct_window_len: int = 512
+    raw_to_mel_spec_scale: float = 0.48693139085749312574067728443989
+    raw_to_mel_spec_offset: float = -1.530891040808645
+    mel_spec_to_linear_scale: float = 15.11100987193986714324861053997
+    mel_spec_to_linear_offset: float = 0
+    ms_abs_exponent: float = 0.25
+    ms_freq_min: float = 0
+    ms_num_filters: int = 256
+    ms_ideal_num_filter_bins: float = 3
+    ms_window_length: int = 4096
+    ms_blend_sharpness: float = 30
+    ms_window_exponents: tuple = (9, 32, 112)
+
+    @property
+    def hop(self) -> int:
+        return self.mdct_window_len // 2
+
+    @property
+    def num_stft_bins(self) -> int:
+        return self.ms_window_length // 2 + 1
+
+
+def ms2_windows(spec: MSDual2Spec) -> Tensor:
+    """:100-106 -- hann ** exponent, each scaled to unit RMS."""
+    hann = torch.hann_window(spec.ms_window_length, periodic=True)
+    w = torch.stack([hann ** e for e in spec.ms_window_exponents], dim=0)
+    return w / w.pow(2).mean(dim=1, keepdim=True).pow(0.5)
+
+
+def ms2_mel_points(spec: MSDual2Spec, n: int) -> Tensor:
+    """frequency_scale.py:144-149 (mel scale)."""
+    lo = 2595.0 * math.log10(1.0 + spec.ms_freq_min / 700.0)
+    hi = 2595.0 * math.log10(1.0 + (spec.sample_rate / 2) / 700.0)
+    return 700.0 * (10.0 ** (torch.linspace(lo, hi, n) / 2595.0) - 1.0)
+
+
+def ms2_slaney_filters(spec: MSDual2Spec) -> Tensor:
+    """FrequencyScale.get_filters (frequency_scale.py:150-169): triangular, slaney norm -> [bins][filters]."""
+    stft_freqs = torch.linspace(0, spec.sample_rate / 2, spec.num_stft_bins)
+    f_pts = ms2_mel_points(spec, spec.ms_num_filters + 2)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - stft_freqs.unsqueeze(1)
+    fb = torch.max(torch.zeros(1), torch.min((-1.0 * slopes[:, :-2]) / f_diff[:-1], slopes[:, 2:] / f_diff[1:]))
+    return fb * (2.0 / (f_pts[2:spec.ms_num_filters + 2] - f_pts[:spec.ms_num_filters])).unsqueeze(0)
+
+
+def ms2_filters(spec: MSDual2Spec) -> Tensor:
+    """:137-138 -- the filterbank the forward direction uses: every filter scaled to unit RMS over the bins."""
+    fb = ms2_slaney_filters(spec)
+    return fb / fb.pow(2).mean(dim=0, keepdim=True).pow(0.5)
+
+
+def ms2_filter_window_weights(spec: MSDual2Spec) -> Tensor:
+    """:121-150 -- per filter, a softmax-like preference over the three windows by how close the window's width is to the
+    width that gives the filter `ms_ideal_num_filter_bins` bins."""
+    import numpy as np
+    mel_freqs = ms2_mel_points(spec, spec.ms_num_filters + 2)
+    bandwidths = mel_freqs[2:] - mel_freqs[:-2]
+    num_filter_bins = bandwidths / spec.sample_rate * spec.num_stft_bins * 2
+    ideal = (spec.ms_ideal_num_filter_bins / num_filter_bins * spec.ms_window_length).to(torch.float64)
+    widths = torch.tensor([2 * np.arccos(2 ** (-1 / e)) / np.pi * 2 * spec.ms_window_length for e in spec.ms_window_exponents],
+                          dtype=torch.float64)
+    out = torch.zeros((spec.ms_num_filters, len(spec.ms_window_exponents)), dtype=torch.float32)
+    for i in range(spec.ms_num_filters):
+        ww = (-spec.ms_blend_sharpness * (ideal[i] / widths).log() ** 2).exp()
+        out[i] = (ww / ww.sum()).to(torch.float32)
+    return out
+
+
+def ms2_stft_mel_density(spec: MSDual2Spec) -> Tensor:
+    return (1127.0 / (700.0 + torch.linspace(0, spec.sample_rate / 2, spec.num_stft_bins))).view(1, 1, -1, 1)
+
+
+def ms2_raw_to_mel_spec(raw: Tensor, spec: MSDual2Spec) -> Tensor:
+    """:198-216."""
+    windows, filters, ww = ms2_windows(spec), ms2_filters(spec), ms2_filter_window_weights(spec)
+    density = ms2_stft_mel_density(spec)
+    blended = None
+    for i in range(len(spec.ms_window_exponents)):
+        packed = raw.reshape(raw.shape[0] * raw.shape[1], raw.shape[2])
+        st = torch.stft(packed, n_fft=spec.ms_window_length, hop_length=spec.hop, win_length=spec.ms_window_length,
+                        window=windows[i], center=True, pad_mode="reflect", normalized=True, onesided=True,
+                        return_complex=True).abs()
+        st = st.view(raw.shape[0], raw.shape[1], st.shape[1], st.shape[2]) / density
+        mel = torch.matmul(st.transpose(-1, -2), filters).transpose(-1, -2) * ww[:, i].view(1, 1, -1, 1)
+        blended = mel if blended is None else blended + mel
+    return (blended ** spec.ms_abs_exponent + spec.raw_to_mel_spec_offset) / spec.raw_to_mel_spec_scale
+
+
+def ms2_mel_spec_to_linear(mel_spec: Tensor, spec: MSDual2Spec) -> Tensor:
+    """:218-223 -- FrequencyScale.unscale(rectify=False) is the minimum-norm least-squares inverse of the (slaney, not the
+    RMS-normalised) filterbank (frequency_scale.py:130-142, driver gels)."""
+    lin = (mel_spec * spec.raw_to_mel_spec_scale - spec.raw_to_mel_spec_offset).clip(min=0) ** (1 / spec.ms_abs_exponent)
+    shape = lin.shape
+    fb = ms2_slaney_filters(spec)
+    sol = torch.linalg.lstsq(fb.transpose(-1, -2)[None], lin.reshape(-1, shape[-2], shape[-1]), driver="gels").solution
+    psd = sol.view(shape[:-2] + (spec.num_stft_bins, shape[-1])) * ms2_stft_mel_density(spec).pow(0.5)
+    return (psd[:, :, :-1, :] + spec.mel_spec_to_linear_offset) / spec.mel_spec_to_linear_scale
+
+
+def ms2_mdct_mel_density(spec: MSDual2Spec) -> Tensor:
+    hz = (torch.arange(spec.mdct_window_len // 2) + 0.5) * spec.sample_rate / spec.mdct_window_len
+    return (1127.0 / (700.0 + hz)).view(1, 1, -1, 1)
+
+
+def ms2_mclt(raw: Tensor, spec: MSDual2Spec) -> Tensor:
+    """utils/mdct/functional.py:9-79 with the sin window (windows.py:95-116), padding=True, return_complex=True."""
+    win = spec.mdct_window_len
+    hop = win // 2
+    window = torch.sin((torch.arange(win) + 0.5) / win * torch.pi)
+    n = raw.shape[-1]
+    shape = raw.shape
+    x = raw.float().flatten(end_dim=-2)
+    n_frames = int(math.ceil(n / hop)) + 1
+    x = torch.nn.functional.pad(x, (hop, (n_frames + 1) * hop - n), mode="reflect")
+    pre = torch.exp(-1j * torch.pi / win * torch.arange(0, win))
+    post = torch.exp(-1j * torch.pi / win * (win / 2 + 1) * torch.arange(0.5, win / 2 + 0.5))
+    fr = x.unfold(-1, win, hop) * window * pre
+    sp = torch.fft.fft(fr, dim=-1)[..., : win // 2] * post                        # [S][frames][bins]
+    sp = sp.transpose(-1, -2)
+    sp = sp.reshape(shape[:-1] + sp.shape[-2:])[..., :-1]
+    return sp * (1.0 / math.sqrt(win * (win // 2)))
+
+
+def ms2_raw_to_mdct(raw: Tensor, spec: MSDual2Spec) -> Tensor:
+    """:247-254 (no phase augmentation)."""
+    return ms2_mclt(raw, spec).real.contiguous() / ms2_mdct_mel_density(spec) / spec.raw_to_mdct_scale
+
+
+def ms2_mdct_to_raw(mdct: Tensor, spec: MSDual2Spec) -> Tensor:
+    """:256-261 + utils/mdct/functional.py:82-150."""
+    win = spec.mdct_window_len
+    hop = win // 2
+    window = torch.sin((torch.arange(win) + 0.5) / win * torch.pi)
+    sp = mdct * ms2_mdct_mel_density(spec) * spec.raw_to_mdct_scale
+    n_freqs, n_frames = sp.shape[-2:]
+    sp = sp / (1.0 / math.sqrt(win * (win // 2)))
+    shape = sp.shape
+    sp = sp.flatten(end_dim=-3)
+    pre = torch.exp(-1j * torch.pi / (2 * n_freqs) * (n_freqs + 1) * torch.arange(n_freqs))
+    post = torch.exp(-1j * torch.pi / (2 * n_freqs) * torch.arange(0.5 + n_freqs / 2, 2 * n_freqs + n_freqs / 2 + 0.5)) / n_freqs
+    y = torch.fft.fft(sp * pre.view(-1, 1), n=2 * n_freqs, dim=1) * post.view(-1, 1)
+    y = 2 * torch.real(y) * window.view(-1, 1)
+    wave = torch.nn.functional.fold(y, output_size=(1, hop * (n_frames + 1)), kernel_size=(1, win), stride=(1, hop))
+    wave = wave[..., hop:-hop]
+    return wave.reshape((*shape[:-2], -1))
+
+
+def ms2_raw_to_mdct_phase_psd(raw: Tensor, spec: MSDual2Spec):
+    """:275-289 (no phase augmentation)."""
+    z = ms2_mclt(raw, spec)
+    psd = z.abs()
+    phase = (z.real / psd.clip(min=1e-20)).clip(min=-1, max=1)
+    psd = (psd / ms2_mdct_mel_density(spec)).pow(spec.mdct_psd_exponent)
+    phase = phase * 2 ** 0.5
+    return phase / spec.mdct_phase_scale, (psd + spec.mdct_psd_offset) / spec.mdct_psd_scale

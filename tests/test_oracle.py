@@ -233,6 +233,51 @@ def test_dae_q4_module_state_dict_matches_reference_layout():
         dae.decode(torch.zeros(1, spec.latent_channels, 4, 4), None)
 
 
+def test_ms_dual2_oracle_vs_golden_reference():
+    """the second MS_MDCT_DualFormat lineage (three-window mel-STFT blended per filter, utils/mdct MDCT)
+    restated in oracle/format_oracle.py against the unmodified reference's outputs (tests/golden/make_golden_ms_dual2.py)."""
+    from oracle import format_oracle as fo
+    g = load_golden("ms_dual2_small.pt")
+    spec = fo.MSDual2Spec()
+    assert torch.equal(fo.ms2_filter_window_weights(spec), g["window_weights"])
+    assert rel_err(fo.ms2_raw_to_mel_spec(g["raw"], spec), g["mel"]) < 1e-6
+    assert rel_err(fo.ms2_mel_spec_to_linear(g["mel"], spec), g["mel_linear"]) < 1e-5
+    assert rel_err(fo.ms2_raw_to_mdct(g["raw"], spec), g["mdct"]) < 1e-6
+    assert rel_err(fo.ms2_raw_to_mdct(g["raw_odd"], spec), g["mdct_odd"]) < 1e-6
+    assert rel_err(fo.ms2_mdct_to_raw(g["mdct"], spec), g["raw_back"]) < 1e-6
+    phase, psd = fo.ms2_raw_to_mdct_phase_psd(g["raw"], spec)
+    assert rel_err(phase, g["phase"]) < 1e-5 and rel_err(psd, g["psd"]) < 1e-6
+
+
+def test_ms_dual2_host_tables_vs_reference_golden():
+    """The product format's host-built tables (fp64 MDCT / inverse MDCT matrices with density and scales folded in, the
+    min-norm inverse mel bank, the constructor's window weights) applied with plain torch on CPU reproduce the unmodified
+    reference's outputs -- the GPU path only has to multiply by them.  Shape helpers as the reference states them."""
+    from dualdiffusion_b200.modules.formats.ms_mdct_dual_2 import MS_MDCT_DualFormat, MS_MDCT_DualFormatConfig
+    g = load_golden("ms_dual2_small.pt")
+    f = MS_MDCT_DualFormat(MS_MDCT_DualFormatConfig())
+    t = f._tables(torch.device("cpu"))
+    assert torch.equal(f.ms_filter_window_weights, g["window_weights"])
+    raw, N = g["raw"], 256
+    n = raw.shape[-1]
+    T = -(-n // N) + 1
+    frames = torch.nn.functional.pad(raw.reshape(4, n), (N, 2 * N), mode="reflect").unfold(-1, 2 * N, N)[:, :T]
+    y = torch.einsum("rk,stk->srt", t["fwd"], frames)
+    assert rel_err(y[:, :N].reshape(2, 2, N, T), g["mdct"]) < 1e-4
+    inv = torch.einsum("skt,kj->stj", g["mdct"].reshape(4, N, T), t["inv"])
+    out = torch.zeros(4, (T + 1) * N)
+    for tt in range(T):
+        out[:, tt * N:tt * N + 2 * N] += inv[:, tt]
+    assert rel_err(out[:, N:-N].reshape(2, 2, -1), g["raw_back"]) < 1e-4
+    c = f.config
+    lin = (g["mel"] - c.raw_to_mel_spec_offset / c.raw_to_mel_spec_scale).clip(min=0) ** (1 / c.ms_abs_exponent)
+    assert rel_err(torch.einsum("bf,scft->scbt", t["pinv"], lin), g["mel_linear"]) < 1e-5
+    assert tuple(f.get_mel_spec_shape(3, 1408768)) == g["mel_spec_shape"] and tuple(f.get_mdct_shape(3, 1408768)) == g["mdct_shape"]
+    assert f.get_raw_crop_width(1408768) == g["raw_crop_width"]
+    with pytest.raises(RuntimeError):
+        f.raw_to_mdct(raw)                                                  # no CPU path
+
+
 def test_mdct_oracle_vs_golden_reference():
     """MCLT / inverse MCLT / PSD / mel -> PSD restatements against the reference's own outputs."""
     from oracle import format_oracle as fo
