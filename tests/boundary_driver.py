@@ -68,7 +68,10 @@ resolved = {}
 for pkg, cls in (("dualdiffusion_b200.modules.daes.dae_edm2_d3", "DAE_D3"),
                  ("dualdiffusion_b200.modules.formats.spectrogram", "SpectrogramFormat"),
                  ("dualdiffusion_b200.modules.unets.unet_edm2_ddec_mclt_b1", "DDec_MCLT_UNet_B1"),
-                 ("dualdiffusion_b200.modules.unets.unet_edm2_q4_ddec", "UNet")):
+                 ("dualdiffusion_b200.modules.unets.unet_edm2_q4_ddec", "UNet"),
+                 ("dualdiffusion_b200.modules.unets.unet_edm2_b4_2", "UNet"),
+                 ("dualdiffusion_b200.modules.daes.dae_edm2_q4", "DAE"),
+                 ("dualdiffusion_b200.modules.formats.ms_mdct_dual_2", "MS_MDCT_DualFormat")):
     c = getattr(importlib.import_module(pkg), cls)
     cc = c.config_class or inspect.signature(c.__init__).parameters["config"].annotation
     resolved[f"{pkg}.{cls}"] = bool(is_dataclass(cc)) and issubclass(c, DualDiffusionModule)
