@@ -267,9 +267,9 @@ __device__ __forceinline__ void strip_reduce_atomic(float (&acc)[8], float* __re
     }
 }
 
-constexpr int kSsbPixPerThread = 8;
+constexpr int kSsbPixPerThread = 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 silu_scale_bwd_kernel(const uint4* __restrict__ dy, float coef, const uint4* __restrict__ pre,
                       const float* __restrict__ scale, uint4* __restrict__ dpre, float* __restrict__ dscale, long npix,
                       int nvec) {
@@ -279,34 +279,41 @@ silu_scale_bwd_kernel(const uint4* __restrict__ dy, float coef, const uint4* __r
     const int b = blockIdx.z;
     const int v = blockIdx.y * 32 + threadIdx.x;
     const bool vok = v < nvec;
-    const long p0 = (long)blockIdx.x * (kRedRows * kSsbPixPerThread) + threadIdx.y;
     float sc[8], acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = vok ? __ldg(scale + (size_t)b * nvec * 8 + v * 8 + j) : 0.f; acc[j] = 0.f; }
-    uint4 qg[kSsbPixPerThread], qx[kSsbPixPerThread];
+    // A CTA walks several 64-pixel strips and keeps the dscale partial sums in registers across them: one shared-memory
+    // reduction and one set of atomics per CTA (one per strip made 700 k atomics onto 2048 addresses at level 0, and the
+    // short CTAs spent their time in launch / drain: 1.8 TB/s).
+    constexpr long kStrip = kRedRows * kSsbPixPerThread;
+#pragma unroll 1
+    for (long s0 = (long)blockIdx.x * kStrip; s0 < npix; s0 += (long)gridDim.x * kStrip) {
+        const long p0 = s0 + threadIdx.y;
+        uint4 qg[kSsbPixPerThread], qx[kSsbPixPerThread];
 #pragma unroll
-    for (int i = 0; i < kSsbPixPerThread; ++i) {
-        const long pix = p0 + (long)i * kRedRows;
-        if (vok && pix < npix) {
-            const size_t off = ((size_t)b * npix + pix) * nvec + v;
-            qg[i] = __ldg(dy + off);
-            qx[i] = __ldg(pre + off);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < kSsbPixPerThread; ++i) {
-        const long pix = p0 + (long)i * kRedRows;
-        if (vok && pix < npix) {
-            float g[8], x[8], o[8];
-            unpack8(qg[i], g);
-            unpack8(qx[i], x);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float t = coef * g[j] * mp_silu_grad(x[j] * sc[j]);
-                o[j] = t * sc[j];
-                acc[j] += t * x[j];
+        for (int i = 0; i < kSsbPixPerThread; ++i) {
+            const long pix = p0 + (long)i * kRedRows;
+            if (vok && pix < npix) {
+                const size_t off = ((size_t)b * npix + pix) * nvec + v;
+                qg[i] = __ldg(dy + off);
+                qx[i] = __ldg(pre + off);
             }
-            dpre[((size_t)b * npix + pix) * nvec + v] = pack8(o);
+        }
+#pragma unroll
+        for (int i = 0; i < kSsbPixPerThread; ++i) {
+            const long pix = p0 + (long)i * kRedRows;
+            if (vok && pix < npix) {
+                float g[8], x[8], o[8];
+                unpack8(qg[i], g);
+                unpack8(qx[i], x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float t = coef * g[j] * mp_silu_grad(x[j] * sc[j]);
+                    o[j] = t * sc[j];
+                    acc[j] += t * x[j];
+                }
+                dpre[((size_t)b * npix + pix) * nvec + v] = pack8(o);
+            }
         }
     }
     strip_reduce_atomic(acc, dscale + (size_t)b * nvec * 8 + v * 8, vok, red);
@@ -318,6 +325,9 @@ silu_scale_bwd_kernel(const uint4* __restrict__ dy, float coef, const uint4* __r
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxVecPerLaneB = 10;    // C <= 2560
 
+// NV = 16-byte vectors per lane (C <= NV * 256), a template parameter: with the bound of the widest layer (10) compiled in,
+// a 256-channel launch executed ten predicated copies of every pass and held 166 registers (12 warps per SM).
+template <int NV>
 __global__ void pixnorm_silu_bwd_kernel(const uint4* __restrict__ g, float ca, const uint4* __restrict__ ds,
                                         const uint4* __restrict__ t0, uint4* __restrict__ dt0, long npix, int C) {
     ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
@@ -326,10 +336,10 @@ __global__ void pixnorm_silu_bwd_kernel(const uint4* __restrict__ g, float ca, c
     const long pix = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pix >= npix) return;
     const int nvec = C >> 3;
-    uint4 rt[kMaxVecPerLaneB];
+    uint4 rt[NV];
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLaneB; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int v = lane + k * 32;
         if (v < nvec) {
             rt[k] = __ldg(t0 + pix * nvec + v);
@@ -344,9 +354,9 @@ __global__ void pixnorm_silu_bwd_kernel(const uint4* __restrict__ g, float ca, c
     const float n = kNormEps + rms, inv = 1.f / n;
     // pass 1: dxn and <dxn, t0>
     float dot = 0.f;
-    uint4 rd[kMaxVecPerLaneB];       // dxn kept as packed fp32 pairs would double registers: keep bf16-packed dxn
+    uint4 rd[NV];       // dxn kept as packed fp32 pairs would double registers: keep bf16-packed dxn
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLaneB; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int v = lane + k * 32;
         if (v < nvec) {
             float ft[8], fg[8], fs[8], dx[8];
@@ -364,7 +374,7 @@ __global__ void pixnorm_silu_bwd_kernel(const uint4* __restrict__ g, float ca, c
     dot = warp_sum(dot);
     const float kb = rms > 0.f ? dot / (n * n * (float)C * rms) : 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLaneB; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int v = lane + k * 32;
         if (v < nvec) {
             float ft[8], dx[8], o[8];
@@ -1070,7 +1080,10 @@ extern "C" int dd_silu_scale_bwd(const void* dy, float coef, const void* pre, co
     DD_REQUIRE(C % 8 == 0 && B > 0 && B <= 65535, "dd_silu_scale_bwd: bad shape");
     if (npix == 0) return 0;
     const int strip = kRedRows * kSsbPixPerThread;
-    const dim3 grid((unsigned)((npix + strip - 1) / strip), ceil_div(C / 8, 32), B);
+    const int ny = ceil_div(C / 8, 32);
+    const long strips = (npix + strip - 1) / strip;
+    const long want = std::max<long>(1, (long)dd_num_sms() * 4 / ((long)ny * B));      // ~4 CTAs per SM over the whole grid
+    const dim3 grid((unsigned)std::min<long>(strips, want), ny, B);
     DD_CHECK_CUDA(dd_launch_pdl(silu_scale_bwd_kernel, dim3(grid), dim3(dim3(32, kRedRows)), 0, stream, static_cast<const uint4*>(dy), coef,
                                                                    static_cast<const uint4*>(pre), scale,
                                                                    static_cast<uint4*>(dpre), dscale, npix, C / 8));
@@ -1085,7 +1098,11 @@ extern "C" int dd_pixnorm_silu_bwd(const void* g, float ca, const void* ds, cons
     DD_REQUIRE(C % 8 == 0 && C <= kMaxVecPerLaneB * 256, "dd_pixnorm_silu_bwd: C=%d unsupported", C);
     if (npix == 0) return 0;
     const int warps = 4;
-    DD_CHECK_CUDA(dd_launch_pdl(pixnorm_silu_bwd_kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), 0, stream, 
+    const int nv = ceil_div(C / 8, 32);
+    auto kernel = nv <= 1 ? pixnorm_silu_bwd_kernel<1> : nv <= 2 ? pixnorm_silu_bwd_kernel<2> : nv <= 3 ? pixnorm_silu_bwd_kernel<3>
+                : nv <= 4 ? pixnorm_silu_bwd_kernel<4> : nv <= 5 ? pixnorm_silu_bwd_kernel<5> : nv <= 6 ? pixnorm_silu_bwd_kernel<6>
+                : nv <= 8 ? pixnorm_silu_bwd_kernel<8> : pixnorm_silu_bwd_kernel<kMaxVecPerLaneB>;
+    DD_CHECK_CUDA(dd_launch_pdl(kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), 0, stream,
         static_cast<const uint4*>(g), ca, static_cast<const uint4*>(ds), static_cast<const uint4*>(t0),
         static_cast<uint4*>(dt0), npix, C));
     DD_CHECK_LAUNCH();

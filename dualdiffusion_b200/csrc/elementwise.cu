@@ -77,6 +77,9 @@ __global__ void weight_prep_kernel(const void* __restrict__ w, void* __restrict_
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxVecPerLane = 10;    // C <= 10*32*8 = 2560
 
+// NV = 16-byte vectors per lane (C <= NV * 256) as a template parameter: compiled for the widest layer only (10), a
+// 256-channel launch executed ten predicated copies of every loop body.
+template <int NV>
 __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restrict__ x_out, uint4* __restrict__ s_out,
                                     long npix, int C) {
     ptx::grid_launch_dependents();
@@ -86,10 +89,10 @@ __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restri
     if (pix >= npix) return;
     const int nvec = C >> 3;
     const uint4* src = t + pix * nvec;
-    uint4 reg[kMaxVecPerLane];
+    uint4 reg[NV];
     float ss = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int v = lane + k * 32;
         if (v < nvec) {
             reg[k] = __ldg(src + v);
@@ -101,7 +104,7 @@ __global__ void pixnorm_silu_kernel(const uint4* __restrict__ t, uint4* __restri
     ss = warp_sum(ss);
     const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)C));
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k) {
+    for (int k = 0; k < NV; ++k) {
         const int v = lane + k * 32;
         if (v < nvec) {
             const uint32_t u[4] = {reg[k].x, reg[k].y, reg[k].z, reg[k].w};
@@ -541,7 +544,11 @@ extern "C" int dd_pixnorm_silu(const void* t, void* x_out, void* s_out, long npi
     DD_REQUIRE(C % 8 == 0 && C <= kMaxVecPerLane * 256, "dd_pixnorm_silu: C=%d unsupported", C);
     if (npix == 0) return 0;
     const int warps = 8;
-    DD_CHECK_CUDA(dd_launch_pdl(pixnorm_silu_kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), 0, stream,
+    const int nv = ceil_div(C / 8, 32);
+    auto kernel = nv <= 1 ? pixnorm_silu_kernel<1> : nv <= 2 ? pixnorm_silu_kernel<2> : nv <= 3 ? pixnorm_silu_kernel<3>
+                : nv <= 4 ? pixnorm_silu_kernel<4> : nv <= 5 ? pixnorm_silu_kernel<5> : nv <= 6 ? pixnorm_silu_kernel<6>
+                : nv <= 8 ? pixnorm_silu_kernel<8> : pixnorm_silu_kernel<kMaxVecPerLane>;
+    DD_CHECK_CUDA(dd_launch_pdl(kernel, dim3((unsigned)((npix + warps - 1) / warps)), dim3(warps * 32), 0, stream,
                                 static_cast<const uint4*>(t), static_cast<uint4*>(x_out), static_cast<uint4*>(s_out), npix,
                                 C));
     return 0;
