@@ -178,69 +178,90 @@ __global__ void weight_prep_batched_kernel(const dd_wprep_desc* __restrict__ des
 // weight-prep backward (batched over parameters): dL/dW_eff -> dL/dW (+ dL/dgain)
 //   forward (mp_tools.py:359-364): w_hat = w / (eps + ||w|| / sqrt(f))  [training], w_eff = w_hat * gain / sqrt(f)
 // ------------------------------------------------------------------------------------------
-__global__ void weight_prep_bwd_kernel(const dd_wbwd_desc* __restrict__ descs, int n_descs) {
+// One warp per weight row (fan-in <= a few thousand elements: no block-wide barriers), kWpbRows consecutive rows per warp so
+// that the descriptor search -- ~log2(n_descs) dependent loads -- is paid once per kWpbRows rows; the row index -> (i, tap)
+// split avoids a division by a run-time value for the two kernel sizes that occur (1 and 9 taps).
+constexpr int kWpbWarps = 8, kWpbRows = 2;
+
+__device__ __forceinline__ void split_tap(int j, int taps, int& i, int& tap) {
+    if (taps == 1) { i = j; tap = 0; }
+    else if (taps == 9) { i = j / 9; tap = j - i * 9; }
+    else { i = j / taps; tap = j - i * taps; }
+}
+
+__global__ void __launch_bounds__(kWpbWarps * 32) weight_prep_bwd_kernel(const dd_wbwd_desc* __restrict__ descs, int n_descs,
+                                                                        int total_rows) {
     ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
     ptx::grid_dependency_wait();
-    __shared__ float red[32];
-    // find the descriptor owning this row (row_begin is an exclusive prefix sum)
+    const int lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * kWpbWarps + (threadIdx.x >> 5)) * kWpbRows;
+    if (row0 >= total_rows) return;
+    // find the descriptor owning the first row (row_begin is an exclusive prefix sum)
     int lo = 0, hi = n_descs - 1;
-    const int row = blockIdx.x;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].row_begin <= row) lo = mid; else hi = mid - 1;
+        if (descs[mid].row_begin <= row0) lo = mid; else hi = mid - 1;
     }
-    const dd_wbwd_desc d = descs[lo];
-    const int o = row - d.row_begin;
-    if (o >= d.O) return;
-    const int f = d.I_g * d.taps;
-    const float rs = rsqrtf((float)f);
-    int o_src = o;
-    if (d.perm == DD_WPERM_QK) {
-        const int head = o / (2 * d.head_dim), rem = o % (2 * d.head_dim);
-        o_src = (rem & 1) * (d.O / 2) + head * d.head_dim + (rem >> 1);
+    dd_wbwd_desc d = descs[lo];
+    for (int r = 0; r < kWpbRows; ++r) {
+        const int row = row0 + r;
+        if (row >= total_rows) return;
+        while (lo + 1 < n_descs && descs[lo + 1].row_begin <= row) d = descs[++lo];
+        const int o = row - d.row_begin;
+        if (o >= d.O) continue;
+        const int f = d.I_g * d.taps;
+        const float rs = rsqrtf((float)f);
+        int o_src = o;
+        if (d.perm == DD_WPERM_QK) {
+            const int head = o / (2 * d.head_dim), rem = o % (2 * d.head_dim);
+            o_src = (rem & 1) * (d.O / 2) + head * d.head_dim + (rem >> 1);
+        }
+        const float* w = d.w + (size_t)o * f;                       // [i][tap]
+        float* dw = d.dw + (size_t)o * f;
+        const float gain = d.gain_host * (d.gain ? *d.gain : 1.f);
+        // dL/dW_eff of (row o, tap, i): [o][tap][i], or for an operand-swapped wgrad [group*I_g + i][taps-1-tap][o % cout_g]
+        const float* g = d.dweff + (size_t)o_src * d.row_stride;
+        size_t s_i = 1, s_tap = (size_t)d.I_g;
+        if (d.t_cout_g > 0) {
+            const int grp = o / d.t_cout_g;
+            const size_t row_t = (size_t)d.taps * d.t_cout_g;
+            g = d.dweff + (size_t)grp * d.I_g * row_t + (size_t)(d.taps - 1) * d.t_cout_g + (o - grp * d.t_cout_g);
+            s_i = row_t;
+            s_tap = (size_t)0 - (size_t)d.t_cout_g;                 // (unsigned wrap: taps run backwards)
+        }
+        float ss = 0.f, gw = 0.f;
+#pragma unroll 4
+        for (int j = lane; j < f; j += 32) {                        // j = i*taps + tap (parameter order)
+            int i, tap;
+            split_tap(j, d.taps, i, tap);
+            const float wv = w[j], gv = g[tap * s_tap + i * s_i];
+            ss += wv * wv;
+            gw += gv * wv;
+        }
+        ss = warp_sum(ss);
+        gw = warp_sum(gw);
+        const float nrm = sqrtf(ss);
+        float a, b;                  // dw = a * G - b * w
+        float dgain;
+        if (d.normalize) {
+            const float n = kNormEps + nrm * rs;
+            a = gain * rs / n;
+            b = nrm > 0.f ? (gain * rs) * gw * rs / (n * n * nrm) : 0.f;
+            dgain = gw * rs / n;
+        } else {
+            a = gain * rs;
+            b = 0.f;
+            dgain = gw * rs;
+        }
+#pragma unroll 4
+        for (int j = lane; j < f; j += 32) {
+            int i, tap;
+            split_tap(j, d.taps, i, tap);
+            const float v = a * g[tap * s_tap + i * s_i] - b * w[j];
+            dw[j] = d.accumulate ? dw[j] + v : v;
+        }
+        if (d.dgain && lane == 0) atomicAdd(d.dgain, dgain * d.gain_host);
     }
-    const float* w = d.w + (size_t)o * f;                       // [i][tap]
-    float* dw = d.dw + (size_t)o * f;
-    const float gain = d.gain_host * (d.gain ? *d.gain : 1.f);
-    // dL/dW_eff of (row o, tap, i): [o][tap][i], or for an operand-swapped wgrad [group*I_g + i][taps-1-tap][o % cout_g]
-    const float* g = d.dweff + (size_t)o_src * d.row_stride;
-    size_t s_i = 1, s_tap = (size_t)d.I_g;
-    if (d.t_cout_g > 0) {
-        const int grp = o / d.t_cout_g;
-        const size_t row_t = (size_t)d.taps * d.t_cout_g;
-        g = d.dweff + (size_t)grp * d.I_g * row_t + (size_t)(d.taps - 1) * d.t_cout_g + (o - grp * d.t_cout_g);
-        s_i = row_t;
-        s_tap = (size_t)0 - (size_t)d.t_cout_g;                 // (unsigned wrap: taps run backwards)
-    }
-
-    float ss = 0.f, gw = 0.f;
-    for (int j = threadIdx.x; j < f; j += blockDim.x) {         // j = i*taps + tap (parameter order)
-        const int i = j / d.taps, tap = j - i * d.taps;
-        const float wv = w[j], gv = g[tap * s_tap + i * s_i];
-        ss += wv * wv;
-        gw += gv * wv;
-    }
-    ss = block_sum_b(ss, red);
-    gw = block_sum_b(gw, red);
-    const float nrm = sqrtf(ss);
-    float a, b;                  // dw = a * G - b * w
-    float dgain;
-    if (d.normalize) {
-        const float n = kNormEps + nrm * rs;
-        a = gain * rs / n;
-        b = nrm > 0.f ? (gain * rs) * gw * rs / (n * n * nrm) : 0.f;
-        dgain = gw * rs / n;
-    } else {
-        a = gain * rs;
-        b = 0.f;
-        dgain = gw * rs;
-    }
-    for (int j = threadIdx.x; j < f; j += blockDim.x) {
-        const int i = j / d.taps, tap = j - i * d.taps;
-        const float v = a * g[tap * s_tap + i * s_i] - b * w[j];
-        dw[j] = d.accumulate ? dw[j] + v : v;
-    }
-    if (d.dgain && threadIdx.x == 0) atomicAdd(d.dgain, dgain * d.gain_host);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1068,7 +1089,8 @@ extern "C" int dd_weight_transpose_batched(const dd_wtrans_desc* descs_dev, int 
 extern "C" int dd_weight_prep_bwd(const dd_wbwd_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_prep_bwd: bad arguments");
-    DD_CHECK_CUDA(dd_launch_pdl(weight_prep_bwd_kernel, dim3(total_rows), dim3(128), 0, stream, descs_dev, n_descs));
+    DD_CHECK_CUDA(dd_launch_pdl(weight_prep_bwd_kernel, dim3(ceil_div(total_rows, kWpbWarps * kWpbRows)), dim3(kWpbWarps * 32), 0, stream, descs_dev,
+                                n_descs, total_rows));
     DD_CHECK_LAUNCH();
     return 0;
 }
