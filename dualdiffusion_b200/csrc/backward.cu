@@ -886,16 +886,36 @@ __global__ void emb_affine_bwd_w_kernel(const dd_affine_bwd_desc* __restrict__ d
     if (o >= d.O) return;
     const int g = o / (d.O / d.groups);
     const float* e0 = emb + (size_t)g * d.I;
+    const bool vec = d.I % 4 == 0 && cemb % 4 == 0 && ((reinterpret_cast<uintptr_t>(d.w) | reinterpret_cast<uintptr_t>(d.dweff) |
+                                                       reinterpret_cast<uintptr_t>(e0)) & 15u) == 0;
     float ss = 0.f;
-    for (int i = lane; i < d.I; i += 32) { const float wv = d.w[(size_t)o * d.I + i]; ss += wv * wv; }
+    if (vec) {
+        const float4* w4 = reinterpret_cast<const float4*>(d.w + (size_t)o * d.I);
+        for (int i = lane; i < d.I / 4; i += 32) { const float4 q = __ldg(w4 + i); ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w; }
+    } else {
+        for (int i = lane; i < d.I; i += 32) { const float wv = d.w[(size_t)o * d.I + i]; ss += wv * wv; }
+    }
     ss = warp_sum(ss);
     float scale = (d.gain ? *d.gain : 1.f) * rsqrtf((float)d.I);
     if (d.normalize) scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)d.I));
     if (lane == 0) d.rowscale[o] = scale;
-    for (int i = lane; i < d.I; i += 32) {
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += d.dout[(size_t)b * d.O + o] * e0[(size_t)b * cemb + i];
-        d.dweff[(size_t)o * d.I + i] = acc;
+    if (vec) {
+        float4* g4 = reinterpret_cast<float4*>(d.dweff + (size_t)o * d.I);
+        for (int i = lane; i < d.I / 4; i += 32) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int b = 0; b < B; ++b) {
+                const float dc = d.dout[(size_t)b * d.O + o];
+                const float4 e = __ldg(reinterpret_cast<const float4*>(e0 + (size_t)b * cemb) + i);
+                acc.x += dc * e.x; acc.y += dc * e.y; acc.z += dc * e.z; acc.w += dc * e.w;
+            }
+            g4[i] = acc;
+        }
+    } else {
+        for (int i = lane; i < d.I; i += 32) {
+            float acc = 0.f;
+            for (int b = 0; b < B; ++b) acc += d.dout[(size_t)b * d.O + o] * e0[(size_t)b * cemb + i];
+            d.dweff[(size_t)o * d.I + i] = acc;
+        }
     }
 }
 
@@ -912,7 +932,21 @@ __global__ void emb_affine_bwd_x_kernel(const dd_affine_bwd_desc* __restrict__ d
     const int r0 = (int)((long)blockIdx.z * rows_g / row_chunks), r1 = (int)((long)(blockIdx.z + 1) * rows_g / row_chunks);
     for (int b0 = 0; b0 < B; b0 += 8) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int r = r0; r < r1; ++r) {
+        int r = r0;
+        for (; r + 4 <= r1; r += 4) {                              // four weight rows in flight per thread
+            const int o = g * rows_g + r;
+            float wv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = __ldg(d.w + (size_t)(o + u) * d.I + i);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float ws = wv[u] * d.rowscale[o + u];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (b0 + j < B) acc[j] += d.dout[(size_t)(b0 + j) * d.O + o + u] * ws;
+            }
+        }
+        for (; r < r1; ++r) {
             const int o = g * rows_g + r;
             const float wv = d.w[(size_t)o * d.I + i] * d.rowscale[o];
 #pragma unroll
