@@ -14,6 +14,7 @@ backward.  Parameters' `.grad` are views of that flat buffer (no per-parameter c
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Optional
 
 import torch
@@ -26,6 +27,18 @@ class GradAllReducer:
         self.sync_now = True
         self.stream: Optional[torch.cuda.Stream] = None
         self.bytes_reduced = 0
+        # DD_DDP_TRACE=1 (tuning): CUDA events around every bucket's all-reduce and at the end of the backward schedule;
+        # `trace_report()` turns the last step's events into (bucket MB, start, end) relative to the backward's end
+        self.trace = os.environ.get("DD_DDP_TRACE", "0") == "1"
+        self._events: list = []
+
+    def trace_report(self) -> list:
+        if not self._events:
+            return []
+        torch.cuda.synchronize()
+        t_end = self._events[-1][2]
+        rows = [(mb, -e0.elapsed_time(t_end), -e1.elapsed_time(t_end)) for mb, e0, e1 in self._events[:-1]]
+        return [(round(mb, 1), round(a, 3), round(b, 3)) for mb, a, b in rows]
 
     @contextlib.contextmanager
     def no_sync(self):
@@ -91,12 +104,24 @@ class GradAllReducer:
             if on_gpu:
                 self.stream.wait_stream(main)
                 with torch.cuda.stream(self.stream):
+                    if self.trace:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
                     self._all_reduce_mean(ts.grad_flat[lo:hi])
+                    if self.trace:
+                        e1.record()
+                        self._events.append(((hi - lo) * 4 / 2 ** 20, e0, e1))
             else:
                 self._all_reduce_mean(ts.grad_flat[lo:hi])
             self.bytes_reduced += (hi - lo) * 4
 
+        if self.trace:
+            self._events = []
         dlabel = backward_fn(net, plan, saved, dD, accumulate=installed, bucket_done=bucket_done)
+        if self.trace and exchange and on_gpu:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()                                   # end of the backward schedule on the main stream
+            self._events.append((0.0, None, e))
         if exchange and on_gpu:
             main.wait_stream(self.stream)
         if exchange:

@@ -17,6 +17,7 @@ running their backward.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -102,8 +103,9 @@ class TrainState:
         cur: List[_ParamSlot] = [_ParamSlot("conv_out.weight", net.conv_out.weight, rows_eff=_CONV_OUT_PAD,
                                             gain=net.out_gain)]
         cur_bytes = 0
-        target = 64 << 20       # >= 64 MB of fp32 gradients per bucket: still at NVLink bandwidth, and the buckets that
-                                # finish last (whose all-reduce is what stays exposed) are smaller
+        # >= 64 MB of fp32 gradients per bucket: still at NVLink bandwidth, and the buckets that finish last (whose
+        # all-reduce is what stays exposed) are smaller.  DD_DDP_BUCKET_MB: tuning experiments.
+        target = int(os.environ.get("DD_DDP_BUCKET_MB", "64")) << 20
         for prefix, blocks in (("dec", net.dec), ("enc", net.enc)):
             for name, blk in reversed(list(blocks.items())):
                 if not isinstance(blk, Block):
