@@ -27,27 +27,6 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Load one token's 64-channel head vector with 8 lanes (one uint4 each), cosine-normalise it.
-// Returns the lane's 8 normalised values; `active` false yields zeros.
-__device__ __forceinline__ void load_norm8(const __nv_bfloat16* src, bool active, float (&f)[8]) {
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (active) q = __ldg(reinterpret_cast<const uint4*>(src));
-    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-    float ss = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 t = unpack_bf16x2(u[j]);
-        f[2 * j] = t.x; f[2 * j + 1] = t.y;
-        ss += t.x * t.x + t.y * t.y;
-    }
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-    const float inv = 1.f / (kNormEps + sqrtf(ss) * 0.125f);   // ||x|| / sqrt(64)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] *= inv;
-}
-
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
     const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_row));
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"

@@ -31,7 +31,6 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kMaxThreads = 448;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccBufs = 8;
 constexpr int DD_EPI_HEAD = 3;   // internal: EDM output head (dd_conv_out)
@@ -1052,15 +1051,6 @@ int choose_n_tile(int cout_g, long m_tiles, int groups, int k_iters, int KC, int
         if (cost < best_cost * 0.999 || (cost <= best_cost * 1.001 && n > best)) { best_cost = cost; best = n; }
     }
     return best;
-}
-
-// Dependent UMMAs into one accumulator issue ~100+ cycles apart while a 128 x n x 16 UMMA occupies the tensor pipe
-// for only n cycles (cta_group::1): tiles narrower than 128 columns spread their k-steps over several accumulators.
-int choose_nacc(int n_tile, int k_steps) {
-    static const int forced = getenv("DD_FORCE_NACC") ? atoi(getenv("DD_FORCE_NACC")) : 0;   // tuning experiments
-    int nacc = 1;       // measured: no gain from splitting the accumulation chain (the epilogue was the limiter)
-    if (forced >= 1) { nacc = 1; while (nacc < forced && 2 * (2 * nacc) * n_tile <= 512 && 2 * nacc <= k_steps) nacc *= 2; }
-    return nacc;
 }
 
 // Epilogue warps: 4 for the plain / head epilogues, 8-12 for the fused ones (tools/exp_epi.py).
