@@ -130,47 +130,59 @@ __global__ void weight_normalize_batched_kernel(const dd_wprep_desc* __restrict_
     for (int i = threadIdx.x; i < f; i += blockDim.x) w[i] *= inv;
 }
 
-// dd_weight_prep for every parameter of a model in one launch (same arithmetic as weight_prep_kernel, elementwise.cu)
-__global__ void weight_prep_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs) {
+// dd_weight_prep for every parameter of a model in one launch (same arithmetic as weight_prep_kernel, elementwise.cu).
+// One warp per weight row, kWpWarpRows consecutive rows per descriptor search, the (tap, i) walk without divisions.
+constexpr int kWpWarps = 8, kWpWarpRows = 2;
+__global__ void __launch_bounds__(kWpWarps * 32) weight_prep_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs,
+                                                                           int total_rows) {
     ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
     ptx::grid_dependency_wait();
-    __shared__ float red[32];
+    const int lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * kWpWarps + (threadIdx.x >> 5)) * kWpWarpRows;
+    if (row0 >= total_rows) return;
     int lo = 0, hi = n_descs - 1;
-    const int row = blockIdx.x;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].row_begin <= row) lo = mid; else hi = mid - 1;
+        if (descs[mid].row_begin <= row0) lo = mid; else hi = mid - 1;
     }
-    const dd_wprep_desc d = descs[lo];
-    const int o = row - d.row_begin;
-    if (o >= d.O) return;
-    const int fan_in = d.I_g * d.taps;
-    const size_t base = (size_t)o * fan_in;
-    const float* wf = static_cast<const float*>(d.w);
-    const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(d.w);
-    float scale = d.gain_host * (d.gain ? *d.gain : 1.f) * rsqrtf((float)fan_in);
-    if (d.normalize) {
-        float ss = 0.f;
-        for (int i = threadIdx.x; i < fan_in; i += blockDim.x) {
-            const float v = d.w_is_bf16 ? __bfloat162float(wb[base + i]) : wf[base + i];
-            ss += v * v;
+    dd_wprep_desc d = descs[lo];
+    for (int r = 0; r < kWpWarpRows; ++r) {
+        const int row = row0 + r;
+        if (row >= total_rows) return;
+        while (lo + 1 < n_descs && descs[lo + 1].row_begin <= row) d = descs[++lo];
+        const int o = row - d.row_begin;
+        if (o >= d.O) continue;
+        const int fan_in = d.I_g * d.taps;
+        const size_t base = (size_t)o * fan_in;
+        const float* wf = static_cast<const float*>(d.w);
+        const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(d.w);
+        float scale = d.gain_host * (d.gain ? *d.gain : 1.f) * rsqrtf((float)fan_in);
+        if (d.normalize) {
+            float ss = 0.f;
+#pragma unroll 4
+            for (int i = lane; i < fan_in; i += 32) {
+                const float v = d.w_is_bf16 ? __bfloat162float(wb[base + i]) : wf[base + i];
+                ss += v * v;
+            }
+            ss = warp_sum(ss);
+            scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)fan_in));
         }
-        ss = block_sum_b(ss, red);
-        scale /= (kNormEps + sqrtf(ss) * rsqrtf((float)fan_in));
-    }
-    int o_dst = o;
-    if (d.perm == DD_WPERM_QK) {
-        const int head = o / (2 * d.head_dim), rem = o % (2 * d.head_dim);
-        o_dst = (rem & 1) * (d.O / 2) + head * d.head_dim + (rem >> 1);
-    } else if (d.perm == DD_WPERM_QKV) {
-        const int head = o / (3 * d.head_dim), rem = o % (3 * d.head_dim);
-        o_dst = (rem % 3) * (d.O / 3) + head * d.head_dim + rem / 3;
-    }
-    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(d.out) + (size_t)o_dst * d.row_stride;
-    for (int j = threadIdx.x; j < fan_in; j += blockDim.x) {          // j = tap * I_g + i  (coalesced writes)
-        const int tap = j / d.I_g, i = j - tap * d.I_g;
-        const size_t src = base + (size_t)i * d.taps + tap;
-        dst[j] = __float2bfloat16_rn((d.w_is_bf16 ? __bfloat162float(wb[src]) : wf[src]) * scale);
+        int o_dst = o;
+        if (d.perm == DD_WPERM_QK) {
+            const int head = o / (2 * d.head_dim), rem = o % (2 * d.head_dim);
+            o_dst = (rem & 1) * (d.O / 2) + head * d.head_dim + (rem >> 1);
+        } else if (d.perm == DD_WPERM_QKV) {
+            const int head = o / (3 * d.head_dim), rem = o % (3 * d.head_dim);
+            o_dst = (rem % 3) * (d.O / 3) + head * d.head_dim + rem / 3;
+        }
+        __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(d.out) + (size_t)o_dst * d.row_stride;
+        for (int tap = 0; tap < d.taps; ++tap) {                        // dst[tap * I_g + i]: coalesced writes
+#pragma unroll 4
+            for (int i = lane; i < d.I_g; i += 32) {
+                const size_t src = base + (size_t)i * d.taps + tap;
+                dst[tap * d.I_g + i] = __float2bfloat16_rn((d.w_is_bf16 ? __bfloat162float(wb[src]) : wf[src]) * scale);
+            }
+        }
     }
 }
 
@@ -1107,7 +1119,8 @@ extern "C" int dd_weight_normalize_batched(const dd_wprep_desc* descs_dev, int n
 extern "C" int dd_weight_prep_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_prep_batched: bad arguments");
-    DD_CHECK_CUDA(dd_launch_pdl(weight_prep_batched_kernel, dim3(total_rows), dim3(128), 0, stream, descs_dev, n_descs));
+    DD_CHECK_CUDA(dd_launch_pdl(weight_prep_batched_kernel, dim3(ceil_div(total_rows, kWpWarps * kWpWarpRows)), dim3(kWpWarps * 32), 0, stream, descs_dev,
+                                n_descs, total_rows));
     DD_CHECK_LAUNCH();
     return 0;
 }

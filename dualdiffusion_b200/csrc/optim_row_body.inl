@@ -1,6 +1,7 @@
 // Body of one row of dd_optim_step_batched (csrc/optim.cu), included textually by the one-CTA-per-row kernels
 // (DD_ROW_EXIT = return) and by the persistent experiment (DD_ROW_EXIT = continue) so that both compile the same source.
-// Expects in scope: descs, lo, unit, h, clip_coef, red.
+// Expects in scope: descs, lo, unit, h, clip_coef; macros DD_ROW_TID / DD_ROW_NT (the thread's index among the DD_ROW_NT
+// threads that share the row) and DD_ROW_SUM(x) (sum over them).
     const dd_optim_desc d = descs[lo];
     const int r = unit - d.row_begin;
     if (r >= d.rows) DD_ROW_EXIT;
@@ -31,7 +32,7 @@
     float ss = 0.f;
     if (vec) {
         const int f4 = f >> 2;
-        for (int i = threadIdx.x; i < f4; i += kThreads) {
+        for (int i = DD_ROW_TID; i < f4; i += DD_ROW_NT) {
             float4 p4 = reinterpret_cast<float4*>(p)[i];
             if (has_g) {
                 const float4 g4 = __ldg(reinterpret_cast<const float4*>(g) + i);
@@ -60,7 +61,7 @@
             ss += p4.x * p4.x + p4.y * p4.y + p4.z * p4.z + p4.w * p4.w;
         }
     } else {
-        for (int i = threadIdx.x; i < f; i += kThreads) {
+        for (int i = DD_ROW_TID; i < f; i += DD_ROW_NT) {
             float pi = p[i];
             if (has_g) {
                 float mi = m[i], vi = v[i];
@@ -89,15 +90,15 @@
         }
     }
     if (!d.normalize) DD_ROW_EXIT;                // uniform over the CTA (descriptor field)
-    ss = block_sum_o(ss, red);
+    ss = DD_ROW_SUM(ss);
     const float inv = row_inv_norm(ss, f);
     if (vec) {
         const int f4 = f >> 2;
-        for (int i = threadIdx.x; i < f4; i += kThreads) {
+        for (int i = DD_ROW_TID; i < f4; i += DD_ROW_NT) {
             float4 p4 = reinterpret_cast<float4*>(p)[i];
             p4.x *= inv; p4.y *= inv; p4.z *= inv; p4.w *= inv;
             reinterpret_cast<float4*>(p)[i] = p4;
         }
     } else {
-        for (int i = threadIdx.x; i < f; i += kThreads) p[i] *= inv;
+        for (int i = DD_ROW_TID; i < f; i += DD_ROW_NT) p[i] *= inv;
     }
