@@ -108,26 +108,36 @@ __global__ void weight_transpose_batched_kernel(const dd_wtrans_desc* __restrict
 
 // normalize_weights() (mp_tools.py:375-378, run by the trainer after every optimizer step, trainer.py:1107-1108) for a
 // whole parameter set in one launch, in place on the fp32 parameters: w <- w / (eps + ||w|| / sqrt(fan_in)) per row.
-__global__ void weight_normalize_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs) {
+__global__ void __launch_bounds__(256) weight_normalize_batched_kernel(const dd_wprep_desc* __restrict__ descs, int n_descs,
+                                                                       int total_rows) {
     ptx::grid_launch_dependents();      // PDL: the next kernel's launch / prologue overlaps this one
     ptx::grid_dependency_wait();
-    __shared__ float red[32];
+    // one warp per weight row, two consecutive rows per descriptor search (as weight_prep_batched_kernel below)
+    const int lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 2;
+    if (row0 >= total_rows) return;
     int lo = 0, hi = n_descs - 1;
-    const int row = blockIdx.x;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].row_begin <= row) lo = mid; else hi = mid - 1;
+        if (descs[mid].row_begin <= row0) lo = mid; else hi = mid - 1;
     }
-    const dd_wprep_desc d = descs[lo];
-    const int o = row - d.row_begin;
-    if (o >= d.O) return;
-    const int f = d.I_g * d.taps;
-    float* w = static_cast<float*>(const_cast<void*>(d.w)) + (size_t)o * f;
-    float ss = 0.f;
-    for (int i = threadIdx.x; i < f; i += blockDim.x) ss += w[i] * w[i];
-    ss = block_sum_b(ss, red);
-    const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)f));
-    for (int i = threadIdx.x; i < f; i += blockDim.x) w[i] *= inv;
+    dd_wprep_desc d = descs[lo];
+    for (int r = 0; r < 2; ++r) {
+        const int row = row0 + r;
+        if (row >= total_rows) return;
+        while (lo + 1 < n_descs && descs[lo + 1].row_begin <= row) d = descs[++lo];
+        const int o = row - d.row_begin;
+        if (o >= d.O) continue;
+        const int f = d.I_g * d.taps;
+        float* w = static_cast<float*>(const_cast<void*>(d.w)) + (size_t)o * f;
+        float ss = 0.f;
+#pragma unroll 4
+        for (int i = lane; i < f; i += 32) ss += w[i] * w[i];
+        ss = warp_sum(ss);
+        const float inv = 1.f / (kNormEps + sqrtf(ss) * rsqrtf((float)f));
+#pragma unroll 4
+        for (int i = lane; i < f; i += 32) w[i] *= inv;
+    }
 }
 
 // dd_weight_prep for every parameter of a model in one launch (same arithmetic as weight_prep_kernel, elementwise.cu).
@@ -1111,7 +1121,7 @@ extern "C" int dd_weight_transpose(const void* w_prepped, void* out, int Cout, i
 extern "C" int dd_weight_normalize_batched(const dd_wprep_desc* descs_dev, int n_descs, int total_rows, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     DD_REQUIRE(descs_dev && n_descs > 0 && total_rows > 0, "dd_weight_normalize_batched: bad arguments");
-    DD_CHECK_CUDA(dd_launch_pdl(weight_normalize_batched_kernel, dim3(total_rows), dim3(128), 0, stream, descs_dev, n_descs));
+    DD_CHECK_CUDA(dd_launch_pdl(weight_normalize_batched_kernel, dim3(ceil_div(total_rows, 16)), dim3(256), 0, stream, descs_dev, n_descs, total_rows));
     DD_CHECK_LAUNCH();
     return 0;
 }
