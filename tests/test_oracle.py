@@ -278,6 +278,37 @@ def test_ms_dual2_host_tables_vs_reference_golden():
         f.raw_to_mdct(raw)                                                  # no CPU path
 
 
+def test_b4_3_oracle_matches_reference_golden():
+    """SURVEY 8(f) N4, the lineage without a CUDA path yet: unet_edm2_b4_3.UNet (time-axis blocks, (1,3) grouped convs,
+    partial RoPE, in-place input skip) restated in oracle/unet_b4_3_oracle.py.  With the reference's hard-coded bf16 body the
+    restatement is bit-identical to the unmodified reference module on CPU (tests/golden/make_golden_b4_3.py); the fp32
+    body differs from it by the bf16 rounding only."""
+    from oracle import unet_b4_3_oracle as bo
+    g = load_golden("unet_b4_3_small.pt")
+    spec = bo.small_b4_3_spec()
+    sd = bo.synth_state_dict(spec, seed=0)
+    assert abs(float(sum(v.double().abs().sum() for v in sd.values())) - g["weight_checksum"]) < 1e-6 * g["weight_checksum"]
+    assert torch.equal(bo.get_embeddings(sd, g["clap"], g["mask"]), g["emb"])
+    assert torch.equal(bo.forward(sd, spec, g["x"], g["sigma"], g["emb"], None, torch.bfloat16), g["d"])
+    assert torch.equal(bo.forward(sd, spec, g["x"], g["sigma"], g["emb"], g["x_ref"], torch.bfloat16), g["d_xref"])
+    assert torch.equal(bo.sigma_loss_logvar(sd, spec, g["sigma"]), g["logvar"])
+    c_skip = 1.0 / (1.0 + g["sigma"].view(-1, 1, 1, 1) ** 2)
+    d32 = bo.forward(sd, spec, g["x"], g["sigma"], g["emb"], None, torch.float32)
+    assert rel_err(d32 - c_skip * g["x"], g["d"] - c_skip * g["x"]) < 3e-2
+    # RoPE's even | odd | tail re-ordering is applied to q and k alike: the scores, hence the output, do not depend on it
+    q = torch.randn(1, 2, 5, 32)
+    k = torch.randn(1, 2, 5, 32)
+    tables = bo.rope_tables(5, 24, 10000.0, torch.float32)
+    scores = bo.rope_rotate(q, tables) @ bo.rope_rotate(k, tables).transpose(-1, -2)
+    cos, sin = tables
+    def rot_in_place(x):
+        y = x.clone()
+        y[..., 0:24:2] = x[..., 0:24:2] * cos - x[..., 1:24:2] * sin
+        y[..., 1:24:2] = x[..., 1:24:2] * cos + x[..., 0:24:2] * sin
+        return y
+    assert rel_err(scores, rot_in_place(q) @ rot_in_place(k).transpose(-1, -2)) < 1e-6
+
+
 def test_mdct_oracle_vs_golden_reference():
     """MCLT / inverse MCLT / PSD / mel -> PSD restatements against the reference's own outputs."""
     from oracle import format_oracle as fo
