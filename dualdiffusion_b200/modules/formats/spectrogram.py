@@ -12,7 +12,6 @@ fp64-precomputed pseudo-inverse P = A^T (A A^T)^-1 (identical solution for the f
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 from typing import Literal, Optional
 

@@ -5,7 +5,6 @@ of logical shape [B, H, W, C]."""
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Optional, Sequence, Tuple
 
 import torch

@@ -309,6 +309,35 @@ def test_b4_3_oracle_matches_reference_golden():
     assert rel_err(scores, rot_in_place(q) @ rot_in_place(k).transpose(-1, -2)) < 1e-6
 
 
+def test_dae_q4_tiled_encode_chunk_placement_host_logic(monkeypatch):
+    """dae_edm2_q4.DAE.tiled_encode (:314-372) is host logic around `encode`: with a purely local stand-in encoder (8x8
+    average pooling, no receptive field beyond the cell) the stitched result must equal the whole-input result exactly,
+    for widths that leave a short last chunk (extended to the left) and for one that fits a single chunk."""
+    from oracle import dae_q4_oracle as qo
+    from dualdiffusion_b200.modules.daes.dae_edm2_q4 import DAE, DAE_Config
+    spec = qo.small_dae_q4_spec()
+    dae = DAE(DAE_Config(model_channels=spec.model_channels, channel_mult_enc=tuple(spec.channel_mult_enc),
+                         channel_mult_dec=tuple(spec.channel_mult_dec), num_enc_layers_per_block=1,
+                         num_dec_layers_per_block=1)).eval()
+    ds, Lc = dae.downsample_ratio, dae.config.latent_channels
+    calls = []
+
+    def fake_encode(x, embeddings=None, training=False):
+        calls.append(x.shape[-1])
+        return torch.nn.functional.avg_pool2d(x.mean(dim=1, keepdim=True), ds).expand(-1, Lc, -1, -1).contiguous()
+
+    monkeypatch.setattr(dae, "encode", fake_encode)
+    g = torch.Generator().manual_seed(5)
+    for width, max_chunk, overlap in ((ds * 40, ds * 16, ds * 2), (ds * 37, ds * 16, ds * 4), (ds * 12, ds * 16, ds * 2)):
+        calls.clear()
+        x = torch.randn(2, 2, ds * 4, width, generator=g)
+        whole = fake_encode(x)
+        calls.clear()
+        tiled = dae.tiled_encode(x, None, max_chunk=max_chunk, overlap=overlap)
+        assert tiled.shape == whole.shape and torch.equal(tiled, whole), (width, max_chunk, overlap)
+        assert all(c <= max_chunk for c in calls) and (len(calls) == 1) == (width <= max_chunk)
+
+
 def test_mdct_oracle_vs_golden_reference():
     """MCLT / inverse MCLT / PSD / mel -> PSD restatements against the reference's own outputs."""
     from oracle import format_oracle as fo
